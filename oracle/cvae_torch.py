@@ -1,0 +1,257 @@
+"""Eager-PyTorch restatement of the reference cVAE path (CPU).  TEST INFRASTRUCTURE ONLY.
+
+This is the "port" CPU baseline and the per-step parity checker.  It restates, in
+compact form, the behaviour of the reference classes:
+
+* ``Encoder``            cVAE.py:140-172
+* ``Decoder``            cVAE.py:174-206
+* ``cVAE``               cVAE.py:391-443, 491-504, 549-555
+* fusion ops             cVAE.py:986-1083, gPoE inline 1154-1157
+* ``cVAE_multimodal``    cVAE.py:1087-1211
+* nmmlp -MSE variant     multimodal_kfold_cvae_nmmlp.py:124-127
+
+Parameter names, shapes and -- critically -- the torch-RNG draw order of the
+constructors (including the *discarded* ``nn.Linear`` layers of cVAE.py:155-157,
+190-191, 220-227) are preserved so that ``torch.manual_seed(s)`` followed by
+construction yields bit-identical weights and leaves the generator in the same
+state as the reference (verified by tests/test_oracle_vs_reference_golden.py
+against vectors produced by oracle/make_golden.py from the real reference).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+LOG_2PI = math.log(2.0 * math.pi)
+
+
+def _burn_linear(n_in: int, n_out: int) -> None:
+    """Consume exactly the RNG draws of one ``nn.Linear(n_in, n_out)`` (weight, bias)."""
+    nn.Linear(n_in, n_out, bias=True)
+
+
+class OracleEncoder(nn.Module):
+    """cVAE.py:140-172.  ``hidden_dim`` already includes the latent size as its last entry."""
+
+    def __init__(self, input_dim, hidden_dim, c_dim, non_linear=False):
+        super().__init__()
+        sizes = [input_dim + c_dim] + list(hidden_dim)
+        body = [nn.Linear(a, b) for a, b in zip(sizes[:-2], sizes[1:-1])]
+        _burn_linear(sizes[-2], sizes[-1])            # the discarded last layer (cVAE.py:155-157)
+        self.encoder_layers = nn.Sequential(*body)
+        self.enc_mean_layer = nn.Linear(sizes[-2], sizes[-1])
+        self.enc_logvar_layer = nn.Linear(sizes[-2], sizes[-1])
+        self.non_linear = non_linear
+        self.c_dim = c_dim
+
+    def forward(self, x, c):
+        h = torch.cat((x, c), dim=1)                  # int64 c promotes to float32 (cVAE.py:163)
+        for layer in self.encoder_layers:
+            h = layer(h)
+            if self.non_linear:
+                h = F.leaky_relu(h)                   # slope 0.01
+        return self.enc_mean_layer(h), self.enc_logvar_layer(h)
+
+
+class OracleDecoder(nn.Module):
+    """cVAE.py:174-206.  Returns (mu_out, logvar_out) instead of a Normal object."""
+
+    def __init__(self, input_dim, hidden_dim, c_dim, non_linear=False, init_logvar=-3.0):
+        super().__init__()
+        rev = list(hidden_dim)[::-1]
+        sizes = rev + [input_dim]
+        sizes[0] = rev[0] + c_dim
+        body = [nn.Linear(a, b) for a, b in zip(sizes[:-2], sizes[1:-1])]
+        _burn_linear(sizes[-2], sizes[-1])            # discarded (cVAE.py:190-191)
+        self.decoder_layers = nn.Sequential(*body)
+        self.decoder_mean_layer = nn.Linear(sizes[-2], sizes[-1])
+        self.logvar_out = nn.Parameter(torch.full((1, input_dim), float(init_logvar)))
+        self.non_linear = non_linear
+        self.c_dim = c_dim
+
+    def forward(self, z, c):
+        g = torch.cat((z, c.reshape(-1, self.c_dim)), dim=1)
+        for layer in self.decoder_layers:
+            g = layer(g)
+            if self.non_linear:
+                g = F.leaky_relu(g)
+        return self.decoder_mean_layer(g), self.logvar_out
+
+
+def _burn_discriminator(hidden_dim) -> None:
+    """RNG draws of ``Discriminator.__init__`` (cVAE.py:210-227): sizes rev(hidden)+[1]."""
+    sizes = list(hidden_dim)[::-1] + [1]
+    for a, b in zip(sizes[:-1], sizes[1:]):
+        _burn_linear(a, b)
+    _burn_linear(sizes[-2], sizes[-1])
+
+
+def gauss_ll(x, mu_out, logvar_out):
+    """``compute_ll`` cVAE.py:14-15 on ``Normal(mu_out, exp(logvar_out)**0.5)``; shape [1]."""
+    var = logvar_out.exp()
+    lp = -((x - mu_out) ** 2) / (2.0 * var) - 0.5 * logvar_out - 0.5 * LOG_2PI
+    return lp.sum(1, keepdim=True).mean(0)
+
+
+def neg_mse_ll(x, mu_out):
+    """nmmlp variant: ``-MSELoss(mean)`` (multimodal_kfold_cvae_nmmlp.py:124-127); scalar."""
+    return -((mu_out - x) ** 2).mean()
+
+
+def kl_term(mu, logvar):
+    """cVAE.py:429-430 / 1138-1139."""
+    return (-0.5 * torch.sum(1 + logvar - mu.pow(2) - logvar.exp(), dim=1)).mean(0)
+
+
+def fuse_latent(mus, variances, combine, alphas=None):
+    """``combine_latent`` cVAE.py:1144-1164 with the expert ops of cVAE.py:986-1083.
+
+    mus, variances: [M, B, Z].  alphas: list of M tensors of shape [1] (gPoE only).
+    """
+    if mus.shape[0] == 1:
+        return mus[0], variances[0]
+    kind = combine.lower()
+    m = mus.shape[0]
+    if kind == "poe":
+        t = 1.0 / variances
+        return (mus * t).sum(0) / t.sum(0), 1.0 / t.sum(0)
+    if kind == "gpoe":
+        a = torch.softmax(torch.stack(list(alphas)), dim=0).reshape(m, 1, 1)
+        w = a / variances
+        return (mus * a / variances).sum(0) / w.sum(0), 1.0 / w.sum(0)
+    if kind == "moe":
+        return mus.sum(0) / m, variances.sum(0) / m
+    if kind == "mopoe":
+        t = 1.0 / variances
+        p_mu, p_var = (mus * t).sum(0) / t.sum(0), 1.0 / t.sum(0)
+        return (mus.sum(0) + p_mu) / (m + 1), (variances.sum(0) + p_var) / (m + 1)
+    raise ValueError("No such combination method")
+
+
+class OracleCVAE(nn.Module):
+    """Single-modality ``cVAE`` (cVAE.py:391-443).  Discriminator draws are burned, not kept."""
+
+    def __init__(self, input_dim, hidden_dim, latent_dim, c_dim, learning_rate=1e-4,
+                 modalities=4, non_linear=False):
+        super().__init__()
+        hd = list(hidden_dim) + [latent_dim]
+        self.encoder = OracleEncoder(input_dim, hd, c_dim, non_linear)
+        self.decoder = OracleDecoder(input_dim, hd, c_dim, non_linear)
+        _burn_discriminator(hd)
+        self.optimizer1 = torch.optim.Adam(
+            list(self.encoder.parameters()) + list(self.decoder.parameters()), lr=learning_rate)
+
+    def step_losses(self, x, c, eps=None):
+        """forward (cVAE.py:435-443) + loss_function (cVAE.py:491-504)."""
+        mu, logvar = self.encoder(x, c)
+        if eps is None:
+            eps = torch.randn_like(mu)
+        z = mu + eps * torch.exp(0.5 * logvar)
+        mu_out, lv_out = self.decoder(z, c)
+        kl = kl_term(mu, logvar)
+        ll = gauss_ll(x, mu_out, lv_out)
+        return {"total": kl - ll, "kl": kl, "ll": ll, "mu": mu, "logvar": logvar, "x_recon": mu_out}
+
+    def pred_recon(self, x, c):
+        """cVAE.py:549-555: decode the *mean*."""
+        with torch.no_grad():
+            mu, _ = self.encoder(x, c)
+            return self.decoder(mu, c)[0]
+
+
+class OracleCVAEMultimodal(nn.Module):
+    """``cVAE_multimodal`` (cVAE.py:1087-1211).  loss_kind: 'gauss_ll' | 'neg_mse'."""
+
+    def __init__(self, input_dim_list, hidden_dim, latent_dim, c_dim, learning_rate=1e-4,
+                 modalities=3, non_linear=False, loss_kind="gauss_ll"):
+        super().__init__()
+        hd = list(hidden_dim) + [latent_dim]
+        self.modalities = modalities
+        self.loss_kind = loss_kind
+        # RNG order: alphas, then encoders, then decoders (cVAE.py:1107-1109)
+        self.alpha_m_list = nn.ParameterList(
+            [nn.Parameter(torch.randn(1)) for _ in range(modalities)])
+        self.encoder_list = nn.ModuleList(
+            [OracleEncoder(input_dim_list[i], hd, c_dim, non_linear) for i in range(modalities)])
+        self.decoder_list = nn.ModuleList(
+            [OracleDecoder(input_dim_list[i], hd, c_dim, non_linear) for i in range(modalities)])
+        self.optimizer1 = torch.optim.Adam(
+            [p for e in self.encoder_list for p in e.parameters()]
+            + [p for d in self.decoder_list for p in d.parameters()]
+            + list(self.alpha_m_list.parameters()), lr=learning_rate)
+
+    def latent(self, xs, cs, combine):
+        enc = [self.encoder_list[i](xs[i], cs[i]) for i in range(self.modalities)]
+        mus = torch.stack([e[0] for e in enc])
+        variances = torch.exp(torch.stack([e[1] for e in enc]))
+        mu_mm, var_mm = fuse_latent(mus, variances, combine, list(self.alpha_m_list))
+        return mu_mm, torch.log(var_mm)
+
+    def step_losses(self, xs, cs, combine, eps=None):
+        """forward_multimodal (cVAE.py:1166-1182) + loss_function_multimodal (1187-1196)."""
+        mu_mm, logvar_mm = self.latent(xs, cs, combine)
+        if eps is None:
+            eps = torch.randn_like(mu_mm)
+        z = mu_mm + eps * torch.exp(0.5 * logvar_mm)
+        recons = [self.decoder_list[i](z, cs[i]) for i in range(self.modalities)]
+        total = kl_sum = ll_sum = 0
+        for i in range(self.modalities):
+            kl = kl_term(mu_mm, logvar_mm)
+            if self.loss_kind == "gauss_ll":
+                ll = gauss_ll(xs[i], recons[i][0], recons[i][1])
+            else:
+                ll = neg_mse_ll(xs[i], recons[i][0])
+            total = total + (kl - ll)
+            kl_sum = kl_sum + kl
+            ll_sum = ll_sum + ll
+        return {"total": total, "kl": kl_sum, "ll": ll_sum, "mu": mu_mm, "logvar": logvar_mm,
+                "x_recons": [r[0] for r in recons]}
+
+    def pred_recon(self, xs, c, combine, eps=None):
+        """cVAE.py:1198-1208: z is *sampled* at test time (eps injectable for determinism)."""
+        with torch.no_grad():
+            cs = [c] * self.modalities
+            mu_mm, logvar_mm = self.latent(xs, cs, combine)
+            if eps is None:
+                eps = torch.randn_like(mu_mm)
+            z = mu_mm + eps * torch.exp(0.5 * logvar_mm)
+            return [self.decoder_list[i](z, c)[0] for i in range(self.modalities)]
+
+
+def reference_train_loop(model, xs, cs, combine, epochs, batch_size=256, eps_fn=None,
+                         lr_fn=None):
+    """The hot loop of multimodal_kfold_train_cvae_supervised.py:177-199 (no shuffle, last
+    batch partial, LR untouched because ``optimizer1.lr = clr`` is a no-op, :183) and, when
+    ``lr_fn`` is given, of multimodal_kfold_cvae_nmmlp.py:374-400 (LR set per step through
+    param_groups).  xs / cs: lists of [N, D_m] / [N, C] tensors.  Returns per-step losses.
+    """
+    n = xs[0].shape[0]
+    log = []
+    step = 0
+    for _ in range(epochs):
+        for lo in range(0, n, batch_size):
+            step += 1
+            if lr_fn is not None:
+                for g in model.optimizer1.param_groups:
+                    g["lr"] = lr_fn(step)
+            xb = [x[lo:lo + batch_size] for x in xs]
+            cb = [c[lo:lo + batch_size] for c in cs]
+            eps = None if eps_fn is None else eps_fn(step - 1, xb[0].shape[0])
+            out = model.step_losses(xb, cb, combine, eps)
+            model.optimizer1.zero_grad()
+            out["total"].backward()
+            model.optimizer1.step()
+            log.append((float(out["total"]), float(out["kl"]), float(out["ll"])))
+    return np.asarray(log, dtype=np.float64)
+
+
+def cyclic_lr(step, n_samples, batch_size=256, base_lr=1e-6, max_lr=5e-5, gamma=0.98):
+    """Triangular cyclic LR of multimodal_kfold_cvae_nmmlp.py:363-381 (1-based global step)."""
+    step_size = 2 * np.ceil(n_samples / batch_size)
+    cycle = np.floor(1 + step / (2 * step_size))
+    x_lr = np.abs(step / step_size - 2 * cycle + 1)
+    return float(base_lr + (max_lr - base_lr) * max(0, 1 - x_lr) * gamma ** cycle)
