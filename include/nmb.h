@@ -1,0 +1,194 @@
+/*
+ * nmb.h -- C ABI of libnmb.so: the B200 (sm_100a) implementation of the ONE hot path of
+ * soz223/multi_modal_normative_modeling: training many small conditional VAEs at once and
+ * scoring per-subject / per-ROI deviations.
+ *
+ * The reference has no FFI layer: its boundary is a Python class + CLI contract
+ * (SURVEY.md section 8b).  Each entry point below names the reference interface
+ * (file:line, relative to the upstream repository) whose work it replaces; the Python
+ * nn.Module shims in multi_modal_normative_modeling_b200/ bind these through ctypes.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only; no torch / C++ types.
+ *   - every function returns 0 on success, non-zero on error; nmb_last_error() returns
+ *     a thread-local message for the last failure.
+ *   - all data pointers are DEVICE pointers owned by the caller (torch tensors) unless a
+ *     parameter is documented as host memory.  All tensors are fp32, row-major.
+ *   - every launch takes the CUDA stream as a void* (cudaStream_t); no internal threads,
+ *     no hidden synchronisation except where documented.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef NMB_H_
+#define NMB_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NMB_MAX_MOD 16    /* modalities per model (HCP uses 12 + early fusion) */
+#define NMB_MAX_HIDDEN 4  /* hidden layers per encoder/decoder (hz_para_list up to "1024 512 256 32") */
+
+/* combine_latent kinds, cVAE.py:1144-1164 (case-insensitive strings in the reference) */
+enum { NMB_COMBINE_POE = 0, NMB_COMBINE_GPOE = 1, NMB_COMBINE_MOE = 2, NMB_COMBINE_MOPOE = 3 };
+/* reconstruction term: Gaussian log-likelihood with learned logvar_out (cVAE.py:14-15,193-206)
+ * or -MSE(mean) (multimodal_kfold_cvae_nmmlp.py:124-127) */
+enum { NMB_LOSS_GAUSS_LL = 0, NMB_LOSS_NEG_MSE = 1 };
+
+/* Architecture of one ensemble member = the constructor arguments of
+ * cVAE_multimodal(input_dim_list, hidden_dim, latent_dim, c_dim, ..., modalities, non_linear)
+ * (cVAE.py:1088-1116); the single-modality cVAE (cVAE.py:391-411) is n_mod == 1. */
+typedef struct {
+  int32_t n_mod;
+  int32_t input_dims[NMB_MAX_MOD];
+  int32_t n_hidden;
+  int32_t hidden[NMB_MAX_HIDDEN];
+  int32_t latent;
+  int32_t c_dim;
+  int32_t combine;    /* NMB_COMBINE_* */
+  int32_t loss_kind;  /* NMB_LOSS_* */
+  int32_t non_linear; /* leaky_relu(0.01) after hidden layers (cVAE.py:166-167) */
+} NmbArch;
+
+/* One tensor of the reference's state_dict inside the packed per-model parameter buffer.
+ * A linear layer (in -> out) is stored as an augmented matrix [out][ld], ld = roundup4(in+1):
+ * row n = { weight[n][0..in-1], bias[n], 0... }.  The mean and logvar heads are stacked
+ * (rows 0..Z-1 = enc_mean_layer, Z..2Z-1 = enc_logvar_layer). */
+enum { NMB_SLOT_ENC = 0, NMB_SLOT_ENC_MEAN = 1, NMB_SLOT_ENC_LOGVAR = 2, NMB_SLOT_DEC = 3,
+       NMB_SLOT_DEC_MEAN = 4, NMB_SLOT_LOGVAR_OUT = 5, NMB_SLOT_ALPHA = 6 };
+typedef struct {
+  int32_t kind;      /* NMB_SLOT_* */
+  int32_t modality;
+  int32_t layer;     /* index inside encoder_layers / decoder_layers */
+  int32_t rows;      /* out features (1 for logvar_out / alpha) */
+  int32_t cols;      /* in features  (D for logvar_out, 1 for alpha) */
+  int32_t ld;        /* row stride in floats */
+  int64_t offset;    /* float offset of element [0][0]; bias of row n is at offset + n*ld + cols */
+} NmbSlot;
+
+/* One ensemble member: architecture, training rows, optimiser settings, state buffers.
+ * Replaces one iteration of the fold / modality / seed loops of
+ * multimodal_kfold_train_cvae_supervised.py:68-212. */
+typedef struct {
+  NmbArch arch;
+  const float* xc[NMB_MAX_MOD]; /* per modality: packed rows [n_rows][ldx] from nmb_pack_rows */
+  int32_t n_rows;               /* training rows (after bootstrap + merge) */
+  int32_t batch;                /* 256 in the reference (train script :116); no shuffle, last batch partial */
+  uint64_t seed;                /* Philox key of the in-kernel eps stream */
+  float lr, beta1, beta2, adam_eps; /* torch.optim.Adam defaults 1e-4, .9, .999, 1e-8 (cVAE.py:1111-1116) */
+  const float* lr_steps;        /* optional [>= total steps] per-step LR (nmmlp cyclic schedule :363-381) */
+  float* params;                /* [n_params] packed, see NmbSlot */
+  float* adam_m;                /* [n_params] exp_avg    */
+  float* adam_v;                /* [n_params] exp_avg_sq */
+  float* grads;                 /* [n_params] or NULL; written when NMB_TRAIN_WRITE_GRADS */
+} NmbMember;
+
+typedef struct NmbEnsemble NmbEnsemble;
+
+/* ---- errors / introspection ------------------------------------------------------- */
+const char* nmb_last_error(void);
+int nmb_version(void);
+int nmb_device_count(int* count);
+
+/* ---- layout ------------------------------------------------------------------------ */
+int nmb_arch_param_count(const NmbArch* arch, int64_t* n_params);
+/* Fills up to max_slots entries in reference state_dict order
+ * (alpha_m_list.*, encoder_list.*, decoder_list.*; cVAE.py:1107-1109); *n_slots = total. */
+int nmb_arch_slots(const NmbArch* arch, NmbSlot* slots, int32_t max_slots, int32_t* n_slots);
+/* Row stride of a packed dataset row [x | c | 1 | 0-pad]. */
+int nmb_packed_row_stride(int32_t d, int32_t c_dim, int32_t* ldx);
+
+/* ---- data staging ------------------------------------------------------------------ */
+/* out[i] = { x[i][0..d), c[i][0..c_dim), 1, 0... }  -- the cat((x, c), dim=1) of
+ * Encoder.forward (cVAE.py:163) done once per dataset instead of once per minibatch,
+ * plus the constant-1 column that carries the bias through the GEMMs. */
+int nmb_pack_rows(const float* x, const float* c, int64_t n_rows, int32_t d, int32_t c_dim,
+                  float* out, void* stream);
+
+/* ---- ensemble ---------------------------------------------------------------------- */
+int nmb_ensemble_create(NmbEnsemble** out, int32_t device, const NmbMember* members /*host*/,
+                        int32_t n_members);
+int nmb_ensemble_destroy(NmbEnsemble* ens);
+int nmb_ensemble_size(const NmbEnsemble* ens, int32_t* n_members);
+/* steps already taken by each member (global_step of the train script :178), host out */
+int nmb_ensemble_steps_done(NmbEnsemble* ens, int64_t* steps /*host [n_members]*/, void* stream);
+
+enum {
+  NMB_TRAIN_NO_ADAM = 1,     /* forward + loss + backward only (parity of gradients) */
+  NMB_TRAIN_WRITE_GRADS = 2, /* store d(total)/d(param) into NmbMember.grads */
+  NMB_TRAIN_KEEP_ACTS = 4    /* keep x_recon in scratch instead of overwriting it with its gradient */
+};
+/* The fused hot loop: for every member, n_steps minibatch steps of
+ *   forward_multimodal -> loss_function_multimodal -> zero_grad -> backward -> optimizer1.step()
+ * (multimodal_kfold_train_cvae_supervised.py:177-199, cVAE.py:1166-1196, torch Adam), one
+ * launch for the whole ensemble.  Step s of a member uses rows [pos*batch, pos*batch+batch)
+ * with pos = s mod ceil(n_rows/batch).
+ *   eps_override : NULL (in-kernel Philox) or [n_members][n_steps][batch][latent] injected draws
+ *   loss_out     : NULL or [n_members][n_steps][3] = (total, kl, ll) per step
+ *                  (the values the train script prints at batch 0, :201-203) */
+int nmb_ensemble_train(NmbEnsemble* ens, int64_t n_steps, const float* eps_override,
+                       float* loss_out, uint32_t flags, void* stream);
+
+/* Activations of the LAST executed step of one member (debug / per-step parity):
+ * mu, logvar: fused latent [rows][latent]; x_recon[m]: [rows][input_dims[m]] (needs
+ * NMB_TRAIN_KEEP_ACTS).  Any pointer may be NULL.  rows = size of that step's minibatch. */
+int nmb_ensemble_peek(NmbEnsemble* ens, int32_t member, float* mu, float* logvar,
+                      float* const* x_recon /*host array of device ptrs*/, int32_t* rows /*host*/,
+                      void* stream);
+
+enum { NMB_RECON_MEAN = 0, NMB_RECON_SAMPLE = 1 };
+/* Test-time reconstruction for every member on its own rows:
+ *   mode MEAN   : decode(mu)                       -- cVAE.pred_recon, cVAE.py:549-555
+ *   mode SAMPLE : decode(mu + eps*exp(logvar/2))   -- cVAE_multimodal.pred_recon, cVAE.py:1198-1208
+ * xc[i*NMB_MAX_MOD+m]   : packed rows of member i, modality m ([n_rows[i]][ldx])
+ * xhat[i*NMB_MAX_MOD+m] : out [n_rows[i]][input_dims[m]]
+ * mu/logvar[i]          : optional out [n_rows[i]][latent] (fused latent; pred_latent :540-547)
+ * eps[i]                : optional injected draws [n_rows[i]][latent] for SAMPLE (else Philox stream 1)
+ * All pointer tables and n_rows are HOST arrays. */
+int nmb_ensemble_reconstruct(NmbEnsemble* ens, const float* const* xc, const int32_t* n_rows,
+                             int32_t mode, const float* const* eps, float* const* xhat,
+                             float* const* mu, float* const* logvar, void* stream);
+
+/* ---- deviation scoring (streaming, HBM-bound) --------------------------------------- */
+/* Batched over `n_seg` independent (member, modality) segments; tables are HOST arrays of
+ * device pointers / sizes. x rows have stride ldx (packed rows) -- only the first d columns
+ * are read; xhat rows have stride d. */
+
+/* Per-ROI normative statistics over the reference rows (mask[i] != 0, or all rows if NULL):
+ *   mean_d = mean_i r_id, std_d = population std_i r_id, r = (x - xhat)^2.
+ * The ROI-space analogue of separate_latent_deviation (utils_vae.py:155-161); defined in
+ * oracle/deviation.py.  out_stats[s] : [2][d] = (mean row, std row). */
+int nmb_normative_stats(int32_t n_seg, const float* const* x, const int32_t* ldx,
+                        const float* const* xhat, const uint8_t* const* mask,
+                        const int32_t* n_rows, const int32_t* d, float* const* out_stats,
+                        void* stream);
+
+/* dev_roi = (x - xhat)^2 (test script :141), dev_subj = sum_d dev_roi / D (cVAE.py:1210-1211),
+ * z = (dev_roi - mean_d) / std_d when stats[s] != NULL.  dev_roi / z may be NULL. */
+int nmb_deviation(int32_t n_seg, const float* const* x, const int32_t* ldx,
+                  const float* const* xhat, const float* const* stats, const int32_t* n_rows,
+                  const int32_t* d, float* const* dev_roi, float* const* z,
+                  float* const* dev_subj, void* stream);
+
+/* ROC-AUC of every column of `scores[s]` ([n_rows][n_cols], row stride n_cols) against
+ * binary labels[s] (uint8, 1 = patient): exact pair counting with tie half-credit
+ * == sklearn roc_curve + auc (multimodal_kfold_cvae_group_analysis_1x1.py:123-124).
+ * out_auc[s]: [n_cols] float64;  out_u2[s] (optional): [n_cols] uint64 pair counts
+ * U2 = sum_{pos,neg} 2*[s_p > s_n] + [s_p == s_n]  (AUC = U2 / (2 n_pos n_neg)). */
+int nmb_auc(int32_t n_seg, const float* const* scores, const uint8_t* const* labels,
+            const int32_t* n_rows, const int32_t* n_cols, double* const* out_auc,
+            unsigned long long* const* out_u2, void* stream);
+
+/* Mean of k score vectors (modality averaging, group analysis :212-215). */
+int nmb_mean_rows(const float* const* src /*host table*/, int32_t k, int64_t n, float* out,
+                  void* stream);
+
+/* In-kernel eps stream exposed for tests: out[i] = eps(seed, step, element i, stream id). */
+int nmb_philox_normal(uint64_t seed, uint64_t step, uint32_t stream_id, int64_t n, float* out,
+                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NMB_H_ */

@@ -1,0 +1,395 @@
+// C ABI of libnmb.so (see include/nmb.h for the contract and the reference citations).
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "nmb_internal.h"
+
+using namespace nmb;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(const std::string& m) { g_err = m; return 1; }
+int cuda_fail(const char* what, cudaError_t e) {
+  g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  return 2;
+}
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(#call, e_); } while (0)
+
+// Host blob -> one stream-ordered device allocation holding all per-call argument tables.
+struct Blob {
+  std::vector<unsigned char> host;
+  void* dev = nullptr;
+  size_t add(const void* p, size_t bytes) {
+    size_t off = (host.size() + 15) & ~size_t(15);
+    host.resize(off + bytes);
+    if (p) std::memcpy(host.data() + off, p, bytes); else std::memset(host.data() + off, 0, bytes);
+    return off;
+  }
+  cudaError_t upload(cudaStream_t st) {
+    cudaError_t e = cudaMallocAsync(&dev, host.size() ? host.size() : 16, st);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyAsync(dev, host.data(), host.size(), cudaMemcpyHostToDevice, st);
+  }
+  template <class T> T* at(size_t off) const { return reinterpret_cast<T*>(static_cast<unsigned char*>(dev) + off); }
+  cudaError_t release(cudaStream_t st) { return dev ? cudaFreeAsync(dev, st) : cudaSuccess; }
+};
+
+bool same_arch(const NmbArch& a, const NmbArch& b) { return std::memcmp(&a, &b, sizeof(NmbArch)) == 0; }
+
+NmbArch canonical(const NmbArch& a) {   // zero the unused tails so memcmp is meaningful
+  NmbArch c;
+  std::memset(&c, 0, sizeof(c));
+  c.n_mod = a.n_mod; c.n_hidden = a.n_hidden; c.latent = a.latent; c.c_dim = a.c_dim;
+  c.combine = a.combine; c.loss_kind = a.loss_kind; c.non_linear = a.non_linear ? 1 : 0;
+  for (int i = 0; i < a.n_mod && i < NMB_MAX_MOD; ++i) c.input_dims[i] = a.input_dims[i];
+  for (int i = 0; i < a.n_hidden && i < NMB_MAX_HIDDEN; ++i) c.hidden[i] = a.hidden[i];
+  return c;
+}
+
+}  // namespace
+
+struct NmbEnsemble {
+  int device = 0;
+  int n_members = 0;
+  std::vector<NmbArch> archs_host;
+  std::vector<ArchDesc> archs;
+  std::vector<int> arch_idx;
+  std::vector<MemberDev> members_host;
+  MemberDev* members_dev = nullptr;
+  ArchDesc* archs_dev = nullptr;
+  float* scratch = nullptr;
+  long long slot_floats = 0;
+  int n_slots = 0;
+  int* work_counter = nullptr;
+};
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+const char* nmb_last_error(void) { return g_err.c_str(); }
+int nmb_version(void) { return 100; }
+
+int nmb_device_count(int* count) {
+  if (!count) return fail("null count");
+  CU(cudaGetDeviceCount(count));
+  return 0;
+}
+
+int nmb_arch_param_count(const NmbArch* arch, int64_t* n_params) {
+  if (!arch || !n_params) return fail("null argument");
+  ArchDesc d; const char* err = nullptr;
+  if (build_arch(*arch, &d, &err)) return fail(err);
+  *n_params = d.n_params;
+  return 0;
+}
+
+int nmb_packed_row_stride(int32_t d, int32_t c_dim, int32_t* ldx) {
+  if (!ldx || d < 1 || c_dim < 0) return fail("bad argument");
+  *ldx = round4(d + c_dim + 1);
+  return 0;
+}
+
+int nmb_arch_slots(const NmbArch* arch, NmbSlot* slots, int32_t max_slots, int32_t* n_slots) {
+  if (!arch || !n_slots) return fail("null argument");
+  ArchDesc d; const char* err = nullptr;
+  if (build_arch(*arch, &d, &err)) return fail(err);
+  std::vector<NmbSlot> v;
+  auto push = [&](int kind, int m, int layer, int rows, int cols, int ld, long long off) {
+    NmbSlot s; s.kind = kind; s.modality = m; s.layer = layer; s.rows = rows; s.cols = cols; s.ld = ld; s.offset = off;
+    v.push_back(s);
+  };
+  for (int m = 0; m < d.M; ++m) push(NMB_SLOT_ALPHA, m, 0, 1, 1, 1, d.alpha_off + m);
+  for (int m = 0; m < d.M; ++m) {
+    const ModDesc& q = d.mod[m];
+    for (int l = 0; l < d.L; ++l) push(NMB_SLOT_ENC, m, l, q.enc[l].out, q.enc[l].in, q.enc[l].ld, q.enc[l].off);
+    push(NMB_SLOT_ENC_MEAN, m, 0, d.Z, q.head.in, q.head.ld, q.head.off);
+    push(NMB_SLOT_ENC_LOGVAR, m, 0, d.Z, q.head.in, q.head.ld, q.head.off + (long long)d.Z * q.head.ld);
+  }
+  for (int m = 0; m < d.M; ++m) {
+    const ModDesc& q = d.mod[m];
+    push(NMB_SLOT_LOGVAR_OUT, m, 0, 1, q.D, round4(q.D), q.lam_off);
+    for (int l = 0; l < d.L; ++l) push(NMB_SLOT_DEC, m, l, q.dec[l].out, q.dec[l].in, q.dec[l].ld, q.dec[l].off);
+    push(NMB_SLOT_DEC_MEAN, m, 0, q.outl.out, q.outl.in, q.outl.ld, q.outl.off);
+  }
+  *n_slots = (int32_t)v.size();
+  if (slots) for (int i = 0; i < (int)v.size() && i < max_slots; ++i) slots[i] = v[i];
+  return 0;
+}
+
+int nmb_pack_rows(const float* x, const float* c, int64_t n_rows, int32_t d, int32_t c_dim, float* out, void* stream) {
+  if (!x || (!c && c_dim > 0) || !out || n_rows < 0 || d < 1 || c_dim < 0) return fail("bad argument");
+  launch_pack_rows(x, c, n_rows, d, c_dim, round4(d + c_dim + 1), out, (cudaStream_t)stream);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int nmb_ensemble_create(NmbEnsemble** out, int32_t device, const NmbMember* members, int32_t n_members) {
+  if (!out || !members || n_members < 1) return fail("bad argument");
+  int count = 0;
+  CU(cudaGetDeviceCount(&count));
+  if (device < 0 || device >= count) return fail("no such CUDA device (libnmb has no CPU fallback)");
+  CU(cudaSetDevice(device));
+  CU(configure_kernels());
+  NmbEnsemble* e = new NmbEnsemble();
+  e->device = device; e->n_members = n_members;
+  long long max_slot = 0;
+  for (int i = 0; i < n_members; ++i) {
+    const NmbMember& mm = members[i];
+    const NmbArch ca = canonical(mm.arch);
+    int ai = -1;
+    for (int k = 0; k < (int)e->archs_host.size(); ++k) if (same_arch(e->archs_host[k], ca)) { ai = k; break; }
+    if (ai < 0) {
+      ArchDesc d; const char* err = nullptr;
+      if (build_arch(ca, &d, &err)) { delete e; return fail(err); }
+      e->archs_host.push_back(ca); e->archs.push_back(d); ai = (int)e->archs.size() - 1;
+    }
+    const ArchDesc& d = e->archs[ai];
+    if (d.scratch_floats > max_slot) max_slot = d.scratch_floats;
+    if (mm.n_rows < 0 || mm.batch < 1 || mm.batch > kMaxBatch) { delete e; return fail("batch must be in 1..256"); }
+    if (!mm.params || !mm.adam_m || !mm.adam_v) { delete e; return fail("null state buffer"); }
+    MemberDev md; std::memset(&md, 0, sizeof(md));
+    md.arch_idx = ai; md.n_rows = mm.n_rows; md.batch = mm.batch;
+    for (int m = 0; m < d.M; ++m) md.xc[m] = mm.xc[m];
+    md.params = mm.params; md.adam_m = mm.adam_m; md.adam_v = mm.adam_v; md.grads = mm.grads;
+    md.lr_steps = mm.lr_steps; md.seed = mm.seed;
+    md.lr = mm.lr; md.beta1 = mm.beta1; md.beta2 = mm.beta2; md.adam_eps = mm.adam_eps;
+    md.steps_done = 0; md.last_rows = 0; md.last_slot = -1;
+    e->members_host.push_back(md); e->arch_idx.push_back(ai);
+  }
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  e->n_slots = 2 * prop.multiProcessorCount;             // 2 resident CTAs per SM
+  e->slot_floats = max_slot;
+  auto cleanup = [&]() { nmb_ensemble_destroy(e); };
+  cudaError_t ce;
+  if ((ce = cudaMalloc(&e->members_dev, sizeof(MemberDev) * n_members)) != cudaSuccess ||
+      (ce = cudaMalloc(&e->archs_dev, sizeof(ArchDesc) * e->archs.size())) != cudaSuccess ||
+      (ce = cudaMalloc(&e->scratch, sizeof(float) * (size_t)e->slot_floats * e->n_slots)) != cudaSuccess ||
+      (ce = cudaMalloc(&e->work_counter, sizeof(int))) != cudaSuccess ||
+      (ce = cudaMemcpy(e->members_dev, e->members_host.data(), sizeof(MemberDev) * n_members, cudaMemcpyHostToDevice)) != cudaSuccess ||
+      (ce = cudaMemcpy(e->archs_dev, e->archs.data(), sizeof(ArchDesc) * e->archs.size(), cudaMemcpyHostToDevice)) != cudaSuccess ||
+      (ce = cudaMemset(e->scratch, 0, sizeof(float) * (size_t)e->slot_floats * e->n_slots)) != cudaSuccess) {
+    cleanup();
+    return cuda_fail("nmb_ensemble_create", ce);
+  }
+  *out = e;
+  return 0;
+}
+
+int nmb_ensemble_destroy(NmbEnsemble* e) {
+  if (!e) return 0;
+  cudaSetDevice(e->device);
+  cudaFree(e->members_dev); cudaFree(e->archs_dev); cudaFree(e->scratch); cudaFree(e->work_counter);
+  delete e;
+  return 0;
+}
+
+int nmb_ensemble_size(const NmbEnsemble* e, int32_t* n) {
+  if (!e || !n) return fail("null argument");
+  *n = e->n_members;
+  return 0;
+}
+
+int nmb_ensemble_steps_done(NmbEnsemble* e, int64_t* steps, void* stream) {
+  if (!e || !steps) return fail("null argument");
+  CU(cudaSetDevice(e->device));
+  CU(cudaMemcpyAsync(e->members_host.data(), e->members_dev, sizeof(MemberDev) * e->n_members,
+                     cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CU(cudaStreamSynchronize((cudaStream_t)stream));
+  for (int i = 0; i < e->n_members; ++i) steps[i] = e->members_host[i].steps_done;
+  return 0;
+}
+
+int nmb_ensemble_train(NmbEnsemble* e, int64_t n_steps, const float* eps_override, float* loss_out, uint32_t flags,
+                       void* stream) {
+  if (!e) return fail("null ensemble");
+  if (n_steps < 0) return fail("negative n_steps");
+  if ((flags & NMB_TRAIN_WRITE_GRADS)) {
+    for (const MemberDev& m : e->members_host) if (!m.grads) return fail("NMB_TRAIN_WRITE_GRADS needs NmbMember.grads");
+  }
+  for (const MemberDev& m : e->members_host) if (m.n_rows < 1) return fail("member without training rows");
+  CU(cudaSetDevice(e->device));
+  TrainLaunch t;
+  t.members = e->members_dev; t.archs = e->archs_dev; t.n_members = e->n_members;
+  t.n_steps = n_steps; t.eps_override = eps_override; t.loss_out = loss_out; t.flags = flags;
+  t.scratch = e->scratch; t.slot_floats = e->slot_floats; t.n_slots = e->n_slots; t.work_counter = e->work_counter;
+  CU(launch_train(t, (cudaStream_t)stream));
+  return 0;
+}
+
+int nmb_ensemble_peek(NmbEnsemble* e, int32_t member, float* mu, float* logvar, float* const* x_recon, int32_t* rows,
+                      void* stream) {
+  if (!e || member < 0 || member >= e->n_members) return fail("bad member");
+  if (e->n_members > e->n_slots) return fail("peek needs n_members <= resident slots (debug API)");
+  cudaStream_t st = (cudaStream_t)stream;
+  CU(cudaSetDevice(e->device));
+  MemberDev md;
+  CU(cudaMemcpyAsync(&md, e->members_dev + member, sizeof(MemberDev), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  if (md.last_slot < 0) return fail("member has not run a step yet");
+  const ArchDesc& a = e->archs[e->arch_idx[member]];
+  const float* S = e->scratch + (long long)md.last_slot * e->slot_floats;
+  if (rows) *rows = md.last_rows;
+  const size_t lat = sizeof(float) * (size_t)md.last_rows * a.Z;
+  if (mu) CU(cudaMemcpyAsync(mu, S + a.s_mub, lat, cudaMemcpyDeviceToDevice, st));
+  if (logvar) CU(cudaMemcpyAsync(logvar, S + a.s_lvb, lat, cudaMemcpyDeviceToDevice, st));
+  if (x_recon) {
+    for (int m = 0; m < a.M; ++m) {
+      if (!x_recon[m]) continue;
+      const ModDesc& q = a.mod[m];
+      CU(cudaMemcpy2DAsync(x_recon[m], sizeof(float) * q.D, S + q.s_xr, sizeof(float) * q.ld_xh, sizeof(float) * q.D,
+                           md.last_rows, cudaMemcpyDeviceToDevice, st));
+    }
+  }
+  return 0;
+}
+
+int nmb_ensemble_reconstruct(NmbEnsemble* e, const float* const* xc, const int32_t* n_rows, int32_t mode,
+                             const float* const* eps, float* const* xhat, float* const* mu, float* const* logvar,
+                             void* stream) {
+  if (!e || !xc || !n_rows || !xhat) return fail("null argument");
+  if (mode != NMB_RECON_MEAN && mode != NMB_RECON_SAMPLE) return fail("bad mode");
+  cudaStream_t st = (cudaStream_t)stream;
+  CU(cudaSetDevice(e->device));
+  std::vector<ReconItem> items;
+  const int n = e->n_members;
+  for (int i = 0; i < n; ++i) {
+    if (n_rows[i] < 0) return fail("negative n_rows");
+    const ArchDesc& a = e->archs[e->arch_idx[i]];
+    for (int m = 0; m < a.M; ++m) if (n_rows[i] > 0 && !xc[i * NMB_MAX_MOD + m]) return fail("null xc entry");
+    for (int r = 0; r < n_rows[i]; r += kMaxBatch) {
+      ReconItem it; it.member = i; it.row0 = r; it.rows = n_rows[i] - r < kMaxBatch ? n_rows[i] - r : kMaxBatch;
+      items.push_back(it);
+    }
+  }
+  if (items.empty()) return 0;
+  Blob b;
+  const size_t o_items = b.add(items.data(), sizeof(ReconItem) * items.size());
+  const size_t o_xc = b.add(xc, sizeof(void*) * (size_t)n * NMB_MAX_MOD);
+  const size_t o_xh = b.add(xhat, sizeof(void*) * (size_t)n * NMB_MAX_MOD);
+  const size_t o_eps = eps ? b.add(eps, sizeof(void*) * n) : 0;
+  const size_t o_mu = mu ? b.add(mu, sizeof(void*) * n) : 0;
+  const size_t o_lv = logvar ? b.add(logvar, sizeof(void*) * n) : 0;
+  CU(b.upload(st));
+  ReconLaunch t;
+  t.members = e->members_dev; t.archs = e->archs_dev;
+  t.items = b.at<ReconItem>(o_items); t.n_items = (int)items.size();
+  t.xc = b.at<const float*>(o_xc); t.xhat = b.at<float*>(o_xh);
+  t.eps = eps ? b.at<const float*>(o_eps) : nullptr;
+  t.mu = mu ? b.at<float*>(o_mu) : nullptr;
+  t.logvar = logvar ? b.at<float*>(o_lv) : nullptr;
+  t.mode = mode; t.scratch = e->scratch; t.slot_floats = e->slot_floats; t.n_slots = e->n_slots;
+  CU(launch_recon(t, st));
+  CU(b.release(st));
+  return 0;
+}
+
+static int seg_common(int32_t n_seg, const int32_t* n_rows, const int32_t* d, int* max_rows, int* max_d) {
+  *max_rows = 0; *max_d = 0;
+  for (int i = 0; i < n_seg; ++i) {
+    if (n_rows[i] < 0 || d[i] < 1) return fail("bad segment size");
+    if (n_rows[i] > *max_rows) *max_rows = n_rows[i];
+    if (d[i] > *max_d) *max_d = d[i];
+  }
+  return 0;
+}
+
+int nmb_normative_stats(int32_t n_seg, const float* const* x, const int32_t* ldx, const float* const* xhat,
+                        const uint8_t* const* mask, const int32_t* n_rows, const int32_t* d,
+                        float* const* out_stats, void* stream) {
+  if (n_seg < 0 || (n_seg && (!x || !ldx || !xhat || !n_rows || !d || !out_stats))) return fail("bad argument");
+  if (n_seg == 0) return 0;
+  int mr, md;
+  if (seg_common(n_seg, n_rows, d, &mr, &md)) return 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  Blob b;
+  SegTable t; std::memset(&t, 0, sizeof(t));
+  const size_t ox = b.add(x, sizeof(void*) * n_seg), ol = b.add(ldx, sizeof(int) * n_seg);
+  const size_t oh = b.add(xhat, sizeof(void*) * n_seg), on = b.add(n_rows, sizeof(int) * n_seg);
+  const size_t od = b.add(d, sizeof(int) * n_seg), oo = b.add(out_stats, sizeof(void*) * n_seg);
+  const size_t om = mask ? b.add(mask, sizeof(void*) * n_seg) : 0;
+  CU(b.upload(st));
+  t.x = b.at<const float*>(ox); t.ldx = b.at<int>(ol); t.xhat = b.at<const float*>(oh);
+  t.n_rows = b.at<int>(on); t.d = b.at<int>(od); t.stats_out = b.at<float*>(oo);
+  t.mask = mask ? b.at<const uint8_t*>(om) : nullptr;
+  launch_stats(t, n_seg, md, st);
+  CU(cudaGetLastError());
+  CU(b.release(st));
+  return 0;
+}
+
+int nmb_deviation(int32_t n_seg, const float* const* x, const int32_t* ldx, const float* const* xhat,
+                  const float* const* stats, const int32_t* n_rows, const int32_t* d, float* const* dev_roi,
+                  float* const* z, float* const* dev_subj, void* stream) {
+  if (n_seg < 0 || (n_seg && (!x || !ldx || !xhat || !n_rows || !d))) return fail("bad argument");
+  if (n_seg == 0) return 0;
+  int mr, md;
+  if (seg_common(n_seg, n_rows, d, &mr, &md)) return 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  Blob b;
+  SegTable t; std::memset(&t, 0, sizeof(t));
+  const size_t ox = b.add(x, sizeof(void*) * n_seg), ol = b.add(ldx, sizeof(int) * n_seg);
+  const size_t oh = b.add(xhat, sizeof(void*) * n_seg), on = b.add(n_rows, sizeof(int) * n_seg);
+  const size_t od = b.add(d, sizeof(int) * n_seg);
+  const size_t os = stats ? b.add(stats, sizeof(void*) * n_seg) : 0;
+  const size_t orr = dev_roi ? b.add(dev_roi, sizeof(void*) * n_seg) : 0;
+  const size_t oz = z ? b.add(z, sizeof(void*) * n_seg) : 0;
+  const size_t oj = dev_subj ? b.add(dev_subj, sizeof(void*) * n_seg) : 0;
+  CU(b.upload(st));
+  t.x = b.at<const float*>(ox); t.ldx = b.at<int>(ol); t.xhat = b.at<const float*>(oh);
+  t.n_rows = b.at<int>(on); t.d = b.at<int>(od);
+  t.stats = stats ? b.at<const float*>(os) : nullptr;
+  t.dev_roi = dev_roi ? b.at<float*>(orr) : nullptr;
+  t.z = z ? b.at<float*>(oz) : nullptr;
+  t.dev_subj = dev_subj ? b.at<float*>(oj) : nullptr;
+  launch_deviation(t, n_seg, mr, st);
+  CU(cudaGetLastError());
+  CU(b.release(st));
+  return 0;
+}
+
+int nmb_auc(int32_t n_seg, const float* const* scores, const uint8_t* const* labels, const int32_t* n_rows,
+            const int32_t* n_cols, double* const* out_auc, unsigned long long* const* out_u2, void* stream) {
+  if (n_seg < 0 || (n_seg && (!scores || !labels || !n_rows || !n_cols || !out_auc))) return fail("bad argument");
+  if (n_seg == 0) return 0;
+  int mr, mc;
+  if (seg_common(n_seg, n_rows, n_cols, &mr, &mc)) return 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  Blob b;
+  AucTable t; std::memset(&t, 0, sizeof(t));
+  const size_t os = b.add(scores, sizeof(void*) * n_seg), ol = b.add(labels, sizeof(void*) * n_seg);
+  const size_t on = b.add(n_rows, sizeof(int) * n_seg), oc = b.add(n_cols, sizeof(int) * n_seg);
+  const size_t oa = b.add(out_auc, sizeof(void*) * n_seg);
+  const size_t ou = out_u2 ? b.add(out_u2, sizeof(void*) * n_seg) : 0;
+  CU(b.upload(st));
+  t.scores = b.at<const float*>(os); t.labels = b.at<const uint8_t*>(ol);
+  t.n_rows = b.at<int>(on); t.n_cols = b.at<int>(oc); t.out_auc = b.at<double*>(oa);
+  t.out_u2 = out_u2 ? b.at<unsigned long long*>(ou) : nullptr;
+  launch_auc(t, n_seg, mc, st);
+  CU(cudaGetLastError());
+  CU(b.release(st));
+  return 0;
+}
+
+int nmb_mean_rows(const float* const* src, int32_t k, int64_t n, float* out, void* stream) {
+  if (!src || !out || k < 1 || k > 16 || n < 0) return fail("bad argument (k must be 1..16)");
+  PtrTable16 t; std::memset(&t, 0, sizeof(t));
+  for (int i = 0; i < k; ++i) { if (!src[i]) return fail("null source"); t.p[i] = src[i]; }
+  launch_mean_rows(t, k, n, out, (cudaStream_t)stream);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int nmb_philox_normal(uint64_t seed, uint64_t step, uint32_t stream_id, int64_t n, float* out, void* stream) {
+  if (!out || n < 0) return fail("bad argument");
+  launch_philox(seed, step, stream_id, n, out, (cudaStream_t)stream);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+#pragma GCC visibility pop
+}  // extern "C"

@@ -1,0 +1,171 @@
+// Shared host/device definitions for libnmb: packed-parameter layout, scratch layout,
+// Philox eps stream, deterministic block reductions.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/nmb.h"
+
+namespace nmb {
+
+constexpr int kThreads = 256;      // threads per CTA of every GEMM-bearing kernel
+constexpr int kMaxBatch = 256;     // minibatch rows a CTA processes per step / row tile
+constexpr float kSlope = 0.01f;    // F.leaky_relu default (cVAE.py:167)
+constexpr float kLog2Pi = 1.8378770664093453f;
+
+__host__ __device__ inline int round4(int v) { return (v + 3) & ~3; }
+
+// One linear layer stored augmented: W_aug[out][ld], ld = round4(in + 1), column `in` = bias.
+struct LinDesc {
+  int in, out, ld;
+  long long off;   // float offset in the packed parameter buffer
+};
+
+struct ModDesc {
+  int D, ldx;                            // ROI count; stride of packed dataset rows [x | c | 1]
+  LinDesc enc[NMB_MAX_HIDDEN], head, dec[NMB_MAX_HIDDEN], outl;
+  long long lam_off;                     // logvar_out [D]
+  // per-CTA scratch (float offsets).  Activations are stored post-nonlinearity with a
+  // constant-1 column appended (index = width) so that biases ride through the GEMMs.
+  long long s_h[NMB_MAX_HIDDEN];  int ld_h[NMB_MAX_HIDDEN];   // encoder hidden
+  long long s_k[NMB_MAX_HIDDEN];  int ld_k[NMB_MAX_HIDDEN];   // decoder hidden
+  long long s_mulv, s_dmulv;      int ld_mulv;                // [mu | logvar] heads and their grads
+  long long s_g0;                 int ld_g0;                  // decoder input [z | c | 1]
+  long long s_xh;                 int ld_xh;                  // d(total)/d(x_recon)
+  long long s_xr;                                             // x_recon kept for nmb_ensemble_peek
+};
+
+struct ArchDesc {
+  int M, L, Z, C, combine, loss_kind, non_linear;
+  int hidden[NMB_MAX_HIDDEN];
+  ModDesc mod[NMB_MAX_MOD];
+  long long alpha_off;
+  long long n_params;
+  long long s_mub, s_lvb, s_eps, s_dz;   // fused mu, fused logvar, eps, d(total)/dz   [B][Z]
+  long long s_ga, s_gb; int ld_g;        // gradient ping-pong buffers [B][ld_g]
+  long long scratch_floats;
+};
+
+// Device-side member record.
+struct MemberDev {
+  int arch_idx;
+  int n_rows, batch;
+  const float* xc[NMB_MAX_MOD];
+  float* params; float* adam_m; float* adam_v; float* grads;
+  const float* lr_steps;
+  unsigned long long seed;
+  float lr, beta1, beta2, adam_eps;
+  long long steps_done;     // mutable: minibatch steps taken so far
+  int last_rows;            // mutable: rows of the last executed minibatch
+  int last_slot;            // mutable: scratch slot that ran the last step
+};
+
+// ---- layout (host) -------------------------------------------------------------------
+inline int build_arch(const NmbArch& a, ArchDesc* d, const char** err) {
+  auto fail = [&](const char* m) { *err = m; return 1; };
+  if (a.n_mod < 1 || a.n_mod > NMB_MAX_MOD) return fail("n_mod out of range");
+  if (a.n_hidden < 1 || a.n_hidden > NMB_MAX_HIDDEN) return fail("n_hidden out of range (1..4)");
+  if (a.latent < 1 || a.c_dim < 0) return fail("bad latent / c_dim");
+  if (a.combine < 0 || a.combine > NMB_COMBINE_MOPOE) return fail("No such combination method");
+  if (a.loss_kind < 0 || a.loss_kind > NMB_LOSS_NEG_MSE) return fail("bad loss_kind");
+  *d = ArchDesc{};
+  d->M = a.n_mod; d->L = a.n_hidden; d->Z = a.latent; d->C = a.c_dim;
+  d->combine = a.combine; d->loss_kind = a.loss_kind; d->non_linear = a.non_linear;
+  for (int l = 0; l < a.n_hidden; ++l) {
+    if (a.hidden[l] < 1) return fail("bad hidden width");
+    d->hidden[l] = a.hidden[l];
+  }
+  long long off = 0, so = 0;
+  const int B = kMaxBatch, L = d->L, Z = d->Z, C = d->C;
+  auto lin = [&](int in, int out) {
+    LinDesc r; r.in = in; r.out = out; r.ld = round4(in + 1); r.off = off;
+    off += (long long)out * r.ld;
+    return r;
+  };
+  auto buf = [&](int ld) { long long r = so; so += (long long)B * ld; return r; };
+  int maxw = 2 * Z;
+  for (int m = 0; m < d->M; ++m) {
+    ModDesc& q = d->mod[m];
+    q.D = a.input_dims[m];
+    if (q.D < 1) return fail("bad input dim");
+    q.ldx = round4(q.D + C + 1);
+    for (int l = 0; l < L; ++l) q.enc[l] = lin(l == 0 ? q.D + C : d->hidden[l - 1], d->hidden[l]);
+    q.head = lin(d->hidden[L - 1], 2 * Z);
+    for (int l = 0; l < L; ++l) q.dec[l] = lin(l == 0 ? Z + C : d->hidden[L - l], d->hidden[L - 1 - l]);
+    q.outl = lin(d->hidden[0], q.D);
+    q.lam_off = off; off += round4(q.D);
+    for (int l = 0; l < L; ++l) {
+      q.ld_h[l] = round4(d->hidden[l] + 1);          q.s_h[l] = buf(q.ld_h[l]);
+      q.ld_k[l] = round4(d->hidden[L - 1 - l] + 1);  q.s_k[l] = buf(q.ld_k[l]);
+      if (d->hidden[l] > maxw) maxw = d->hidden[l];
+    }
+    q.ld_mulv = round4(2 * Z); q.s_mulv = buf(q.ld_mulv); q.s_dmulv = buf(q.ld_mulv);
+    q.ld_g0 = round4(Z + C + 1); q.s_g0 = buf(q.ld_g0);
+    q.ld_xh = round4(q.D); q.s_xh = buf(q.ld_xh); q.s_xr = buf(q.ld_xh);
+  }
+  d->alpha_off = off; off += round4(d->M);
+  d->n_params = off;
+  d->s_mub = buf(Z); d->s_lvb = buf(Z); d->s_eps = buf(Z); d->s_dz = buf(Z);
+  d->ld_g = round4(maxw);
+  d->s_ga = buf(d->ld_g); d->s_gb = buf(d->ld_g);
+  d->scratch_floats = (so + 3) & ~3LL;
+  return 0;
+}
+
+// ---- Philox4x32-10 + Box-Muller (stream definition: oracle/philox.py) --------------------
+__host__ __device__ inline void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1, uint32_t out[4]) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+    uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
+    k0 += W0; k1 += W1;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// eps values of elements 4*group .. 4*group+3 of minibatch `step`.
+__device__ inline void philox_normal4(unsigned long long seed, unsigned long long step,
+                                      uint32_t stream, uint32_t group, float n[4]) {
+  uint32_t w[4];
+  philox4x32_10(group, (uint32_t)step, (uint32_t)(step >> 32), stream, (uint32_t)seed,
+                (uint32_t)(seed >> 32), w);
+  float u[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) u[i] = ((float)(w[i] >> 9) + 0.5f) * 1.1920928955078125e-07f;  // 2^-23
+#pragma unroll
+  for (int i = 0; i < 4; i += 2) {
+    float r = sqrtf(-2.0f * logf(u[i]));
+    float s, c;
+    sincosf(6.283185307179586f * u[i + 1], &s, &c);
+    n[i] = r * c; n[i + 1] = r * s;
+  }
+}
+
+// ---- deterministic block reductions (fixed shuffle tree, fixed cross-warp order) -----------
+__device__ inline float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// red must hold >= kThreads/32 + 1 floats.  All threads of the CTA must call.
+__device__ inline float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[w] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < kThreads / 32; ++i) s += red[i];
+    red[kThreads / 32] = s;
+  }
+  __syncthreads();
+  return red[kThreads / 32];
+}
+
+}  // namespace nmb

@@ -1,0 +1,270 @@
+// Streaming (HBM-bound) kernels of the scoring half of the hot path: row packing,
+// per-ROI normative statistics, deviation / z-score tables, ROC-AUC by exact pair counting.
+//
+// Reference behaviour replaced:
+//   (x - xhat)^2 per ROI                 multimodal_kfold_test_cvae_supervised.py:141
+//   sum_d (x - xhat)^2 / D per subject   cVAE.py:1210-1211, utils_vae.py:147-148
+//   HC-referenced z-score                utils_vae.py:155-161 (latent space) -> ROI space,
+//                                        definition in oracle/deviation.py
+//   roc_curve + auc                      multimodal_kfold_cvae_group_analysis_1x1.py:123-124
+#include "nmb_internal.h"
+
+namespace nmb {
+
+// ---- pack rows: [x | c | 1 | 0] ------------------------------------------------------------
+__global__ void pack_rows_kernel(const float* __restrict__ x, const float* __restrict__ c, long long n_rows,
+                                 int d, int c_dim, int ldx, float* __restrict__ out) {
+  const long long total = n_rows * ldx;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / ldx;
+    const int j = (int)(i - r * ldx);
+    float v = 0.f;
+    if (j < d) v = x[r * d + j];
+    else if (j < d + c_dim) v = c[r * c_dim + (j - d)];
+    else if (j == d + c_dim) v = 1.f;
+    out[i] = v;
+  }
+}
+
+void launch_pack_rows(const float* x, const float* c, long long n_rows, int d, int c_dim, int ldx, float* out,
+                      cudaStream_t st) {
+  const long long total = n_rows * ldx;
+  if (total == 0) return;
+  const int blocks = (int)min((total + 255) / 256, (long long)148 * 16);
+  pack_rows_kernel<<<blocks, 256, 0, st>>>(x, c, n_rows, d, c_dim, ldx, out);
+}
+
+// ---- normative statistics -------------------------------------------------------------------
+// grid = (ceil(max_d/32), n_seg); block = 32 columns x 8 row groups.  Consecutive lanes read
+// consecutive ROIs (coalesced 128 B rows); sums are accumulated in fp64 and combined across the
+// 8 row groups in a fixed order, so the result does not depend on the launch geometry.
+__global__ void __launch_bounds__(256) stats_kernel(SegTable t) {
+  const int s = blockIdx.y;
+  const int d = t.d[s];
+  const int col = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int rg = threadIdx.x >> 5;
+  const float* x = t.x[s];
+  const float* xh = t.xhat[s];
+  const uint8_t* mask = t.mask ? t.mask[s] : nullptr;
+  const int n = t.n_rows[s], ldx = t.ldx[s];
+  double sum = 0.0, sq = 0.0;
+  int cnt = 0;
+  if (col < d) {
+    for (int i = rg; i < n; i += 8) {
+      if (mask && !mask[i]) continue;
+      const float r = x[(long long)i * ldx + col] - xh[(long long)i * d + col];
+      const double r2 = (double)(r * r);
+      sum += r2; sq += r2 * r2; ++cnt;
+    }
+  }
+  __shared__ double s_sum[8][32], s_sq[8][32];
+  __shared__ int s_cnt[8][32];
+  s_sum[rg][threadIdx.x & 31] = sum; s_sq[rg][threadIdx.x & 31] = sq; s_cnt[rg][threadIdx.x & 31] = cnt;
+  __syncthreads();
+  if (rg == 0 && col < d) {
+    double a = 0.0, b = 0.0; int c = 0;
+    for (int g = 0; g < 8; ++g) { a += s_sum[g][threadIdx.x]; b += s_sq[g][threadIdx.x]; c += s_cnt[g][threadIdx.x]; }
+    float* out = t.stats_out[s];
+    if (c > 0) {
+      const double mean = a / c;
+      double var = b / c - mean * mean;
+      if (var < 0.0) var = 0.0;
+      out[col] = (float)mean; out[d + col] = (float)sqrt(var);
+    } else {
+      out[col] = nanf(""); out[d + col] = nanf("");
+    }
+  }
+}
+
+void launch_stats(const SegTable& t, int n_seg, int max_d, cudaStream_t st) {
+  if (n_seg == 0 || max_d == 0) return;
+  dim3 grid((max_d + 31) / 32, n_seg);
+  stats_kernel<<<grid, 256, 0, st>>>(t);
+}
+
+// ---- deviation tables ------------------------------------------------------------------------
+// One warp per subject row; lanes stride over ROIs (float4 when the row is 16 B aligned),
+// warp-shuffle reduction for the per-subject mean.  grid = (row blocks, n_seg).
+__global__ void __launch_bounds__(256) deviation_kernel(SegTable t) {
+  const int s = blockIdx.y;
+  const int d = t.d[s], n = t.n_rows[s], ldx = t.ldx[s];
+  const float* x = t.x[s];
+  const float* xh = t.xhat[s];
+  const float* stats = t.stats ? t.stats[s] : nullptr;
+  float* roi = t.dev_roi ? t.dev_roi[s] : nullptr;
+  float* zs = (t.z && stats) ? t.z[s] : nullptr;
+  float* subj = t.dev_subj ? t.dev_subj[s] : nullptr;
+  const int lane = threadIdx.x & 31;
+  const int warps = (blockDim.x >> 5) * gridDim.x;
+  const bool vec = (d & 3) == 0;
+  for (int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += warps) {
+    const float* xr = x + (long long)i * ldx;
+    const float* hr = xh + (long long)i * d;
+    float acc = 0.f;
+    if (vec) {
+      for (int j = lane * 4; j < d; j += 128) {
+        const float4 a = *reinterpret_cast<const float4*>(xr + j);
+        const float4 b = *reinterpret_cast<const float4*>(hr + j);
+        float4 r = make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
+        r.x *= r.x; r.y *= r.y; r.z *= r.z; r.w *= r.w;
+        acc += (r.x + r.y) + (r.z + r.w);
+        if (roi) *reinterpret_cast<float4*>(roi + (long long)i * d + j) = r;
+        if (zs) {
+          const float4 mu = *reinterpret_cast<const float4*>(stats + j);
+          const float4 sd = *reinterpret_cast<const float4*>(stats + d + j);
+          *reinterpret_cast<float4*>(zs + (long long)i * d + j) =
+              make_float4((r.x - mu.x) / sd.x, (r.y - mu.y) / sd.y, (r.z - mu.z) / sd.z, (r.w - mu.w) / sd.w);
+        }
+      }
+    } else {
+      for (int j = lane; j < d; j += 32) {
+        float r = xr[j] - hr[j];
+        r *= r;
+        acc += r;
+        if (roi) roi[(long long)i * d + j] = r;
+        if (zs) zs[(long long)i * d + j] = (r - stats[j]) / stats[d + j];
+      }
+    }
+    acc = warp_sum(acc);
+    if (subj && lane == 0) subj[i] = acc / d;
+  }
+}
+
+void launch_deviation(const SegTable& t, int n_seg, int max_rows, cudaStream_t st) {
+  if (n_seg == 0 || max_rows == 0) return;
+  int bx = (max_rows + 7) / 8;
+  const int cap = max(1, (148 * 8) / n_seg);   // ~8 CTAs per SM over all segments
+  if (bx > cap) bx = cap;
+  dim3 grid(bx, n_seg);
+  deviation_kernel<<<grid, 256, 0, st>>>(t);
+}
+
+// ---- ROC-AUC by exact pair counting ------------------------------------------------------------
+// CTA = (column, segment).  Negatives are sorted in shared memory (bitonic, chunked when they do
+// not fit); every positive is binary-searched: U2 += 2*#(neg < s) + #(neg == s).  Integer
+// arithmetic -> bit-exact against oracle/deviation.py:auc_pairs.
+constexpr int kAucChunk = 8192;   // negatives per sorted chunk (32 KB)
+
+__device__ inline void bitonic_sort(float* v, int n_pow2) {
+  for (int k = 2; k <= n_pow2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
+        const int p = i ^ j;
+        if (p > i) {
+          const float a = v[i], b = v[p];
+          const bool up = (i & k) == 0;
+          if ((a > b) == up) { v[i] = b; v[p] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) auc_kernel(AucTable t) {
+  extern __shared__ float neg[];
+  __shared__ unsigned long long s_part[8];
+  __shared__ int s_cnt[8];
+  const int s = blockIdx.y;
+  const int n_cols = t.n_cols[s];
+  const int col = blockIdx.x;
+  if (col >= n_cols) return;
+  const float* sc = t.scores[s] + col;
+  const uint8_t* lab = t.labels[s];
+  const int n = t.n_rows[s];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  unsigned long long u2 = 0;
+  int n_neg_total = 0;
+  for (int r0 = 0; r0 < n; r0 += kAucChunk) {
+    const int m = min(kAucChunk, n - r0);
+    int p2 = 1;
+    while (p2 < m) p2 <<= 1;
+    // non-negatives and the pow2 tail become +inf sentinels that sort behind every real negative
+    int cnt = 0;
+    for (int i = threadIdx.x; i < p2; i += blockDim.x) {
+      const bool is_neg = i < m && lab[r0 + i] == 0;
+      neg[i] = is_neg ? sc[(long long)(r0 + i) * n_cols] : __int_as_float(0x7f800000);
+      cnt += is_neg;
+    }
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) s_cnt[w] = cnt;
+    __syncthreads();
+    int n_neg = 0;
+    for (int k = 0; k < nw; ++k) n_neg += s_cnt[k];
+    bitonic_sort(neg, p2);
+    if (n_neg > 0) {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        if (lab[i] == 0) continue;
+        const float v = sc[(long long)i * n_cols];
+        int lo = 0, hi = n_neg;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (neg[mid] < v) lo = mid + 1; else hi = mid; }
+        const int less = lo;
+        hi = n_neg;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (neg[mid] <= v) lo = mid + 1; else hi = mid; }
+        u2 += 2ull * less + (unsigned long long)(lo - less);
+      }
+    }
+    n_neg_total += n_neg;
+    __syncthreads();   // everyone is done with this chunk before it is overwritten
+  }
+  int n_pos = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) n_pos += lab[i] != 0;
+  for (int o = 16; o > 0; o >>= 1) {
+    u2 += __shfl_xor_sync(0xffffffffu, u2, o);
+    n_pos += __shfl_xor_sync(0xffffffffu, n_pos, o);
+  }
+  if (lane == 0) { s_part[w] = u2; s_cnt[w] = n_pos; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long tot = 0;
+    int npos = 0;
+    for (int k = 0; k < nw; ++k) { tot += s_part[k]; npos += s_cnt[k]; }
+    if (t.out_u2 && t.out_u2[s]) t.out_u2[s][col] = tot;
+    t.out_auc[s][col] = (npos > 0 && n_neg_total > 0)
+        ? (double)tot / (2.0 * (double)npos * (double)n_neg_total) : nan("");
+  }
+}
+
+void launch_auc(const AucTable& t, int n_seg, int max_cols, cudaStream_t st) {
+  if (n_seg == 0 || max_cols == 0) return;
+  dim3 grid(max_cols, n_seg);
+  auc_kernel<<<grid, 256, kAucChunk * sizeof(float), st>>>(t);
+}
+
+// ---- misc -----------------------------------------------------------------------------------
+__global__ void mean_rows_kernel(PtrTable16 src, int k, long long n, float* out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    float a = 0.f;
+    for (int j = 0; j < k; ++j) a += src.p[j][i];
+    out[i] = a / k;
+  }
+}
+
+void launch_mean_rows(const PtrTable16& src, int k, long long n, float* out, cudaStream_t st) {
+  if (n == 0) return;
+  const int blocks = (int)min((n + 255) / 256, (long long)148 * 8);
+  mean_rows_kernel<<<blocks, 256, 0, st>>>(src, k, n, out);
+}
+
+__global__ void philox_kernel(unsigned long long seed, unsigned long long step, uint32_t stream_id, long long n,
+                              float* out) {
+  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g * 4 < n;
+       g += (long long)gridDim.x * blockDim.x) {
+    float v[4];
+    philox_normal4(seed, step, stream_id, (uint32_t)g, v);
+    for (int j = 0; j < 4; ++j)
+      if (g * 4 + j < n) out[g * 4 + j] = v[j];
+  }
+}
+
+void launch_philox(unsigned long long seed, unsigned long long step, uint32_t stream_id, long long n, float* out,
+                   cudaStream_t st) {
+  if (n == 0) return;
+  const long long groups = (n + 3) / 4;
+  const int blocks = (int)min((groups + 255) / 256, (long long)148 * 8);
+  philox_kernel<<<blocks, 256, 0, st>>>(seed, step, stream_id, n, out);
+}
+
+}  // namespace nmb

@@ -1,0 +1,60 @@
+// Internal (non-ABI) declarations shared by the translation units of libnmb.
+#pragma once
+#include "nmb_common.cuh"
+
+namespace nmb {
+
+// Device-resident argument tables (arrays of per-segment pointers / sizes).
+struct SegTable {
+  const float* const* x;        // packed rows [n][ldx]
+  const int* ldx;
+  const float* const* xhat;     // [n][d]
+  const uint8_t* const* mask;   // optional table (entries may be NULL)
+  const int* n_rows;
+  const int* d;
+  float* const* stats_out;      // [2][d]
+  const float* const* stats;    // optional
+  float* const* dev_roi;        // optional
+  float* const* z;              // optional
+  float* const* dev_subj;       // optional
+};
+
+struct AucTable {
+  const float* const* scores;
+  const uint8_t* const* labels;
+  const int* n_rows;
+  const int* n_cols;
+  double* const* out_auc;
+  unsigned long long* const* out_u2;   // optional
+};
+
+struct PtrTable16 { const float* p[16]; };
+
+void launch_pack_rows(const float* x, const float* c, long long n_rows, int d, int c_dim, int ldx, float* out,
+                      cudaStream_t st);
+void launch_stats(const SegTable& t, int n_seg, int max_d, cudaStream_t st);
+void launch_deviation(const SegTable& t, int n_seg, int max_rows, cudaStream_t st);
+void launch_auc(const AucTable& t, int n_seg, int max_cols, cudaStream_t st);
+void launch_mean_rows(const PtrTable16& src, int k, long long n, float* out, cudaStream_t st);
+void launch_philox(unsigned long long seed, unsigned long long step, uint32_t stream_id, long long n, float* out,
+                   cudaStream_t st);
+
+// nmb_train.cu
+struct TrainLaunch {
+  MemberDev* members; const ArchDesc* archs; int n_members;
+  long long n_steps; const float* eps_override; float* loss_out; unsigned flags;
+  float* scratch; long long slot_floats; int n_slots; int* work_counter;
+};
+cudaError_t launch_train(const TrainLaunch& t, cudaStream_t st);
+
+struct ReconItem { int member; int row0; int rows; };
+struct ReconLaunch {
+  MemberDev* members; const ArchDesc* archs;
+  const ReconItem* items; int n_items;
+  const float* const* xc; const float* const* eps; float* const* xhat; float* const* mu; float* const* logvar;
+  int mode; float* scratch; long long slot_floats; int n_slots;
+};
+cudaError_t launch_recon(const ReconLaunch& t, cudaStream_t st);
+cudaError_t configure_kernels();
+
+}  // namespace nmb

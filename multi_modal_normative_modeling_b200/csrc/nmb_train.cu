@@ -1,0 +1,547 @@
+// Fused ensemble kernels: one CTA owns one ensemble member and runs, per minibatch step,
+//   encoders -> latent fusion -> Philox reparameterisation -> decoders -> Gaussian-LL/-MSE + KL
+//   -> backward -> Adam
+// entirely inside a single launch for the whole ensemble (no host round trips between steps).
+//
+// Reference behaviour replaced (file:line in soz223/multi_modal_normative_modeling):
+//   hot loop                     multimodal_kfold_train_cvae_supervised.py:177-199
+//   Encoder/Decoder.forward      cVAE.py:161-172, 197-206
+//   combine_latent + experts     cVAE.py:1144-1164, 986-1083
+//   reparameterise               cVAE.py:1130-1133
+//   calc_kl / compute_ll         cVAE.py:1138-1139, 14-15   (-MSE: ..._nmmlp.py:124-127)
+//   loss_function_multimodal     cVAE.py:1187-1196
+//   optimizer1 = Adam(enc+dec+alpha), torch defaults        cVAE.py:1111-1116
+//   pred_recon (mean / sampled)  cVAE.py:549-555, 1198-1208
+// The formulas are those of oracle/cvae_numpy.py.
+#include "nmb_gemm.cuh"
+#include "nmb_internal.h"
+
+namespace nmb {
+
+struct StepCtx {
+  const ArchDesc* a;
+  MemberDev* mb;
+  float* scratch;
+  float* smem;      // GEMM tiles
+  float* red;       // reduction scratch (>= 16 floats)
+  int rows, row0;
+  long long step;   // global 0-based step index of this member
+  unsigned flags;
+  // Adam scalars of this step
+  float step_size, bc2_sqrt, b1, b2, aeps;
+};
+
+// ---- epilogues ---------------------------------------------------------------------------
+struct EpiHidden {     // h = leaky_relu(a) (bias already inside a via the ones column)
+  float* dst; int ld; int nl;
+  __device__ __forceinline__ void operator()(int m, int n, float v) {
+    dst[(long long)m * ld + n] = (nl && v <= 0.f) ? kSlope * v : v;
+  }
+};
+
+struct EpiStore {
+  float* dst; int ld;
+  __device__ __forceinline__ void operator()(int m, int n, float v) { dst[(long long)m * ld + n] = v; }
+};
+
+// x_recon epilogue: loss terms + d(total)/d(x_recon) in one pass.
+struct EpiRecon {
+  const float* x; int ldx;        // targets: packed rows (first D columns)
+  const float* lam;               // logvar_out [D]
+  float* dxh; int ld;             // out: gradient (or x_recon itself when keep)
+  float* keep;                    // optional copy of x_recon (ld) for peek
+  float inv_rows, inv_rows_d;     // 1/B, 1/(B*D)
+  int gauss;
+  float ll_acc;                   // per-thread partial of sum over elements
+  __device__ __forceinline__ void operator()(int m, int n, float v) {
+    const float r = x[(long long)m * ldx + n] - v;
+    float g;
+    if (gauss) {
+      const float l = lam[n];
+      const float iv = __expf(-l);            // 1 / sigma^2
+      ll_acc += -0.5f * r * r * iv - 0.5f * l - 0.5f * kLog2Pi;
+      g = -r * iv * inv_rows;
+    } else {
+      ll_acc += -r * r;
+      g = -2.f * r * inv_rows_d;
+    }
+    if (keep) keep[(long long)m * ld + n] = v;
+    dxh[(long long)m * ld + n] = g;
+  }
+};
+
+struct EpiDgrad {      // d_pre = d_act * leaky_relu'(pre), sign recovered from the stored activation
+  float* dst; int ld;
+  const float* act; int ld_act; int nl;
+  __device__ __forceinline__ void operator()(int m, int n, float v) {
+    const float h = act[(long long)m * ld_act + n];
+    dst[(long long)m * ld + n] = (nl && h <= 0.f) ? kSlope * v : v;
+  }
+};
+
+struct EpiDz {
+  float* dz; int Z; int accumulate;
+  __device__ __forceinline__ void operator()(int m, int n, float v) {
+    float* p = dz + m * Z + n;
+    *p = accumulate ? *p + v : v;
+  }
+};
+
+struct AdamCfg {
+  float* p; float* m; float* v; float* g;
+  float step_size, bc2_sqrt, b1, b2, eps;
+  unsigned flags;
+  __device__ __forceinline__ void apply(long long idx, float grad) const {
+    if (flags & NMB_TRAIN_WRITE_GRADS) g[idx] = grad;
+    if (!(flags & NMB_TRAIN_NO_ADAM)) {
+      const float m1 = b1 * m[idx] + (1.f - b1) * grad;
+      const float v1 = b2 * v[idx] + (1.f - b2) * grad * grad;
+      m[idx] = m1; v[idx] = v1;
+      p[idx] -= step_size * (m1 / (sqrtf(v1) / bc2_sqrt + eps));
+    }
+  }
+};
+
+struct EpiWgradAdam {  // weight (+bias column) gradient fused with the optimiser update
+  AdamCfg ad; long long off; int ld;
+  __device__ __forceinline__ void operator()(int m, int n, float v) { ad.apply(off + (long long)m * ld + n, v); }
+};
+
+__device__ __forceinline__ AdamCfg make_adam(const StepCtx& c) {
+  AdamCfg ad;
+  ad.p = c.mb->params; ad.m = c.mb->adam_m; ad.v = c.mb->adam_v; ad.g = c.mb->grads;
+  ad.step_size = c.step_size; ad.bc2_sqrt = c.bc2_sqrt; ad.b1 = c.b1; ad.b2 = c.b2; ad.eps = c.aeps;
+  ad.flags = c.flags;
+  return ad;
+}
+
+// ---- latent fusion (cVAE.py:1144-1164) -----------------------------------------------------
+// Forward for one (row, z) element.  mu[m], lv[m] are the per-modality heads.
+struct Fused { float mu, lv; };
+
+__device__ inline void softmax_alpha(const float* alpha, int M, float* out) {
+  float mx = alpha[0];
+  for (int m = 1; m < M; ++m) mx = fmaxf(mx, alpha[m]);
+  float s = 0.f;
+  for (int m = 0; m < M; ++m) { out[m] = expf(alpha[m] - mx); s += out[m]; }
+  for (int m = 0; m < M; ++m) out[m] /= s;
+}
+
+__device__ inline Fused fuse_forward(const float* mu, const float* lv, int M, int combine, const float* w) {
+  Fused f;
+  if (M == 1) { f.mu = mu[0]; f.lv = lv[0]; return f; }
+  if (combine == NMB_COMBINE_MOE) {
+    float sm = 0.f, sv = 0.f;
+    for (int m = 0; m < M; ++m) { sm += mu[m]; sv += expf(lv[m]); }
+    f.mu = sm / M; f.lv = logf(sv / M);
+    return f;
+  }
+  float s = 0.f, num = 0.f, sm = 0.f, sv = 0.f;
+  for (int m = 0; m < M; ++m) {
+    const float v = expf(lv[m]);
+    const float t = (combine == NMB_COMBINE_GPOE ? w[m] : 1.f) / v;
+    s += t; num += mu[m] * t; sm += mu[m]; sv += v;
+  }
+  const float pmu = num / s, pvar = 1.f / s;
+  if (combine == NMB_COMBINE_MOPOE) { f.mu = (sm + pmu) / (M + 1); f.lv = logf((sv + pvar) / (M + 1)); }
+  else { f.mu = pmu; f.lv = logf(pvar); }
+  return f;
+}
+
+// Backward for one element: given d_mu_bar, d_lv_bar produce d_mu[m], d_lv[m] and the per-element
+// contribution to d(alpha_softmax_weight)[m] (gPoE).  See oracle/cvae_numpy.py:fuse_backward.
+__device__ inline void fuse_backward(const float* mu, const float* lv, int M, int combine, const float* w,
+                                     float dmu_bar, float dlv_bar, float* dmu, float* dlv, float* dw) {
+  if (M == 1) { dmu[0] = dmu_bar; dlv[0] = dlv_bar; return; }
+  float v[NMB_MAX_MOD];
+  float sv = 0.f, sm = 0.f;
+  for (int m = 0; m < M; ++m) { v[m] = expf(lv[m]); sv += v[m]; sm += mu[m]; }
+  if (combine == NMB_COMBINE_MOE) {
+    const float var_bar = sv / M;
+    const float dvar = dlv_bar / var_bar;
+    for (int m = 0; m < M; ++m) { dmu[m] = dmu_bar / M; dlv[m] = dvar / M * v[m]; }
+    return;
+  }
+  float s = 0.f, num = 0.f;
+  for (int m = 0; m < M; ++m) {
+    const float t = (combine == NMB_COMBINE_GPOE ? w[m] : 1.f) / v[m];
+    s += t; num += mu[m] * t;
+  }
+  const float pmu = num / s, pvar = 1.f / s;
+  float dpm, dpv, base_mu = 0.f, base_v = 0.f;
+  if (combine == NMB_COMBINE_MOPOE) {
+    const float var_bar = (sv + pvar) / (M + 1);
+    const float dvar = dlv_bar / var_bar;
+    base_mu = dmu_bar / (M + 1); base_v = dvar / (M + 1);
+    dpm = base_mu; dpv = base_v;
+  } else {
+    dpm = dmu_bar; dpv = dlv_bar / pvar;
+  }
+  for (int m = 0; m < M; ++m) {
+    const float a = (combine == NMB_COMBINE_GPOE ? w[m] : 1.f);
+    const float t = a / v[m];
+    const float dt = dpm * (mu[m] - pmu) / s - dpv * pvar * pvar;
+    dmu[m] = base_mu + dpm * t / s;
+    const float dv = base_v - dt * a / (v[m] * v[m]);
+    dlv[m] = dv * v[m];
+    if (dw) dw[m] = dt / v[m];
+  }
+}
+
+// Constant-1 columns of the augmented activation buffers of this CTA's scratch slot.  Pad
+// columns and stale rows are never read (every GEMM operand load is bounds-guarded).
+__device__ void prepare_slot(const StepCtx& c) {
+  const ArchDesc& a = *c.a;
+  for (int m = 0; m < a.M; ++m) {
+    const ModDesc& q = a.mod[m];
+    for (int b = threadIdx.x; b < kMaxBatch; b += kThreads) {
+      for (int l = 0; l < a.L; ++l) {
+        c.scratch[q.s_h[l] + (long long)b * q.ld_h[l] + a.hidden[l]] = 1.f;
+        c.scratch[q.s_k[l] + (long long)b * q.ld_k[l] + a.hidden[a.L - 1 - l]] = 1.f;
+      }
+      c.scratch[q.s_g0 + (long long)b * q.ld_g0 + a.Z + a.C] = 1.f;
+    }
+  }
+  __syncthreads();
+}
+
+// ---- forward ---------------------------------------------------------------------------------
+// Encoders of all modalities on rows [row0, row0+rows) of xc -> heads in scratch (s_mulv).
+__device__ void encoders_forward(const StepCtx& c, const float* const* xc) {
+  const ArchDesc& a = *c.a;
+  const float* P = c.mb->params;
+  for (int m = 0; m < a.M; ++m) {
+    const ModDesc& q = a.mod[m];
+    Opnd A{xc[m] + (long long)c.row0 * q.ldx, q.ldx, 1};
+    for (int l = 0; l < a.L; ++l) {
+      const LinDesc& w = q.enc[l];
+      EpiHidden e{c.scratch + q.s_h[l], q.ld_h[l], a.non_linear};
+      gemm_auto(c.rows, w.out, w.in + 1, A, Opnd{P + w.off, w.ld, 1}, e, c.smem);
+      A = Opnd{c.scratch + q.s_h[l], q.ld_h[l], 1};
+    }
+    EpiStore e{c.scratch + q.s_mulv, q.ld_mulv};
+    gemm_auto(c.rows, q.head.out, q.head.in + 1, A, Opnd{P + q.head.off, q.head.ld, 1}, e, c.smem);
+  }
+}
+
+// Fusion + reparameterisation + KL.  Writes fused mu/logvar, eps, and the decoder inputs
+// [z | c | 1] of every modality.  Returns sum over elements of the KL integrand (all threads).
+//   eps_mode: 0 = Philox(stream_id), 1 = injected (eps_src [rows][Z]), 2 = zero (decode the mean)
+__device__ float latent_forward(const StepCtx& c, const float* const* xc, int eps_mode,
+                                const float* eps_src, uint32_t stream_id, unsigned long long eps_step) {
+  const ArchDesc& a = *c.a;
+  const int Z = a.Z, M = a.M, n = c.rows * Z;
+  float* S = c.scratch;
+  float w[NMB_MAX_MOD];
+  if (M > 1 && a.combine == NMB_COMBINE_GPOE) softmax_alpha(c.mb->params + a.alpha_off, M, w);
+  float kl = 0.f;
+  for (int g = threadIdx.x; g * 4 < n; g += kThreads) {
+    float nrm[4] = {0.f, 0.f, 0.f, 0.f};
+    if (eps_mode == 0) philox_normal4(c.mb->seed, eps_step, stream_id, (uint32_t)g, nrm);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int e = g * 4 + j;
+      if (e >= n) break;
+      const int b = e / Z, z = e - b * Z;
+      float mu[NMB_MAX_MOD], lv[NMB_MAX_MOD];
+      for (int m = 0; m < M; ++m) {
+        const float* h = S + a.mod[m].s_mulv + (long long)b * a.mod[m].ld_mulv;
+        mu[m] = h[z]; lv[m] = h[Z + z];
+      }
+      const Fused f = fuse_forward(mu, lv, M, a.combine, w);
+      const float eps = eps_mode == 1 ? eps_src[e] : nrm[j];
+      S[a.s_mub + e] = f.mu; S[a.s_lvb + e] = f.lv; S[a.s_eps + e] = eps;
+      const float zz = f.mu + eps * expf(0.5f * f.lv);
+      for (int m = 0; m < M; ++m) S[a.mod[m].s_g0 + (long long)b * a.mod[m].ld_g0 + z] = zz;
+      kl += -0.5f * (1.f + f.lv - f.mu * f.mu - expf(f.lv));
+    }
+  }
+  // covariates into the decoder inputs (Decoder.forward: cat((z, c)), cVAE.py:199)
+  for (int m = 0; m < M; ++m) {
+    const ModDesc& q = a.mod[m];
+    const float* src = xc[m] + (long long)c.row0 * q.ldx + q.D;
+    float* dst = S + q.s_g0 + Z;
+    for (int e = threadIdx.x; e < c.rows * a.C; e += kThreads) {
+      const int b = e / a.C, j = e - b * a.C;
+      dst[(long long)b * q.ld_g0 + j] = src[(long long)b * q.ldx + j];
+    }
+  }
+  __syncthreads();
+  return kl;
+}
+
+// Decoder hidden layers of modality m; returns the operand feeding decoder_mean_layer.
+__device__ Opnd decoder_hidden(const StepCtx& c, int m) {
+  const ArchDesc& a = *c.a;
+  const ModDesc& q = a.mod[m];
+  const float* P = c.mb->params;
+  Opnd A{c.scratch + q.s_g0, q.ld_g0, 1};
+  for (int l = 0; l < a.L; ++l) {
+    const LinDesc& w = q.dec[l];
+    EpiHidden e{c.scratch + q.s_k[l], q.ld_k[l], a.non_linear};
+    gemm_auto(c.rows, w.out, w.in + 1, A, Opnd{P + w.off, w.ld, 1}, e, c.smem);
+    A = Opnd{c.scratch + q.s_k[l], q.ld_k[l], 1};
+  }
+  return A;
+}
+
+// ---- one training step ---------------------------------------------------------------------
+__device__ void train_step(StepCtx& c, const float* eps_src, float* loss_out) {
+  const ArchDesc& a = *c.a;
+  MemberDev& mb = *c.mb;
+  float* S = c.scratch;
+  float* P = mb.params;
+  const int M = a.M, L = a.L, Z = a.Z, rows = c.rows;
+  const float inv_rows = 1.f / rows;
+  const int gauss = a.loss_kind == NMB_LOSS_GAUSS_LL;
+
+  // ---------------- forward ----------------
+  encoders_forward(c, mb.xc);
+  float kl = latent_forward(c, mb.xc, eps_src ? 1 : 0, eps_src, 0u, (unsigned long long)c.step);
+  kl = block_sum(kl, c.red) * inv_rows;
+  float ll_sum = 0.f;
+  for (int m = 0; m < M; ++m) {
+    const ModDesc& q = a.mod[m];
+    Opnd A = decoder_hidden(c, m);
+    EpiRecon e;
+    e.x = mb.xc[m] + (long long)c.row0 * q.ldx; e.ldx = q.ldx;
+    e.lam = P + q.lam_off;
+    e.dxh = S + q.s_xh; e.ld = q.ld_xh;
+    e.keep = (c.flags & NMB_TRAIN_KEEP_ACTS) ? S + q.s_xr : nullptr;
+    e.inv_rows = inv_rows; e.inv_rows_d = inv_rows / q.D; e.gauss = gauss; e.ll_acc = 0.f;
+    gemm_auto(rows, q.D, q.outl.in + 1, A, Opnd{P + q.outl.off, q.outl.ld, 1}, e, c.smem);
+    const float s = block_sum(e.ll_acc, c.red);
+    ll_sum += gauss ? s * inv_rows : s * inv_rows / q.D;
+  }
+  if (loss_out && threadIdx.x == 0) {
+    loss_out[0] = M * kl - ll_sum; loss_out[1] = M * kl; loss_out[2] = ll_sum;   // cVAE.py:1187-1196
+  }
+
+  // ---------------- backward + Adam ----------------
+  const AdamCfg ad = make_adam(c);
+  float* gbuf[2] = {S + a.s_ga, S + a.s_gb};
+  for (int m = 0; m < M; ++m) {
+    const ModDesc& q = a.mod[m];
+    float* dxh = S + q.s_xh;
+    // logvar_out: d/d lam_n = sum_b 0.5 (1 - r^2/sigma^2) / B, with r/sigma^2 = -B * dxh
+    if (gauss) {
+      for (int n = threadIdx.x; n < q.D; n += kThreads) {
+        const float var = __expf(P[q.lam_off + n]);
+        float acc = 0.f;
+        for (int b = 0; b < rows; ++b) {
+          const float t = dxh[(long long)b * q.ld_xh + n] * rows;
+          acc += 0.5f * (1.f - t * t * var);
+        }
+        ad.apply(q.lam_off + n, acc * inv_rows);
+      }
+    }
+    int cur = 0;
+    // decoder_mean_layer
+    {
+      const LinDesc& w = q.outl;
+      const float* act = S + q.s_k[L - 1]; const int ld_act = q.ld_k[L - 1];
+      EpiDgrad eg{gbuf[cur], a.ld_g, act, ld_act, a.non_linear};
+      gemm_auto(rows, w.in, w.out, Opnd{dxh, q.ld_xh, 1}, Opnd{P + w.off, w.ld, 0}, eg, c.smem);
+      EpiWgradAdam ew{ad, w.off, w.ld};
+      gemm_auto(w.out, w.in + 1, rows, Opnd{dxh, q.ld_xh, 0}, Opnd{act, ld_act, 0}, ew, c.smem);
+    }
+    for (int l = L - 1; l >= 0; --l) {
+      const LinDesc& w = q.dec[l];
+      const float* dy = gbuf[cur];
+      const float* in_act = l == 0 ? S + q.s_g0 : S + q.s_k[l - 1];
+      const int ld_in = l == 0 ? q.ld_g0 : q.ld_k[l - 1];
+      if (l > 0) {
+        EpiDgrad eg{gbuf[cur ^ 1], a.ld_g, in_act, ld_in, a.non_linear};
+        gemm_auto(rows, w.in, w.out, Opnd{dy, a.ld_g, 1}, Opnd{P + w.off, w.ld, 0}, eg, c.smem);
+      } else {
+        EpiDz ez{S + a.s_dz, Z, m > 0};
+        gemm_auto(rows, Z, w.out, Opnd{dy, a.ld_g, 1}, Opnd{P + w.off, w.ld, 0}, ez, c.smem);
+      }
+      EpiWgradAdam ew{ad, w.off, w.ld};
+      gemm_auto(w.out, w.in + 1, rows, Opnd{dy, a.ld_g, 0}, Opnd{in_act, ld_in, 0}, ew, c.smem);
+      cur ^= 1;
+    }
+  }
+
+  // latent backward: d mu_bar = dz + M mu/B ; d lv_bar = dz eps s/2 + M (e^lv - 1)/(2B)
+  {
+    float w[NMB_MAX_MOD], dw_acc[NMB_MAX_MOD];
+    const bool gpoe = M > 1 && a.combine == NMB_COMBINE_GPOE;
+    if (gpoe) softmax_alpha(P + a.alpha_off, M, w);
+    for (int m = 0; m < M; ++m) dw_acc[m] = 0.f;
+    for (int e = threadIdx.x; e < rows * Z; e += kThreads) {
+      const int b = e / Z, z = e - b * Z;
+      const float mub = S[a.s_mub + e], lvb = S[a.s_lvb + e], eps = S[a.s_eps + e], dz = S[a.s_dz + e];
+      const float sd = expf(0.5f * lvb);
+      const float dmu_bar = dz + M * mub * inv_rows;
+      const float dlv_bar = dz * eps * sd * 0.5f + M * (expf(lvb) - 1.f) * 0.5f * inv_rows;
+      float mu[NMB_MAX_MOD], lv[NMB_MAX_MOD], dmu[NMB_MAX_MOD], dlv[NMB_MAX_MOD], dw[NMB_MAX_MOD];
+      for (int m = 0; m < M; ++m) {
+        const float* h = S + a.mod[m].s_mulv + (long long)b * a.mod[m].ld_mulv;
+        mu[m] = h[z]; lv[m] = h[Z + z];
+      }
+      fuse_backward(mu, lv, M, a.combine, w, dmu_bar, dlv_bar, dmu, dlv, gpoe ? dw : nullptr);
+      for (int m = 0; m < M; ++m) {
+        float* d = S + a.mod[m].s_dmulv + (long long)b * a.mod[m].ld_mulv;
+        d[z] = dmu[m]; d[Z + z] = dlv[m];
+        if (gpoe) dw_acc[m] += dw[m];
+      }
+    }
+    if (gpoe) {   // softmax backward + Adam on alpha_m (cVAE.py:1154)
+      float dw_tot[NMB_MAX_MOD];
+      for (int m = 0; m < M; ++m) dw_tot[m] = block_sum(dw_acc[m], c.red);
+      if (threadIdx.x == 0) {
+        float dot = 0.f;
+        for (int m = 0; m < M; ++m) dot += w[m] * dw_tot[m];
+        for (int m = 0; m < M; ++m) ad.apply(a.alpha_off + m, w[m] * (dw_tot[m] - dot));
+      }
+    }
+    __syncthreads();
+  }
+
+  for (int m = 0; m < M; ++m) {
+    const ModDesc& q = a.mod[m];
+    const float* dmulv = S + q.s_dmulv;
+    int cur = 0;
+    {
+      const LinDesc& w = q.head;
+      const float* act = S + q.s_h[L - 1]; const int ld_act = q.ld_h[L - 1];
+      EpiDgrad eg{gbuf[cur], a.ld_g, act, ld_act, a.non_linear};
+      gemm_auto(rows, w.in, w.out, Opnd{dmulv, q.ld_mulv, 1}, Opnd{P + w.off, w.ld, 0}, eg, c.smem);
+      EpiWgradAdam ew{ad, w.off, w.ld};
+      gemm_auto(w.out, w.in + 1, rows, Opnd{dmulv, q.ld_mulv, 0}, Opnd{act, ld_act, 0}, ew, c.smem);
+    }
+    for (int l = L - 1; l >= 0; --l) {
+      const LinDesc& w = q.enc[l];
+      const float* dy = gbuf[cur];
+      const float* in_act = l == 0 ? mb.xc[m] + (long long)c.row0 * q.ldx : S + q.s_h[l - 1];
+      const int ld_in = l == 0 ? q.ldx : q.ld_h[l - 1];
+      if (l > 0) {
+        EpiDgrad eg{gbuf[cur ^ 1], a.ld_g, in_act, ld_in, a.non_linear};
+        gemm_auto(rows, w.in, w.out, Opnd{dy, a.ld_g, 1}, Opnd{P + w.off, w.ld, 0}, eg, c.smem);
+      }
+      EpiWgradAdam ew{ad, w.off, w.ld};
+      gemm_auto(w.out, w.in + 1, rows, Opnd{dy, a.ld_g, 0}, Opnd{in_act, ld_in, 0}, ew, c.smem);
+      cur ^= 1;
+    }
+  }
+}
+
+// ---- kernels -------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 2) train_kernel(TrainLaunch t) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ float red[16];
+  __shared__ int s_member;
+  for (;;) {
+    int mi;
+    if ((int)gridDim.x >= t.n_members) {
+      mi = blockIdx.x;
+    } else {
+      if (threadIdx.x == 0) s_member = atomicAdd(t.work_counter, 1);
+      __syncthreads();
+      mi = s_member;
+      __syncthreads();
+    }
+    if (mi >= t.n_members) return;
+    MemberDev& mb = t.members[mi];
+    const ArchDesc& a = t.archs[mb.arch_idx];
+    StepCtx c;
+    c.a = &a; c.mb = &mb; c.smem = smem; c.red = red; c.flags = t.flags;
+    c.scratch = t.scratch + (long long)blockIdx.x * t.slot_floats;
+    c.b1 = mb.beta1; c.b2 = mb.beta2; c.aeps = mb.adam_eps;
+    prepare_slot(c);
+    const int spe = (mb.n_rows + mb.batch - 1) / mb.batch;   // steps per epoch
+    const long long s0 = mb.steps_done;
+    int rows = 0;
+    for (long long i = 0; i < t.n_steps; ++i) {
+      const long long s = s0 + i;
+      const int pos = (int)(s % spe);
+      c.step = s;
+      c.row0 = pos * mb.batch;
+      c.rows = rows = min(mb.batch, mb.n_rows - c.row0);
+      const double tt = (double)(s + 1);
+      const float lr = mb.lr_steps ? mb.lr_steps[s] : mb.lr;
+      c.step_size = (float)((double)lr / (1.0 - pow((double)mb.beta1, tt)));
+      c.bc2_sqrt = (float)sqrt(1.0 - pow((double)mb.beta2, tt));
+      const float* eps = t.eps_override
+          ? t.eps_override + ((long long)mi * t.n_steps + i) * mb.batch * a.Z : nullptr;
+      float* lo = t.loss_out ? t.loss_out + ((long long)mi * t.n_steps + i) * 3 : nullptr;
+      train_step(c, eps, lo);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      mb.steps_done = s0 + t.n_steps;
+      mb.last_rows = rows;
+      mb.last_slot = blockIdx.x;
+    }
+    if ((int)gridDim.x >= t.n_members) return;
+  }
+}
+
+// Test-time reconstruction.  Work item = (member, tile of up to 256 rows).
+__global__ void __launch_bounds__(kThreads, 2) recon_kernel(ReconLaunch t) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ float red[16];
+  for (int it = blockIdx.x; it < t.n_items; it += gridDim.x) {
+    const ReconItem item = t.items[it];
+    MemberDev& mb = t.members[item.member];
+    const ArchDesc& a = t.archs[mb.arch_idx];
+    StepCtx c;
+    c.a = &a; c.mb = &mb; c.smem = smem; c.red = red; c.flags = 0;
+    c.scratch = t.scratch + (long long)blockIdx.x * t.slot_floats;
+    c.rows = item.rows; c.row0 = item.row0; c.step = 0;
+    const float* const* xc = t.xc + (long long)item.member * NMB_MAX_MOD;
+    prepare_slot(c);
+    encoders_forward(c, xc);
+    const float* eps = (t.mode == NMB_RECON_SAMPLE && t.eps && t.eps[item.member])
+        ? t.eps[item.member] + (long long)item.row0 * a.Z : nullptr;
+    const int eps_mode = t.mode == NMB_RECON_MEAN ? 2 : (eps ? 1 : 0);
+    // Philox test stream: counter "step" = row tile index so that tiles draw disjoint numbers
+    latent_forward(c, xc, eps_mode, eps, 1u, (unsigned long long)(item.row0 / kMaxBatch));
+    if (t.mu && t.mu[item.member]) {
+      float* mu = t.mu[item.member] + (long long)item.row0 * a.Z;
+      for (int e = threadIdx.x; e < item.rows * a.Z; e += kThreads) mu[e] = c.scratch[a.s_mub + e];
+    }
+    if (t.logvar && t.logvar[item.member]) {
+      float* lv = t.logvar[item.member] + (long long)item.row0 * a.Z;
+      for (int e = threadIdx.x; e < item.rows * a.Z; e += kThreads) lv[e] = c.scratch[a.s_lvb + e];
+    }
+    for (int m = 0; m < a.M; ++m) {
+      const ModDesc& q = a.mod[m];
+      Opnd A = decoder_hidden(c, m);
+      float* out = t.xhat[(long long)item.member * NMB_MAX_MOD + m];
+      if (!out) continue;
+      EpiStore e{out + (long long)item.row0 * q.D, q.D};
+      gemm_auto(item.rows, q.D, q.outl.in + 1, A, Opnd{mb.params + q.outl.off, q.outl.ld, 1}, e, c.smem);
+    }
+    __syncthreads();
+  }
+}
+
+constexpr size_t kGemmSmemBytes = kGemmSmemFloats * sizeof(float);
+
+cudaError_t configure_kernels() {
+  cudaError_t e = cudaFuncSetAttribute(train_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(recon_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes);
+}
+
+cudaError_t launch_train(const TrainLaunch& t, cudaStream_t st) {
+  const int grid = t.n_members < t.n_slots ? t.n_members : t.n_slots;
+  if (grid <= 0 || t.n_steps <= 0) return cudaSuccess;
+  if (grid < t.n_members) {
+    cudaError_t e = cudaMemsetAsync(t.work_counter, 0, sizeof(int), st);
+    if (e != cudaSuccess) return e;
+  }
+  train_kernel<<<grid, kThreads, kGemmSmemBytes, st>>>(t);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_recon(const ReconLaunch& t, cudaStream_t st) {
+  const int grid = t.n_items < t.n_slots ? t.n_items : t.n_slots;
+  if (grid <= 0) return cudaSuccess;
+  recon_kernel<<<grid, kThreads, kGemmSmemBytes, st>>>(t);
+  return cudaGetLastError();
+}
+
+}  // namespace nmb

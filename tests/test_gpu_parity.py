@@ -1,0 +1,303 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes -> libnmb.so), against
+(a) vectors recorded from the UNMODIFIED reference (tests/golden) and (b) the CPU oracle on the
+same seeded inputs.
+
+Tolerances (BASELINE.json north_star): per-step forward/backward outputs within 1e-4 relative
+error of the reference's PyTorch path on identical weights and eps draws; integer / index work
+(AUC pair counts) bit-exact; deviations 1e-5 relative (fp32 vs the reference's fp64 host math).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-4
+MM_CASES = ["mm_M1_small", "mm_M3_poe", "mm_M3_gpoe", "mm_M2_moe", "mm_M4_mopoe", "mm_M1_D116_full"]
+
+
+def load(golden_dir, name):
+    return dict(np.load(os.path.join(golden_dir, name + ".npz"), allow_pickle=False))
+
+
+def sub(g, prefix):
+    return {k[len(prefix):]: v for k, v in g.items() if k.startswith(prefix)}
+
+
+def relerr(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
+
+
+def make_trainer(g, sd_prefix="init/", keep_grads=True, batch=None, loss_kind="gauss_ll", n_copies=1):
+    from multi_modal_normative_modeling_b200 import EnsembleTrainer, MemberSpec, pack_rows
+    dims = [int(d) for d in g["dims"]]
+    c = torch.from_numpy(g["c"]).cuda()
+    xc = [pack_rows(torch.from_numpy(g[f"x{i}"]).cuda(), c) for i in range(len(dims))]
+    sd = {k: torch.from_numpy(v) for k, v in sub(g, sd_prefix).items()}
+    specs = [MemberSpec(input_dims=dims, hidden=[int(h) for h in g["hidden"]], latent=int(g["z"]),
+                        c_dim=int(g["c_dim"]), xc=xc, combine=str(g["combine"]), loss_kind=loss_kind,
+                        batch=batch or g["c"].shape[0], seed=7 + k, state_dict=sd) for k in range(n_copies)]
+    return EnsembleTrainer(specs, keep_grads=keep_grads), xc
+
+
+@pytest.mark.parametrize("name", MM_CASES)
+def test_step_forward_backward_vs_reference(golden_dir, name):
+    from multi_modal_normative_modeling_b200 import _lib
+    g = load(golden_dir, name)
+    tr, _ = make_trainer(g)
+    eps = torch.from_numpy(g["eps"][:1]).cuda()[None]          # [1 member, 1 step, B, Z]
+    losses = tr.train_steps(1, eps=eps, record_losses=True,
+                            flags=_lib.TRAIN_NO_ADAM | _lib.TRAIN_WRITE_GRADS | _lib.TRAIN_KEEP_ACTS)
+    torch.cuda.synchronize()
+    got = losses[0, 0].cpu().numpy()
+    assert np.allclose(got, g["losses"][0], rtol=REL), (got, g["losses"][0])
+    mu, lv, xr = tr.peek(0)
+    assert relerr(mu.cpu().numpy(), g["mu"]) < REL
+    assert relerr(lv.cpu().numpy(), g["logvar"]) < REL
+    for i in range(len(xr)):
+        assert relerr(xr[i].cpu().numpy(), g[f"xrecon{i}"]) < REL
+    grads = tr.state_dict(0, "grads")
+    ref = sub(g, "grad/")
+    for k, v in ref.items():
+        assert relerr(grads[k].cpu().numpy(), v) < REL, k
+    for k in grads:       # parameters without a reference gradient stay untouched (Adam skips them)
+        if k not in ref:
+            assert float(grads[k].abs().max()) == 0.0, k
+    # NO_ADAM must leave the parameters bit-identical
+    for k, v in sub(g, "init/").items():
+        assert np.array_equal(tr.state_dict(0)[k].cpu().numpy().reshape(v.shape), v), k
+    tr.close()
+
+
+@pytest.mark.parametrize("name", MM_CASES)
+def test_adam_trajectory_vs_reference(golden_dir, name):
+    g = load(golden_dir, name)
+    tr, _ = make_trainer(g, keep_grads=False)
+    steps = g["eps"].shape[0]
+    eps = torch.from_numpy(g["eps"]).cuda()[None]
+    losses = tr.train_steps(steps, eps=eps, record_losses=True)
+    torch.cuda.synchronize()
+    assert np.allclose(losses[0].cpu().numpy(), g["losses"], rtol=REL)
+    assert int(tr.steps_done()[0]) == steps
+    sd = tr.state_dict(0)
+    init = sub(g, "init/")
+    for k, v in sub(g, "final/").items():
+        got = sd[k].cpu().numpy().reshape(v.shape)
+        # compare the UPDATE (final - init): Adam moves every weight by ~lr per step, so the
+        # parameter itself would pass trivially
+        d_ref, d_got = v - init[k], got - init[k]
+        if np.abs(d_ref).max() == 0:
+            assert np.abs(d_got).max() == 0, k
+        else:
+            assert np.abs(d_got - d_ref).max() / np.abs(d_ref).max() < 2e-3, k
+        assert relerr(got, v) < 1e-5, k
+    tr.close()
+
+
+def test_split_calls_equal_one_call(golden_dir):
+    """steps_done / Adam step count persist across launches: 1+2 steps == 3 steps, bit for bit."""
+    g = load(golden_dir, "mm_M3_gpoe")
+    eps = torch.from_numpy(g["eps"]).cuda()[None]
+    tr1, _ = make_trainer(g, keep_grads=False)
+    tr1.train_steps(3, eps=eps)
+    tr2, _ = make_trainer(g, keep_grads=False)
+    tr2.train_steps(1, eps=eps[:, :1].contiguous())
+    tr2.train_steps(2, eps=eps[:, 1:].contiguous())
+    torch.cuda.synchronize()
+    assert torch.equal(tr1.params, tr2.params)
+    tr1.close(); tr2.close()
+
+
+@pytest.mark.parametrize("name", MM_CASES)
+def test_reconstruct_and_deviation_vs_reference(golden_dir, name):
+    from multi_modal_normative_modeling_b200 import scoring
+    g = load(golden_dir, name)
+    tr, xc = make_trainer(g, sd_prefix="final/", keep_grads=False)
+    xhat, mu, lv = tr.reconstruct([xc], mode="sample", eps=[torch.from_numpy(g["eps_test"]).cuda()],
+                                  want_latent=True)
+    torch.cuda.synchronize()
+    for i in range(len(xc)):
+        assert relerr(xhat[0][i].cpu().numpy(), g[f"pred{i}"]) < REL
+    roi, _, subj = scoring.deviation(xc, xhat[0])
+    for i in range(len(xc)):
+        assert relerr(roi[i].cpu().numpy(), g[f"dev_roi{i}"]) < 5e-4      # squares amplify xhat error x2
+        assert relerr(subj[i].cpu().numpy(), g[f"dev{i}"]) < 5e-4
+    # the deviation kernel itself, fed the reference's own reconstruction: 1e-5
+    ref_hat = [torch.from_numpy(g[f"pred{i}"]).cuda() for i in range(len(xc))]
+    roi, _, subj = scoring.deviation(xc, ref_hat)
+    for i in range(len(xc)):
+        assert relerr(roi[i].cpu().numpy(), g[f"dev_roi{i}"]) < 1e-5
+        assert relerr(subj[i].cpu().numpy(), g[f"dev{i}"]) < 1e-5
+    tr.close()
+
+
+def test_single_modality_cvae_mean_decode(golden_dir):
+    """cVAE.pred_recon decodes the mean (cVAE.py:549-555); cVAE state_dict names are accepted."""
+    from multi_modal_normative_modeling_b200 import EnsembleTrainer, MemberSpec, pack_rows
+    g = load(golden_dir, "cvae_D116_full")
+    xc = [pack_rows(torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["c"]).cuda())]
+    sd = {k: torch.from_numpy(v) for k, v in sub(g, "final/").items() if not k.startswith("discriminator")}
+    tr = EnsembleTrainer([MemberSpec([int(g["d"])], [int(h) for h in g["hidden"]], int(g["z"]), int(g["c_dim"]),
+                                     xc, state_dict=sd)])
+    xhat, mu, lv = tr.reconstruct([xc], mode="mean", want_latent=True)
+    torch.cuda.synchronize()
+    assert relerr(xhat[0][0].cpu().numpy(), g["pred"]) < REL
+    assert relerr(mu[0].cpu().numpy(), g["latent"]) < REL
+    assert relerr(lv[0].exp().cpu().numpy(), g["latent_var"]) < REL
+    tr.close()
+
+
+def test_epochs_partial_batches_and_heterogeneous_ensemble_vs_oracle():
+    """Several members of DIFFERENT architectures in one launch, ragged last batch, 3 epochs,
+    against the numpy oracle's restatement of the reference loop."""
+    from oracle import cvae_numpy, cvae_torch
+    from multi_modal_normative_modeling_b200 import EnsembleTrainer, MemberSpec, pack_rows
+    rng = np.random.RandomState(0)
+    cfgs = [([17], [12, 9], 4, "poe", "gauss_ll"), ([9, 5], [8], 4, "gPoE", "gauss_ll"),
+            ([6, 7, 8], [10, 6, 5], 4, "mopoe", "neg_mse"), ([33], [20, 12], 4, "moe", "gauss_ll")]
+    n, batch, epochs, c_dim = 23, 8, 3, 6
+    spe = -(-n // batch)
+    specs, ref = [], []
+    for k, (dims, hidden, z, combine, loss) in enumerate(cfgs):
+        torch.manual_seed(100 + k)
+        model = cvae_torch.OracleCVAEMultimodal(dims, hidden, z, c_dim, 1e-4, len(dims), True, loss)
+        sd = {a: b.detach().clone() for a, b in model.state_dict().items()}
+        xs = [rng.randn(n, d).astype(np.float32) for d in dims]
+        c = np.zeros((n, c_dim), np.float32)
+        c[np.arange(n), rng.randint(0, 4, n)] = 1
+        c[np.arange(n), 4 + rng.randint(0, 2, n)] = 1
+        eps = rng.randn(epochs * spe, batch, z).astype(np.float32)
+        lr_steps = (1e-4 * (1 + 0.5 * np.sin(np.arange(epochs * spe)))).astype(np.float32)
+        specs.append(MemberSpec(dims, hidden, z, c_dim, [pack_rows(torch.from_numpy(x).cuda(), torch.from_numpy(c).cuda())
+                                                          for x in xs], combine=combine, loss_kind=loss, batch=batch,
+                                state_dict=sd, lr_steps=torch.from_numpy(lr_steps).cuda()))
+        p = {a: b.numpy().astype(np.float64) for a, b in sd.items()}
+        log = cvae_numpy.train(p, [x.astype(np.float64) for x in xs], [c.astype(np.float64)] * len(dims),
+                               eps.astype(np.float64), combine, epochs, batch, lr_steps=lr_steps.astype(np.float64),
+                               loss_kind=loss)
+        ref.append((p, log, eps, sd))
+    tr = EnsembleTrainer(specs)
+    eps_all = torch.from_numpy(np.stack([r[2] for r in ref])).cuda()
+    losses = tr.train_steps(epochs * spe, eps=eps_all, record_losses=True).cpu().numpy()
+    for k, (p, log, _, sd0) in enumerate(ref):
+        assert np.allclose(losses[k], log, rtol=REL, atol=1e-5), k
+        got = tr.state_dict(k)
+        for name, v in p.items():
+            if name.startswith("alpha") and name not in got:
+                continue
+            d_ref = v - sd0[name].numpy()
+            d_got = got[name].cpu().numpy().reshape(v.shape) - sd0[name].numpy()
+            if np.abs(d_ref).max() == 0:
+                assert np.abs(d_got).max() == 0, (k, name)
+            else:
+                assert np.abs(d_got - d_ref).max() / np.abs(d_ref).max() < 5e-3, (k, name)
+    tr.close()
+
+
+def test_philox_stream_vs_oracle():
+    from oracle import philox
+    from multi_modal_normative_modeling_b200 import scoring
+    for seed, step, stream, n in ((1234, 0, 0, 2560), (2**40 + 17, 2**33 + 5, 1, 1001), (0, 0, 0, 3)):
+        got = scoring.philox_normal(seed, step, n, stream).cpu().numpy()
+        want = philox.normals(seed, step, n, stream)
+        assert np.abs(got - want).max() < 2e-5, (seed, step)       # libm vs CUDA logf/sincosf
+
+
+def test_production_eps_is_the_philox_stream():
+    """Without injected eps the kernel must draw exactly the documented Philox stream: training
+    with in-kernel RNG == training with that stream injected."""
+    from multi_modal_normative_modeling_b200 import scoring
+    from multi_modal_normative_modeling_b200 import EnsembleTrainer, MemberSpec, pack_rows
+    rng = np.random.RandomState(3)
+    n, d, c_dim, z, batch = 20, 11, 5, 4, 8
+    x = torch.from_numpy(rng.randn(n, d).astype(np.float32)).cuda()
+    c = torch.zeros(n, c_dim).cuda(); c[:, 0] = 1
+    xc = [pack_rows(x, c)]
+    from oracle import cvae_torch
+    torch.manual_seed(5)
+    sd = cvae_torch.OracleCVAEMultimodal([d], [9, 7], z, c_dim, modalities=1, non_linear=True).state_dict()
+    sd = {k: v.detach().clone() for k, v in sd.items()}
+    steps = 5
+    a = EnsembleTrainer([MemberSpec([d], [9, 7], z, c_dim, xc, batch=batch, seed=99, state_dict=sd)])
+    a.train_steps(steps)
+    eps = torch.stack([torch.nn.functional.pad(scoring.philox_normal(99, s, batch * z, 0), (0, 0)).view(batch, z)
+                       for s in range(steps)])[None]
+    b = EnsembleTrainer([MemberSpec([d], [9, 7], z, c_dim, xc, batch=batch, seed=1, state_dict=sd)])
+    b.train_steps(steps, eps=eps)
+    torch.cuda.synchronize()
+    assert torch.equal(a.params, b.params)
+    a.close(); b.close()
+
+
+def test_stats_zscores_auc_vs_oracle():
+    from oracle import deviation as odev
+    from multi_modal_normative_modeling_b200 import scoring, pack_rows
+    rng = np.random.RandomState(11)
+    segs = [(200, 116), (57, 150), (1000, 348), (3, 5)]
+    xs, hats, masks, labels = [], [], [], []
+    for n, d in segs:
+        x = rng.randn(n, d).astype(np.float32)
+        xs.append(pack_rows(torch.from_numpy(x).cuda(), torch.zeros(n, 2).cuda()))
+        hats.append(torch.from_numpy((x + 0.3 * rng.randn(n, d)).astype(np.float32)).cuda())
+        m = (rng.rand(n) < 0.7)
+        m[0] = True
+        masks.append(torch.from_numpy(m.astype(np.uint8)).cuda())
+        lab = (rng.rand(n) < 0.3).astype(np.uint8)
+        lab[0], lab[-1] = 0, 1
+        labels.append(torch.from_numpy(lab).cuda())
+    stats = scoring.normative_stats(xs, hats, masks)
+    roi, z, subj = scoring.deviation(xs, hats, stats)
+    aucs, u2 = scoring.auc(z, labels, want_pairs=True)
+    subj_auc, subj_u2 = scoring.auc(subj, labels, want_pairs=True)
+    torch.cuda.synchronize()
+    for s, (n, d) in enumerate(segs):
+        x64 = xs[s][:, :d].cpu().numpy().astype(np.float64)
+        r = odev.recon_deviation_roi(x64, hats[s].cpu().numpy())
+        mean, std = odev.normative_stats(r[masks[s].cpu().numpy().astype(bool)])
+        assert relerr(stats[s][0].cpu().numpy(), mean) < 1e-5
+        assert relerr(stats[s][1].cpu().numpy(), std) < 1e-5
+        assert relerr(roi[s].cpu().numpy(), r) < 1e-5
+        assert relerr(subj[s].cpu().numpy(), odev.recon_deviation(x64, hats[s].cpu().numpy())) < 1e-5
+        zz = odev.zscores(r, mean, std)
+        assert np.abs(z[s].cpu().numpy() - zz).max() < 1e-3 * max(1.0, np.abs(zz).max())
+        # AUC: integer pair counts on the kernel's own scores are bit-exact against the oracle
+        zk = z[s].cpu().numpy()
+        lab = labels[s].cpu().numpy()
+        for col in range(0, d, max(1, d // 7)):
+            want_u2, n1, n0 = odev.auc_pairs(zk[:, col], lab)
+            assert int(u2[s][col]) == want_u2, (s, col)
+            assert float(aucs[s][col]) == want_u2 / (2.0 * n1 * n0)
+        want_u2, n1, n0 = odev.auc_pairs(subj[s].cpu().numpy(), lab)
+        assert int(subj_u2[s][0]) == want_u2
+
+
+def test_auc_ties_chunks_and_degenerate():
+    from oracle import deviation as odev
+    from multi_modal_normative_modeling_b200 import scoring
+    rng = np.random.RandomState(5)
+    n = 20000                                   # > one 8192-row chunk
+    sc = np.round(rng.randn(n, 3), 1).astype(np.float32)      # heavy ties
+    lab = (rng.rand(n) < 0.4).astype(np.uint8)
+    allneg = np.zeros(50, np.uint8)
+    out, u2 = scoring.auc([torch.from_numpy(sc).cuda(), torch.from_numpy(sc[:50]).cuda()],
+                          [torch.from_numpy(lab).cuda(), torch.from_numpy(allneg).cuda()], want_pairs=True)
+    for col in range(3):
+        want, n1, n0 = odev.auc_pairs(sc[:, col], lab)
+        assert int(u2[0][col]) == want
+        assert float(out[0][col]) == want / (2.0 * n1 * n0)
+    assert torch.isnan(out[1]).all()            # no positives -> undefined, like sklearn's error case
+
+
+def test_error_behaviour():
+    from multi_modal_normative_modeling_b200 import _lib, EnsembleTrainer, MemberSpec, pack_rows
+    with pytest.raises(ValueError, match="No such combination method"):      # cVAE.py:1163
+        _lib.make_arch([4], [3], 2, 1, combine="concat")
+    x = pack_rows(torch.zeros(4, 5).cuda(), torch.zeros(4, 2).cuda())
+    with pytest.raises(ValueError):
+        EnsembleTrainer([MemberSpec([7], [3], 2, 2, [x])])                    # wrong packed width
+    with pytest.raises(RuntimeError):
+        pack_rows(torch.zeros(4, 5), torch.zeros(4, 2))                       # CPU tensors: no fallback
