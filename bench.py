@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""Benchmark of the cVAE-ensemble hot path (BASELINE.json metric: cVAE train samples/s (all
+models) & deviation subjects/s at 1/2/4/8 B200 vs CPU).
+
+    python bench.py --gpus N --steps K --warmup W            # this framework (CUDA, libnmb.so)
+    python bench.py --impl reference --steps K --warmup W    # the reference's PyTorch CPU path
+
+Workload (config.workload = "cfg4"): 5 folds x {T1w, T2w, fMRI (D=116), early fusion (D=348)} x 24
+seeds = 480 independent cVAEs per GPU (weak scaling: every rank trains its own 480-member
+ensemble with distinct seeds), hidden [110,110], latent 10, C=29, batch 256, 800 bootstrap rows
+per fold, synthetic HCP-shaped data, reference-exact random initialisation.
+One "step" = `--epochs-per-step` epochs (default 5 = 20 minibatch steps) of EVERY member in ONE
+fused kernel launch (forward + loss + backward + Adam).  `value` counts training samples only;
+deviation scoring is timed separately and reported under "deviation".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "cVAE train samples/s (all models)"
+UNIT = "samples/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--seeds", type=int, default=24, help="seeds per (fold, modality): 24 -> 480 members per GPU")
+    ap.add_argument("--epochs-per-step", type=int, default=5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-deviation", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the bounded CPU sample")
+    return ap.parse_args()
+
+
+def config(args, extra=None):
+    c = {"workload": "cfg4: 5 folds x 4 modalities (D=116,116,116,348) x %d seeds = %d cVAEs per GPU"
+                     % (args.seeds, 20 * args.seeds),
+         "hidden": [110, 110], "latent": 10, "c_dim": 29, "batch": 256, "n_train": 800, "n_test": 200,
+         "epochs_per_step": args.epochs_per_step, "members_per_gpu": 20 * args.seeds,
+         "parallelism": "member-sharded, no gradient collective",
+         "l2": "working set (params+Adam+scratch > 600 MB) exceeds the 126 MB L2"}
+    if extra:
+        c.update(extra)
+    return c
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU baseline: the reference's eager PyTorch loop, restated in oracle/cvae_torch.py (the reference
+# is Python and cannot travel to the GPU box; kind = "port").
+def cpu_reference_sample(hw, epochs, budget_s, threads=None):
+    import torch
+    from oracle import cvae_torch
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    names = hw.names
+    done_samples, t_total, models = 0, 0.0, 0
+    fold = hw.folds[0]
+    for name in names:                      # one fold x all 4 modalities keeps the 3:1 D=116 : D=348 mix
+        d = hw.dims[name]
+        torch.manual_seed(42)
+        model = cvae_torch.OracleCVAEMultimodal([d], list(hw.hidden), hw.latent, hw.c_dim, 1e-4, 1, True)
+        x = torch.from_numpy(fold.train_x[name])
+        c = torch.from_numpy(fold.train_c).long()          # int64 one-hots (utils_vae.py:24)
+        t0 = time.perf_counter()
+        cvae_torch.reference_train_loop(model, [x], [c], "gPoE", epochs, hw.batch)
+        t_total += time.perf_counter() - t0
+        done_samples += x.shape[0] * epochs
+        models += 1
+        if t_total > budget_s:
+            break
+    return done_samples / t_total, threads, models, t_total
+
+
+def cpu_deviation_sample(hw, threads):
+    """pred_recon + deviation + roc/auc on the host for one fold x 4 modalities (subjects/s)."""
+    import numpy as np
+    import torch
+    from oracle import cvae_torch, deviation as odev
+    torch.set_num_threads(threads)
+    fold = hw.folds[0]
+    labels = (fold.test_df["DIA"].to_numpy() != hw.hc_label).astype(np.int64)
+    n, t_total = 0, 0.0
+    for name in hw.names:
+        d = hw.dims[name]
+        torch.manual_seed(42)
+        model = cvae_torch.OracleCVAEMultimodal([d], list(hw.hidden), hw.latent, hw.c_dim, 1e-4, 1, True)
+        x = torch.from_numpy(fold.test_x[name]); c = torch.from_numpy(fold.test_c).long()
+        xt = torch.from_numpy(fold.train_x[name]); ct = torch.from_numpy(fold.train_c).long()
+        t0 = time.perf_counter()
+        pred = model.pred_recon([x], c, "gPoE")[0].numpy()
+        pred_tr = model.pred_recon([xt], ct, "gPoE")[0].numpy()
+        roi = odev.recon_deviation_roi(fold.test_x64[name], pred)
+        subj = odev.recon_deviation(fold.test_x64[name], pred)
+        mean, std = odev.normative_stats(odev.recon_deviation_roi(fold.train_x[name], pred_tr))
+        z = odev.zscores(roi, mean, std)
+        _ = [odev.auc(z[:, j], labels) for j in range(d)]
+        _ = odev.auc(subj, labels)
+        t_total += time.perf_counter() - t0
+        n += x.shape[0]
+    return n / t_total
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from multi_modal_normative_modeling_b200 import workloads
+    hw = workloads.build_host_workload()
+    threads = os.cpu_count() or 1
+    # each step = a bounded sample (1 fold x 4 modalities x epochs_per_step epochs = 16k samples)
+    for _ in range(args.warmup):
+        cpu_reference_sample(hw, 1, 1e9, threads)
+    t0 = time.perf_counter()
+    samples = 0
+    for _ in range(args.steps):
+        rate, _, models, dt = cpu_reference_sample(hw, args.epochs_per_step, 1e9, threads)
+        samples += rate * dt
+    el = time.perf_counter() - t0
+    value = samples / el
+    sample = "1 fold x 4 modalities x %d epochs per step, oracle/cvae_torch.py eager loop" % args.epochs_per_step
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / max(args.steps, 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config(args),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """nvidia-smi-equivalent clock / throttle-reason samples (NVML) during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                     "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                     "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                     "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+            while not self.stop_flag:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+                time.sleep(0.02)
+        except Exception as e:          # NVML unavailable: report that instead of inventing numbers
+            self.reasons.add("nvml_error:%s" % type(e).__name__)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from multi_modal_normative_modeling_b200 import EnsembleTrainer, pack_rows, scoring, workloads
+    from multi_modal_normative_modeling_b200 import distributed as nd
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    hw = workloads.build_host_workload()
+    wl = workloads.to_device(hw, dev, n_seeds=args.seeds, seed0=rank * args.seeds, pin=True)
+    tr = EnsembleTrainer(wl.specs, device=dev)
+    spe = tr.steps_per_epoch[0]
+    n_steps = args.epochs_per_step * spe
+    samples_per_step = wl.samples_per_epoch * args.epochs_per_step
+    flops_per_step = wl.flops_per_epoch * args.epochs_per_step
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident throughput (`value`) ------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        tr.train_steps(n_steps)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches0 = tr.gpu_launches
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for a, b in ev:
+        a.record()
+        tr.train_steps(n_steps)
+        b.record()
+    t_end.record()
+    barrier()
+    sampler.stop_flag = True
+    sampler.join()
+    elapsed_ms = t_start.elapsed_time(t_end)
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    launches = tr.gpu_launches - launches0
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t[0])
+    value = world * samples_per_step * args.steps / (elapsed_ms * 1e-3)
+
+    # ---- end-to-end through the public API with HOST buffers ----------------------------------
+    keys = list(wl.host_buffers)
+    h2d = sum(x.numel() * 4 + c.numel() * 4 for x, c in wl.host_buffers.values())
+    loss_host = torch.empty((tr.n, n_steps, 3), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        for k in keys:
+            x, c = wl.host_buffers[k]
+            pack_rows(x.to(dev, non_blocking=True), c.to(dev, non_blocking=True), out=wl.packed[k])
+        losses = tr.train_steps(n_steps, record_losses=True)
+        loss_host.copy_(losses, non_blocking=True)
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t[0])
+    e2e_value = world * samples_per_step * args.steps / (e2e_ms * 1e-3)
+    final_loss = float(loss_host[:, -1, 0].mean())
+
+    # ---- deviation scoring: reconstruct -> normative stats -> deviation/z -> AUC -> all-gather --
+    deviation = None
+    if not args.no_deviation:
+        train_xc = [s.xc for s in wl.specs]
+        dmax = max(int(s.input_dims[0]) for s in wl.specs)
+        groups = {}
+        for i, s in enumerate(wl.specs):
+            groups.setdefault(int(s.input_dims[0]), []).append(i)
+        groups = {d: torch.tensor(v, device=dev) for d, v in groups.items()}
+
+        def dev_step():
+            xhat_tr, _, _ = tr.reconstruct(train_xc, mode="mean")
+            xhat_te, _, _ = tr.reconstruct(wl.test_xc, mode="mean")
+            x_tr = [t[0] for t in train_xc]; x_te = [t[0] for t in wl.test_xc]
+            stats = scoring.normative_stats(x_tr, [h[0] for h in xhat_tr], wl.train_hc_mask)
+            roi, z, subj = scoring.deviation(x_te, [h[0] for h in xhat_te], stats)
+            roi_auc = scoring.auc(z, wl.test_labels)
+            subj_auc = scoring.auc(subj, wl.test_labels)
+            # fixed-size per-member record {subject AUC | per-ROI mean | per-ROI std | per-ROI AUC}, padded to Dmax
+            rec = torch.zeros((tr.n, 1 + 3 * dmax), dtype=torch.float64, device=dev)
+            rec[:, 0] = torch.cat(subj_auc)
+            for d, idx in groups.items():
+                st = torch.stack([stats[i] for i in idx]).double()
+                rec[idx, 1:1 + d] = st[:, 0]
+                rec[idx, 1 + dmax:1 + dmax + d] = st[:, 1]
+                rec[idx, 1 + 2 * dmax:1 + 2 * dmax + d] = torch.stack([roi_auc[i] for i in idx])
+            owned = list(range(rank * tr.n, (rank + 1) * tr.n))
+            table = nd.gather_member_tables(rec, owned, world * tr.n)      # NCCL all-gather over NVLink
+            return table, subj_auc
+        for _ in range(2):
+            dev_step()
+        barrier()
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = max(3, min(args.steps, 10))
+        d0.record()
+        for _ in range(reps):
+            table, subj_auc = dev_step()
+        d1.record()
+        barrier()
+        dms = d0.elapsed_time(d1)
+        if world > 1:
+            t = torch.tensor([dms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dms = float(t[0])
+        # algorithmic bytes of the streaming deviation kernel: read x (ldx) + xhat, write roi + z + subj
+        dev_bytes = sum(t[0].shape[0] * (4 * (3 * s.input_dims[0] + t[0].shape[1]) + 4)
+                        for t, s in zip(wl.test_xc, wl.specs))
+        deviation = {"value": world * wl.test_subjects * reps / (dms * 1e-3), "unit": "subjects/s",
+                     "ms_per_pass": dms / reps, "subjects_per_pass": world * wl.test_subjects,
+                     "mean_subject_auc": float(torch.cat(subj_auc).mean()),
+                     "gathered_table": list(table.shape), "launches_per_pass": 6,
+                     "streaming_kernel_algorithmic_bytes": dev_bytes}
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak_tf = peaks.get("bf16_tflops_sustained") or 1400.0
+        peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained"
+        achieved = flops_per_step / (kernel_ms * 1e-3) / 1e12
+        clocks = sampler.summary()
+        sm_mhz = clocks["sm_mhz"] or 1965
+        fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12          # FFMA roof at the clock seen under load
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "train_kernel_traffic.json"))).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": config(args, {"final_mean_total_loss": final_loss}),
+                "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                             "frac": achieved / peak_tf, "traffic": traffic, "kernel": "nmb::train_kernel",
+                             "kernel_ms": kernel_ms, "algorithmic_flops_per_launch": flops_per_step,
+                             "peak_source": peak_src,
+                             "note": "kernel computes in FP32 FFMA (1e-4 parity bar rules out single-pass TF32/BF16); "
+                                     "FP32 FFMA roof at the sampled clock = %.1f TFLOP/s -> frac_of_fp32 = %.3f"
+                                     % (fp32_peak, achieved / fp32_peak),
+                             "fp32_ffma_peak": fp32_peak, "frac_of_fp32": achieved / fp32_peak},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": loss_host.numel() * 4, "ms_per_step": e2e_ms / args.steps},
+                "gpu_launches": launches, "clocks": clocks}
+        if deviation:
+            line["deviation"] = deviation
+        if not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            rate, cores, models, dt = cpu_reference_sample(hw, 5, args.cpu_seconds, threads)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": "%d model(s) of fold 0 (modalities in order) x 5 epochs, %.1f s, "
+                                              "oracle/cvae_torch.py eager PyTorch loop" % (models, dt),
+                                    "deviation_subjects_per_s": cpu_deviation_sample(hw, threads)}
+        print(json.dumps(line))
+    tr.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -130,6 +130,13 @@ enum {
 int nmb_ensemble_train(NmbEnsemble* ens, int64_t n_steps, const float* eps_override,
                        float* loss_out, uint32_t flags, void* stream);
 
+/* Stand-alone Adam update over a packed buffer: optimizer1.step() (torch.optim.Adam defaults,
+ * cVAE.py:1111-1116) for the per-step nn.Module API, where forward/backward and step() are
+ * separate calls.  t = 1-based step count.  Entries with zero gradient and zero state do not move,
+ * which reproduces torch's "skip parameters whose grad is None". */
+int nmb_adam_step(float* params, const float* grads, float* adam_m, float* adam_v, int64_t n,
+                  int64_t t, float lr, float beta1, float beta2, float adam_eps, void* stream);
+
 /* Activations of the LAST executed step of one member (debug / per-step parity):
  * mu, logvar: fused latent [rows][latent]; x_recon[m]: [rows][input_dims[m]] (needs
  * NMB_TRAIN_KEEP_ACTS).  Any pointer may be NULL.  rows = size of that step's minibatch. */

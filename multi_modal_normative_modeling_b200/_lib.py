@@ -48,6 +48,8 @@ _PROTOS = {
     "nmb_ensemble_size": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
     "nmb_ensemble_steps_done": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]),
     "nmb_ensemble_train": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
+    "nmb_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_float,
+                                C.c_float, C.c_float, C.c_float, C.c_void_p]),
     "nmb_ensemble_peek": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p),
                                     C.POINTER(C.c_int32), C.c_void_p]),
     "nmb_ensemble_reconstruct": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_int32,

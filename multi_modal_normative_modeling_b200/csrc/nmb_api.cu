@@ -1,4 +1,5 @@
 // C ABI of libnmb.so (see include/nmb.h for the contract and the reference citations).
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -380,6 +381,16 @@ int nmb_mean_rows(const float* const* src, int32_t k, int64_t n, float* out, voi
   PtrTable16 t; std::memset(&t, 0, sizeof(t));
   for (int i = 0; i < k; ++i) { if (!src[i]) return fail("null source"); t.p[i] = src[i]; }
   launch_mean_rows(t, k, n, out, (cudaStream_t)stream);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int nmb_adam_step(float* params, const float* grads, float* adam_m, float* adam_v, int64_t n, int64_t t, float lr,
+                  float beta1, float beta2, float adam_eps, void* stream) {
+  if (!params || !grads || !adam_m || !adam_v || n < 0 || t < 1) return fail("bad argument");
+  const double bc1 = 1.0 - pow((double)beta1, (double)t), bc2 = 1.0 - pow((double)beta2, (double)t);
+  launch_adam(params, grads, adam_m, adam_v, n, (float)((double)lr / bc1), (float)sqrt(bc2), beta1, beta2, adam_eps,
+              (cudaStream_t)stream);
   CU(cudaGetLastError());
   return 0;
 }

@@ -248,6 +248,24 @@ void launch_mean_rows(const PtrTable16& src, int k, long long n, float* out, cud
   mean_rows_kernel<<<blocks, 256, 0, st>>>(src, k, n, out);
 }
 
+__global__ void adam_kernel(float* p, const float* g, float* m, float* v, long long n, float step_size,
+                            float bc2_sqrt, float b1, float b2, float eps) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float grad = g[i];
+    const float m1 = b1 * m[i] + (1.f - b1) * grad;
+    const float v1 = b2 * v[i] + (1.f - b2) * grad * grad;
+    m[i] = m1; v[i] = v1;
+    p[i] -= step_size * (m1 / (sqrtf(v1) / bc2_sqrt + eps));
+  }
+}
+
+void launch_adam(float* p, const float* g, float* m, float* v, long long n, float step_size, float bc2_sqrt,
+                 float b1, float b2, float eps, cudaStream_t st) {
+  if (n == 0) return;
+  const int blocks = (int)min((n + 255) / 256, (long long)148 * 8);
+  adam_kernel<<<blocks, 256, 0, st>>>(p, g, m, v, n, step_size, bc2_sqrt, b1, b2, eps);
+}
+
 __global__ void philox_kernel(unsigned long long seed, unsigned long long step, uint32_t stream_id, long long n,
                               float* out) {
   for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g * 4 < n;

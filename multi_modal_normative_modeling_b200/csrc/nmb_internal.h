@@ -36,6 +36,8 @@ void launch_stats(const SegTable& t, int n_seg, int max_d, cudaStream_t st);
 void launch_deviation(const SegTable& t, int n_seg, int max_rows, cudaStream_t st);
 void launch_auc(const AucTable& t, int n_seg, int max_cols, cudaStream_t st);
 void launch_mean_rows(const PtrTable16& src, int k, long long n, float* out, cudaStream_t st);
+void launch_adam(float* p, const float* g, float* m, float* v, long long n, float step_size, float bc2_sqrt,
+                 float b1, float b2, float eps, cudaStream_t st);
 void launch_philox(unsigned long long seed, unsigned long long step, uint32_t stream_id, long long n, float* out,
                    cudaStream_t st);
 

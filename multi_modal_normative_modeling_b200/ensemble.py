@@ -30,7 +30,7 @@ def _stream_ptr(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
-def pack_rows(x: torch.Tensor, c: torch.Tensor) -> torch.Tensor:
+def pack_rows(x: torch.Tensor, c: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """[x | c | 1 | 0-pad] rows (``torch.cat((x, c), dim=1)`` of cVAE.py:163 done once per dataset).
 
     x: [N, D] float32 CUDA, c: [N, C] any dtype (int64 one-hots are cast like ``cat`` promotes)."""
@@ -40,7 +40,10 @@ def pack_rows(x: torch.Tensor, c: torch.Tensor) -> torch.Tensor:
     c = c.detach().to(device=x.device, dtype=torch.float32).reshape(x.shape[0], -1).contiguous()
     n, d = x.shape
     ldx = _lib.packed_row_stride(d, c.shape[1])
-    out = torch.empty((n, ldx), dtype=torch.float32, device=x.device)
+    if out is None:
+        out = torch.empty((n, ldx), dtype=torch.float32, device=x.device)
+    elif tuple(out.shape) != (n, ldx) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != x.device:
+        raise ValueError(f"out must be a contiguous float32 [{n},{ldx}] tensor on {x.device}")
     with torch.cuda.device(x.device):
         _lib.check(_lib.load().nmb_pack_rows(x.data_ptr(), c.data_ptr(), n, d, c.shape[1], out.data_ptr(),
                                              _stream_ptr(x.device)), "nmb_pack_rows")
