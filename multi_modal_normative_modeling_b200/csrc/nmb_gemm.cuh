@@ -98,7 +98,7 @@ struct TileLoader {
 };
 
 // All threads of the CTA must call with identical arguments.  `smem` >= kGemmSmemFloats floats.
-// epi(m, n, value) is invoked exactly once for every (m < M, n < N).
+// epi.row<TN>(m, nb, N, v) receives the TN values of row m at columns nb + 16*j (valid if < N).
 template <int TN, class Epi>
 __device__ __noinline__ void gemm(int M, int N, int K, Opnd A, Opnd B, Epi& epi, float* smem) {
   constexpr int BN = 16 * TN;
@@ -120,8 +120,7 @@ __device__ __noinline__ void gemm(int M, int N, int K, Opnd A, Opnd B, Epi& epi,
       TileLoader<BN> lb;
       la.load(A, m0, M, 0, K);
       lb.load(B, n0, N, 0, K);
-      __syncthreads();               // previous tile's readers are done with buffer 0
-      la.store(A, As);
+      la.store(A, As);               // buffer 0 is free: the previous tile ended on a barrier
       lb.store(B, Bs);
       __syncthreads();
 
@@ -133,7 +132,7 @@ __device__ __noinline__ void gemm(int M, int N, int K, Opnd A, Opnd B, Epi& epi,
         }
         const float* as = As + cur * BK * LDA + ty * TM;
         const float* bs = Bs + cur * BK * LDB + tx;
-#pragma unroll
+#pragma unroll 4
         for (int kk = 0; kk < BK; ++kk) {
           const float4 a0 = *reinterpret_cast<const float4*>(as + kk * LDA);
           const float4 a1 = *reinterpret_cast<const float4*>(as + kk * LDA + 4);
@@ -153,16 +152,13 @@ __device__ __noinline__ void gemm(int M, int N, int K, Opnd A, Opnd B, Epi& epi,
         __syncthreads();
       }
 
+      // Epilogue, one output row per call: the functor first issues ALL of its global loads for the
+      // row (targets, activations, Adam state ...) and only then computes and stores, so a thread has
+      // TN..3*TN independent loads in flight instead of one load -> use -> store chain per element.
 #pragma unroll
       for (int i = 0; i < TM; ++i) {
         const int m = m0 + ty * TM + i;
-        if (m < M) {
-#pragma unroll
-          for (int j = 0; j < TN; ++j) {
-            const int n = n0 + tx + 16 * j;
-            if (n < N) epi(m, n, acc[i][j]);
-          }
-        }
+        if (m < M) epi.template row<TN>(m, n0 + tx, N, acc[i]);
       }
     }
   }

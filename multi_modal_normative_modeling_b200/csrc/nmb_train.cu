@@ -32,58 +32,94 @@ struct StepCtx {
 };
 
 // ---- epilogues ---------------------------------------------------------------------------
+// row<TN>(m, nb, N, v): v[j] is C[m][nb + 16*j].  Loads first, then math + stores (see gemm()).
 struct EpiHidden {     // h = leaky_relu(a) (bias already inside a via the ones column)
   float* dst; int ld; int nl;
-  __device__ __forceinline__ void operator()(int m, int n, float v) {
-    dst[(long long)m * ld + n] = (nl && v <= 0.f) ? kSlope * v : v;
+  template <int TN>
+  __device__ __forceinline__ void row(int m, int nb, int N, const float (&v)[TN]) {
+    float* d = dst + (long long)m * ld + nb;
+#pragma unroll
+    for (int j = 0; j < TN; ++j)
+      if (nb + 16 * j < N) d[16 * j] = (nl && v[j] <= 0.f) ? kSlope * v[j] : v[j];
   }
 };
 
 struct EpiStore {
   float* dst; int ld;
-  __device__ __forceinline__ void operator()(int m, int n, float v) { dst[(long long)m * ld + n] = v; }
+  template <int TN>
+  __device__ __forceinline__ void row(int m, int nb, int N, const float (&v)[TN]) {
+    float* d = dst + (long long)m * ld + nb;
+#pragma unroll
+    for (int j = 0; j < TN; ++j)
+      if (nb + 16 * j < N) d[16 * j] = v[j];
+  }
 };
 
 // x_recon epilogue: loss terms + d(total)/d(x_recon) in one pass.
 struct EpiRecon {
   const float* x; int ldx;        // targets: packed rows (first D columns)
   const float* lam;               // logvar_out [D]
-  float* dxh; int ld;             // out: gradient (or x_recon itself when keep)
+  float* dxh; int ld;             // out: gradient d(total)/d(x_recon)
   float* keep;                    // optional copy of x_recon (ld) for peek
   float inv_rows, inv_rows_d;     // 1/B, 1/(B*D)
   int gauss;
   float ll_acc;                   // per-thread partial of sum over elements
-  __device__ __forceinline__ void operator()(int m, int n, float v) {
-    const float r = x[(long long)m * ldx + n] - v;
-    float g;
-    if (gauss) {
-      const float l = lam[n];
-      const float iv = __expf(-l);            // 1 / sigma^2
-      ll_acc += -0.5f * r * r * iv - 0.5f * l - 0.5f * kLog2Pi;
-      g = -r * iv * inv_rows;
-    } else {
-      ll_acc += -r * r;
-      g = -2.f * r * inv_rows_d;
+  template <int TN>
+  __device__ __forceinline__ void row(int m, int nb, int N, const float (&v)[TN]) {
+    float xt[TN], l[TN];
+    const float* xr = x + (long long)m * ldx + nb;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const bool ok = nb + 16 * j < N;
+      xt[j] = ok ? xr[16 * j] : 0.f;
+      l[j] = (ok && gauss) ? lam[nb + 16 * j] : 0.f;
     }
-    if (keep) keep[(long long)m * ld + n] = v;
-    dxh[(long long)m * ld + n] = g;
+    float* g = dxh + (long long)m * ld + nb;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      if (nb + 16 * j < N) {
+        const float r = xt[j] - v[j];
+        if (gauss) {
+          const float iv = __expf(-l[j]);            // 1 / sigma^2
+          ll_acc += -0.5f * r * r * iv - 0.5f * l[j] - 0.5f * kLog2Pi;
+          g[16 * j] = -r * iv * inv_rows;
+        } else {
+          ll_acc += -r * r;
+          g[16 * j] = -2.f * r * inv_rows_d;
+        }
+        if (keep) keep[(long long)m * ld + nb + 16 * j] = v[j];
+      }
+    }
   }
 };
 
 struct EpiDgrad {      // d_pre = d_act * leaky_relu'(pre), sign recovered from the stored activation
   float* dst; int ld;
   const float* act; int ld_act; int nl;
-  __device__ __forceinline__ void operator()(int m, int n, float v) {
-    const float h = act[(long long)m * ld_act + n];
-    dst[(long long)m * ld + n] = (nl && h <= 0.f) ? kSlope * v : v;
+  template <int TN>
+  __device__ __forceinline__ void row(int m, int nb, int N, const float (&v)[TN]) {
+    float h[TN];
+    const float* a = act + (long long)m * ld_act + nb;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) h[j] = (nl && nb + 16 * j < N) ? a[16 * j] : 1.f;
+    float* d = dst + (long long)m * ld + nb;
+#pragma unroll
+    for (int j = 0; j < TN; ++j)
+      if (nb + 16 * j < N) d[16 * j] = h[j] <= 0.f ? kSlope * v[j] : v[j];
   }
 };
 
 struct EpiDz {
   float* dz; int Z; int accumulate;
-  __device__ __forceinline__ void operator()(int m, int n, float v) {
-    float* p = dz + m * Z + n;
-    *p = accumulate ? *p + v : v;
+  template <int TN>
+  __device__ __forceinline__ void row(int m, int nb, int N, const float (&v)[TN]) {
+    float old[TN];
+    float* p = dz + m * Z + nb;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) old[j] = (accumulate && nb + 16 * j < N) ? p[16 * j] : 0.f;
+#pragma unroll
+    for (int j = 0; j < TN; ++j)
+      if (nb + 16 * j < N) p[16 * j] = old[j] + v[j];
   }
 };
 
@@ -91,20 +127,48 @@ struct AdamCfg {
   float* p; float* m; float* v; float* g;
   float step_size, bc2_sqrt, b1, b2, eps;
   unsigned flags;
+  __device__ __forceinline__ float update(float& m1, float& v1, float p0, float grad) const {
+    m1 = b1 * m1 + (1.f - b1) * grad;
+    v1 = b2 * v1 + (1.f - b2) * grad * grad;
+    return p0 - step_size * (m1 / (sqrtf(v1) / bc2_sqrt + eps));
+  }
   __device__ __forceinline__ void apply(long long idx, float grad) const {
     if (flags & NMB_TRAIN_WRITE_GRADS) g[idx] = grad;
     if (!(flags & NMB_TRAIN_NO_ADAM)) {
-      const float m1 = b1 * m[idx] + (1.f - b1) * grad;
-      const float v1 = b2 * v[idx] + (1.f - b2) * grad * grad;
-      m[idx] = m1; v[idx] = v1;
-      p[idx] -= step_size * (m1 / (sqrtf(v1) / bc2_sqrt + eps));
+      float m1 = m[idx], v1 = v[idx];
+      const float p1 = update(m1, v1, p[idx], grad);
+      m[idx] = m1; v[idx] = v1; p[idx] = p1;
     }
   }
 };
 
 struct EpiWgradAdam {  // weight (+bias column) gradient fused with the optimiser update
   AdamCfg ad; long long off; int ld;
-  __device__ __forceinline__ void operator()(int m, int n, float v) { ad.apply(off + (long long)m * ld + n, v); }
+  template <int TN>
+  __device__ __forceinline__ void row(int m, int nb, int N, const float (&gr)[TN]) {
+    const long long base = off + (long long)m * ld + nb;
+    if (ad.flags & NMB_TRAIN_WRITE_GRADS) {
+#pragma unroll
+      for (int j = 0; j < TN; ++j)
+        if (nb + 16 * j < N) ad.g[base + 16 * j] = gr[j];
+    }
+    if (ad.flags & NMB_TRAIN_NO_ADAM) return;
+    float p0[TN], m1[TN], v1[TN];
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const bool ok = nb + 16 * j < N;
+      p0[j] = ok ? ad.p[base + 16 * j] : 0.f;
+      m1[j] = ok ? ad.m[base + 16 * j] : 0.f;
+      v1[j] = ok ? ad.v[base + 16 * j] : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      if (nb + 16 * j < N) {
+        const float p1 = ad.update(m1[j], v1[j], p0[j], gr[j]);
+        ad.m[base + 16 * j] = m1[j]; ad.v[base + 16 * j] = v1[j]; ad.p[base + 16 * j] = p1;
+      }
+    }
+  }
 };
 
 __device__ __forceinline__ AdamCfg make_adam(const StepCtx& c) {
@@ -327,11 +391,17 @@ __device__ void train_step(StepCtx& c, const float* eps_src, float* loss_out) {
     if (gauss) {
       for (int n = threadIdx.x; n < q.D; n += kThreads) {
         const float var = __expf(P[q.lam_off + n]);
+        const float* col = dxh + n;
         float acc = 0.f;
-        for (int b = 0; b < rows; ++b) {
-          const float t = dxh[(long long)b * q.ld_xh + n] * rows;
-          acc += 0.5f * (1.f - t * t * var);
+        int b = 0;
+        for (; b + 8 <= rows; b += 8) {
+          float t[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) t[u] = col[(long long)(b + u) * q.ld_xh];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) { const float w = t[u] * rows; acc += 0.5f * (1.f - w * w * var); }
         }
+        for (; b < rows; ++b) { const float w = col[(long long)b * q.ld_xh] * rows; acc += 0.5f * (1.f - w * w * var); }
         ad.apply(q.lam_off + n, acc * inv_rows);
       }
     }
