@@ -2,6 +2,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
+#include <numeric>
 #include <string>
 #include <vector>
 
@@ -66,6 +68,7 @@ struct NmbEnsemble {
   long long slot_floats = 0;
   int n_slots = 0;
   int* work_counter = nullptr;
+  int* order_dev = nullptr;
 };
 
 extern "C" {
@@ -166,11 +169,21 @@ int nmb_ensemble_create(NmbEnsemble** out, int32_t device, const NmbMember* memb
   e->n_slots = 2 * prop.multiProcessorCount;             // 2 resident CTAs per SM
   e->slot_floats = max_slot;
   auto cleanup = [&]() { nmb_ensemble_destroy(e); };
+  // dynamic dealing order: most expensive members first, so the tail of the launch is short
+  std::vector<int> order(n_members);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+    const long long ca = e->archs[e->arch_idx[a]].n_params * (long long)e->members_host[a].n_rows;
+    const long long cb = e->archs[e->arch_idx[b]].n_params * (long long)e->members_host[b].n_rows;
+    return ca > cb;
+  });
   cudaError_t ce;
   if ((ce = cudaMalloc(&e->members_dev, sizeof(MemberDev) * n_members)) != cudaSuccess ||
       (ce = cudaMalloc(&e->archs_dev, sizeof(ArchDesc) * e->archs.size())) != cudaSuccess ||
       (ce = cudaMalloc(&e->scratch, sizeof(float) * (size_t)e->slot_floats * e->n_slots)) != cudaSuccess ||
       (ce = cudaMalloc(&e->work_counter, sizeof(int))) != cudaSuccess ||
+      (ce = cudaMalloc(&e->order_dev, sizeof(int) * n_members)) != cudaSuccess ||
+      (ce = cudaMemcpy(e->order_dev, order.data(), sizeof(int) * n_members, cudaMemcpyHostToDevice)) != cudaSuccess ||
       (ce = cudaMemcpy(e->members_dev, e->members_host.data(), sizeof(MemberDev) * n_members, cudaMemcpyHostToDevice)) != cudaSuccess ||
       (ce = cudaMemcpy(e->archs_dev, e->archs.data(), sizeof(ArchDesc) * e->archs.size(), cudaMemcpyHostToDevice)) != cudaSuccess ||
       (ce = cudaMemset(e->scratch, 0, sizeof(float) * (size_t)e->slot_floats * e->n_slots)) != cudaSuccess) {
@@ -184,7 +197,7 @@ int nmb_ensemble_create(NmbEnsemble** out, int32_t device, const NmbMember* memb
 int nmb_ensemble_destroy(NmbEnsemble* e) {
   if (!e) return 0;
   cudaSetDevice(e->device);
-  cudaFree(e->members_dev); cudaFree(e->archs_dev); cudaFree(e->scratch); cudaFree(e->work_counter);
+  cudaFree(e->members_dev); cudaFree(e->archs_dev); cudaFree(e->scratch); cudaFree(e->work_counter); cudaFree(e->order_dev);
   delete e;
   return 0;
 }
@@ -217,7 +230,7 @@ int nmb_ensemble_train(NmbEnsemble* e, int64_t n_steps, const float* eps_overrid
   TrainLaunch t;
   t.members = e->members_dev; t.archs = e->archs_dev; t.n_members = e->n_members;
   t.n_steps = n_steps; t.eps_override = eps_override; t.loss_out = loss_out; t.flags = flags;
-  t.scratch = e->scratch; t.slot_floats = e->slot_floats; t.n_slots = e->n_slots; t.work_counter = e->work_counter;
+  t.scratch = e->scratch; t.slot_floats = e->slot_floats; t.n_slots = e->n_slots; t.work_counter = e->work_counter; t.order = e->order_dev;
   CU(launch_train(t, (cudaStream_t)stream));
   return 0;
 }

@@ -46,6 +46,7 @@ struct TrainLaunch {
   MemberDev* members; const ArchDesc* archs; int n_members;
   long long n_steps; const float* eps_override; float* loss_out; unsigned flags;
   float* scratch; long long slot_floats; int n_slots; int* work_counter;
+  const int* order;   // members sorted by decreasing cost (longest-processing-time-first dealing)
 };
 cudaError_t launch_train(const TrainLaunch& t, cudaStream_t st);
 

@@ -511,6 +511,8 @@ __global__ void __launch_bounds__(kThreads, 2) train_kernel(TrainLaunch t) {
       __syncthreads();
       mi = s_member;
       __syncthreads();
+      if (mi >= t.n_members) return;
+      mi = t.order[mi];
     }
     if (mi >= t.n_members) return;
     MemberDev& mb = t.members[mi];

@@ -1,0 +1,156 @@
+"""End-to-end GPU tests: k-fold training + deviation scoring against the CPU oracle on synthetic
+HCP-shaped data (|dAUC| <= 0.01, north_star), the multimodal_kfold_* CLI file contract, and the
+drop-in nn.Module per-step API against the reference's golden vectors."""
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def load(golden_dir, name):
+    return dict(np.load(os.path.join(golden_dir, name + ".npz"), allow_pickle=False))
+
+
+def sub(g, prefix):
+    return {k[len(prefix):]: v for k, v in g.items() if k.startswith(prefix)}
+
+
+def relerr(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
+
+
+def test_kfold_train_and_score_vs_oracle_auc():
+    """cfg1 shape (single modality, 5 folds): identical weights and identical eps draws in the oracle
+    (eager PyTorch restatement of the reference loop) and in the fused kernels; final per-subject
+    deviation AUC, per-ROI AUC and HC-referenced z-scores must agree (|dAUC| <= 0.01)."""
+    from oracle import cvae_torch, deviation as odev
+    from multi_modal_normative_modeling_b200 import EnsembleTrainer, MemberSpec, pack_rows, scoring, workloads
+    hw = workloads.build_host_workload(n_subjects=400, d=150, n_splits=5, early_fusion=False, hidden=(110, 110))
+    name, epochs, batch = "T1w_sMRI", 6, 256
+    dev = torch.device("cuda", 0)
+    rng = np.random.RandomState(0)
+    specs, oracle_out, eps_all, eps_test_all = [], [], [], []
+    for fd in hw.folds:
+        x, c = fd.train_x[name], fd.train_c
+        spe = -(-x.shape[0] // batch)
+        torch.manual_seed(42)
+        model = cvae_torch.OracleCVAEMultimodal([150], [110, 110], 10, 29, 1e-4, 1, True)
+        sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+        eps = rng.randn(epochs * spe, batch, 10).astype(np.float32)
+        eps_test = rng.randn(fd.test_x[name].shape[0], 10).astype(np.float32)
+        cvae_torch.reference_train_loop(model, [torch.from_numpy(x)], [torch.from_numpy(c).long()], "gPoE", epochs, batch,
+                                        eps_fn=lambda s, rows, e=eps: torch.from_numpy(e[s][:rows]))
+        xt, ct = torch.from_numpy(fd.test_x[name]), torch.from_numpy(fd.test_c).long()
+        pred = model.pred_recon([xt], ct, "gPoE", torch.from_numpy(eps_test))[0].numpy()
+        pred_tr = model.pred_recon([torch.from_numpy(x)], torch.from_numpy(c).long(), "gPoE",
+                                   torch.zeros(x.shape[0], 10))[0].numpy()
+        hc = fd.train_df["DIA"].to_numpy() == 1
+        mean, std = odev.normative_stats(odev.recon_deviation_roi(x, pred_tr)[hc])
+        roi = odev.recon_deviation_roi(fd.test_x64[name], pred)
+        labels = (fd.test_df["DIA"].to_numpy() != 1).astype(np.uint8)
+        oracle_out.append(dict(subj=odev.recon_deviation(fd.test_x64[name], pred), z=odev.zscores(roi, mean, std),
+                               labels=labels, hc=hc))
+        xc = [pack_rows(torch.from_numpy(x).to(dev), torch.from_numpy(c).to(dev))]
+        specs.append(MemberSpec([150], [110, 110], 10, 29, xc, batch=batch, state_dict=sd))
+        eps_all.append(eps); eps_test_all.append(eps_test)
+    tr = EnsembleTrainer(specs, device=dev)
+    tr.train_steps(eps_all[0].shape[0], eps=torch.from_numpy(np.stack(eps_all)).to(dev))
+    test_xc = [[pack_rows(torch.from_numpy(fd.test_x[name]).to(dev), torch.from_numpy(fd.test_c).to(dev))]
+               for fd in hw.folds]
+    xhat, _, _ = tr.reconstruct(test_xc, mode="sample", eps=[torch.from_numpy(e).to(dev) for e in eps_test_all])
+    xhat_tr, _, _ = tr.reconstruct([s.xc for s in specs], mode="mean")
+    stats = scoring.normative_stats([s.xc[0] for s in specs], [h[0] for h in xhat_tr],
+                                    [torch.from_numpy(o["hc"].astype(np.uint8)).to(dev) for o in oracle_out])
+    roi, z, subj = scoring.deviation([t[0] for t in test_xc], [h[0] for h in xhat], stats)
+    labels = [torch.from_numpy(o["labels"]).to(dev) for o in oracle_out]
+    subj_auc = scoring.auc(subj, labels)
+    roi_auc = scoring.auc(z, labels)
+    torch.cuda.synchronize()
+    for f, o in enumerate(oracle_out):
+        want = odev.auc(o["subj"], o["labels"])
+        assert abs(float(subj_auc[f][0]) - want) <= 0.01, (f, float(subj_auc[f][0]), want)
+        assert relerr(subj[f].cpu().numpy(), o["subj"]) < 1e-3
+        zz = z[f].cpu().numpy()
+        assert np.abs(zz - o["z"]).max() < 2e-2 * max(1.0, np.abs(o["z"]).max())       # z tolerance: 2 % of range
+        for col in range(0, 150, 13):
+            assert abs(float(roi_auc[f][col]) - odev.auc(o["z"][:, col], o["labels"])) <= 0.01
+    tr.close()
+
+
+def test_cli_file_contract(tmp_path):
+    """train -> test -> group analysis on a synthetic HCPimage dataset, reference file layout."""
+    import argparse
+    from multi_modal_normative_modeling_b200 import cli, synthetic
+    synthetic.write_dataset(str(tmp_path), "HCPimage", n=240, seed=3)
+    ns = dict(dataset_resourse="HCPimage", hz_para_list=[32, 24, 6], combine=None, procedure="SE-gPoE", n_splits=3,
+              epochs=3, oversample_percentage=1, model="cVAE_multimodal", single_modality=None,
+              base_learning_rate=1e-4, max_learning_rate=5e-3, training_class="nm", ensemble_seeds=2, nmmlp=False)
+    losses = cli.train_main(argparse.Namespace(**ns), root=tmp_path)
+    assert losses.shape == (6, 3, 3) and np.isfinite(losses).all()
+    kf = tmp_path / "outputs" / "kfold_analysis"
+    assert (kf / "train_ids_002.csv").exists() and (kf / "supervised_cvae" / "001" / "cVAE_model.pkl").exists()
+    cli.test_main(argparse.Namespace(**ns), root=tmp_path)
+    for name in ("T1w_sMRI", "T2w_sMRI", "fMRI"):
+        d = tmp_path / "deviation" / "supervised_cvae" / "HCPimage" / "SE-gPoE" / "path_model" / name
+        nrm = pd.read_csv(d / f"normalized_{name}.csv")
+        rec = pd.read_csv(d / f"reconstruction_{name}.csv")
+        roi = pd.read_csv(d / f"reconstruction_error_roi_{name}.csv")
+        err = pd.read_csv(d / f"reconstruction_error_{name}.csv")
+        fi = pd.read_csv(d / f"deviation_as_feature_importance_{name}.csv")
+        assert len(nrm) == 240 and list(nrm.columns[:4]) == ["participant_id", "DIA", "AGE", "PTGENDER"]
+        a, b, r = nrm.iloc[:, 4:].to_numpy(), rec.iloc[:, 4:].to_numpy(), roi.iloc[:, 4:].to_numpy()
+        # the stored-CSV identities of the reference's own artefacts
+        assert np.abs((a - b) ** 2 - r).max() < 1e-4 * max(1.0, np.abs(r).max())
+        assert np.abs(r.mean(1) - err["Reconstruction error"].to_numpy()).max() < 1e-4 * max(1.0, r.mean(1).max())
+        assert list(fi.columns[4:]) == [str(i) for i in range(1, 117)] and np.array_equal(fi.iloc[:, 4:].to_numpy(), r)
+    summary = cli.analysis_main(argparse.Namespace(**ns), root=tmp_path)
+    assert len(summary) == 1 and 0.0 <= summary[0][2][0] <= 1.0
+    aucs = np.loadtxt(tmp_path / "cvae_auc_and_std.csv", delimiter=",")
+    assert len(aucs) == 4 and abs(np.std(aucs[:-1]) - aucs[-1]) < 1e-15
+
+
+@pytest.mark.parametrize("name", ["mm_M1_small", "mm_M3_gpoe", "mm_M4_mopoe"])
+def test_module_per_step_api_vs_reference(golden_dir, name):
+    """The reference's own loop body on the drop-in module: forward_multimodal -> loss ->
+    zero_grad -> backward -> optimizer1.step(), with the reference's eps draws injected through
+    torch.randn (as the reference itself consumes them)."""
+    from multi_modal_normative_modeling_b200.cVAE import cVAE_multimodal
+    g = load(golden_dir, name)
+    dims = [int(d) for d in g["dims"]]
+    torch.manual_seed(int(g["seed"]))
+    model = cVAE_multimodal(dims, [int(h) for h in g["hidden"]], int(g["z"]), int(g["c_dim"]), learning_rate=1e-4,
+                            modalities=len(dims), non_linear=True)
+    for k, v in model.state_dict().items():                        # seed-exact initialisation
+        assert np.array_equal(v.numpy(), g["init/" + k]), k
+    model.to("cuda")
+    xs = [torch.from_numpy(g[f"x{i}"]).cuda() for i in range(len(dims))]
+    cs = [torch.from_numpy(g["c"]).long().cuda() for _ in dims]
+    real_randn = torch.randn
+    losses = []
+    for s in range(g["eps"].shape[0]):
+        torch.randn = lambda *a, **k: torch.from_numpy(g["eps"][s]).to(k.get("device", "cpu"))
+        try:
+            fwd = model.forward_multimodal(xs, cs, str(g["combine"]))
+        finally:
+            torch.randn = real_randn
+        loss = model.loss_function_multimodal(xs, fwd)
+        model.optimizer1.zero_grad()
+        loss["total"].backward()
+        if s == 0:
+            assert relerr(fwd["mu_multimodal"].cpu().numpy(), g["mu"]) < 1e-4
+            assert relerr(fwd["x_recons"][0].loc.cpu().numpy(), g["xrecon0"]) < 1e-4
+            for k, p in model.named_parameters():
+                if "grad/" + k in g:
+                    assert relerr(p.grad.cpu().numpy(), g["grad/" + k]) < 1e-4, k
+        model.optimizer1.step()
+        losses.append([float(loss["total"]), float(loss["kl"]), float(loss["ll"])])
+    assert np.allclose(np.array(losses), g["losses"], rtol=1e-4)
+    for k, v in model.state_dict().items():
+        assert relerr(v.cpu().numpy(), g["final/" + k]) < 1e-5, k
+    with pytest.raises(ValueError, match="No such combination method"):
+        model.forward_multimodal(xs, cs, "concat")
