@@ -117,7 +117,9 @@ int nmb_ensemble_steps_done(NmbEnsemble* ens, int64_t* steps /*host [n_members]*
 enum {
   NMB_TRAIN_NO_ADAM = 1,     /* forward + loss + backward only (parity of gradients) */
   NMB_TRAIN_WRITE_GRADS = 2, /* store d(total)/d(param) into NmbMember.grads */
-  NMB_TRAIN_KEEP_ACTS = 4    /* keep x_recon in scratch instead of overwriting it with its gradient */
+  NMB_TRAIN_KEEP_ACTS = 4,   /* keep x_recon in scratch instead of overwriting it with its gradient */
+  NMB_TRAIN_FP32 = 8         /* run every dense stage on the FP32 FFMA engine (bit-stable trajectories) instead of
+                                the default tcgen05 engine (error-compensated BF16x3 products, FP32 accumulate) */
 };
 /* The fused hot loop: for every member, n_steps minibatch steps of
  *   forward_multimodal -> loss_function_multimodal -> zero_grad -> backward -> optimizer1.step()
@@ -194,6 +196,13 @@ int nmb_mean_rows(const float* const* src /*host table*/, int32_t k, int64_t n, 
 /* In-kernel eps stream exposed for tests: out[i] = eps(seed, step, element i, stream id). */
 int nmb_philox_normal(uint64_t seed, uint64_t step, uint32_t stream_id, int64_t n, float* out,
                       void* stream);
+
+/* Test hook for the tensor-core GEMM engine of the fused kernels: one CTA computes
+ *   C[m][n] = sum_k A(m,k) * B(n,k),  A(i,k) = a[i*lda + k] (a_kmajor) or a[k*lda + i], same for B,
+ * with the BF16x3 split on tcgen05.  lda/ldb multiples of 4 floats, 16-byte aligned bases.
+ * Not part of the reference's interface. */
+int nmb_debug_tc_gemm(const float* a, int32_t lda, int32_t a_kmajor, const float* b, int32_t ldb,
+                      int32_t b_kmajor, float* c, int32_t ldc, int32_t m, int32_t n, int32_t k, void* stream);
 
 #ifdef __cplusplus
 }

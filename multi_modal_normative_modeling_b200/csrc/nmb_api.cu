@@ -415,5 +415,13 @@ int nmb_philox_normal(uint64_t seed, uint64_t step, uint32_t stream_id, int64_t 
   return 0;
 }
 
+int nmb_debug_tc_gemm(const float* a, int32_t lda, int32_t a_kmajor, const float* b, int32_t ldb, int32_t b_kmajor,
+                      float* c, int32_t ldc, int32_t m, int32_t n, int32_t k, void* stream) {
+  if (!a || !b || !c || m < 1 || n < 1 || k < 1 || (lda & 3) || (ldb & 3)) return fail("bad argument");
+  CU(configure_kernels());
+  CU(launch_debug_tc_gemm(a, lda, a_kmajor, b, ldb, b_kmajor, c, ldc, m, n, k, (cudaStream_t)stream));
+  return 0;
+}
+
 #pragma GCC visibility pop
 }  // extern "C"

@@ -49,6 +49,8 @@ struct TrainLaunch {
   const int* order;   // members sorted by decreasing cost (longest-processing-time-first dealing)
 };
 cudaError_t launch_train(const TrainLaunch& t, cudaStream_t st);
+cudaError_t launch_debug_tc_gemm(const float* A, int lda, int a_kmajor, const float* B, int ldb, int b_kmajor,
+                                 float* C, int ldc, int M, int N, int K, cudaStream_t st);
 
 struct ReconItem { int member; int row0; int rows; };
 struct ReconLaunch {

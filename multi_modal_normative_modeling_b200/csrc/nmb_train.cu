@@ -13,7 +13,7 @@
 //   optimizer1 = Adam(enc+dec+alpha), torch defaults        cVAE.py:1111-1116
 //   pred_recon (mean / sampled)  cVAE.py:549-555, 1198-1208
 // The formulas are those of oracle/cvae_numpy.py.
-#include "nmb_gemm.cuh"
+#include "nmb_tc_gemm.cuh"
 #include "nmb_internal.h"
 
 namespace nmb {
@@ -22,7 +22,8 @@ struct StepCtx {
   const ArchDesc* a;
   MemberDev* mb;
   float* scratch;
-  float* smem;      // GEMM tiles
+  float* smem;      // FP32 engine: GEMM tiles
+  tc::Ctx* tc;      // tensor-core engine context (null for the FP32 engine)
   float* red;       // reduction scratch (>= 16 floats)
   int rows, row0;
   long long step;   // global 0-based step index of this member
@@ -30,6 +31,33 @@ struct StepCtx {
   // Adam scalars of this step
   float step_size, bc2_sqrt, b1, b2, aeps;
 };
+
+
+// ---- 16-wide row segments (tensor-core engine epilogues) -------------------------------------
+// p is 16-byte aligned; only the first `nvalid` of the 16 floats exist / may be written.
+__device__ __forceinline__ void load16(const float* p, int nvalid, float fill, float (&o)[16]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    if (4 * q + 3 < nvalid) {
+      const float4 t = *reinterpret_cast<const float4*>(p + 4 * q);
+      o[4 * q] = t.x; o[4 * q + 1] = t.y; o[4 * q + 2] = t.z; o[4 * q + 3] = t.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[4 * q + j] = (4 * q + j < nvalid) ? p[4 * q + j] : fill;
+    }
+  }
+}
+__device__ __forceinline__ void store16(float* p, int nvalid, const float (&o)[16]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    if (4 * q + 3 < nvalid) {
+      *reinterpret_cast<float4*>(p + 4 * q) = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) if (4 * q + j < nvalid) p[4 * q + j] = o[4 * q + j];
+    }
+  }
+}
 
 // ---- epilogues ---------------------------------------------------------------------------
 // row<TN>(m, nb, N, v): v[j] is C[m][nb + 16*j].  Loads first, then math + stores (see gemm()).
@@ -42,6 +70,13 @@ struct EpiHidden {     // h = leaky_relu(a) (bias already inside a via the ones 
     for (int j = 0; j < TN; ++j)
       if (nb + 16 * j < N) d[16 * j] = (nl && v[j] <= 0.f) ? kSlope * v[j] : v[j];
   }
+  // tensor-core engine: v = C[m][n0 .. n0+16), first nvalid entries inside N
+  __device__ __forceinline__ void rowc(int m, int n0, int nvalid, const float (&v)[16]) {
+    float o[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) o[j] = (nl && v[j] <= 0.f) ? kSlope * v[j] : v[j];
+    store16(dst + (long long)m * ld + n0, nvalid, o);
+  }
 };
 
 struct EpiStore {
@@ -52,6 +87,12 @@ struct EpiStore {
 #pragma unroll
     for (int j = 0; j < TN; ++j)
       if (nb + 16 * j < N) d[16 * j] = v[j];
+  }
+  __device__ __forceinline__ void rowc(int m, int n0, int nvalid, const float (&v)[16]) {
+    float* d = dst + (long long)m * ld + n0;
+    if ((ld & 3) == 0) { store16(d, nvalid, v); return; }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) if (j < nvalid) d[j] = v[j];
   }
 };
 
@@ -91,6 +132,28 @@ struct EpiRecon {
       }
     }
   }
+  __device__ __forceinline__ void rowc(int m, int n0, int nvalid, const float (&v)[16]) {
+    float xt[16], l[16], g[16];
+    load16(x + (long long)m * ldx + n0, nvalid, 0.f, xt);
+    if (gauss) load16(lam + n0, nvalid, 0.f, l);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float r = xt[j] - v[j];
+      float t, gg;
+      if (gauss) {
+        const float iv = __expf(-l[j]);
+        t = -0.5f * r * r * iv - 0.5f * l[j] - 0.5f * kLog2Pi;
+        gg = -r * iv * inv_rows;
+      } else {
+        t = -r * r;
+        gg = -2.f * r * inv_rows_d;
+      }
+      if (j < nvalid) ll_acc += t;
+      g[j] = gg;
+    }
+    store16(dxh + (long long)m * ld + n0, nvalid, g);
+    if (keep) store16(keep + (long long)m * ld + n0, nvalid, v);
+  }
 };
 
 struct EpiDgrad {      // d_pre = d_act * leaky_relu'(pre), sign recovered from the stored activation
@@ -107,6 +170,13 @@ struct EpiDgrad {      // d_pre = d_act * leaky_relu'(pre), sign recovered from 
     for (int j = 0; j < TN; ++j)
       if (nb + 16 * j < N) d[16 * j] = h[j] <= 0.f ? kSlope * v[j] : v[j];
   }
+  __device__ __forceinline__ void rowc(int m, int n0, int nvalid, const float (&v)[16]) {
+    float h[16], o[16];
+    if (nl) load16(act + (long long)m * ld_act + n0, nvalid, 1.f, h);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) o[j] = (nl && h[j] <= 0.f) ? kSlope * v[j] : v[j];
+    store16(dst + (long long)m * ld + n0, nvalid, o);
+  }
 };
 
 struct EpiDz {
@@ -120,6 +190,12 @@ struct EpiDz {
 #pragma unroll
     for (int j = 0; j < TN; ++j)
       if (nb + 16 * j < N) p[16 * j] = old[j] + v[j];
+  }
+  __device__ __forceinline__ void rowc(int m, int n0, int nvalid, const float (&v)[16]) {
+    float* p = dz + m * Z + n0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (j < nvalid) p[j] = accumulate ? p[j] + v[j] : v[j];
   }
 };
 
@@ -169,6 +245,20 @@ struct EpiWgradAdam {  // weight (+bias column) gradient fused with the optimise
       }
     }
   }
+  __device__ __forceinline__ void rowc(int m, int n0, int nvalid, const float (&gr)[16]) {
+    const long long base = off + (long long)m * ld + n0;
+    if (ad.flags & NMB_TRAIN_WRITE_GRADS) store16(ad.g + base, nvalid, gr);
+    if (ad.flags & NMB_TRAIN_NO_ADAM) return;
+    float p0[16], m1[16], v1[16];
+    load16(ad.p + base, nvalid, 0.f, p0);
+    load16(ad.m + base, nvalid, 0.f, m1);
+    load16(ad.v + base, nvalid, 0.f, v1);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) p0[j] = ad.update(m1[j], v1[j], p0[j], gr[j]);
+    store16(ad.m + base, nvalid, m1);
+    store16(ad.v + base, nvalid, v1);
+    store16(ad.p + base, nvalid, p0);
+  }
 };
 
 __device__ __forceinline__ AdamCfg make_adam(const StepCtx& c) {
@@ -177,6 +267,13 @@ __device__ __forceinline__ AdamCfg make_adam(const StepCtx& c) {
   ad.step_size = c.step_size; ad.bc2_sqrt = c.bc2_sqrt; ad.b1 = c.b1; ad.b2 = c.b2; ad.eps = c.aeps;
   ad.flags = c.flags;
   return ad;
+}
+
+// Engine dispatch: FP32 FFMA tiles (gemm_auto) or tcgen05 BF16x3 (tc::gemm).
+template <bool TC, class Epi>
+__device__ __forceinline__ void mm(const StepCtx& c, int M, int N, int K, Opnd A, Opnd B, Epi& epi) {
+  if constexpr (TC) tc::gemm(M, N, K, A, B, epi, *c.tc);
+  else gemm_auto(M, N, K, A, B, epi, c.smem);
 }
 
 // ---- latent fusion (cVAE.py:1144-1164) -----------------------------------------------------
@@ -271,6 +368,7 @@ __device__ void prepare_slot(const StepCtx& c) {
 
 // ---- forward ---------------------------------------------------------------------------------
 // Encoders of all modalities on rows [row0, row0+rows) of xc -> heads in scratch (s_mulv).
+template <bool TC>
 __device__ void encoders_forward(const StepCtx& c, const float* const* xc) {
   const ArchDesc& a = *c.a;
   const float* P = c.mb->params;
@@ -280,11 +378,11 @@ __device__ void encoders_forward(const StepCtx& c, const float* const* xc) {
     for (int l = 0; l < a.L; ++l) {
       const LinDesc& w = q.enc[l];
       EpiHidden e{c.scratch + q.s_h[l], q.ld_h[l], a.non_linear};
-      gemm_auto(c.rows, w.out, w.in + 1, A, Opnd{P + w.off, w.ld, 1}, e, c.smem);
+      mm<TC>(c, c.rows, w.out, w.in + 1, A, Opnd{P + w.off, w.ld, 1}, e);
       A = Opnd{c.scratch + q.s_h[l], q.ld_h[l], 1};
     }
     EpiStore e{c.scratch + q.s_mulv, q.ld_mulv};
-    gemm_auto(c.rows, q.head.out, q.head.in + 1, A, Opnd{P + q.head.off, q.head.ld, 1}, e, c.smem);
+    mm<TC>(c, c.rows, q.head.out, q.head.in + 1, A, Opnd{P + q.head.off, q.head.ld, 1}, e);
   }
 }
 
@@ -335,6 +433,7 @@ __device__ float latent_forward(const StepCtx& c, const float* const* xc, int ep
 }
 
 // Decoder hidden layers of modality m; returns the operand feeding decoder_mean_layer.
+template <bool TC>
 __device__ Opnd decoder_hidden(const StepCtx& c, int m) {
   const ArchDesc& a = *c.a;
   const ModDesc& q = a.mod[m];
@@ -343,13 +442,14 @@ __device__ Opnd decoder_hidden(const StepCtx& c, int m) {
   for (int l = 0; l < a.L; ++l) {
     const LinDesc& w = q.dec[l];
     EpiHidden e{c.scratch + q.s_k[l], q.ld_k[l], a.non_linear};
-    gemm_auto(c.rows, w.out, w.in + 1, A, Opnd{P + w.off, w.ld, 1}, e, c.smem);
+    mm<TC>(c, c.rows, w.out, w.in + 1, A, Opnd{P + w.off, w.ld, 1}, e);
     A = Opnd{c.scratch + q.s_k[l], q.ld_k[l], 1};
   }
   return A;
 }
 
 // ---- one training step ---------------------------------------------------------------------
+template <bool TC>
 __device__ void train_step(StepCtx& c, const float* eps_src, float* loss_out) {
   const ArchDesc& a = *c.a;
   MemberDev& mb = *c.mb;
@@ -360,20 +460,20 @@ __device__ void train_step(StepCtx& c, const float* eps_src, float* loss_out) {
   const int gauss = a.loss_kind == NMB_LOSS_GAUSS_LL;
 
   // ---------------- forward ----------------
-  encoders_forward(c, mb.xc);
+  encoders_forward<TC>(c, mb.xc);
   float kl = latent_forward(c, mb.xc, eps_src ? 1 : 0, eps_src, 0u, (unsigned long long)c.step);
   kl = block_sum(kl, c.red) * inv_rows;
   float ll_sum = 0.f;
   for (int m = 0; m < M; ++m) {
     const ModDesc& q = a.mod[m];
-    Opnd A = decoder_hidden(c, m);
+    Opnd A = decoder_hidden<TC>(c, m);
     EpiRecon e;
     e.x = mb.xc[m] + (long long)c.row0 * q.ldx; e.ldx = q.ldx;
     e.lam = P + q.lam_off;
     e.dxh = S + q.s_xh; e.ld = q.ld_xh;
     e.keep = (c.flags & NMB_TRAIN_KEEP_ACTS) ? S + q.s_xr : nullptr;
     e.inv_rows = inv_rows; e.inv_rows_d = inv_rows / q.D; e.gauss = gauss; e.ll_acc = 0.f;
-    gemm_auto(rows, q.D, q.outl.in + 1, A, Opnd{P + q.outl.off, q.outl.ld, 1}, e, c.smem);
+    mm<TC>(c, rows, q.D, q.outl.in + 1, A, Opnd{P + q.outl.off, q.outl.ld, 1}, e);
     const float s = block_sum(e.ll_acc, c.red);
     ll_sum += gauss ? s * inv_rows : s * inv_rows / q.D;
   }
@@ -411,9 +511,9 @@ __device__ void train_step(StepCtx& c, const float* eps_src, float* loss_out) {
       const LinDesc& w = q.outl;
       const float* act = S + q.s_k[L - 1]; const int ld_act = q.ld_k[L - 1];
       EpiDgrad eg{gbuf[cur], a.ld_g, act, ld_act, a.non_linear};
-      gemm_auto(rows, w.in, w.out, Opnd{dxh, q.ld_xh, 1}, Opnd{P + w.off, w.ld, 0}, eg, c.smem);
+      mm<TC>(c, rows, w.in, w.out, Opnd{dxh, q.ld_xh, 1}, Opnd{P + w.off, w.ld, 0}, eg);
       EpiWgradAdam ew{ad, w.off, w.ld};
-      gemm_auto(w.out, w.in + 1, rows, Opnd{dxh, q.ld_xh, 0}, Opnd{act, ld_act, 0}, ew, c.smem);
+      mm<TC>(c, w.out, w.in + 1, rows, Opnd{dxh, q.ld_xh, 0}, Opnd{act, ld_act, 0}, ew);
     }
     for (int l = L - 1; l >= 0; --l) {
       const LinDesc& w = q.dec[l];
@@ -422,13 +522,13 @@ __device__ void train_step(StepCtx& c, const float* eps_src, float* loss_out) {
       const int ld_in = l == 0 ? q.ld_g0 : q.ld_k[l - 1];
       if (l > 0) {
         EpiDgrad eg{gbuf[cur ^ 1], a.ld_g, in_act, ld_in, a.non_linear};
-        gemm_auto(rows, w.in, w.out, Opnd{dy, a.ld_g, 1}, Opnd{P + w.off, w.ld, 0}, eg, c.smem);
+        mm<TC>(c, rows, w.in, w.out, Opnd{dy, a.ld_g, 1}, Opnd{P + w.off, w.ld, 0}, eg);
       } else {
         EpiDz ez{S + a.s_dz, Z, m > 0};
-        gemm_auto(rows, Z, w.out, Opnd{dy, a.ld_g, 1}, Opnd{P + w.off, w.ld, 0}, ez, c.smem);
+        mm<TC>(c, rows, Z, w.out, Opnd{dy, a.ld_g, 1}, Opnd{P + w.off, w.ld, 0}, ez);
       }
       EpiWgradAdam ew{ad, w.off, w.ld};
-      gemm_auto(w.out, w.in + 1, rows, Opnd{dy, a.ld_g, 0}, Opnd{in_act, ld_in, 0}, ew, c.smem);
+      mm<TC>(c, w.out, w.in + 1, rows, Opnd{dy, a.ld_g, 0}, Opnd{in_act, ld_in, 0}, ew);
       cur ^= 1;
     }
   }
@@ -477,9 +577,9 @@ __device__ void train_step(StepCtx& c, const float* eps_src, float* loss_out) {
       const LinDesc& w = q.head;
       const float* act = S + q.s_h[L - 1]; const int ld_act = q.ld_h[L - 1];
       EpiDgrad eg{gbuf[cur], a.ld_g, act, ld_act, a.non_linear};
-      gemm_auto(rows, w.in, w.out, Opnd{dmulv, q.ld_mulv, 1}, Opnd{P + w.off, w.ld, 0}, eg, c.smem);
+      mm<TC>(c, rows, w.in, w.out, Opnd{dmulv, q.ld_mulv, 1}, Opnd{P + w.off, w.ld, 0}, eg);
       EpiWgradAdam ew{ad, w.off, w.ld};
-      gemm_auto(w.out, w.in + 1, rows, Opnd{dmulv, q.ld_mulv, 0}, Opnd{act, ld_act, 0}, ew, c.smem);
+      mm<TC>(c, w.out, w.in + 1, rows, Opnd{dmulv, q.ld_mulv, 0}, Opnd{act, ld_act, 0}, ew);
     }
     for (int l = L - 1; l >= 0; --l) {
       const LinDesc& w = q.enc[l];
@@ -488,28 +588,27 @@ __device__ void train_step(StepCtx& c, const float* eps_src, float* loss_out) {
       const int ld_in = l == 0 ? q.ldx : q.ld_h[l - 1];
       if (l > 0) {
         EpiDgrad eg{gbuf[cur ^ 1], a.ld_g, in_act, ld_in, a.non_linear};
-        gemm_auto(rows, w.in, w.out, Opnd{dy, a.ld_g, 1}, Opnd{P + w.off, w.ld, 0}, eg, c.smem);
+        mm<TC>(c, rows, w.in, w.out, Opnd{dy, a.ld_g, 1}, Opnd{P + w.off, w.ld, 0}, eg);
       }
       EpiWgradAdam ew{ad, w.off, w.ld};
-      gemm_auto(w.out, w.in + 1, rows, Opnd{dy, a.ld_g, 0}, Opnd{in_act, ld_in, 0}, ew, c.smem);
+      mm<TC>(c, w.out, w.in + 1, rows, Opnd{dy, a.ld_g, 0}, Opnd{in_act, ld_in, 0}, ew);
       cur ^= 1;
     }
   }
 }
 
 // ---- kernels -------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 2) train_kernel(TrainLaunch t) {
-  extern __shared__ __align__(16) float smem[];
-  __shared__ float red[16];
-  __shared__ int s_member;
+// One CTA = one ensemble member at a time; TC selects the GEMM engine of every dense stage.
+template <bool TC>
+__device__ __forceinline__ void train_body(const TrainLaunch& t, float* smem_f, tc::Ctx* tcx, float* red, int* s_member) {
   for (;;) {
     int mi;
     if ((int)gridDim.x >= t.n_members) {
       mi = blockIdx.x;
     } else {
-      if (threadIdx.x == 0) s_member = atomicAdd(t.work_counter, 1);
+      if (threadIdx.x == 0) *s_member = atomicAdd(t.work_counter, 1);
       __syncthreads();
-      mi = s_member;
+      mi = *s_member;
       __syncthreads();
       if (mi >= t.n_members) return;
       mi = t.order[mi];
@@ -518,7 +617,7 @@ __global__ void __launch_bounds__(kThreads, 2) train_kernel(TrainLaunch t) {
     MemberDev& mb = t.members[mi];
     const ArchDesc& a = t.archs[mb.arch_idx];
     StepCtx c;
-    c.a = &a; c.mb = &mb; c.smem = smem; c.red = red; c.flags = t.flags;
+    c.a = &a; c.mb = &mb; c.smem = smem_f; c.tc = tcx; c.red = red; c.flags = t.flags;
     c.scratch = t.scratch + (long long)blockIdx.x * t.slot_floats;
     c.b1 = mb.beta1; c.b2 = mb.beta2; c.aeps = mb.adam_eps;
     prepare_slot(c);
@@ -538,7 +637,7 @@ __global__ void __launch_bounds__(kThreads, 2) train_kernel(TrainLaunch t) {
       const float* eps = t.eps_override
           ? t.eps_override + ((long long)mi * t.n_steps + i) * mb.batch * a.Z : nullptr;
       float* lo = t.loss_out ? t.loss_out + ((long long)mi * t.n_steps + i) * 3 : nullptr;
-      train_step(c, eps, lo);
+      train_step<TC>(c, eps, lo);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -550,6 +649,53 @@ __global__ void __launch_bounds__(kThreads, 2) train_kernel(TrainLaunch t) {
   }
 }
 
+// FP32 FFMA engine: bit-stable trajectories (NMB_TRAIN_FP32).
+__global__ void __launch_bounds__(kThreads, 2) train_kernel(TrainLaunch t) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ float red[16];
+  __shared__ int s_member;
+  train_body<false>(t, smem, nullptr, red, &s_member);
+}
+
+// tcgen05 engine (default): BF16x3 split products, FP32 accumulation in TMEM.
+__global__ void __launch_bounds__(kThreads, 2) train_tc_kernel(TrainLaunch t) {
+  extern __shared__ __align__(128) unsigned char smem_tc[];
+  __shared__ float red[16];
+  __shared__ int s_member;
+  __shared__ uint32_t s_tmem;
+  __shared__ __align__(8) uint64_t s_mbar;
+  if (threadIdx.x < 32) tc::tmem_alloc(&s_tmem, tc::kTmemCols);
+  if (threadIdx.x == 0) tc::mbar_init(&s_mbar, 1);
+  tc::fence_before();
+  __syncthreads();
+  tc::fence_after();
+  tc::Ctx tcx;
+  tcx.smem = smem_tc; tcx.mbar = &s_mbar; tcx.tmem_base = s_tmem; tcx.phase = 0;
+  train_body<true>(t, nullptr, &tcx, red, &s_member);
+  tc::fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) tc::tmem_free(tcx.tmem_base, tc::kTmemCols);
+}
+
+// Test hook: one CTA computes C[m][n] = sum_k A(m,k) B(n,k) with the tensor-core engine.
+__global__ void __launch_bounds__(kThreads, 2) debug_tc_gemm_kernel(Opnd A, Opnd B, float* C, int ldc, int M, int N, int K) {
+  extern __shared__ __align__(128) unsigned char smem_tc[];
+  __shared__ uint32_t s_tmem;
+  __shared__ __align__(8) uint64_t s_mbar;
+  if (threadIdx.x < 32) tc::tmem_alloc(&s_tmem, tc::kTmemCols);
+  if (threadIdx.x == 0) tc::mbar_init(&s_mbar, 1);
+  tc::fence_before();
+  __syncthreads();
+  tc::fence_after();
+  tc::Ctx tcx;
+  tcx.smem = smem_tc; tcx.mbar = &s_mbar; tcx.tmem_base = s_tmem; tcx.phase = 0;
+  EpiStore e{C, ldc};
+  tc::gemm(M, N, K, A, B, e, tcx);
+  tc::fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) tc::tmem_free(tcx.tmem_base, tc::kTmemCols);
+}
+
 // Test-time reconstruction.  Work item = (member, tile of up to 256 rows).
 __global__ void __launch_bounds__(kThreads, 2) recon_kernel(ReconLaunch t) {
   extern __shared__ __align__(16) float smem[];
@@ -559,12 +705,12 @@ __global__ void __launch_bounds__(kThreads, 2) recon_kernel(ReconLaunch t) {
     MemberDev& mb = t.members[item.member];
     const ArchDesc& a = t.archs[mb.arch_idx];
     StepCtx c;
-    c.a = &a; c.mb = &mb; c.smem = smem; c.red = red; c.flags = 0;
+    c.a = &a; c.mb = &mb; c.smem = smem; c.tc = nullptr; c.red = red; c.flags = 0;
     c.scratch = t.scratch + (long long)blockIdx.x * t.slot_floats;
     c.rows = item.rows; c.row0 = item.row0; c.step = 0;
     const float* const* xc = t.xc + (long long)item.member * NMB_MAX_MOD;
     prepare_slot(c);
-    encoders_forward(c, xc);
+    encoders_forward<false>(c, xc);
     const float* eps = (t.mode == NMB_RECON_SAMPLE && t.eps && t.eps[item.member])
         ? t.eps[item.member] + (long long)item.row0 * a.Z : nullptr;
     const int eps_mode = t.mode == NMB_RECON_MEAN ? 2 : (eps ? 1 : 0);
@@ -580,11 +726,11 @@ __global__ void __launch_bounds__(kThreads, 2) recon_kernel(ReconLaunch t) {
     }
     for (int m = 0; m < a.M; ++m) {
       const ModDesc& q = a.mod[m];
-      Opnd A = decoder_hidden(c, m);
+      Opnd A = decoder_hidden<false>(c, m);
       float* out = t.xhat[(long long)item.member * NMB_MAX_MOD + m];
       if (!out) continue;
       EpiStore e{out + (long long)item.row0 * q.D, q.D};
-      gemm_auto(item.rows, q.D, q.outl.in + 1, A, Opnd{mb.params + q.outl.off, q.outl.ld, 1}, e, c.smem);
+      mm<false>(c, item.rows, q.D, q.outl.in + 1, A, Opnd{mb.params + q.outl.off, q.outl.ld, 1}, e);
     }
     __syncthreads();
   }
@@ -594,6 +740,10 @@ constexpr size_t kGemmSmemBytes = kGemmSmemFloats * sizeof(float);
 
 cudaError_t configure_kernels() {
   cudaError_t e = cudaFuncSetAttribute(train_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(train_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(debug_tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
   if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(recon_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes);
 }
@@ -605,7 +755,14 @@ cudaError_t launch_train(const TrainLaunch& t, cudaStream_t st) {
     cudaError_t e = cudaMemsetAsync(t.work_counter, 0, sizeof(int), st);
     if (e != cudaSuccess) return e;
   }
-  train_kernel<<<grid, kThreads, kGemmSmemBytes, st>>>(t);
+  if (t.flags & NMB_TRAIN_FP32) train_kernel<<<grid, kThreads, kGemmSmemBytes, st>>>(t);
+  else train_tc_kernel<<<grid, kThreads, tc::kSmemBytes, st>>>(t);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_debug_tc_gemm(const float* A, int lda, int a_kmajor, const float* B, int ldb, int b_kmajor,
+                                 float* C, int ldc, int M, int N, int K, cudaStream_t st) {
+  debug_tc_gemm_kernel<<<1, kThreads, tc::kSmemBytes, st>>>(Opnd{A, lda, a_kmajor}, Opnd{B, ldb, b_kmajor}, C, ldc, M, N, K);
   return cudaGetLastError();
 }
 
