@@ -111,6 +111,9 @@ int nmb_ensemble_create(NmbEnsemble** out, int32_t device, const NmbMember* memb
                         int32_t n_members);
 int nmb_ensemble_destroy(NmbEnsemble* ens);
 int nmb_ensemble_size(const NmbEnsemble* ens, int32_t* n_members);
+/* Which engine nmb_ensemble_train runs for these flags: 2 = pipelined tcgen05 kernel, 1 = generic tcgen05
+ * engine, 0 = FP32 FFMA engine.  (Introspection for tests / benchmarks.) */
+int nmb_ensemble_engine(const NmbEnsemble* ens, uint32_t flags, int32_t* engine);
 /* steps already taken by each member (global_step of the train script :178), host out */
 int nmb_ensemble_steps_done(NmbEnsemble* ens, int64_t* steps /*host [n_members]*/, void* stream);
 
@@ -118,8 +121,10 @@ enum {
   NMB_TRAIN_NO_ADAM = 1,     /* forward + loss + backward only (parity of gradients) */
   NMB_TRAIN_WRITE_GRADS = 2, /* store d(total)/d(param) into NmbMember.grads */
   NMB_TRAIN_KEEP_ACTS = 4,   /* keep x_recon in scratch instead of overwriting it with its gradient */
-  NMB_TRAIN_FP32 = 8         /* run every dense stage on the FP32 FFMA engine (bit-stable trajectories) instead of
+  NMB_TRAIN_FP32 = 8,        /* run every dense stage on the FP32 FFMA engine (bit-stable trajectories) instead of
                                 the default tcgen05 engine (error-compensated BF16x3 products, FP32 accumulate) */
+  NMB_TRAIN_TC_SIMPLE = 16   /* tcgen05 engine without the operand pipeline (the generic engine that also serves
+                                architectures the pipelined kernel does not cover, e.g. hidden width > 127) */
 };
 /* The fused hot loop: for every member, n_steps minibatch steps of
  *   forward_multimodal -> loss_function_multimodal -> zero_grad -> backward -> optimizer1.step()

@@ -69,7 +69,104 @@ struct NmbEnsemble {
   int n_slots = 0;
   int* work_counter = nullptr;
   int* order_dev = nullptr;
+  // pipelined tensor-core path (nmb_tcp.h); built when every architecture is eligible
+  bool tcp_ok = false;
+  int n_sm = 0;
+  std::vector<void*> tcp_allocs;
+  tcp::ProgramDev* progs_dev = nullptr;
+  tcp::MemberTc* mtc_dev = nullptr;
+  tcp::XPrepItem* xprep_dev = nullptr;
+  int n_xprep = 0, xprep_max_blocks = 0;
+  unsigned char* stash = nullptr;
+  long long stash_bytes = 0;
 };
+
+namespace {
+// Programs, weight planes, dataset planes and the backward stash of the pipelined path.
+int setup_tcp(NmbEnsemble* e) {
+  std::vector<tcp::Program> progs;
+  for (const ArchDesc& d : e->archs) {
+    progs.push_back(tcp::build_program(d));
+    if (!progs.back().eligible) return 0;            // e.g. hidden width > 127: generic engine is used
+  }
+  auto dev_alloc = [&](size_t bytes, void** out) {
+    cudaError_t ce = cudaMalloc(out, bytes ? bytes : 16);
+    if (ce == cudaSuccess) { e->tcp_allocs.push_back(*out); ce = cudaMemset(*out, 0, bytes ? bytes : 16); }
+    return ce;
+  };
+  auto upload = [&](const void* src, size_t bytes, void** out) {
+    cudaError_t ce = dev_alloc(bytes, out);
+    if (ce == cudaSuccess && bytes) ce = cudaMemcpy(*out, src, bytes, cudaMemcpyHostToDevice);
+    return ce;
+  };
+  std::vector<tcp::ProgramDev> pd(progs.size());
+  long long max_stash = 0;
+  for (size_t i = 0; i < progs.size(); ++i) {
+    tcp::Program& P = progs[i];
+    void *ds, *de, *dw;
+    CU(upload(P.steps.data(), sizeof(tcp::Step) * P.steps.size(), &ds));
+    CU(upload(P.epis.data(), sizeof(tcp::Epi) * P.epis.size(), &de));
+    CU(upload(P.wblocks.data(), sizeof(tcp::WBlock) * P.wblocks.size(), &dw));
+    pd[i].steps = (const tcp::Step*)ds; pd[i].epis = (const tcp::Epi*)de; pd[i].wblocks = (const tcp::WBlock*)dw;
+    pd[i].n_steps = (int)P.steps.size(); pd[i].n_epis = (int)P.epis.size(); pd[i].n_wblocks = (int)P.wblocks.size();
+    pd[i].lay = P.lay;
+    if (P.lay.stash_bytes > max_stash) max_stash = P.lay.stash_bytes;
+  }
+  void* p = nullptr;
+  CU(upload(pd.data(), sizeof(tcp::ProgramDev) * pd.size(), &p));
+  e->progs_dev = (tcp::ProgramDev*)p;
+  e->stash_bytes = (max_stash + 1023) & ~1023LL;
+  CU(dev_alloc((size_t)e->stash_bytes * e->n_sm, &p));
+  e->stash = (unsigned char*)p;
+  // weight planes: one slice per member
+  long long wtotal = 0;
+  std::vector<long long> woff(e->n_members);
+  for (int i = 0; i < e->n_members; ++i) { woff[i] = wtotal; wtotal += progs[e->arch_idx[i]].lay.wplanes_bytes; }
+  void* wbuf = nullptr;
+  CU(dev_alloc((size_t)wtotal, &wbuf));
+  // dataset planes: one buffer per distinct (rows pointer, n_rows, batch, width)
+  struct Key { const float* xc; int n_rows, batch, ldx, k_valid; };
+  std::vector<Key> keys; std::vector<unsigned char*> bufs; std::vector<tcp::XPrepItem> items;
+  std::vector<tcp::MemberTc> mtc(e->n_members);
+  for (int i = 0; i < e->n_members; ++i) {
+    const MemberDev& md = e->members_host[i];
+    const ArchDesc& d = e->archs[e->arch_idx[i]];
+    tcp::MemberTc& mt = mtc[i];
+    std::memset(&mt, 0, sizeof(mt));
+    mt.wplanes = (unsigned char*)wbuf + woff[i];
+    mt.n_half = (md.batch + 127) / 128;
+    for (int m = 0; m < d.M; ++m) {
+      const ModDesc& q = d.mod[m];
+      Key k{md.xc[m], md.n_rows, md.batch, q.ldx, q.D + d.C + 1};
+      int found = -1;
+      for (size_t j = 0; j < keys.size(); ++j)
+        if (keys[j].xc == k.xc && keys[j].n_rows == k.n_rows && keys[j].batch == k.batch && keys[j].ldx == k.ldx &&
+            keys[j].k_valid == k.k_valid) { found = (int)j; break; }
+      if (found < 0) {
+        const int cg = tcp::round16(k.k_valid) / 8;
+        const int spe = (k.n_rows + k.batch - 1) / k.batch;
+        const long long blocks = (long long)(spe > 0 ? spe : 1) * mt.n_half;
+        void* xb = nullptr;
+        CU(dev_alloc((size_t)(blocks * cg * 4096), &xb));
+        keys.push_back(k); bufs.push_back((unsigned char*)xb);
+        tcp::XPrepItem it{k.xc, (unsigned char*)xb, k.n_rows, k.batch, k.ldx, k.k_valid, cg, mt.n_half};
+        items.push_back(it);
+        if ((int)blocks > e->xprep_max_blocks) e->xprep_max_blocks = (int)blocks;
+        found = (int)keys.size() - 1;
+      }
+      mt.xplanes[m] = bufs[found];
+    }
+  }
+  CU(upload(mtc.data(), sizeof(tcp::MemberTc) * mtc.size(), &p));
+  e->mtc_dev = (tcp::MemberTc*)p;
+  CU(upload(items.data(), sizeof(tcp::XPrepItem) * items.size(), &p));
+  e->xprep_dev = (tcp::XPrepItem*)p;
+  e->n_xprep = (int)items.size();
+  CU(configure_tcp());
+  e->tcp_ok = true;
+  return 0;
+}
+}  // namespace
 
 extern "C" {
 #pragma GCC visibility push(default)
@@ -167,6 +264,7 @@ int nmb_ensemble_create(NmbEnsemble** out, int32_t device, const NmbMember* memb
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, device));
   e->n_slots = 2 * prop.multiProcessorCount;             // 2 resident CTAs per SM
+  e->n_sm = prop.multiProcessorCount;
   e->slot_floats = max_slot;
   auto cleanup = [&]() { nmb_ensemble_destroy(e); };
   // dynamic dealing order: most expensive members first, so the tail of the launch is short
@@ -190,6 +288,7 @@ int nmb_ensemble_create(NmbEnsemble** out, int32_t device, const NmbMember* memb
     cleanup();
     return cuda_fail("nmb_ensemble_create", ce);
   }
+  if (int rc = setup_tcp(e)) { cleanup(); return rc; }
   *out = e;
   return 0;
 }
@@ -198,6 +297,7 @@ int nmb_ensemble_destroy(NmbEnsemble* e) {
   if (!e) return 0;
   cudaSetDevice(e->device);
   cudaFree(e->members_dev); cudaFree(e->archs_dev); cudaFree(e->scratch); cudaFree(e->work_counter); cudaFree(e->order_dev);
+  for (void* p : e->tcp_allocs) cudaFree(p);
   delete e;
   return 0;
 }
@@ -205,6 +305,12 @@ int nmb_ensemble_destroy(NmbEnsemble* e) {
 int nmb_ensemble_size(const NmbEnsemble* e, int32_t* n) {
   if (!e || !n) return fail("null argument");
   *n = e->n_members;
+  return 0;
+}
+
+int nmb_ensemble_engine(const NmbEnsemble* e, uint32_t flags, int32_t* engine) {
+  if (!e || !engine) return fail("null argument");
+  *engine = (flags & NMB_TRAIN_FP32) ? 0 : ((e->tcp_ok && !(flags & NMB_TRAIN_TC_SIMPLE)) ? 2 : 1);
   return 0;
 }
 
@@ -231,7 +337,13 @@ int nmb_ensemble_train(NmbEnsemble* e, int64_t n_steps, const float* eps_overrid
   t.members = e->members_dev; t.archs = e->archs_dev; t.n_members = e->n_members;
   t.n_steps = n_steps; t.eps_override = eps_override; t.loss_out = loss_out; t.flags = flags;
   t.scratch = e->scratch; t.slot_floats = e->slot_floats; t.n_slots = e->n_slots; t.work_counter = e->work_counter; t.order = e->order_dev;
-  CU(launch_train(t, (cudaStream_t)stream));
+  if (e->tcp_ok && !(flags & (NMB_TRAIN_FP32 | NMB_TRAIN_TC_SIMPLE))) {
+    // dataset rows may have been re-packed since the last call: refresh their planes (cheap, streaming)
+    CU(launch_xprep(e->xprep_dev, e->n_xprep, e->xprep_max_blocks, (cudaStream_t)stream));
+    CU(launch_train_tcp(t, e->progs_dev, e->mtc_dev, e->stash, e->stash_bytes, e->n_sm, (cudaStream_t)stream));
+  } else {
+    CU(launch_train(t, (cudaStream_t)stream));
+  }
   return 0;
 }
 

@@ -1,6 +1,7 @@
 // Internal (non-ABI) declarations shared by the translation units of libnmb.
 #pragma once
 #include "nmb_common.cuh"
+#include "nmb_tcp.h"
 
 namespace nmb {
 
@@ -61,5 +62,11 @@ struct ReconLaunch {
 };
 cudaError_t launch_recon(const ReconLaunch& t, cudaStream_t st);
 cudaError_t configure_kernels();
+
+// nmb_train_tcp.cu: pipelined tensor-core path
+cudaError_t configure_tcp();
+cudaError_t launch_xprep(const void* items_dev, int n_items, int max_blocks, cudaStream_t st);
+cudaError_t launch_train_tcp(const TrainLaunch& t, const tcp::ProgramDev* progs, const tcp::MemberTc* mtc,
+                             unsigned char* stash, long long stash_bytes, int n_sm, cudaStream_t st);
 
 }  // namespace nmb

@@ -1,0 +1,530 @@
+// Pipelined tensor-core training path ("TCP"): host-built step program + device structures.
+//
+// The fused cVAE step (forward, loss, backward, Adam; cVAE.py:1166-1196 + torch Adam) is a chain of
+// small dense contractions.  On B200 the chain is bound by bytes moved between L2 and the SM, so
+// this path keeps every matrix in ONE storage format that the tensor core consumes directly --
+// BF16 hi/lo planes tiled in the UMMA no-swizzle 8x8 core matrices -- and lets three roles of one
+// persistent CTA walk a host-built program:
+//   * producer (1 thread): cp.async.bulk (TMA) copies of operand tiles into a 3-slot ring,
+//   * MMA      (1 thread): tcgen05.mma, 3 passes (hi*hi, lo*hi, hi*lo) per K=16 step into TMEM,
+//   * epilogue (8 warps) : tcgen05.ld -> activation / loss / leaky-relu' / Adam -> planes written to
+//                          shared memory (next operand, no staging pass) and to the backward stash.
+// The minibatch is processed as two independent 128-row halves so that the epilogue of one half
+// overlaps the MMAs of the other.
+//
+// Canonical block (R rows, cg column groups of 8):   byte(r, c, plane) =
+//        (c >> 3) * 32R  +  plane * 16R  +  r * 16  +  (c & 7) * 2
+// The same bytes serve as a K-major operand (MN index = r, K index = c: SBO = 128, LBO = 32R) and as
+// an MN-major operand (MN index = c, K index = r: SBO = 32R, LBO = 128), so activations, output
+// gradients and weights are each stored once and used by forward, dgrad and wgrad.
+#pragma once
+#include <map>
+#include <vector>
+
+#include "nmb_common.cuh"
+
+namespace nmb {
+namespace tcp {
+
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kThreadsP = kEpiThreads + 64;        // + MMA warp + producer warp
+constexpr int kActBytes = 65536;                   // one 128-row operand block, up to 128 columns (hi + lo)
+constexpr int kSlotBytes = 32768;                  // one ring tile
+constexpr int kSlots = 3;
+constexpr int kSmemRing = 2 * kActBytes;
+constexpr int kSmemCtrl = kSmemRing + kSlots * kSlotBytes;
+constexpr int kSmemBytes = kSmemCtrl + 1024;       // 230 400 B <= 227 KB
+constexpr int kAcc0 = 0, kWacc0 = 256;             // TMEM columns: acc[h] = 128 h, wacc[b] = 256 + 128 b
+
+enum Space : int { SP_NONE = 0, SP_W = 1, SP_STASH = 2, SP_X = 3 };
+
+enum EpiKind : int {
+  EK_HIDDEN = 0,      // leaky-relu, planes -> ACT[h] + stash
+  EK_HEAD,            // [mu | logvar] fp32 -> mulv array
+  EK_LATENT,          // fusion + reparameterisation + KL; decoder inputs [z | c | 1]
+  EK_COPY,            // stash block -> ACT[h]
+  EK_RECON,           // loss terms + d/dx_recon planes -> stash; logvar_out gradient partials
+  EK_LAM,             // Adam on logvar_out
+  EK_DGRAD,           // leaky-relu' -> planes -> ACT[h]
+  EK_DZ,              // accumulate d/dz
+  EK_LATENT_BWD,      // latent + fusion backward -> d[mu | logvar] planes
+  EK_WGRAD,           // weight gradient (rows = out) fused with Adam; planes of the new weights
+  EK_WGRAD_T,         // transposed weight gradient of decoder_mean_layer (rows = in)
+  EK_STEP_END         // loss reduction, alpha (gPoE) update
+};
+
+// One ring tile (+ optional A tile) and the MMAs issued on it.
+struct Step {
+  long long b_off, a_off;           // byte offsets inside their spaces
+  unsigned b_bytes, a_bytes;        // a_bytes == 0: A is resident in ACT[half]
+  int dep;                          // epilogue item (index + 1, this step) that produced the tile data; 0 = none
+  int mma_dep;                      // epilogue item (index + 1) that must finish before these MMAs issue; 0 = none
+  unsigned a_start;                 // byte offset inside ACT[half]
+  unsigned a_lbo, a_sbo, a_kadv, a_lo;
+  unsigned b_lbo, b_sbo, b_kadv, b_lo;
+  unsigned short ksteps, n, tmem_col;
+  unsigned char half, b_space, a_space, x_mod;
+  unsigned char a_mn, b_mn;         // 1 = MN-major
+  unsigned char first;              // first MMA overwrites the accumulator
+  unsigned char commit;             // 0 none, 1 always, 2 only when half 1 is inactive
+  unsigned char commit_buf;         // accumulator barrier 0..3
+  unsigned char pad_[3];
+};
+
+struct Epi {
+  int kind, half, buf, mod;         // half: 0/1, 2 = joint.  buf: accumulator barrier to wait on, -1 = none
+  int n_mma, n_valid, n_cols;       // MMA N; valid output columns; columns written (multiple of 16)
+  int tmem_col;                     // absolute TMEM column of the accumulator
+  int col0;                         // first logical column / row handled by this item (chunked ops)
+  int to_act;                       // planes also written to ACT[half]
+  long long stash_off;              // destination block (bytes, stash space), -1 = none
+  long long src_off;                // EK_COPY source / EK_DGRAD sign source (stash space), -1 = none
+  int src_cg;                       // EK_COPY: column groups to copy
+  // parameters (EK_WGRAD / EK_WGRAD_T / EK_LAM)
+  long long p_off; int p_ld, p_rows, p_cols;   // float offset of the augmented matrix, row stride, out, in + 1
+  long long wp_off; int wp_R;       // weight planes block (byte offset in SP_W) and its R
+  int row0;                         // EK_WGRAD: first weight row of this planes block (out-layer blocks)
+  int last;                         // EK_RECON: last tile of the modality (lam partials complete)
+};
+
+// Weight block of the per-member planes buffer (prologue conversion fp32 -> planes).
+struct WBlock {
+  long long p_off; int p_ld, row0, rows_valid, cols_valid;
+  long long wp_off; int R, cg;
+};
+
+// fp32 side arrays inside the stash slot (byte offsets) and their strides (floats).
+struct Layout {
+  long long mulv[NMB_MAX_MOD]; int ld_mulv;      // [256][ld_mulv] heads per modality
+  long long g0[NMB_MAX_MOD][2], dmulv[NMB_MAX_MOD][2];   // decoder-input / head-gradient blocks per half
+  int wout_cg[NMB_MAX_MOD];                       // column groups of a decoder_mean_layer planes block
+  long long zbuf, dz;                             // [256][Z]
+  long long lampart[NMB_MAX_MOD];                 // [8][round4(D)] logvar_out gradient partials
+  long long dxh_blk[NMB_MAX_MOD];                 // first d/dx_recon block of half 0 (blocks of 32 KB, [half][j])
+  int n_dxh_blk[NMB_MAX_MOD];
+  long long stash_bytes;
+  long long wplanes_bytes;
+  int x_cg[NMB_MAX_MOD];                          // column groups of a dataset block
+};
+
+struct Program {
+  std::vector<Step> steps;
+  std::vector<Epi> epis;
+  std::vector<WBlock> wblocks;
+  Layout lay;
+  bool eligible = false;
+};
+
+struct ProgramDev {          // per architecture, device pointers
+  const Step* steps; const Epi* epis; const WBlock* wblocks;
+  int n_steps, n_epis, n_wblocks;
+  Layout lay;
+};
+
+struct MemberTc {            // per member
+  unsigned char* wplanes;
+  const unsigned char* xplanes[NMB_MAX_MOD];   // dataset blocks [pos][half], 128 rows each
+  int n_half;                                  // halves per minibatch = ceil(batch / 128)
+};
+
+// One dataset (packed fp32 rows of one modality) to be re-tiled into 128-row blocks per (minibatch, half).
+struct XPrepItem { const float* xc; unsigned char* out; int n_rows, batch, ldx, k_valid, cg, n_half; };
+
+__host__ __device__ inline int round16(int v) { return (v + 15) & ~15; }
+
+// ---- host: build the step program of one architecture ------------------------------------------
+inline Program build_program(const ArchDesc& a) {
+  Program P;
+  const int M = a.M, L = a.L, Z = a.Z, C = a.C;
+  if (2 * Z > 128 || Z + C + 1 > 128) return P;
+  for (int l = 0; l < L; ++l) if (a.hidden[l] > 127) return P;
+  P.eligible = true;
+  Layout& lay = P.lay;
+  lay = Layout{};
+
+  // ---- stash + planes layout ----
+  long long so = 0, wo = 0;
+  auto alloc = [&](long long bytes) { long long r = so; so += (bytes + 127) & ~127LL; return r; };
+  auto act_block = [&](int cols) { return alloc((long long)(round16(cols) / 8) * 4096); };
+  struct WRef { long long wp_off; int R, cg, row0, rows; };
+  auto wblock = [&](const LinDesc& w, int row0, int rows, int R) {
+    WBlock b; b.p_off = w.off; b.p_ld = w.ld; b.row0 = row0; b.rows_valid = rows; b.cols_valid = w.in + 1;
+    b.R = R; b.cg = round16(w.in + 1) / 8; b.wp_off = wo;
+    wo += (long long)b.cg * 32 * R;
+    P.wblocks.push_back(b);
+    return WRef{b.wp_off, R, b.cg, row0, rows};
+  };
+  // per-half activation blocks: [m][h]
+  std::vector<std::vector<long long>> s_h(M), s_k(M);     // [m][l*2+h]
+  std::vector<long long> s_g0(M * 2), s_dmulv(M * 2);
+  std::vector<std::vector<WRef>> w_enc(M), w_dec(M), w_out(M);
+  std::vector<WRef> w_head(M);
+  lay.ld_mulv = round4(2 * Z);
+  for (int m = 0; m < M; ++m) {
+    const ModDesc& q = a.mod[m];
+    s_h[m].resize(L * 2); s_k[m].resize(L * 2);
+    for (int l = 0; l < L; ++l)
+      for (int h = 0; h < 2; ++h) {
+        s_h[m][l * 2 + h] = act_block(a.hidden[l] + 1);
+        s_k[m][l * 2 + h] = act_block(a.hidden[L - 1 - l] + 1);
+      }
+    for (int h = 0; h < 2; ++h) {
+      s_g0[m * 2 + h] = act_block(Z + C + 1); s_dmulv[m * 2 + h] = act_block(2 * Z);
+      lay.g0[m][h] = s_g0[m * 2 + h]; lay.dmulv[m][h] = s_dmulv[m * 2 + h];
+    }
+    lay.wout_cg[m] = round16(q.outl.in + 1) / 8;
+    lay.n_dxh_blk[m] = (q.D + 63) / 64;
+    lay.dxh_blk[m] = alloc((long long)2 * lay.n_dxh_blk[m] * 32768);
+    lay.mulv[m] = alloc((long long)256 * lay.ld_mulv * 4);
+    lay.lampart[m] = alloc((long long)8 * round4(q.D) * 4);
+    lay.x_cg[m] = round16(q.D + C + 1) / 8;
+    for (int l = 0; l < L; ++l) w_enc[m].push_back(wblock(q.enc[l], 0, q.enc[l].out, round16(q.enc[l].out)));
+    w_head[m] = wblock(q.head, 0, q.head.out, round16(q.head.out));
+    for (int l = 0; l < L; ++l) w_dec[m].push_back(wblock(q.dec[l], 0, q.dec[l].out, round16(q.dec[l].out)));
+    for (int t = 0; t < lay.n_dxh_blk[m]; ++t)
+      w_out[m].push_back(wblock(q.outl, 64 * t, q.D - 64 * t < 64 ? q.D - 64 * t : 64, 64));
+  }
+  lay.zbuf = alloc((long long)256 * Z * 4);
+  lay.dz = alloc((long long)256 * Z * 4);
+  lay.stash_bytes = so;
+  lay.wplanes_bytes = (wo + 127) & ~127LL;
+
+  // ---- program ----
+  int act_ready[2] = {0, 0};    // epilogue item (index+1) after which ACT[h] holds what the next MMA group reads
+  int acc_free[4] = {0, 0, 0, 0};
+  auto accbuf = [](int h) { return h; };
+  std::map<long long, int> ready;   // stash block -> epilogue item (index + 1) that wrote it
+  auto push_epi = [&](Epi e) {      // returns index + 1
+    P.epis.push_back(e);
+    const int id = (int)P.epis.size();
+    if (e.stash_off >= 0) ready[e.stash_off] = id;
+    return id;
+  };
+  auto new_epi = [&](int kind, int half, int buf, int mod) {
+    Epi e{}; e.kind = kind; e.half = half; e.buf = buf; e.mod = mod; e.stash_off = -1; e.src_off = -1;
+    e.tmem_col = buf < 0 ? 0 : (buf < 2 ? kAcc0 + 128 * buf : kWacc0 + 128 * (buf - 2));
+    return e;
+  };
+  auto base_step = [&](int h) {
+    Step s{}; s.half = (unsigned char)h; s.b_space = SP_NONE; s.a_space = SP_NONE;
+    return s;
+  };
+  auto set_a_kmajor = [](Step& s, unsigned start) {   // 128-row block (ACT or ring), K-major
+    s.a_mn = 0; s.a_start = start; s.a_lbo = 4096; s.a_sbo = 128; s.a_kadv = 8192; s.a_lo = 2048;
+  };
+  auto set_a_mnmajor = [](Step& s) {                  // ACT[h] as MN-major A (M = columns), K = 128 rows
+    s.a_mn = 1; s.a_start = 0; s.a_sbo = 4096; s.a_lbo = 128; s.a_kadv = 256; s.a_lo = 2048;
+  };
+  auto set_b = [](Step& s, int space, long long off, int R, int g0, int ng, bool mn) {
+    s.b_space = (unsigned char)space; s.b_off = off + (long long)g0 * 32 * R; s.b_bytes = (unsigned)(ng * 32 * R);
+    s.b_mn = mn ? 1 : 0; s.b_lo = 16 * R;
+    if (mn) { s.b_sbo = 32 * R; s.b_lbo = 128; s.b_kadv = 256; }
+    else { s.b_lbo = 32 * R; s.b_sbo = 128; s.b_kadv = 64 * R; }
+  };
+  auto tile_groups = [](int R) { int g = 1024 / R; return g > 16 ? 16 : (g < 2 ? 2 : g & ~1); };
+
+  // forward-type group: acc[h][0..N) = sum_k A[.,k] B[n,k]; A from ACT[h] or ring tiles (a_space/a_base)
+  auto emit_fwd = [&](int h, const WRef& w, int a_space, long long a_base, int a_dep, int x_mod) {
+    const int buf = accbuf(h);
+    const int tg = tile_groups(w.R) > 8 && a_space != SP_NONE ? 8 : tile_groups(w.R);
+    for (int g0 = 0, j = 0; g0 < w.cg; g0 += tg, ++j) {
+      const int ng = w.cg - g0 < tg ? w.cg - g0 : tg;
+      Step s = base_step(h);
+      set_b(s, SP_W, w.wp_off, w.R, g0, ng, false);
+      if (a_space == SP_NONE) set_a_kmajor(s, (unsigned)g0 * 4096);
+      else {
+        set_a_kmajor(s, 0);
+        s.a_space = (unsigned char)a_space; s.a_off = a_base + (long long)g0 * 4096; s.a_bytes = (unsigned)ng * 4096;
+        s.x_mod = (unsigned char)x_mod;
+      }
+      s.dep = a_dep;
+      s.ksteps = (unsigned short)(ng / 2); s.n = (unsigned short)w.R; s.tmem_col = (unsigned short)(kAcc0 + 128 * buf);
+      s.first = j == 0;
+      if (j == 0) s.mma_dep = a_space == SP_NONE ? (act_ready[h] > acc_free[buf] ? act_ready[h] : acc_free[buf]) : acc_free[buf];
+      s.commit = g0 + tg >= w.cg ? 1 : 0; s.commit_buf = (unsigned char)buf;
+      P.steps.push_back(s);
+    }
+  };
+  // dgrad-type group: acc[h][i] = sum_o ACT[h][., o] W[o][i], N-chunks of the weight block
+  auto emit_dgrad = [&](int h, const WRef& w, int n_need) {
+    const int buf = accbuf(h);
+    const int tg = tile_groups(w.R);
+    const int cg = (round16(n_need) / 8) < w.cg ? round16(n_need) / 8 : w.cg;
+    for (int g0 = 0, j = 0; g0 < cg; g0 += tg, ++j) {
+      const int ng = cg - g0 < tg ? cg - g0 : tg;
+      Step s = base_step(h);
+      set_b(s, SP_W, w.wp_off, w.R, g0, ng, true);
+      set_a_kmajor(s, 0);
+      s.ksteps = (unsigned short)(w.R / 16); s.n = (unsigned short)(ng * 8);
+      s.tmem_col = (unsigned short)(kAcc0 + 128 * buf + g0 * 8);
+      s.first = 1;
+      if (j == 0) s.mma_dep = act_ready[h] > acc_free[buf] ? act_ready[h] : acc_free[buf];
+      s.commit = g0 + tg >= cg ? 1 : 0; s.commit_buf = (unsigned char)buf;
+      P.steps.push_back(s);
+    }
+  };
+  // wgrad part for half h: wacc[wb][.., 64 j + ..) += ACT[h]^T (MN-major A) x B tiles (MN-major, N-chunks)
+  auto emit_wgrad_part = [&](int h, int wb, int b_space, long long b_base, int g_first, int g_count, int x_mod) {
+    const int b_dep = b_space == SP_STASH ? ready[b_base] : 0;
+    for (int g0 = 0; g0 < g_count; g0 += 8) {
+      const int ng = g_count - g0 < 8 ? g_count - g0 : 8;
+      Step s = base_step(h);
+      set_b(s, b_space, b_base, 128, g_first + g0, ng, true);
+      s.x_mod = (unsigned char)x_mod;
+      set_a_mnmajor(s);
+      s.dep = b_dep;
+      s.ksteps = 8; s.n = (unsigned short)(ng * 8); s.tmem_col = (unsigned short)(kWacc0 + 128 * wb + g0 * 8);
+      s.first = h == 0;
+      if (g0 == 0) s.mma_dep = act_ready[h] > acc_free[2 + wb] ? act_ready[h] : acc_free[2 + wb];
+      const bool last = g0 + 8 >= g_count;
+      s.commit = !last ? 0 : (h == 1 ? 1 : 2);
+      s.commit_buf = (unsigned char)(2 + wb);
+      P.steps.push_back(s);
+    }
+  };
+
+  int wacc_next = 0;
+  const int nl = a.non_linear;
+  (void)nl;
+
+  // ================= forward =================
+  for (int m = 0; m < M; ++m) {
+    const ModDesc& q = a.mod[m];
+    for (int l = 0; l < L; ++l) {
+      for (int h = 0; h < 2; ++h) {
+        if (l == 0) emit_fwd(h, w_enc[m][0], SP_X, 0, 0, m);
+        else emit_fwd(h, w_enc[m][l], SP_NONE, 0, 0, 0);
+        Epi e = new_epi(EK_HIDDEN, h, accbuf(h), m);
+        e.n_mma = w_enc[m][l].R; e.n_valid = q.enc[l].out; e.n_cols = round16(q.enc[l].out + 1);
+        e.to_act = 1; e.stash_off = s_h[m][l * 2 + h];
+        const int id = push_epi(e);
+        act_ready[h] = id; acc_free[accbuf(h)] = id;
+      }
+    }
+    for (int h = 0; h < 2; ++h) {
+      emit_fwd(h, w_head[m], SP_NONE, 0, 0, 0);
+      Epi e = new_epi(EK_HEAD, h, accbuf(h), m);
+      e.n_mma = w_head[m].R; e.n_valid = 2 * Z; e.n_cols = round16(2 * Z);
+      const int id = push_epi(e);
+      acc_free[accbuf(h)] = id;
+      if (act_ready[h] < id) act_ready[h] = id;      // ACT[h] may be overwritten only after the head read it
+    }
+  }
+  for (int h = 0; h < 2; ++h) {
+    Epi e = new_epi(EK_LATENT, h, -1, 0);
+    e.to_act = 1;
+    const int id = push_epi(e);
+    act_ready[h] = id;
+    for (int m = 0; m < M; ++m) ready[s_g0[m * 2 + h]] = id;
+  }
+  std::vector<int> dxh_ready(M * 2, 0);   // [m*2+h]: item after which all dxh blocks of (m,h) exist
+  for (int m = 0; m < M; ++m) {
+    const ModDesc& q = a.mod[m];
+    if (m > 0) {
+      for (int h = 0; h < 2; ++h) {
+        Epi e = new_epi(EK_COPY, h, -1, m);
+        e.src_off = s_g0[m * 2 + h]; e.src_cg = round16(Z + C + 1) / 8;
+        act_ready[h] = push_epi(e);
+      }
+    }
+    for (int l = 0; l < L; ++l) {
+      for (int h = 0; h < 2; ++h) {
+        emit_fwd(h, w_dec[m][l], SP_NONE, 0, 0, 0);
+        Epi e = new_epi(EK_HIDDEN, h, accbuf(h), m);
+        e.n_mma = w_dec[m][l].R; e.n_valid = q.dec[l].out; e.n_cols = round16(q.dec[l].out + 1);
+        e.to_act = 1; e.stash_off = s_k[m][l * 2 + h];
+        const int id = push_epi(e);
+        act_ready[h] = id; acc_free[accbuf(h)] = id;
+      }
+    }
+    for (int t = 0; t < lay.n_dxh_blk[m]; ++t) {
+      for (int h = 0; h < 2; ++h) {
+        emit_fwd(h, w_out[m][t], SP_NONE, 0, 0, 0);
+        Epi e = new_epi(EK_RECON, h, accbuf(h), m);
+        e.n_mma = 64; e.n_valid = w_out[m][t].rows; e.n_cols = 64; e.col0 = 64 * t;
+        e.stash_off = lay.dxh_blk[m] + ((long long)h * lay.n_dxh_blk[m] + t) * 32768;
+        e.last = t == lay.n_dxh_blk[m] - 1;
+        const int id = push_epi(e);
+        acc_free[accbuf(h)] = id;
+        dxh_ready[m * 2 + h] = id;
+      }
+    }
+  }
+
+  // ================= backward =================
+  for (int m = 0; m < M; ++m) {
+    const ModDesc& q = a.mod[m];
+    if (a.loss_kind == NMB_LOSS_GAUSS_LL) {
+      Epi e = new_epi(EK_LAM, 2, -1, m);
+      e.p_off = q.lam_off; e.p_cols = q.D;
+      push_epi(e);
+    }
+    if (m > 0) {   // ACT[h] <- last decoder hidden activation of this modality (transposed wgrad A operand)
+      for (int h = 0; h < 2; ++h) {
+        Epi e = new_epi(EK_COPY, h, -1, m);
+        e.src_off = s_k[m][(L - 1) * 2 + h]; e.src_cg = round16(q.outl.in + 1) / 8;
+        act_ready[h] = push_epi(e);
+      }
+    } else if (M > 1) {
+      // modality 0's activations were overwritten by later modalities' forward passes
+      for (int h = 0; h < 2; ++h) {
+        Epi e = new_epi(EK_COPY, h, -1, m);
+        e.src_off = s_k[m][(L - 1) * 2 + h]; e.src_cg = round16(q.outl.in + 1) / 8;
+        act_ready[h] = push_epi(e);
+      }
+    }
+    // decoder_mean_layer.  The dgrad MMAs are issued FIRST (they must read the pre-update weights, and the
+    // Adam epilogues below rewrite the weight planes); their epilogues -- which overwrite ACT[h], the A
+    // operand of the transposed wgrad -- run LAST.
+    int dg_ready[2];
+    for (int h = 0; h < 2; ++h) {
+      const int buf = accbuf(h);
+      for (int t = 0; t < lay.n_dxh_blk[m]; ++t) {
+        const WRef& w = w_out[m][t];
+        Step s = base_step(h);
+        set_b(s, SP_W, w.wp_off, 64, 0, w.cg, true);
+        set_a_kmajor(s, 0);
+        s.a_space = SP_STASH; s.a_off = lay.dxh_blk[m] + ((long long)h * lay.n_dxh_blk[m] + t) * 32768; s.a_bytes = 32768;
+        s.dep = dxh_ready[m * 2 + h];
+        s.ksteps = 4; s.n = (unsigned short)(w.cg * 8); s.tmem_col = (unsigned short)(kAcc0 + 128 * buf);
+        s.first = t == 0;
+        if (t == 0) s.mma_dep = acc_free[buf];
+        s.commit = t == lay.n_dxh_blk[m] - 1 ? 1 : 0; s.commit_buf = (unsigned char)buf;
+        P.steps.push_back(s);
+      }
+      dg_ready[h] = 0;
+    }
+    // transposed wgrad, two 64-column blocks of D per item
+    for (int t0 = 0; t0 < lay.n_dxh_blk[m]; t0 += 2) {
+      const int wb = wacc_next; wacc_next ^= 1;
+      const int nt = lay.n_dxh_blk[m] - t0 < 2 ? lay.n_dxh_blk[m] - t0 : 2;
+      for (int h = 0; h < 2; ++h) {
+        for (int t = t0; t < t0 + nt; ++t) {
+          Step s = base_step(h);
+          set_b(s, SP_STASH, lay.dxh_blk[m] + ((long long)h * lay.n_dxh_blk[m] + t) * 32768, 128, 0, 8, true);
+          set_a_mnmajor(s);
+          s.dep = dxh_ready[m * 2 + h];
+          s.ksteps = 8; s.n = 64; s.tmem_col = (unsigned short)(kWacc0 + 128 * wb + 64 * (t - t0));
+          s.first = h == 0;
+          if (t == t0) s.mma_dep = act_ready[h] > acc_free[2 + wb] ? act_ready[h] : acc_free[2 + wb];
+          const bool last = t == t0 + nt - 1;
+          s.commit = !last ? 0 : (h == 1 ? 1 : 2);
+          s.commit_buf = (unsigned char)(2 + wb);
+          P.steps.push_back(s);
+        }
+      }
+      Epi e = new_epi(EK_WGRAD_T, 2, 2 + wb, m);
+      e.n_mma = 64 * nt; e.col0 = 64 * t0;
+      e.p_off = q.outl.off; e.p_ld = q.outl.ld; e.p_rows = q.outl.out; e.p_cols = q.outl.in + 1;
+      e.wp_off = w_out[m][0].wp_off; e.wp_R = 64; e.src_cg = w_out[m][0].cg;
+      acc_free[2 + wb] = push_epi(e);
+    }
+    for (int h = 0; h < 2; ++h) {
+      const int buf = accbuf(h);
+      Epi e = new_epi(EK_DGRAD, h, buf, m);
+      e.n_mma = round16(q.outl.in + 1); e.n_valid = q.outl.in; e.n_cols = round16(q.outl.in);
+      e.to_act = 1; e.src_off = s_k[m][(L - 1) * 2 + h];
+      const int id = push_epi(e);
+      act_ready[h] = id; acc_free[buf] = id;
+      (void)dg_ready;
+    }
+    // decoder hidden layers
+    for (int l = L - 1; l >= 0; --l) {
+      const LinDesc& w = q.dec[l];
+      const int in_cg = round16(w.in + 1) / 8;
+      const int wb0 = wacc_next;
+      const int n_items = (in_cg + 15) / 16;
+      for (int h = 0; h < 2; ++h) {
+        int wb = wb0;
+        for (int it = 0; it < n_items; ++it, wb ^= 1) {
+          const int gf = it * 16, gc = in_cg - gf < 16 ? in_cg - gf : 16;
+          emit_wgrad_part(h, wb, SP_STASH, l == 0 ? s_g0[m * 2 + h] : s_k[m][(l - 1) * 2 + h], gf, gc, 0);
+        }
+        if (l > 0) {
+          emit_dgrad(h, w_dec[m][l], w.in);
+          Epi e = new_epi(EK_DGRAD, h, accbuf(h), m);
+          e.n_mma = round16(w.in); e.n_valid = w.in; e.n_cols = round16(w.in);
+          e.to_act = 1; e.src_off = s_k[m][(l - 1) * 2 + h];
+          const int id = push_epi(e);
+          act_ready[h] = id; acc_free[accbuf(h)] = id;
+        } else {
+          emit_dgrad(h, w_dec[m][0], Z);
+          Epi e = new_epi(EK_DZ, h, accbuf(h), m);
+          e.n_mma = round16(Z); e.n_valid = Z;
+          const int id = push_epi(e);
+          act_ready[h] = id; acc_free[accbuf(h)] = id;
+        }
+      }
+      int wb = wb0;
+      for (int it = 0; it < n_items; ++it, wb ^= 1) {
+        Epi e = new_epi(EK_WGRAD, 2, 2 + wb, m);
+        e.col0 = it * 128; e.n_mma = (in_cg - it * 16 < 16 ? in_cg - it * 16 : 16) * 8;
+        e.p_off = w.off; e.p_ld = w.ld; e.p_rows = w.out; e.p_cols = w.in + 1;
+        e.wp_off = w_dec[m][l].wp_off; e.wp_R = w_dec[m][l].R;
+        acc_free[2 + wb] = push_epi(e);
+      }
+      if (n_items & 1) wacc_next ^= 1;
+    }
+  }
+  for (int h = 0; h < 2; ++h) {
+    Epi e = new_epi(EK_LATENT_BWD, h, -1, 0);
+    e.to_act = 1;
+    act_ready[h] = push_epi(e);
+    for (int m = 0; m < M; ++m) ready[s_dmulv[m * 2 + h]] = act_ready[h];
+  }
+  for (int m = 0; m < M; ++m) {
+    const ModDesc& q = a.mod[m];
+    if (m > 0) {
+      for (int h = 0; h < 2; ++h) {
+        Epi e = new_epi(EK_COPY, h, -1, m);
+        e.src_off = s_dmulv[m * 2 + h]; e.src_cg = round16(2 * Z) / 8;
+        act_ready[h] = push_epi(e);
+      }
+    }
+    // head, then encoder hidden layers
+    for (int l = L; l >= 0; --l) {
+      const bool is_head = l == L;
+      const LinDesc& w = is_head ? q.head : q.enc[l];
+      const WRef& wr = is_head ? w_head[m] : w_enc[m][l];
+      const int in_cg = round16(w.in + 1) / 8;
+      const int n_items = (in_cg + 15) / 16;
+      // two wgrad accumulators: items are emitted in pairs (only layer 0 -- which has no dgrad -- can
+      // have more than one item, its input being the [x | c | 1] row)
+      for (int it0 = 0; it0 < n_items; it0 += 2) {
+        const int it1 = it0 + 2 < n_items ? it0 + 2 : n_items;
+        const int wb0 = wacc_next;
+        for (int h = 0; h < 2; ++h) {
+          int wb = wb0;
+          for (int it = it0; it < it1; ++it, wb ^= 1) {
+            const int gf = it * 16, gc = in_cg - gf < 16 ? in_cg - gf : 16;
+            if (!is_head && l == 0) emit_wgrad_part(h, wb, SP_X, 0, gf, gc, m);
+            else emit_wgrad_part(h, wb, SP_STASH, s_h[m][((is_head ? L : l) - 1) * 2 + h], gf, gc, 0);
+          }
+          if ((is_head || l > 0) && it1 == n_items) {
+            emit_dgrad(h, wr, w.in);
+            Epi e = new_epi(EK_DGRAD, h, accbuf(h), m);
+            e.n_mma = round16(w.in); e.n_valid = w.in; e.n_cols = round16(w.in);
+            e.to_act = 1; e.src_off = s_h[m][((is_head ? L : l) - 1) * 2 + h];
+            const int id = push_epi(e);
+            act_ready[h] = id; acc_free[accbuf(h)] = id;
+          }
+        }
+        int wb = wb0;
+        for (int it = it0; it < it1; ++it, wb ^= 1) {
+          Epi e = new_epi(EK_WGRAD, 2, 2 + wb, m);
+          e.col0 = it * 128; e.n_mma = (in_cg - it * 16 < 16 ? in_cg - it * 16 : 16) * 8;
+          e.p_off = w.off; e.p_ld = w.ld; e.p_rows = w.out; e.p_cols = w.in + 1;
+          e.wp_off = wr.wp_off; e.wp_R = wr.R;
+          acc_free[2 + wb] = push_epi(e);
+        }
+        if ((it1 - it0) & 1) wacc_next ^= 1;
+      }
+    }
+  }
+  push_epi(new_epi(EK_STEP_END, 2, -1, 0));
+  return P;
+}
+
+}  // namespace tcp
+}  // namespace nmb

@@ -223,6 +223,12 @@ class EnsembleTrainer:
         self.gpu_launches += 1
         return losses
 
+    def engine(self, flags: int = 0) -> str:
+        """Engine train_steps(flags=...) runs: 'tcgen05-pipelined', 'tcgen05-generic' or 'fp32'."""
+        out = C.c_int32(0)
+        _lib.check(self.lib.nmb_ensemble_engine(self.handle, int(flags), C.byref(out)), "nmb_ensemble_engine")
+        return {2: "tcgen05-pipelined", 1: "tcgen05-generic", 0: "fp32"}[out.value]
+
     def train_epochs(self, epochs: int, **kw):
         spe = set(self.steps_per_epoch)
         if len(spe) != 1:
