@@ -209,6 +209,12 @@ int nmb_philox_normal(uint64_t seed, uint64_t step, uint32_t stream_id, int64_t 
 int nmb_debug_tc_gemm(const float* a, int32_t lda, int32_t a_kmajor, const float* b, int32_t ldb,
                       int32_t b_kmajor, float* c, int32_t ldc, int32_t m, int32_t n, int32_t k, void* stream);
 
+/* Test hook: timeline trace of the pipelined training kernel.  buf (device, >= 8 * (3*items + 5*steps)
+ * bytes, or NULL to switch tracing off) receives %globaltimer stamps of launch-local minibatch step
+ * `step` of CTA 0: per epilogue item {arrive, start, end}, per MMA step {deps ready, tiles ready,
+ * issued}, per producer step {deps ready, issued}.  tools/trace_tcp.py prints it. */
+int nmb_debug_tcp_trace(uint64_t* buf, int32_t step);
+
 #ifdef __cplusplus
 }
 #endif

@@ -79,6 +79,8 @@ struct NmbEnsemble {
   int n_xprep = 0, xprep_max_blocks = 0;
   unsigned char* stash = nullptr;
   long long stash_bytes = 0;
+  float* master = nullptr;
+  long long master_floats = 0;
 };
 
 namespace {
@@ -103,7 +105,10 @@ int setup_tcp(NmbEnsemble* e) {
   long long max_stash = 0;
   for (size_t i = 0; i < progs.size(); ++i) {
     tcp::Program& P = progs[i];
-    void *ds, *de, *dw;
+    void *ds, *de, *dw, *dm;
+    CU(upload(P.mlayers.data(), sizeof(tcp::MLayer) * P.mlayers.size(), &dm));
+    pd[i].mlayers = (const tcp::MLayer*)dm; pd[i].n_mlayers = (int)P.mlayers.size();
+    if (P.lay.master_floats > e->master_floats) e->master_floats = P.lay.master_floats;
     CU(upload(P.steps.data(), sizeof(tcp::Step) * P.steps.size(), &ds));
     CU(upload(P.epis.data(), sizeof(tcp::Epi) * P.epis.size(), &de));
     CU(upload(P.wblocks.data(), sizeof(tcp::WBlock) * P.wblocks.size(), &dw));
@@ -118,6 +123,8 @@ int setup_tcp(NmbEnsemble* e) {
   e->stash_bytes = (max_stash + 1023) & ~1023LL;
   CU(dev_alloc((size_t)e->stash_bytes * e->n_sm, &p));
   e->stash = (unsigned char*)p;
+  CU(dev_alloc((size_t)e->master_floats * 3 * sizeof(float) * e->n_sm, &p));
+  e->master = (float*)p;
   // weight planes: one slice per member
   long long wtotal = 0;
   std::vector<long long> woff(e->n_members);
@@ -340,7 +347,8 @@ int nmb_ensemble_train(NmbEnsemble* e, int64_t n_steps, const float* eps_overrid
   if (e->tcp_ok && !(flags & (NMB_TRAIN_FP32 | NMB_TRAIN_TC_SIMPLE))) {
     // dataset rows may have been re-packed since the last call: refresh their planes (cheap, streaming)
     CU(launch_xprep(e->xprep_dev, e->n_xprep, e->xprep_max_blocks, (cudaStream_t)stream));
-    CU(launch_train_tcp(t, e->progs_dev, e->mtc_dev, e->stash, e->stash_bytes, e->n_sm, (cudaStream_t)stream));
+    CU(launch_train_tcp(t, e->progs_dev, e->mtc_dev, e->stash, e->stash_bytes, e->master, e->master_floats, e->n_sm,
+                        (cudaStream_t)stream));
   } else {
     CU(launch_train(t, (cudaStream_t)stream));
   }
@@ -524,6 +532,11 @@ int nmb_philox_normal(uint64_t seed, uint64_t step, uint32_t stream_id, int64_t 
   if (!out || n < 0) return fail("bad argument");
   launch_philox(seed, step, stream_id, n, out, (cudaStream_t)stream);
   CU(cudaGetLastError());
+  return 0;
+}
+
+int nmb_debug_tcp_trace(uint64_t* buf, int32_t step) {
+  CU(set_tcp_trace((unsigned long long*)buf, step));
   return 0;
 }
 

@@ -65,8 +65,10 @@ cudaError_t configure_kernels();
 
 // nmb_train_tcp.cu: pipelined tensor-core path
 cudaError_t configure_tcp();
+cudaError_t set_tcp_trace(unsigned long long* buf, int step);
 cudaError_t launch_xprep(const void* items_dev, int n_items, int max_blocks, cudaStream_t st);
 cudaError_t launch_train_tcp(const TrainLaunch& t, const tcp::ProgramDev* progs, const tcp::MemberTc* mtc,
-                             unsigned char* stash, long long stash_bytes, int n_sm, cudaStream_t st);
+                             unsigned char* stash, long long stash_bytes, float* master, long long master_floats,
+                             int n_sm, cudaStream_t st);
 
 }  // namespace nmb

@@ -26,7 +26,8 @@
 namespace nmb {
 namespace tcp {
 
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 12;                     // 4 warps per TMEM lane quadrant
+constexpr int kEpiParts = kEpiWarps / 4;          // column partitions of an accumulator
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kThreadsP = kEpiThreads + 64;        // + MMA warp + producer warp
 constexpr int kActBytes = 65536;                   // one 128-row operand block, up to 128 columns (hi + lo)
@@ -51,11 +52,12 @@ enum EpiKind : int {
   EK_LATENT_BWD,      // latent + fusion backward -> d[mu | logvar] planes
   EK_WGRAD,           // weight gradient (rows = out) fused with Adam; planes of the new weights
   EK_WGRAD_T,         // transposed weight gradient of decoder_mean_layer (rows = in)
-  EK_STEP_END         // loss reduction, alpha (gPoE) update
+  EK_STEP_END,        // loss reduction, alpha (gPoE) update; publishes the new weight planes to the TMA proxy
+  EK_FENCE            // publishes every stash block written so far to the TMA proxy (start of the backward pass)
 };
 
 // One ring tile (+ optional A tile) and the MMAs issued on it.
-struct Step {
+struct alignas(16) Step {
   long long b_off, a_off;           // byte offsets inside their spaces
   unsigned b_bytes, a_bytes;        // a_bytes == 0: A is resident in ACT[half]
   int dep;                          // epilogue item (index + 1, this step) that produced the tile data; 0 = none
@@ -72,7 +74,7 @@ struct Step {
   unsigned char pad_[3];
 };
 
-struct Epi {
+struct alignas(16) Epi {
   int kind, half, buf, mod;         // half: 0/1, 2 = joint.  buf: accumulator barrier to wait on, -1 = none
   int n_mma, n_valid, n_cols;       // MMA N; valid output columns; columns written (multiple of 16)
   int tmem_col;                     // absolute TMEM column of the accumulator
@@ -84,6 +86,7 @@ struct Epi {
   // parameters (EK_WGRAD / EK_WGRAD_T / EK_LAM)
   long long p_off; int p_ld, p_rows, p_cols;   // float offset of the augmented matrix, row stride, out, in + 1
   long long wp_off; int wp_R;       // weight planes block (byte offset in SP_W) and its R
+  long long mst_off; int mst_R;     // Adam master state of the layer (float offset in the slot's master buffer, lane extent)
   int row0;                         // EK_WGRAD: first weight row of this planes block (out-layer blocks)
   int last;                         // EK_RECON: last tile of the modality (lam partials complete)
 };
@@ -92,6 +95,16 @@ struct Epi {
 struct WBlock {
   long long p_off; int p_ld, row0, rows_valid, cols_valid;
   long long wp_off; int R, cg;
+};
+
+// Adam master state of one linear layer inside the per-slot master buffer.  While a member is resident its
+// fp32 parameters and moments live in a lane-major layout so that the Adam epilogues are coalesced:
+//   kind 0 (lane = output row o):  float index = ((i >> 2) * R + o) * 4 + (i & 3)
+//   kind 1 (lane = input index i): float index = ((o >> 2) * R + i) * 4 + (o & 3)     (decoder_mean_layer)
+// They are gathered from / scattered back to the caller's row-major buffers at member start / end.
+struct MLayer {
+  long long p_off; int p_ld, rows, cols;   // augmented matrix [rows][p_ld], cols = in + 1
+  long long mst_off; int R, kind;
 };
 
 // fp32 side arrays inside the stash slot (byte offsets) and their strides (floats).
@@ -105,6 +118,7 @@ struct Layout {
   int n_dxh_blk[NMB_MAX_MOD];
   long long stash_bytes;
   long long wplanes_bytes;
+  long long master_floats;                        // per moment; the slot holds 3 of them (p, m, v)
   int x_cg[NMB_MAX_MOD];                          // column groups of a dataset block
 };
 
@@ -112,13 +126,14 @@ struct Program {
   std::vector<Step> steps;
   std::vector<Epi> epis;
   std::vector<WBlock> wblocks;
+  std::vector<MLayer> mlayers;
   Layout lay;
   bool eligible = false;
 };
 
 struct ProgramDev {          // per architecture, device pointers
-  const Step* steps; const Epi* epis; const WBlock* wblocks;
-  int n_steps, n_epis, n_wblocks;
+  const Step* steps; const Epi* epis; const WBlock* wblocks; const MLayer* mlayers;
+  int n_steps, n_epis, n_wblocks, n_mlayers;
   Layout lay;
 };
 
@@ -155,6 +170,17 @@ inline Program build_program(const ArchDesc& a) {
     P.wblocks.push_back(b);
     return WRef{b.wp_off, R, b.cg, row0, rows};
   };
+  long long mo = 0;
+  std::map<long long, MLayer> mst;   // keyed by the layer's parameter offset
+  auto master = [&](const LinDesc& w, int kind) {
+    MLayer ml; ml.p_off = w.off; ml.p_ld = w.ld; ml.rows = w.out; ml.cols = w.in + 1; ml.kind = kind;
+    const int lanes = kind == 0 ? w.out : w.in + 1, other = kind == 0 ? w.in + 1 : w.out;
+    ml.R = (lanes + 31) & ~31;
+    ml.mst_off = mo;
+    mo += (long long)((other + 3) / 4) * ml.R * 4;
+    P.mlayers.push_back(ml);
+    mst[w.off] = ml;
+  };
   // per-half activation blocks: [m][h]
   std::vector<std::vector<long long>> s_h(M), s_k(M);     // [m][l*2+h]
   std::vector<long long> s_g0(M * 2), s_dmulv(M * 2);
@@ -179,6 +205,8 @@ inline Program build_program(const ArchDesc& a) {
     lay.mulv[m] = alloc((long long)256 * lay.ld_mulv * 4);
     lay.lampart[m] = alloc((long long)8 * round4(q.D) * 4);
     lay.x_cg[m] = round16(q.D + C + 1) / 8;
+    for (int l = 0; l < L; ++l) { master(q.enc[l], 0); master(q.dec[l], 0); }
+    master(q.head, 0); master(q.outl, 1);
     for (int l = 0; l < L; ++l) w_enc[m].push_back(wblock(q.enc[l], 0, q.enc[l].out, round16(q.enc[l].out)));
     w_head[m] = wblock(q.head, 0, q.head.out, round16(q.head.out));
     for (int l = 0; l < L; ++l) w_dec[m].push_back(wblock(q.dec[l], 0, q.dec[l].out, round16(q.dec[l].out)));
@@ -189,6 +217,7 @@ inline Program build_program(const ArchDesc& a) {
   lay.dz = alloc((long long)256 * Z * 4);
   lay.stash_bytes = so;
   lay.wplanes_bytes = (wo + 127) & ~127LL;
+  lay.master_floats = (mo + 31) & ~31LL;
 
   // ---- program ----
   int act_ready[2] = {0, 0};    // epilogue item (index+1) after which ACT[h] holds what the next MMA group reads
@@ -353,6 +382,7 @@ inline Program build_program(const ArchDesc& a) {
   }
 
   // ================= backward =================
+  const int fence_id = push_epi(new_epi(EK_FENCE, 2, -1, 0));
   for (int m = 0; m < M; ++m) {
     const ModDesc& q = a.mod[m];
     if (a.loss_kind == NMB_LOSS_GAUSS_LL) {
@@ -418,6 +448,7 @@ inline Program build_program(const ArchDesc& a) {
       e.n_mma = 64 * nt; e.col0 = 64 * t0;
       e.p_off = q.outl.off; e.p_ld = q.outl.ld; e.p_rows = q.outl.out; e.p_cols = q.outl.in + 1;
       e.wp_off = w_out[m][0].wp_off; e.wp_R = 64; e.src_cg = w_out[m][0].cg;
+      e.mst_off = mst[q.outl.off].mst_off; e.mst_R = mst[q.outl.off].R;
       acc_free[2 + wb] = push_epi(e);
     }
     for (int h = 0; h < 2; ++h) {
@@ -462,6 +493,7 @@ inline Program build_program(const ArchDesc& a) {
         e.col0 = it * 128; e.n_mma = (in_cg - it * 16 < 16 ? in_cg - it * 16 : 16) * 8;
         e.p_off = w.off; e.p_ld = w.ld; e.p_rows = w.out; e.p_cols = w.in + 1;
         e.wp_off = w_dec[m][l].wp_off; e.wp_R = w_dec[m][l].R;
+        e.mst_off = mst[w.off].mst_off; e.mst_R = mst[w.off].R;
         acc_free[2 + wb] = push_epi(e);
       }
       if (n_items & 1) wacc_next ^= 1;
@@ -516,6 +548,7 @@ inline Program build_program(const ArchDesc& a) {
           e.col0 = it * 128; e.n_mma = (in_cg - it * 16 < 16 ? in_cg - it * 16 : 16) * 8;
           e.p_off = w.off; e.p_ld = w.ld; e.p_rows = w.out; e.p_cols = w.in + 1;
           e.wp_off = wr.wp_off; e.wp_R = wr.R;
+          e.mst_off = mst[w.off].mst_off; e.mst_R = mst[w.off].R;
           acc_free[2 + wb] = push_epi(e);
         }
         if ((it1 - it0) & 1) wacc_next ^= 1;
@@ -523,6 +556,10 @@ inline Program build_program(const ArchDesc& a) {
     }
   }
   push_epi(new_epi(EK_STEP_END, 2, -1, 0));
+  // Generic-proxy stores to the stash become visible to the TMA (async proxy) at the EK_FENCE item only:
+  // every stash-sourced tile waits for it (all of them are consumed in the backward pass).
+  for (Step& s : P.steps)
+    if ((s.a_space == SP_STASH || s.b_space == SP_STASH) && s.dep < fence_id) s.dep = fence_id;
   return P;
 }
 

@@ -16,6 +16,16 @@
 namespace nmb {
 namespace tcp {
 
+// Optional timeline trace (test hook): globaltimer stamps of one minibatch step of CTA 0.
+__device__ unsigned long long* g_trace = nullptr;
+__device__ int g_trace_step = 2;
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define TRACE(cond, idx) do { if (cond) g_trace[idx] = gtime(); } while (0)
+
 struct Ctrl {
   uint64_t full[kSlots], empty[kSlots], accbar[4];
   uint32_t tmem;
@@ -24,25 +34,30 @@ struct Ctrl {
   float red[40];
 };
 
-__device__ __forceinline__ uint32_t ld_acquire(const volatile uint32_t* p) {
+__device__ __forceinline__ uint32_t ld_relaxed(const volatile uint32_t* p) {
   uint32_t v;
-  asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(tc::smem_u32((const void*)p)) : "memory");
+  asm volatile("ld.volatile.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(tc::smem_u32((const void*)p)) : "memory");
   return v;
 }
 __device__ __forceinline__ void st_release(volatile uint32_t* p, uint32_t v) {
-  asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(tc::smem_u32((const void*)p)), "r"(v) : "memory");
+  __threadfence_block();
+  asm volatile("st.volatile.shared::cta.u32 [%0], %1;" ::"r"(tc::smem_u32((const void*)p)), "r"(v) : "memory");
 }
-// Bounded spin (a protocol bug must trap, not hang the GPU).
+// Bounded spin with back-off (a protocol bug must trap, not hang the GPU; the spinning single-thread
+// warps must not steal issue slots from the epilogue warps of their scheduler).
 __device__ __forceinline__ void wait_epi(const volatile uint32_t* p, uint32_t need) {
-  if (ld_acquire(p) >= need) return;
-  const long long t0 = clock64();
-  while (ld_acquire(p) < need) {
-    __nanosleep(32);
-    if (clock64() - t0 > 4000000000LL) __trap();
+  if (ld_relaxed(p) < need) {
+    const long long t0 = clock64();
+    while (ld_relaxed(p) < need) {
+      __nanosleep(100);
+      if (clock64() - t0 > 4000000000LL) __trap();
+    }
   }
+  __threadfence_block();
 }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
 __device__ __forceinline__ void fence_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ void expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc::smem_u32(bar)), "r"(bytes) : "memory");
@@ -78,12 +93,15 @@ __device__ void producer_role(const TrainLaunch& t, const ProgramDev& pg, const 
   unsigned char* ring = smem + kSmemRing;
   for (long long i = 0; i < t.n_steps; ++i) {
     const StepVars sv = step_vars(mb, mb.steps_done + i, i, pg.n_epis);
+    const bool tr = g_trace && blockIdx.x == 0 && i == g_trace_step;
+    const int tb = 3 * pg.n_epis + 3 * pg.n_steps;
     for (int k = 0; k < pg.n_steps; ++k) {
       const Step& st = pg.steps[k];
       if (sv.rows_h[st.half] == 0) continue;
       uint32_t need = st.dep ? sv.base + (uint32_t)st.dep : 0u;
       if (st.b_space == SP_W) need = max(need, sv.base);
       if (need) wait_epi(&ctl->epi_done, need);
+      TRACE(tr, tb + 2 * k);
       for (int which = 0; which < 2; ++which) {
         const int space = which == 0 ? st.a_space : st.b_space;
         const uint32_t bytes = which == 0 ? st.a_bytes : st.b_bytes;
@@ -99,6 +117,7 @@ __device__ void producer_role(const TrainLaunch& t, const ProgramDev& pg, const 
         bulk_load(ring + slot * kSlotBytes, src, bytes, &ctl->full[slot]);
         ++seq;
       }
+      TRACE(tr, tb + 2 * k + 1);
     }
   }
 }
@@ -109,13 +128,20 @@ __device__ void mma_role(const TrainLaunch& t, const ProgramDev& pg, const Membe
                          Ctrl* ctl, uint32_t tmem, uint32_t& seq) {
   const uint32_t ring = tc::smem_u32(smem + kSmemRing);
   const uint32_t act0 = tc::smem_u32(smem);
+  const long long s0 = mb.steps_done;
+  const int n_steps = pg.n_steps, n_epis = pg.n_epis;
+  const Step* __restrict__ steps = pg.steps;
   for (long long i = 0; i < t.n_steps; ++i) {
-    const StepVars sv = step_vars(mb, mb.steps_done + i, i, pg.n_epis);
+    const StepVars sv = step_vars(mb, s0 + i, i, n_epis);
+    const bool half1 = sv.rows_h[1] > 0;
     wait_epi(&ctl->epi_done, sv.base);
-    for (int k = 0; k < pg.n_steps; ++k) {
-      const Step& st = pg.steps[k];
-      if (sv.rows_h[st.half] == 0) continue;
+    const bool tr = g_trace && blockIdx.x == 0 && i == g_trace_step;
+    const int tb = 3 * n_epis;
+    for (int k = 0; k < n_steps; ++k) {
+      const Step st = steps[k];
+      if (st.half && !half1) continue;
       if (st.mma_dep) wait_epi(&ctl->epi_done, sv.base + (uint32_t)st.mma_dep);
+      TRACE(tr, tb + 3 * k);
       uint32_t a_base, slot_a = 0xFFFFFFFFu;
       if (st.a_bytes) {
         slot_a = seq % kSlots;
@@ -129,20 +155,24 @@ __device__ void mma_role(const TrainLaunch& t, const ProgramDev& pg, const Membe
       tc::mbar_wait(&ctl->full[slot_b], (seq / kSlots) & 1u);
       const uint32_t b_base = ring + slot_b * kSlotBytes;
       ++seq;
+      TRACE(tr, tb + 3 * k + 1);
       tc::fence_after();
       const uint32_t idesc = tc::make_idesc(st.n, st.a_mn, st.b_mn);
       const uint32_t d = tmem + st.tmem_col;
+      uint64_t da = make_desc(a_base, st.a_lbo, st.a_sbo), db = make_desc(b_base, st.b_lbo, st.b_sbo);
+      const uint64_t a_lo = st.a_lo >> 4, b_lo = st.b_lo >> 4, a_adv = st.a_kadv >> 4, b_adv = st.b_kadv >> 4;
+      uint32_t acc = st.first ? 0u : 1u;
       for (int ks = 0; ks < st.ksteps; ++ks) {
-        const uint32_t a_hi = a_base + ks * st.a_kadv, b_hi = b_base + ks * st.b_kadv;
-        const uint64_t da_hi = make_desc(a_hi, st.a_lbo, st.a_sbo), da_lo = make_desc(a_hi + st.a_lo, st.a_lbo, st.a_sbo);
-        const uint64_t db_hi = make_desc(b_hi, st.b_lbo, st.b_sbo), db_lo = make_desc(b_hi + st.b_lo, st.b_lbo, st.b_sbo);
-        tc::mma_bf16(d, da_hi, db_hi, idesc, (st.first && ks == 0) ? 0u : 1u);
-        tc::mma_bf16(d, da_lo, db_hi, idesc, 1u);
-        tc::mma_bf16(d, da_hi, db_lo, idesc, 1u);
+        tc::mma_bf16(d, da, db, idesc, acc);
+        tc::mma_bf16(d, da + a_lo, db, idesc, 1u);
+        tc::mma_bf16(d, da, db + b_lo, idesc, 1u);
+        acc = 1u;
+        da += a_adv; db += b_adv;
       }
       tc::mma_commit(&ctl->empty[slot_b]);
       if (slot_a != 0xFFFFFFFFu) tc::mma_commit(&ctl->empty[slot_a]);
-      if (st.commit == 1 || (st.commit == 2 && sv.rows_h[1] == 0)) tc::mma_commit(&ctl->accbar[st.commit_buf]);
+      if (st.commit == 1 || (st.commit == 2 && !half1)) tc::mma_commit(&ctl->accbar[st.commit_buf]);
+      TRACE(tr, tb + 3 * k + 2);
     }
   }
 }
@@ -152,14 +182,16 @@ __device__ void mma_role(const TrainLaunch& t, const ProgramDev& pg, const Membe
 struct EpiCtx {
   const ArchDesc* a; const ProgramDev* pg; MemberDev* mb; const MemberTc* mt;
   unsigned char* smem; unsigned char* stash; float* scratch; Ctrl* ctl;
+  float* mst_p; float* mst_m; float* mst_v;     // lane-major Adam master state of the resident member
   uint32_t tmem;
   int warp, lane, row, cpart, tid;
   unsigned flags;
-  StepVars sv;
+  int rows, rows_h0, rows_h1, row0;
   long long step;           // global 0-based minibatch step of this member (Philox counter, Adam t - 1)
-  float step_size, bc2_sqrt, b1, b2, aeps;
+  float step_size, inv_bc2, b1, b2, aeps;
   float kl_acc, ll_acc;
-  float dw_acc[NMB_MAX_MOD];
+  float* dw_acc;            // [NMB_MAX_MOD] gPoE alpha-gradient partials (local array of the role)
+  __device__ __forceinline__ int rows_of(int h) const { return h ? rows_h1 : rows_h0; }
 };
 
 // 8 values -> hi / lo planes at (group g, row) of a 128-row block
@@ -171,10 +203,14 @@ __device__ __forceinline__ void put_planes(unsigned char* blk, int g, int row, c
   *reinterpret_cast<uint4*>(p + 2048) = l;
 }
 
+// torch.optim.Adam element update; sqrt / reciprocal on the SFU (2 ulp, far inside the parity budget)
 __device__ __forceinline__ float adam_update(const EpiCtx& c, float& m1, float& v1, float p0, float g) {
   m1 = c.b1 * m1 + (1.f - c.b1) * g;
   v1 = c.b2 * v1 + (1.f - c.b2) * g * g;
-  return p0 - c.step_size * (m1 / (sqrtf(v1) / c.bc2_sqrt + c.aeps));
+  float sq;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(sq) : "f"(v1));
+  const float denom = fmaf(sq, c.inv_bc2, c.aeps);
+  return p0 - c.step_size * __fdividef(m1, denom);
 }
 __device__ __forceinline__ void adam_scalar(const EpiCtx& c, long long idx, float g) {
   MemberDev& mb = *c.mb;
@@ -204,7 +240,7 @@ __device__ __forceinline__ float block_sum_epi(EpiCtx& c, float v) {
 // fp32 parameters -> BF16 hi/lo planes (member start)
 __device__ void build_weight_planes(const EpiCtx& c) {
   const ProgramDev& pg = *c.pg;
-  const float* P = c.mb->params;
+  const float* __restrict__ P = c.mb->params;
   for (int b = 0; b < pg.n_wblocks; ++b) {
     const WBlock wb = pg.wblocks[b];
     const int units = wb.R * wb.cg;
@@ -229,16 +265,59 @@ __device__ void build_weight_planes(const EpiCtx& c) {
   }
 }
 
-__device__ void epi_hidden(EpiCtx& c, const Epi& e) {
+// Row-major parameters / Adam moments of the caller <-> lane-major master state of the slot.
+// gather = true at member start, false (scatter back) at member end.
+__device__ void move_master(const EpiCtx& c, bool gather) {
+  const ProgramDev& pg = *c.pg;
+  float* ext[3] = {c.mb->params, c.mb->adam_m, c.mb->adam_v};
+  float* mst[3] = {c.mst_p, c.mst_m, c.mst_v};
+  for (int b = 0; b < pg.n_mlayers; ++b) {
+    const MLayer ml = pg.mlayers[b];
+    const int lanes = ml.kind == 0 ? ml.rows : ml.cols, other = ml.kind == 0 ? ml.cols : ml.rows;
+    const int quads = (other + 3) >> 2;
+    for (int u = c.tid; u < quads * ml.R; u += kEpiThreads) {
+      const int lane = u % ml.R, qd = u / ml.R;
+      if (lane >= lanes) continue;
+      const long long mi = ml.mst_off + ((long long)qd * ml.R + lane) * 4;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        float* vv = reinterpret_cast<float*>(&v);
+        if (gather) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int oth = 4 * qd + j;
+            if (oth < other) vv[j] = ml.kind == 0 ? ext[k][ml.p_off + (long long)lane * ml.p_ld + oth]
+                                                  : ext[k][ml.p_off + (long long)oth * ml.p_ld + lane];
+          }
+          *reinterpret_cast<float4*>(mst[k] + mi) = v;
+        } else {
+          v = *reinterpret_cast<const float4*>(mst[k] + mi);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int oth = 4 * qd + j;
+            if (oth < other) {
+              if (ml.kind == 0) ext[k][ml.p_off + (long long)lane * ml.p_ld + oth] = vv[j];
+              else ext[k][ml.p_off + (long long)oth * ml.p_ld + lane] = vv[j];
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void epi_hidden(EpiCtx& c, const Epi& e) {
   const int h = e.half;
-  const bool vr = c.row < c.sv.rows_h[h];
+  const bool vr = c.row < c.rows_of(h);
   unsigned char* act = c.smem + h * kActBytes;
   unsigned char* st = c.stash + e.stash_off;
   const int nl = c.a->non_linear;
-  for (int ch = c.cpart; ch * 16 < e.n_cols; ch += 2) {
+  const int n_cols = e.n_cols, n_mma = e.n_mma, n_valid = e.n_valid, tcol = e.tmem_col;
+  for (int ch = c.cpart; ch * 16 < n_cols; ch += kEpiParts) {
     const int col = ch * 16;
     float v[16];
-    if (col < e.n_mma) tc::tmem_ld16(taddr(c, e.tmem_col + col), v);
+    if (col < n_mma) tc::tmem_ld16(taddr(c, tcol + col), v);
     else {
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = 0.f;
@@ -248,31 +327,37 @@ __device__ void epi_hidden(EpiCtx& c, const Epi& e) {
       const int cc = col + j;
       float x = v[j];
       x = (nl && x <= 0.f) ? kSlope * x : x;
-      v[j] = !vr ? 0.f : (cc < e.n_valid ? x : (cc == e.n_valid ? 1.f : 0.f));
+      v[j] = !vr ? 0.f : (cc < n_valid ? x : (cc == n_valid ? 1.f : 0.f));
     }
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
       float x[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) x[j] = v[8 * q + j];
-      put_planes(act, 2 * ch + q, c.row, x);
-      put_planes(st, 2 * ch + q, c.row, x);
+      uint4 hh, ll;
+      tc::split8(x, hh, ll);
+      const long long off = (long long)(2 * ch + q) * 4096 + c.row * 16;
+      *reinterpret_cast<uint4*>(act + off) = hh;
+      *reinterpret_cast<uint4*>(act + off + 2048) = ll;
+      *reinterpret_cast<uint4*>(st + off) = hh;
+      *reinterpret_cast<uint4*>(st + off + 2048) = ll;
     }
   }
 }
 
-__device__ void epi_head(EpiCtx& c, const Epi& e) {
+__device__ __forceinline__ void epi_head(EpiCtx& c, const Epi& e) {
   const int h = e.half;
-  const bool vr = c.row < c.sv.rows_h[h];
+  const bool vr = c.row < c.rows_of(h);
   const int ld = c.pg->lay.ld_mulv;
   float* dst = reinterpret_cast<float*>(c.stash + c.pg->lay.mulv[e.mod]) + (long long)(128 * h + c.row) * ld;
-  for (int ch = c.cpart; ch * 16 < e.n_cols; ch += 2) {
+  const int n_cols = e.n_cols, n_valid = e.n_valid, tcol = e.tmem_col;
+  for (int ch = c.cpart; ch * 16 < n_cols; ch += kEpiParts) {
     float v[16];
     __syncwarp();
-    tc::tmem_ld16(taddr(c, e.tmem_col + ch * 16), v);
+    tc::tmem_ld16(taddr(c, tcol + ch * 16), v);
     if (vr) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) if (ch * 16 + j < e.n_valid) dst[ch * 16 + j] = v[j];
+      for (int j = 0; j < 16; ++j) if (ch * 16 + j < n_valid) dst[ch * 16 + j] = v[j];
     }
   }
 }
@@ -281,7 +366,7 @@ __device__ void epi_head(EpiCtx& c, const Epi& e) {
 __device__ void epi_latent(EpiCtx& c, const Epi& e, const float* eps_src) {
   const ArchDesc& a = *c.a;
   const Layout& lay = c.pg->lay;
-  const int h = e.half, Z = a.Z, M = a.M, rows = c.sv.rows_h[h];
+  const int h = e.half, Z = a.Z, M = a.M, rows = c.rows_of(h);
   float* S = c.scratch;
   float* zbuf = reinterpret_cast<float*>(c.stash + lay.zbuf);
   float w[NMB_MAX_MOD];
@@ -297,12 +382,18 @@ __device__ void epi_latent(EpiCtx& c, const Epi& e, const float* eps_src) {
       if (el >= n) break;
       const int b = el / Z, z = el - b * Z;
       const int gb = 128 * h + b;
-      float mu[NMB_MAX_MOD], lv[NMB_MAX_MOD];
-      for (int m = 0; m < M; ++m) {
-        const float* hd = reinterpret_cast<const float*>(c.stash + lay.mulv[m]) + (long long)gb * lay.ld_mulv;
-        mu[m] = hd[z]; lv[m] = hd[Z + z];
+      Fused f;
+      if (M == 1) {
+        const float* hd = reinterpret_cast<const float*>(c.stash + lay.mulv[0]) + (long long)gb * lay.ld_mulv;
+        f.mu = hd[z]; f.lv = hd[Z + z];
+      } else {
+        float mu[NMB_MAX_MOD], lv[NMB_MAX_MOD];
+        for (int m = 0; m < M; ++m) {
+          const float* hd = reinterpret_cast<const float*>(c.stash + lay.mulv[m]) + (long long)gb * lay.ld_mulv;
+          mu[m] = hd[z]; lv[m] = hd[Z + z];
+        }
+        f = fuse_forward(mu, lv, M, a.combine, w);
       }
-      const Fused f = fuse_forward(mu, lv, M, a.combine, w);
       const float eps = eps_src ? eps_src[gb * Z + z] : nrm[j];
       S[a.s_mub + gb * Z + z] = f.mu; S[a.s_lvb + gb * Z + z] = f.lv; S[a.s_eps + gb * Z + z] = eps;
       zbuf[gb * Z + z] = f.mu + eps * expf(0.5f * f.lv);
@@ -314,7 +405,8 @@ __device__ void epi_latent(EpiCtx& c, const Epi& e, const float* eps_src) {
   for (int m = 0; m < M; ++m) {
     const ModDesc& q = a.mod[m];
     unsigned char* st = c.stash + lay.g0[m][h];
-    const float* xc = c.mb->xc[m] + (long long)(c.sv.row0 + 128 * h) * q.ldx + q.D;
+    const float* xc = c.mb->xc[m] + (long long)(c.row0 + 128 * h) * q.ldx + q.D;
+    const int ldx = q.ldx, C = a.C;
     for (int u = c.tid; u < 128 * cg; u += kEpiThreads) {
       const int r = u & 127, g = u >> 7;
       float x[8];
@@ -324,8 +416,8 @@ __device__ void epi_latent(EpiCtx& c, const Epi& e, const float* eps_src) {
         float val = 0.f;
         if (r < rows) {
           if (cc < Z) val = zbuf[(128 * h + r) * Z + cc];
-          else if (cc < Z + a.C) val = xc[(long long)r * q.ldx + (cc - Z)];
-          else if (cc == Z + a.C) val = 1.f;
+          else if (cc < Z + C) val = xc[(long long)r * ldx + (cc - Z)];
+          else if (cc == Z + C) val = 1.f;
         }
         x[j] = val;
       }
@@ -335,39 +427,41 @@ __device__ void epi_latent(EpiCtx& c, const Epi& e, const float* eps_src) {
   }
 }
 
-__device__ void epi_copy(EpiCtx& c, const Epi& e) {
+__device__ __forceinline__ void epi_copy(EpiCtx& c, const Epi& e) {
   const uint4* src = reinterpret_cast<const uint4*>(c.stash + e.src_off);
   uint4* dst = reinterpret_cast<uint4*>(c.smem + e.half * kActBytes);
   const int n = e.src_cg * 256;       // 16-byte units
   for (int u = c.tid; u < n; u += kEpiThreads) dst[u] = src[u];
 }
 
-__device__ void epi_recon(EpiCtx& c, const Epi& e) {
+__device__ __forceinline__ void epi_recon(EpiCtx& c, const Epi& e) {
   const ArchDesc& a = *c.a;
   const ModDesc& q = a.mod[e.mod];
   const Layout& lay = c.pg->lay;
   const int h = e.half;
-  const bool vr = c.row < c.sv.rows_h[h];
+  const bool vr = c.row < c.rows_of(h);
   const int gauss = a.loss_kind == NMB_LOSS_GAUSS_LL;
-  const float inv_rows = 1.f / c.sv.rows;
+  const float inv_rows = 1.f / c.rows;
   const float inv_rows_d = inv_rows / q.D;
   const float ll_scale = gauss ? inv_rows : inv_rows_d;
   const float* P = c.mb->params;
   unsigned char* st = c.stash + e.stash_off;
-  const int grow = c.sv.row0 + 128 * h + c.row;
+  const int grow = c.row0 + 128 * h + c.row;
   const float* xrow = c.mb->xc[e.mod] + (long long)grow * q.ldx;
   float* keep = (c.flags & NMB_TRAIN_KEEP_ACTS) ? c.scratch + q.s_xr + (long long)(128 * h + c.row) * q.ld_xh : nullptr;
   float* lampart = reinterpret_cast<float*>(c.stash + lay.lampart[e.mod]) + (long long)(h * 4 + (c.warp & 3)) * round4(q.D);
-  for (int ch = c.cpart; ch < 4; ch += 2) {
-    const int col = ch * 16, gc = e.col0 + col;
-    int nv = e.n_valid - col; nv = nv < 0 ? 0 : (nv > 16 ? 16 : nv);
+  const int n_valid = e.n_valid, col0 = e.col0, tcol = e.tmem_col;
+  const long long lam_off = q.lam_off;
+  for (int ch = c.cpart; ch < 4; ch += kEpiParts) {
+    const int col = ch * 16, gc = col0 + col;
+    int nv = n_valid - col; nv = nv < 0 ? 0 : (nv > 16 ? 16 : nv);
     float v[16], xt[16], l[16], gr[16], qv[16];
-    __syncwarp();
-    tc::tmem_ld16(taddr(c, e.tmem_col + col), v);
 #pragma unroll
     for (int j = 0; j < 16; ++j) { xt[j] = 0.f; l[j] = 0.f; }
     if (vr && nv > 0) load16(xrow + gc, nv, 0.f, xt);
-    if (gauss && nv > 0) load16(P + q.lam_off + gc, nv, 0.f, l);
+    if (gauss && nv > 0) load16(P + lam_off + gc, nv, 0.f, l);
+    __syncwarp();
+    tc::tmem_ld16(taddr(c, tcol + col), v);
     float ll = 0.f;
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
@@ -397,21 +491,42 @@ __device__ void epi_recon(EpiCtx& c, const Epi& e) {
     }
     if (keep && vr && nv > 0) store16(keep + gc, nv, v);
     if (gauss) {
+      // column sums over the 32 rows of this warp: 16 values -> lanes 0..15 in 16+8+4+2+1 shuffles
+      float s8[8], s4[4], s2[2], s1;
+      const bool up16 = c.lane & 16, up8 = c.lane & 8, up4 = c.lane & 4, up2 = c.lane & 2;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float s = warp_sum(qv[j]);
-        if (c.lane == j && j < nv) lampart[gc + j] = s;
+      for (int j = 0; j < 8; ++j) {
+        const float keepv = up16 ? qv[j + 8] : qv[j], send = up16 ? qv[j] : qv[j + 8];
+        s8[j] = keepv + __shfl_xor_sync(0xffffffffu, send, 16);
       }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float keepv = up8 ? s8[j + 4] : s8[j], send = up8 ? s8[j] : s8[j + 4];
+        s4[j] = keepv + __shfl_xor_sync(0xffffffffu, send, 8);
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const float keepv = up4 ? s4[j + 2] : s4[j], send = up4 ? s4[j] : s4[j + 2];
+        s2[j] = keepv + __shfl_xor_sync(0xffffffffu, send, 4);
+      }
+      {
+        const float keepv = up2 ? s2[1] : s2[0], send = up2 ? s2[0] : s2[1];
+        s1 = keepv + __shfl_xor_sync(0xffffffffu, send, 2);
+      }
+      s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+      // lane holds column: bit4 -> +8, bit3 -> +4, bit2 -> +2, bit1 -> +1
+      const int cj = ((c.lane >> 4) & 1) * 8 + ((c.lane >> 3) & 1) * 4 + ((c.lane >> 2) & 1) * 2 + ((c.lane >> 1) & 1);
+      if (!(c.lane & 1) && cj < nv) lampart[gc + cj] = s1;
     }
   }
 }
 
-__device__ void epi_lam(EpiCtx& c, const Epi& e) {
+__device__ __forceinline__ void epi_lam(EpiCtx& c, const Epi& e) {
   const ModDesc& q = c.a->mod[e.mod];
   const float* part = reinterpret_cast<const float*>(c.stash + c.pg->lay.lampart[e.mod]);
   const int ld = round4(q.D);
-  const int np = c.sv.rows_h[1] > 0 ? 8 : 4;
-  const float inv_rows = 1.f / c.sv.rows;
+  const int np = c.rows_h1 > 0 ? 8 : 4;
+  const float inv_rows = 1.f / c.rows;
   for (int n = c.tid; n < q.D; n += kEpiThreads) {
     float s = 0.f;
     for (int k = 0; k < np; ++k) s += part[k * ld + n];
@@ -419,13 +534,14 @@ __device__ void epi_lam(EpiCtx& c, const Epi& e) {
   }
 }
 
-__device__ void epi_dgrad(EpiCtx& c, const Epi& e) {
+__device__ __forceinline__ void epi_dgrad(EpiCtx& c, const Epi& e) {
   const int h = e.half;
-  const bool vr = c.row < c.sv.rows_h[h];
+  const bool vr = c.row < c.rows_of(h);
   unsigned char* act = c.smem + h * kActBytes;
   const unsigned char* sg = c.stash + e.src_off;
   const int nl = c.a->non_linear;
-  for (int ch = c.cpart; ch * 16 < e.n_cols; ch += 2) {
+  const int n_cols = e.n_cols, n_mma = e.n_mma, n_valid = e.n_valid, tcol = e.tmem_col;
+  for (int ch = c.cpart; ch * 16 < n_cols; ch += kEpiParts) {
     const int col = ch * 16;
     uint4 s0 = make_uint4(0, 0, 0, 0), s1 = s0;
     if (nl) {
@@ -433,7 +549,7 @@ __device__ void epi_dgrad(EpiCtx& c, const Epi& e) {
       s1 = *reinterpret_cast<const uint4*>(sg + (long long)(2 * ch + 1) * 4096 + c.row * 16);
     }
     float v[16];
-    if (col < e.n_mma) tc::tmem_ld16(taddr(c, e.tmem_col + col), v);
+    if (col < n_mma) tc::tmem_ld16(taddr(c, tcol + col), v);
     else {
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = 0.f;
@@ -444,7 +560,7 @@ __device__ void epi_dgrad(EpiCtx& c, const Epi& e) {
       const uint32_t hb = (sw[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu;      // bf16 bits of the stored activation
       const bool nonpos = nl && ((hb & 0x8000u) || (hb & 0x7FFFu) == 0u);
       const float x = nonpos ? kSlope * v[j] : v[j];
-      v[j] = (vr && col + j < e.n_valid) ? x : 0.f;
+      v[j] = (vr && col + j < n_valid) ? x : 0.f;
     }
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
@@ -456,19 +572,20 @@ __device__ void epi_dgrad(EpiCtx& c, const Epi& e) {
   }
 }
 
-__device__ void epi_dz(EpiCtx& c, const Epi& e) {
+__device__ __forceinline__ void epi_dz(EpiCtx& c, const Epi& e) {
   const int h = e.half, Z = c.a->Z;
-  const bool vr = c.row < c.sv.rows_h[h];
+  const bool vr = c.row < c.rows_of(h);
   float* dz = reinterpret_cast<float*>(c.stash + c.pg->lay.dz) + (long long)(128 * h + c.row) * Z;
-  for (int ch = c.cpart; ch * 16 < e.n_mma; ch += 2) {
+  const int n_mma = e.n_mma, tcol = e.tmem_col, acc = e.mod > 0;
+  for (int ch = c.cpart; ch * 16 < n_mma; ch += kEpiParts) {
     float v[16];
     __syncwarp();
-    tc::tmem_ld16(taddr(c, e.tmem_col + ch * 16), v);
+    tc::tmem_ld16(taddr(c, tcol + ch * 16), v);
     if (vr) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const int cc = ch * 16 + j;
-        if (cc < Z) dz[cc] = e.mod > 0 ? dz[cc] + v[j] : v[j];
+        if (cc < Z) dz[cc] = acc ? dz[cc] + v[j] : v[j];
       }
     }
   }
@@ -478,11 +595,11 @@ __device__ void epi_dz(EpiCtx& c, const Epi& e) {
 __device__ void epi_latent_bwd(EpiCtx& c, const Epi& e) {
   const ArchDesc& a = *c.a;
   const Layout& lay = c.pg->lay;
-  const int h = e.half, Z = a.Z, M = a.M, rows = c.sv.rows_h[h];
+  const int h = e.half, Z = a.Z, M = a.M, rows = c.rows_of(h);
   const float* S = c.scratch;
   const float* P = c.mb->params;
   const float* dzb = reinterpret_cast<const float*>(c.stash + lay.dz);
-  const float inv_rows = 1.f / c.sv.rows;
+  const float inv_rows = 1.f / c.rows;
   float w[NMB_MAX_MOD];
   const bool gpoe = M > 1 && a.combine == NMB_COMBINE_GPOE;
   if (gpoe) softmax_alpha(P + a.alpha_off, M, w);
@@ -493,16 +610,21 @@ __device__ void epi_latent_bwd(EpiCtx& c, const Epi& e) {
     const float sd = expf(0.5f * lvb);
     const float dmu_bar = dz + M * mub * inv_rows;
     const float dlv_bar = dz * eps * sd * 0.5f + M * (expf(lvb) - 1.f) * 0.5f * inv_rows;
-    float mu[NMB_MAX_MOD], lv[NMB_MAX_MOD], dmu[NMB_MAX_MOD], dlv[NMB_MAX_MOD], dw[NMB_MAX_MOD];
-    for (int m = 0; m < M; ++m) {
-      const float* hd = reinterpret_cast<const float*>(c.stash + lay.mulv[m]) + (long long)(128 * h + b) * lay.ld_mulv;
-      mu[m] = hd[z]; lv[m] = hd[Z + z];
-    }
-    fuse_backward(mu, lv, M, a.combine, w, dmu_bar, dlv_bar, dmu, dlv, gpoe ? dw : nullptr);
-    for (int m = 0; m < M; ++m) {
-      float* hd = reinterpret_cast<float*>(c.stash + lay.mulv[m]) + (long long)(128 * h + b) * lay.ld_mulv;
-      hd[z] = dmu[m]; hd[Z + z] = dlv[m];
-      if (gpoe) c.dw_acc[m] += dw[m];
+    if (M == 1) {
+      float* hd = reinterpret_cast<float*>(c.stash + lay.mulv[0]) + (long long)(128 * h + b) * lay.ld_mulv;
+      hd[z] = dmu_bar; hd[Z + z] = dlv_bar;
+    } else {
+      float mu[NMB_MAX_MOD], lv[NMB_MAX_MOD], dmu[NMB_MAX_MOD], dlv[NMB_MAX_MOD], dw[NMB_MAX_MOD];
+      for (int m = 0; m < M; ++m) {
+        const float* hd = reinterpret_cast<const float*>(c.stash + lay.mulv[m]) + (long long)(128 * h + b) * lay.ld_mulv;
+        mu[m] = hd[z]; lv[m] = hd[Z + z];
+      }
+      fuse_backward(mu, lv, M, a.combine, w, dmu_bar, dlv_bar, dmu, dlv, gpoe ? dw : nullptr);
+      for (int m = 0; m < M; ++m) {
+        float* hd = reinterpret_cast<float*>(c.stash + lay.mulv[m]) + (long long)(128 * h + b) * lay.ld_mulv;
+        hd[z] = dmu[m]; hd[Z + z] = dlv[m];
+        if (gpoe) c.dw_acc[m] += dw[m];
+      }
     }
   }
   epi_bar();
@@ -510,13 +632,14 @@ __device__ void epi_latent_bwd(EpiCtx& c, const Epi& e) {
   for (int m = 0; m < M; ++m) {
     const float* hd0 = reinterpret_cast<const float*>(c.stash + lay.mulv[m]) + (long long)(128 * h) * lay.ld_mulv;
     unsigned char* st = c.stash + lay.dmulv[m][h];
+    const int ld = lay.ld_mulv;
     for (int u = c.tid; u < 128 * cg; u += kEpiThreads) {
       const int r = u & 127, g = u >> 7;
       float x[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int cc = 8 * g + j;
-        x[j] = (r < rows && cc < 2 * Z) ? hd0[(long long)r * lay.ld_mulv + cc] : 0.f;
+        x[j] = (r < rows && cc < 2 * Z) ? hd0[(long long)r * ld + cc] : 0.f;
       }
       if (m == 0) put_planes(c.smem + h * kActBytes, g, r, x);
       else put_planes(st, g, r, x);
@@ -524,86 +647,121 @@ __device__ void epi_latent_bwd(EpiCtx& c, const Epi& e) {
   }
 }
 
-// weight gradient (lane = output row) fused with Adam; rewrites the BF16 planes of the layer
-__device__ void epi_wgrad(EpiCtx& c, const Epi& e) {
+// weight gradient (lane = output row) fused with Adam on the lane-major master state; rewrites the
+// BF16 planes of the layer
+__device__ __forceinline__ void epi_wgrad(EpiCtx& c, const Epi& e) {
   MemberDev& mb = *c.mb;
   const int o = c.row;
   const bool vo = o < e.p_rows;
-  unsigned char* wp = c.mt->wplanes + e.wp_off;
-  const int wp_cg = round16(e.p_cols) / 8;
-  for (int ch = c.cpart; ch * 16 < e.n_mma; ch += 2) {
-    const int col = e.col0 + ch * 16;
-    float g[16];
+  const int wp_R = e.wp_R, p_ld = e.p_ld, p_cols = e.p_cols, n_mma = e.n_mma, col0 = e.col0, tcol = e.tmem_col;
+  const int R4 = e.mst_R * 4;
+  unsigned char* wp = c.mt->wplanes + e.wp_off + o * 16;
+  const long long rowbase = e.p_off + (long long)o * p_ld;
+  const long long mbase = e.mst_off + (long long)o * 4;
+  float* __restrict__ Pp = c.mst_p; float* __restrict__ Pm = c.mst_m; float* __restrict__ Pv = c.mst_v;
+  const bool adam = !(c.flags & NMB_TRAIN_NO_ADAM), wg = c.flags & NMB_TRAIN_WRITE_GRADS;
+  for (int ch = c.cpart; ch * 8 < n_mma; ch += kEpiParts) {        // 8 columns (one plane group) at a time
+    const int col = col0 + ch * 8;
+    const bool on = vo && col < p_cols;
+    const bool full = col + 4 < p_cols;
+    const long long mi = mbase + (long long)(col >> 2) * R4;
+    float g[8];
+    float4 pa, pb, ma, mb4, va, vb;
+    pa = pb = ma = mb4 = va = vb = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (on && adam) {            // state loads first: they overlap the TMEM read
+      pa = *reinterpret_cast<const float4*>(Pp + mi); ma = *reinterpret_cast<const float4*>(Pm + mi);
+      va = *reinterpret_cast<const float4*>(Pv + mi);
+      if (full) {
+        pb = *reinterpret_cast<const float4*>(Pp + mi + R4); mb4 = *reinterpret_cast<const float4*>(Pm + mi + R4);
+        vb = *reinterpret_cast<const float4*>(Pv + mi + R4);
+      }
+    }
     __syncwarp();
-    tc::tmem_ld16(taddr(c, e.tmem_col + ch * 16), g);
-    int nv = e.p_ld - col; nv = nv < 0 ? 0 : (nv > 16 ? 16 : nv);
-    if (vo && nv > 0) {
-      const long long base = e.p_off + (long long)o * e.p_ld + col;
-      if (c.flags & NMB_TRAIN_WRITE_GRADS) store16(mb.grads + base, nv, g);
-      if (!(c.flags & NMB_TRAIN_NO_ADAM)) {
-        float p0[16], m1[16], v1[16];
-        load16(mb.params + base, nv, 0.f, p0);
-        load16(mb.adam_m + base, nv, 0.f, m1);
-        load16(mb.adam_v + base, nv, 0.f, v1);
+    tc::tmem_ld8(taddr(c, tcol + ch * 8), g);
+    if (on) {
+      if (wg) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) p0[j] = adam_update(c, m1[j], v1[j], p0[j], g[j]);
-        store16(mb.adam_m + base, nv, m1);
-        store16(mb.adam_v + base, nv, v1);
-        store16(mb.params + base, nv, p0);
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const int gi = col / 8 + q;
-          if (gi < wp_cg) {
-            float x[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) x[j] = (col + 8 * q + j < e.p_cols) ? p0[8 * q + j] : 0.f;
-            uint4 hh, ll;
-            tc::split8(x, hh, ll);
-            unsigned char* p = wp + (long long)gi * 32 * e.wp_R + o * 16;
-            *reinterpret_cast<uint4*>(p) = hh;
-            *reinterpret_cast<uint4*>(p + 16 * e.wp_R) = ll;
-          }
+        for (int j = 0; j < 8; ++j) if (col + j < p_cols) mb.grads[rowbase + col + j] = g[j];
+      }
+      if (adam) {
+        float x[8];
+        x[0] = adam_update(c, ma.x, va.x, pa.x, g[0]); x[1] = adam_update(c, ma.y, va.y, pa.y, g[1]);
+        x[2] = adam_update(c, ma.z, va.z, pa.z, g[2]); x[3] = adam_update(c, ma.w, va.w, pa.w, g[3]);
+        x[4] = adam_update(c, mb4.x, vb.x, pb.x, g[4]); x[5] = adam_update(c, mb4.y, vb.y, pb.y, g[5]);
+        x[6] = adam_update(c, mb4.z, vb.z, pb.z, g[6]); x[7] = adam_update(c, mb4.w, vb.w, pb.w, g[7]);
+        *reinterpret_cast<float4*>(Pm + mi) = ma; *reinterpret_cast<float4*>(Pv + mi) = va;
+        *reinterpret_cast<float4*>(Pp + mi) = make_float4(x[0], x[1], x[2], x[3]);
+        if (full) {
+          *reinterpret_cast<float4*>(Pm + mi + R4) = mb4; *reinterpret_cast<float4*>(Pv + mi + R4) = vb;
+          *reinterpret_cast<float4*>(Pp + mi + R4) = make_float4(x[4], x[5], x[6], x[7]);
         }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = (col + j < p_cols) ? x[j] : 0.f;
+        uint4 hh, ll;
+        tc::split8(x, hh, ll);
+        unsigned char* p = wp + (long long)(col >> 3) * 32 * wp_R;
+        *reinterpret_cast<uint4*>(p) = hh;
+        *reinterpret_cast<uint4*>(p + 16 * wp_R) = ll;
       }
     }
   }
 }
 
 // transposed weight gradient of decoder_mean_layer: lane = input index i, columns = output rows o
-__device__ void epi_wgrad_t(EpiCtx& c, const Epi& e) {
+__device__ __forceinline__ void epi_wgrad_t(EpiCtx& c, const Epi& e) {
   MemberDev& mb = *c.mb;
   const int i = c.row;
   const bool vi = i < e.p_cols;
-  unsigned char* wp = c.mt->wplanes + e.wp_off;
+  const int p_ld = e.p_ld, p_rows = e.p_rows, n_mma = e.n_mma, col0 = e.col0, tcol = e.tmem_col;
+  const int R4 = e.mst_R * 4;
+  unsigned char* wp = c.mt->wplanes + e.wp_off + (long long)(i >> 3) * 2048 + (i & 7) * 2;
   const long long blk_bytes = (long long)e.src_cg * 2048;     // one 64-row planes block
-  for (int ch = c.cpart; ch * 16 < e.n_mma; ch += 2) {
-    float g[16];
+  float* __restrict__ Pp = c.mst_p; float* __restrict__ Pm = c.mst_m; float* __restrict__ Pv = c.mst_v;
+  const bool adam = !(c.flags & NMB_TRAIN_NO_ADAM), wg = c.flags & NMB_TRAIN_WRITE_GRADS;
+  const long long colbase = e.p_off + i;
+  const long long mbase = e.mst_off + (long long)i * 4;
+  for (int ch = c.cpart; ch * 8 < n_mma; ch += kEpiParts) {
+    const int o0 = col0 + ch * 8;
+    const bool on = vi && o0 < p_rows;
+    const bool full = o0 + 4 < p_rows;
+    const long long mi = mbase + (long long)(o0 >> 2) * R4;
+    float g[8];
+    float4 pa, pb, ma, mb4, va, vb;
+    pa = pb = ma = mb4 = va = vb = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (on && adam) {
+      pa = *reinterpret_cast<const float4*>(Pp + mi); ma = *reinterpret_cast<const float4*>(Pm + mi);
+      va = *reinterpret_cast<const float4*>(Pv + mi);
+      if (full) {
+        pb = *reinterpret_cast<const float4*>(Pp + mi + R4); mb4 = *reinterpret_cast<const float4*>(Pm + mi + R4);
+        vb = *reinterpret_cast<const float4*>(Pv + mi + R4);
+      }
+    }
     __syncwarp();
-    tc::tmem_ld16(taddr(c, e.tmem_col + ch * 16), g);
-    if (vi) {
-      const int o0 = e.col0 + ch * 16;
-      float p0[16], m1[16], v1[16];
-      const bool adam = !(c.flags & NMB_TRAIN_NO_ADAM);
+    tc::tmem_ld8(taddr(c, tcol + ch * 8), g);
+    if (on) {
+      if (wg) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const long long idx = e.p_off + (long long)(o0 + j) * e.p_ld + i;
-        const bool ok = o0 + j < e.p_rows;
-        if (ok && (c.flags & NMB_TRAIN_WRITE_GRADS)) mb.grads[idx] = g[j];
-        p0[j] = (ok && adam) ? mb.params[idx] : 0.f;
-        m1[j] = (ok && adam) ? mb.adam_m[idx] : 0.f;
-        v1[j] = (ok && adam) ? mb.adam_v[idx] : 0.f;
+        for (int j = 0; j < 8; ++j) if (o0 + j < p_rows) mb.grads[colbase + (long long)(o0 + j) * p_ld] = g[j];
       }
       if (adam) {
+        float x[8];
+        x[0] = adam_update(c, ma.x, va.x, pa.x, g[0]); x[1] = adam_update(c, ma.y, va.y, pa.y, g[1]);
+        x[2] = adam_update(c, ma.z, va.z, pa.z, g[2]); x[3] = adam_update(c, ma.w, va.w, pa.w, g[3]);
+        x[4] = adam_update(c, mb4.x, vb.x, pb.x, g[4]); x[5] = adam_update(c, mb4.y, vb.y, pb.y, g[5]);
+        x[6] = adam_update(c, mb4.z, vb.z, pb.z, g[6]); x[7] = adam_update(c, mb4.w, vb.w, pb.w, g[7]);
+        *reinterpret_cast<float4*>(Pm + mi) = ma; *reinterpret_cast<float4*>(Pv + mi) = va;
+        *reinterpret_cast<float4*>(Pp + mi) = make_float4(x[0], x[1], x[2], x[3]);
+        if (full) {
+          *reinterpret_cast<float4*>(Pm + mi + R4) = mb4; *reinterpret_cast<float4*>(Pv + mi + R4) = vb;
+          *reinterpret_cast<float4*>(Pp + mi + R4) = make_float4(x[4], x[5], x[6], x[7]);
+        }
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
+        for (int j = 0; j < 8; ++j) {
           const int o = o0 + j;
-          if (o < e.p_rows) {
-            const long long idx = e.p_off + (long long)o * e.p_ld + i;
-            const float p1 = adam_update(c, m1[j], v1[j], p0[j], g[j]);
-            mb.adam_m[idx] = m1[j]; mb.adam_v[idx] = v1[j]; mb.params[idx] = p1;
-            const __nv_bfloat16 hb = __float2bfloat16_rn(p1);
-            const __nv_bfloat16 lb = __float2bfloat16_rn(p1 - __bfloat162float(hb));
-            unsigned char* p = wp + (long long)(o >> 6) * blk_bytes + (long long)(i >> 3) * 2048 + (o & 63) * 16 + (i & 7) * 2;
+          if (o < p_rows) {
+            const __nv_bfloat16 hb = __float2bfloat16_rn(x[j]);
+            const __nv_bfloat16 lb = __float2bfloat16_rn(x[j] - __bfloat162float(hb));
+            unsigned char* p = wp + (long long)(o >> 6) * blk_bytes + (o & 63) * 16;
             *reinterpret_cast<__nv_bfloat16*>(p) = hb;
             *reinterpret_cast<__nv_bfloat16*>(p + 1024) = lb;
           }
@@ -616,7 +774,7 @@ __device__ void epi_wgrad_t(EpiCtx& c, const Epi& e) {
 __device__ void epi_step_end(EpiCtx& c, float* loss_out) {
   const ArchDesc& a = *c.a;
   const int M = a.M;
-  const float kl = block_sum_epi(c, c.kl_acc) / c.sv.rows;
+  const float kl = block_sum_epi(c, c.kl_acc) / c.rows;
   const float ll = block_sum_epi(c, c.ll_acc);
   if (loss_out && c.tid == 0) { loss_out[0] = M * kl - ll; loss_out[1] = M * kl; loss_out[2] = ll; }
   if (M > 1 && a.combine == NMB_COMBINE_GPOE) {
@@ -638,53 +796,69 @@ __device__ void epilogue_role(const TrainLaunch& t, int mi, EpiCtx& c, uint32_t&
   const ProgramDev& pg = *c.pg;
   MemberDev& mb = *c.mb;
   c.kl_acc = 0.f; c.ll_acc = 0.f;
-  for (int m = 0; m < NMB_MAX_MOD; ++m) c.dw_acc[m] = 0.f;
+  float dw_acc[NMB_MAX_MOD];
+  for (int m = 0; m < NMB_MAX_MOD; ++m) dw_acc[m] = 0.f;
+  c.dw_acc = dw_acc;
   build_weight_planes(c);
+  const bool adam_on = !(c.flags & NMB_TRAIN_NO_ADAM);
+  if (adam_on) move_master(c, true);
   fence_async_all();
   epi_bar();
   if (c.tid == 0) st_release(&c.ctl->epi_done, 1u);
   const long long s0 = mb.steps_done;
+  const int n_epis = pg.n_epis;
+  const Epi* __restrict__ epis = pg.epis;
   for (long long i = 0; i < t.n_steps; ++i) {
     const long long s = s0 + i;
-    c.sv = step_vars(mb, s, i, pg.n_epis);
+    const StepVars sv = step_vars(mb, s, i, n_epis);
+    c.rows = sv.rows; c.rows_h0 = sv.rows_h[0]; c.rows_h1 = sv.rows_h[1]; c.row0 = sv.row0;
     c.step = s;
     {
       const double tt = (double)(s + 1);
       const float lr = mb.lr_steps ? mb.lr_steps[s] : mb.lr;
       c.step_size = (float)((double)lr / (1.0 - pow((double)mb.beta1, tt)));
-      c.bc2_sqrt = (float)sqrt(1.0 - pow((double)mb.beta2, tt));
+      c.inv_bc2 = (float)(1.0 / sqrt(1.0 - pow((double)mb.beta2, tt)));
     }
     const float* eps = t.eps_override ? t.eps_override + ((long long)mi * t.n_steps + i) * mb.batch * c.a->Z : nullptr;
     float* lo = t.loss_out ? t.loss_out + ((long long)mi * t.n_steps + i) * 3 : nullptr;
-    for (int k = 0; k < pg.n_epis; ++k) {
-      const Epi& e = pg.epis[k];
-      const bool active = e.half == 2 ? true : c.sv.rows_h[e.half] > 0;
-      if (!active) continue;
+    for (int k = 0; k < n_epis; ++k) {
+      const Epi e = epis[k];
+      if (e.half == 1 && c.rows_h1 == 0) continue;
+      const bool tr = g_trace && blockIdx.x == 0 && i == g_trace_step && c.tid == 0;
+      TRACE(tr, 3 * k);
       if (e.buf >= 0) {
         tc::mbar_wait(&c.ctl->accbar[e.buf], (acc_par >> e.buf) & 1u);
         acc_par ^= 1u << e.buf;
         tc::fence_after();
       }
+      TRACE(tr, 3 * k + 1);
+      // proxy fences: ACT[h] (shared memory, read by the next MMAs) per item; global data read by the TMA
+      // (stash blocks, weight planes) only at EK_FENCE / EK_STEP_END, so the stores drain in the background
+      int fence = 0;              // 1 = shared memory, 2 = everything
       switch (e.kind) {
-        case EK_HIDDEN: epi_hidden(c, e); break;
+        case EK_HIDDEN: epi_hidden(c, e); fence = 1; break;
         case EK_HEAD: epi_head(c, e); break;
-        case EK_LATENT: epi_latent(c, e, eps); break;
-        case EK_COPY: epi_copy(c, e); break;
+        case EK_LATENT: epi_latent(c, e, eps); fence = 1; break;
+        case EK_COPY: epi_copy(c, e); fence = 1; break;
         case EK_RECON: epi_recon(c, e); break;
         case EK_LAM: epi_lam(c, e); break;
-        case EK_DGRAD: epi_dgrad(c, e); break;
+        case EK_DGRAD: epi_dgrad(c, e); fence = 1; break;
         case EK_DZ: epi_dz(c, e); break;
-        case EK_LATENT_BWD: epi_latent_bwd(c, e); break;
+        case EK_LATENT_BWD: epi_latent_bwd(c, e); fence = 1; break;
         case EK_WGRAD: epi_wgrad(c, e); break;
         case EK_WGRAD_T: epi_wgrad_t(c, e); break;
-        default: epi_step_end(c, lo); break;
+        case EK_FENCE: fence = 2; break;
+        default: epi_step_end(c, lo); fence = 2; break;
       }
-      tc::fence_before();
-      fence_async_all();
+      if (e.buf >= 0) tc::fence_before();
+      if (fence == 1) fence_async_smem();
+      else if (fence == 2) { __threadfence(); fence_async_all(); }
       epi_bar();
-      if (c.tid == 0) st_release(&c.ctl->epi_done, c.sv.base + (uint32_t)k + 1u);
+      if (c.tid == 0) st_release(&c.ctl->epi_done, sv.base + (uint32_t)k + 1u);
+      TRACE(tr, 3 * k + 2);
     }
   }
+  if (adam_on) move_master(c, false);
 }
 
 struct LaunchP {
@@ -693,6 +867,8 @@ struct LaunchP {
   const MemberTc* mtc;
   unsigned char* stash;
   long long stash_bytes;
+  float* master;            // per slot: 3 x master_floats (p, m, v)
+  long long master_floats;
 };
 
 __global__ void __launch_bounds__(kThreadsP, 1) train_tcp_kernel(LaunchP L) {
@@ -732,6 +908,8 @@ __global__ void __launch_bounds__(kThreadsP, 1) train_tcp_kernel(LaunchP L) {
       EpiCtx c;
       c.a = &t.archs[mb.arch_idx]; c.pg = &pg; c.mb = &mb; c.mt = &mt;
       c.smem = smem; c.stash = stash; c.scratch = t.scratch + (long long)blockIdx.x * t.slot_floats; c.ctl = ctl;
+      c.mst_p = L.master + (long long)blockIdx.x * 3 * L.master_floats;
+      c.mst_m = c.mst_p + L.master_floats; c.mst_v = c.mst_m + L.master_floats;
       c.tmem = tmem; c.warp = warp; c.lane = lane; c.row = ((warp & 3) << 5) + lane; c.cpart = warp >> 2;
       c.tid = threadIdx.x; c.flags = t.flags;
       c.b1 = mb.beta1; c.b2 = mb.beta2; c.aeps = mb.adam_eps;
@@ -787,6 +965,12 @@ __global__ void __launch_bounds__(256) xprep_kernel(const XPrepItem* items, int 
 
 }  // namespace tcp
 
+cudaError_t set_tcp_trace(unsigned long long* buf, int step) {
+  cudaError_t e = cudaMemcpyToSymbol(tcp::g_trace, &buf, sizeof(buf));
+  if (e != cudaSuccess) return e;
+  return cudaMemcpyToSymbol(tcp::g_trace_step, &step, sizeof(step));
+}
+
 cudaError_t configure_tcp() {
   return cudaFuncSetAttribute(tcp::train_tcp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tcp::kSmemBytes);
 }
@@ -799,7 +983,8 @@ cudaError_t launch_xprep(const void* items_dev, int n_items, int max_blocks, cud
 }
 
 cudaError_t launch_train_tcp(const TrainLaunch& t, const tcp::ProgramDev* progs, const tcp::MemberTc* mtc,
-                             unsigned char* stash, long long stash_bytes, int n_sm, cudaStream_t st) {
+                             unsigned char* stash, long long stash_bytes, float* master, long long master_floats,
+                             int n_sm, cudaStream_t st) {
   const int grid = t.n_members < n_sm ? t.n_members : n_sm;
   if (grid <= 0 || t.n_steps <= 0) return cudaSuccess;
   if (grid < t.n_members) {
@@ -808,6 +993,7 @@ cudaError_t launch_train_tcp(const TrainLaunch& t, const tcp::ProgramDev* progs,
   }
   tcp::LaunchP L;
   L.t = t; L.progs = progs; L.mtc = mtc; L.stash = stash; L.stash_bytes = stash_bytes;
+  L.master = master; L.master_floats = master_floats;
   tcp::train_tcp_kernel<<<grid, tcp::kThreadsP, tcp::kSmemBytes, st>>>(L);
   return cudaGetLastError();
 }

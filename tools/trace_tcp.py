@@ -1,0 +1,35 @@
+"""Dev tool: timeline of one minibatch step of the pipelined training kernel (CTA 0)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from multi_modal_normative_modeling_b200 import EnsembleTrainer, workloads, _lib
+
+seeds = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+dev = torch.device("cuda", 0)
+hw = workloads.build_host_workload()
+wl = workloads.to_device(hw, dev, n_seeds=seeds)
+tr = EnsembleTrainer(wl.specs, device=dev)
+tr.train_steps(8)
+buf = torch.zeros(4096, dtype=torch.int64, device=dev)
+lib = _lib.load()
+_lib.check(lib.nmb_debug_tcp_trace(buf.data_ptr(), 2))
+tr.train_steps(8)
+torch.cuda.synchronize()
+_lib.check(lib.nmb_debug_tcp_trace(None, 0))
+b = buf.cpu().numpy().astype(np.int64)
+nz = b[b > 0]
+t0 = nz.min()
+E = 37 if len(sys.argv) <= 2 else int(sys.argv[2]); S = 62 if len(sys.argv) <= 3 else int(sys.argv[3])
+print("span us", (nz.max() - t0) / 1e3)
+print("epilogue items: arrive start end (us)  | wait work")
+for k in range(E):
+    a, s, e = b[3 * k:3 * k + 3]
+    if a: print("E%02d %8.2f %8.2f %8.2f | %6.2f %6.2f" % (k + 1, (a - t0) / 1e3, (s - t0) / 1e3, (e - t0) / 1e3, (s - a) / 1e3, (e - s) / 1e3))
+print("mma steps: deps tiles issued")
+for k in range(S):
+    a, s, e = b[3 * E + 3 * k:3 * E + 3 * k + 3]
+    if a: print("S%02d %8.2f %8.2f %8.2f | %6.2f %6.2f" % (k, (a - t0) / 1e3, (s - t0) / 1e3, (e - t0) / 1e3, (s - a) / 1e3, (e - s) / 1e3))
+print("producer steps: deps issued")
+for k in range(S):
+    a, e = b[3 * E + 3 * S + 2 * k:3 * E + 3 * S + 2 * k + 2]
+    if a: print("P%02d %8.2f %8.2f" % (k, (a - t0) / 1e3, (e - t0) / 1e3))
