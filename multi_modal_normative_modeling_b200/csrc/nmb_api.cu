@@ -81,6 +81,8 @@ struct NmbEnsemble {
   long long stash_bytes = 0;
   float* master = nullptr;
   long long master_floats = 0;
+  std::vector<tcp::MStep> msteps;            // MMA step tables of all architectures (kernel parameters)
+  std::vector<int> ms_off, ms_cnt;
 };
 
 namespace {
@@ -91,6 +93,12 @@ int setup_tcp(NmbEnsemble* e) {
     progs.push_back(tcp::build_program(d));
     if (!progs.back().eligible) return 0;            // e.g. hidden width > 127: generic engine is used
   }
+  if (progs.size() > (size_t)tcp::kMaxParamArchs) return 0;
+  for (const tcp::Program& P : progs) {
+    e->ms_off.push_back((int)e->msteps.size()); e->ms_cnt.push_back((int)P.steps.size());
+    for (const tcp::Step& s : P.steps) e->msteps.push_back(tcp::to_mstep(s));
+  }
+  if (e->msteps.size() > (size_t)tcp::kMaxParamSteps) return 0;     // too many distinct architectures: generic engine
   auto dev_alloc = [&](size_t bytes, void** out) {
     cudaError_t ce = cudaMalloc(out, bytes ? bytes : 16);
     if (ce == cudaSuccess) { e->tcp_allocs.push_back(*out); ce = cudaMemset(*out, 0, bytes ? bytes : 16); }
@@ -347,7 +355,8 @@ int nmb_ensemble_train(NmbEnsemble* e, int64_t n_steps, const float* eps_overrid
   if (e->tcp_ok && !(flags & (NMB_TRAIN_FP32 | NMB_TRAIN_TC_SIMPLE))) {
     // dataset rows may have been re-packed since the last call: refresh their planes (cheap, streaming)
     CU(launch_xprep(e->xprep_dev, e->n_xprep, e->xprep_max_blocks, (cudaStream_t)stream));
-    CU(launch_train_tcp(t, e->progs_dev, e->mtc_dev, e->stash, e->stash_bytes, e->master, e->master_floats, e->n_sm,
+    CU(launch_train_tcp(t, e->progs_dev, e->mtc_dev, e->stash, e->stash_bytes, e->master, e->master_floats,
+                        e->msteps.data(), e->ms_off.data(), e->ms_cnt.data(), (int)e->ms_off.size(), e->n_sm,
                         (cudaStream_t)stream));
   } else {
     CU(launch_train(t, (cudaStream_t)stream));

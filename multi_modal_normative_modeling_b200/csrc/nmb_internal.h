@@ -69,6 +69,7 @@ cudaError_t set_tcp_trace(unsigned long long* buf, int step);
 cudaError_t launch_xprep(const void* items_dev, int n_items, int max_blocks, cudaStream_t st);
 cudaError_t launch_train_tcp(const TrainLaunch& t, const tcp::ProgramDev* progs, const tcp::MemberTc* mtc,
                              unsigned char* stash, long long stash_bytes, float* master, long long master_floats,
+                             const tcp::MStep* msteps, const int* ms_off, const int* ms_cnt, int n_archs,
                              int n_sm, cudaStream_t st);
 
 }  // namespace nmb

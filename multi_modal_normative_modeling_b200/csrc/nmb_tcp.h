@@ -26,8 +26,11 @@
 namespace nmb {
 namespace tcp {
 
-constexpr int kEpiWarps = 12;                     // 4 warps per TMEM lane quadrant
-constexpr int kEpiParts = kEpiWarps / 4;          // column partitions of an accumulator
+constexpr int kEpiWarps = 16;                     // 4 warps per TMEM lane quadrant
+constexpr int kEpiParts = kEpiWarps / 4;          // column partitions of an accumulator (joint items)
+constexpr int kGroupWarps = kEpiWarps / 2;        // the epilogue runs as two groups, one per minibatch half
+constexpr int kGroupThreads = kGroupWarps * 32;
+constexpr int kGroupParts = kGroupWarps / 4;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kThreadsP = kEpiThreads + 64;        // + MMA warp + producer warp
 constexpr int kActBytes = 65536;                   // one 128-row operand block, up to 128 columns (hi + lo)
@@ -60,8 +63,9 @@ enum EpiKind : int {
 struct alignas(16) Step {
   long long b_off, a_off;           // byte offsets inside their spaces
   unsigned b_bytes, a_bytes;        // a_bytes == 0: A is resident in ACT[half]
-  int dep;                          // epilogue item (index + 1, this step) that produced the tile data; 0 = none
-  int mma_dep;                      // epilogue item (index + 1) that must finish before these MMAs issue; 0 = none
+  int dep;                          // joint epilogue item (index + 1, this step) that published the tile data; 0 = none
+  int mma_dep;                      // item of this half's epilogue group that must finish before these MMAs issue
+  int mma_dep_joint;                // joint item (run by both groups) that must finish before these MMAs issue
   unsigned a_start;                 // byte offset inside ACT[half]
   unsigned a_lbo, a_sbo, a_kadv, a_lo;
   unsigned b_lbo, b_sbo, b_kadv, b_lo;
@@ -73,6 +77,33 @@ struct alignas(16) Step {
   unsigned char commit_buf;         // accumulator barrier 0..3
   unsigned char pad_[3];
 };
+
+// Compact copy of the MMA-relevant fields of a Step.  The table travels in the KERNEL PARAMETERS (constant
+// bank), so the MMA warp reads it with uniform loads and issues tcgen05.mma straight from uniform registers.
+struct MStep {
+  unsigned a_start;                                   // byte offset inside ACT[half] (A resident)
+  unsigned short a_lbo, a_sbo, a_kadv, a_lo;          // descriptor strides in 16-byte units
+  unsigned short b_lbo, b_sbo, b_kadv, b_lo;
+  unsigned short ksteps, n, tmem_col;
+  short mma_dep, mma_dep_joint;
+  unsigned char half, a_tile, a_mn, b_mn, first, commit, commit_buf, pad_;
+};
+constexpr int kMaxParamSteps = 640;                   // 40 B each: 25.6 KB of the 32 KB parameter space
+constexpr int kMaxParamArchs = 8;
+
+inline MStep to_mstep(const Step& s) {
+  MStep m{};
+  m.a_start = s.a_start;
+  m.a_lbo = (unsigned short)(s.a_lbo >> 4); m.a_sbo = (unsigned short)(s.a_sbo >> 4);
+  m.a_kadv = (unsigned short)(s.a_kadv >> 4); m.a_lo = (unsigned short)(s.a_lo >> 4);
+  m.b_lbo = (unsigned short)(s.b_lbo >> 4); m.b_sbo = (unsigned short)(s.b_sbo >> 4);
+  m.b_kadv = (unsigned short)(s.b_kadv >> 4); m.b_lo = (unsigned short)(s.b_lo >> 4);
+  m.ksteps = s.ksteps; m.n = s.n; m.tmem_col = s.tmem_col;
+  m.mma_dep = (short)s.mma_dep; m.mma_dep_joint = (short)s.mma_dep_joint;
+  m.half = s.half; m.a_tile = s.a_bytes ? 1 : 0; m.a_mn = s.a_mn; m.b_mn = s.b_mn;
+  m.first = s.first; m.commit = s.commit; m.commit_buf = s.commit_buf;
+  return m;
+}
 
 struct alignas(16) Epi {
   int kind, half, buf, mod;         // half: 0/1, 2 = joint.  buf: accumulator barrier to wait on, -1 = none
@@ -235,6 +266,12 @@ inline Program build_program(const ArchDesc& a) {
     e.tmem_col = buf < 0 ? 0 : (buf < 2 ? kAcc0 + 128 * buf : kWacc0 + 128 * (buf - 2));
     return e;
   };
+  // MMA-issue dependencies: items of the step's own half go to that group's counter, joint items to both
+  auto need = [&](Step& s, int id) {
+    if (id <= 0) return;
+    if (P.epis[id - 1].half == 2) { if (id > s.mma_dep_joint) s.mma_dep_joint = id; }
+    else if (id > s.mma_dep) s.mma_dep = id;
+  };
   auto base_step = [&](int h) {
     Step s{}; s.half = (unsigned char)h; s.b_space = SP_NONE; s.a_space = SP_NONE;
     return s;
@@ -270,7 +307,7 @@ inline Program build_program(const ArchDesc& a) {
       s.dep = a_dep;
       s.ksteps = (unsigned short)(ng / 2); s.n = (unsigned short)w.R; s.tmem_col = (unsigned short)(kAcc0 + 128 * buf);
       s.first = j == 0;
-      if (j == 0) s.mma_dep = a_space == SP_NONE ? (act_ready[h] > acc_free[buf] ? act_ready[h] : acc_free[buf]) : acc_free[buf];
+      if (j == 0) { need(s, acc_free[buf]); if (a_space == SP_NONE) need(s, act_ready[h]); }
       s.commit = g0 + tg >= w.cg ? 1 : 0; s.commit_buf = (unsigned char)buf;
       P.steps.push_back(s);
     }
@@ -288,7 +325,7 @@ inline Program build_program(const ArchDesc& a) {
       s.ksteps = (unsigned short)(w.R / 16); s.n = (unsigned short)(ng * 8);
       s.tmem_col = (unsigned short)(kAcc0 + 128 * buf + g0 * 8);
       s.first = 1;
-      if (j == 0) s.mma_dep = act_ready[h] > acc_free[buf] ? act_ready[h] : acc_free[buf];
+      if (j == 0) { need(s, act_ready[h]); need(s, acc_free[buf]); }
       s.commit = g0 + tg >= cg ? 1 : 0; s.commit_buf = (unsigned char)buf;
       P.steps.push_back(s);
     }
@@ -305,7 +342,7 @@ inline Program build_program(const ArchDesc& a) {
       s.dep = b_dep;
       s.ksteps = 8; s.n = (unsigned short)(ng * 8); s.tmem_col = (unsigned short)(kWacc0 + 128 * wb + g0 * 8);
       s.first = h == 0;
-      if (g0 == 0) s.mma_dep = act_ready[h] > acc_free[2 + wb] ? act_ready[h] : acc_free[2 + wb];
+      if (g0 == 0) { need(s, act_ready[h]); need(s, acc_free[2 + wb]); }
       const bool last = g0 + 8 >= g_count;
       s.commit = !last ? 0 : (h == 1 ? 1 : 2);
       s.commit_buf = (unsigned char)(2 + wb);
@@ -419,7 +456,7 @@ inline Program build_program(const ArchDesc& a) {
         s.dep = dxh_ready[m * 2 + h];
         s.ksteps = 4; s.n = (unsigned short)(w.cg * 8); s.tmem_col = (unsigned short)(kAcc0 + 128 * buf);
         s.first = t == 0;
-        if (t == 0) s.mma_dep = acc_free[buf];
+        if (t == 0) need(s, acc_free[buf]);
         s.commit = t == lay.n_dxh_blk[m] - 1 ? 1 : 0; s.commit_buf = (unsigned char)buf;
         P.steps.push_back(s);
       }
@@ -437,7 +474,7 @@ inline Program build_program(const ArchDesc& a) {
           s.dep = dxh_ready[m * 2 + h];
           s.ksteps = 8; s.n = 64; s.tmem_col = (unsigned short)(kWacc0 + 128 * wb + 64 * (t - t0));
           s.first = h == 0;
-          if (t == t0) s.mma_dep = act_ready[h] > acc_free[2 + wb] ? act_ready[h] : acc_free[2 + wb];
+          if (t == t0) { need(s, act_ready[h]); need(s, acc_free[2 + wb]); }
           const bool last = t == t0 + nt - 1;
           s.commit = !last ? 0 : (h == 1 ? 1 : 2);
           s.commit_buf = (unsigned char)(2 + wb);

@@ -8,6 +8,8 @@
 //   loss_function_multimodal     cVAE.py:1187-1196
 //   optimizer1 = Adam(...)       cVAE.py:1111-1116 (torch defaults)
 // One persistent CTA per SM; a member's minibatch steps all run inside one launch.
+#include <cstring>
+
 #include "nmb_tc_gemm.cuh"
 #include "nmb_internal.h"
 #include "nmb_tcp.h"
@@ -29,7 +31,7 @@ __device__ __forceinline__ unsigned long long gtime() {
 struct Ctrl {
   uint64_t full[kSlots], empty[kSlots], accbar[4];
   uint32_t tmem;
-  volatile uint32_t epi_done;
+  volatile uint32_t epi_done[2];   // per epilogue group: items finished (1 + step * n_epis + index + 1)
   int member;
   float red[40];
 };
@@ -55,7 +57,11 @@ __device__ __forceinline__ void wait_epi(const volatile uint32_t* p, uint32_t ne
   }
   __threadfence_block();
 }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
+__device__ __forceinline__ void wait_both(const volatile uint32_t* p, uint32_t need) {
+  wait_epi(p, need);
+  wait_epi(p + 1, need);
+}
+__device__ __forceinline__ void bar_n(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void fence_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -100,7 +106,7 @@ __device__ void producer_role(const TrainLaunch& t, const ProgramDev& pg, const 
       if (sv.rows_h[st.half] == 0) continue;
       uint32_t need = st.dep ? sv.base + (uint32_t)st.dep : 0u;
       if (st.b_space == SP_W) need = max(need, sv.base);
-      if (need) wait_epi(&ctl->epi_done, need);
+      if (need) wait_both(ctl->epi_done, need);
       TRACE(tr, tb + 2 * k);
       for (int which = 0; which < 2; ++which) {
         const int space = which == 0 ? st.a_space : st.b_space;
@@ -122,28 +128,48 @@ __device__ void producer_role(const TrainLaunch& t, const ProgramDev& pg, const 
   }
 }
 
+struct LaunchP {
+  TrainLaunch t;
+  const ProgramDev* progs;
+  const MemberTc* mtc;
+  unsigned char* stash;
+  long long stash_bytes;
+  float* master;            // per slot: 3 x master_floats (p, m, v)
+  long long master_floats;
+  int ms_off[kMaxParamArchs], ms_cnt[kMaxParamArchs];   // slice of msteps per architecture
+  MStep msteps[kMaxParamSteps];
+};
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ------------------------------------------------------------------------------------------------
-// MMA issuer: 3 BF16 passes per K = 16 step
-__device__ void mma_role(const TrainLaunch& t, const ProgramDev& pg, const MemberDev& mb, unsigned char* smem,
-                         Ctrl* ctl, uint32_t tmem, uint32_t& seq) {
+// MMA issuer: 3 BF16 passes per K = 16 step.  The WHOLE warp walks the step table (kernel parameters ->
+// uniform loads); one elected lane issues, so descriptors never leave the uniform datapath.
+__device__ void mma_role(const LaunchP& L, int ai, const MemberDev& mb, unsigned char* smem, Ctrl* ctl, uint32_t tmem,
+                         uint32_t& seq, int n_epis) {
+  const TrainLaunch& t = L.t;
   const uint32_t ring = tc::smem_u32(smem + kSmemRing);
   const uint32_t act0 = tc::smem_u32(smem);
   const long long s0 = mb.steps_done;
-  const int n_steps = pg.n_steps, n_epis = pg.n_epis;
-  const Step* __restrict__ steps = pg.steps;
+  const int k0 = L.ms_off[ai], k1 = k0 + L.ms_cnt[ai];
   for (long long i = 0; i < t.n_steps; ++i) {
     const StepVars sv = step_vars(mb, s0 + i, i, n_epis);
-    const bool half1 = sv.rows_h[1] > 0;
-    wait_epi(&ctl->epi_done, sv.base);
+    const bool half1 = __any_sync(0xffffffffu, sv.rows_h[1] > 0);
+    wait_both(ctl->epi_done, sv.base);
     const bool tr = g_trace && blockIdx.x == 0 && i == g_trace_step;
     const int tb = 3 * n_epis;
-    for (int k = 0; k < n_steps; ++k) {
-      const Step st = steps[k];
+    for (int k = k0; k < k1; ++k) {
+      const MStep& st = L.msteps[k];
       if (st.half && !half1) continue;
-      if (st.mma_dep) wait_epi(&ctl->epi_done, sv.base + (uint32_t)st.mma_dep);
-      TRACE(tr, tb + 3 * k);
-      uint32_t a_base, slot_a = 0xFFFFFFFFu;
-      if (st.a_bytes) {
+      if (st.mma_dep) wait_epi(&ctl->epi_done[st.half], sv.base + (uint32_t)st.mma_dep);
+      if (st.mma_dep_joint) wait_both(ctl->epi_done, sv.base + (uint32_t)st.mma_dep_joint);
+      if (tr && (threadIdx.x & 31) == 0) g_trace[tb + 3 * (k - k0)] = gtime();
+      uint32_t a_base, slot_a = kSlots;
+      if (st.a_tile) {
         slot_a = seq % kSlots;
         tc::mbar_wait(&ctl->full[slot_a], (seq / kSlots) & 1u);
         a_base = ring + slot_a * kSlotBytes;
@@ -155,24 +181,28 @@ __device__ void mma_role(const TrainLaunch& t, const ProgramDev& pg, const Membe
       tc::mbar_wait(&ctl->full[slot_b], (seq / kSlots) & 1u);
       const uint32_t b_base = ring + slot_b * kSlotBytes;
       ++seq;
-      TRACE(tr, tb + 3 * k + 1);
       tc::fence_after();
       const uint32_t idesc = tc::make_idesc(st.n, st.a_mn, st.b_mn);
       const uint32_t d = tmem + st.tmem_col;
-      uint64_t da = make_desc(a_base, st.a_lbo, st.a_sbo), db = make_desc(b_base, st.b_lbo, st.b_sbo);
-      const uint64_t a_lo = st.a_lo >> 4, b_lo = st.b_lo >> 4, a_adv = st.a_kadv >> 4, b_adv = st.b_kadv >> 4;
-      uint32_t acc = st.first ? 0u : 1u;
-      for (int ks = 0; ks < st.ksteps; ++ks) {
-        tc::mma_bf16(d, da, db, idesc, acc);
-        tc::mma_bf16(d, da + a_lo, db, idesc, 1u);
-        tc::mma_bf16(d, da, db + b_lo, idesc, 1u);
-        acc = 1u;
-        da += a_adv; db += b_adv;
+      const uint64_t hi_a = ((uint64_t)st.a_sbo << 32) | (1ull << 46) | ((uint64_t)st.a_lbo << 16);
+      const uint64_t hi_b = ((uint64_t)st.b_sbo << 32) | (1ull << 46) | ((uint64_t)st.b_lbo << 16);
+      uint64_t da = hi_a | ((a_base & 0x3FFFFu) >> 4), db = hi_b | ((b_base & 0x3FFFFu) >> 4);
+      if (elect_one()) {
+        if (tr) g_trace[tb + 3 * (k - k0) + 1] = gtime();
+        uint32_t acc = st.first ? 0u : 1u;
+        for (int ks = 0; ks < st.ksteps; ++ks) {
+          tc::mma_bf16(d, da, db, idesc, acc);
+          tc::mma_bf16(d, da + st.a_lo, db, idesc, 1u);
+          tc::mma_bf16(d, da, db + st.b_lo, idesc, 1u);
+          acc = 1u;
+          da += st.a_kadv; db += st.b_kadv;
+        }
+        tc::mma_commit(&ctl->empty[slot_b]);
+        if (slot_a != kSlots) tc::mma_commit(&ctl->empty[slot_a]);
+        if (st.commit == 1 || (st.commit == 2 && !half1)) tc::mma_commit(&ctl->accbar[st.commit_buf]);
+        if (tr) g_trace[tb + 3 * (k - k0) + 2] = gtime();
       }
-      tc::mma_commit(&ctl->empty[slot_b]);
-      if (slot_a != 0xFFFFFFFFu) tc::mma_commit(&ctl->empty[slot_a]);
-      if (st.commit == 1 || (st.commit == 2 && !half1)) tc::mma_commit(&ctl->accbar[st.commit_buf]);
-      TRACE(tr, tb + 3 * k + 2);
+      __syncwarp();
     }
   }
 }
@@ -184,7 +214,11 @@ struct EpiCtx {
   unsigned char* smem; unsigned char* stash; float* scratch; Ctrl* ctl;
   float* mst_p; float* mst_m; float* mst_v;     // lane-major Adam master state of the resident member
   uint32_t tmem;
-  int warp, lane, row, cpart, tid;
+  int warp, lane, row;      // row = TMEM lane of this thread: 32 * (warp % 4) + lane
+  int grp;                  // epilogue group = minibatch half this warp serves
+  int cpart, parts;         // column partition of the current item (within the group, or across both for joint items)
+  int tid, nthr;            // thread index / count of the current item's worker set
+  int bar_id, bar_nthr;     // named barrier of that worker set
   unsigned flags;
   int rows, rows_h0, rows_h1, row0;
   long long step;           // global 0-based minibatch step of this member (Philox counter, Adam t - 1)
@@ -226,11 +260,12 @@ __device__ __forceinline__ uint32_t taddr(const EpiCtx& c, int col) {
   return c.tmem + ((uint32_t)((c.warp & 3) << 5) << 16) + (uint32_t)col;
 }
 
+// sum over ALL epilogue threads (joint items only: both groups call it)
 __device__ __forceinline__ float block_sum_epi(EpiCtx& c, float v) {
   v = warp_sum(v);
-  epi_bar();
+  bar_n(3, kEpiWarps * 32);
   if (c.lane == 0) c.ctl->red[c.warp] = v;
-  epi_bar();
+  bar_n(3, kEpiWarps * 32);
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < kEpiWarps; ++i) s += c.ctl->red[i];
@@ -245,7 +280,7 @@ __device__ void build_weight_planes(const EpiCtx& c) {
     const WBlock wb = pg.wblocks[b];
     const int units = wb.R * wb.cg;
     unsigned char* dst = c.mt->wplanes + wb.wp_off;
-    for (int u = c.tid; u < units; u += kEpiThreads) {
+    for (int u = c.tid; u < units; u += c.nthr) {
       const int r = u % wb.R, g = u / wb.R;
       float x[8];
 #pragma unroll
@@ -275,7 +310,7 @@ __device__ void move_master(const EpiCtx& c, bool gather) {
     const MLayer ml = pg.mlayers[b];
     const int lanes = ml.kind == 0 ? ml.rows : ml.cols, other = ml.kind == 0 ? ml.cols : ml.rows;
     const int quads = (other + 3) >> 2;
-    for (int u = c.tid; u < quads * ml.R; u += kEpiThreads) {
+    for (int u = c.tid; u < quads * ml.R; u += c.nthr) {
       const int lane = u % ml.R, qd = u / ml.R;
       if (lane >= lanes) continue;
       const long long mi = ml.mst_off + ((long long)qd * ml.R + lane) * 4;
@@ -314,7 +349,7 @@ __device__ __forceinline__ void epi_hidden(EpiCtx& c, const Epi& e) {
   unsigned char* st = c.stash + e.stash_off;
   const int nl = c.a->non_linear;
   const int n_cols = e.n_cols, n_mma = e.n_mma, n_valid = e.n_valid, tcol = e.tmem_col;
-  for (int ch = c.cpart; ch * 16 < n_cols; ch += kEpiParts) {
+  for (int ch = c.cpart; ch * 16 < n_cols; ch += c.parts) {
     const int col = ch * 16;
     float v[16];
     if (col < n_mma) tc::tmem_ld16(taddr(c, tcol + col), v);
@@ -351,7 +386,7 @@ __device__ __forceinline__ void epi_head(EpiCtx& c, const Epi& e) {
   const int ld = c.pg->lay.ld_mulv;
   float* dst = reinterpret_cast<float*>(c.stash + c.pg->lay.mulv[e.mod]) + (long long)(128 * h + c.row) * ld;
   const int n_cols = e.n_cols, n_valid = e.n_valid, tcol = e.tmem_col;
-  for (int ch = c.cpart; ch * 16 < n_cols; ch += kEpiParts) {
+  for (int ch = c.cpart; ch * 16 < n_cols; ch += c.parts) {
     float v[16];
     __syncwarp();
     tc::tmem_ld16(taddr(c, tcol + ch * 16), v);
@@ -373,7 +408,7 @@ __device__ void epi_latent(EpiCtx& c, const Epi& e, const float* eps_src) {
   if (M > 1 && a.combine == NMB_COMBINE_GPOE) softmax_alpha(c.mb->params + a.alpha_off, M, w);
   const int n = rows * Z;
   const int g_base = (128 * h * Z) / 4;
-  for (int g = c.tid; g * 4 < n; g += kEpiThreads) {
+  for (int g = c.tid; g * 4 < n; g += c.nthr) {
     float nrm[4] = {0.f, 0.f, 0.f, 0.f};
     if (!eps_src) philox_normal4(c.mb->seed, (unsigned long long)c.step, 0u, (uint32_t)(g_base + g), nrm);
 #pragma unroll
@@ -400,14 +435,14 @@ __device__ void epi_latent(EpiCtx& c, const Epi& e, const float* eps_src) {
       c.kl_acc += -0.5f * (1.f + f.lv - f.mu * f.mu - expf(f.lv));
     }
   }
-  epi_bar();
+  bar_n(c.bar_id, c.bar_nthr);
   const int cg = round16(Z + a.C + 1) / 8;
   for (int m = 0; m < M; ++m) {
     const ModDesc& q = a.mod[m];
     unsigned char* st = c.stash + lay.g0[m][h];
     const float* xc = c.mb->xc[m] + (long long)(c.row0 + 128 * h) * q.ldx + q.D;
     const int ldx = q.ldx, C = a.C;
-    for (int u = c.tid; u < 128 * cg; u += kEpiThreads) {
+    for (int u = c.tid; u < 128 * cg; u += c.nthr) {
       const int r = u & 127, g = u >> 7;
       float x[8];
 #pragma unroll
@@ -431,7 +466,7 @@ __device__ __forceinline__ void epi_copy(EpiCtx& c, const Epi& e) {
   const uint4* src = reinterpret_cast<const uint4*>(c.stash + e.src_off);
   uint4* dst = reinterpret_cast<uint4*>(c.smem + e.half * kActBytes);
   const int n = e.src_cg * 256;       // 16-byte units
-  for (int u = c.tid; u < n; u += kEpiThreads) dst[u] = src[u];
+  for (int u = c.tid; u < n; u += c.nthr) dst[u] = src[u];
 }
 
 __device__ __forceinline__ void epi_recon(EpiCtx& c, const Epi& e) {
@@ -452,7 +487,7 @@ __device__ __forceinline__ void epi_recon(EpiCtx& c, const Epi& e) {
   float* lampart = reinterpret_cast<float*>(c.stash + lay.lampart[e.mod]) + (long long)(h * 4 + (c.warp & 3)) * round4(q.D);
   const int n_valid = e.n_valid, col0 = e.col0, tcol = e.tmem_col;
   const long long lam_off = q.lam_off;
-  for (int ch = c.cpart; ch < 4; ch += kEpiParts) {
+  for (int ch = c.cpart; ch < 4; ch += c.parts) {
     const int col = ch * 16, gc = col0 + col;
     int nv = n_valid - col; nv = nv < 0 ? 0 : (nv > 16 ? 16 : nv);
     float v[16], xt[16], l[16], gr[16], qv[16];
@@ -527,7 +562,7 @@ __device__ __forceinline__ void epi_lam(EpiCtx& c, const Epi& e) {
   const int ld = round4(q.D);
   const int np = c.rows_h1 > 0 ? 8 : 4;
   const float inv_rows = 1.f / c.rows;
-  for (int n = c.tid; n < q.D; n += kEpiThreads) {
+  for (int n = c.tid; n < q.D; n += c.nthr) {
     float s = 0.f;
     for (int k = 0; k < np; ++k) s += part[k * ld + n];
     adam_scalar(c, q.lam_off + n, s * inv_rows);
@@ -541,7 +576,7 @@ __device__ __forceinline__ void epi_dgrad(EpiCtx& c, const Epi& e) {
   const unsigned char* sg = c.stash + e.src_off;
   const int nl = c.a->non_linear;
   const int n_cols = e.n_cols, n_mma = e.n_mma, n_valid = e.n_valid, tcol = e.tmem_col;
-  for (int ch = c.cpart; ch * 16 < n_cols; ch += kEpiParts) {
+  for (int ch = c.cpart; ch * 16 < n_cols; ch += c.parts) {
     const int col = ch * 16;
     uint4 s0 = make_uint4(0, 0, 0, 0), s1 = s0;
     if (nl) {
@@ -577,7 +612,7 @@ __device__ __forceinline__ void epi_dz(EpiCtx& c, const Epi& e) {
   const bool vr = c.row < c.rows_of(h);
   float* dz = reinterpret_cast<float*>(c.stash + c.pg->lay.dz) + (long long)(128 * h + c.row) * Z;
   const int n_mma = e.n_mma, tcol = e.tmem_col, acc = e.mod > 0;
-  for (int ch = c.cpart; ch * 16 < n_mma; ch += kEpiParts) {
+  for (int ch = c.cpart; ch * 16 < n_mma; ch += c.parts) {
     float v[16];
     __syncwarp();
     tc::tmem_ld16(taddr(c, tcol + ch * 16), v);
@@ -603,7 +638,7 @@ __device__ void epi_latent_bwd(EpiCtx& c, const Epi& e) {
   float w[NMB_MAX_MOD];
   const bool gpoe = M > 1 && a.combine == NMB_COMBINE_GPOE;
   if (gpoe) softmax_alpha(P + a.alpha_off, M, w);
-  for (int el = c.tid; el < rows * Z; el += kEpiThreads) {
+  for (int el = c.tid; el < rows * Z; el += c.nthr) {
     const int b = el / Z, z = el - b * Z;
     const int gi = (128 * h + b) * Z + z;
     const float mub = S[a.s_mub + gi], lvb = S[a.s_lvb + gi], eps = S[a.s_eps + gi], dz = dzb[gi];
@@ -627,13 +662,13 @@ __device__ void epi_latent_bwd(EpiCtx& c, const Epi& e) {
       }
     }
   }
-  epi_bar();
+  bar_n(c.bar_id, c.bar_nthr);
   const int cg = round16(2 * Z) / 8;
   for (int m = 0; m < M; ++m) {
     const float* hd0 = reinterpret_cast<const float*>(c.stash + lay.mulv[m]) + (long long)(128 * h) * lay.ld_mulv;
     unsigned char* st = c.stash + lay.dmulv[m][h];
     const int ld = lay.ld_mulv;
-    for (int u = c.tid; u < 128 * cg; u += kEpiThreads) {
+    for (int u = c.tid; u < 128 * cg; u += c.nthr) {
       const int r = u & 127, g = u >> 7;
       float x[8];
 #pragma unroll
@@ -660,7 +695,7 @@ __device__ __forceinline__ void epi_wgrad(EpiCtx& c, const Epi& e) {
   const long long mbase = e.mst_off + (long long)o * 4;
   float* __restrict__ Pp = c.mst_p; float* __restrict__ Pm = c.mst_m; float* __restrict__ Pv = c.mst_v;
   const bool adam = !(c.flags & NMB_TRAIN_NO_ADAM), wg = c.flags & NMB_TRAIN_WRITE_GRADS;
-  for (int ch = c.cpart; ch * 8 < n_mma; ch += kEpiParts) {        // 8 columns (one plane group) at a time
+  for (int ch = c.cpart; ch * 8 < n_mma; ch += c.parts) {        // 8 columns (one plane group) at a time
     const int col = col0 + ch * 8;
     const bool on = vo && col < p_cols;
     const bool full = col + 4 < p_cols;
@@ -720,7 +755,7 @@ __device__ __forceinline__ void epi_wgrad_t(EpiCtx& c, const Epi& e) {
   const bool adam = !(c.flags & NMB_TRAIN_NO_ADAM), wg = c.flags & NMB_TRAIN_WRITE_GRADS;
   const long long colbase = e.p_off + i;
   const long long mbase = e.mst_off + (long long)i * 4;
-  for (int ch = c.cpart; ch * 8 < n_mma; ch += kEpiParts) {
+  for (int ch = c.cpart; ch * 8 < n_mma; ch += c.parts) {
     const int o0 = col0 + ch * 8;
     const bool on = vi && o0 < p_rows;
     const bool full = o0 + 4 < p_rows;
@@ -781,7 +816,7 @@ __device__ void epi_step_end(EpiCtx& c, float* loss_out) {
     float w[NMB_MAX_MOD], dw_tot[NMB_MAX_MOD];
     softmax_alpha(c.mb->params + a.alpha_off, M, w);
     for (int m = 0; m < M; ++m) dw_tot[m] = block_sum_epi(c, c.dw_acc[m]);
-    epi_bar();
+    bar_n(c.bar_id, c.bar_nthr);
     if (c.tid == 0) {
       float dot = 0.f;
       for (int m = 0; m < M; ++m) dot += w[m] * dw_tot[m];
@@ -792,6 +827,23 @@ __device__ void epi_step_end(EpiCtx& c, float* loss_out) {
   for (int m = 0; m < M; ++m) c.dw_acc[m] = 0.f;
 }
 
+// Worker set of an item: the group of its half (per-half items) or both groups (joint items).
+__device__ __forceinline__ void set_workers(EpiCtx& c, bool joint) {
+  const int lw = c.warp % kGroupWarps;
+  if (joint) {
+    c.tid = c.warp * 32 + c.lane; c.nthr = kEpiWarps * 32;
+    c.cpart = (lw >> 2) + c.grp * kGroupParts; c.parts = kEpiParts;
+    c.bar_id = 3; c.bar_nthr = kEpiWarps * 32;
+  } else {
+    c.tid = lw * 32 + c.lane; c.nthr = kGroupThreads;
+    c.cpart = lw >> 2; c.parts = kGroupParts;
+    c.bar_id = 1 + c.grp; c.bar_nthr = kGroupThreads;
+  }
+}
+
+// The epilogue runs as TWO groups of warps, one per 128-row half of the minibatch: each walks the item list,
+// executes the items of its own half and -- together with the other group -- the joint items (Adam, fences,
+// loss).  The two dependency chains (half 0, half 1) therefore overlap each other's latencies.
 __device__ void epilogue_role(const TrainLaunch& t, int mi, EpiCtx& c, uint32_t& acc_par) {
   const ProgramDev& pg = *c.pg;
   MemberDev& mb = *c.mb;
@@ -799,15 +851,18 @@ __device__ void epilogue_role(const TrainLaunch& t, int mi, EpiCtx& c, uint32_t&
   float dw_acc[NMB_MAX_MOD];
   for (int m = 0; m < NMB_MAX_MOD; ++m) dw_acc[m] = 0.f;
   c.dw_acc = dw_acc;
+  set_workers(c, true);
   build_weight_planes(c);
   const bool adam_on = !(c.flags & NMB_TRAIN_NO_ADAM);
   if (adam_on) move_master(c, true);
+  __threadfence();
   fence_async_all();
-  epi_bar();
-  if (c.tid == 0) st_release(&c.ctl->epi_done, 1u);
+  bar_n(3, kEpiWarps * 32);
+  if (c.tid == 0) { st_release(&c.ctl->epi_done[0], 1u); st_release(&c.ctl->epi_done[1], 1u); }
   const long long s0 = mb.steps_done;
   const int n_epis = pg.n_epis;
   const Epi* __restrict__ epis = pg.epis;
+  const bool pub = (c.warp % kGroupWarps) == 0 && c.lane == 0;     // the thread that publishes its group's counter
   for (long long i = 0; i < t.n_steps; ++i) {
     const long long s = s0 + i;
     const StepVars sv = step_vars(mb, s, i, n_epis);
@@ -823,15 +878,19 @@ __device__ void epilogue_role(const TrainLaunch& t, int mi, EpiCtx& c, uint32_t&
     float* lo = t.loss_out ? t.loss_out + ((long long)mi * t.n_steps + i) * 3 : nullptr;
     for (int k = 0; k < n_epis; ++k) {
       const Epi e = epis[k];
-      if (e.half == 1 && c.rows_h1 == 0) continue;
-      const bool tr = g_trace && blockIdx.x == 0 && i == g_trace_step && c.tid == 0;
-      TRACE(tr, 3 * k);
+      const bool joint = e.half == 2;
+      if (!joint && (e.half != c.grp || (e.half == 1 && c.rows_h1 == 0))) continue;
+      set_workers(c, joint);
+      const bool tr = g_trace && blockIdx.x == 0 && i == g_trace_step && c.lane == 0 && (c.warp % kGroupWarps) == 0;
+      const int tbase = c.grp == 0 ? 0 : 3 * n_epis + 5 * pg.n_steps;   // group 1 stamps after the MMA / producer records
+      if (tr && (!joint || c.grp == 0)) g_trace[tbase + 3 * k] = gtime();
+      if (joint) bar_n(3, kEpiWarps * 32);          // both groups have finished everything before this item
       if (e.buf >= 0) {
         tc::mbar_wait(&c.ctl->accbar[e.buf], (acc_par >> e.buf) & 1u);
         acc_par ^= 1u << e.buf;
         tc::fence_after();
       }
-      TRACE(tr, 3 * k + 1);
+      if (tr && (!joint || c.grp == 0)) g_trace[tbase + 3 * k + 1] = gtime();
       // proxy fences: ACT[h] (shared memory, read by the next MMAs) per item; global data read by the TMA
       // (stash blocks, weight planes) only at EK_FENCE / EK_STEP_END, so the stores drain in the background
       int fence = 0;              // 1 = shared memory, 2 = everything
@@ -853,25 +912,18 @@ __device__ void epilogue_role(const TrainLaunch& t, int mi, EpiCtx& c, uint32_t&
       if (e.buf >= 0) tc::fence_before();
       if (fence == 1) fence_async_smem();
       else if (fence == 2) { __threadfence(); fence_async_all(); }
-      epi_bar();
-      if (c.tid == 0) st_release(&c.ctl->epi_done, sv.base + (uint32_t)k + 1u);
-      TRACE(tr, 3 * k + 2);
+      bar_n(1 + c.grp, kGroupThreads);
+      if (pub) st_release(&c.ctl->epi_done[c.grp], sv.base + (uint32_t)k + 1u);
+      if (tr && (!joint || c.grp == 0)) g_trace[tbase + 3 * k + 2] = gtime();
     }
   }
+  set_workers(c, true);
+  bar_n(3, kEpiWarps * 32);
   if (adam_on) move_master(c, false);
 }
 
-struct LaunchP {
-  TrainLaunch t;
-  const ProgramDev* progs;
-  const MemberTc* mtc;
-  unsigned char* stash;
-  long long stash_bytes;
-  float* master;            // per slot: 3 x master_floats (p, m, v)
-  long long master_floats;
-};
 
-__global__ void __launch_bounds__(kThreadsP, 1) train_tcp_kernel(LaunchP L) {
+__global__ void __launch_bounds__(kThreadsP, 1) train_tcp_kernel(const __grid_constant__ LaunchP L) {
   extern __shared__ __align__(1024) unsigned char smem[];
   Ctrl* ctl = reinterpret_cast<Ctrl*>(smem + kSmemCtrl);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -895,7 +947,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) train_tcp_kernel(LaunchP L) {
       if (dynamic) { mi = atomicAdd(t.work_counter, 1); if (mi < t.n_members) mi = t.order[mi]; else mi = t.n_members; }
       else if (first) mi = blockIdx.x;
       ctl->member = mi;
-      ctl->epi_done = 0;
+      ctl->epi_done[0] = 0; ctl->epi_done[1] = 0;
     }
     first = false;
     __syncthreads();
@@ -910,12 +962,13 @@ __global__ void __launch_bounds__(kThreadsP, 1) train_tcp_kernel(LaunchP L) {
       c.smem = smem; c.stash = stash; c.scratch = t.scratch + (long long)blockIdx.x * t.slot_floats; c.ctl = ctl;
       c.mst_p = L.master + (long long)blockIdx.x * 3 * L.master_floats;
       c.mst_m = c.mst_p + L.master_floats; c.mst_v = c.mst_m + L.master_floats;
-      c.tmem = tmem; c.warp = warp; c.lane = lane; c.row = ((warp & 3) << 5) + lane; c.cpart = warp >> 2;
-      c.tid = threadIdx.x; c.flags = t.flags;
+      c.tmem = tmem; c.warp = warp; c.lane = lane; c.row = ((warp & 3) << 5) + lane;
+      c.grp = warp / kGroupWarps; c.flags = t.flags;
       c.b1 = mb.beta1; c.b2 = mb.beta2; c.aeps = mb.adam_eps;
       epilogue_role(t, mi, c, acc_par);
     } else if (warp == kEpiWarps) {
-      if (lane == 0) mma_role(t, pg, mb, smem, ctl, tmem, seq);
+      const int ai = __shfl_sync(0xffffffffu, mb.arch_idx, 0);
+      mma_role(L, ai, mb, smem, ctl, tmem, seq, pg.n_epis);
     } else {
       if (lane == 0) producer_role(t, pg, mb, mt, stash, smem, ctl, seq);
     }
@@ -984,6 +1037,7 @@ cudaError_t launch_xprep(const void* items_dev, int n_items, int max_blocks, cud
 
 cudaError_t launch_train_tcp(const TrainLaunch& t, const tcp::ProgramDev* progs, const tcp::MemberTc* mtc,
                              unsigned char* stash, long long stash_bytes, float* master, long long master_floats,
+                             const tcp::MStep* msteps, const int* ms_off, const int* ms_cnt, int n_archs,
                              int n_sm, cudaStream_t st) {
   const int grid = t.n_members < n_sm ? t.n_members : n_sm;
   if (grid <= 0 || t.n_steps <= 0) return cudaSuccess;
@@ -994,6 +1048,8 @@ cudaError_t launch_train_tcp(const TrainLaunch& t, const tcp::ProgramDev* progs,
   tcp::LaunchP L;
   L.t = t; L.progs = progs; L.mtc = mtc; L.stash = stash; L.stash_bytes = stash_bytes;
   L.master = master; L.master_floats = master_floats;
+  for (int a = 0; a < n_archs; ++a) { L.ms_off[a] = ms_off[a]; L.ms_cnt[a] = ms_cnt[a]; }
+  std::memcpy(L.msteps, msteps, sizeof(tcp::MStep) * (size_t)(ms_off[n_archs - 1] + ms_cnt[n_archs - 1]));
   tcp::train_tcp_kernel<<<grid, tcp::kThreadsP, tcp::kSmemBytes, st>>>(L);
   return cudaGetLastError();
 }
