@@ -15,6 +15,16 @@ import torch
 pytestmark = pytest.mark.gpu
 
 REL = 1e-4
+# engines of the fused training kernel: "tc" = default (pipelined tcgen05, BF16x3 split products),
+# "tcs" = generic tcgen05 engine, "fp32" = FFMA engine (bit-stable trajectories)
+ENGINES = ["tc", "tcs", "fp32"]
+
+
+def engine_flags(engine):
+    from multi_modal_normative_modeling_b200 import _lib
+    return {"tc": 0, "tcs": _lib.TRAIN_TC_SIMPLE, "fp32": _lib.TRAIN_FP32}[engine]
+
+
 MM_CASES = ["mm_M1_small", "mm_M3_poe", "mm_M3_gpoe", "mm_M2_moe", "mm_M4_mopoe", "mm_M1_D116_full"]
 
 
@@ -44,14 +54,17 @@ def make_trainer(g, sd_prefix="init/", keep_grads=True, batch=None, loss_kind="g
     return EnsembleTrainer(specs, keep_grads=keep_grads), xc
 
 
+@pytest.mark.parametrize("engine", ENGINES)
 @pytest.mark.parametrize("name", MM_CASES)
-def test_step_forward_backward_vs_reference(golden_dir, name):
+def test_step_forward_backward_vs_reference(golden_dir, name, engine):
     from multi_modal_normative_modeling_b200 import _lib
     g = load(golden_dir, name)
     tr, _ = make_trainer(g)
+    if engine == "tc":
+        assert tr.engine() == "tcgen05-pipelined"          # the default path IS the pipelined tensor-core kernel
     eps = torch.from_numpy(g["eps"][:1]).cuda()[None]          # [1 member, 1 step, B, Z]
-    losses = tr.train_steps(1, eps=eps, record_losses=True,
-                            flags=_lib.TRAIN_NO_ADAM | _lib.TRAIN_WRITE_GRADS | _lib.TRAIN_KEEP_ACTS)
+    losses = tr.train_steps(1, eps=eps, record_losses=True, flags=engine_flags(engine) |
+                            _lib.TRAIN_NO_ADAM | _lib.TRAIN_WRITE_GRADS | _lib.TRAIN_KEEP_ACTS)
     torch.cuda.synchronize()
     got = losses[0, 0].cpu().numpy()
     assert np.allclose(got, g["losses"][0], rtol=REL), (got, g["losses"][0])
@@ -73,13 +86,22 @@ def test_step_forward_backward_vs_reference(golden_dir, name):
     tr.close()
 
 
+@pytest.mark.parametrize("engine", ENGINES)
 @pytest.mark.parametrize("name", MM_CASES)
-def test_adam_trajectory_vs_reference(golden_dir, name):
+def test_adam_trajectory_vs_reference(golden_dir, name, engine):
+    """Losses and parameters after several Adam steps against the unmodified reference.
+
+    Adam's first steps move every weight by ~lr * sign(g): an element whose gradient is within
+    rounding distance of zero can take a different step under ANY change of summation order.  The
+    FP32 engine (error ~1e-7 of the gradient scale) is held to the max-norm bound on every element;
+    the tensor-core engines (BF16x3 products, gradients within 1e-4 relative, see the step test) are
+    held to the same bound on 99.9 % of the elements, with the rest bounded by one sign flip per
+    step, and to the max-norm bound on the parameters themselves."""
     g = load(golden_dir, name)
     tr, _ = make_trainer(g, keep_grads=False)
     steps = g["eps"].shape[0]
     eps = torch.from_numpy(g["eps"]).cuda()[None]
-    losses = tr.train_steps(steps, eps=eps, record_losses=True)
+    losses = tr.train_steps(steps, eps=eps, record_losses=True, flags=engine_flags(engine))
     torch.cuda.synchronize()
     assert np.allclose(losses[0].cpu().numpy(), g["losses"], rtol=REL)
     assert int(tr.steps_done()[0]) == steps
@@ -92,9 +114,44 @@ def test_adam_trajectory_vs_reference(golden_dir, name):
         d_ref, d_got = v - init[k], got - init[k]
         if np.abs(d_ref).max() == 0:
             assert np.abs(d_got).max() == 0, k
-        else:
+        elif engine == "fp32":
             assert np.abs(d_got - d_ref).max() / np.abs(d_ref).max() < 2e-3, k
-        assert relerr(got, v) < 1e-5, k
+        else:
+            dev = np.sort(np.abs(d_got - d_ref).ravel() / np.abs(d_ref).max())
+            n_out = min(max(2, dev.size // 1000), dev.size - 1)   # at most 0.1 % of the elements (>= 2) may flip
+            assert dev[-n_out - 1] < 2e-3, k
+            assert dev[-1] <= 2.0 + 1e-3, k                    # never worse than a sign flip at every step
+        assert relerr(got, v) < (1e-5 if engine == "fp32" else REL), k
+    tr.close()
+
+
+@pytest.mark.parametrize("engine", ["tc", "tcs"])
+@pytest.mark.parametrize("name", ["mm_M1_D116_full", "mm_M3_gpoe"])
+def test_adam_arithmetic_on_the_kernels_own_gradients(golden_dir, name, engine):
+    """The fused Adam epilogue (SFU sqrt / reciprocal) == torch.optim.Adam's formula applied to the
+    gradients the same launch wrote out: isolates the optimiser arithmetic from gradient rounding."""
+    from oracle import cvae_numpy
+    from multi_modal_normative_modeling_b200 import _lib
+    g = load(golden_dir, name)
+    tr, _ = make_trainer(g)
+    eps = torch.from_numpy(g["eps"][:2]).cuda()[None]
+    before = {k: v.cpu().numpy().astype(np.float64) for k, v in tr.state_dict(0).items()}
+    m = {k: np.zeros_like(v) for k, v in before.items()}
+    v2 = {k: np.zeros_like(v) for k, v in before.items()}
+    for t in (1, 2):
+        tr.train_steps(1, eps=eps[:, t - 1:t].contiguous(), flags=engine_flags(engine) | _lib.TRAIN_WRITE_GRADS)
+        torch.cuda.synchronize()
+        grads = {k: v.cpu().numpy().astype(np.float64) for k, v in tr.state_dict(0, "grads").items()}
+        after = {k: v.cpu().numpy().astype(np.float64) for k, v in tr.state_dict(0).items()}
+        for k in before:
+            if np.abs(grads[k]).max() == 0:
+                continue
+            want = before[k].copy()
+            cvae_numpy.adam_update(want, grads[k], m[k], v2[k], t)
+            upd = np.abs(want - before[k]).max()
+            ulp = 1.2e-7 * np.abs(want).max()                   # the parameters are stored in fp32
+            assert np.abs(after[k] - want).max() <= 2e-5 * upd + 2 * ulp, (k, t)
+        before = after
     tr.close()
 
 
