@@ -59,27 +59,33 @@ def config(args, extra=None):
 # CPU baseline: the reference's eager PyTorch loop, restated in oracle/cvae_torch.py (the reference
 # is Python and cannot travel to the GPU box; kind = "port").
 def cpu_reference_sample(hw, epochs, budget_s, threads=None):
+    """Reference training loop on the host for fold 0 x all 4 modalities (keeps the 3:1 D=116 : D=348 mix).
+    With a finite `budget_s` the number of epochs is calibrated so that the sample takes about that long."""
     import torch
     from oracle import cvae_torch
     threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
-    names = hw.names
-    done_samples, t_total, models = 0, 0.0, 0
     fold = hw.folds[0]
-    for name in names:                      # one fold x all 4 modalities keeps the 3:1 D=116 : D=348 mix
-        d = hw.dims[name]
-        torch.manual_seed(42)
-        model = cvae_torch.OracleCVAEMultimodal([d], list(hw.hidden), hw.latent, hw.c_dim, 1e-4, 1, True)
-        x = torch.from_numpy(fold.train_x[name])
-        c = torch.from_numpy(fold.train_c).long()          # int64 one-hots (utils_vae.py:24)
-        t0 = time.perf_counter()
-        cvae_torch.reference_train_loop(model, [x], [c], "gPoE", epochs, hw.batch)
-        t_total += time.perf_counter() - t0
-        done_samples += x.shape[0] * epochs
-        models += 1
-        if t_total > budget_s:
-            break
-    return done_samples / t_total, threads, models, t_total
+
+    def one_pass(n_epochs):
+        samples, t_total = 0, 0.0
+        for name in hw.names:
+            d = hw.dims[name]
+            torch.manual_seed(42)
+            model = cvae_torch.OracleCVAEMultimodal([d], list(hw.hidden), hw.latent, hw.c_dim, 1e-4, 1, True)
+            x = torch.from_numpy(fold.train_x[name])
+            c = torch.from_numpy(fold.train_c).long()          # int64 one-hots (utils_vae.py:24)
+            t0 = time.perf_counter()
+            cvae_torch.reference_train_loop(model, [x], [c], "gPoE", n_epochs, hw.batch)
+            t_total += time.perf_counter() - t0
+            samples += x.shape[0] * n_epochs
+        return samples, t_total
+
+    if budget_s < 1e8:
+        s0, t0 = one_pass(2)                                   # calibration (also warms the thread pool)
+        epochs = max(epochs, int(budget_s / max(t0 / 2, 1e-6)))
+    samples, t_total = one_pass(epochs)
+    return samples / t_total, threads, len(hw.names), t_total, epochs
 
 
 def cpu_deviation_sample(hw, threads):
@@ -124,7 +130,7 @@ def run_reference(args):
     t0 = time.perf_counter()
     samples = 0
     for _ in range(args.steps):
-        rate, _, models, dt = cpu_reference_sample(hw, args.epochs_per_step, 1e9, threads)
+        rate, _, models, dt, _ = cpu_reference_sample(hw, args.epochs_per_step, 1e9, threads)
         samples += rate * dt
     el = time.perf_counter() - t0
     value = samples / el
@@ -321,25 +327,27 @@ def run_b200(args):
         peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained"
         achieved = flops_per_step / (kernel_ms * 1e-3) / 1e12
         clocks = sampler.summary()
-        sm_mhz = clocks["sm_mhz"] or 1965
-        fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12          # FFMA roof at the clock seen under load
         traffic = None
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "train_kernel_traffic.json"))).get("dram_bytes_per_launch")
         except Exception:
             pass
+        engine = tr.engine()
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": config(args, {"final_mean_total_loss": final_loss}),
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16x3->f32" if engine != "fp32" else "f32",
+                "data": "synthetic",
+                "config": config(args, {"final_mean_total_loss": final_loss, "engine": engine}),
                 "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                             "frac": achieved / peak_tf, "traffic": traffic, "kernel": "nmb::train_kernel",
+                             "frac": achieved / peak_tf, "traffic": traffic,
+                             "kernel": "nmb::tcp::train_tcp_kernel" if engine == "tcgen05-pipelined" else "nmb::train_kernel",
                              "kernel_ms": kernel_ms, "algorithmic_flops_per_launch": flops_per_step,
                              "peak_source": peak_src,
-                             "note": "kernel computes in FP32 FFMA (1e-4 parity bar rules out single-pass TF32/BF16); "
-                                     "FP32 FFMA roof at the sampled clock = %.1f TFLOP/s -> frac_of_fp32 = %.3f"
-                                     % (fp32_peak, achieved / fp32_peak),
-                             "fp32_ffma_peak": fp32_peak, "frac_of_fp32": achieved / fp32_peak},
+                             "note": "achieved = algorithmic (FP32-equivalent) FLOPs; every product is executed as 3 BF16 "
+                                     "tcgen05 passes (hi*hi, lo*hi, hi*lo, FP32 accumulate) to meet the 1e-4 parity bar, so "
+                                     "the tensor pipe executes 3x these FLOPs: executed_frac = %.4f of the measured peak"
+                                     % (3 * achieved / peak_tf),
+                             "executed_tensor_frac": 3 * achieved / peak_tf},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": loss_host.numel() * 4, "ms_per_step": e2e_ms / args.steps},
                 "gpu_launches": launches, "clocks": clocks}
@@ -347,10 +355,10 @@ def run_b200(args):
             line["deviation"] = deviation
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            rate, cores, models, dt = cpu_reference_sample(hw, 5, args.cpu_seconds, threads)
+            rate, cores, models, dt, ep = cpu_reference_sample(hw, 5, args.cpu_seconds, threads)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": "%d model(s) of fold 0 (modalities in order) x 5 epochs, %.1f s, "
-                                              "oracle/cvae_torch.py eager PyTorch loop" % (models, dt),
+                                    "sample": "fold 0 x %d modalities (3 x D=116 + D=348) x %d epochs, %.1f s, "
+                                              "oracle/cvae_torch.py eager PyTorch loop" % (models, ep, dt),
                                     "deviation_subjects_per_s": cpu_deviation_sample(hw, threads)}
         print(json.dumps(line))
     tr.close()

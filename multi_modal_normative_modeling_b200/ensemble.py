@@ -220,8 +220,16 @@ class EnsembleTrainer:
             _lib.check(self.lib.nmb_ensemble_train(self.handle, int(n_steps), eps_ptr,
                                                    losses.data_ptr() if losses is not None else None,
                                                    int(flags), _stream_ptr(self.device)), "nmb_ensemble_train")
-        self.gpu_launches += 1
+        # the pipelined engine launches the dataset re-tiling kernel (xprep) before the fused train kernel
+        self.gpu_launches += 2 if self._engine_cached(int(flags)) == "tcgen05-pipelined" else 1
         return losses
+
+    def _engine_cached(self, flags: int) -> str:
+        key = flags & (_lib.TRAIN_FP32 | _lib.TRAIN_TC_SIMPLE)
+        cache = self.__dict__.setdefault("_engines", {})
+        if key not in cache:
+            cache[key] = self.engine(key)
+        return cache[key]
 
     def engine(self, flags: int = 0) -> str:
         """Engine train_steps(flags=...) runs: 'tcgen05-pipelined', 'tcgen05-generic' or 'fp32'."""
