@@ -828,9 +828,15 @@ __device__ void epi_step_end(EpiCtx& c, float* loss_out) {
 }
 
 // Worker set of an item: the group of its half (per-half items) or both groups (joint items).
-__device__ __forceinline__ void set_workers(EpiCtx& c, bool joint) {
+// `split` joint items (the Adam epilogues) need no data from the other group: each group processes its own
+// column partitions whenever it gets there, without a rendezvous.
+__device__ __forceinline__ void set_workers(EpiCtx& c, bool joint, bool split = false) {
   const int lw = c.warp % kGroupWarps;
-  if (joint) {
+  if (joint && split) {
+    c.tid = lw * 32 + c.lane; c.nthr = kGroupThreads;
+    c.cpart = (lw >> 2) + c.grp * kGroupParts; c.parts = kEpiParts;
+    c.bar_id = 1 + c.grp; c.bar_nthr = kGroupThreads;
+  } else if (joint) {
     c.tid = c.warp * 32 + c.lane; c.nthr = kEpiWarps * 32;
     c.cpart = (lw >> 2) + c.grp * kGroupParts; c.parts = kEpiParts;
     c.bar_id = 3; c.bar_nthr = kEpiWarps * 32;
@@ -880,17 +886,18 @@ __device__ void epilogue_role(const TrainLaunch& t, int mi, EpiCtx& c, uint32_t&
       const Epi e = epis[k];
       const bool joint = e.half == 2;
       if (!joint && (e.half != c.grp || (e.half == 1 && c.rows_h1 == 0))) continue;
-      set_workers(c, joint);
+      const bool split = e.kind == EK_WGRAD || e.kind == EK_WGRAD_T;
+      set_workers(c, joint, split);
       const bool tr = g_trace && blockIdx.x == 0 && i == g_trace_step && c.lane == 0 && (c.warp % kGroupWarps) == 0;
       const int tbase = c.grp == 0 ? 0 : 3 * n_epis + 5 * pg.n_steps;   // group 1 stamps after the MMA / producer records
-      if (tr && (!joint || c.grp == 0)) g_trace[tbase + 3 * k] = gtime();
-      if (joint) bar_n(3, kEpiWarps * 32);          // both groups have finished everything before this item
+      if (tr) g_trace[tbase + 3 * k] = gtime();
+      if (joint && !split) bar_n(3, kEpiWarps * 32);   // both groups have finished everything before this item
       if (e.buf >= 0) {
         tc::mbar_wait(&c.ctl->accbar[e.buf], (acc_par >> e.buf) & 1u);
         acc_par ^= 1u << e.buf;
         tc::fence_after();
       }
-      if (tr && (!joint || c.grp == 0)) g_trace[tbase + 3 * k + 1] = gtime();
+      if (tr) g_trace[tbase + 3 * k + 1] = gtime();
       // proxy fences: ACT[h] (shared memory, read by the next MMAs) per item; global data read by the TMA
       // (stash blocks, weight planes) only at EK_FENCE / EK_STEP_END, so the stores drain in the background
       int fence = 0;              // 1 = shared memory, 2 = everything
@@ -914,7 +921,7 @@ __device__ void epilogue_role(const TrainLaunch& t, int mi, EpiCtx& c, uint32_t&
       else if (fence == 2) { __threadfence(); fence_async_all(); }
       bar_n(1 + c.grp, kGroupThreads);
       if (pub) st_release(&c.ctl->epi_done[c.grp], sv.base + (uint32_t)k + 1u);
-      if (tr && (!joint || c.grp == 0)) g_trace[tbase + 3 * k + 2] = gtime();
+      if (tr) g_trace[tbase + 3 * k + 2] = gtime();
     }
   }
   set_workers(c, true);
