@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--epochs-per-step", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-deviation", action="store_true")
-    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the bounded CPU sample")
+    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the bounded CPU sample")
     return ap.parse_args()
 
 
@@ -267,32 +267,16 @@ def run_b200(args):
     # ---- deviation scoring: reconstruct -> normative stats -> deviation/z -> AUC -> all-gather --
     deviation = None
     if not args.no_deviation:
-        train_xc = [s.xc for s in wl.specs]
-        dmax = max(int(s.input_dims[0]) for s in wl.specs)
-        groups = {}
-        for i, s in enumerate(wl.specs):
-            groups.setdefault(int(s.input_dims[0]), []).append(i)
-        groups = {d: torch.tensor(v, device=dev) for d, v in groups.items()}
+        scorer = scoring.DeviationScorer(tr, [s.xc for s in wl.specs], wl.test_xc, wl.train_hc_mask, wl.test_labels)
 
         def dev_step():
-            xhat_tr, _, _ = tr.reconstruct(train_xc, mode="mean")
-            xhat_te, _, _ = tr.reconstruct(wl.test_xc, mode="mean")
-            x_tr = [t[0] for t in train_xc]; x_te = [t[0] for t in wl.test_xc]
-            stats = scoring.normative_stats(x_tr, [h[0] for h in xhat_tr], wl.train_hc_mask)
-            roi, z, subj = scoring.deviation(x_te, [h[0] for h in xhat_te], stats)
-            roi_auc = scoring.auc(z, wl.test_labels)
-            subj_auc = scoring.auc(subj, wl.test_labels)
-            # fixed-size per-member record {subject AUC | per-ROI mean | per-ROI std | per-ROI AUC}, padded to Dmax
-            rec = torch.zeros((tr.n, 1 + 3 * dmax), dtype=torch.float64, device=dev)
-            rec[:, 0] = torch.cat(subj_auc)
-            for d, idx in groups.items():
-                st = torch.stack([stats[i] for i in idx]).double()
-                rec[idx, 1:1 + d] = st[:, 0]
-                rec[idx, 1 + dmax:1 + dmax + d] = st[:, 1]
-                rec[idx, 1 + 2 * dmax:1 + 2 * dmax + d] = torch.stack([roi_auc[i] for i in idx])
+            # 6 libnmb launches (2 x reconstruct, stats, deviation / z, 2 x AUC), then one fixed-size record per
+            # member {subject AUC | per-ROI mean | std | AUC} and the all-gather (NCCL over NVLink when N > 1)
+            scorer.run()
+            rec = scorer.member_records()
             owned = list(range(rank * tr.n, (rank + 1) * tr.n))
-            table = nd.gather_member_tables(rec, owned, world * tr.n)      # NCCL all-gather over NVLink
-            return table, subj_auc
+            table = nd.gather_member_tables(rec, owned, world * tr.n)
+            return table, scorer.auc_subj
         for _ in range(2):
             dev_step()
         barrier()
@@ -313,7 +297,7 @@ def run_b200(args):
                         for t, s in zip(wl.test_xc, wl.specs))
         deviation = {"value": world * wl.test_subjects * reps / (dms * 1e-3), "unit": "subjects/s",
                      "ms_per_pass": dms / reps, "subjects_per_pass": world * wl.test_subjects,
-                     "mean_subject_auc": float(torch.cat(subj_auc).mean()),
+                     "mean_subject_auc": float(subj_auc.mean()),
                      "gathered_table": list(table.shape), "launches_per_pass": 6,
                      "streaming_kernel_algorithmic_bytes": dev_bytes}
 

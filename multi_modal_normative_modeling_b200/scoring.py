@@ -113,3 +113,126 @@ def philox_normal(seed: int, step: int, n: int, stream_id: int = 0, device="cuda
         _lib.check(_lib.load().nmb_philox_normal(int(seed), int(step), int(stream_id), n, out.data_ptr(),
                                                  _stream_ptr(out.device)), "nmb_philox_normal")
     return out
+
+
+class DeviationScorer:
+    """Whole-ensemble deviation scoring with all buffers and argument tables prepared ONCE.
+
+    One ``run()`` = the test script + group analysis of the reference for every member
+    (multimodal_kfold_test_cvae_supervised.py:107-141, ..._group_analysis_1x1.py:105-157):
+    reconstruct the training and the test rows, per-ROI normative statistics over the healthy-control
+    training rows, per-ROI / per-subject deviations and z-scores of the test rows, ROC-AUC of every
+    ROI z-score and of the subject score -- six libnmb launches, no per-member Python work.
+    Segments are (member, modality) pairs in member-major order."""
+
+    def __init__(self, trainer, train_xc, test_xc, train_hc_mask, test_labels, mode: str = "mean"):
+        self.tr = trainer
+        self.lib = _lib.load()
+        self.dev = trainer.device
+        self.mode = _lib.RECON_MEAN if mode == "mean" else _lib.RECON_SAMPLE
+        n = trainer.n
+        dev = self.dev
+        self._keep = [train_xc, test_xc, train_hc_mask, test_labels]
+        seg_member, seg_d, seg_ldx, n_tr, n_te = [], [], [], [], []
+        for i, s in enumerate(trainer.specs):
+            for k, d in enumerate(s.input_dims):
+                seg_member.append(i); seg_d.append(int(d)); seg_ldx.append(int(train_xc[i][k].shape[1]))
+                n_tr.append(int(train_xc[i][k].shape[0])); n_te.append(int(test_xc[i][k].shape[0]))
+        self.seg_member, self.seg_d, self.n_seg = seg_member, seg_d, len(seg_d)
+        self.n_train, self.n_test = n_tr, n_te
+        import numpy as np
+        d = np.asarray(seg_d, np.int64); ntr = np.asarray(n_tr, np.int64); nte = np.asarray(n_te, np.int64)
+        off = lambda sizes: np.concatenate([[0], np.cumsum((sizes + 3) // 4 * 4)])     # 16-byte aligned segments
+        self.o_hat_tr, self.o_hat_te, self.o_stats = off(ntr * d), off(nte * d), off(2 * d)
+        self.o_subj, self.o_auc = off(nte), off(d)
+        f32 = lambda m: torch.empty((int(m),), dtype=torch.float32, device=dev)
+        self.xhat_train, self.xhat_test = f32(self.o_hat_tr[-1]), f32(self.o_hat_te[-1])
+        self.stats, self.roi, self.z, self.subj = f32(self.o_stats[-1]), f32(self.o_hat_te[-1]), f32(self.o_hat_te[-1]), f32(self.o_subj[-1])
+        self.auc_roi = torch.empty((int(self.o_auc[-1]),), dtype=torch.float64, device=dev)
+        self.auc_subj = torch.empty((self.n_seg,), dtype=torch.float64, device=dev)
+        masks = [None if m is None else m.to(device=dev, dtype=torch.uint8).contiguous() for m in train_hc_mask]
+        labels = [l.to(device=dev, dtype=torch.uint8).contiguous() for l in test_labels]
+        self._keep += [masks, labels]
+        M = _lib.NMB_MAX_MOD
+
+        def member_table(xc, base, offsets):
+            xt, ot = [None] * (n * M), [None] * (n * M)
+            s = 0
+            for i, sp in enumerate(trainer.specs):
+                for k in range(len(sp.input_dims)):
+                    xt[i * M + k] = xc[i][k].data_ptr(); ot[i * M + k] = base.data_ptr() + 4 * int(offsets[s]); s += 1
+            return _lib.ptr_table(xt), _lib.ptr_table(ot)
+        self.t_xc_tr, self.t_hat_tr = member_table(train_xc, self.xhat_train, self.o_hat_tr)
+        self.t_xc_te, self.t_hat_te = member_table(test_xc, self.xhat_test, self.o_hat_te)
+        self.t_rows_tr = _lib.int_table([int(train_xc[i][0].shape[0]) for i in range(n)])
+        self.t_rows_te = _lib.int_table([int(test_xc[i][0].shape[0]) for i in range(n)])
+        seg = range(self.n_seg)
+        ptrs = lambda base, offsets, size: _lib.ptr_table([base.data_ptr() + size * int(offsets[s]) for s in seg])
+        flat = lambda xc: [xc[i][k] for i, sp in enumerate(trainer.specs) for k in range(len(sp.input_dims))]
+        self.s_x_tr = _lib.ptr_table([t.data_ptr() for t in flat(train_xc)])
+        self.s_x_te = _lib.ptr_table([t.data_ptr() for t in flat(test_xc)])
+        self.s_hat_tr, self.s_hat_te = ptrs(self.xhat_train, self.o_hat_tr, 4), ptrs(self.xhat_test, self.o_hat_te, 4)
+        self.s_stats, self.s_roi, self.s_z = ptrs(self.stats, self.o_stats, 4), ptrs(self.roi, self.o_hat_te, 4), ptrs(self.z, self.o_hat_te, 4)
+        self.s_subj, self.s_auc_roi = ptrs(self.subj, self.o_subj, 4), ptrs(self.auc_roi, self.o_auc, 8)
+        self.s_auc_subj = _lib.ptr_table([self.auc_subj.data_ptr() + 8 * s for s in seg])
+        self.s_mask = _lib.ptr_table([None if masks[seg_member[s]] is None else masks[seg_member[s]].data_ptr() for s in seg])
+        self.s_lab = _lib.ptr_table([labels[seg_member[s]].data_ptr() for s in seg])
+        self.s_ldx, self.s_d = _lib.int_table(seg_ldx), _lib.int_table(seg_d)
+        self.s_ntr, self.s_nte, self.s_one = _lib.int_table(n_tr), _lib.int_table(n_te), _lib.int_table([1] * self.n_seg)
+        self.launches_per_run = 6
+
+    def run(self):
+        lib, st = self.lib, _stream_ptr(self.dev)
+        with torch.cuda.device(self.dev):
+            _lib.check(lib.nmb_ensemble_reconstruct(self.tr.handle, self.t_xc_tr, self.t_rows_tr, self.mode, None,
+                                                    self.t_hat_tr, None, None, st), "nmb_ensemble_reconstruct")
+            _lib.check(lib.nmb_ensemble_reconstruct(self.tr.handle, self.t_xc_te, self.t_rows_te, self.mode, None,
+                                                    self.t_hat_te, None, None, st), "nmb_ensemble_reconstruct")
+            _lib.check(lib.nmb_normative_stats(self.n_seg, self.s_x_tr, self.s_ldx, self.s_hat_tr, self.s_mask, self.s_ntr,
+                                               self.s_d, self.s_stats, st), "nmb_normative_stats")
+            _lib.check(lib.nmb_deviation(self.n_seg, self.s_x_te, self.s_ldx, self.s_hat_te, self.s_stats, self.s_nte,
+                                         self.s_d, self.s_roi, self.s_z, self.s_subj, st), "nmb_deviation")
+            _lib.check(lib.nmb_auc(self.n_seg, self.s_z, self.s_lab, self.s_nte, self.s_d, self.s_auc_roi, None, st), "nmb_auc")
+            _lib.check(lib.nmb_auc(self.n_seg, self.s_subj, self.s_lab, self.s_nte, self.s_one, self.s_auc_subj, None, st),
+                       "nmb_auc")
+        self.tr.gpu_launches += self.launches_per_run
+        return self
+
+    # ---- views of segment s ----------------------------------------------------------------
+    def seg_stats(self, s):
+        return self.stats[int(self.o_stats[s]):int(self.o_stats[s]) + 2 * self.seg_d[s]].view(2, self.seg_d[s])
+
+    def seg_roi(self, s):
+        return self.roi[int(self.o_hat_te[s]):int(self.o_hat_te[s]) + self.n_test[s] * self.seg_d[s]].view(self.n_test[s], self.seg_d[s])
+
+    def seg_z(self, s):
+        return self.z[int(self.o_hat_te[s]):int(self.o_hat_te[s]) + self.n_test[s] * self.seg_d[s]].view(self.n_test[s], self.seg_d[s])
+
+    def seg_subj(self, s):
+        return self.subj[int(self.o_subj[s]):int(self.o_subj[s]) + self.n_test[s]]
+
+    def seg_auc_roi(self, s):
+        return self.auc_roi[int(self.o_auc[s]):int(self.o_auc[s]) + self.seg_d[s]]
+
+    def member_records(self) -> torch.Tensor:
+        """Fixed-size float64 record per segment {subject AUC | per-ROI mean | per-ROI std | per-ROI AUC}, padded
+        to the widest segment -- the payload of the multi-GPU all-gather (distributed.gather_member_tables)."""
+        import numpy as np
+        if not hasattr(self, "_rec_idx"):
+            dmax = max(self.seg_d)
+            w = 1 + 3 * dmax
+            src_s, dst_s, src_a, dst_a = [], [], [], []
+            for s, d in enumerate(self.seg_d):
+                cols = np.arange(d)
+                src_s += [self.o_stats[s] + cols, self.o_stats[s] + d + cols]
+                dst_s += [s * w + 1 + cols, s * w + 1 + dmax + cols]
+                src_a.append(self.o_auc[s] + cols); dst_a.append(s * w + 1 + 2 * dmax + cols)
+            t = lambda a: torch.from_numpy(np.concatenate(a).astype(np.int64)).to(self.dev)
+            self._rec_idx = (w, t(src_s), t(dst_s), t(src_a), t(dst_a),
+                             torch.arange(self.n_seg, device=self.dev, dtype=torch.long) * w)
+        w, src_s, dst_s, src_a, dst_a, dst0 = self._rec_idx
+        rec = torch.zeros((self.n_seg * w,), dtype=torch.float64, device=self.dev)
+        rec.index_copy_(0, dst_s, self.stats.index_select(0, src_s).double())
+        rec.index_copy_(0, dst_a, self.auc_roi.index_select(0, src_a))
+        rec.index_copy_(0, dst0, self.auc_subj)
+        return rec.view(self.n_seg, w)

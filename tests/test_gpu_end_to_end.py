@@ -154,3 +154,46 @@ def test_module_per_step_api_vs_reference(golden_dir, name):
         assert relerr(v.cpu().numpy(), g["final/" + k]) < 1e-5, k
     with pytest.raises(ValueError, match="No such combination method"):
         model.forward_multimodal(xs, cs, "concat")
+
+
+def test_deviation_scorer_equals_the_per_call_api():
+    """DeviationScorer (buffers + argument tables prepared once, six launches per pass) == the per-call
+    scoring API, bit for bit, on a heterogeneous ensemble with ragged / unaligned segment sizes."""
+    import numpy as np
+    import torch
+    from multi_modal_normative_modeling_b200 import EnsembleTrainer, MemberSpec, pack_rows, scoring
+    rng = np.random.RandomState(3)
+    specs, train, test, masks, labels = [], [], [], [], []
+    for k, (dims, n_tr, n_te) in enumerate([([17], 41, 13), ([9, 6], 30, 9), ([116], 64, 20), ([7], 25, 11)]):
+        c_tr = torch.zeros(n_tr, 5).cuda(); c_tr[:, k % 5] = 1
+        c_te = torch.zeros(n_te, 5).cuda(); c_te[:, k % 5] = 1
+        tr_x = [pack_rows(torch.from_numpy(rng.randn(n_tr, d).astype(np.float32)).cuda(), c_tr) for d in dims]
+        te_x = [pack_rows(torch.from_numpy(rng.randn(n_te, d).astype(np.float32)).cuda(), c_te) for d in dims]
+        specs.append(MemberSpec(dims, [12, 10], 4, 5, tr_x, batch=16, seed=k))
+        train.append(tr_x); test.append(te_x)
+        m = rng.rand(n_tr) < 0.7; m[:2] = True
+        masks.append(torch.from_numpy(m.astype(np.uint8)).cuda())
+        lab = (rng.rand(n_te) < 0.4).astype(np.uint8); lab[0], lab[-1] = 0, 1
+        labels.append(torch.from_numpy(lab).cuda())
+    torch.manual_seed(0)
+    tr = EnsembleTrainer(specs)
+    tr.params.normal_(0, 0.1)
+    tr.train_steps(3)
+    sc = scoring.DeviationScorer(tr, train, test, masks, labels).run()
+    hat_tr, _, _ = tr.reconstruct(train, mode="mean")
+    hat_te, _, _ = tr.reconstruct(test, mode="mean")
+    s = 0
+    for i, sp in enumerate(specs):
+        for k in range(len(sp.input_dims)):
+            stats = scoring.normative_stats([train[i][k]], [hat_tr[i][k]], [masks[i]])
+            roi, z, subj = scoring.deviation([test[i][k]], [hat_te[i][k]], stats)
+            assert torch.equal(sc.seg_stats(s), stats[0])
+            assert torch.equal(sc.seg_roi(s), roi[0]) and torch.equal(sc.seg_z(s), z[0]) and torch.equal(sc.seg_subj(s), subj[0])
+            assert torch.equal(sc.seg_auc_roi(s), scoring.auc(z, [labels[i]])[0])
+            assert torch.equal(sc.auc_subj[s:s + 1], scoring.auc(subj, [labels[i]])[0])
+            s += 1
+    rec = sc.member_records()
+    assert rec.shape == (sc.n_seg, 1 + 3 * 116)
+    assert torch.equal(rec[3, 1:117], sc.seg_stats(3)[0].double()) and torch.equal(rec[:, 0], sc.auc_subj)
+    assert torch.equal(rec[0, 1 + 2 * 116:1 + 2 * 116 + 17], sc.seg_auc_roi(0)) and float(rec[0, 1 + 17:1 + 116].abs().max()) == 0
+    tr.close()
