@@ -75,7 +75,8 @@ struct alignas(16) Step {
   unsigned char first;              // first MMA overwrites the accumulator
   unsigned char commit;             // 0 none, 1 always, 2 only when half 1 is inactive
   unsigned char commit_buf;         // accumulator barrier 0..3
-  unsigned char pad_[3];
+  unsigned char commit2, commit2_buf;   // optional second commit of the same step (same encoding)
+  unsigned char dep_grp;            // epilogue group whose counter `dep` refers to (0 / 1; 2 = both)
 };
 
 // Compact copy of the MMA-relevant fields of a Step.  The table travels in the KERNEL PARAMETERS (constant
@@ -86,7 +87,7 @@ struct MStep {
   unsigned short b_lbo, b_sbo, b_kadv, b_lo;
   unsigned short ksteps, n, tmem_col;
   short mma_dep, mma_dep_joint;
-  unsigned char half, a_tile, a_mn, b_mn, first, commit, commit_buf, pad_;
+  unsigned char half, a_tile, a_mn, b_mn, first, commit, commit_buf, commit2;   // commit2_buf = accumulator of `half`
 };
 constexpr int kMaxParamSteps = 640;                   // 40 B each: 25.6 KB of the 32 KB parameter space
 constexpr int kMaxParamArchs = 8;
@@ -101,7 +102,7 @@ inline MStep to_mstep(const Step& s) {
   m.ksteps = s.ksteps; m.n = s.n; m.tmem_col = s.tmem_col;
   m.mma_dep = (short)s.mma_dep; m.mma_dep_joint = (short)s.mma_dep_joint;
   m.half = s.half; m.a_tile = s.a_bytes ? 1 : 0; m.a_mn = s.a_mn; m.b_mn = s.b_mn;
-  m.first = s.first; m.commit = s.commit; m.commit_buf = s.commit_buf;
+  m.first = s.first; m.commit = s.commit; m.commit_buf = s.commit_buf; m.commit2 = s.commit2;
   return m;
 }
 
@@ -231,16 +232,20 @@ inline Program build_program(const ArchDesc& a) {
       lay.g0[m][h] = s_g0[m * 2 + h]; lay.dmulv[m][h] = s_dmulv[m * 2 + h];
     }
     lay.wout_cg[m] = round16(q.outl.in + 1) / 8;
-    lay.n_dxh_blk[m] = (q.D + 63) / 64;
-    lay.dxh_blk[m] = alloc((long long)2 * lay.n_dxh_blk[m] * 32768);
+    // decoder_mean_layer: with one modality and D <= 128 its output gradient stays in ACT[h] (regular layer);
+    // otherwise d/dx_recon goes through 64-column stash blocks and the weight gradient is transposed
+    const bool fast_out = M == 1 && q.D <= 128;
+    lay.n_dxh_blk[m] = fast_out ? 0 : (q.D + 63) / 64;
+    lay.dxh_blk[m] = alloc((long long)2 * lay.n_dxh_blk[m] * 32768 + 128);
     lay.mulv[m] = alloc((long long)256 * lay.ld_mulv * 4);
     lay.lampart[m] = alloc((long long)8 * round4(q.D) * 4);
     lay.x_cg[m] = round16(q.D + C + 1) / 8;
     for (int l = 0; l < L; ++l) { master(q.enc[l], 0); master(q.dec[l], 0); }
-    master(q.head, 0); master(q.outl, 1);
+    master(q.head, 0); master(q.outl, fast_out ? 0 : 1);
     for (int l = 0; l < L; ++l) w_enc[m].push_back(wblock(q.enc[l], 0, q.enc[l].out, round16(q.enc[l].out)));
     w_head[m] = wblock(q.head, 0, q.head.out, round16(q.head.out));
     for (int l = 0; l < L; ++l) w_dec[m].push_back(wblock(q.dec[l], 0, q.dec[l].out, round16(q.dec[l].out)));
+    if (fast_out) w_out[m].push_back(wblock(q.outl, 0, q.D, round16(q.D)));
     for (int t = 0; t < lay.n_dxh_blk[m]; ++t)
       w_out[m].push_back(wblock(q.outl, 64 * t, q.D - 64 * t < 64 ? q.D - 64 * t : 64, 64));
   }
@@ -313,7 +318,7 @@ inline Program build_program(const ArchDesc& a) {
     }
   };
   // dgrad-type group: acc[h][i] = sum_o ACT[h][., o] W[o][i], N-chunks of the weight block
-  auto emit_dgrad = [&](int h, const WRef& w, int n_need) {
+  auto emit_dgrad = [&](int h, const WRef& w, int n_need, bool commit) {
     const int buf = accbuf(h);
     const int tg = tile_groups(w.R);
     const int cg = (round16(n_need) / 8) < w.cg ? round16(n_need) / 8 : w.cg;
@@ -326,12 +331,15 @@ inline Program build_program(const ArchDesc& a) {
       s.tmem_col = (unsigned short)(kAcc0 + 128 * buf + g0 * 8);
       s.first = 1;
       if (j == 0) { need(s, act_ready[h]); need(s, acc_free[buf]); }
-      s.commit = g0 + tg >= cg ? 1 : 0; s.commit_buf = (unsigned char)buf;
+      s.commit = (commit && g0 + tg >= cg) ? 1 : 0; s.commit_buf = (unsigned char)buf;
       P.steps.push_back(s);
     }
   };
   // wgrad part for half h: wacc[wb][.., 64 j + ..) += ACT[h]^T (MN-major A) x B tiles (MN-major, N-chunks)
-  auto emit_wgrad_part = [&](int h, int wb, int b_space, long long b_base, int g_first, int g_count, int x_mod) {
+  // acc_commit: the part also commits acc[h] on its last step -- the preceding dgrad group of the same half
+  // left it open so that the epilogue overwriting ACT[h] cannot start before these MMAs have read ACT[h].
+  auto emit_wgrad_part = [&](int h, int wb, int b_space, long long b_base, int g_first, int g_count, int x_mod,
+                             bool acc_commit) {
     const int b_dep = b_space == SP_STASH ? ready[b_base] : 0;
     for (int g0 = 0; g0 < g_count; g0 += 8) {
       const int ng = g_count - g0 < 8 ? g_count - g0 : 8;
@@ -346,6 +354,7 @@ inline Program build_program(const ArchDesc& a) {
       const bool last = g0 + 8 >= g_count;
       s.commit = !last ? 0 : (h == 1 ? 1 : 2);
       s.commit_buf = (unsigned char)(2 + wb);
+      if (last && acc_commit) { s.commit2 = 1; s.commit2_buf = (unsigned char)accbuf(h); }
       P.steps.push_back(s);
     }
   };
@@ -404,6 +413,16 @@ inline Program build_program(const ArchDesc& a) {
         act_ready[h] = id; acc_free[accbuf(h)] = id;
       }
     }
+    if (lay.n_dxh_blk[m] == 0) {          // fast path: one tile, d/dx_recon planes land in ACT[h]
+      for (int h = 0; h < 2; ++h) {
+        emit_fwd(h, w_out[m][0], SP_NONE, 0, 0, 0);
+        Epi e = new_epi(EK_RECON, h, accbuf(h), m);
+        e.n_mma = w_out[m][0].R; e.n_valid = q.D; e.n_cols = round16(q.D); e.col0 = 0;
+        e.to_act = 1; e.last = 1;
+        const int id = push_epi(e);
+        act_ready[h] = id; acc_free[accbuf(h)] = id;
+      }
+    }
     for (int t = 0; t < lay.n_dxh_blk[m]; ++t) {
       for (int h = 0; h < 2; ++h) {
         emit_fwd(h, w_out[m][t], SP_NONE, 0, 0, 0);
@@ -419,128 +438,130 @@ inline Program build_program(const ArchDesc& a) {
   }
 
   // ================= backward =================
-  const int fence_id = push_epi(new_epi(EK_FENCE, 2, -1, 0));
-  for (int m = 0; m < M; ++m) {
-    const ModDesc& q = a.mod[m];
-    if (a.loss_kind == NMB_LOSS_GAUSS_LL) {
-      Epi e = new_epi(EK_LAM, 2, -1, m);
-      e.p_off = q.lam_off; e.p_cols = q.D;
-      push_epi(e);
-    }
-    if (m > 0) {   // ACT[h] <- last decoder hidden activation of this modality (transposed wgrad A operand)
-      for (int h = 0; h < 2; ++h) {
-        Epi e = new_epi(EK_COPY, h, -1, m);
-        e.src_off = s_k[m][(L - 1) * 2 + h]; e.src_cg = round16(q.outl.in + 1) / 8;
-        act_ready[h] = push_epi(e);
-      }
-    } else if (M > 1) {
-      // modality 0's activations were overwritten by later modalities' forward passes
-      for (int h = 0; h < 2; ++h) {
-        Epi e = new_epi(EK_COPY, h, -1, m);
-        e.src_off = s_k[m][(L - 1) * 2 + h]; e.src_cg = round16(q.outl.in + 1) / 8;
-        act_ready[h] = push_epi(e);
-      }
-    }
-    // decoder_mean_layer.  The dgrad MMAs are issued FIRST (they must read the pre-update weights, and the
-    // Adam epilogues below rewrite the weight planes); their epilogues -- which overwrite ACT[h], the A
-    // operand of the transposed wgrad -- run LAST.
-    int dg_ready[2];
-    for (int h = 0; h < 2; ++h) {
-      const int buf = accbuf(h);
-      for (int t = 0; t < lay.n_dxh_blk[m]; ++t) {
-        const WRef& w = w_out[m][t];
-        Step s = base_step(h);
-        set_b(s, SP_W, w.wp_off, 64, 0, w.cg, true);
-        set_a_kmajor(s, 0);
-        s.a_space = SP_STASH; s.a_off = lay.dxh_blk[m] + ((long long)h * lay.n_dxh_blk[m] + t) * 32768; s.a_bytes = 32768;
-        s.dep = dxh_ready[m * 2 + h];
-        s.ksteps = 4; s.n = (unsigned short)(w.cg * 8); s.tmem_col = (unsigned short)(kAcc0 + 128 * buf);
-        s.first = t == 0;
-        if (t == 0) need(s, acc_free[buf]);
-        s.commit = t == lay.n_dxh_blk[m] - 1 ? 1 : 0; s.commit_buf = (unsigned char)buf;
-        P.steps.push_back(s);
-      }
-      dg_ready[h] = 0;
-    }
-    // transposed wgrad, two 64-column blocks of D per item
-    for (int t0 = 0; t0 < lay.n_dxh_blk[m]; t0 += 2) {
-      const int wb = wacc_next; wacc_next ^= 1;
-      const int nt = lay.n_dxh_blk[m] - t0 < 2 ? lay.n_dxh_blk[m] - t0 : 2;
-      for (int h = 0; h < 2; ++h) {
-        for (int t = t0; t < t0 + nt; ++t) {
-          Step s = base_step(h);
-          set_b(s, SP_STASH, lay.dxh_blk[m] + ((long long)h * lay.n_dxh_blk[m] + t) * 32768, 128, 0, 8, true);
-          set_a_mnmajor(s);
-          s.dep = dxh_ready[m * 2 + h];
-          s.ksteps = 8; s.n = 64; s.tmem_col = (unsigned short)(kWacc0 + 128 * wb + 64 * (t - t0));
-          s.first = h == 0;
-          if (t == t0) { need(s, act_ready[h]); need(s, acc_free[2 + wb]); }
-          const bool last = t == t0 + nt - 1;
-          s.commit = !last ? 0 : (h == 1 ? 1 : 2);
-          s.commit_buf = (unsigned char)(2 + wb);
-          P.steps.push_back(s);
-        }
-      }
-      Epi e = new_epi(EK_WGRAD_T, 2, 2 + wb, m);
-      e.n_mma = 64 * nt; e.col0 = 64 * t0;
-      e.p_off = q.outl.off; e.p_ld = q.outl.ld; e.p_rows = q.outl.out; e.p_cols = q.outl.in + 1;
-      e.wp_off = w_out[m][0].wp_off; e.wp_R = 64; e.src_cg = w_out[m][0].cg;
-      e.mst_off = mst[q.outl.off].mst_off; e.mst_R = mst[q.outl.off].R;
-      acc_free[2 + wb] = push_epi(e);
-    }
-    for (int h = 0; h < 2; ++h) {
-      const int buf = accbuf(h);
-      Epi e = new_epi(EK_DGRAD, h, buf, m);
-      e.n_mma = round16(q.outl.in + 1); e.n_valid = q.outl.in; e.n_cols = round16(q.outl.in);
-      e.to_act = 1; e.src_off = s_k[m][(L - 1) * 2 + h];
-      const int id = push_epi(e);
-      act_ready[h] = id; acc_free[buf] = id;
-      (void)dg_ready;
-    }
-    // decoder hidden layers
-    for (int l = L - 1; l >= 0; --l) {
-      const LinDesc& w = q.dec[l];
-      const int in_cg = round16(w.in + 1) / 8;
+  // Generic-proxy stores to the stash become visible to the TMA (async proxy) at the per-half EK_FENCE item:
+  // every stash-sourced tile of half h waits for it (all of them are consumed in the backward pass).
+  int fence_id[2];
+  for (int h = 0; h < 2; ++h) fence_id[h] = push_epi(new_epi(EK_FENCE, h, -1, 0));
+
+  // One linear layer: [dgrad(h) ->] wgrad parts(h) per half, then the Adam items.  The dgrad MMAs come first
+  // so that they have consumed the pre-update weight planes before the wgrad accumulator is committed (the
+  // Adam epilogue waits for that commit); acc[h] is committed after the wgrad part, so the epilogue that
+  // overwrites ACT[h] cannot start before the wgrad MMAs have read it.
+  //   dg_kind: 0 = no data gradient (first encoder layer), 1 = EK_DGRAD, 2 = EK_DZ (decoder input: d/dz only)
+  auto layer_backward = [&](int m, const LinDesc& w, const WRef& wr, int b_space, const long long in_base[2],
+                            int dg_kind, int n_need, int x_mod) {
+    const int in_cg = round16(w.in + 1) / 8;
+    const int n_items = (in_cg + 15) / 16;
+    for (int it0 = 0; it0 < n_items; it0 += 2) {
+      const int it1 = it0 + 2 < n_items ? it0 + 2 : n_items;
+      const bool last_pair = it1 == n_items;
       const int wb0 = wacc_next;
-      const int n_items = (in_cg + 15) / 16;
       for (int h = 0; h < 2; ++h) {
+        if (dg_kind && it0 == 0) emit_dgrad(h, wr, n_need, false);
         int wb = wb0;
-        for (int it = 0; it < n_items; ++it, wb ^= 1) {
+        for (int it = it0; it < it1; ++it, wb ^= 1) {
           const int gf = it * 16, gc = in_cg - gf < 16 ? in_cg - gf : 16;
-          emit_wgrad_part(h, wb, SP_STASH, l == 0 ? s_g0[m * 2 + h] : s_k[m][(l - 1) * 2 + h], gf, gc, 0);
+          emit_wgrad_part(h, wb, b_space, in_base[h], gf, gc, x_mod, dg_kind && last_pair && it == it1 - 1);
         }
-        if (l > 0) {
-          emit_dgrad(h, w_dec[m][l], w.in);
-          Epi e = new_epi(EK_DGRAD, h, accbuf(h), m);
-          e.n_mma = round16(w.in); e.n_valid = w.in; e.n_cols = round16(w.in);
-          e.to_act = 1; e.src_off = s_k[m][(l - 1) * 2 + h];
-          const int id = push_epi(e);
-          act_ready[h] = id; acc_free[accbuf(h)] = id;
-        } else {
-          emit_dgrad(h, w_dec[m][0], Z);
-          Epi e = new_epi(EK_DZ, h, accbuf(h), m);
-          e.n_mma = round16(Z); e.n_valid = Z;
+        if (dg_kind && last_pair) {
+          Epi e = new_epi(dg_kind == 1 ? EK_DGRAD : EK_DZ, h, accbuf(h), m);
+          e.n_mma = round16(n_need); e.n_valid = n_need;
+          if (dg_kind == 1) { e.n_cols = round16(n_need); e.to_act = 1; e.src_off = in_base[h]; }
           const int id = push_epi(e);
           act_ready[h] = id; acc_free[accbuf(h)] = id;
         }
       }
       int wb = wb0;
-      for (int it = 0; it < n_items; ++it, wb ^= 1) {
+      for (int it = it0; it < it1; ++it, wb ^= 1) {
         Epi e = new_epi(EK_WGRAD, 2, 2 + wb, m);
         e.col0 = it * 128; e.n_mma = (in_cg - it * 16 < 16 ? in_cg - it * 16 : 16) * 8;
         e.p_off = w.off; e.p_ld = w.ld; e.p_rows = w.out; e.p_cols = w.in + 1;
-        e.wp_off = w_dec[m][l].wp_off; e.wp_R = w_dec[m][l].R;
+        e.wp_off = wr.wp_off; e.wp_R = wr.R;
         e.mst_off = mst[w.off].mst_off; e.mst_R = mst[w.off].R;
         acc_free[2 + wb] = push_epi(e);
       }
-      if (n_items & 1) wacc_next ^= 1;
+      if ((it1 - it0) & 1) wacc_next ^= 1;
+    }
+  };
+
+  for (int m = 0; m < M; ++m) {
+    const ModDesc& q = a.mod[m];
+    const long long k_last[2] = {s_k[m][(L - 1) * 2 + 0], s_k[m][(L - 1) * 2 + 1]};
+    if (lay.n_dxh_blk[m] == 0) {
+      // decoder_mean_layer as a regular layer: ACT[h] holds d/dx_recon (written by EK_RECON)
+      layer_backward(m, q.outl, w_out[m][0], SP_STASH, k_last, 1, q.outl.in, 0);
+    } else {
+      if (M > 1) {   // ACT[h] <- last decoder hidden activation of this modality (transposed wgrad A operand)
+        for (int h = 0; h < 2; ++h) {
+          Epi e = new_epi(EK_COPY, h, -1, m);
+          e.src_off = k_last[h]; e.src_cg = round16(q.outl.in + 1) / 8;
+          act_ready[h] = push_epi(e);
+        }
+      }
+      // dgrad MMAs first (pre-update weights), K-chunks over the d/dx_recon blocks; acc[h] is committed by the
+      // last transposed-wgrad part of the half, and the EK_DGRAD epilogues (which overwrite ACT[h]) come last
+      for (int h = 0; h < 2; ++h) {
+        const int buf = accbuf(h);
+        for (int t = 0; t < lay.n_dxh_blk[m]; ++t) {
+          const WRef& w = w_out[m][t];
+          Step s = base_step(h);
+          set_b(s, SP_W, w.wp_off, 64, 0, w.cg, true);
+          set_a_kmajor(s, 0);
+          s.a_space = SP_STASH; s.a_off = lay.dxh_blk[m] + ((long long)h * lay.n_dxh_blk[m] + t) * 32768; s.a_bytes = 32768;
+          s.ksteps = 4; s.n = (unsigned short)(w.cg * 8); s.tmem_col = (unsigned short)(kAcc0 + 128 * buf);
+          s.first = t == 0;
+          if (t == 0) need(s, acc_free[buf]);
+          s.commit_buf = (unsigned char)buf;
+          P.steps.push_back(s);
+        }
+      }
+      // transposed wgrad, two 64-column blocks of D per item
+      for (int t0 = 0; t0 < lay.n_dxh_blk[m]; t0 += 2) {
+        const int wb = wacc_next; wacc_next ^= 1;
+        const int nt = lay.n_dxh_blk[m] - t0 < 2 ? lay.n_dxh_blk[m] - t0 : 2;
+        const bool last_item = t0 + 2 >= lay.n_dxh_blk[m];
+        for (int h = 0; h < 2; ++h) {
+          for (int t = t0; t < t0 + nt; ++t) {
+            Step s = base_step(h);
+            set_b(s, SP_STASH, lay.dxh_blk[m] + ((long long)h * lay.n_dxh_blk[m] + t) * 32768, 128, 0, 8, true);
+            set_a_mnmajor(s);
+            s.ksteps = 8; s.n = 64; s.tmem_col = (unsigned short)(kWacc0 + 128 * wb + 64 * (t - t0));
+            s.first = h == 0;
+            if (t == t0) { need(s, act_ready[h]); need(s, acc_free[2 + wb]); }
+            const bool last = t == t0 + nt - 1;
+            s.commit = !last ? 0 : (h == 1 ? 1 : 2);
+            s.commit_buf = (unsigned char)(2 + wb);
+            if (last && last_item) { s.commit2 = 1; s.commit2_buf = (unsigned char)accbuf(h); }
+            P.steps.push_back(s);
+          }
+        }
+        Epi e = new_epi(EK_WGRAD_T, 2, 2 + wb, m);
+        e.n_mma = 64 * nt; e.col0 = 64 * t0;
+        e.p_off = q.outl.off; e.p_ld = q.outl.ld; e.p_rows = q.outl.out; e.p_cols = q.outl.in + 1;
+        e.wp_off = w_out[m][0].wp_off; e.wp_R = 64; e.src_cg = w_out[m][0].cg;
+        e.mst_off = mst[q.outl.off].mst_off; e.mst_R = mst[q.outl.off].R;
+        acc_free[2 + wb] = push_epi(e);
+      }
+      for (int h = 0; h < 2; ++h) {
+        const int buf = accbuf(h);
+        Epi e = new_epi(EK_DGRAD, h, buf, m);
+        e.n_mma = round16(q.outl.in + 1); e.n_valid = q.outl.in; e.n_cols = round16(q.outl.in);
+        e.to_act = 1; e.src_off = k_last[h];
+        const int id = push_epi(e);
+        act_ready[h] = id; acc_free[buf] = id;
+      }
+    }
+    // decoder hidden layers
+    for (int l = L - 1; l >= 0; --l) {
+      const long long in_base[2] = {l == 0 ? s_g0[m * 2 + 0] : s_k[m][(l - 1) * 2 + 0],
+                                    l == 0 ? s_g0[m * 2 + 1] : s_k[m][(l - 1) * 2 + 1]};
+      layer_backward(m, q.dec[l], w_dec[m][l], SP_STASH, in_base, l > 0 ? 1 : 2, l > 0 ? q.dec[l].in : Z, 0);
     }
   }
   for (int h = 0; h < 2; ++h) {
     Epi e = new_epi(EK_LATENT_BWD, h, -1, 0);
     e.to_act = 1;
     act_ready[h] = push_epi(e);
-    for (int m = 0; m < M; ++m) ready[s_dmulv[m * 2 + h]] = act_ready[h];
   }
   for (int m = 0; m < M; ++m) {
     const ModDesc& q = a.mod[m];
@@ -556,47 +577,30 @@ inline Program build_program(const ArchDesc& a) {
       const bool is_head = l == L;
       const LinDesc& w = is_head ? q.head : q.enc[l];
       const WRef& wr = is_head ? w_head[m] : w_enc[m][l];
-      const int in_cg = round16(w.in + 1) / 8;
-      const int n_items = (in_cg + 15) / 16;
-      // two wgrad accumulators: items are emitted in pairs (only layer 0 -- which has no dgrad -- can
-      // have more than one item, its input being the [x | c | 1] row)
-      for (int it0 = 0; it0 < n_items; it0 += 2) {
-        const int it1 = it0 + 2 < n_items ? it0 + 2 : n_items;
-        const int wb0 = wacc_next;
-        for (int h = 0; h < 2; ++h) {
-          int wb = wb0;
-          for (int it = it0; it < it1; ++it, wb ^= 1) {
-            const int gf = it * 16, gc = in_cg - gf < 16 ? in_cg - gf : 16;
-            if (!is_head && l == 0) emit_wgrad_part(h, wb, SP_X, 0, gf, gc, m);
-            else emit_wgrad_part(h, wb, SP_STASH, s_h[m][((is_head ? L : l) - 1) * 2 + h], gf, gc, 0);
-          }
-          if ((is_head || l > 0) && it1 == n_items) {
-            emit_dgrad(h, wr, w.in);
-            Epi e = new_epi(EK_DGRAD, h, accbuf(h), m);
-            e.n_mma = round16(w.in); e.n_valid = w.in; e.n_cols = round16(w.in);
-            e.to_act = 1; e.src_off = s_h[m][((is_head ? L : l) - 1) * 2 + h];
-            const int id = push_epi(e);
-            act_ready[h] = id; acc_free[accbuf(h)] = id;
-          }
-        }
-        int wb = wb0;
-        for (int it = it0; it < it1; ++it, wb ^= 1) {
-          Epi e = new_epi(EK_WGRAD, 2, 2 + wb, m);
-          e.col0 = it * 128; e.n_mma = (in_cg - it * 16 < 16 ? in_cg - it * 16 : 16) * 8;
-          e.p_off = w.off; e.p_ld = w.ld; e.p_rows = w.out; e.p_cols = w.in + 1;
-          e.wp_off = wr.wp_off; e.wp_R = wr.R;
-          e.mst_off = mst[w.off].mst_off; e.mst_R = mst[w.off].R;
-          acc_free[2 + wb] = push_epi(e);
-        }
-        if ((it1 - it0) & 1) wacc_next ^= 1;
+      if (!is_head && l == 0) {
+        const long long xb[2] = {0, 0};
+        layer_backward(m, w, wr, SP_X, xb, 0, 0, m);
+      } else {
+        const int li = (is_head ? L : l) - 1;
+        const long long in_base[2] = {s_h[m][li * 2 + 0], s_h[m][li * 2 + 1]};
+        layer_backward(m, w, wr, SP_STASH, in_base, 1, w.in, 0);
       }
     }
   }
+  // logvar_out: needs the partial sums of BOTH halves -> joint item, placed at the end of the step so that the
+  // rendezvous of the two epilogue groups costs nothing (the value is next used by EK_RECON of the next step)
+  if (a.loss_kind == NMB_LOSS_GAUSS_LL) {
+    for (int m = 0; m < M; ++m) {
+      Epi e = new_epi(EK_LAM, 2, -1, m);
+      e.p_off = a.mod[m].lam_off; e.p_cols = a.mod[m].D;
+      push_epi(e);
+    }
+  }
   push_epi(new_epi(EK_STEP_END, 2, -1, 0));
-  // Generic-proxy stores to the stash become visible to the TMA (async proxy) at the EK_FENCE item only:
-  // every stash-sourced tile waits for it (all of them are consumed in the backward pass).
-  for (Step& s : P.steps)
-    if ((s.a_space == SP_STASH || s.b_space == SP_STASH) && s.dep < fence_id) s.dep = fence_id;
+  for (Step& s : P.steps) {
+    s.dep_grp = 2;
+    if (s.a_space == SP_STASH || s.b_space == SP_STASH) { s.dep = fence_id[s.half]; s.dep_grp = s.half; }
+  }
   return P;
 }
 

@@ -104,9 +104,11 @@ __device__ void producer_role(const TrainLaunch& t, const ProgramDev& pg, const 
     for (int k = 0; k < pg.n_steps; ++k) {
       const Step& st = pg.steps[k];
       if (sv.rows_h[st.half] == 0) continue;
-      uint32_t need = st.dep ? sv.base + (uint32_t)st.dep : 0u;
-      if (st.b_space == SP_W) need = max(need, sv.base);
-      if (need) wait_both(ctl->epi_done, need);
+      if (st.dep) {              // data written by an epilogue item of this step (stash blocks behind their fence)
+        if (st.dep_grp < 2) wait_epi(&ctl->epi_done[st.dep_grp], sv.base + (uint32_t)st.dep);
+        else wait_both(ctl->epi_done, sv.base + (uint32_t)st.dep);
+      }
+      if (st.b_space == SP_W) wait_both(ctl->epi_done, sv.base);   // weight planes: every Adam item of the previous step
       TRACE(tr, tb + 2 * k);
       for (int which = 0; which < 2; ++which) {
         const int space = which == 0 ? st.a_space : st.b_space;
@@ -200,6 +202,7 @@ __device__ void mma_role(const LaunchP& L, int ai, const MemberDev& mb, unsigned
         tc::mma_commit(&ctl->empty[slot_b]);
         if (slot_a != kSlots) tc::mma_commit(&ctl->empty[slot_a]);
         if (st.commit == 1 || (st.commit == 2 && !half1)) tc::mma_commit(&ctl->accbar[st.commit_buf]);
+        if (st.commit2) tc::mma_commit(&ctl->accbar[st.half]);
         if (tr) g_trace[tb + 3 * (k - k0) + 2] = gtime();
       }
       __syncwarp();
@@ -480,14 +483,14 @@ __device__ __forceinline__ void epi_recon(EpiCtx& c, const Epi& e) {
   const float inv_rows_d = inv_rows / q.D;
   const float ll_scale = gauss ? inv_rows : inv_rows_d;
   const float* P = c.mb->params;
-  unsigned char* st = c.stash + e.stash_off;
+  unsigned char* st = e.to_act ? c.smem + h * kActBytes : c.stash + e.stash_off;   // d/dx_recon planes
   const int grow = c.row0 + 128 * h + c.row;
   const float* xrow = c.mb->xc[e.mod] + (long long)grow * q.ldx;
   float* keep = (c.flags & NMB_TRAIN_KEEP_ACTS) ? c.scratch + q.s_xr + (long long)(128 * h + c.row) * q.ld_xh : nullptr;
   float* lampart = reinterpret_cast<float*>(c.stash + lay.lampart[e.mod]) + (long long)(h * 4 + (c.warp & 3)) * round4(q.D);
-  const int n_valid = e.n_valid, col0 = e.col0, tcol = e.tmem_col;
+  const int n_valid = e.n_valid, col0 = e.col0, tcol = e.tmem_col, n_cols = e.n_cols;
   const long long lam_off = q.lam_off;
-  for (int ch = c.cpart; ch < 4; ch += c.parts) {
+  for (int ch = c.cpart; ch * 16 < n_cols; ch += c.parts) {
     const int col = ch * 16, gc = col0 + col;
     int nv = n_valid - col; nv = nv < 0 ? 0 : (nv > 16 ? 16 : nv);
     float v[16], xt[16], l[16], gr[16], qv[16];
@@ -906,7 +909,7 @@ __device__ void epilogue_role(const TrainLaunch& t, int mi, EpiCtx& c, uint32_t&
         case EK_HEAD: epi_head(c, e); break;
         case EK_LATENT: epi_latent(c, e, eps); fence = 1; break;
         case EK_COPY: epi_copy(c, e); fence = 1; break;
-        case EK_RECON: epi_recon(c, e); break;
+        case EK_RECON: epi_recon(c, e); fence = e.to_act ? 1 : 0; break;
         case EK_LAM: epi_lam(c, e); break;
         case EK_DGRAD: epi_dgrad(c, e); fence = 1; break;
         case EK_DZ: epi_dz(c, e); break;
