@@ -140,8 +140,9 @@ int setup_tcp(NmbEnsemble* e) {
   void* wbuf = nullptr;
   CU(dev_alloc((size_t)wtotal, &wbuf));
   // dataset planes: one buffer per distinct (rows pointer, n_rows, batch, width)
-  struct Key { const float* xc; int n_rows, batch, ldx, k_valid; };
-  std::vector<Key> keys; std::vector<unsigned char*> bufs; std::vector<tcp::XPrepItem> items;
+  struct Key { const float* xc; int n_rows, batch, ldx, k_valid, z, c; };
+  struct Bufs { unsigned char* x; unsigned char* cp; float* xlm; };
+  std::vector<Key> keys; std::vector<Bufs> bufs; std::vector<tcp::XPrepItem> items;
   std::vector<tcp::MemberTc> mtc(e->n_members);
   for (int i = 0; i < e->n_members; ++i) {
     const MemberDev& md = e->members_host[i];
@@ -152,24 +153,28 @@ int setup_tcp(NmbEnsemble* e) {
     mt.n_half = (md.batch + 127) / 128;
     for (int m = 0; m < d.M; ++m) {
       const ModDesc& q = d.mod[m];
-      Key k{md.xc[m], md.n_rows, md.batch, q.ldx, q.D + d.C + 1};
+      Key k{md.xc[m], md.n_rows, md.batch, q.ldx, q.D + d.C + 1, d.Z, d.C};
       int found = -1;
       for (size_t j = 0; j < keys.size(); ++j)
         if (keys[j].xc == k.xc && keys[j].n_rows == k.n_rows && keys[j].batch == k.batch && keys[j].ldx == k.ldx &&
-            keys[j].k_valid == k.k_valid) { found = (int)j; break; }
+            keys[j].k_valid == k.k_valid && keys[j].z == k.z && keys[j].c == k.c) { found = (int)j; break; }
       if (found < 0) {
         const int cg = tcp::round16(k.k_valid) / 8;
         const int spe = (k.n_rows + k.batch - 1) / k.batch;
         const long long blocks = (long long)(spe > 0 ? spe : 1) * mt.n_half;
-        void* xb = nullptr;
+        const int c_cg = tcp::round16(d.Z + d.C + 1) / 8, quads = (q.D + 3) / 4;
+        void *xb = nullptr, *cb = nullptr, *lb = nullptr;
         CU(dev_alloc((size_t)(blocks * cg * 4096), &xb));
-        keys.push_back(k); bufs.push_back((unsigned char*)xb);
-        tcp::XPrepItem it{k.xc, (unsigned char*)xb, k.n_rows, k.batch, k.ldx, k.k_valid, cg, mt.n_half};
+        CU(dev_alloc((size_t)(blocks * c_cg * 4096), &cb));
+        CU(dev_alloc((size_t)(blocks * quads * 2048), &lb));
+        keys.push_back(k); bufs.push_back(Bufs{(unsigned char*)xb, (unsigned char*)cb, (float*)lb});
+        tcp::XPrepItem it{k.xc, (unsigned char*)xb, (unsigned char*)cb, (float*)lb, k.n_rows, k.batch, k.ldx, k.k_valid,
+                          cg, mt.n_half, q.D, d.C, d.Z, c_cg, quads};
         items.push_back(it);
         if ((int)blocks > e->xprep_max_blocks) e->xprep_max_blocks = (int)blocks;
         found = (int)keys.size() - 1;
       }
-      mt.xplanes[m] = bufs[found];
+      mt.xplanes[m] = bufs[found].x; mt.cplanes[m] = bufs[found].cp; mt.xlm[m] = bufs[found].xlm;
     }
   }
   CU(upload(mtc.data(), sizeof(tcp::MemberTc) * mtc.size(), &p));

@@ -56,7 +56,9 @@ enum EpiKind : int {
   EK_WGRAD,           // weight gradient (rows = out) fused with Adam; planes of the new weights
   EK_WGRAD_T,         // transposed weight gradient of decoder_mean_layer (rows = in)
   EK_STEP_END,        // loss reduction, alpha (gPoE) update; publishes the new weight planes to the TMA proxy
-  EK_FENCE            // publishes every stash block written so far to the TMA proxy (start of the backward pass)
+  EK_FENCE,           // publishes every stash block written so far to the TMA proxy (start of the backward pass)
+  EK_HEAD_LATENT,     // one modality, Z <= 16: head accumulator -> reparameterisation -> [z | c | 1] planes, in registers
+  EK_DZ_LATENT_BWD    // one modality, Z <= 16: d/dz accumulator -> d[mu | logvar] planes, in registers
 };
 
 // One ring tile (+ optional A tile) and the MMAs issued on it.
@@ -152,6 +154,8 @@ struct Layout {
   long long wplanes_bytes;
   long long master_floats;                        // per moment; the slot holds 3 of them (p, m, v)
   int x_cg[NMB_MAX_MOD];                          // column groups of a dataset block
+  int x_quads[NMB_MAX_MOD];                       // 4-column groups of a lane-major target block
+  int c_cg;                                       // column groups of a decoder-input template block
 };
 
 struct Program {
@@ -172,11 +176,16 @@ struct ProgramDev {          // per architecture, device pointers
 struct MemberTc {            // per member
   unsigned char* wplanes;
   const unsigned char* xplanes[NMB_MAX_MOD];   // dataset blocks [pos][half], 128 rows each
+  const unsigned char* cplanes[NMB_MAX_MOD];   // decoder-input templates [0 (Z) | c | 1] per block, canonical planes
+  const float* xlm[NMB_MAX_MOD];               // ROI targets per block, lane-major fp32: [(col>>2)][row][4]
   int n_half;                                  // halves per minibatch = ceil(batch / 128)
 };
 
 // One dataset (packed fp32 rows of one modality) to be re-tiled into 128-row blocks per (minibatch, half).
-struct XPrepItem { const float* xc; unsigned char* out; int n_rows, batch, ldx, k_valid, cg, n_half; };
+struct XPrepItem {
+  const float* xc; unsigned char* out; unsigned char* cplanes; float* xlm;
+  int n_rows, batch, ldx, k_valid, cg, n_half, d, c_dim, z, c_cg, quads;
+};
 
 __host__ __device__ inline int round16(int v) { return (v + 15) & ~15; }
 
@@ -219,6 +228,7 @@ inline Program build_program(const ArchDesc& a) {
   std::vector<std::vector<WRef>> w_enc(M), w_dec(M), w_out(M);
   std::vector<WRef> w_head(M);
   lay.ld_mulv = round4(2 * Z);
+  lay.c_cg = round16(Z + C + 1) / 8;
   for (int m = 0; m < M; ++m) {
     const ModDesc& q = a.mod[m];
     s_h[m].resize(L * 2); s_k[m].resize(L * 2);
@@ -240,6 +250,7 @@ inline Program build_program(const ArchDesc& a) {
     lay.mulv[m] = alloc((long long)256 * lay.ld_mulv * 4);
     lay.lampart[m] = alloc((long long)8 * round4(q.D) * 4);
     lay.x_cg[m] = round16(q.D + C + 1) / 8;
+    lay.x_quads[m] = (q.D + 3) / 4;
     for (int l = 0; l < L; ++l) { master(q.enc[l], 0); master(q.dec[l], 0); }
     master(q.head, 0); master(q.outl, fast_out ? 0 : 1);
     for (int l = 0; l < L; ++l) w_enc[m].push_back(wblock(q.enc[l], 0, q.enc[l].out, round16(q.enc[l].out)));
@@ -360,6 +371,7 @@ inline Program build_program(const ArchDesc& a) {
   };
 
   int wacc_next = 0;
+  const bool fused_latent = M == 1 && Z <= 16;     // head -> latent and d/dz -> latent backward stay in registers
   const int nl = a.non_linear;
   (void)nl;
 
@@ -377,7 +389,15 @@ inline Program build_program(const ArchDesc& a) {
         act_ready[h] = id; acc_free[accbuf(h)] = id;
       }
     }
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < 2 && fused_latent; ++h) {
+      emit_fwd(h, w_head[m], SP_NONE, 0, 0, 0);
+      Epi e = new_epi(EK_HEAD_LATENT, h, accbuf(h), m);
+      e.n_mma = w_head[m].R; e.to_act = 1;
+      const int id = push_epi(e);
+      act_ready[h] = id; acc_free[accbuf(h)] = id;
+      ready[s_g0[m * 2 + h]] = id;
+    }
+    for (int h = 0; h < 2 && !fused_latent; ++h) {
       emit_fwd(h, w_head[m], SP_NONE, 0, 0, 0);
       Epi e = new_epi(EK_HEAD, h, accbuf(h), m);
       e.n_mma = w_head[m].R; e.n_valid = 2 * Z; e.n_cols = round16(2 * Z);
@@ -386,7 +406,7 @@ inline Program build_program(const ArchDesc& a) {
       if (act_ready[h] < id) act_ready[h] = id;      // ACT[h] may be overwritten only after the head read it
     }
   }
-  for (int h = 0; h < 2; ++h) {
+  for (int h = 0; h < 2 && !fused_latent; ++h) {
     Epi e = new_epi(EK_LATENT, h, -1, 0);
     e.to_act = 1;
     const int id = push_epi(e);
@@ -464,9 +484,10 @@ inline Program build_program(const ArchDesc& a) {
           emit_wgrad_part(h, wb, b_space, in_base[h], gf, gc, x_mod, dg_kind && last_pair && it == it1 - 1);
         }
         if (dg_kind && last_pair) {
-          Epi e = new_epi(dg_kind == 1 ? EK_DGRAD : EK_DZ, h, accbuf(h), m);
+          Epi e = new_epi(dg_kind == 1 ? EK_DGRAD : (fused_latent ? EK_DZ_LATENT_BWD : EK_DZ), h, accbuf(h), m);
           e.n_mma = round16(n_need); e.n_valid = n_need;
           if (dg_kind == 1) { e.n_cols = round16(n_need); e.to_act = 1; e.src_off = in_base[h]; }
+          else if (fused_latent) e.to_act = 1;
           const int id = push_epi(e);
           act_ready[h] = id; acc_free[accbuf(h)] = id;
         }
@@ -558,7 +579,7 @@ inline Program build_program(const ArchDesc& a) {
       layer_backward(m, q.dec[l], w_dec[m][l], SP_STASH, in_base, l > 0 ? 1 : 2, l > 0 ? q.dec[l].in : Z, 0);
     }
   }
-  for (int h = 0; h < 2; ++h) {
+  for (int h = 0; h < 2 && !fused_latent; ++h) {
     Epi e = new_epi(EK_LATENT_BWD, h, -1, 0);
     e.to_act = 1;
     act_ready[h] = push_epi(e);

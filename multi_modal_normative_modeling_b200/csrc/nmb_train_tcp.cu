@@ -223,7 +223,7 @@ struct EpiCtx {
   int tid, nthr;            // thread index / count of the current item's worker set
   int bar_id, bar_nthr;     // named barrier of that worker set
   unsigned flags;
-  int rows, rows_h0, rows_h1, row0;
+  int rows, rows_h0, rows_h1, row0, pos;
   long long step;           // global 0-based minibatch step of this member (Philox counter, Adam t - 1)
   float step_size, inv_bc2, b1, b2, aeps;
   float kl_acc, ll_acc;
@@ -472,6 +472,8 @@ __device__ __forceinline__ void epi_copy(EpiCtx& c, const Epi& e) {
   for (int u = c.tid; u < n; u += c.nthr) dst[u] = src[u];
 }
 
+// x_recon tile: loss terms, d(total)/d(x_recon) planes (ACT[h] or stash), logvar_out gradient partials.
+// 8 columns (one plane group) per iteration keeps the live registers under the 96-register budget.
 __device__ __forceinline__ void epi_recon(EpiCtx& c, const Epi& e) {
   const ArchDesc& a = *c.a;
   const ModDesc& q = a.mod[e.mod];
@@ -482,27 +484,39 @@ __device__ __forceinline__ void epi_recon(EpiCtx& c, const Epi& e) {
   const float inv_rows = 1.f / c.rows;
   const float inv_rows_d = inv_rows / q.D;
   const float ll_scale = gauss ? inv_rows : inv_rows_d;
-  const float* P = c.mb->params;
+  const float* __restrict__ lam = c.mb->params + q.lam_off;
   unsigned char* st = e.to_act ? c.smem + h * kActBytes : c.stash + e.stash_off;   // d/dx_recon planes
-  const int grow = c.row0 + 128 * h + c.row;
-  const float* xrow = c.mb->xc[e.mod] + (long long)grow * q.ldx;
+  // ROI targets of this row, lane-major: float4 (col quad) of 32 consecutive rows = 512 contiguous bytes
+  const float* __restrict__ xq = c.mt->xlm[e.mod] + ((long long)(c.pos * c.mt->n_half + h) * lay.x_quads[e.mod] * 128 + c.row) * 4;
   float* keep = (c.flags & NMB_TRAIN_KEEP_ACTS) ? c.scratch + q.s_xr + (long long)(128 * h + c.row) * q.ld_xh : nullptr;
   float* lampart = reinterpret_cast<float*>(c.stash + lay.lampart[e.mod]) + (long long)(h * 4 + (c.warp & 3)) * round4(q.D);
-  const int n_valid = e.n_valid, col0 = e.col0, tcol = e.tmem_col, n_cols = e.n_cols;
-  const long long lam_off = q.lam_off;
-  for (int ch = c.cpart; ch * 16 < n_cols; ch += c.parts) {
-    const int col = ch * 16, gc = col0 + col;
-    int nv = n_valid - col; nv = nv < 0 ? 0 : (nv > 16 ? 16 : nv);
-    float v[16], xt[16], l[16], gr[16], qv[16];
+  const int n_valid = e.n_valid, col0 = e.col0, tcol = e.tmem_col, n_cols = e.n_cols, D = q.D;
+  float ll = 0.f;
+  for (int ch = c.cpart; ch * 8 < n_cols; ch += c.parts) {
+    const int col = ch * 8, gc = col0 + col;
+    const int nv = min(max(n_valid - col, 0), 8);
+    float v[8], xt[8], l[8];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) { xt[j] = 0.f; l[j] = 0.f; }
-    if (vr && nv > 0) load16(xrow + gc, nv, 0.f, xt);
-    if (gauss && nv > 0) load16(P + lam_off + gc, nv, 0.f, l);
+    for (int j = 0; j < 8; ++j) { xt[j] = 0.f; l[j] = 0.f; }
+    if (nv > 0) {
+      if (vr) {
+        const float4 t0 = *reinterpret_cast<const float4*>(xq + (long long)(gc >> 2) * 512);
+        xt[0] = t0.x; xt[1] = t0.y; xt[2] = t0.z; xt[3] = t0.w;
+        if (gc + 4 < D) {
+          const float4 t1 = *reinterpret_cast<const float4*>(xq + (long long)((gc >> 2) + 1) * 512);
+          xt[4] = t1.x; xt[5] = t1.y; xt[6] = t1.z; xt[7] = t1.w;
+        }
+      }
+      if (gauss) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if (j < nv) l[j] = lam[gc + j];
+      }
+    }
     __syncwarp();
-    tc::tmem_ld16(taddr(c, tcol + col), v);
-    float ll = 0.f;
+    tc::tmem_ld8(taddr(c, tcol + col), v);
+    float gr[8], qv[8];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
+    for (int j = 0; j < 8; ++j) {
       const bool ok = vr && j < nv;
       const float r = xt[j] - v[j];
       float t, g, qq = 0.f;
@@ -519,44 +533,36 @@ __device__ __forceinline__ void epi_recon(EpiCtx& c, const Epi& e) {
       gr[j] = ok ? g : 0.f;
       qv[j] = ok ? qq : 0.f;
     }
-    c.ll_acc += ll * ll_scale;
+    put_planes(st, ch, c.row, gr);
+    if (keep && vr && nv > 0) {
 #pragma unroll
-    for (int qd = 0; qd < 2; ++qd) {
-      float x[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) x[j] = gr[8 * qd + j];
-      put_planes(st, 2 * ch + qd, c.row, x);
+      for (int j = 0; j < 8; ++j) if (j < nv) keep[gc + j] = v[j];
     }
-    if (keep && vr && nv > 0) store16(keep + gc, nv, v);
     if (gauss) {
-      // column sums over the 32 rows of this warp: 16 values -> lanes 0..15 in 16+8+4+2+1 shuffles
-      float s8[8], s4[4], s2[2], s1;
-      const bool up16 = c.lane & 16, up8 = c.lane & 8, up4 = c.lane & 4, up2 = c.lane & 2;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float keepv = up16 ? qv[j + 8] : qv[j], send = up16 ? qv[j] : qv[j + 8];
-        s8[j] = keepv + __shfl_xor_sync(0xffffffffu, send, 16);
-      }
+      // column sums over the 32 rows of this warp: 8 values -> lanes (bit4,bit3,bit2) in 4+2+1+1+1 shuffles
+      float s4[4], s2[2], s1;
+      const bool up16 = c.lane & 16, up8 = c.lane & 8, up4 = c.lane & 4;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float keepv = up8 ? s8[j + 4] : s8[j], send = up8 ? s8[j] : s8[j + 4];
-        s4[j] = keepv + __shfl_xor_sync(0xffffffffu, send, 8);
+        const float keepv = up16 ? qv[j + 4] : qv[j], send = up16 ? qv[j] : qv[j + 4];
+        s4[j] = keepv + __shfl_xor_sync(0xffffffffu, send, 16);
       }
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        const float keepv = up4 ? s4[j + 2] : s4[j], send = up4 ? s4[j] : s4[j + 2];
-        s2[j] = keepv + __shfl_xor_sync(0xffffffffu, send, 4);
+        const float keepv = up8 ? s4[j + 2] : s4[j], send = up8 ? s4[j] : s4[j + 2];
+        s2[j] = keepv + __shfl_xor_sync(0xffffffffu, send, 8);
       }
       {
-        const float keepv = up2 ? s2[1] : s2[0], send = up2 ? s2[0] : s2[1];
-        s1 = keepv + __shfl_xor_sync(0xffffffffu, send, 2);
+        const float keepv = up4 ? s2[1] : s2[0], send = up4 ? s2[0] : s2[1];
+        s1 = keepv + __shfl_xor_sync(0xffffffffu, send, 4);
       }
+      s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
       s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
-      // lane holds column: bit4 -> +8, bit3 -> +4, bit2 -> +2, bit1 -> +1
-      const int cj = ((c.lane >> 4) & 1) * 8 + ((c.lane >> 3) & 1) * 4 + ((c.lane >> 2) & 1) * 2 + ((c.lane >> 1) & 1);
-      if (!(c.lane & 1) && cj < nv) lampart[gc + cj] = s1;
+      const int cj = ((c.lane >> 4) & 1) * 4 + ((c.lane >> 3) & 1) * 2 + ((c.lane >> 2) & 1);
+      if (!(c.lane & 3) && cj < nv) lampart[gc + cj] = s1;
     }
   }
+  c.ll_acc += ll * ll_scale;
 }
 
 __device__ __forceinline__ void epi_lam(EpiCtx& c, const Epi& e) {
@@ -809,6 +815,115 @@ __device__ __forceinline__ void epi_wgrad_t(EpiCtx& c, const Epi& e) {
   }
 }
 
+// ---- one modality, Z <= 16: head accumulator -> reparameterisation -> decoder input, all in registers --------
+// One thread per minibatch row (the 4 warps of the group that own the TMEM lanes); cVAE.py:1130-1139, 199.
+__device__ __forceinline__ float bf16pair_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16pair_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+
+// Pre-phase (before the accumulator barrier is waited on, so it overlaps the head GEMM): the Philox draws of this
+// half, spread over the whole group, written to the eps array the backward pass reads anyway.
+__device__ void epi_head_latent_pre(EpiCtx& c, const Epi& e, const float* eps_src) {
+  if (eps_src) return;
+  const ArchDesc& a = *c.a;
+  const int h = e.half, Z = a.Z, n = c.rows_of(h) * Z;
+  float* eps = c.scratch + a.s_eps + 128 * h * Z;
+  const int g_base = (128 * h * Z) / 4;
+  for (int g = c.tid; g * 4 < n; g += c.nthr) {
+    float nrm[4];
+    philox_normal4(c.mb->seed, (unsigned long long)c.step, 0u, (uint32_t)(g_base + g), nrm);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) if (g * 4 + j < n) eps[g * 4 + j] = nrm[j];
+  }
+  bar_n(c.bar_id, c.bar_nthr);
+}
+
+__device__ void epi_head_latent(EpiCtx& c, const Epi& e, const float* eps_src) {
+  if ((c.warp % kGroupWarps) >= 4) return;
+  const ArchDesc& a = *c.a;
+  const Layout& lay = c.pg->lay;
+  const int h = e.half, Z = a.Z, C = a.C, rows = c.rows_of(h);
+  const bool vr = c.row < rows;
+  const int gb = 128 * h + c.row;
+  float mu[16], lv[16], zz[16];
+  tc::tmem_ld16(taddr(c, e.tmem_col), mu);            // columns 0 .. 15: mu[0 .. Z)
+  tc::tmem_ld16(taddr(c, e.tmem_col + Z), lv);        // columns Z .. Z + 15: logvar[0 .. Z)
+  float* S = c.scratch;
+  const uint32_t e0 = (uint32_t)gb * (uint32_t)Z;     // first element of this row in the [rows x Z] eps stream
+  const float* __restrict__ epsrow = (eps_src ? eps_src : S + a.s_eps) + e0;
+  float kl = 0.f;
+#pragma unroll
+  for (int z = 0; z < 16; ++z) {
+    zz[z] = 0.f;
+    if (z < Z && vr) {
+      const float eps = epsrow[z];
+      const float m_ = mu[z], l_ = lv[z];
+      S[a.s_mub + e0 + z] = m_; S[a.s_lvb + e0 + z] = l_;
+      if (eps_src) S[a.s_eps + e0 + z] = eps;
+      zz[z] = m_ + eps * expf(0.5f * l_);
+      kl += -0.5f * (1.f + l_ - m_ * m_ - expf(l_));
+    }
+  }
+  c.kl_acc += kl;
+  // [z | c | 1]: the covariate part comes from the dataset's template block (coalesced 16-byte reads)
+  const unsigned char* tp = c.mt->cplanes[0] + (long long)(c.pos * c.mt->n_half + h) * lay.c_cg * 4096 + c.row * 16;
+  unsigned char* act = c.smem + h * kActBytes + c.row * 16;
+  unsigned char* st = c.stash + lay.g0[0][h] + c.row * 16;
+  const int zg = (Z + 7) >> 3;                          // groups that contain z columns (<= 2)
+  for (int g = 0; g < lay.c_cg; ++g) {
+    uint4 hi = *reinterpret_cast<const uint4*>(tp + (long long)g * 4096);
+    uint4 lo = *reinterpret_cast<const uint4*>(tp + (long long)g * 4096 + 2048);
+    if (g < zg) {
+      const uint32_t hw[4] = {hi.x, hi.y, hi.z, hi.w}, lw[4] = {lo.x, lo.y, lo.z, lo.w};
+      float x[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float t = (j & 1) ? bf16pair_hi(hw[j >> 1]) + bf16pair_hi(lw[j >> 1]) : bf16pair_lo(hw[j >> 1]) + bf16pair_lo(lw[j >> 1]);
+        const int cc = 8 * g + j;
+        x[j] = cc < Z ? (g == 0 ? zz[j] : zz[8 + j]) : t;
+      }
+      tc::split8(x, hi, lo);
+    }
+    *reinterpret_cast<uint4*>(act + (long long)g * 4096) = hi;
+    *reinterpret_cast<uint4*>(act + (long long)g * 4096 + 2048) = lo;
+    *reinterpret_cast<uint4*>(st + (long long)g * 4096) = hi;
+    *reinterpret_cast<uint4*>(st + (long long)g * 4096 + 2048) = lo;
+  }
+  (void)C;
+}
+
+// ---- one modality, Z <= 16: d/dz accumulator -> latent backward -> d[mu | logvar] planes in ACT[h] ------------
+__device__ void epi_dz_latent_bwd(EpiCtx& c, const Epi& e) {
+  if ((c.warp % kGroupWarps) >= 4) return;
+  const ArchDesc& a = *c.a;
+  const int h = e.half, Z = a.Z, rows = c.rows_of(h);
+  const bool vr = c.row < rows;
+  const int gb = 128 * h + c.row;
+  const float* S = c.scratch;
+  const float inv_rows = 1.f / c.rows;
+  float dz[16], out[32];
+  tc::tmem_ld16(taddr(c, e.tmem_col), dz);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) out[j] = 0.f;
+#pragma unroll
+  for (int z = 0; z < 16; ++z) {
+    if (z < Z && vr) {
+      const int gi = gb * Z + z;
+      const float mub = S[a.s_mub + gi], lvb = S[a.s_lvb + gi], eps = S[a.s_eps + gi];
+      const float sd = expf(0.5f * lvb);
+      out[z] = dz[z] + mub * inv_rows;                                                   // d/dmu  (M = 1)
+      out[Z + z] = dz[z] * eps * sd * 0.5f + (expf(lvb) - 1.f) * 0.5f * inv_rows;       // d/dlogvar
+    }
+  }
+  unsigned char* act = c.smem + h * kActBytes;
+  const int cg = round16(2 * Z) / 8;
+  for (int g = 0; g < cg; ++g) {
+    float x[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = out[8 * g + j];
+    put_planes(act, g, c.row, x);
+  }
+}
+
 __device__ void epi_step_end(EpiCtx& c, float* loss_out) {
   const ArchDesc& a = *c.a;
   const int M = a.M;
@@ -875,7 +990,7 @@ __device__ void epilogue_role(const TrainLaunch& t, int mi, EpiCtx& c, uint32_t&
   for (long long i = 0; i < t.n_steps; ++i) {
     const long long s = s0 + i;
     const StepVars sv = step_vars(mb, s, i, n_epis);
-    c.rows = sv.rows; c.rows_h0 = sv.rows_h[0]; c.rows_h1 = sv.rows_h[1]; c.row0 = sv.row0;
+    c.rows = sv.rows; c.rows_h0 = sv.rows_h[0]; c.rows_h1 = sv.rows_h[1]; c.row0 = sv.row0; c.pos = sv.pos;
     c.step = s;
     {
       const double tt = (double)(s + 1);
@@ -887,6 +1002,7 @@ __device__ void epilogue_role(const TrainLaunch& t, int mi, EpiCtx& c, uint32_t&
     float* lo = t.loss_out ? t.loss_out + ((long long)mi * t.n_steps + i) * 3 : nullptr;
     for (int k = 0; k < n_epis; ++k) {
       const Epi e = epis[k];
+      if (c.lane == 0 && k + 2 < n_epis) asm volatile("prefetch.global.L1 [%0];" ::"l"(epis + k + 2));
       const bool joint = e.half == 2;
       if (!joint && (e.half != c.grp || (e.half == 1 && c.rows_h1 == 0))) continue;
       const bool split = e.kind == EK_WGRAD || e.kind == EK_WGRAD_T;
@@ -895,6 +1011,7 @@ __device__ void epilogue_role(const TrainLaunch& t, int mi, EpiCtx& c, uint32_t&
       const int tbase = c.grp == 0 ? 0 : 3 * n_epis + 5 * pg.n_steps;   // group 1 stamps after the MMA / producer records
       if (tr) g_trace[tbase + 3 * k] = gtime();
       if (joint && !split) bar_n(3, kEpiWarps * 32);   // both groups have finished everything before this item
+      if (e.kind == EK_HEAD_LATENT) epi_head_latent_pre(c, e, eps);
       if (e.buf >= 0) {
         tc::mbar_wait(&c.ctl->accbar[e.buf], (acc_par >> e.buf) & 1u);
         acc_par ^= 1u << e.buf;
@@ -917,6 +1034,8 @@ __device__ void epilogue_role(const TrainLaunch& t, int mi, EpiCtx& c, uint32_t&
         case EK_WGRAD: epi_wgrad(c, e); break;
         case EK_WGRAD_T: epi_wgrad_t(c, e); break;
         case EK_FENCE: fence = 2; break;
+        case EK_HEAD_LATENT: epi_head_latent(c, e, eps); fence = 1; break;
+        case EK_DZ_LATENT_BWD: epi_dz_latent_bwd(c, e); fence = 1; break;
         default: epi_step_end(c, lo); fence = 2; break;
       }
       if (e.buf >= 0) tc::fence_before();
@@ -1021,6 +1140,35 @@ __global__ void __launch_bounds__(256) xprep_kernel(const XPrepItem* items, int 
           for (int j = 0; j < 8; ++j) if (j < nv) v[j] = src[j];
         }
         put_planes(blk, g, r, v);
+      }
+      // decoder-input template [0 (Z) | c | 1 | 0]
+      unsigned char* cb = x.cplanes + (long long)b * x.c_cg * 4096;
+      for (int u = threadIdx.x; u < 128 * x.c_cg; u += 256) {
+        const int r = u & 127, g = u >> 7;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int cc = 8 * g + j;
+          float val = 0.f;
+          if (r < rows) {
+            if (cc >= x.z && cc < x.z + x.c_dim) val = x.xc[(long long)(r0 + r) * x.ldx + x.d + (cc - x.z)];
+            else if (cc == x.z + x.c_dim) val = 1.f;
+          }
+          v[j] = val;
+        }
+        put_planes(cb, g, r, v);
+      }
+      // ROI targets, lane-major fp32
+      float* xb = x.xlm + (long long)b * x.quads * 512;
+      for (int u = threadIdx.x; u < 128 * x.quads; u += 256) {
+        const int r = u & 127, qd = u >> 7;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < rows) {
+          const float* src = x.xc + (long long)(r0 + r) * x.ldx + 4 * qd;
+          const int nv = x.d - 4 * qd;
+          v.x = src[0]; if (nv > 1) v.y = src[1]; if (nv > 2) v.z = src[2]; if (nv > 3) v.w = src[3];
+        }
+        *reinterpret_cast<float4*>(xb + ((long long)qd * 128 + r) * 4) = v;
       }
     }
   }
