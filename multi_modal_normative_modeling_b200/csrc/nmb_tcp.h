@@ -26,11 +26,10 @@
 namespace nmb {
 namespace tcp {
 
-constexpr int kEpiWarps = 16;                     // 4 warps per TMEM lane quadrant
-constexpr int kEpiParts = kEpiWarps / 4;          // column partitions of an accumulator (joint items)
-constexpr int kGroupWarps = kEpiWarps / 2;        // the epilogue runs as two groups, one per minibatch half
+constexpr int kGroups = 3;                        // epilogue groups: minibatch half 0, half 1, optimiser (Adam)
+constexpr int kGroupWarps = 4;                    // one warp per TMEM lane quadrant
 constexpr int kGroupThreads = kGroupWarps * 32;
-constexpr int kGroupParts = kGroupWarps / 4;
+constexpr int kEpiWarps = kGroups * kGroupWarps;  // 12 + MMA + producer = 14 warps -> 128 registers per thread
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kThreadsP = kEpiThreads + 64;        // + MMA warp + producer warp
 constexpr int kActBytes = 65536;                   // one 128-row operand block, up to 128 columns (hi + lo)
@@ -67,7 +66,7 @@ struct alignas(16) Step {
   unsigned b_bytes, a_bytes;        // a_bytes == 0: A is resident in ACT[half]
   int dep;                          // joint epilogue item (index + 1, this step) that published the tile data; 0 = none
   int mma_dep;                      // item of this half's epilogue group that must finish before these MMAs issue
-  int mma_dep_joint;                // joint item (run by both groups) that must finish before these MMAs issue
+  int mma_dep_joint;                // item of the optimiser group (Adam epilogue) that must finish before these MMAs issue
   unsigned a_start;                 // byte offset inside ACT[half]
   unsigned a_lbo, a_sbo, a_kadv, a_lo;
   unsigned b_lbo, b_sbo, b_kadv, b_lo;
@@ -285,7 +284,8 @@ inline Program build_program(const ArchDesc& a) {
   // MMA-issue dependencies: items of the step's own half go to that group's counter, joint items to both
   auto need = [&](Step& s, int id) {
     if (id <= 0) return;
-    if (P.epis[id - 1].half == 2) { if (id > s.mma_dep_joint) s.mma_dep_joint = id; }
+    const int kind = P.epis[id - 1].kind;
+    if (kind == EK_WGRAD || kind == EK_WGRAD_T) { if (id > s.mma_dep_joint) s.mma_dep_joint = id; }
     else if (id > s.mma_dep) s.mma_dep = id;
   };
   auto base_step = [&](int h) {
@@ -468,8 +468,10 @@ inline Program build_program(const ArchDesc& a) {
   // Adam epilogue waits for that commit); acc[h] is committed after the wgrad part, so the epilogue that
   // overwrites ACT[h] cannot start before the wgrad MMAs have read it.
   //   dg_kind: 0 = no data gradient (first encoder layer), 1 = EK_DGRAD, 2 = EK_DZ (decoder input: d/dz only)
+  //   guard_act: no dgrad, but an epilogue-only item of the same half overwrites ACT[h] next (EK_COPY of the next
+  //   modality): the wgrad part commits acc[h] and that item waits for it.
   auto layer_backward = [&](int m, const LinDesc& w, const WRef& wr, int b_space, const long long in_base[2],
-                            int dg_kind, int n_need, int x_mod) {
+                            int dg_kind, int n_need, int x_mod, bool guard_act) {
     const int in_cg = round16(w.in + 1) / 8;
     const int n_items = (in_cg + 15) / 16;
     for (int it0 = 0; it0 < n_items; it0 += 2) {
@@ -481,7 +483,7 @@ inline Program build_program(const ArchDesc& a) {
         int wb = wb0;
         for (int it = it0; it < it1; ++it, wb ^= 1) {
           const int gf = it * 16, gc = in_cg - gf < 16 ? in_cg - gf : 16;
-          emit_wgrad_part(h, wb, b_space, in_base[h], gf, gc, x_mod, dg_kind && last_pair && it == it1 - 1);
+          emit_wgrad_part(h, wb, b_space, in_base[h], gf, gc, x_mod, (dg_kind || guard_act) && last_pair && it == it1 - 1);
         }
         if (dg_kind && last_pair) {
           Epi e = new_epi(dg_kind == 1 ? EK_DGRAD : (fused_latent ? EK_DZ_LATENT_BWD : EK_DZ), h, accbuf(h), m);
@@ -510,7 +512,7 @@ inline Program build_program(const ArchDesc& a) {
     const long long k_last[2] = {s_k[m][(L - 1) * 2 + 0], s_k[m][(L - 1) * 2 + 1]};
     if (lay.n_dxh_blk[m] == 0) {
       // decoder_mean_layer as a regular layer: ACT[h] holds d/dx_recon (written by EK_RECON)
-      layer_backward(m, q.outl, w_out[m][0], SP_STASH, k_last, 1, q.outl.in, 0);
+      layer_backward(m, q.outl, w_out[m][0], SP_STASH, k_last, 1, q.outl.in, 0, false);
     } else {
       if (M > 1) {   // ACT[h] <- last decoder hidden activation of this modality (transposed wgrad A operand)
         for (int h = 0; h < 2; ++h) {
@@ -576,7 +578,7 @@ inline Program build_program(const ArchDesc& a) {
     for (int l = L - 1; l >= 0; --l) {
       const long long in_base[2] = {l == 0 ? s_g0[m * 2 + 0] : s_k[m][(l - 1) * 2 + 0],
                                     l == 0 ? s_g0[m * 2 + 1] : s_k[m][(l - 1) * 2 + 1]};
-      layer_backward(m, q.dec[l], w_dec[m][l], SP_STASH, in_base, l > 0 ? 1 : 2, l > 0 ? q.dec[l].in : Z, 0);
+      layer_backward(m, q.dec[l], w_dec[m][l], SP_STASH, in_base, l > 0 ? 1 : 2, l > 0 ? q.dec[l].in : Z, 0, false);
     }
   }
   for (int h = 0; h < 2 && !fused_latent; ++h) {
@@ -588,9 +590,10 @@ inline Program build_program(const ArchDesc& a) {
     const ModDesc& q = a.mod[m];
     if (m > 0) {
       for (int h = 0; h < 2; ++h) {
-        Epi e = new_epi(EK_COPY, h, -1, m);
+        Epi e = new_epi(EK_COPY, h, accbuf(h), m);      // waits for the previous modality's last wgrad MMAs (guard_act)
         e.src_off = s_dmulv[m * 2 + h]; e.src_cg = round16(2 * Z) / 8;
-        act_ready[h] = push_epi(e);
+        const int id = push_epi(e);
+        act_ready[h] = id; acc_free[accbuf(h)] = id;
       }
     }
     // head, then encoder hidden layers
@@ -600,23 +603,15 @@ inline Program build_program(const ArchDesc& a) {
       const WRef& wr = is_head ? w_head[m] : w_enc[m][l];
       if (!is_head && l == 0) {
         const long long xb[2] = {0, 0};
-        layer_backward(m, w, wr, SP_X, xb, 0, 0, m);
+        layer_backward(m, w, wr, SP_X, xb, 0, 0, m, m + 1 < M);
       } else {
         const int li = (is_head ? L : l) - 1;
         const long long in_base[2] = {s_h[m][li * 2 + 0], s_h[m][li * 2 + 1]};
-        layer_backward(m, w, wr, SP_STASH, in_base, 1, w.in, 0);
+        layer_backward(m, w, wr, SP_STASH, in_base, 1, w.in, 0, false);
       }
     }
   }
-  // logvar_out: needs the partial sums of BOTH halves -> joint item, placed at the end of the step so that the
-  // rendezvous of the two epilogue groups costs nothing (the value is next used by EK_RECON of the next step)
-  if (a.loss_kind == NMB_LOSS_GAUSS_LL) {
-    for (int m = 0; m < M; ++m) {
-      Epi e = new_epi(EK_LAM, 2, -1, m);
-      e.p_off = a.mod[m].lam_off; e.p_cols = a.mod[m].D;
-      push_epi(e);
-    }
-  }
+  // logvar_out (needs the partial sums of both halves) is updated inside EK_STEP_END, after the rendezvous
   push_epi(new_epi(EK_STEP_END, 2, -1, 0));
   for (Step& s : P.steps) {
     s.dep_grp = 2;

@@ -31,7 +31,7 @@ __device__ __forceinline__ unsigned long long gtime() {
 struct Ctrl {
   uint64_t full[kSlots], empty[kSlots], accbar[4];
   uint32_t tmem;
-  volatile uint32_t epi_done[2];   // per epilogue group: items finished (1 + step * n_epis + index + 1)
+  volatile uint32_t epi_done[kGroups];   // per epilogue group: items finished (1 + step * n_epis + index + 1)
   int member;
   float red[40];
 };
@@ -57,9 +57,9 @@ __device__ __forceinline__ void wait_epi(const volatile uint32_t* p, uint32_t ne
   }
   __threadfence_block();
 }
-__device__ __forceinline__ void wait_both(const volatile uint32_t* p, uint32_t need) {
-  wait_epi(p, need);
-  wait_epi(p + 1, need);
+__device__ __forceinline__ void wait_all(const volatile uint32_t* p, uint32_t need) {
+#pragma unroll
+  for (int g = 0; g < kGroups; ++g) wait_epi(p + g, need);
 }
 __device__ __forceinline__ void bar_n(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void fence_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
@@ -106,9 +106,9 @@ __device__ void producer_role(const TrainLaunch& t, const ProgramDev& pg, const 
       if (sv.rows_h[st.half] == 0) continue;
       if (st.dep) {              // data written by an epilogue item of this step (stash blocks behind their fence)
         if (st.dep_grp < 2) wait_epi(&ctl->epi_done[st.dep_grp], sv.base + (uint32_t)st.dep);
-        else wait_both(ctl->epi_done, sv.base + (uint32_t)st.dep);
+        else wait_all(ctl->epi_done, sv.base + (uint32_t)st.dep);
       }
-      if (st.b_space == SP_W) wait_both(ctl->epi_done, sv.base);   // weight planes: every Adam item of the previous step
+      if (st.b_space == SP_W) wait_all(ctl->epi_done, sv.base);   // weight planes: every Adam item of the previous step
       TRACE(tr, tb + 2 * k);
       for (int which = 0; which < 2; ++which) {
         const int space = which == 0 ? st.a_space : st.b_space;
@@ -161,14 +161,14 @@ __device__ void mma_role(const LaunchP& L, int ai, const MemberDev& mb, unsigned
   for (long long i = 0; i < t.n_steps; ++i) {
     const StepVars sv = step_vars(mb, s0 + i, i, n_epis);
     const bool half1 = __any_sync(0xffffffffu, sv.rows_h[1] > 0);
-    wait_both(ctl->epi_done, sv.base);
+    wait_all(ctl->epi_done, sv.base);
     const bool tr = g_trace && blockIdx.x == 0 && i == g_trace_step;
     const int tb = 3 * n_epis;
     for (int k = k0; k < k1; ++k) {
       const MStep& st = L.msteps[k];
       if (st.half && !half1) continue;
       if (st.mma_dep) wait_epi(&ctl->epi_done[st.half], sv.base + (uint32_t)st.mma_dep);
-      if (st.mma_dep_joint) wait_both(ctl->epi_done, sv.base + (uint32_t)st.mma_dep_joint);
+      if (st.mma_dep_joint) wait_epi(&ctl->epi_done[2], sv.base + (uint32_t)st.mma_dep_joint);
       if (tr && (threadIdx.x & 31) == 0) g_trace[tb + 3 * (k - k0)] = gtime();
       uint32_t a_base, slot_a = kSlots;
       if (st.a_tile) {
@@ -266,9 +266,9 @@ __device__ __forceinline__ uint32_t taddr(const EpiCtx& c, int col) {
 // sum over ALL epilogue threads (joint items only: both groups call it)
 __device__ __forceinline__ float block_sum_epi(EpiCtx& c, float v) {
   v = warp_sum(v);
-  bar_n(3, kEpiWarps * 32);
+  bar_n(4, kEpiWarps * 32);
   if (c.lane == 0) c.ctl->red[c.warp] = v;
-  bar_n(3, kEpiWarps * 32);
+  bar_n(4, kEpiWarps * 32);
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < kEpiWarps; ++i) s += c.ctl->red[i];
@@ -492,25 +492,29 @@ __device__ __forceinline__ void epi_recon(EpiCtx& c, const Epi& e) {
   float* lampart = reinterpret_cast<float*>(c.stash + lay.lampart[e.mod]) + (long long)(h * 4 + (c.warp & 3)) * round4(q.D);
   const int n_valid = e.n_valid, col0 = e.col0, tcol = e.tmem_col, n_cols = e.n_cols, D = q.D;
   float ll = 0.f;
+  // targets of chunk k + 1 are in flight while chunk k is processed
+  float4 xa = make_float4(0.f, 0.f, 0.f, 0.f), xb = xa;
+#define NMB_LOAD_X(CH)                                                                                   \
+  do {                                                                                                   \
+    const int gc_ = col0 + (CH) * 8;                                                                     \
+    xa = xb = make_float4(0.f, 0.f, 0.f, 0.f);                                                           \
+    if (vr && (CH) * 8 < n_valid) {                                                                      \
+      xa = *reinterpret_cast<const float4*>(xq + (long long)(gc_ >> 2) * 512);                           \
+      if (gc_ + 4 < D) xb = *reinterpret_cast<const float4*>(xq + (long long)((gc_ >> 2) + 1) * 512);    \
+    }                                                                                                    \
+  } while (0)
+  if (c.cpart * 8 < n_cols) NMB_LOAD_X(c.cpart);
   for (int ch = c.cpart; ch * 8 < n_cols; ch += c.parts) {
     const int col = ch * 8, gc = col0 + col;
     const int nv = min(max(n_valid - col, 0), 8);
-    float v[8], xt[8], l[8];
+    float v[8], l[8];
+    const float xt[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+    if ((ch + c.parts) * 8 < n_cols) NMB_LOAD_X(ch + c.parts);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { xt[j] = 0.f; l[j] = 0.f; }
-    if (nv > 0) {
-      if (vr) {
-        const float4 t0 = *reinterpret_cast<const float4*>(xq + (long long)(gc >> 2) * 512);
-        xt[0] = t0.x; xt[1] = t0.y; xt[2] = t0.z; xt[3] = t0.w;
-        if (gc + 4 < D) {
-          const float4 t1 = *reinterpret_cast<const float4*>(xq + (long long)((gc >> 2) + 1) * 512);
-          xt[4] = t1.x; xt[5] = t1.y; xt[6] = t1.z; xt[7] = t1.w;
-        }
-      }
-      if (gauss) {
+    for (int j = 0; j < 8; ++j) l[j] = 0.f;
+    if (nv > 0 && gauss) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) if (j < nv) l[j] = lam[gc + j];
-      }
+      for (int j = 0; j < 8; ++j) if (j < nv) l[j] = __ldg(lam + gc + j);
     }
     __syncwarp();
     tc::tmem_ld8(taddr(c, tcol + col), v);
@@ -704,22 +708,32 @@ __device__ __forceinline__ void epi_wgrad(EpiCtx& c, const Epi& e) {
   const long long mbase = e.mst_off + (long long)o * 4;
   float* __restrict__ Pp = c.mst_p; float* __restrict__ Pm = c.mst_m; float* __restrict__ Pv = c.mst_v;
   const bool adam = !(c.flags & NMB_TRAIN_NO_ADAM), wg = c.flags & NMB_TRAIN_WRITE_GRADS;
+  // Software pipeline: the state (p, m, v) of chunk k + 1 is in flight while chunk k is updated and stored.
+  float4 n0, n1, n2, n3, n4, n5;
+  n0 = n1 = n2 = n3 = n4 = n5 = make_float4(0.f, 0.f, 0.f, 0.f);
+#define NMB_LOAD_STATE(CH)                                                                                       \
+  do {                                                                                                           \
+    const int col_ = col0 + (CH) * 8;                                                                            \
+    n0 = n1 = n2 = n3 = n4 = n5 = make_float4(0.f, 0.f, 0.f, 0.f);                                                \
+    if (vo && col_ < p_cols && adam) {                                                                           \
+      const long long mi_ = mbase + (long long)(col_ >> 2) * R4;                                                 \
+      n0 = *reinterpret_cast<const float4*>(Pp + mi_); n2 = *reinterpret_cast<const float4*>(Pm + mi_);          \
+      n4 = *reinterpret_cast<const float4*>(Pv + mi_);                                                           \
+      if (col_ + 4 < p_cols) {                                                                                   \
+        n1 = *reinterpret_cast<const float4*>(Pp + mi_ + R4); n3 = *reinterpret_cast<const float4*>(Pm + mi_ + R4); \
+        n5 = *reinterpret_cast<const float4*>(Pv + mi_ + R4);                                                    \
+      }                                                                                                          \
+    }                                                                                                            \
+  } while (0)
+  if (c.cpart * 8 < n_mma) NMB_LOAD_STATE(c.cpart);
   for (int ch = c.cpart; ch * 8 < n_mma; ch += c.parts) {        // 8 columns (one plane group) at a time
     const int col = col0 + ch * 8;
     const bool on = vo && col < p_cols;
     const bool full = col + 4 < p_cols;
     const long long mi = mbase + (long long)(col >> 2) * R4;
     float g[8];
-    float4 pa, pb, ma, mb4, va, vb;
-    pa = pb = ma = mb4 = va = vb = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (on && adam) {            // state loads first: they overlap the TMEM read
-      pa = *reinterpret_cast<const float4*>(Pp + mi); ma = *reinterpret_cast<const float4*>(Pm + mi);
-      va = *reinterpret_cast<const float4*>(Pv + mi);
-      if (full) {
-        pb = *reinterpret_cast<const float4*>(Pp + mi + R4); mb4 = *reinterpret_cast<const float4*>(Pm + mi + R4);
-        vb = *reinterpret_cast<const float4*>(Pv + mi + R4);
-      }
-    }
+    float4 pa = n0, pb = n1, ma = n2, mb4 = n3, va = n4, vb = n5;
+    if ((ch + c.parts) * 8 < n_mma) NMB_LOAD_STATE(ch + c.parts);
     __syncwarp();
     tc::tmem_ld8(taddr(c, tcol + ch * 8), g);
     if (on) {
@@ -838,7 +852,7 @@ __device__ void epi_head_latent_pre(EpiCtx& c, const Epi& e, const float* eps_sr
 }
 
 __device__ void epi_head_latent(EpiCtx& c, const Epi& e, const float* eps_src) {
-  if ((c.warp % kGroupWarps) >= 4) return;
+  
   const ArchDesc& a = *c.a;
   const Layout& lay = c.pg->lay;
   const int h = e.half, Z = a.Z, C = a.C, rows = c.rows_of(h);
@@ -893,7 +907,7 @@ __device__ void epi_head_latent(EpiCtx& c, const Epi& e, const float* eps_src) {
 
 // ---- one modality, Z <= 16: d/dz accumulator -> latent backward -> d[mu | logvar] planes in ACT[h] ------------
 __device__ void epi_dz_latent_bwd(EpiCtx& c, const Epi& e) {
-  if ((c.warp % kGroupWarps) >= 4) return;
+  
   const ArchDesc& a = *c.a;
   const int h = e.half, Z = a.Z, rows = c.rows_of(h);
   const bool vr = c.row < rows;
@@ -924,9 +938,30 @@ __device__ void epi_dz_latent_bwd(EpiCtx& c, const Epi& e) {
   }
 }
 
+// While the optimiser group waits for a weight-gradient accumulator it pulls that item's Adam state towards L2
+// (the per-slot master buffers of 148 resident members exceed the L2, so the first touch is an HBM miss).
+__device__ __forceinline__ void prefetch_adam_state(const EpiCtx& c, const Epi& e) {
+  if (c.flags & NMB_TRAIN_NO_ADAM) return;
+  const bool t_ = e.kind == EK_WGRAD_T;
+  const int lanes = t_ ? e.p_cols : e.p_rows, other = t_ ? e.p_rows : e.p_cols;
+  if (c.row >= lanes) return;
+  const int q0 = e.col0 >> 2, q1 = min((e.col0 + e.n_mma + 3) >> 2, (other + 3) >> 2);
+  const long long base = e.mst_off + (long long)c.row * 4;
+  for (int qd = q0; qd < q1; ++qd) {
+    const long long mi = base + (long long)qd * e.mst_R * 4;
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(c.mst_p + mi));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(c.mst_m + mi));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(c.mst_v + mi));
+  }
+}
+
 __device__ void epi_step_end(EpiCtx& c, float* loss_out) {
   const ArchDesc& a = *c.a;
   const int M = a.M;
+  if (a.loss_kind == NMB_LOSS_GAUSS_LL) {        // logvar_out: partial sums of both halves are complete here
+    Epi lam{};
+    for (int m = 0; m < M; ++m) { lam.mod = m; epi_lam(c, lam); }
+  }
   const float kl = block_sum_epi(c, c.kl_acc) / c.rows;
   const float ll = block_sum_epi(c, c.ll_acc);
   if (loss_out && c.tid == 0) { loss_out[0] = M * kl - ll; loss_out[1] = M * kl; loss_out[2] = ll; }
@@ -945,29 +980,21 @@ __device__ void epi_step_end(EpiCtx& c, float* loss_out) {
   for (int m = 0; m < M; ++m) c.dw_acc[m] = 0.f;
 }
 
-// Worker set of an item: the group of its half (per-half items) or both groups (joint items).
-// `split` joint items (the Adam epilogues) need no data from the other group: each group processes its own
-// column partitions whenever it gets there, without a rendezvous.
-__device__ __forceinline__ void set_workers(EpiCtx& c, bool joint, bool split = false) {
+// Worker set of an item: the item's group (128 threads, one warp per TMEM lane quadrant) or all epilogue warps.
+__device__ __forceinline__ void set_workers(EpiCtx& c, bool all) {
   const int lw = c.warp % kGroupWarps;
-  if (joint && split) {
-    c.tid = lw * 32 + c.lane; c.nthr = kGroupThreads;
-    c.cpart = (lw >> 2) + c.grp * kGroupParts; c.parts = kEpiParts;
-    c.bar_id = 1 + c.grp; c.bar_nthr = kGroupThreads;
-  } else if (joint) {
-    c.tid = c.warp * 32 + c.lane; c.nthr = kEpiWarps * 32;
-    c.cpart = (lw >> 2) + c.grp * kGroupParts; c.parts = kEpiParts;
-    c.bar_id = 3; c.bar_nthr = kEpiWarps * 32;
+  c.cpart = 0; c.parts = 1;
+  if (all) {
+    c.tid = c.warp * 32 + c.lane; c.nthr = kEpiWarps * 32; c.bar_id = 4; c.bar_nthr = kEpiWarps * 32;
   } else {
-    c.tid = lw * 32 + c.lane; c.nthr = kGroupThreads;
-    c.cpart = lw >> 2; c.parts = kGroupParts;
-    c.bar_id = 1 + c.grp; c.bar_nthr = kGroupThreads;
+    c.tid = lw * 32 + c.lane; c.nthr = kGroupThreads; c.bar_id = 1 + c.grp; c.bar_nthr = kGroupThreads;
   }
 }
 
-// The epilogue runs as TWO groups of warps, one per 128-row half of the minibatch: each walks the item list,
-// executes the items of its own half and -- together with the other group -- the joint items (Adam, fences,
-// loss).  The two dependency chains (half 0, half 1) therefore overlap each other's latencies.
+// The epilogue runs as THREE groups of 4 warps: one per 128-row half of the minibatch (activations, losses,
+// data gradients: two independent dependency chains whose latencies overlap) and the optimiser group, which
+// consumes the weight-gradient accumulators (Adam + new weight planes) off both chains.  Every group walks the
+// item list and executes its own items; EK_STEP_END is the only rendezvous.
 __device__ void epilogue_role(const TrainLaunch& t, int mi, EpiCtx& c, uint32_t& acc_par) {
   const ProgramDev& pg = *c.pg;
   MemberDev& mb = *c.mb;
@@ -981,8 +1008,11 @@ __device__ void epilogue_role(const TrainLaunch& t, int mi, EpiCtx& c, uint32_t&
   if (adam_on) move_master(c, true);
   __threadfence();
   fence_async_all();
-  bar_n(3, kEpiWarps * 32);
-  if (c.tid == 0) { st_release(&c.ctl->epi_done[0], 1u); st_release(&c.ctl->epi_done[1], 1u); }
+  bar_n(4, kEpiWarps * 32);
+  if (c.tid == 0) {
+#pragma unroll
+    for (int g = 0; g < kGroups; ++g) st_release(&c.ctl->epi_done[g], 1u);
+  }
   const long long s0 = mb.steps_done;
   const int n_epis = pg.n_epis;
   const Epi* __restrict__ epis = pg.epis;
@@ -1003,15 +1033,17 @@ __device__ void epilogue_role(const TrainLaunch& t, int mi, EpiCtx& c, uint32_t&
     for (int k = 0; k < n_epis; ++k) {
       const Epi e = epis[k];
       if (c.lane == 0 && k + 2 < n_epis) asm volatile("prefetch.global.L1 [%0];" ::"l"(epis + k + 2));
-      const bool joint = e.half == 2;
-      if (!joint && (e.half != c.grp || (e.half == 1 && c.rows_h1 == 0))) continue;
-      const bool split = e.kind == EK_WGRAD || e.kind == EK_WGRAD_T;
-      set_workers(c, joint, split);
-      const bool tr = g_trace && blockIdx.x == 0 && i == g_trace_step && c.lane == 0 && (c.warp % kGroupWarps) == 0;
-      const int tbase = c.grp == 0 ? 0 : 3 * n_epis + 5 * pg.n_steps;   // group 1 stamps after the MMA / producer records
+      const bool all = e.kind == EK_STEP_END;
+      const bool optim = e.kind == EK_WGRAD || e.kind == EK_WGRAD_T;
+      const int owner = all ? c.grp : (optim ? 2 : e.half);
+      if (owner != c.grp || (e.half == 1 && c.rows_h1 == 0)) continue;
+      set_workers(c, all);
+      const bool tr = g_trace && blockIdx.x == 0 && i == g_trace_step && pub && (!all || c.grp == 0);
+      const int tbase = c.grp == 0 ? 0 : 3 * n_epis * c.grp + 5 * pg.n_steps;   // groups 1, 2 stamp after the MMA / producer records
       if (tr) g_trace[tbase + 3 * k] = gtime();
-      if (joint && !split) bar_n(3, kEpiWarps * 32);   // both groups have finished everything before this item
+      if (all) bar_n(4, kEpiWarps * 32);           // every group has finished everything before this item
       if (e.kind == EK_HEAD_LATENT) epi_head_latent_pre(c, e, eps);
+      if (optim) prefetch_adam_state(c, e);
       if (e.buf >= 0) {
         tc::mbar_wait(&c.ctl->accbar[e.buf], (acc_par >> e.buf) & 1u);
         acc_par ^= 1u << e.buf;
@@ -1027,7 +1059,6 @@ __device__ void epilogue_role(const TrainLaunch& t, int mi, EpiCtx& c, uint32_t&
         case EK_LATENT: epi_latent(c, e, eps); fence = 1; break;
         case EK_COPY: epi_copy(c, e); fence = 1; break;
         case EK_RECON: epi_recon(c, e); fence = e.to_act ? 1 : 0; break;
-        case EK_LAM: epi_lam(c, e); break;
         case EK_DGRAD: epi_dgrad(c, e); fence = 1; break;
         case EK_DZ: epi_dz(c, e); break;
         case EK_LATENT_BWD: epi_latent_bwd(c, e); fence = 1; break;
@@ -1047,10 +1078,9 @@ __device__ void epilogue_role(const TrainLaunch& t, int mi, EpiCtx& c, uint32_t&
     }
   }
   set_workers(c, true);
-  bar_n(3, kEpiWarps * 32);
+  bar_n(4, kEpiWarps * 32);
   if (adam_on) move_master(c, false);
 }
-
 
 __global__ void __launch_bounds__(kThreadsP, 1) train_tcp_kernel(const __grid_constant__ LaunchP L) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -1076,7 +1106,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) train_tcp_kernel(const __grid_co
       if (dynamic) { mi = atomicAdd(t.work_counter, 1); if (mi < t.n_members) mi = t.order[mi]; else mi = t.n_members; }
       else if (first) mi = blockIdx.x;
       ctl->member = mi;
-      ctl->epi_done[0] = 0; ctl->epi_done[1] = 0;
+      for (int g = 0; g < kGroups; ++g) ctl->epi_done[g] = 0;
     }
     first = false;
     __syncthreads();

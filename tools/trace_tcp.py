@@ -25,11 +25,12 @@ print("epilogue items: arrive start end (us)  | wait work")
 for k in range(E):
     a, s, e = b[3 * k:3 * k + 3]
     if a: print("E%02d %8.2f %8.2f %8.2f | %6.2f %6.2f" % (k + 1, (a - t0) / 1e3, (s - t0) / 1e3, (e - t0) / 1e3, (s - a) / 1e3, (e - s) / 1e3))
-print("group 1 items")
-o1 = 3 * E + 5 * S
-for k in range(E):
-    a, s_, e = b[o1 + 3 * k:o1 + 3 * k + 3]
-    if a: print("G%02d %8.2f %8.2f %8.2f | %6.2f %6.2f" % (k + 1, (a - t0) / 1e3, (s_ - t0) / 1e3, (e - t0) / 1e3, (s_ - a) / 1e3, (e - s_) / 1e3))
+for grp, tag in ((1, "G"), (2, "A")):
+    print("group %d items" % grp)
+    o1 = 3 * E * grp + 5 * S
+    for k in range(E):
+        a, s_, e = b[o1 + 3 * k:o1 + 3 * k + 3]
+        if a: print("%s%02d %8.2f %8.2f %8.2f | %6.2f %6.2f" % (tag, k + 1, (a - t0) / 1e3, (s_ - t0) / 1e3, (e - t0) / 1e3, (s_ - a) / 1e3, (e - s_) / 1e3))
 print("mma steps: deps tiles issued")
 for k in range(S):
     a, s, e = b[3 * E + 3 * k:3 * E + 3 * k + 3]
