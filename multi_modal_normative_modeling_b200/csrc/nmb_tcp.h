@@ -122,6 +122,9 @@ struct alignas(16) Epi {
   long long mst_off; int mst_R;     // Adam master state of the layer (float offset in the slot's master buffer, lane extent)
   int row0;                         // EK_WGRAD: first weight row of this planes block (out-layer blocks)
   int last;                         // EK_RECON: last tile of the modality (lam partials complete)
+  int split_all;                    // Adam item after the last per-half item of the step: all three groups share it
+  int wait_optim;                   // split_all: last optimiser-only item (index + 1) an activation group must see finished
+                                    // before it trusts its view of the accumulator barrier phases
 };
 
 // Weight block of the per-member planes buffer (prologue conversion fp32 -> planes).
@@ -612,6 +615,19 @@ inline Program build_program(const ArchDesc& a) {
     }
   }
   // logvar_out (needs the partial sums of both halves) is updated inside EK_STEP_END, after the rendezvous
+  {   // the Adam items behind the last per-half item find both activation groups idle: they help (column split)
+    int last_half_item = -1;
+    for (int k = 0; k < (int)P.epis.size(); ++k) if (P.epis[k].half != 2) last_half_item = k;
+    int last_optim_only = 0;
+    for (int k = 0; k <= last_half_item; ++k)
+      if (P.epis[k].kind == EK_WGRAD || P.epis[k].kind == EK_WGRAD_T) last_optim_only = k + 1;
+    for (int k = last_half_item + 1; k < (int)P.epis.size(); ++k)
+      if (P.epis[k].kind == EK_WGRAD || P.epis[k].kind == EK_WGRAD_T) { P.epis[k].split_all = 1; P.epis[k].wait_optim = last_optim_only; }
+  }
+  // an accumulator consumed by a shared (split_all) Adam item is free only when ALL groups are done with it:
+  // encoded as a negative optimiser dependency
+  for (Step& st : P.steps)
+    if (st.mma_dep_joint > 0 && P.epis[st.mma_dep_joint - 1].split_all) st.mma_dep_joint = -st.mma_dep_joint;
   push_epi(new_epi(EK_STEP_END, 2, -1, 0));
   for (Step& s : P.steps) {
     s.dep_grp = 2;

@@ -168,7 +168,8 @@ __device__ void mma_role(const LaunchP& L, int ai, const MemberDev& mb, unsigned
       const MStep& st = L.msteps[k];
       if (st.half && !half1) continue;
       if (st.mma_dep) wait_epi(&ctl->epi_done[st.half], sv.base + (uint32_t)st.mma_dep);
-      if (st.mma_dep_joint) wait_epi(&ctl->epi_done[2], sv.base + (uint32_t)st.mma_dep_joint);
+      if (st.mma_dep_joint > 0) wait_epi(&ctl->epi_done[2], sv.base + (uint32_t)st.mma_dep_joint);
+      else if (st.mma_dep_joint < 0) wait_all(ctl->epi_done, sv.base + (uint32_t)(-st.mma_dep_joint));
       if (tr && (threadIdx.x & 31) == 0) g_trace[tb + 3 * (k - k0)] = gtime();
       uint32_t a_base, slot_a = kSlots;
       if (st.a_tile) {
@@ -1035,9 +1036,17 @@ __device__ void epilogue_role(const TrainLaunch& t, int mi, EpiCtx& c, uint32_t&
       if (c.lane == 0 && k + 2 < n_epis) asm volatile("prefetch.global.L1 [%0];" ::"l"(epis + k + 2));
       const bool all = e.kind == EK_STEP_END;
       const bool optim = e.kind == EK_WGRAD || e.kind == EK_WGRAD_T;
-      const int owner = all ? c.grp : (optim ? 2 : e.half);
-      if (owner != c.grp || (e.half == 1 && c.rows_h1 == 0)) continue;
+      const int owner = (all || e.split_all) ? c.grp : (optim ? 2 : e.half);
+      if (owner != c.grp || (e.half == 1 && c.rows_h1 == 0)) {
+        if (optim) acc_par ^= 1u << e.buf;       // keep this group's view of the accumulator barrier phases in step
+        continue;
+      }
       set_workers(c, all);
+      if (e.split_all) {
+        c.cpart = c.grp; c.parts = kGroups;
+        // an idle activation group may be far ahead of the optimiser: mbarrier parity only disambiguates one phase
+        if (c.grp != 2 && e.wait_optim) wait_epi(&c.ctl->epi_done[2], sv.base + (uint32_t)e.wait_optim);
+      }
       const bool tr = g_trace && blockIdx.x == 0 && i == g_trace_step && pub && (!all || c.grp == 0);
       const int tbase = c.grp == 0 ? 0 : 3 * n_epis * c.grp + 5 * pg.n_steps;   // groups 1, 2 stamp after the MMA / producer records
       if (tr) g_trace[tbase + 3 * k] = gtime();

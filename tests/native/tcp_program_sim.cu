@@ -16,47 +16,80 @@ int main(int argc, char** argv){
   for (int k = 0; k < NS; ++k) { const auto& s = P.steps[k]; first_tile[k] = tiles.size();
     if (s.a_bytes) tiles.push_back({k, s.dep, s.dep_grp, false});
     tiles.push_back({k, s.dep, s.dep_grp, s.b_space == tcp::SP_W}); n_tiles[k] = tiles.size() - first_tile[k]; }
-  int issued = 0, consumed = 0, mi = 0; int epi_done[3] = {0, 0, 0}; int commits[4] = {0,0,0,0}; int waited[3][4] = {{0}};
-  int ep[3] = {0, 0, 0};
   auto owner = [&](const tcp::Epi& e, int g) {
-    if (e.kind == tcp::EK_STEP_END) return g;
+    if (e.kind == tcp::EK_STEP_END || e.split_all) return g;
     if (e.kind == tcp::EK_WGRAD || e.kind == tcp::EK_WGRAD_T) return 2;
     return e.half;
   };
-  for (int iter = 0; iter < 100000; ++iter) {
-    bool prog = false;
-    // producer
-    while (issued < (int)tiles.size() && issued - consumed < 3) {
-      const Tile& t = tiles[issued]; bool ok = true;
-      if (t.dep) { if (t.grp < 2) ok = epi_done[t.grp] >= t.dep; else ok = epi_done[0] >= t.dep && epi_done[1] >= t.dep && epi_done[2] >= t.dep; }
-      if (!ok) break; ++issued; prog = true; }
-    // mma
-    while (mi < NS) { const auto& s = P.steps[mi];
-      if (s.mma_dep && epi_done[s.half] < s.mma_dep) break;
-      if (s.mma_dep_joint && epi_done[2] < s.mma_dep_joint) break;
-      if (issued < first_tile[mi] + n_tiles[mi]) break;
-      consumed += n_tiles[mi]; if (s.commit == 1) commits[s.commit_buf]++; if (s.commit2) commits[s.half]++; ++mi; prog = true; }
-    // epilogue groups
-    for (int g = 0; g < 3; ++g) {
-      while (ep[g] < NE) { const auto& e = P.epis[ep[g]];
-        if (owner(e, g) != g) { ++ep[g]; continue; }
-        if (e.kind == tcp::EK_STEP_END) {        // rendezvous: every group must be waiting at this item
-          bool all = true;
-          for (int o = 0; o < 3; ++o) {
-            int q = ep[o]; while (q < NE && owner(P.epis[q], o) != o) ++q;
-            if (q != ep[g]) all = false;
-          }
-          if (!all) break;
-          for (int o = 0; o < 3; ++o) { epi_done[o] = ep[g] + 1; ep[o] = ep[g] + 1; }   // released together
-          prog = true; continue;
+  // accumulator hazard check: the MMAs of use #u of an accumulator buffer may only be issued when every group that
+  // owns the epilogue item of use #u-1 has finished reading it
+  std::vector<int> uses[4];
+  for (int k = 0; k < NE; ++k) if (P.epis[k].buf >= 0) uses[P.epis[k].buf].push_back(k);
+  // Randomised interleaving: each trial advances one randomly chosen role by one unit at a time, so that any
+  // ordering the hardware could produce between the roles is sampled (300 seeds).
+  for (unsigned seed = 1; seed <= 300; ++seed) {
+    unsigned rng = seed * 2654435761u;
+    auto rnd = [&]() { rng ^= rng << 13; rng ^= rng >> 17; rng ^= rng << 5; return rng; };
+    int issued = 0, consumed = 0, mi = 0; int epi_done[3] = {0, 0, 0}; int commits[4] = {0,0,0,0}; int waited[3][4] = {{0}};
+    int ep[3] = {0, 0, 0}; int use_idx[4] = {0, 0, 0, 0};
+    auto step_producer = [&]() {
+      if (!(issued < (int)tiles.size() && issued - consumed < 3)) return false;
+      const Tile& t = tiles[issued];
+      if (t.dep) { const bool ok = t.grp < 2 ? epi_done[t.grp] >= t.dep : (epi_done[0] >= t.dep && epi_done[1] >= t.dep && epi_done[2] >= t.dep); if (!ok) return false; }
+      ++issued; return true; };
+    auto step_mma = [&]() -> int {
+      if (mi >= NS) return 0;
+      const auto& s = P.steps[mi];
+      if (s.mma_dep && epi_done[s.half] < s.mma_dep) return 0;
+      if (s.mma_dep_joint > 0 && epi_done[2] < s.mma_dep_joint) return 0;
+      if (s.mma_dep_joint < 0 && (epi_done[0] < -s.mma_dep_joint || epi_done[1] < -s.mma_dep_joint || epi_done[2] < -s.mma_dep_joint)) return 0;
+      if (issued < first_tile[mi] + n_tiles[mi]) return 0;
+      const int b = s.tmem_col / 128, u = use_idx[b];
+      if (u > 0) {
+        const int prev = uses[b][u - 1];
+        for (int g = 0; g < 3; ++g)
+          if (owner(P.epis[prev], g) == g && ep[g] <= prev) { printf("HAZARD (seed %u): step %d overwrites accumulator %d before group %d finished item %d\n", seed, mi, b, g, prev); return -1; }
+      }
+      consumed += n_tiles[mi];
+      if (s.commit == 1) { commits[s.commit_buf]++; use_idx[s.commit_buf]++; }
+      if (s.commit2) { commits[s.half]++; use_idx[s.half]++; }
+      ++mi; return 1; };
+    auto step_group = [&](int g) {
+      while (ep[g] < NE && owner(P.epis[ep[g]], g) != g) {
+        const auto& e = P.epis[ep[g]];
+        if (e.kind == tcp::EK_WGRAD || e.kind == tcp::EK_WGRAD_T) waited[g][e.buf]++;
+        ++ep[g];
+      }
+      if (ep[g] >= NE) return false;
+      const auto& e = P.epis[ep[g]];
+      if (e.kind == tcp::EK_STEP_END) {
+        for (int o = 0; o < 3; ++o) {
+          int q = ep[o]; while (q < NE && owner(P.epis[q], o) != o) ++q;
+          if (q != ep[g]) return false;
         }
-        if (e.buf >= 0) { if (commits[e.buf] <= waited[g][e.buf]) break; waited[g][e.buf]++; }
-        epi_done[g] = ep[g] + 1; ++ep[g]; prog = true; }
+        for (int o = 0; o < 3; ++o) { epi_done[o] = ep[g] + 1; ep[o] = ep[g] + 1; }
+        return true;
+      }
+      if (e.split_all && g != 2 && e.wait_optim && epi_done[2] < e.wait_optim) return false;
+      if (e.buf >= 0) {
+        if (commits[e.buf] <= waited[g][e.buf]) return false;
+        if (commits[e.buf] - waited[g][e.buf] > 1) { printf("PHASE ALIAS (seed %u): group %d item %d\n", seed, g, ep[g]); exit(4); }
+        waited[g][e.buf]++;
+      }
+      epi_done[g] = ep[g] + 1; ++ep[g]; return true; };
+    int idle = 0;
+    while (!(mi == NS && ep[0] >= NE && ep[1] >= NE && ep[2] >= NE)) {
+      const unsigned r = rnd() % 5;
+      int ok = 0;
+      if (r == 0) ok = step_producer(); else if (r == 1) { ok = step_mma(); if (ok < 0) return 3; } else ok = step_group((int)r - 2);
+      idle = ok ? 0 : idle + 1;
+      if (idle > 200) {
+        const bool any = step_producer() || step_mma() > 0 || step_group(0) || step_group(1) || step_group(2);
+        if (!any) { printf("STUCK (seed %u): issued %d consumed %d mma step %d ep %d %d %d epi_done %d %d %d\n", seed, issued, consumed, mi, ep[0], ep[1], ep[2], epi_done[0], epi_done[1], epi_done[2]); return 1; }
+        idle = 0;
+      }
     }
-    if (mi == NS && ep[0] == NE && ep[1] == NE && ep[2] == NE) { printf("OK all done (iters %d)\n", iter); return 0; }
-    if (!prog) { printf("STUCK: issued %d consumed %d mma step %d (dep %d optim-dep %d half %d) ep %d %d %d epi_done %d %d %d commits %d %d %d %d\n",
-       issued, consumed, mi, mi < NS ? P.steps[mi].mma_dep : -1, mi < NS ? P.steps[mi].mma_dep_joint : -1, mi < NS ? P.steps[mi].half : -1,
-       ep[0], ep[1], ep[2], epi_done[0], epi_done[1], epi_done[2], commits[0], commits[1], commits[2], commits[3]); return 1; }
   }
+  printf("OK all done (300 random interleavings)\n");
   return 0;
 }
