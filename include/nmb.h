@@ -151,7 +151,8 @@ int nmb_ensemble_peek(NmbEnsemble* ens, int32_t member, float* mu, float* logvar
                       float* const* x_recon /*host array of device ptrs*/, int32_t* rows /*host*/,
                       void* stream);
 
-enum { NMB_RECON_MEAN = 0, NMB_RECON_SAMPLE = 1 };
+enum { NMB_RECON_MEAN = 0, NMB_RECON_SAMPLE = 1,
+       NMB_RECON_FP32 = 16 /* OR into `mode`: FP32 FFMA engine instead of the default tcgen05 (BF16x3) engine */ };
 /* Test-time reconstruction for every member on its own rows:
  *   mode MEAN   : decode(mu)                       -- cVAE.pred_recon, cVAE.py:549-555
  *   mode SAMPLE : decode(mu + eps*exp(logvar/2))   -- cVAE_multimodal.pred_recon, cVAE.py:1198-1208

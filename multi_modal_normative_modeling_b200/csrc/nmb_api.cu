@@ -400,6 +400,8 @@ int nmb_ensemble_reconstruct(NmbEnsemble* e, const float* const* xc, const int32
                              const float* const* eps, float* const* xhat, float* const* mu, float* const* logvar,
                              void* stream) {
   if (!e || !xc || !n_rows || !xhat) return fail("null argument");
+  const int fp32 = (mode & NMB_RECON_FP32) ? 1 : 0;
+  mode &= ~NMB_RECON_FP32;
   if (mode != NMB_RECON_MEAN && mode != NMB_RECON_SAMPLE) return fail("bad mode");
   cudaStream_t st = (cudaStream_t)stream;
   CU(cudaSetDevice(e->device));
@@ -430,7 +432,7 @@ int nmb_ensemble_reconstruct(NmbEnsemble* e, const float* const* xc, const int32
   t.eps = eps ? b.at<const float*>(o_eps) : nullptr;
   t.mu = mu ? b.at<float*>(o_mu) : nullptr;
   t.logvar = logvar ? b.at<float*>(o_lv) : nullptr;
-  t.mode = mode; t.scratch = e->scratch; t.slot_floats = e->slot_floats; t.n_slots = e->n_slots;
+  t.mode = mode; t.scratch = e->scratch; t.slot_floats = e->slot_floats; t.n_slots = e->n_slots; t.fp32 = fp32;
   CU(launch_recon(t, st));
   CU(b.release(st));
   return 0;

@@ -59,6 +59,7 @@ struct ReconLaunch {
   const ReconItem* items; int n_items;
   const float* const* xc; const float* const* eps; float* const* xhat; float* const* mu; float* const* logvar;
   int mode; float* scratch; long long slot_floats; int n_slots;
+  int fp32;   // FP32 FFMA engine instead of tcgen05
 };
 cudaError_t launch_recon(const ReconLaunch& t, cudaStream_t st);
 cudaError_t configure_kernels();

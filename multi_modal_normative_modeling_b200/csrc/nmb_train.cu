@@ -599,20 +599,19 @@ __global__ void __launch_bounds__(kThreads, 2) debug_tc_gemm_kernel(Opnd A, Opnd
 }
 
 // Test-time reconstruction.  Work item = (member, tile of up to 256 rows).
-__global__ void __launch_bounds__(kThreads, 2) recon_kernel(ReconLaunch t) {
-  extern __shared__ __align__(16) float smem[];
-  __shared__ float red[16];
+template <bool TC>
+__device__ __forceinline__ void recon_body(const ReconLaunch& t, float* smem_f, tc::Ctx* tcx, float* red) {
   for (int it = blockIdx.x; it < t.n_items; it += gridDim.x) {
     const ReconItem item = t.items[it];
     MemberDev& mb = t.members[item.member];
     const ArchDesc& a = t.archs[mb.arch_idx];
     StepCtx c;
-    c.a = &a; c.mb = &mb; c.smem = smem; c.tc = nullptr; c.red = red; c.flags = 0;
+    c.a = &a; c.mb = &mb; c.smem = smem_f; c.tc = tcx; c.red = red; c.flags = 0;
     c.scratch = t.scratch + (long long)blockIdx.x * t.slot_floats;
     c.rows = item.rows; c.row0 = item.row0; c.step = 0;
     const float* const* xc = t.xc + (long long)item.member * NMB_MAX_MOD;
     prepare_slot(c);
-    encoders_forward<false>(c, xc);
+    encoders_forward<TC>(c, xc);
     const float* eps = (t.mode == NMB_RECON_SAMPLE && t.eps && t.eps[item.member])
         ? t.eps[item.member] + (long long)item.row0 * a.Z : nullptr;
     const int eps_mode = t.mode == NMB_RECON_MEAN ? 2 : (eps ? 1 : 0);
@@ -628,14 +627,40 @@ __global__ void __launch_bounds__(kThreads, 2) recon_kernel(ReconLaunch t) {
     }
     for (int m = 0; m < a.M; ++m) {
       const ModDesc& q = a.mod[m];
-      Opnd A = decoder_hidden<false>(c, m);
+      Opnd A = decoder_hidden<TC>(c, m);
       float* out = t.xhat[(long long)item.member * NMB_MAX_MOD + m];
       if (!out) continue;
       EpiStore e{out + (long long)item.row0 * q.D, q.D};
-      mm<false>(c, item.rows, q.D, q.outl.in + 1, A, Opnd{mb.params + q.outl.off, q.outl.ld, 1}, e);
+      mm<TC>(c, item.rows, q.D, q.outl.in + 1, A, Opnd{mb.params + q.outl.off, q.outl.ld, 1}, e);
     }
     __syncthreads();
   }
+}
+
+// FP32 engine (NMB_RECON_FP32 bit of `mode`)
+__global__ void __launch_bounds__(kThreads, 2) recon_kernel(ReconLaunch t) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ float red[16];
+  recon_body<false>(t, smem, nullptr, red);
+}
+
+// tcgen05 engine (default): BF16x3 split products, FP32 accumulation in TMEM
+__global__ void __launch_bounds__(kThreads, 2) recon_tc_kernel(ReconLaunch t) {
+  extern __shared__ __align__(128) unsigned char smem_tc[];
+  __shared__ float red[16];
+  __shared__ uint32_t s_tmem;
+  __shared__ __align__(8) uint64_t s_mbar;
+  if (threadIdx.x < 32) tc::tmem_alloc(&s_tmem, tc::kTmemCols);
+  if (threadIdx.x == 0) tc::mbar_init(&s_mbar, 1);
+  tc::fence_before();
+  __syncthreads();
+  tc::fence_after();
+  tc::Ctx tcx;
+  tcx.smem = smem_tc; tcx.mbar = &s_mbar; tcx.tmem_base = s_tmem; tcx.phase = 0;
+  recon_body<true>(t, nullptr, &tcx, red);
+  tc::fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) tc::tmem_free(tcx.tmem_base, tc::kTmemCols);
 }
 
 constexpr size_t kGemmSmemBytes = kGemmSmemFloats * sizeof(float);
@@ -646,6 +671,8 @@ cudaError_t configure_kernels() {
   e = cudaFuncSetAttribute(train_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(debug_tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(recon_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
   if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(recon_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes);
 }
@@ -671,7 +698,8 @@ cudaError_t launch_debug_tc_gemm(const float* A, int lda, int a_kmajor, const fl
 cudaError_t launch_recon(const ReconLaunch& t, cudaStream_t st) {
   const int grid = t.n_items < t.n_slots ? t.n_items : t.n_slots;
   if (grid <= 0) return cudaSuccess;
-  recon_kernel<<<grid, kThreads, kGemmSmemBytes, st>>>(t);
+  if (t.fp32) recon_kernel<<<grid, kThreads, kGemmSmemBytes, st>>>(t);
+  else recon_tc_kernel<<<grid, kThreads, tc::kSmemBytes, st>>>(t);
   return cudaGetLastError();
 }
 
