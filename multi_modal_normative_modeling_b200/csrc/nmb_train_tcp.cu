@@ -245,10 +245,11 @@ __device__ __forceinline__ void put_planes(unsigned char* blk, int g, int row, c
 __device__ __forceinline__ float adam_update(const EpiCtx& c, float& m1, float& v1, float p0, float g) {
   m1 = c.b1 * m1 + (1.f - c.b1) * g;
   v1 = c.b2 * v1 + (1.f - c.b2) * g * g;
-  float sq;
-  asm("sqrt.approx.f32 %0, %1;" : "=f"(sq) : "f"(v1));
+  float sq, rc;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(v1));
   const float denom = fmaf(sq, c.inv_bc2, c.aeps);
-  return p0 - c.step_size * __fdividef(m1, denom);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(denom));
+  return fmaf(-c.step_size * m1, rc, p0);
 }
 __device__ __forceinline__ void adam_scalar(const EpiCtx& c, long long idx, float g) {
   MemberDev& mb = *c.mb;

@@ -2,7 +2,8 @@
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from multi_modal_normative_modeling_b200 import EnsembleTrainer, workloads
+from multi_modal_normative_modeling_b200 import EnsembleTrainer, workloads, _lib
+if os.environ.get('NMB_LIB'): _lib.LIB_PATH = os.path.abspath(os.environ['NMB_LIB'])   # A/B against another build
 
 dev = torch.device("cuda", 0)
 hw = workloads.build_host_workload()
@@ -27,9 +28,12 @@ def run(idx, label):
     tr.close()
 small = [i for i, t in enumerate(wl.tags) if not t[1].startswith("early")]
 big = [i for i, t in enumerate(wl.tags) if t[1].startswith("early")]
+quick = "quick" in sys.argv
 run(small[:148], "D=116 x148 (1 wave)")
-run(small[:296], "D=116 x296 (2 waves)")
+if not quick:
+    run(small[:296], "D=116 x296 (2 waves)")
 run(small[:37], "D=116 x37 (quarter chip)")
 run(big[:120], "D=348 x120")
-run(big[:30], "D=348 x30")
+if not quick:
+    run(big[:30], "D=348 x30")
 run(list(range(len(wl.specs))), "cfg4 all 480")
