@@ -83,6 +83,8 @@ struct NmbEnsemble {
   long long master_floats = 0;
   std::vector<tcp::MStep> msteps;            // MMA step tables of all architectures (kernel parameters)
   std::vector<int> ms_off, ms_cnt;
+  std::vector<tcp::EpiP> epis_p;             // compact epilogue item tables (kernel parameters) where they fit
+  std::vector<int> ep_off, ep_cnt;
 };
 
 namespace {
@@ -99,6 +101,12 @@ int setup_tcp(NmbEnsemble* e) {
     for (const tcp::Step& s : P.steps) e->msteps.push_back(tcp::to_mstep(s));
   }
   if (e->msteps.size() > (size_t)tcp::kMaxParamSteps) return 0;     // too many distinct architectures: generic engine
+  for (const tcp::Program& P : progs) {       // item tables: parameters while they fit, else the global-memory copy
+    bool fits = e->epis_p.size() + P.epis.size() <= (size_t)tcp::kMaxParamEpis;
+    for (const tcp::Epi& ep : P.epis) fits = fits && tcp::epip_fits(ep);
+    e->ep_off.push_back((int)e->epis_p.size()); e->ep_cnt.push_back(fits ? (int)P.epis.size() : 0);
+    if (fits) for (const tcp::Epi& ep : P.epis) e->epis_p.push_back(tcp::to_epip(ep));
+  }
   auto dev_alloc = [&](size_t bytes, void** out) {
     cudaError_t ce = cudaMalloc(out, bytes ? bytes : 16);
     if (ce == cudaSuccess) { e->tcp_allocs.push_back(*out); ce = cudaMemset(*out, 0, bytes ? bytes : 16); }
@@ -361,7 +369,8 @@ int nmb_ensemble_train(NmbEnsemble* e, int64_t n_steps, const float* eps_overrid
     // dataset rows may have been re-packed since the last call: refresh their planes (cheap, streaming)
     CU(launch_xprep(e->xprep_dev, e->n_xprep, e->xprep_max_blocks, (cudaStream_t)stream));
     CU(launch_train_tcp(t, e->progs_dev, e->mtc_dev, e->stash, e->stash_bytes, e->master, e->master_floats,
-                        e->msteps.data(), e->ms_off.data(), e->ms_cnt.data(), (int)e->ms_off.size(), e->n_sm,
+                        e->msteps.data(), e->ms_off.data(), e->ms_cnt.data(), (int)e->ms_off.size(),
+                        e->epis_p.data(), e->ep_off.data(), e->ep_cnt.data(), e->n_sm,
                         (cudaStream_t)stream));
   } else {
     CU(launch_train(t, (cudaStream_t)stream));

@@ -90,7 +90,7 @@ struct MStep {
   short mma_dep, mma_dep_joint;
   unsigned char half, a_tile, a_mn, b_mn, first, commit, commit_buf, commit2;   // commit2_buf = accumulator of `half`
 };
-constexpr int kMaxParamSteps = 640;                   // 40 B each: 25.6 KB of the 32 KB parameter space
+constexpr int kMaxParamSteps = 448;                   // 40 B each: 17.9 KB of the 32 KB parameter space
 constexpr int kMaxParamArchs = 8;
 
 inline MStep to_mstep(const Step& s) {
@@ -127,6 +127,47 @@ struct alignas(16) Epi {
                                     // before it trusts its view of the accumulator barrier phases
 };
 
+// Compact copy of an Epi (64 B).  Like the MMA step table it travels in the KERNEL PARAMETERS, so that decoding an
+// item costs a few uniform loads from the constant bank instead of a 144-byte read through L2 on the critical path
+// of every item.  Architectures whose items do not fit (kMaxParamEpis in total) read the global-memory table.
+struct alignas(16) EpiP {
+  int stash_off, src_off, p_off, wp_off, mst_off;       // byte / float offsets (all < 2^31), -1 = none
+  unsigned short n_mma, n_valid, n_cols, tmem_col, col0, src_cg, p_ld, p_rows, p_cols, wp_R, mst_R, row0, wait_optim;
+  signed char kind, half, buf, mod;
+  unsigned char to_act, last, split_all, pad_;
+  int pad2_[2];
+};
+static_assert(sizeof(EpiP) == 64, "EpiP must stay 64 bytes");
+constexpr int kMaxParamEpis = 160;                    // 10 KB
+
+inline bool epip_fits(const Epi& e) {
+  return e.stash_off < (1LL << 31) && e.src_off < (1LL << 31) && e.p_off < (1LL << 31) && e.wp_off < (1LL << 31) &&
+         e.mst_off < (1LL << 31) && e.p_ld < 65536 && e.p_rows < 65536 && e.p_cols < 65536;
+}
+inline EpiP to_epip(const Epi& e) {
+  EpiP q{};
+  q.stash_off = (int)e.stash_off; q.src_off = (int)e.src_off; q.p_off = (int)e.p_off; q.wp_off = (int)e.wp_off;
+  q.mst_off = (int)e.mst_off;
+  q.n_mma = (unsigned short)e.n_mma; q.n_valid = (unsigned short)e.n_valid; q.n_cols = (unsigned short)e.n_cols;
+  q.tmem_col = (unsigned short)e.tmem_col; q.col0 = (unsigned short)e.col0; q.src_cg = (unsigned short)e.src_cg;
+  q.p_ld = (unsigned short)e.p_ld; q.p_rows = (unsigned short)e.p_rows; q.p_cols = (unsigned short)e.p_cols;
+  q.wp_R = (unsigned short)e.wp_R; q.mst_R = (unsigned short)e.mst_R; q.row0 = (unsigned short)e.row0;
+  q.wait_optim = (unsigned short)e.wait_optim;
+  q.kind = (signed char)e.kind; q.half = (signed char)e.half; q.buf = (signed char)e.buf; q.mod = (signed char)e.mod;
+  q.to_act = (unsigned char)e.to_act; q.last = (unsigned char)e.last; q.split_all = (unsigned char)e.split_all;
+  return q;
+}
+__host__ __device__ inline Epi from_epip(const EpiP& q) {
+  Epi e;
+  e.kind = q.kind; e.half = q.half; e.buf = q.buf; e.mod = q.mod;
+  e.n_mma = q.n_mma; e.n_valid = q.n_valid; e.n_cols = q.n_cols; e.tmem_col = q.tmem_col; e.col0 = q.col0;
+  e.to_act = q.to_act; e.stash_off = q.stash_off; e.src_off = q.src_off; e.src_cg = q.src_cg;
+  e.p_off = q.p_off; e.p_ld = q.p_ld; e.p_rows = q.p_rows; e.p_cols = q.p_cols;
+  e.wp_off = q.wp_off; e.wp_R = q.wp_R; e.mst_off = q.mst_off; e.mst_R = q.mst_R;
+  e.row0 = q.row0; e.last = q.last; e.split_all = q.split_all; e.wait_optim = q.wait_optim;
+  return e;
+}
+
 // Weight block of the per-member planes buffer (prologue conversion fp32 -> planes).
 struct WBlock {
   long long p_off; int p_ld, row0, rows_valid, cols_valid;
@@ -150,6 +191,7 @@ struct Layout {
   int wout_cg[NMB_MAX_MOD];                       // column groups of a decoder_mean_layer planes block
   long long zbuf, dz;                             // [256][Z]
   long long lampart[NMB_MAX_MOD];                 // [8][round4(D)] logvar_out gradient partials
+  long long ivtab[NMB_MAX_MOD];                   // [round4(D) + 8] exp(-logvar_out), zero padded
   long long dxh_blk[NMB_MAX_MOD];                 // first d/dx_recon block of half 0 (blocks of 32 KB, [half][j])
   int n_dxh_blk[NMB_MAX_MOD];
   long long stash_bytes;
@@ -251,6 +293,7 @@ inline Program build_program(const ArchDesc& a) {
     lay.dxh_blk[m] = alloc((long long)2 * lay.n_dxh_blk[m] * 32768 + 128);
     lay.mulv[m] = alloc((long long)256 * lay.ld_mulv * 4);
     lay.lampart[m] = alloc((long long)8 * round4(q.D) * 4);
+    lay.ivtab[m] = alloc((long long)(round4(q.D) + 8) * 4);
     lay.x_cg[m] = round16(q.D + C + 1) / 8;
     lay.x_quads[m] = (q.D + 3) / 4;
     for (int l = 0; l < L; ++l) { master(q.enc[l], 0); master(q.dec[l], 0); }

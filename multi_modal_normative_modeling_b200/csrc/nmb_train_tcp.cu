@@ -139,7 +139,9 @@ struct LaunchP {
   float* master;            // per slot: 3 x master_floats (p, m, v)
   long long master_floats;
   int ms_off[kMaxParamArchs], ms_cnt[kMaxParamArchs];   // slice of msteps per architecture
+  int ep_off[kMaxParamArchs], ep_cnt[kMaxParamArchs];   // slice of epis_p per architecture; cnt 0 = global-memory table
   MStep msteps[kMaxParamSteps];
+  EpiP epis_p[kMaxParamEpis];
 };
 
 __device__ __forceinline__ bool elect_one() {
@@ -349,10 +351,11 @@ __device__ void move_master(const EpiCtx& c, bool gather) {
 
 __device__ __forceinline__ void epi_hidden(EpiCtx& c, const Epi& e) {
   const int h = e.half;
-  const bool vr = c.row < c.rows_of(h);
-  unsigned char* act = c.smem + h * kActBytes;
-  unsigned char* st = c.stash + e.stash_off;
-  const int nl = c.a->non_linear;
+  const int rows = c.rows_of(h);
+  const bool vr = c.row < rows;
+  unsigned char* act = c.smem + h * kActBytes + c.row * 16;
+  unsigned char* st = c.stash + e.stash_off + c.row * 16;
+  const float slope = c.a->non_linear ? kSlope : 1.f;        // leaky-relu(x) = max(x, slope * x)
   const int n_cols = e.n_cols, n_mma = e.n_mma, n_valid = e.n_valid, tcol = e.tmem_col;
   for (int ch = c.cpart; ch * 16 < n_cols; ch += c.parts) {
     const int col = ch * 16;
@@ -362,12 +365,16 @@ __device__ __forceinline__ void epi_hidden(EpiCtx& c, const Epi& e) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = 0.f;
     }
+    if (rows == 128 && col + 16 <= n_valid) {      // whole chunk inside the layer's outputs, every row live: no masks
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const int cc = col + j;
-      float x = v[j];
-      x = (nl && x <= 0.f) ? kSlope * x : x;
-      v[j] = !vr ? 0.f : (cc < n_valid ? x : (cc == n_valid ? 1.f : 0.f));
+      for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], slope * v[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int cc = col + j;
+        const float x = fmaxf(v[j], slope * v[j]);
+        v[j] = !vr ? 0.f : (cc < n_valid ? x : (cc == n_valid ? 1.f : 0.f));     // bias column: constant 1
+      }
     }
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
@@ -376,7 +383,7 @@ __device__ __forceinline__ void epi_hidden(EpiCtx& c, const Epi& e) {
       for (int j = 0; j < 8; ++j) x[j] = v[8 * q + j];
       uint4 hh, ll;
       tc::split8(x, hh, ll);
-      const long long off = (long long)(2 * ch + q) * 4096 + c.row * 16;
+      const long long off = (long long)(2 * ch + q) * 4096;
       *reinterpret_cast<uint4*>(act + off) = hh;
       *reinterpret_cast<uint4*>(act + off + 2048) = ll;
       *reinterpret_cast<uint4*>(st + off) = hh;
@@ -474,8 +481,47 @@ __device__ __forceinline__ void epi_copy(EpiCtx& c, const Epi& e) {
   for (int u = c.tid; u < n; u += c.nthr) dst[u] = src[u];
 }
 
+// Column sums over the 32 rows of a warp: 8 values per lane -> lanes (bit4, bit3, bit2) hold one column each, in
+// 4 + 2 + 1 + 1 + 1 shuffles.  Returns the sum of column cj (valid in lanes with (lane & 3) == 0).
+__device__ __forceinline__ float warp_colsum8(const float (&qv)[8], int lane, int& cj) {
+  float s4[4], s2[2], s1;
+  const bool up16 = lane & 16, up8 = lane & 8, up4 = lane & 4;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float keepv = up16 ? qv[j + 4] : qv[j], send = up16 ? qv[j] : qv[j + 4];
+    s4[j] = keepv + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const float keepv = up8 ? s4[j + 2] : s4[j], send = up8 ? s4[j] : s4[j + 2];
+    s2[j] = keepv + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  {
+    const float keepv = up4 ? s2[1] : s2[0], send = up4 ? s2[0] : s2[1];
+    s1 = keepv + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+  s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+  cj = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+  return s1;
+}
+
+// exp(-logvar_out) per ROI, zero-padded by 8: refreshed whenever logvar_out changes (member start, EK_STEP_END), so
+// the reconstruction epilogue needs one coalesced float4 pair per chunk instead of 8 loads + 8 exponentials.
+__device__ void build_iv_table(const EpiCtx& c) {
+  const ArchDesc& a = *c.a;
+  if (a.loss_kind != NMB_LOSS_GAUSS_LL) return;
+  for (int m = 0; m < a.M; ++m) {
+    const ModDesc& q = a.mod[m];
+    float* iv = reinterpret_cast<float*>(c.stash + c.pg->lay.ivtab[m]);
+    for (int n = c.tid; n < round4(q.D) + 8; n += c.nthr) iv[n] = n < q.D ? __expf(-c.mb->params[q.lam_off + n]) : 0.f;
+  }
+}
+
 // x_recon tile: loss terms, d(total)/d(x_recon) planes (ACT[h] or stash), logvar_out gradient partials.
-// 8 columns (one plane group) per iteration keeps the live registers under the 96-register budget.
+// Gaussian LL per element: -0.5 r^2 e^{-lam} - 0.5 lam - 0.5 log 2pi.  Only the first term is accumulated here; the
+// row-independent rest is added once per step in epi_lam.  Rows beyond the minibatch and columns beyond D need no
+// masks: their targets, reconstructions (zero operand rows / weight rows) and table entries are exactly zero.
 __device__ __forceinline__ void epi_recon(EpiCtx& c, const Epi& e) {
   const ArchDesc& a = *c.a;
   const ModDesc& q = a.mod[e.mod];
@@ -485,17 +531,17 @@ __device__ __forceinline__ void epi_recon(EpiCtx& c, const Epi& e) {
   const int gauss = a.loss_kind == NMB_LOSS_GAUSS_LL;
   const float inv_rows = 1.f / c.rows;
   const float inv_rows_d = inv_rows / q.D;
-  const float ll_scale = gauss ? inv_rows : inv_rows_d;
-  const float* __restrict__ lam = c.mb->params + q.lam_off;
+  const float gscale = gauss ? -inv_rows : -2.f * inv_rows_d;
   unsigned char* st = e.to_act ? c.smem + h * kActBytes : c.stash + e.stash_off;   // d/dx_recon planes
   // ROI targets of this row, lane-major: float4 (col quad) of 32 consecutive rows = 512 contiguous bytes
   const float* __restrict__ xq = c.mt->xlm[e.mod] + ((long long)(c.pos * c.mt->n_half + h) * lay.x_quads[e.mod] * 128 + c.row) * 4;
+  const float* ivt = reinterpret_cast<const float*>(c.stash + lay.ivtab[e.mod]);
   float* keep = (c.flags & NMB_TRAIN_KEEP_ACTS) ? c.scratch + q.s_xr + (long long)(128 * h + c.row) * q.ld_xh : nullptr;
   float* lampart = reinterpret_cast<float*>(c.stash + lay.lampart[e.mod]) + (long long)(h * 4 + (c.warp & 3)) * round4(q.D);
   const int n_valid = e.n_valid, col0 = e.col0, tcol = e.tmem_col, n_cols = e.n_cols, D = q.D;
   float ll = 0.f;
-  // targets of chunk k + 1 are in flight while chunk k is processed
-  float4 xa = make_float4(0.f, 0.f, 0.f, 0.f), xb = xa;
+  // targets and table entries of chunk k + 1 are in flight while chunk k is processed
+  float4 xa = make_float4(0.f, 0.f, 0.f, 0.f), xb = xa, ia = xa, ib = xa;
 #define NMB_LOAD_X(CH)                                                                                   \
   do {                                                                                                   \
     const int gc_ = col0 + (CH) * 8;                                                                     \
@@ -504,99 +550,101 @@ __device__ __forceinline__ void epi_recon(EpiCtx& c, const Epi& e) {
       xa = *reinterpret_cast<const float4*>(xq + (long long)(gc_ >> 2) * 512);                           \
       if (gc_ + 4 < D) xb = *reinterpret_cast<const float4*>(xq + (long long)((gc_ >> 2) + 1) * 512);    \
     }                                                                                                    \
+    if (gauss) {                                                                                         \
+      ia = *reinterpret_cast<const float4*>(ivt + gc_);                                                  \
+      ib = *reinterpret_cast<const float4*>(ivt + gc_ + 4);                                              \
+    }                                                                                                    \
   } while (0)
   if (c.cpart * 8 < n_cols) NMB_LOAD_X(c.cpart);
+  float qprev[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) qprev[j] = 0.f;
+  int gc_prev = -1, nv_prev = 0;
   for (int ch = c.cpart; ch * 8 < n_cols; ch += c.parts) {
     const int col = ch * 8, gc = col0 + col;
     const int nv = min(max(n_valid - col, 0), 8);
-    float v[8], l[8];
     const float xt[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+    const float iv[8] = {ia.x, ia.y, ia.z, ia.w, ib.x, ib.y, ib.z, ib.w};
     if ((ch + c.parts) * 8 < n_cols) NMB_LOAD_X(ch + c.parts);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) l[j] = 0.f;
-    if (nv > 0 && gauss) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) if (j < nv) l[j] = __ldg(lam + gc + j);
-    }
+    uint32_t raw[8];
     __syncwarp();
-    tc::tmem_ld8(taddr(c, tcol + col), v);
-    float gr[8], qv[8];
+    tc::tmem_ld8_issue(taddr(c, tcol + col), raw);
+    if (gauss && gc_prev >= 0) {     // column sums of the previous chunk overlap the accumulator load of this one
+      int cj;
+      const float s1 = warp_colsum8(qprev, c.lane, cj);
+      if (!(c.lane & 3) && cj < nv_prev) lampart[gc_prev + cj] = s1;
+    }
+    tc::tmem_ld_wait8(raw);
+    float gr[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const bool ok = vr && j < nv;
-      const float r = xt[j] - v[j];
-      float t, g, qq = 0.f;
-      if (gauss) {
-        const float iv = __expf(-l[j]);
-        t = -0.5f * r * r * iv - 0.5f * l[j] - 0.5f * kLog2Pi;
-        g = -r * iv * inv_rows;
-        qq = 0.5f * (1.f - r * r * iv);
-      } else {
-        t = -r * r;
-        g = -2.f * r * inv_rows_d;
-      }
-      ll += ok ? t : 0.f;
-      gr[j] = ok ? g : 0.f;
-      qv[j] = ok ? qq : 0.f;
+      const float r = xt[j] - __uint_as_float(raw[j]);
+      const float ri = gauss ? r * iv[j] : r;
+      const float rri = r * ri;
+      ll += rri;
+      gr[j] = ri * gscale;
+      qprev[j] = rri;
+    }
+    if (!vr) {          // ragged minibatch: keep the invariant "rows beyond the minibatch are zero" explicit
+#pragma unroll
+      for (int j = 0; j < 8; ++j) gr[j] = 0.f;
     }
     put_planes(st, ch, c.row, gr);
     if (keep && vr && nv > 0) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) if (j < nv) keep[gc + j] = v[j];
+      for (int j = 0; j < 8; ++j) if (j < nv) keep[gc + j] = __uint_as_float(raw[j]);
     }
-    if (gauss) {
-      // column sums over the 32 rows of this warp: 8 values -> lanes (bit4,bit3,bit2) in 4+2+1+1+1 shuffles
-      float s4[4], s2[2], s1;
-      const bool up16 = c.lane & 16, up8 = c.lane & 8, up4 = c.lane & 4;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float keepv = up16 ? qv[j + 4] : qv[j], send = up16 ? qv[j] : qv[j + 4];
-        s4[j] = keepv + __shfl_xor_sync(0xffffffffu, send, 16);
-      }
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const float keepv = up8 ? s4[j + 2] : s4[j], send = up8 ? s4[j] : s4[j + 2];
-        s2[j] = keepv + __shfl_xor_sync(0xffffffffu, send, 8);
-      }
-      {
-        const float keepv = up4 ? s2[1] : s2[0], send = up4 ? s2[0] : s2[1];
-        s1 = keepv + __shfl_xor_sync(0xffffffffu, send, 4);
-      }
-      s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
-      s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
-      const int cj = ((c.lane >> 4) & 1) * 4 + ((c.lane >> 3) & 1) * 2 + ((c.lane >> 2) & 1);
-      if (!(c.lane & 3) && cj < nv) lampart[gc + cj] = s1;
-    }
+    gc_prev = gc; nv_prev = nv;
   }
-  c.ll_acc += ll * ll_scale;
+  if (gauss && gc_prev >= 0) {
+    int cj;
+    const float s1 = warp_colsum8(qprev, c.lane, cj);
+    if (!(c.lane & 3) && cj < nv_prev) lampart[gc_prev + cj] = s1;
+  }
+#undef NMB_LOAD_X
+  c.ll_acc += ll * (gauss ? -0.5f * inv_rows : -inv_rows_d);
 }
 
+// logvar_out: gradient from the per-warp partial sums of r^2 e^{-lam} (both halves complete), Adam, refreshed
+// exp(-lam) table; also adds the row-independent part of the Gaussian LL of this step (pre-update values).
 __device__ __forceinline__ void epi_lam(EpiCtx& c, const Epi& e) {
   const ModDesc& q = c.a->mod[e.mod];
   const float* part = reinterpret_cast<const float*>(c.stash + c.pg->lay.lampart[e.mod]);
+  float* iv = reinterpret_cast<float*>(c.stash + c.pg->lay.ivtab[e.mod]);
   const int ld = round4(q.D);
   const int np = c.rows_h1 > 0 ? 8 : 4;
   const float inv_rows = 1.f / c.rows;
+  float llc = 0.f;
   for (int n = c.tid; n < q.D; n += c.nthr) {
     float s = 0.f;
     for (int k = 0; k < np; ++k) s += part[k * ld + n];
-    adam_scalar(c, q.lam_off + n, s * inv_rows);
+    llc += -0.5f * c.mb->params[q.lam_off + n] - 0.5f * kLog2Pi;
+    adam_scalar(c, q.lam_off + n, 0.5f - 0.5f * s * inv_rows);       // mean over rows of 0.5 (1 - r^2 e^{-lam})
+    iv[n] = __expf(-c.mb->params[q.lam_off + n]);
   }
+  c.ll_acc += llc;
 }
 
 __device__ __forceinline__ void epi_dgrad(EpiCtx& c, const Epi& e) {
   const int h = e.half;
-  const bool vr = c.row < c.rows_of(h);
+  const int rows = c.rows_of(h);
+  const bool vr = c.row < rows;
   unsigned char* act = c.smem + h * kActBytes;
-  const unsigned char* sg = c.stash + e.src_off;
+  const unsigned char* sg = c.stash + e.src_off + c.row * 16;
   const int nl = c.a->non_linear;
   const int n_cols = e.n_cols, n_mma = e.n_mma, n_valid = e.n_valid, tcol = e.tmem_col;
+  // the sign source of chunk k + 1 (hi plane of the stored activation) is in flight while chunk k is processed
+  uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0;
+  if (nl && c.cpart * 16 < n_cols) {
+    n0 = *reinterpret_cast<const uint4*>(sg + (long long)(2 * c.cpart) * 4096);
+    n1 = *reinterpret_cast<const uint4*>(sg + (long long)(2 * c.cpart + 1) * 4096);
+  }
   for (int ch = c.cpart; ch * 16 < n_cols; ch += c.parts) {
     const int col = ch * 16;
-    uint4 s0 = make_uint4(0, 0, 0, 0), s1 = s0;
-    if (nl) {
-      s0 = *reinterpret_cast<const uint4*>(sg + (long long)(2 * ch) * 4096 + c.row * 16);
-      s1 = *reinterpret_cast<const uint4*>(sg + (long long)(2 * ch + 1) * 4096 + c.row * 16);
+    const uint4 s0 = n0, s1 = n1;
+    if (nl && (ch + c.parts) * 16 < n_cols) {
+      n0 = *reinterpret_cast<const uint4*>(sg + (long long)(2 * (ch + c.parts)) * 4096);
+      n1 = *reinterpret_cast<const uint4*>(sg + (long long)(2 * (ch + c.parts) + 1) * 4096);
     }
     float v[16];
     if (col < n_mma) tc::tmem_ld16(taddr(c, tcol + col), v);
@@ -605,12 +653,17 @@ __device__ __forceinline__ void epi_dgrad(EpiCtx& c, const Epi& e) {
       for (int j = 0; j < 16; ++j) v[j] = 0.f;
     }
     const uint32_t sw[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    if (nl) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const uint32_t hb = (sw[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu;      // bf16 bits of the stored activation
-      const bool nonpos = nl && ((hb & 0x8000u) || (hb & 0x7FFFu) == 0u);
-      const float x = nonpos ? kSlope * v[j] : v[j];
-      v[j] = (vr && col + j < n_valid) ? x : 0.f;
+      for (int j = 0; j < 16; ++j) {
+        // stored activation (bf16 hi) > 0  <=>  pre-activation > 0: derivative 1, else the slope
+        const float a = __uint_as_float((j & 1) ? (sw[j >> 1] & 0xFFFF0000u) : (sw[j >> 1] << 16));
+        v[j] = a > 0.f ? v[j] : kSlope * v[j];
+      }
+    }
+    if (!(rows == 128 && col + 16 <= n_valid)) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = (vr && col + j < n_valid) ? v[j] : 0.f;
     }
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
@@ -997,7 +1050,8 @@ __device__ __forceinline__ void set_workers(EpiCtx& c, bool all) {
 // data gradients: two independent dependency chains whose latencies overlap) and the optimiser group, which
 // consumes the weight-gradient accumulators (Adam + new weight planes) off both chains.  Every group walks the
 // item list and executes its own items; EK_STEP_END is the only rendezvous.
-__device__ void epilogue_role(const TrainLaunch& t, int mi, EpiCtx& c, uint32_t& acc_par) {
+__device__ void epilogue_role(const LaunchP& L, int ai, int mi, EpiCtx& c, uint32_t& acc_par) {
+  const TrainLaunch& t = L.t;
   const ProgramDev& pg = *c.pg;
   MemberDev& mb = *c.mb;
   c.kl_acc = 0.f; c.ll_acc = 0.f;
@@ -1006,6 +1060,7 @@ __device__ void epilogue_role(const TrainLaunch& t, int mi, EpiCtx& c, uint32_t&
   c.dw_acc = dw_acc;
   set_workers(c, true);
   build_weight_planes(c);
+  build_iv_table(c);
   const bool adam_on = !(c.flags & NMB_TRAIN_NO_ADAM);
   if (adam_on) move_master(c, true);
   __threadfence();
@@ -1018,6 +1073,8 @@ __device__ void epilogue_role(const TrainLaunch& t, int mi, EpiCtx& c, uint32_t&
   const long long s0 = mb.steps_done;
   const int n_epis = pg.n_epis;
   const Epi* __restrict__ epis = pg.epis;
+  const bool in_params = L.ep_cnt[ai] > 0;      // item table in the kernel parameters (constant bank)
+  const int ep0 = L.ep_off[ai];
   const bool pub = (c.warp % kGroupWarps) == 0 && c.lane == 0;     // the thread that publishes its group's counter
   for (long long i = 0; i < t.n_steps; ++i) {
     const long long s = s0 + i;
@@ -1033,8 +1090,12 @@ __device__ void epilogue_role(const TrainLaunch& t, int mi, EpiCtx& c, uint32_t&
     const float* eps = t.eps_override ? t.eps_override + ((long long)mi * t.n_steps + i) * mb.batch * c.a->Z : nullptr;
     float* lo = t.loss_out ? t.loss_out + ((long long)mi * t.n_steps + i) * 3 : nullptr;
     for (int k = 0; k < n_epis; ++k) {
-      const Epi e = epis[k];
-      if (c.lane == 0 && k + 2 < n_epis) asm volatile("prefetch.global.L1 [%0];" ::"l"(epis + k + 2));
+      Epi e;
+      if (in_params) e = from_epip(L.epis_p[ep0 + k]);
+      else {
+        e = epis[k];
+        if (c.lane == 0 && k + 2 < n_epis) asm volatile("prefetch.global.L1 [%0];" ::"l"(epis + k + 2));
+      }
       const bool all = e.kind == EK_STEP_END;
       const bool optim = e.kind == EK_WGRAD || e.kind == EK_WGRAD_T;
       const int owner = (all || e.split_all) ? c.grp : (optim ? 2 : e.half);
@@ -1134,7 +1195,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) train_tcp_kernel(const __grid_co
       c.tmem = tmem; c.warp = warp; c.lane = lane; c.row = ((warp & 3) << 5) + lane;
       c.grp = warp / kGroupWarps; c.flags = t.flags;
       c.b1 = mb.beta1; c.b2 = mb.beta2; c.aeps = mb.adam_eps;
-      epilogue_role(t, mi, c, acc_par);
+      epilogue_role(L, mb.arch_idx, mi, c, acc_par);
     } else if (warp == kEpiWarps) {
       const int ai = __shfl_sync(0xffffffffu, mb.arch_idx, 0);
       mma_role(L, ai, mb, smem, ctl, tmem, seq, pg.n_epis);
@@ -1236,6 +1297,7 @@ cudaError_t launch_xprep(const void* items_dev, int n_items, int max_blocks, cud
 cudaError_t launch_train_tcp(const TrainLaunch& t, const tcp::ProgramDev* progs, const tcp::MemberTc* mtc,
                              unsigned char* stash, long long stash_bytes, float* master, long long master_floats,
                              const tcp::MStep* msteps, const int* ms_off, const int* ms_cnt, int n_archs,
+                             const tcp::EpiP* epis_p, const int* ep_off, const int* ep_cnt,
                              int n_sm, cudaStream_t st) {
   const int grid = t.n_members < n_sm ? t.n_members : n_sm;
   if (grid <= 0 || t.n_steps <= 0) return cudaSuccess;
@@ -1246,7 +1308,12 @@ cudaError_t launch_train_tcp(const TrainLaunch& t, const tcp::ProgramDev* progs,
   tcp::LaunchP L;
   L.t = t; L.progs = progs; L.mtc = mtc; L.stash = stash; L.stash_bytes = stash_bytes;
   L.master = master; L.master_floats = master_floats;
-  for (int a = 0; a < n_archs; ++a) { L.ms_off[a] = ms_off[a]; L.ms_cnt[a] = ms_cnt[a]; }
+  for (int a = 0; a < n_archs; ++a) { L.ms_off[a] = ms_off[a]; L.ms_cnt[a] = ms_cnt[a]; L.ep_off[a] = ep_off[a]; L.ep_cnt[a] = ep_cnt[a]; }
+  {
+    int n_ep = 0;
+    for (int a = 0; a < n_archs; ++a) if (ep_cnt[a] > 0 && ep_off[a] + ep_cnt[a] > n_ep) n_ep = ep_off[a] + ep_cnt[a];
+    if (n_ep > 0) std::memcpy(L.epis_p, epis_p, sizeof(tcp::EpiP) * (size_t)n_ep);
+  }
   std::memcpy(L.msteps, msteps, sizeof(tcp::MStep) * (size_t)(ms_off[n_archs - 1] + ms_cnt[n_archs - 1]));
   tcp::train_tcp_kernel<<<grid, tcp::kThreadsP, tcp::kSmemBytes, st>>>(L);
   return cudaGetLastError();
