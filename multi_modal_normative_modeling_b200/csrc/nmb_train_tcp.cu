@@ -47,11 +47,15 @@ __device__ __forceinline__ void st_release(volatile uint32_t* p, uint32_t v) {
 }
 // Bounded spin with back-off (a protocol bug must trap, not hang the GPU; the spinning single-thread
 // warps must not steal issue slots from the epilogue warps of their scheduler).
+#ifndef NMB_POLL_NS
+#define NMB_POLL_NS 100
+#endif
+constexpr unsigned kPollSleepNs = NMB_POLL_NS;
 __device__ __forceinline__ void wait_epi(const volatile uint32_t* p, uint32_t need) {
   if (ld_relaxed(p) < need) {
     const long long t0 = clock64();
     while (ld_relaxed(p) < need) {
-      __nanosleep(100);
+      __nanosleep(kPollSleepNs);
       if (clock64() - t0 > 4000000000LL) __trap();
     }
   }
@@ -94,15 +98,35 @@ __device__ __forceinline__ StepVars step_vars(const MemberDev& mb, long long s, 
 
 // ------------------------------------------------------------------------------------------------
 // producer: TMA bulk copies of operand tiles, in program order, into the ring
+// The fields of a Step the producer needs, fetched one step ahead (the table lives in global memory: an L2 round
+// trip per step would otherwise sit on the single producer thread's critical path).
+struct PStep {
+  long long b_off, a_off;
+  unsigned b_bytes, a_bytes;
+  int dep;
+  unsigned char half, b_space, a_space, x_mod, dep_grp;
+};
+__device__ __forceinline__ PStep load_pstep(const Step* steps, int k) {
+  const Step& st = steps[k];
+  PStep p;
+  p.b_off = st.b_off; p.a_off = st.a_off; p.b_bytes = st.b_bytes; p.a_bytes = st.a_bytes; p.dep = st.dep;
+  p.half = st.half; p.b_space = st.b_space; p.a_space = st.a_space; p.x_mod = st.x_mod; p.dep_grp = st.dep_grp;
+  return p;
+}
+
 __device__ void producer_role(const TrainLaunch& t, const ProgramDev& pg, const MemberDev& mb, const MemberTc& mt,
                               const unsigned char* stash, unsigned char* smem, Ctrl* ctl, uint32_t& seq) {
   unsigned char* ring = smem + kSmemRing;
+  const Step* __restrict__ steps = pg.steps;
+  const int n_steps = pg.n_steps;
+  PStep nxt = load_pstep(steps, 0);
   for (long long i = 0; i < t.n_steps; ++i) {
     const StepVars sv = step_vars(mb, mb.steps_done + i, i, pg.n_epis);
     const bool tr = g_trace && blockIdx.x == 0 && i == g_trace_step;
     const int tb = 3 * pg.n_epis + 3 * pg.n_steps;
-    for (int k = 0; k < pg.n_steps; ++k) {
-      const Step& st = pg.steps[k];
+    for (int k = 0; k < n_steps; ++k) {
+      const PStep st = nxt;
+      nxt = load_pstep(steps, k + 1 < n_steps ? k + 1 : 0);
       if (sv.rows_h[st.half] == 0) continue;
       if (st.dep) {              // data written by an epilogue item of this step (stash blocks behind their fence)
         if (st.dep_grp < 2) wait_epi(&ctl->epi_done[st.dep_grp], sv.base + (uint32_t)st.dep);
