@@ -267,6 +267,11 @@ __device__ __forceinline__ void put_planes(unsigned char* blk, int g, int row, c
   *reinterpret_cast<uint4*>(p + 2048) = l;
 }
 
+// Adam master state is a pure stream (read once, written once per step, re-read a whole step later): keep it from
+// displacing the weight planes and the backward stash in L2.
+__device__ __forceinline__ float4 ld_stream4(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void st_stream4(float* p, const float4& v) { __stcs(reinterpret_cast<float4*>(p), v); }
+
 // torch.optim.Adam element update; sqrt / reciprocal on the SFU (2 ulp, far inside the parity budget)
 __device__ __forceinline__ float adam_update(const EpiCtx& c, float& m1, float& v1, float p0, float g) {
   m1 = c.b1 * m1 + (1.f - c.b1) * g;
@@ -775,46 +780,53 @@ __device__ void epi_latent_bwd(EpiCtx& c, const Epi& e) {
 }
 
 // weight gradient (lane = output row) fused with Adam on the lane-major master state; rewrites the
-// BF16 planes of the layer
+// BF16 planes of the layer.  Every address is a cursor advanced by a constant stride per chunk.
 __device__ __forceinline__ void epi_wgrad(EpiCtx& c, const Epi& e) {
   MemberDev& mb = *c.mb;
   const int o = c.row;
   const bool vo = o < e.p_rows;
-  const int wp_R = e.wp_R, p_ld = e.p_ld, p_cols = e.p_cols, n_mma = e.n_mma, col0 = e.col0, tcol = e.tmem_col;
-  const int R4 = e.mst_R * 4;
-  unsigned char* wp = c.mt->wplanes + e.wp_off + o * 16;
-  const long long rowbase = e.p_off + (long long)o * p_ld;
-  const long long mbase = e.mst_off + (long long)o * 4;
-  float* __restrict__ Pp = c.mst_p; float* __restrict__ Pm = c.mst_m; float* __restrict__ Pv = c.mst_v;
+  const int p_cols = e.p_cols, n_mma = e.n_mma, col0 = e.col0;
   const bool adam = !(c.flags & NMB_TRAIN_NO_ADAM), wg = c.flags & NMB_TRAIN_WRITE_GRADS;
-  // Software pipeline: the state (p, m, v) of chunk k + 1 is in flight while chunk k is updated and stored.
+  const long long R4 = (long long)e.mst_R * 4;                       // floats between consecutive column quads
+  const long long m0 = e.mst_off + (long long)o * 4 + (long long)((col0 >> 2) + 2 * c.cpart) * R4;
+  float* __restrict__ pp = c.mst_p + m0; float* __restrict__ pm = c.mst_m + m0; float* __restrict__ pv = c.mst_v + m0;
+  const long long mstride = 2 * c.parts * R4;
+  unsigned char* wp = c.mt->wplanes + e.wp_off + o * 16 + (long long)((col0 >> 3) + c.cpart) * 32 * e.wp_R;
+  const long long wstride = (long long)c.parts * 32 * e.wp_R;
+  const int lo_off = 16 * e.wp_R;
+  uint32_t ta = taddr(c, e.tmem_col + 8 * c.cpart);
+  const uint32_t tstride = 8 * c.parts;
+  const long long rowbase = e.p_off + (long long)o * e.p_ld;
+  const bool live = vo && adam;
+  // Software pipeline: the state (p, m, v) of chunk k + 1 is in flight while chunk k is updated and stored; the
+  // lines of chunk k + 2 are on their way to L1.
   float4 n0, n1, n2, n3, n4, n5;
   n0 = n1 = n2 = n3 = n4 = n5 = make_float4(0.f, 0.f, 0.f, 0.f);
-#define NMB_LOAD_STATE(CH)                                                                                       \
+#define NMB_LOAD_STATE(COL, OFF)                                                                                 \
   do {                                                                                                           \
-    const int col_ = col0 + (CH) * 8;                                                                            \
     n0 = n1 = n2 = n3 = n4 = n5 = make_float4(0.f, 0.f, 0.f, 0.f);                                                \
-    if (vo && col_ < p_cols && adam) {                                                                           \
-      const long long mi_ = mbase + (long long)(col_ >> 2) * R4;                                                 \
-      n0 = *reinterpret_cast<const float4*>(Pp + mi_); n2 = *reinterpret_cast<const float4*>(Pm + mi_);          \
-      n4 = *reinterpret_cast<const float4*>(Pv + mi_);                                                           \
-      if (col_ + 4 < p_cols) {                                                                                   \
-        n1 = *reinterpret_cast<const float4*>(Pp + mi_ + R4); n3 = *reinterpret_cast<const float4*>(Pm + mi_ + R4); \
-        n5 = *reinterpret_cast<const float4*>(Pv + mi_ + R4);                                                    \
+    if (live && (COL) < p_cols) {                                                                                \
+      n0 = ld_stream4(pp + (OFF)); n2 = ld_stream4(pm + (OFF));      \
+      n4 = ld_stream4(pv + (OFF));                                                         \
+      if ((COL) + 4 < p_cols) {                                                                                  \
+        n1 = ld_stream4(pp + (OFF) + R4); n3 = ld_stream4(pm + (OFF) + R4); \
+        n5 = ld_stream4(pv + (OFF) + R4);                                                  \
       }                                                                                                          \
     }                                                                                                            \
   } while (0)
-  if (c.cpart * 8 < n_mma) NMB_LOAD_STATE(c.cpart);
-  for (int ch = c.cpart; ch * 8 < n_mma; ch += c.parts) {        // 8 columns (one plane group) at a time
-    const int col = col0 + ch * 8;
+  int col = col0 + 8 * c.cpart;
+  const int cstep = 8 * c.parts, col_end = col0 + n_mma;
+  if (col < col_end) NMB_LOAD_STATE(col, 0);
+  for (; col < col_end; col += cstep) {        // 8 columns (one plane group) at a time
     const bool on = vo && col < p_cols;
     const bool full = col + 4 < p_cols;
-    const long long mi = mbase + (long long)(col >> 2) * R4;
     float g[8];
     float4 pa = n0, pb = n1, ma = n2, mb4 = n3, va = n4, vb = n5;
-    if ((ch + c.parts) * 8 < n_mma) NMB_LOAD_STATE(ch + c.parts);
+    if (col + cstep < col_end) {
+      NMB_LOAD_STATE(col + cstep, mstride);
+    }
     __syncwarp();
-    tc::tmem_ld8(taddr(c, tcol + ch * 8), g);
+    tc::tmem_ld8(ta, g);
     if (on) {
       if (wg) {
 #pragma unroll
@@ -826,22 +838,25 @@ __device__ __forceinline__ void epi_wgrad(EpiCtx& c, const Epi& e) {
         x[2] = adam_update(c, ma.z, va.z, pa.z, g[2]); x[3] = adam_update(c, ma.w, va.w, pa.w, g[3]);
         x[4] = adam_update(c, mb4.x, vb.x, pb.x, g[4]); x[5] = adam_update(c, mb4.y, vb.y, pb.y, g[5]);
         x[6] = adam_update(c, mb4.z, vb.z, pb.z, g[6]); x[7] = adam_update(c, mb4.w, vb.w, pb.w, g[7]);
-        *reinterpret_cast<float4*>(Pm + mi) = ma; *reinterpret_cast<float4*>(Pv + mi) = va;
-        *reinterpret_cast<float4*>(Pp + mi) = make_float4(x[0], x[1], x[2], x[3]);
+        st_stream4(pm, ma); st_stream4(pv, va);
+        st_stream4(pp, make_float4(x[0], x[1], x[2], x[3]));
         if (full) {
-          *reinterpret_cast<float4*>(Pm + mi + R4) = mb4; *reinterpret_cast<float4*>(Pv + mi + R4) = vb;
-          *reinterpret_cast<float4*>(Pp + mi + R4) = make_float4(x[4], x[5], x[6], x[7]);
+          st_stream4(pm + R4, mb4); st_stream4(pv + R4, vb);
+          st_stream4(pp + R4, make_float4(x[4], x[5], x[6], x[7]));
         }
+        if (col + 8 > p_cols) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] = (col + j < p_cols) ? x[j] : 0.f;
+          for (int j = 0; j < 8; ++j) x[j] = (col + j < p_cols) ? x[j] : 0.f;
+        }
         uint4 hh, ll;
         tc::split8(x, hh, ll);
-        unsigned char* p = wp + (long long)(col >> 3) * 32 * wp_R;
-        *reinterpret_cast<uint4*>(p) = hh;
-        *reinterpret_cast<uint4*>(p + 16 * wp_R) = ll;
+        *reinterpret_cast<uint4*>(wp) = hh;
+        *reinterpret_cast<uint4*>(wp + lo_off) = ll;
       }
     }
+    pp += mstride; pm += mstride; pv += mstride; wp += wstride; ta += tstride;
   }
+#undef NMB_LOAD_STATE
 }
 
 // transposed weight gradient of decoder_mean_layer: lane = input index i, columns = output rows o
