@@ -139,7 +139,7 @@ int setup_tcp(NmbEnsemble* e) {
   e->stash_bytes = (max_stash + 1023) & ~1023LL;
   CU(dev_alloc((size_t)e->stash_bytes * e->n_sm, &p));
   e->stash = (unsigned char*)p;
-  CU(dev_alloc((size_t)e->master_floats * 3 * sizeof(float) * e->n_sm, &p));
+  CU(dev_alloc((size_t)e->master_floats * 3 * sizeof(float) * e->n_members, &p));     // lane-major Adam state, per member
   e->master = (float*)p;
   // weight planes: one slice per member
   long long wtotal = 0;
@@ -286,7 +286,7 @@ int nmb_ensemble_create(NmbEnsemble** out, int32_t device, const NmbMember* memb
     md.params = mm.params; md.adam_m = mm.adam_m; md.adam_v = mm.adam_v; md.grads = mm.grads;
     md.lr_steps = mm.lr_steps; md.seed = mm.seed;
     md.lr = mm.lr; md.beta1 = mm.beta1; md.beta2 = mm.beta2; md.adam_eps = mm.adam_eps;
-    md.steps_done = 0; md.last_rows = 0; md.last_slot = -1;
+    md.steps_done = 0; md.last_rows = 0; md.last_slot = -1; md.launch_base = 0;
     e->members_host.push_back(md); e->arch_idx.push_back(ai);
   }
   cudaDeviceProp prop;

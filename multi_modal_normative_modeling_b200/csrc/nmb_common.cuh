@@ -58,6 +58,7 @@ struct MemberDev {
   long long steps_done;     // mutable: minibatch steps taken so far
   int last_rows;            // mutable: rows of the last executed minibatch
   int last_slot;            // mutable: scratch slot that ran the last step
+  long long launch_base;    // mutable: steps_done when the current pipelined launch started (work items wait on it)
 };
 
 // ---- layout (host) -------------------------------------------------------------------

@@ -36,11 +36,12 @@ __device__ __forceinline__ void store16(float* p, int nvalid, const float (&o)[1
 // Forward for one (row, z) element.  mu[m], lv[m] are the per-modality heads.
 struct Fused { float mu, lv; };
 
+// (.cg loads: alpha is updated every step, possibly by another SM between two work items of the member)
 __device__ inline void softmax_alpha(const float* alpha, int M, float* out) {
-  float mx = alpha[0];
-  for (int m = 1; m < M; ++m) mx = fmaxf(mx, alpha[m]);
+  float mx = __ldcg(alpha);
+  for (int m = 1; m < M; ++m) mx = fmaxf(mx, __ldcg(alpha + m));
   float s = 0.f;
-  for (int m = 0; m < M; ++m) { out[m] = expf(alpha[m] - mx); s += out[m]; }
+  for (int m = 0; m < M; ++m) { out[m] = expf(__ldcg(alpha + m) - mx); s += out[m]; }
   for (int m = 0; m < M; ++m) out[m] /= s;
 }
 

@@ -8,6 +8,7 @@
 //   loss_function_multimodal     cVAE.py:1187-1196
 //   optimizer1 = Adam(...)       cVAE.py:1111-1116 (torch defaults)
 // One persistent CTA per SM; a member's minibatch steps all run inside one launch.
+#include <cstdlib>
 #include <cstring>
 
 #include "nmb_tc_gemm.cuh"
@@ -33,6 +34,8 @@ struct Ctrl {
   uint32_t tmem;
   volatile uint32_t epi_done[kGroups];   // per epilogue group: items finished (1 + step * n_epis + index + 1)
   int member;
+  int chunk_i0, chunk_n;                 // launch-relative first step and step count of the current work item
+  long long chunk_s0;                    // member-global index of its first step
   float red[40];
 };
 
@@ -119,10 +122,13 @@ __device__ void producer_role(const TrainLaunch& t, const ProgramDev& pg, const 
   unsigned char* ring = smem + kSmemRing;
   const Step* __restrict__ steps = pg.steps;
   const int n_steps = pg.n_steps;
+  const long long s0 = ctl->chunk_s0;
+  const int i0 = ctl->chunk_i0, n_chunk = ctl->chunk_n;
+  fence_async_all();          // weight planes may have been written by another SM (previous work item of this member)
   PStep nxt = load_pstep(steps, 0);
-  for (long long i = 0; i < t.n_steps; ++i) {
-    const StepVars sv = step_vars(mb, mb.steps_done + i, i, pg.n_epis);
-    const bool tr = g_trace && blockIdx.x == 0 && i == g_trace_step;
+  for (long long i = 0; i < n_chunk; ++i) {
+    const StepVars sv = step_vars(mb, s0 + i, i, pg.n_epis);
+    const bool tr = g_trace && blockIdx.x == 0 && i0 + i == g_trace_step;
     const int tb = 3 * pg.n_epis + 3 * pg.n_steps;
     for (int k = 0; k < n_steps; ++k) {
       const PStep st = nxt;
@@ -163,6 +169,7 @@ struct LaunchP {
   float* master;            // per slot: 3 x master_floats (p, m, v)
   long long master_floats;
   int ms_off[kMaxParamArchs], ms_cnt[kMaxParamArchs];   // slice of msteps per architecture
+  int n_chunks;             // a member's steps of this launch are dealt as n_chunks work items (consecutive step ranges)
   int ep_off[kMaxParamArchs], ep_cnt[kMaxParamArchs];   // slice of epis_p per architecture; cnt 0 = global-memory table
   MStep msteps[kMaxParamSteps];
   EpiP epis_p[kMaxParamEpis];
@@ -179,16 +186,16 @@ __device__ __forceinline__ bool elect_one() {
 // uniform loads); one elected lane issues, so descriptors never leave the uniform datapath.
 __device__ void mma_role(const LaunchP& L, int ai, const MemberDev& mb, unsigned char* smem, Ctrl* ctl, uint32_t tmem,
                          uint32_t& seq, int n_epis) {
-  const TrainLaunch& t = L.t;
   const uint32_t ring = tc::smem_u32(smem + kSmemRing);
   const uint32_t act0 = tc::smem_u32(smem);
-  const long long s0 = mb.steps_done;
+  const long long s0 = ctl->chunk_s0;
+  const int i0 = ctl->chunk_i0, n_chunk = ctl->chunk_n;
   const int k0 = L.ms_off[ai], k1 = k0 + L.ms_cnt[ai];
-  for (long long i = 0; i < t.n_steps; ++i) {
+  for (long long i = 0; i < n_chunk; ++i) {
     const StepVars sv = step_vars(mb, s0 + i, i, n_epis);
     const bool half1 = __any_sync(0xffffffffu, sv.rows_h[1] > 0);
     wait_all(ctl->epi_done, sv.base);
-    const bool tr = g_trace && blockIdx.x == 0 && i == g_trace_step;
+    const bool tr = g_trace && blockIdx.x == 0 && i0 + i == g_trace_step;
     const int tb = 3 * n_epis;
     for (int k = k0; k < k1; ++k) {
       const MStep& st = L.msteps[k];
@@ -269,7 +276,8 @@ __device__ __forceinline__ void put_planes(unsigned char* blk, int g, int row, c
 
 // Adam master state is a pure stream (read once, written once per step, re-read a whole step later): keep it from
 // displacing the weight planes and the backward stash in L2.
-__device__ __forceinline__ float4 ld_stream4(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
+// (.cg: the previous work item of the member may have run on another SM -- never trust this SM's L1 for it)
+__device__ __forceinline__ float4 ld_stream4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void st_stream4(float* p, const float4& v) { __stcs(reinterpret_cast<float4*>(p), v); }
 
 // torch.optim.Adam element update; sqrt / reciprocal on the SFU (2 ulp, far inside the parity budget)
@@ -286,8 +294,8 @@ __device__ __forceinline__ void adam_scalar(const EpiCtx& c, long long idx, floa
   MemberDev& mb = *c.mb;
   if (c.flags & NMB_TRAIN_WRITE_GRADS) mb.grads[idx] = g;
   if (!(c.flags & NMB_TRAIN_NO_ADAM)) {
-    float m1 = mb.adam_m[idx], v1 = mb.adam_v[idx];
-    const float p1 = adam_update(c, m1, v1, mb.params[idx], g);
+    float m1 = __ldcg(mb.adam_m + idx), v1 = __ldcg(mb.adam_v + idx);
+    const float p1 = adam_update(c, m1, v1, __ldcg(mb.params + idx), g);
     mb.adam_m[idx] = m1; mb.adam_v[idx] = v1; mb.params[idx] = p1;
   }
 }
@@ -309,14 +317,13 @@ __device__ __forceinline__ float block_sum_epi(EpiCtx& c, float v) {
 }
 
 // fp32 parameters -> BF16 hi/lo planes (member start)
-__device__ void build_weight_planes(const EpiCtx& c) {
-  const ProgramDev& pg = *c.pg;
-  const float* __restrict__ P = c.mb->params;
+__device__ void build_weight_planes(const ProgramDev& pg, const MemberDev& mb, const MemberTc& mt, int tid, int nthr) {
+  const float* __restrict__ P = mb.params;
   for (int b = 0; b < pg.n_wblocks; ++b) {
     const WBlock wb = pg.wblocks[b];
     const int units = wb.R * wb.cg;
-    unsigned char* dst = c.mt->wplanes + wb.wp_off;
-    for (int u = c.tid; u < units; u += c.nthr) {
+    unsigned char* dst = mt.wplanes + wb.wp_off;
+    for (int u = tid; u < units; u += nthr) {
       const int r = u % wb.R, g = u / wb.R;
       float x[8];
 #pragma unroll
@@ -336,17 +343,35 @@ __device__ void build_weight_planes(const EpiCtx& c) {
   }
 }
 
-// Row-major parameters / Adam moments of the caller <-> lane-major master state of the slot.
-// gather = true at member start, false (scatter back) at member end.
-__device__ void move_master(const EpiCtx& c, bool gather) {
-  const ProgramDev& pg = *c.pg;
-  float* ext[3] = {c.mb->params, c.mb->adam_m, c.mb->adam_v};
-  float* mst[3] = {c.mst_p, c.mst_m, c.mst_v};
+// Row-major parameters / Adam moments of the caller <-> lane-major master state of the member.
+// gather = true before the persistent kernel, false (scatter back) after it.  Layers whose lanes are output rows
+// move whole float4 quads: the gather reads the caller's rows coalesced (quad index fastest), the scatter reads the
+// master state coalesced (lane fastest); the other side of each is a fire-and-forget 16-byte store.
+__device__ void move_master(const ProgramDev& pg, const MemberDev& mb, float* mst_p, long long master_floats,
+                            int tid, int nthr, bool gather) {
+  float* ext[3] = {mb.params, mb.adam_m, mb.adam_v};
+  float* mst[3] = {mst_p, mst_p + master_floats, mst_p + 2 * master_floats};
+  const bool aligned = ((reinterpret_cast<unsigned long long>(ext[0]) | reinterpret_cast<unsigned long long>(ext[1]) |
+                         reinterpret_cast<unsigned long long>(ext[2])) & 15ull) == 0ull;
   for (int b = 0; b < pg.n_mlayers; ++b) {
     const MLayer ml = pg.mlayers[b];
     const int lanes = ml.kind == 0 ? ml.rows : ml.cols, other = ml.kind == 0 ? ml.cols : ml.rows;
     const int quads = (other + 3) >> 2;
-    for (int u = c.tid; u < quads * ml.R; u += c.nthr) {
+    if (ml.kind == 0 && aligned && quads * 4 <= ml.p_ld) {
+      const int n = quads * lanes;
+      for (int u = tid; u < n; u += nthr) {
+        const int lane = gather ? u / quads : u % lanes, qd = gather ? u % quads : u / lanes;
+        const long long mi = ml.mst_off + ((long long)qd * ml.R + lane) * 4;
+        const long long ei = ml.p_off + (long long)lane * ml.p_ld + 4 * qd;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          if (gather) __stcs(reinterpret_cast<float4*>(mst[k] + mi), __ldcs(reinterpret_cast<const float4*>(ext[k] + ei)));
+          else __stcs(reinterpret_cast<float4*>(ext[k] + ei), __ldcs(reinterpret_cast<const float4*>(mst[k] + mi)));
+        }
+      }
+      continue;
+    }
+    for (int u = tid; u < quads * ml.R; u += nthr) {
       const int lane = u % ml.R, qd = u / ml.R;
       if (lane >= lanes) continue;
       const long long mi = ml.mst_off + ((long long)qd * ml.R + lane) * 4;
@@ -543,7 +568,7 @@ __device__ void build_iv_table(const EpiCtx& c) {
   for (int m = 0; m < a.M; ++m) {
     const ModDesc& q = a.mod[m];
     float* iv = reinterpret_cast<float*>(c.stash + c.pg->lay.ivtab[m]);
-    for (int n = c.tid; n < round4(q.D) + 8; n += c.nthr) iv[n] = n < q.D ? __expf(-c.mb->params[q.lam_off + n]) : 0.f;
+    for (int n = c.tid; n < round4(q.D) + 8; n += c.nthr) iv[n] = n < q.D ? __expf(-__ldcg(c.mb->params + q.lam_off + n)) : 0.f;
   }
 }
 
@@ -647,9 +672,9 @@ __device__ __forceinline__ void epi_lam(EpiCtx& c, const Epi& e) {
   for (int n = c.tid; n < q.D; n += c.nthr) {
     float s = 0.f;
     for (int k = 0; k < np; ++k) s += part[k * ld + n];
-    llc += -0.5f * c.mb->params[q.lam_off + n] - 0.5f * kLog2Pi;
+    llc += -0.5f * __ldcg(c.mb->params + q.lam_off + n) - 0.5f * kLog2Pi;
     adam_scalar(c, q.lam_off + n, 0.5f - 0.5f * s * inv_rows);       // mean over rows of 0.5 (1 - r^2 e^{-lam})
-    iv[n] = __expf(-c.mb->params[q.lam_off + n]);
+    iv[n] = __expf(-__ldcg(c.mb->params + q.lam_off + n));
   }
   c.ll_acc += llc;
 }
@@ -881,11 +906,11 @@ __device__ __forceinline__ void epi_wgrad_t(EpiCtx& c, const Epi& e) {
     float4 pa, pb, ma, mb4, va, vb;
     pa = pb = ma = mb4 = va = vb = make_float4(0.f, 0.f, 0.f, 0.f);
     if (on && adam) {
-      pa = *reinterpret_cast<const float4*>(Pp + mi); ma = *reinterpret_cast<const float4*>(Pm + mi);
-      va = *reinterpret_cast<const float4*>(Pv + mi);
+      pa = ld_stream4(Pp + mi); ma = ld_stream4(Pm + mi);
+      va = ld_stream4(Pv + mi);
       if (full) {
-        pb = *reinterpret_cast<const float4*>(Pp + mi + R4); mb4 = *reinterpret_cast<const float4*>(Pm + mi + R4);
-        vb = *reinterpret_cast<const float4*>(Pv + mi + R4);
+        pb = ld_stream4(Pp + mi + R4); mb4 = ld_stream4(Pm + mi + R4);
+        vb = ld_stream4(Pv + mi + R4);
       }
     }
     __syncwarp();
@@ -1098,10 +1123,7 @@ __device__ void epilogue_role(const LaunchP& L, int ai, int mi, EpiCtx& c, uint3
   for (int m = 0; m < NMB_MAX_MOD; ++m) dw_acc[m] = 0.f;
   c.dw_acc = dw_acc;
   set_workers(c, true);
-  build_weight_planes(c);
-  build_iv_table(c);
-  const bool adam_on = !(c.flags & NMB_TRAIN_NO_ADAM);
-  if (adam_on) move_master(c, true);
+  build_iv_table(c);          // weight planes and the lane-major master state were prepared by tcp_prepare_kernel
   __threadfence();
   fence_async_all();
   bar_n(4, kEpiWarps * 32);
@@ -1109,13 +1131,14 @@ __device__ void epilogue_role(const LaunchP& L, int ai, int mi, EpiCtx& c, uint3
 #pragma unroll
     for (int g = 0; g < kGroups; ++g) st_release(&c.ctl->epi_done[g], 1u);
   }
-  const long long s0 = mb.steps_done;
+  const long long s0 = c.ctl->chunk_s0;
+  const int i0 = c.ctl->chunk_i0, n_chunk = c.ctl->chunk_n;
   const int n_epis = pg.n_epis;
   const Epi* __restrict__ epis = pg.epis;
   const bool in_params = L.ep_cnt[ai] > 0;      // item table in the kernel parameters (constant bank)
   const int ep0 = L.ep_off[ai];
   const bool pub = (c.warp % kGroupWarps) == 0 && c.lane == 0;     // the thread that publishes its group's counter
-  for (long long i = 0; i < t.n_steps; ++i) {
+  for (long long i = 0; i < n_chunk; ++i) {
     const long long s = s0 + i;
     const StepVars sv = step_vars(mb, s, i, n_epis);
     c.rows = sv.rows; c.rows_h0 = sv.rows_h[0]; c.rows_h1 = sv.rows_h[1]; c.row0 = sv.row0; c.pos = sv.pos;
@@ -1126,8 +1149,8 @@ __device__ void epilogue_role(const LaunchP& L, int ai, int mi, EpiCtx& c, uint3
       c.step_size = (float)((double)lr / (1.0 - pow((double)mb.beta1, tt)));
       c.inv_bc2 = (float)(1.0 / sqrt(1.0 - pow((double)mb.beta2, tt)));
     }
-    const float* eps = t.eps_override ? t.eps_override + ((long long)mi * t.n_steps + i) * mb.batch * c.a->Z : nullptr;
-    float* lo = t.loss_out ? t.loss_out + ((long long)mi * t.n_steps + i) * 3 : nullptr;
+    const float* eps = t.eps_override ? t.eps_override + ((long long)mi * t.n_steps + i0 + i) * mb.batch * c.a->Z : nullptr;
+    float* lo = t.loss_out ? t.loss_out + ((long long)mi * t.n_steps + i0 + i) * 3 : nullptr;
     for (int k = 0; k < n_epis; ++k) {
       Epi e;
       if (in_params) e = from_epip(L.epis_p[ep0 + k]);
@@ -1148,7 +1171,7 @@ __device__ void epilogue_role(const LaunchP& L, int ai, int mi, EpiCtx& c, uint3
         // an idle activation group may be far ahead of the optimiser: mbarrier parity only disambiguates one phase
         if (c.grp != 2 && e.wait_optim) wait_epi(&c.ctl->epi_done[2], sv.base + (uint32_t)e.wait_optim);
       }
-      const bool tr = g_trace && blockIdx.x == 0 && i == g_trace_step && pub && (!all || c.grp == 0);
+      const bool tr = g_trace && blockIdx.x == 0 && i0 + i == g_trace_step && pub && (!all || c.grp == 0);
       const int tbase = c.grp == 0 ? 0 : 3 * n_epis * c.grp + 5 * pg.n_steps;   // groups 1, 2 stamp after the MMA / producer records
       if (tr) g_trace[tbase + 3 * k] = gtime();
       if (all) bar_n(4, kEpiWarps * 32);           // every group has finished everything before this item
@@ -1187,9 +1210,6 @@ __device__ void epilogue_role(const LaunchP& L, int ai, int mi, EpiCtx& c, uint3
       if (tr) g_trace[tbase + 3 * k + 2] = gtime();
     }
   }
-  set_workers(c, true);
-  bar_n(4, kEpiWarps * 32);
-  if (adam_on) move_master(c, false);
 }
 
 __global__ void __launch_bounds__(kThreadsP, 1) train_tcp_kernel(const __grid_constant__ LaunchP L) {
@@ -1208,13 +1228,36 @@ __global__ void __launch_bounds__(kThreadsP, 1) train_tcp_kernel(const __grid_co
   const uint32_t tmem = ctl->tmem;
   uint32_t seq = 0, acc_par = 0;
   unsigned char* stash = L.stash + (long long)blockIdx.x * L.stash_bytes;
-  const bool dynamic = (int)gridDim.x < t.n_members;
+  // Work items = (member, chunk of consecutive minibatch steps), dealt longest-member-first, all chunks 0 before
+  // all chunks 1 ...  A chunk waits (thread 0, acquire) until the member's previous chunk -- possibly on another
+  // SM -- has published its last step: finer items than whole members keep the tail of the launch short.
+  const int n_items = t.n_members * L.n_chunks;
+  const bool dynamic = (int)gridDim.x < n_items;
   bool first = true;
   for (;;) {
     if (threadIdx.x == 0) {
+      int it = n_items;
+      if (dynamic) it = atomicAdd(t.work_counter, 1);
+      else if (first) it = blockIdx.x;
       int mi = t.n_members;
-      if (dynamic) { mi = atomicAdd(t.work_counter, 1); if (mi < t.n_members) mi = t.order[mi]; else mi = t.n_members; }
-      else if (first) mi = blockIdx.x;
+      if (it < n_items) {
+        const int chunk = it / t.n_members;
+        mi = dynamic ? t.order[it - chunk * t.n_members] : it;
+        MemberDev& m = t.members[mi];
+        const long long i0 = t.n_steps * chunk / L.n_chunks, i1 = t.n_steps * (chunk + 1) / L.n_chunks;
+        const long long need = m.launch_base + i0;
+        if (chunk > 0) {
+          const long long t0 = clock64();
+          long long have;
+          for (;;) {
+            asm volatile("ld.acquire.gpu.global.s64 %0, [%1];" : "=l"(have) : "l"(&m.steps_done) : "memory");
+            if (have >= need) break;
+            __nanosleep(200);
+            if (clock64() - t0 > 8000000000LL) __trap();
+          }
+        }
+        ctl->chunk_i0 = (int)i0; ctl->chunk_n = (int)(i1 - i0); ctl->chunk_s0 = need;
+      }
       ctl->member = mi;
       for (int g = 0; g < kGroups; ++g) ctl->epi_done[g] = 0;
     }
@@ -1225,29 +1268,34 @@ __global__ void __launch_bounds__(kThreadsP, 1) train_tcp_kernel(const __grid_co
     MemberDev& mb = t.members[mi];
     const ProgramDev& pg = L.progs[mb.arch_idx];
     const MemberTc& mt = L.mtc[mi];
-    if (warp < kEpiWarps) {
-      EpiCtx c;
-      c.a = &t.archs[mb.arch_idx]; c.pg = &pg; c.mb = &mb; c.mt = &mt;
-      c.smem = smem; c.stash = stash; c.scratch = t.scratch + (long long)blockIdx.x * t.slot_floats; c.ctl = ctl;
-      c.mst_p = L.master + (long long)blockIdx.x * 3 * L.master_floats;
-      c.mst_m = c.mst_p + L.master_floats; c.mst_v = c.mst_m + L.master_floats;
-      c.tmem = tmem; c.warp = warp; c.lane = lane; c.row = ((warp & 3) << 5) + lane;
-      c.grp = warp / kGroupWarps; c.flags = t.flags;
-      c.b1 = mb.beta1; c.b2 = mb.beta2; c.aeps = mb.adam_eps;
-      epilogue_role(L, mb.arch_idx, mi, c, acc_par);
-    } else if (warp == kEpiWarps) {
-      const int ai = __shfl_sync(0xffffffffu, mb.arch_idx, 0);
-      mma_role(L, ai, mb, smem, ctl, tmem, seq, pg.n_epis);
-    } else {
-      if (lane == 0) producer_role(t, pg, mb, mt, stash, smem, ctl, seq);
+    if (ctl->chunk_n > 0) {
+      if (warp < kEpiWarps) {
+        EpiCtx c;
+        c.a = &t.archs[mb.arch_idx]; c.pg = &pg; c.mb = &mb; c.mt = &mt;
+        c.smem = smem; c.stash = stash; c.scratch = t.scratch + (long long)blockIdx.x * t.slot_floats; c.ctl = ctl;
+        c.mst_p = L.master + (long long)mi * 3 * L.master_floats;        // per member, persistent across work items
+        c.mst_m = c.mst_p + L.master_floats; c.mst_v = c.mst_m + L.master_floats;
+        c.tmem = tmem; c.warp = warp; c.lane = lane; c.row = ((warp & 3) << 5) + lane;
+        c.grp = warp / kGroupWarps; c.flags = t.flags;
+        c.b1 = mb.beta1; c.b2 = mb.beta2; c.aeps = mb.adam_eps;
+        epilogue_role(L, mb.arch_idx, mi, c, acc_par);
+      } else if (warp == kEpiWarps) {
+        const int ai = __shfl_sync(0xffffffffu, mb.arch_idx, 0);
+        mma_role(L, ai, mb, smem, ctl, tmem, seq, pg.n_epis);
+      } else {
+        if (lane == 0) producer_role(t, pg, mb, mt, stash, smem, ctl, seq);
+      }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
       const int spe = (mb.n_rows + mb.batch - 1) / mb.batch;
-      const long long last = mb.steps_done + t.n_steps - 1;
-      mb.last_rows = min(mb.batch, mb.n_rows - (int)(last % spe) * mb.batch);
-      mb.steps_done += t.n_steps;
-      mb.last_slot = blockIdx.x;
+      const long long done = ctl->chunk_s0 + ctl->chunk_n;
+      if (ctl->chunk_n > 0) {
+        mb.last_rows = min(mb.batch, mb.n_rows - (int)((done - 1) % spe) * mb.batch);
+        mb.last_slot = blockIdx.x;
+      }
+      __threadfence();       // everything this CTA wrote for the member is visible before the step count is
+      asm volatile("st.release.gpu.global.s64 [%0], %1;" ::"l"(&mb.steps_done), "l"(done) : "memory");
     }
     __syncthreads();
   }
@@ -1333,18 +1381,54 @@ cudaError_t launch_xprep(const void* items_dev, int n_items, int max_blocks, cud
   return cudaGetLastError();
 }
 
+namespace tcp {
+struct PrepArgs {
+  MemberDev* members; const ProgramDev* progs; const MemberTc* mtc; float* master; long long master_floats;
+  int n_members; int adam;
+};
+// Before the persistent kernel: BF16 planes of every member's weights, row-major (caller) -> lane-major master state.
+__global__ void __launch_bounds__(256) tcp_prepare_kernel(const PrepArgs a) {
+  for (int mi = blockIdx.x; mi < a.n_members; mi += gridDim.x) {
+    MemberDev& mb = a.members[mi];
+    const ProgramDev& pg = a.progs[mb.arch_idx];
+    build_weight_planes(pg, mb, a.mtc[mi], threadIdx.x, blockDim.x);
+    if (a.adam) move_master(pg, mb, a.master + (long long)mi * 3 * a.master_floats, a.master_floats, threadIdx.x, blockDim.x, true);
+    if (threadIdx.x == 0) mb.launch_base = mb.steps_done;
+  }
+}
+// After it: lane-major master state -> the caller's row-major parameters and Adam moments.
+__global__ void __launch_bounds__(256) tcp_finish_kernel(const PrepArgs a) {
+  for (int mi = blockIdx.x; mi < a.n_members; mi += gridDim.x) {
+    MemberDev& mb = a.members[mi];
+    move_master(a.progs[mb.arch_idx], mb, a.master + (long long)mi * 3 * a.master_floats, a.master_floats, threadIdx.x, blockDim.x, false);
+  }
+}
+}  // namespace tcp
+
 cudaError_t launch_train_tcp(const TrainLaunch& t, const tcp::ProgramDev* progs, const tcp::MemberTc* mtc,
                              unsigned char* stash, long long stash_bytes, float* master, long long master_floats,
                              const tcp::MStep* msteps, const int* ms_off, const int* ms_cnt, int n_archs,
                              const tcp::EpiP* epis_p, const int* ep_off, const int* ep_cnt,
                              int n_sm, cudaStream_t st) {
-  const int grid = t.n_members < n_sm ? t.n_members : n_sm;
-  if (grid <= 0 || t.n_steps <= 0) return cudaSuccess;
-  if (grid < t.n_members) {
+  if (t.n_members <= 0 || t.n_steps <= 0) return cudaSuccess;
+  // more members than SMs: deal chunks of >= 4 steps, so that the launch does not end on a few whole members
+  int n_chunks = 1;
+  if (t.n_members > n_sm) {
+    n_chunks = (int)(t.n_steps / 4 < 8 ? t.n_steps / 4 : 8);
+    if (n_chunks < 1) n_chunks = 1;
+    if (const char* u = getenv("NMB_TCP_CHUNKS")) { const int v = atoi(u); if (v >= 1 && v <= t.n_steps) n_chunks = v; }   // dev knob
+  }
+  const long long n_items = (long long)t.n_members * n_chunks;
+  const int grid = n_items < n_sm ? (int)n_items : n_sm;
+  if (grid < n_items) {
     cudaError_t e = cudaMemsetAsync(t.work_counter, 0, sizeof(int), st);
     if (e != cudaSuccess) return e;
   }
+  tcp::PrepArgs pa{t.members, progs, mtc, master, master_floats, t.n_members, (t.flags & NMB_TRAIN_NO_ADAM) ? 0 : 1};
+  const int pgrid = t.n_members < 8 * n_sm ? t.n_members : 8 * n_sm;
+  tcp::tcp_prepare_kernel<<<pgrid, 256, 0, st>>>(pa);
   tcp::LaunchP L;
+  L.n_chunks = n_chunks;
   L.t = t; L.progs = progs; L.mtc = mtc; L.stash = stash; L.stash_bytes = stash_bytes;
   L.master = master; L.master_floats = master_floats;
   for (int a = 0; a < n_archs; ++a) { L.ms_off[a] = ms_off[a]; L.ms_cnt[a] = ms_cnt[a]; L.ep_off[a] = ep_off[a]; L.ep_cnt[a] = ep_cnt[a]; }
@@ -1355,6 +1439,7 @@ cudaError_t launch_train_tcp(const TrainLaunch& t, const tcp::ProgramDev* progs,
   }
   std::memcpy(L.msteps, msteps, sizeof(tcp::MStep) * (size_t)(ms_off[n_archs - 1] + ms_cnt[n_archs - 1]));
   tcp::train_tcp_kernel<<<grid, tcp::kThreadsP, tcp::kSmemBytes, st>>>(L);
+  if (pa.adam) tcp::tcp_finish_kernel<<<pgrid, 256, 0, st>>>(pa);
   return cudaGetLastError();
 }
 
