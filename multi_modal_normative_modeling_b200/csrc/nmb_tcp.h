@@ -658,14 +658,20 @@ inline Program build_program(const ArchDesc& a) {
     }
   }
   // logvar_out (needs the partial sums of both halves) is updated inside EK_STEP_END, after the rendezvous
-  {   // the Adam items behind the last per-half item find both activation groups idle: they help (column split)
+  {   // Adam items every group helps with (column split): those behind the last per-half item of the step (both
+      // activation groups are idle by then) and the transposed weight gradients of decoder_mean_layer (the
+      // activation groups' next items wait on exactly those MMAs and Adam items).  A group joining a shared item
+      // first waits until the optimiser has finished its last optimiser-only item before it (wait_optim), so that
+      // its view of the accumulator barrier phases cannot alias.
     int last_half_item = -1;
     for (int k = 0; k < (int)P.epis.size(); ++k) if (P.epis[k].half != 2) last_half_item = k;
     int last_optim_only = 0;
-    for (int k = 0; k <= last_half_item; ++k)
-      if (P.epis[k].kind == EK_WGRAD || P.epis[k].kind == EK_WGRAD_T) last_optim_only = k + 1;
-    for (int k = last_half_item + 1; k < (int)P.epis.size(); ++k)
-      if (P.epis[k].kind == EK_WGRAD || P.epis[k].kind == EK_WGRAD_T) { P.epis[k].split_all = 1; P.epis[k].wait_optim = last_optim_only; }
+    for (int k = 0; k < (int)P.epis.size(); ++k) {
+      Epi& ep = P.epis[k];
+      if (ep.kind != EK_WGRAD && ep.kind != EK_WGRAD_T) continue;
+      if (k > last_half_item || ep.kind == EK_WGRAD_T) { ep.split_all = 1; ep.wait_optim = last_optim_only; }
+      else last_optim_only = k + 1;
+    }
   }
   // an accumulator consumed by a shared (split_all) Adam item is free only when ALL groups are done with it:
   // encoded as a negative optimiser dependency

@@ -884,37 +884,47 @@ __device__ __forceinline__ void epi_wgrad(EpiCtx& c, const Epi& e) {
 #undef NMB_LOAD_STATE
 }
 
-// transposed weight gradient of decoder_mean_layer: lane = input index i, columns = output rows o
+// transposed weight gradient of decoder_mean_layer: lane = input index i, columns = output rows o.
+// Same software pipeline as epi_wgrad: the state of chunk k + 1 is in flight while chunk k is updated.
 __device__ __forceinline__ void epi_wgrad_t(EpiCtx& c, const Epi& e) {
   MemberDev& mb = *c.mb;
   const int i = c.row;
   const bool vi = i < e.p_cols;
-  const int p_ld = e.p_ld, p_rows = e.p_rows, n_mma = e.n_mma, col0 = e.col0, tcol = e.tmem_col;
-  const int R4 = e.mst_R * 4;
+  const int p_ld = e.p_ld, p_rows = e.p_rows, n_mma = e.n_mma, col0 = e.col0;
+  const long long R4 = (long long)e.mst_R * 4;
   unsigned char* wp = c.mt->wplanes + e.wp_off + (long long)(i >> 3) * 2048 + (i & 7) * 2;
   const long long blk_bytes = (long long)e.src_cg * 2048;     // one 64-row planes block
-  float* __restrict__ Pp = c.mst_p; float* __restrict__ Pm = c.mst_m; float* __restrict__ Pv = c.mst_v;
   const bool adam = !(c.flags & NMB_TRAIN_NO_ADAM), wg = c.flags & NMB_TRAIN_WRITE_GRADS;
   const long long colbase = e.p_off + i;
-  const long long mbase = e.mst_off + (long long)i * 4;
-  for (int ch = c.cpart; ch * 8 < n_mma; ch += c.parts) {
-    const int o0 = col0 + ch * 8;
+  const long long m0 = e.mst_off + (long long)i * 4 + (long long)((col0 >> 2) + 2 * c.cpart) * R4;
+  float* __restrict__ pp = c.mst_p + m0; float* __restrict__ pm = c.mst_m + m0; float* __restrict__ pv = c.mst_v + m0;
+  const long long mstride = 2 * c.parts * R4;
+  uint32_t ta = taddr(c, e.tmem_col + 8 * c.cpart);
+  const uint32_t tstride = 8 * c.parts;
+  const bool live = vi && adam;
+  float4 n0, n1, n2, n3, n4, n5;
+  n0 = n1 = n2 = n3 = n4 = n5 = make_float4(0.f, 0.f, 0.f, 0.f);
+#define NMB_LOAD_STATE_T(O0, OFF)                                                                                \
+  do {                                                                                                           \
+    n0 = n1 = n2 = n3 = n4 = n5 = make_float4(0.f, 0.f, 0.f, 0.f);                                                \
+    if (live && (O0) < p_rows) {                                                                                 \
+      n0 = ld_stream4(pp + (OFF)); n2 = ld_stream4(pm + (OFF)); n4 = ld_stream4(pv + (OFF));                     \
+      if ((O0) + 4 < p_rows) {                                                                                   \
+        n1 = ld_stream4(pp + (OFF) + R4); n3 = ld_stream4(pm + (OFF) + R4); n5 = ld_stream4(pv + (OFF) + R4);    \
+      }                                                                                                          \
+    }                                                                                                            \
+  } while (0)
+  int o0 = col0 + 8 * c.cpart;
+  const int ostep = 8 * c.parts, o_end = col0 + n_mma;
+  if (o0 < o_end) NMB_LOAD_STATE_T(o0, 0);
+  for (; o0 < o_end; o0 += ostep) {
     const bool on = vi && o0 < p_rows;
     const bool full = o0 + 4 < p_rows;
-    const long long mi = mbase + (long long)(o0 >> 2) * R4;
     float g[8];
-    float4 pa, pb, ma, mb4, va, vb;
-    pa = pb = ma = mb4 = va = vb = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (on && adam) {
-      pa = ld_stream4(Pp + mi); ma = ld_stream4(Pm + mi);
-      va = ld_stream4(Pv + mi);
-      if (full) {
-        pb = ld_stream4(Pp + mi + R4); mb4 = ld_stream4(Pm + mi + R4);
-        vb = ld_stream4(Pv + mi + R4);
-      }
-    }
+    float4 pa = n0, pb = n1, ma = n2, mb4 = n3, va = n4, vb = n5;
+    if (o0 + ostep < o_end) NMB_LOAD_STATE_T(o0 + ostep, mstride);
     __syncwarp();
-    tc::tmem_ld8(taddr(c, tcol + ch * 8), g);
+    tc::tmem_ld8(ta, g);
     if (on) {
       if (wg) {
 #pragma unroll
@@ -926,26 +936,32 @@ __device__ __forceinline__ void epi_wgrad_t(EpiCtx& c, const Epi& e) {
         x[2] = adam_update(c, ma.z, va.z, pa.z, g[2]); x[3] = adam_update(c, ma.w, va.w, pa.w, g[3]);
         x[4] = adam_update(c, mb4.x, vb.x, pb.x, g[4]); x[5] = adam_update(c, mb4.y, vb.y, pb.y, g[5]);
         x[6] = adam_update(c, mb4.z, vb.z, pb.z, g[6]); x[7] = adam_update(c, mb4.w, vb.w, pb.w, g[7]);
-        *reinterpret_cast<float4*>(Pm + mi) = ma; *reinterpret_cast<float4*>(Pv + mi) = va;
-        *reinterpret_cast<float4*>(Pp + mi) = make_float4(x[0], x[1], x[2], x[3]);
+        st_stream4(pm, ma); st_stream4(pv, va);
+        st_stream4(pp, make_float4(x[0], x[1], x[2], x[3]));
         if (full) {
-          *reinterpret_cast<float4*>(Pm + mi + R4) = mb4; *reinterpret_cast<float4*>(Pv + mi + R4) = vb;
-          *reinterpret_cast<float4*>(Pp + mi + R4) = make_float4(x[4], x[5], x[6], x[7]);
+          st_stream4(pm + R4, mb4); st_stream4(pv + R4, vb);
+          st_stream4(pp + R4, make_float4(x[4], x[5], x[6], x[7]));
         }
+        // planes of W[o][i]: K-major 64-row blocks, this lane owns column i -> 2-byte elements, 8 rows per chunk
+        unsigned char* pb0 = wp + (long long)(o0 >> 6) * blk_bytes + (o0 & 63) * 16;     // chunks never straddle a block
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int o = o0 + j;
-          if (o < p_rows) {
-            const __nv_bfloat16 hb = __float2bfloat16_rn(x[j]);
-            const __nv_bfloat16 lb = __float2bfloat16_rn(x[j] - __bfloat162float(hb));
-            unsigned char* p = wp + (long long)(o >> 6) * blk_bytes + (o & 63) * 16;
-            *reinterpret_cast<__nv_bfloat16*>(p) = hb;
-            *reinterpret_cast<__nv_bfloat16*>(p + 1024) = lb;
+        for (int j = 0; j < 8; j += 2) {
+          uint32_t hi, lo;
+          tc::split2(x[j], x[j + 1], hi, lo);
+          if (o0 + j < p_rows) {
+            *reinterpret_cast<unsigned short*>(pb0 + j * 16) = (unsigned short)(hi & 0xFFFFu);
+            *reinterpret_cast<unsigned short*>(pb0 + j * 16 + 1024) = (unsigned short)(lo & 0xFFFFu);
+          }
+          if (o0 + j + 1 < p_rows) {
+            *reinterpret_cast<unsigned short*>(pb0 + (j + 1) * 16) = (unsigned short)(hi >> 16);
+            *reinterpret_cast<unsigned short*>(pb0 + (j + 1) * 16 + 1024) = (unsigned short)(lo >> 16);
           }
         }
       }
     }
+    pp += mstride; pm += mstride; pv += mstride; ta += tstride;
   }
+#undef NMB_LOAD_STATE_T
 }
 
 // ---- one modality, Z <= 16: head accumulator -> reparameterisation -> decoder input, all in registers --------

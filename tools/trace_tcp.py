@@ -9,7 +9,11 @@ seeds = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 dev = torch.device("cuda", 0)
 hw = workloads.build_host_workload()
 wl = workloads.to_device(hw, dev, n_seeds=seeds)
-tr = EnsembleTrainer(wl.specs, device=dev)
+specs = wl.specs
+if 'big' in sys.argv:      # trace an early-fusion (D=348) member
+    specs = [sp for sp, t in zip(wl.specs, wl.tags) if t[1].startswith('early')]
+    sys.argv.remove('big')
+tr = EnsembleTrainer(specs, device=dev)
 tr.train_steps(8)
 buf = torch.zeros(4096, dtype=torch.int64, device=dev)
 lib = _lib.load()
