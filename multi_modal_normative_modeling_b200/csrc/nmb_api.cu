@@ -85,6 +85,7 @@ struct NmbEnsemble {
   std::vector<int> ms_off, ms_cnt;
   std::vector<tcp::EpiP> epis_p;             // compact epilogue item tables (kernel parameters) where they fit
   std::vector<int> ep_off, ep_cnt;
+  int max_mlayers = 1;                       // layers with Adam master state, over all architectures
 };
 
 namespace {
@@ -124,6 +125,7 @@ int setup_tcp(NmbEnsemble* e) {
     void *ds, *de, *dw, *dm;
     CU(upload(P.mlayers.data(), sizeof(tcp::MLayer) * P.mlayers.size(), &dm));
     pd[i].mlayers = (const tcp::MLayer*)dm; pd[i].n_mlayers = (int)P.mlayers.size();
+    if ((int)P.mlayers.size() > e->max_mlayers) e->max_mlayers = (int)P.mlayers.size();
     if (P.lay.master_floats > e->master_floats) e->master_floats = P.lay.master_floats;
     CU(upload(P.steps.data(), sizeof(tcp::Step) * P.steps.size(), &ds));
     CU(upload(P.epis.data(), sizeof(tcp::Epi) * P.epis.size(), &de));
@@ -370,7 +372,7 @@ int nmb_ensemble_train(NmbEnsemble* e, int64_t n_steps, const float* eps_overrid
     CU(launch_xprep(e->xprep_dev, e->n_xprep, e->xprep_max_blocks, (cudaStream_t)stream));
     CU(launch_train_tcp(t, e->progs_dev, e->mtc_dev, e->stash, e->stash_bytes, e->master, e->master_floats,
                         e->msteps.data(), e->ms_off.data(), e->ms_cnt.data(), (int)e->ms_off.size(),
-                        e->epis_p.data(), e->ep_off.data(), e->ep_cnt.data(), e->n_sm,
+                        e->epis_p.data(), e->ep_off.data(), e->ep_cnt.data(), e->max_mlayers, e->n_sm,
                         (cudaStream_t)stream));
   } else {
     CU(launch_train(t, (cudaStream_t)stream));

@@ -72,6 +72,6 @@ cudaError_t launch_train_tcp(const TrainLaunch& t, const tcp::ProgramDev* progs,
                              unsigned char* stash, long long stash_bytes, float* master, long long master_floats,
                              const tcp::MStep* msteps, const int* ms_off, const int* ms_cnt, int n_archs,
                              const tcp::EpiP* epis_p, const int* ep_off, const int* ep_cnt,
-                             int n_sm, cudaStream_t st);
+                             int max_mlayers, int n_sm, cudaStream_t st);
 
 }  // namespace nmb

@@ -343,66 +343,6 @@ __device__ void build_weight_planes(const ProgramDev& pg, const MemberDev& mb, c
   }
 }
 
-// Row-major parameters / Adam moments of the caller <-> lane-major master state of the member.
-// gather = true before the persistent kernel, false (scatter back) after it.  Layers whose lanes are output rows
-// move whole float4 quads: the gather reads the caller's rows coalesced (quad index fastest), the scatter reads the
-// master state coalesced (lane fastest); the other side of each is a fire-and-forget 16-byte store.
-__device__ void move_master(const ProgramDev& pg, const MemberDev& mb, float* mst_p, long long master_floats,
-                            int tid, int nthr, bool gather) {
-  float* ext[3] = {mb.params, mb.adam_m, mb.adam_v};
-  float* mst[3] = {mst_p, mst_p + master_floats, mst_p + 2 * master_floats};
-  const bool aligned = ((reinterpret_cast<unsigned long long>(ext[0]) | reinterpret_cast<unsigned long long>(ext[1]) |
-                         reinterpret_cast<unsigned long long>(ext[2])) & 15ull) == 0ull;
-  for (int b = 0; b < pg.n_mlayers; ++b) {
-    const MLayer ml = pg.mlayers[b];
-    const int lanes = ml.kind == 0 ? ml.rows : ml.cols, other = ml.kind == 0 ? ml.cols : ml.rows;
-    const int quads = (other + 3) >> 2;
-    if (ml.kind == 0 && aligned && quads * 4 <= ml.p_ld) {
-      const int n = quads * lanes;
-      for (int u = tid; u < n; u += nthr) {
-        const int lane = gather ? u / quads : u % lanes, qd = gather ? u % quads : u / lanes;
-        const long long mi = ml.mst_off + ((long long)qd * ml.R + lane) * 4;
-        const long long ei = ml.p_off + (long long)lane * ml.p_ld + 4 * qd;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          if (gather) __stcs(reinterpret_cast<float4*>(mst[k] + mi), __ldcs(reinterpret_cast<const float4*>(ext[k] + ei)));
-          else __stcs(reinterpret_cast<float4*>(ext[k] + ei), __ldcs(reinterpret_cast<const float4*>(mst[k] + mi)));
-        }
-      }
-      continue;
-    }
-    for (int u = tid; u < quads * ml.R; u += nthr) {
-      const int lane = u % ml.R, qd = u / ml.R;
-      if (lane >= lanes) continue;
-      const long long mi = ml.mst_off + ((long long)qd * ml.R + lane) * 4;
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        float* vv = reinterpret_cast<float*>(&v);
-        if (gather) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int oth = 4 * qd + j;
-            if (oth < other) vv[j] = ml.kind == 0 ? ext[k][ml.p_off + (long long)lane * ml.p_ld + oth]
-                                                  : ext[k][ml.p_off + (long long)oth * ml.p_ld + lane];
-          }
-          *reinterpret_cast<float4*>(mst[k] + mi) = v;
-        } else {
-          v = *reinterpret_cast<const float4*>(mst[k] + mi);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int oth = 4 * qd + j;
-            if (oth < other) {
-              if (ml.kind == 0) ext[k][ml.p_off + (long long)lane * ml.p_ld + oth] = vv[j];
-              else ext[k][ml.p_off + (long long)oth * ml.p_ld + lane] = vv[j];
-            }
-          }
-        }
-      }
-    }
-  }
-}
-
 __device__ __forceinline__ void epi_hidden(EpiCtx& c, const Epi& e) {
   const int h = e.half;
   const int rows = c.rows_of(h);
@@ -1402,21 +1342,69 @@ struct PrepArgs {
   MemberDev* members; const ProgramDev* progs; const MemberTc* mtc; float* master; long long master_floats;
   int n_members; int adam;
 };
-// Before the persistent kernel: BF16 planes of every member's weights, row-major (caller) -> lane-major master state.
-__global__ void __launch_bounds__(256) tcp_prepare_kernel(const PrepArgs a) {
-  for (int mi = blockIdx.x; mi < a.n_members; mi += gridDim.x) {
-    MemberDev& mb = a.members[mi];
-    const ProgramDev& pg = a.progs[mb.arch_idx];
-    build_weight_planes(pg, mb, a.mtc[mi], threadIdx.x, blockDim.x);
-    if (a.adam) move_master(pg, mb, a.master + (long long)mi * 3 * a.master_floats, a.master_floats, threadIdx.x, blockDim.x, true);
-    if (threadIdx.x == 0) mb.launch_base = mb.steps_done;
+// Before the persistent kernel: BF16 planes of every member's weights (grid.y == 0) and the caller's row-major
+// parameters / Adam moments -> lane-major master state.  After it (gather == 0): master state -> caller's layout.
+// One CTA per (member, layer); 32-row x 128-column tiles go through shared memory so that BOTH sides are read and
+// written in contiguous 128-byte (row-major side) / 512-byte (lane-major side) warp accesses.
+//   kind 0 (lane = output row o):  master float4 (quad qd, lane o) = W[o][4 qd .. 4 qd + 3]
+//   kind 1 (lane = input index i): master float4 (quad qd, lane i) = W[4 qd .. 4 qd + 3][i]
+__global__ void __launch_bounds__(256) tcp_move_kernel(const PrepArgs a, const int gather) {
+  __shared__ float T[32][129];
+  const int mi = blockIdx.x, layer = blockIdx.y;
+  MemberDev& mb = a.members[mi];
+  const ProgramDev& pg = a.progs[mb.arch_idx];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (gather && layer == 0) {
+    build_weight_planes(pg, mb, a.mtc[mi], tid, blockDim.x);
+    if (tid == 0) mb.launch_base = mb.steps_done;
   }
-}
-// After it: lane-major master state -> the caller's row-major parameters and Adam moments.
-__global__ void __launch_bounds__(256) tcp_finish_kernel(const PrepArgs a) {
-  for (int mi = blockIdx.x; mi < a.n_members; mi += gridDim.x) {
-    MemberDev& mb = a.members[mi];
-    move_master(a.progs[mb.arch_idx], mb, a.master + (long long)mi * 3 * a.master_floats, a.master_floats, threadIdx.x, blockDim.x, false);
+  if (!a.adam || layer >= pg.n_mlayers) return;
+  const MLayer ml = pg.mlayers[layer];
+  float* ext[3] = {mb.params, mb.adam_m, mb.adam_v};
+  float* mst0 = a.master + (long long)mi * 3 * a.master_floats;
+  for (int r0 = 0; r0 < ml.rows; r0 += 32) {
+    const int nr = min(32, ml.rows - r0);
+    for (int c0 = 0; c0 < ml.cols; c0 += 128) {
+      const int nc = min(128, ml.cols - c0);
+      for (int k = 0; k < 3; ++k) {
+        float* E = ext[k] + ml.p_off + (long long)r0 * ml.p_ld + c0;
+        float* M = mst0 + k * a.master_floats + ml.mst_off;
+        if (gather) {
+          for (int r = warp; r < 32; r += 8)
+            for (int cc = lane; cc < 128; cc += 32) T[r][cc] = (r < nr && cc < nc) ? E[(long long)r * ml.p_ld + cc] : 0.f;
+        } else if (ml.kind == 0) {
+          // lane = row: quads of this column block, 512 contiguous bytes per warp
+          for (int q = warp; q * 4 < nc; q += 8) {
+            const float4 v = lane < nr ? *reinterpret_cast<const float4*>(M + ((long long)((c0 >> 2) + q) * ml.R + r0 + lane) * 4)
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+            T[lane][4 * q] = v.x; T[lane][4 * q + 1] = v.y; T[lane][4 * q + 2] = v.z; T[lane][4 * q + 3] = v.w;
+          }
+        } else {
+          // lane = column: the 8 row quads of this row block
+          for (int q = warp; q * 4 < nr; q += 8)
+            for (int cc = lane; cc < nc; cc += 32) {
+              const float4 v = *reinterpret_cast<const float4*>(M + ((long long)((r0 >> 2) + q) * ml.R + c0 + cc) * 4);
+              T[4 * q][cc] = v.x; T[4 * q + 1][cc] = v.y; T[4 * q + 2][cc] = v.z; T[4 * q + 3][cc] = v.w;
+            }
+        }
+        __syncthreads();
+        if (!gather) {
+          for (int r = warp; r < nr; r += 8)
+            for (int cc = lane; cc < nc; cc += 32) E[(long long)r * ml.p_ld + cc] = T[r][cc];
+        } else if (ml.kind == 0) {
+          for (int q = warp; q * 4 < nc; q += 8)
+            if (lane < nr)
+              *reinterpret_cast<float4*>(M + ((long long)((c0 >> 2) + q) * ml.R + r0 + lane) * 4) =
+                  make_float4(T[lane][4 * q], T[lane][4 * q + 1], T[lane][4 * q + 2], T[lane][4 * q + 3]);
+        } else {
+          for (int q = warp; q * 4 < nr; q += 8)
+            for (int cc = lane; cc < nc; cc += 32)
+              *reinterpret_cast<float4*>(M + ((long long)((r0 >> 2) + q) * ml.R + c0 + cc) * 4) =
+                  make_float4(T[4 * q][cc], T[4 * q + 1][cc], T[4 * q + 2][cc], T[4 * q + 3][cc]);
+        }
+        __syncthreads();
+      }
+    }
   }
 }
 }  // namespace tcp
@@ -1425,7 +1413,7 @@ cudaError_t launch_train_tcp(const TrainLaunch& t, const tcp::ProgramDev* progs,
                              unsigned char* stash, long long stash_bytes, float* master, long long master_floats,
                              const tcp::MStep* msteps, const int* ms_off, const int* ms_cnt, int n_archs,
                              const tcp::EpiP* epis_p, const int* ep_off, const int* ep_cnt,
-                             int n_sm, cudaStream_t st) {
+                             int max_mlayers, int n_sm, cudaStream_t st) {
   if (t.n_members <= 0 || t.n_steps <= 0) return cudaSuccess;
   // more members than SMs: deal chunks of >= 4 steps, so that the launch does not end on a few whole members
   int n_chunks = 1;
@@ -1441,8 +1429,8 @@ cudaError_t launch_train_tcp(const TrainLaunch& t, const tcp::ProgramDev* progs,
     if (e != cudaSuccess) return e;
   }
   tcp::PrepArgs pa{t.members, progs, mtc, master, master_floats, t.n_members, (t.flags & NMB_TRAIN_NO_ADAM) ? 0 : 1};
-  const int pgrid = t.n_members < 8 * n_sm ? t.n_members : 8 * n_sm;
-  tcp::tcp_prepare_kernel<<<pgrid, 256, 0, st>>>(pa);
+  const dim3 pgrid((unsigned)t.n_members, (unsigned)(pa.adam ? max_mlayers : 1));
+  tcp::tcp_move_kernel<<<pgrid, 256, 0, st>>>(pa, 1);
   tcp::LaunchP L;
   L.n_chunks = n_chunks;
   L.t = t; L.progs = progs; L.mtc = mtc; L.stash = stash; L.stash_bytes = stash_bytes;
@@ -1455,7 +1443,7 @@ cudaError_t launch_train_tcp(const TrainLaunch& t, const tcp::ProgramDev* progs,
   }
   std::memcpy(L.msteps, msteps, sizeof(tcp::MStep) * (size_t)(ms_off[n_archs - 1] + ms_cnt[n_archs - 1]));
   tcp::train_tcp_kernel<<<grid, tcp::kThreadsP, tcp::kSmemBytes, st>>>(L);
-  if (pa.adam) tcp::tcp_finish_kernel<<<pgrid, 256, 0, st>>>(pa);
+  if (pa.adam) tcp::tcp_move_kernel<<<pgrid, 256, 0, st>>>(pa, 0);
   return cudaGetLastError();
 }
 

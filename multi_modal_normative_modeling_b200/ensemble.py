@@ -220,8 +220,12 @@ class EnsembleTrainer:
             _lib.check(self.lib.nmb_ensemble_train(self.handle, int(n_steps), eps_ptr,
                                                    losses.data_ptr() if losses is not None else None,
                                                    int(flags), _stream_ptr(self.device)), "nmb_ensemble_train")
-        # the pipelined engine launches the dataset re-tiling kernel (xprep) before the fused train kernel
-        self.gpu_launches += 2 if self._engine_cached(int(flags)) == "tcgen05-pipelined" else 1
+        # the pipelined engine launches xprep (dataset re-tiling), tcp_prepare (weight planes + lane-major Adam
+        # state), the fused train kernel and, with Adam on, tcp_finish (state back to the caller's layout)
+        if self._engine_cached(int(flags)) == "tcgen05-pipelined":
+            self.gpu_launches += 3 if (int(flags) & _lib.TRAIN_NO_ADAM) else 4
+        else:
+            self.gpu_launches += 1
         return losses
 
     def _engine_cached(self, flags: int) -> str:
