@@ -317,10 +317,13 @@ __device__ __forceinline__ float block_sum_epi(EpiCtx& c, float v) {
 }
 
 // fp32 parameters -> BF16 hi/lo planes (member start)
-__device__ void build_weight_planes(const ProgramDev& pg, const MemberDev& mb, const MemberTc& mt, int tid, int nthr) {
+// fp32 parameters -> BF16 hi/lo planes of the layer whose augmented matrix starts at float offset p_off (< 0: all)
+__device__ void build_weight_planes(const ProgramDev& pg, const MemberDev& mb, const MemberTc& mt, int tid, int nthr,
+                                    long long p_off) {
   const float* __restrict__ P = mb.params;
   for (int b = 0; b < pg.n_wblocks; ++b) {
     const WBlock wb = pg.wblocks[b];
+    if (p_off >= 0 && wb.p_off != p_off) continue;
     const int units = wb.R * wb.cg;
     unsigned char* dst = mt.wplanes + wb.wp_off;
     for (int u = tid; u < units; u += nthr) {
@@ -1354,12 +1357,11 @@ __global__ void __launch_bounds__(256) tcp_move_kernel(const PrepArgs a, const i
   MemberDev& mb = a.members[mi];
   const ProgramDev& pg = a.progs[mb.arch_idx];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (gather && layer == 0) {
-    build_weight_planes(pg, mb, a.mtc[mi], tid, blockDim.x);
-    if (tid == 0) mb.launch_base = mb.steps_done;
-  }
-  if (!a.adam || layer >= pg.n_mlayers) return;
+  if (gather && layer == 0 && tid == 0) mb.launch_base = mb.steps_done;
+  if (layer >= pg.n_mlayers) return;
   const MLayer ml = pg.mlayers[layer];
+  if (gather) build_weight_planes(pg, mb, a.mtc[mi], tid, blockDim.x, ml.p_off);     // this layer's planes
+  if (!a.adam) return;
   float* ext[3] = {mb.params, mb.adam_m, mb.adam_v};
   float* mst0 = a.master + (long long)mi * 3 * a.master_floats;
   for (int r0 = 0; r0 < ml.rows; r0 += 32) {
@@ -1429,7 +1431,7 @@ cudaError_t launch_train_tcp(const TrainLaunch& t, const tcp::ProgramDev* progs,
     if (e != cudaSuccess) return e;
   }
   tcp::PrepArgs pa{t.members, progs, mtc, master, master_floats, t.n_members, (t.flags & NMB_TRAIN_NO_ADAM) ? 0 : 1};
-  const dim3 pgrid((unsigned)t.n_members, (unsigned)(pa.adam ? max_mlayers : 1));
+  const dim3 pgrid((unsigned)t.n_members, (unsigned)max_mlayers);
   tcp::tcp_move_kernel<<<pgrid, 256, 0, st>>>(pa, 1);
   tcp::LaunchP L;
   L.n_chunks = n_chunks;
