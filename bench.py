@@ -241,19 +241,51 @@ def run_b200(args):
     h2d = sum(x.numel() * 4 + c.numel() * 4 for x, c in wl.host_buffers.values())
     loss_host = torch.empty((tr.n, n_steps, 3), dtype=torch.float32).pin_memory()
 
-    def e2e_step():
-        for k in keys:
-            x, c = wl.host_buffers[k]
-            pack_rows(x.to(dev, non_blocking=True), c.to(dev, non_blocking=True), out=wl.packed[k])
-        losses = tr.train_steps(n_steps, record_losses=True)
-        loss_host.copy_(losses, non_blocking=True)
-    for _ in range(2):
-        e2e_step()
+    # Every step: pinned host -> device copy of every dataset, re-pack, train, losses back to pinned host memory.
+    # The copies of step i + 1 travel on a side stream (two staging sets) while step i trains; the losses of step i
+    # leave on a third stream.  All of it is inside the timed region.
+    main = torch.cuda.current_stream(dev)
+    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    stage = [{k: (torch.empty_like(x, device=dev), torch.empty_like(c, device=dev)) for k, (x, c) in wl.host_buffers.items()}
+             for _ in range(2)]
+    ev_in = [torch.cuda.Event() for _ in range(2)]        # staging set filled
+    ev_free = [torch.cuda.Event() for _ in range(2)]      # staging set consumed by pack_rows
+    ev_loss = torch.cuda.Event()
+
+    def upload(slot):
+        with torch.cuda.stream(s_in):
+            s_in.wait_event(ev_free[slot])
+            for k in keys:
+                x, c = wl.host_buffers[k]
+                stage[slot][k][0].copy_(x, non_blocking=True)
+                stage[slot][k][1].copy_(c, non_blocking=True)
+            ev_in[slot].record(s_in)
+
+    def e2e_run(n):
+        for e in ev_free:
+            e.record(main)
+        upload(0)
+        for i in range(n):
+            slot = i & 1
+            if i + 1 < n:
+                upload(slot ^ 1)
+            main.wait_event(ev_in[slot])
+            for k in keys:
+                pack_rows(stage[slot][k][0], stage[slot][k][1], out=wl.packed[k])
+            ev_free[slot].record(main)
+            s_out.wait_event(ev_loss)                     # previous losses have left before the buffer is rewritten
+            losses = tr.train_steps(n_steps, record_losses=True)
+            ev_loss.record(main)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_loss)
+                loss_host.copy_(losses, non_blocking=True)
+                losses.record_stream(s_out)
+        main.wait_stream(s_out)
+    e2e_run(2)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
-        e2e_step()
+    e2e_run(args.steps)
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1)

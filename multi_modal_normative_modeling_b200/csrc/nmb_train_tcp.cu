@@ -544,8 +544,8 @@ __device__ __forceinline__ void epi_recon(EpiCtx& c, const Epi& e) {
     const int gc_ = col0 + (CH) * 8;                                                                     \
     xa = xb = make_float4(0.f, 0.f, 0.f, 0.f);                                                           \
     if (vr && (CH) * 8 < n_valid) {                                                                      \
-      xa = *reinterpret_cast<const float4*>(xq + (long long)(gc_ >> 2) * 512);                           \
-      if (gc_ + 4 < D) xb = *reinterpret_cast<const float4*>(xq + (long long)((gc_ >> 2) + 1) * 512);    \
+      xa = __ldg(reinterpret_cast<const float4*>(xq + (long long)(gc_ >> 2) * 512));                     \
+      if (gc_ + 4 < D) xb = __ldg(reinterpret_cast<const float4*>(xq + (long long)((gc_ >> 2) + 1) * 512)); \
     }                                                                                                    \
     if (gauss) {                                                                                         \
       ia = *reinterpret_cast<const float4*>(ivt + gc_);                                                  \
@@ -962,8 +962,8 @@ __device__ void epi_head_latent(EpiCtx& c, const Epi& e, const float* eps_src) {
   unsigned char* st = c.stash + lay.g0[0][h] + c.row * 16;
   const int zg = (Z + 7) >> 3;                          // groups that contain z columns (<= 2)
   for (int g = 0; g < lay.c_cg; ++g) {
-    uint4 hi = *reinterpret_cast<const uint4*>(tp + (long long)g * 4096);
-    uint4 lo = *reinterpret_cast<const uint4*>(tp + (long long)g * 4096 + 2048);
+    uint4 hi = __ldg(reinterpret_cast<const uint4*>(tp + (long long)g * 4096));          // read-only dataset planes
+    uint4 lo = __ldg(reinterpret_cast<const uint4*>(tp + (long long)g * 4096 + 2048));
     if (g < zg) {
       const uint32_t hw[4] = {hi.x, hi.y, hi.z, hi.w}, lw[4] = {lo.x, lo.y, lo.z, lo.w};
       float x[8];

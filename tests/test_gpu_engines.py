@@ -49,3 +49,18 @@ def test_pipelined_kernel_is_deterministic(workload):
     l1, p1, _ = run(wl, 0, 8)
     l2, p2, _ = run(wl, 0, 8)
     assert np.array_equal(l1, l2) and np.array_equal(p1, p2)
+
+
+def test_chunked_work_items_equal_whole_members(workload, monkeypatch):
+    """More members than SMs: a member's steps of one launch are dealt as several work items that may run on
+    different SMs (acquire/release hand-off of its state).  The trajectory must not depend on the dealing."""
+    hw, wl = workload
+    monkeypatch.setenv("NMB_TCP_CHUNKS", "1")
+    l1, p1, name = run(wl, 0, 19)                  # 16 + 3 steps, whole members
+    assert name == "tcgen05-pipelined"
+    monkeypatch.setenv("NMB_TCP_CHUNKS", "4")
+    l4, p4, _ = run(wl, 0, 19)                     # the 16-step launch as 4 chunks of 4 steps
+    monkeypatch.delenv("NMB_TCP_CHUNKS")
+    ld, pd, _ = run(wl, 0, 19)                     # default dealing
+    assert np.array_equal(l1, l4) and np.array_equal(p1, p4)
+    assert np.array_equal(l1, ld) and np.array_equal(p1, pd)
