@@ -152,6 +152,8 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        self.armed = False          # NVML is initialised during the warm-up; samples count only inside the timed region
+        self.ready = threading.Event()
 
     def run(self):
         try:
@@ -163,15 +165,18 @@ class ClockSampler(threading.Thread):
                      "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
                      "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
                      "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+            self.ready.set()
             while not self.stop_flag:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
-                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                for k, bit in names.items():
-                    if r & bit:
-                        self.reasons.add(k)
-                time.sleep(0.02)
+                if self.armed:
+                    self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    for k, bit in names.items():
+                        if r & bit:
+                            self.reasons.add(k)
+                time.sleep(0.005)
         except Exception as e:          # NVML unavailable: report that instead of inventing numbers
             self.reasons.add("nvml_error:%s" % type(e).__name__)
+            self.ready.set()
 
     def summary(self):
         s = sorted(self.samples)
@@ -210,11 +215,13 @@ def run_b200(args):
         torch.cuda.synchronize(dev)
 
     # ---- device-resident throughput (`value`) ------------------------------------------------
-    for _ in range(max(args.warmup, 3)):
-        tr.train_steps(n_steps)
-    barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        tr.train_steps(n_steps)
+    sampler.ready.wait(5.0)
+    barrier()
+    sampler.armed = True
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     launches0 = tr.gpu_launches
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -364,6 +371,14 @@ def run_b200(args):
                              "kernel": "nmb::tcp::train_tcp_kernel" if engine == "tcgen05-pipelined" else "nmb::train_kernel",
                              "kernel_ms": kernel_ms, "algorithmic_flops_per_launch": flops_per_step,
                              "peak_source": peak_src,
+                             "kernel_ms_note": "CUDA events bracket the four launches of a training call (xprep, state "
+                                               "conversion in, persistent kernel, state conversion out); the persistent kernel is "
+                                               "0.91 of it (profiles/r01b_launch_list_summary.txt)",
+                             "hbm": None if not traffic else {
+                                 "achieved_GBps": traffic / (kernel_ms * 1e-3) / 1e9, "peak_GBps": peaks.get("hbm_gbs"),
+                                 "frac": (traffic / (kernel_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]) if peaks.get("hbm_gbs") else None,
+                                 "note": "measured DRAM bytes per launch (ncu, profiles/train_kernel_traffic.json) over the "
+                                         "live launch time: the kernel is latency-bound between its two roofs"},
                              "note": "achieved = algorithmic (FP32-equivalent) FLOPs; every product is executed as 3 BF16 "
                                      "tcgen05 passes (hi*hi, lo*hi, hi*lo, FP32 accumulate) to meet the 1e-4 parity bar, so "
                                      "the tensor pipe executes 3x these FLOPs: executed_frac = %.4f of the measured peak"

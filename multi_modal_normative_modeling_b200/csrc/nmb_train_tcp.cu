@@ -28,6 +28,13 @@ __device__ __forceinline__ unsigned long long gtime() {
   return t;
 }
 #define TRACE(cond, idx) do { if (cond) g_trace[idx] = gtime(); } while (0)
+// Fine-grained stamps inside the items (dev builds only: -DNMB_TCP_FINE_TRACE; SM clock cycles of one thread).
+#ifdef NMB_TCP_FINE_TRACE
+__device__ unsigned long long* g_fine = nullptr;      // cursor of the traced thread, nullptr = off
+#define TR3() do { if (g_fine) *g_fine++ = (unsigned long long)clock64(); } while (0)
+#else
+#define TR3() do { } while (0)
+#endif
 
 struct Ctrl {
   uint64_t full[kSlots], empty[kSlots], accbar[4];
@@ -564,6 +571,7 @@ __device__ __forceinline__ void epi_recon(EpiCtx& c, const Epi& e) {
     const float iv[8] = {ia.x, ia.y, ia.z, ia.w, ib.x, ib.y, ib.z, ib.w};
     if ((ch + c.parts) * 8 < n_cols) NMB_LOAD_X(ch + c.parts);
     uint32_t raw[8];
+    TR3();
     __syncwarp();
     tc::tmem_ld8_issue(taddr(c, tcol + col), raw);
     if (gauss && gc_prev >= 0) {     // column sums of the previous chunk overlap the accumulator load of this one
@@ -571,7 +579,9 @@ __device__ __forceinline__ void epi_recon(EpiCtx& c, const Epi& e) {
       const float s1 = warp_colsum8(qprev, c.lane, cj);
       if (!(c.lane & 3) && cj < nv_prev) lampart[gc_prev + cj] = s1;
     }
+    TR3();
     tc::tmem_ld_wait8(raw);
+    TR3();
     float gr[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -586,7 +596,9 @@ __device__ __forceinline__ void epi_recon(EpiCtx& c, const Epi& e) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) gr[j] = 0.f;
     }
+    TR3();
     put_planes(st, ch, c.row, gr);
+    TR3();
     if (keep && vr && nv > 0) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) if (j < nv) keep[gc + j] = __uint_as_float(raw[j]);
@@ -937,8 +949,10 @@ __device__ void epi_head_latent(EpiCtx& c, const Epi& e, const float* eps_src) {
   const bool vr = c.row < rows;
   const int gb = 128 * h + c.row;
   float mu[16], lv[16], zz[16];
+  TR3();
   tc::tmem_ld16(taddr(c, e.tmem_col), mu);            // columns 0 .. 15: mu[0 .. Z)
   tc::tmem_ld16(taddr(c, e.tmem_col + Z), lv);        // columns Z .. Z + 15: logvar[0 .. Z)
+  TR3();
   float* S = c.scratch;
   const uint32_t e0 = (uint32_t)gb * (uint32_t)Z;     // first element of this row in the [rows x Z] eps stream
   const float* __restrict__ epsrow = (eps_src ? eps_src : S + a.s_eps) + e0;
@@ -956,6 +970,7 @@ __device__ void epi_head_latent(EpiCtx& c, const Epi& e, const float* eps_src) {
     }
   }
   c.kl_acc += kl;
+  TR3();
   // [z | c | 1]: the covariate part comes from the dataset's template block (coalesced 16-byte reads)
   const unsigned char* tp = c.mt->cplanes[0] + (long long)(c.pos * c.mt->n_half + h) * lay.c_cg * 4096 + c.row * 16;
   unsigned char* act = c.smem + h * kActBytes + c.row * 16;
@@ -979,6 +994,7 @@ __device__ void epi_head_latent(EpiCtx& c, const Epi& e, const float* eps_src) {
     *reinterpret_cast<uint4*>(act + (long long)g * 4096 + 2048) = lo;
     *reinterpret_cast<uint4*>(st + (long long)g * 4096) = hi;
     *reinterpret_cast<uint4*>(st + (long long)g * 4096 + 2048) = lo;
+    TR3();
   }
   (void)C;
 }
@@ -1142,6 +1158,13 @@ __device__ void epilogue_role(const LaunchP& L, int ai, int mi, EpiCtx& c, uint3
         tc::fence_after();
       }
       if (tr) g_trace[tbase + 3 * k + 1] = gtime();
+#ifdef NMB_TCP_FINE_TRACE
+      g_fine = nullptr;
+      if (tr && c.grp == 0 && e.half == 0) {
+        if (e.kind == EK_HEAD_LATENT) g_fine = g_trace + 2048;
+        if (e.kind == EK_RECON && e.col0 == 0) g_fine = g_trace + 2048 + 64;
+      }
+#endif
       // proxy fences: ACT[h] (shared memory, read by the next MMAs) per item; global data read by the TMA
       // (stash blocks, weight planes) only at EK_FENCE / EK_STEP_END, so the stores drain in the background
       int fence = 0;              // 1 = shared memory, 2 = everything
