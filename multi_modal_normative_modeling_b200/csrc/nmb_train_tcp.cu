@@ -30,8 +30,7 @@ __device__ __forceinline__ unsigned long long gtime() {
 #define TRACE(cond, idx) do { if (cond) g_trace[idx] = gtime(); } while (0)
 // Fine-grained stamps inside the items (dev builds only: -DNMB_TCP_FINE_TRACE; SM clock cycles of one thread).
 #ifdef NMB_TCP_FINE_TRACE
-__device__ unsigned long long* g_fine = nullptr;      // cursor of the traced thread, nullptr = off
-#define TR3() do { if (g_fine) *g_fine++ = (unsigned long long)clock64(); } while (0)
+#define TR3() do { if (c.tr_ptr) *c.tr_ptr++ = (unsigned long long)clock64(); } while (0)   // per-thread cursor in EpiCtx
 #else
 #define TR3() do { } while (0)
 #endif
@@ -269,6 +268,9 @@ struct EpiCtx {
   float step_size, inv_bc2, b1, b2, aeps;
   float kl_acc, ll_acc;
   float* dw_acc;            // [NMB_MAX_MOD] gPoE alpha-gradient partials (local array of the role)
+#ifdef NMB_TCP_FINE_TRACE
+  unsigned long long* tr_ptr;
+#endif
   __device__ __forceinline__ int rows_of(int h) const { return h ? rows_h1 : rows_h0; }
 };
 
@@ -574,14 +576,13 @@ __device__ __forceinline__ void epi_recon(EpiCtx& c, const Epi& e) {
     TR3();
     __syncwarp();
     tc::tmem_ld8_issue(taddr(c, tcol + col), raw);
-    if (gauss && gc_prev >= 0) {     // column sums of the previous chunk overlap the accumulator load of this one
-      int cj;
-      const float s1 = warp_colsum8(qprev, c.lane, cj);
-      if (!(c.lane & 3) && cj < nv_prev) lampart[gc_prev + cj] = s1;
-    }
     TR3();
     tc::tmem_ld_wait8(raw);
     TR3();
+    // column sums of the previous chunk (zeros on the first pass): unconditional, so that the shuffles sit in the same
+    // basic block as this chunk's independent element arithmetic and their latencies overlap it
+    int cjp;
+    const float s1p = warp_colsum8(qprev, c.lane, cjp);
     float gr[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -592,6 +593,7 @@ __device__ __forceinline__ void epi_recon(EpiCtx& c, const Epi& e) {
       gr[j] = ri * gscale;
       qprev[j] = rri;
     }
+    if (gauss && gc_prev >= 0 && !(c.lane & 3) && cjp < nv_prev) lampart[gc_prev + cjp] = s1p;
     if (!vr) {          // ragged minibatch: keep the invariant "rows beyond the minibatch are zero" explicit
 #pragma unroll
       for (int j = 0; j < 8; ++j) gr[j] = 0.f;
@@ -927,6 +929,14 @@ __device__ __forceinline__ float bf16pair_hi(uint32_t w) { return __uint_as_floa
 // Pre-phase (before the accumulator barrier is waited on, so it overlaps the head GEMM): the Philox draws of this
 // half, spread over the whole group, written to the eps array the backward pass reads anyway.
 __device__ void epi_head_latent_pre(EpiCtx& c, const Epi& e, const float* eps_src) {
+  {   // this row's decoder-input template planes start their way to L1 while the head GEMM finishes (no registers held)
+    const Layout& lay = c.pg->lay;
+    const unsigned char* tp = c.mt->cplanes[0] + (long long)(c.pos * c.mt->n_half + e.half) * lay.c_cg * 4096 + c.row * 16;
+    for (int g = 0; g < lay.c_cg; ++g) {
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(tp + (long long)g * 4096));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(tp + (long long)g * 4096 + 2048));
+    }
+  }
   if (eps_src) return;
   const ArchDesc& a = *c.a;
   const int h = e.half, Z = a.Z, n = c.rows_of(h) * Z;
@@ -949,22 +959,25 @@ __device__ void epi_head_latent(EpiCtx& c, const Epi& e, const float* eps_src) {
   const bool vr = c.row < rows;
   const int gb = 128 * h + c.row;
   float mu[16], lv[16], zz[16];
+  float* S = c.scratch;
+  const uint32_t e0 = (uint32_t)gb * (uint32_t)Z;     // first element of this row in the [rows x Z] eps stream
+  const float* __restrict__ epsrow = (eps_src ? eps_src : S + a.s_eps) + e0;
+  // all draws of the row first (a store to the scratch array could alias a later load: the compiler keeps program
+  // order, which exposed one L2 round trip per latent element); zz[] holds eps until the arithmetic
+#pragma unroll
+  for (int z = 0; z < 16; ++z) zz[z] = (z < Z && vr) ? epsrow[z] : 0.f;
   TR3();
   tc::tmem_ld16(taddr(c, e.tmem_col), mu);            // columns 0 .. 15: mu[0 .. Z)
   tc::tmem_ld16(taddr(c, e.tmem_col + Z), lv);        // columns Z .. Z + 15: logvar[0 .. Z)
   TR3();
-  float* S = c.scratch;
-  const uint32_t e0 = (uint32_t)gb * (uint32_t)Z;     // first element of this row in the [rows x Z] eps stream
-  const float* __restrict__ epsrow = (eps_src ? eps_src : S + a.s_eps) + e0;
   float kl = 0.f;
+  const long long s_mub = a.s_mub, s_lvb = a.s_lvb, s_eps = a.s_eps;
 #pragma unroll
   for (int z = 0; z < 16; ++z) {
-    zz[z] = 0.f;
     if (z < Z && vr) {
-      const float eps = epsrow[z];
-      const float m_ = mu[z], l_ = lv[z];
-      S[a.s_mub + e0 + z] = m_; S[a.s_lvb + e0 + z] = l_;
-      if (eps_src) S[a.s_eps + e0 + z] = eps;
+      const float m_ = mu[z], l_ = lv[z], eps = zz[z];
+      S[s_mub + e0 + z] = m_; S[s_lvb + e0 + z] = l_;
+      if (eps_src) S[s_eps + e0 + z] = eps;
       zz[z] = m_ + eps * expf(0.5f * l_);
       kl += -0.5f * (1.f + l_ - m_ * m_ - expf(l_));
     }
@@ -1159,10 +1172,10 @@ __device__ void epilogue_role(const LaunchP& L, int ai, int mi, EpiCtx& c, uint3
       }
       if (tr) g_trace[tbase + 3 * k + 1] = gtime();
 #ifdef NMB_TCP_FINE_TRACE
-      g_fine = nullptr;
+      c.tr_ptr = nullptr;
       if (tr && c.grp == 0 && e.half == 0) {
-        if (e.kind == EK_HEAD_LATENT) g_fine = g_trace + 2048;
-        if (e.kind == EK_RECON && e.col0 == 0) g_fine = g_trace + 2048 + 64;
+        if (e.kind == EK_HEAD_LATENT) c.tr_ptr = g_trace + 2048;
+        if (e.kind == EK_RECON && e.col0 == 0) c.tr_ptr = g_trace + 2048 + 64;
       }
 #endif
       // proxy fences: ACT[h] (shared memory, read by the next MMAs) per item; global data read by the TMA

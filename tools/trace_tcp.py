@@ -22,7 +22,7 @@ tr.train_steps(8)
 torch.cuda.synchronize()
 _lib.check(lib.nmb_debug_tcp_trace(None, 0))
 b = buf.cpu().numpy().astype(np.int64)
-nz = b[b > 0]
+nz = b[:2048][b[:2048] > 0]        # wall-clock stamps; the fine (cycle) stamps live above 2048
 t0 = nz.min()
 E = 37 if len(sys.argv) <= 2 else int(sys.argv[2]); S = 62 if len(sys.argv) <= 3 else int(sys.argv[3])
 print("span us", (nz.max() - t0) / 1e3)
@@ -44,3 +44,16 @@ print("producer steps: deps issued")
 for k in range(S):
     a, e = b[3 * E + 3 * S + 2 * k:3 * E + 3 * S + 2 * k + 2]
     if a: print("P%02d %8.2f %8.2f" % (k, (a - t0) / 1e3, (e - t0) / 1e3))
+
+# fine stamps (libraries built with -DNMB_TCP_FINE_TRACE only): SM clock cycles of group 0's publishing thread
+def fine(name, off, n, per):
+    v = b[off:off + n]
+    v = v[v > 0]
+    if len(v) < 2:
+        return
+    d = np.diff(v)
+    print(name, "(deltas in SM cycles, %d per row)" % per)
+    for i in range(0, len(d), per):
+        print("   " + " ".join("%6d" % x for x in d[i:i + per]))
+fine("head->latent item, half 0: [tmem ld | z math + scratch stores | per plane group: template load, split, 4 stores ...]", 2048, 64, 12)
+fine("reconstruction item, half 0, per chunk: [ld issue | column sums of previous chunk | ld wait | math | planes | loop + prefetch]", 2048 + 64, 256, 5)
