@@ -45,14 +45,15 @@ struct Ctrl {
   float red[40];
 };
 
-__device__ __forceinline__ uint32_t ld_relaxed(const volatile uint32_t* p) {
+// Item counters: release store by the publishing thread, acquire load by the waiting role (CTA scope) -- no
+// separate MEMBAR on either side.
+__device__ __forceinline__ uint32_t ld_acquire(const volatile uint32_t* p) {
   uint32_t v;
-  asm volatile("ld.volatile.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(tc::smem_u32((const void*)p)) : "memory");
+  asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(tc::smem_u32((const void*)p)) : "memory");
   return v;
 }
 __device__ __forceinline__ void st_release(volatile uint32_t* p, uint32_t v) {
-  __threadfence_block();
-  asm volatile("st.volatile.shared::cta.u32 [%0], %1;" ::"r"(tc::smem_u32((const void*)p)), "r"(v) : "memory");
+  asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(tc::smem_u32((const void*)p)), "r"(v) : "memory");
 }
 // Bounded spin with back-off (a protocol bug must trap, not hang the GPU; the spinning single-thread
 // warps must not steal issue slots from the epilogue warps of their scheduler).
@@ -61,14 +62,13 @@ __device__ __forceinline__ void st_release(volatile uint32_t* p, uint32_t v) {
 #endif
 constexpr unsigned kPollSleepNs = NMB_POLL_NS;
 __device__ __forceinline__ void wait_epi(const volatile uint32_t* p, uint32_t need) {
-  if (ld_relaxed(p) < need) {
+  if (ld_acquire(p) < need) {
     const long long t0 = clock64();
-    while (ld_relaxed(p) < need) {
+    while (ld_acquire(p) < need) {
       __nanosleep(kPollSleepNs);
       if (clock64() - t0 > 4000000000LL) __trap();
     }
   }
-  __threadfence_block();
 }
 __device__ __forceinline__ void wait_all(const volatile uint32_t* p, uint32_t need) {
 #pragma unroll
