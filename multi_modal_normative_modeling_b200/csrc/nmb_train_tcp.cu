@@ -1400,6 +1400,10 @@ __global__ void __launch_bounds__(256) tcp_move_kernel(const PrepArgs a, const i
   if (!a.adam) return;
   float* ext[3] = {mb.params, mb.adam_m, mb.adam_v};
   float* mst0 = a.master + (long long)mi * 3 * a.master_floats;
+  // float4 access to the caller's rows: every row starts on a 16-byte boundary (row stride and matrix offsets are
+  // multiples of 4 floats) when the three base pointers do, and a 128-column block never reads past the row stride
+  const bool vec = ((reinterpret_cast<unsigned long long>(ext[0]) | reinterpret_cast<unsigned long long>(ext[1]) |
+                     reinterpret_cast<unsigned long long>(ext[2])) & 15ull) == 0ull && (ml.p_ld & 3) == 0 && (ml.p_off & 3) == 0;
   for (int r0 = 0; r0 < ml.rows; r0 += 32) {
     const int nr = min(32, ml.rows - r0);
     for (int c0 = 0; c0 < ml.cols; c0 += 128) {
@@ -1408,8 +1412,18 @@ __global__ void __launch_bounds__(256) tcp_move_kernel(const PrepArgs a, const i
         float* E = ext[k] + ml.p_off + (long long)r0 * ml.p_ld + c0;
         float* M = mst0 + k * a.master_floats + ml.mst_off;
         if (gather) {
-          for (int r = warp; r < 32; r += 8)
-            for (int cc = lane; cc < 128; cc += 32) T[r][cc] = (r < nr && cc < nc) ? E[(long long)r * ml.p_ld + cc] : 0.f;
+          if (vec) {            // one 512-byte warp access per row: 32 lanes x float4 (the row padding is readable)
+            for (int r = warp; r < 32; r += 8) {
+              float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (r < nr && 4 * lane < nc) v = __ldcs(reinterpret_cast<const float4*>(E + (long long)r * ml.p_ld + 4 * lane));
+              const int cc = 4 * lane;
+              T[r][cc] = cc < nc ? v.x : 0.f; T[r][cc + 1] = cc + 1 < nc ? v.y : 0.f;
+              T[r][cc + 2] = cc + 2 < nc ? v.z : 0.f; T[r][cc + 3] = cc + 3 < nc ? v.w : 0.f;
+            }
+          } else {
+            for (int r = warp; r < 32; r += 8)
+              for (int cc = lane; cc < 128; cc += 32) T[r][cc] = (r < nr && cc < nc) ? E[(long long)r * ml.p_ld + cc] : 0.f;
+          }
         } else if (ml.kind == 0) {
           // lane = row: quads of this column block, 512 contiguous bytes per warp
           for (int q = warp; q * 4 < nc; q += 8) {
@@ -1427,8 +1441,24 @@ __global__ void __launch_bounds__(256) tcp_move_kernel(const PrepArgs a, const i
         }
         __syncthreads();
         if (!gather) {
-          for (int r = warp; r < nr; r += 8)
-            for (int cc = lane; cc < nc; cc += 32) E[(long long)r * ml.p_ld + cc] = T[r][cc];
+          if (vec) {            // whole quads; a quad that straddles the last column keeps the caller's padding (zeros)
+            for (int r = warp; r < nr; r += 8) {
+              const int cc = 4 * lane;
+              if (cc < nc) {
+                float4 v = make_float4(T[r][cc], T[r][cc + 1], T[r][cc + 2], T[r][cc + 3]);
+                if (cc + 4 > nc) {
+                  const float4 old = *reinterpret_cast<const float4*>(E + (long long)r * ml.p_ld + cc);
+                  if (cc + 1 >= nc) v.y = old.y;
+                  if (cc + 2 >= nc) v.z = old.z;
+                  v.w = old.w;
+                }
+                __stcs(reinterpret_cast<float4*>(E + (long long)r * ml.p_ld + cc), v);
+              }
+            }
+          } else {
+            for (int r = warp; r < nr; r += 8)
+              for (int cc = lane; cc < nc; cc += 32) E[(long long)r * ml.p_ld + cc] = T[r][cc];
+          }
         } else if (ml.kind == 0) {
           for (int q = warp; q * 4 < nc; q += 8)
             if (lane < nr)
