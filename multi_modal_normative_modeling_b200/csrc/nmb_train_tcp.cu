@@ -1396,8 +1396,10 @@ __global__ void __launch_bounds__(256) tcp_move_kernel(const PrepArgs a, const i
   if (gather && layer == 0 && tid == 0) mb.launch_base = mb.steps_done;
   if (layer >= pg.n_mlayers) return;
   const MLayer ml = pg.mlayers[layer];
-  if (gather) build_weight_planes(pg, mb, a.mtc[mi], tid, blockDim.x, ml.p_off);     // this layer's planes
-  if (!a.adam) return;
+  if (!a.adam) {          // forward / backward only: just this layer's BF16 planes
+    if (gather) build_weight_planes(pg, mb, a.mtc[mi], tid, blockDim.x, ml.p_off);
+    return;
+  }
   float* ext[3] = {mb.params, mb.adam_m, mb.adam_v};
   float* mst0 = a.master + (long long)mi * 3 * a.master_floats;
   // float4 access to the caller's rows: every row starts on a 16-byte boundary (row stride and matrix offsets are
@@ -1440,6 +1442,27 @@ __global__ void __launch_bounds__(256) tcp_move_kernel(const PrepArgs a, const i
             }
         }
         __syncthreads();
+        if (gather && k == 0) {
+          // BF16 hi/lo planes of these 32 rows x 128 columns straight from the tile (parameters are read once):
+          // thread = (row, 8-column group); consecutive rows -> 512 contiguous bytes per warp store
+          for (int b = 0; b < pg.n_wblocks; ++b) {
+            const WBlock wb = pg.wblocks[b];
+            if (wb.p_off != ml.p_off || r0 < wb.row0 || r0 >= wb.row0 + wb.R) continue;
+            unsigned char* dst = a.mtc[mi].wplanes + wb.wp_off;
+            for (int u = tid; u < 32 * 16; u += 256) {
+              const int r = u & 31, gl = u >> 5, g = (c0 >> 3) + gl, rb = r0 - wb.row0 + r;
+              if (g >= wb.cg || rb >= wb.R) continue;
+              float x[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) x[j] = (r < nr && rb < wb.rows_valid) ? T[r][8 * gl + j] : 0.f;
+              uint4 h, l;
+              tc::split8(x, h, l);
+              unsigned char* p = dst + (long long)g * 32 * wb.R + rb * 16;
+              *reinterpret_cast<uint4*>(p) = h;
+              *reinterpret_cast<uint4*>(p + 16 * wb.R) = l;
+            }
+          }
+        }
         if (!gather) {
           if (vec) {            // whole quads; a quad that straddles the last column keeps the caller's padding (zeros)
             for (int r = warp; r < nr; r += 8) {
