@@ -357,3 +357,42 @@ def test_error_behaviour():
         EnsembleTrainer([MemberSpec([7], [3], 2, 2, [x])])                    # wrong packed width
     with pytest.raises(RuntimeError):
         pack_rows(torch.zeros(4, 5), torch.zeros(4, 2))                       # CPU tensors: no fallback
+
+
+def test_repeated_calls_hit_the_table_cache_and_changed_tables_do_not():
+    """The C ABI keeps the argument tables of a repeated call on the device (second use onwards).  Same tables ->
+    same results; different buffers / sizes in an otherwise identical call must never see a stale table."""
+    from oracle import deviation as odev
+    from multi_modal_normative_modeling_b200 import scoring, pack_rows
+    rng = np.random.RandomState(3)
+
+    def make(n, d):
+        x = rng.randn(n, d).astype(np.float32)
+        xc = pack_rows(torch.from_numpy(x).cuda(), torch.zeros(n, 2).cuda())
+        hat = torch.from_numpy((x + 0.2 * rng.randn(n, d)).astype(np.float32)).cuda()
+        return x, xc, hat
+
+    x1, xc1, hat1 = make(64, 20)
+    outs = []
+    for _ in range(4):                                     # miss, promote, hit, hit
+        roi, _, subj = scoring.deviation([xc1], [hat1])
+        outs.append((roi[0].clone(), subj[0].clone()))
+    torch.cuda.synchronize()
+    want = odev.recon_deviation_roi(x1.astype(np.float64), hat1.cpu().numpy())
+    for roi, subj in outs:
+        assert relerr(roi.cpu().numpy(), want) < 1e-5
+        assert torch.equal(roi, outs[0][0]) and torch.equal(subj, outs[0][1])
+    # same shapes, other buffers; then other shapes
+    for n, d in ((64, 20), (65, 20), (64, 24)):
+        x2, xc2, hat2 = make(n, d)
+        for _ in range(3):
+            roi, _, subj = scoring.deviation([xc2], [hat2])
+        torch.cuda.synchronize()
+        assert relerr(roi[0].cpu().numpy(), odev.recon_deviation_roi(x2.astype(np.float64), hat2.cpu().numpy())) < 1e-5
+    # more distinct tables than cache entries: eviction must keep results right
+    for i in range(40):
+        x3, xc3, hat3 = make(16 + i, 8)
+        for _ in range(2):
+            roi, _, subj = scoring.deviation([xc3], [hat3])
+        torch.cuda.synchronize()
+        assert relerr(roi[0].cpu().numpy(), odev.recon_deviation_roi(x3.astype(np.float64), hat3.cpu().numpy())) < 1e-5
