@@ -508,6 +508,15 @@ inline Program build_program(const ArchDesc& a) {
   // every stash-sourced tile of half h waits for it (all of them are consumed in the backward pass).
   int fence_id[2];
   for (int h = 0; h < 2; ++h) fence_id[h] = push_epi(new_epi(EK_FENCE, h, -1, 0));
+  // logvar_out: its gradient partials are complete once both halves have finished their reconstruction items.  The
+  // optimiser group, idle until the first weight gradient arrives, applies Adam to it here instead of inside the
+  // step-end rendezvous (n_valid / n_cols: the items of groups 0 / 1 it waits for).
+  if (a.loss_kind == NMB_LOSS_GAUSS_LL)
+    for (int m = 0; m < M; ++m) {
+      Epi e = new_epi(EK_LAM, 2, -1, m);
+      e.n_valid = fence_id[0]; e.n_cols = fence_id[1];
+      push_epi(e);
+    }
 
   // One linear layer: [dgrad(h) ->] wgrad parts(h) per half, then the Adam items.  The dgrad MMAs come first
   // so that they have consumed the pre-update weight planes before the wgrad accumulator is committed (the

@@ -1065,10 +1065,6 @@ __device__ __forceinline__ void prefetch_adam_state(const EpiCtx& c, const Epi& 
 __device__ void epi_step_end(EpiCtx& c, float* loss_out) {
   const ArchDesc& a = *c.a;
   const int M = a.M;
-  if (a.loss_kind == NMB_LOSS_GAUSS_LL) {        // logvar_out: partial sums of both halves are complete here
-    Epi lam{};
-    for (int m = 0; m < M; ++m) { lam.mod = m; epi_lam(c, lam); }
-  }
   const float kl = block_sum_epi(c, c.kl_acc) / c.rows;
   const float ll = block_sum_epi(c, c.ll_acc);
   if (loss_out && c.tid == 0) { loss_out[0] = M * kl - ll; loss_out[1] = M * kl; loss_out[2] = ll; }
@@ -1162,6 +1158,10 @@ __device__ void epilogue_role(const LaunchP& L, int ai, int mi, EpiCtx& c, uint3
       const bool tr = g_trace && blockIdx.x == 0 && i0 + i == g_trace_step && pub && (!all || c.grp == 0);
       const int tbase = c.grp == 0 ? 0 : 3 * n_epis * c.grp + 5 * pg.n_steps;   // groups 1, 2 stamp after the MMA / producer records
       if (tr) g_trace[tbase + 3 * k] = gtime();
+      if (e.kind == EK_LAM) {        // both halves' reconstruction items (and their stash fences) are behind these counters
+        wait_epi(&c.ctl->epi_done[0], sv.base + (uint32_t)e.n_valid);
+        if (c.rows_h1 > 0) wait_epi(&c.ctl->epi_done[1], sv.base + (uint32_t)e.n_cols);
+      }
       if (all) bar_n(4, kEpiWarps * 32);           // every group has finished everything before this item
       if (e.kind == EK_HEAD_LATENT) epi_head_latent_pre(c, e, eps);
       if (optim) prefetch_adam_state(c, e);
@@ -1193,6 +1193,7 @@ __device__ void epilogue_role(const LaunchP& L, int ai, int mi, EpiCtx& c, uint3
         case EK_WGRAD: epi_wgrad(c, e); break;
         case EK_WGRAD_T: epi_wgrad_t(c, e); break;
         case EK_FENCE: fence = 2; break;
+        case EK_LAM: epi_lam(c, e); break;
         case EK_HEAD_LATENT: epi_head_latent(c, e, eps); fence = 1; break;
         case EK_DZ_LATENT_BWD: epi_dz_latent_bwd(c, e); fence = 1; break;
         default: epi_step_end(c, lo); fence = 2; break;

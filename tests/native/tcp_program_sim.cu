@@ -71,6 +71,7 @@ int main(int argc, char** argv){
         return true;
       }
       if (e.split_all && g != 2 && e.wait_optim && epi_done[2] < e.wait_optim) return false;
+      if (e.kind == tcp::EK_LAM && (epi_done[0] < e.n_valid || epi_done[1] < e.n_cols)) return false;   // waits for both halves
       if (e.buf >= 0) {
         if (commits[e.buf] <= waited[g][e.buf]) return false;
         if (commits[e.buf] - waited[g][e.buf] > 1) { printf("PHASE ALIAS (seed %u): group %d item %d\n", seed, g, ep[g]); exit(4); }
