@@ -485,6 +485,7 @@ inline Program build_program(const ArchDesc& a) {
         Epi e = new_epi(EK_RECON, h, accbuf(h), m);
         e.n_mma = w_out[m][0].R; e.n_valid = q.D; e.n_cols = round16(q.D); e.col0 = 0;
         e.to_act = 1; e.last = 1;
+        e.src_cg = (M == 1) ? 1 : 0;       // one modality: last forward item of the half, it publishes the stash early
         const int id = push_epi(e);
         act_ready[h] = id; acc_free[accbuf(h)] = id;
       }
@@ -507,7 +508,11 @@ inline Program build_program(const ArchDesc& a) {
   // Generic-proxy stores to the stash become visible to the TMA (async proxy) at the per-half EK_FENCE item:
   // every stash-sourced tile of half h waits for it (all of them are consumed in the backward pass).
   int fence_id[2];
-  for (int h = 0; h < 2; ++h) fence_id[h] = push_epi(new_epi(EK_FENCE, h, -1, 0));
+  for (int h = 0; h < 2; ++h) {
+    Epi e = new_epi(EK_FENCE, h, -1, 0);
+    e.src_cg = (M == 1 && lay.n_dxh_blk[0] == 0) ? 1 : 0;      // already published by the reconstruction item
+    fence_id[h] = push_epi(e);
+  }
   // logvar_out: its gradient partials are complete once both halves have finished their reconstruction items.  The
   // optimiser group, idle until the first weight gradient arrives, applies Adam to it here instead of inside the
   // step-end rendezvous (n_valid / n_cols: the items of groups 0 / 1 it waits for).

@@ -1065,8 +1065,17 @@ __device__ __forceinline__ void prefetch_adam_state(const EpiCtx& c, const Epi& 
 __device__ void epi_step_end(EpiCtx& c, float* loss_out) {
   const ArchDesc& a = *c.a;
   const int M = a.M;
-  const float kl = block_sum_epi(c, c.kl_acc) / c.rows;
-  const float ll = block_sum_epi(c, c.ll_acc);
+  // both loss sums in one pass over the barrier pair (red[] holds 12 + 12 partials)
+  float kl, ll;
+  {
+    const float a0 = warp_sum(c.kl_acc), a1 = warp_sum(c.ll_acc);      // (the item started with a rendezvous: red[] is free)
+    if (c.lane == 0) { c.ctl->red[c.warp] = a0; c.ctl->red[kEpiWarps + c.warp] = a1; }
+    bar_n(4, kEpiWarps * 32);
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < kEpiWarps; ++i) { s0 += c.ctl->red[i]; s1 += c.ctl->red[kEpiWarps + i]; }
+    kl = s0 / c.rows; ll = s1;
+  }
   if (loss_out && c.tid == 0) { loss_out[0] = M * kl - ll; loss_out[1] = M * kl; loss_out[2] = ll; }
   if (M > 1 && a.combine == NMB_COMBINE_GPOE) {
     float w[NMB_MAX_MOD], dw_tot[NMB_MAX_MOD];
@@ -1164,6 +1173,9 @@ __device__ void epilogue_role(const LaunchP& L, int ai, int mi, EpiCtx& c, uint3
       }
       if (all) bar_n(4, kEpiWarps * 32);           // every group has finished everything before this item
       if (e.kind == EK_HEAD_LATENT) epi_head_latent_pre(c, e, eps);
+      // every stash block of this half's forward pass has been written by now and this item writes none: the
+      // generic -> async proxy publication (MEMBAR.GPU + proxy fence) runs while the group waits for its accumulator
+      if (e.kind == EK_RECON && e.src_cg) { __threadfence(); fence_async_all(); }
       if (optim) prefetch_adam_state(c, e);
       if (e.buf >= 0) {
         tc::mbar_wait(&c.ctl->accbar[e.buf], (acc_par >> e.buf) & 1u);
@@ -1192,7 +1204,7 @@ __device__ void epilogue_role(const LaunchP& L, int ai, int mi, EpiCtx& c, uint3
         case EK_LATENT_BWD: epi_latent_bwd(c, e); fence = 1; break;
         case EK_WGRAD: epi_wgrad(c, e); break;
         case EK_WGRAD_T: epi_wgrad_t(c, e); break;
-        case EK_FENCE: fence = 2; break;
+        case EK_FENCE: fence = e.src_cg ? 0 : 2; break;      // src_cg: already published before the last forward item
         case EK_LAM: epi_lam(c, e); break;
         case EK_HEAD_LATENT: epi_head_latent(c, e, eps); fence = 1; break;
         case EK_DZ_LATENT_BWD: epi_dz_latent_bwd(c, e); fence = 1; break;
