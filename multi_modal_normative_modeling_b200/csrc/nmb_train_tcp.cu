@@ -1176,6 +1176,14 @@ __device__ void epilogue_role(const LaunchP& L, int ai, int mi, EpiCtx& c, uint3
       // every stash block of this half's forward pass has been written by now and this item writes none: the
       // generic -> async proxy publication (MEMBAR.GPU + proxy fence) runs while the group waits for its accumulator
       if (e.kind == EK_RECON && e.src_cg) { __threadfence(); fence_async_all(); }
+      if (e.kind == EK_RECON) {      // first chunk's targets and exp(-logvar_out) entries towards L1 during the wait
+        const Layout& lay = pg.lay;
+        const float* xq = c.mt->xlm[e.mod] + ((long long)(c.pos * c.mt->n_half + e.half) * lay.x_quads[e.mod] * 128 + c.row) * 4
+                          + (long long)(e.col0 >> 2) * 512;
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(xq));
+        if (e.col0 + 4 < c.a->mod[e.mod].D) asm volatile("prefetch.global.L1 [%0];" ::"l"(xq + 512));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(c.stash + lay.ivtab[e.mod] + (long long)e.col0 * 4));
+      }
       if (optim) prefetch_adam_state(c, e);
       if (e.buf >= 0) {
         tc::mbar_wait(&c.ctl->accbar[e.buf], (acc_par >> e.buf) & 1u);

@@ -5,5 +5,5 @@ python bench.py --steps 10 --warmup 3 > gpurun_out/bench_r01b.json 2> gpurun_out
 python tools/time_scoring.py > gpurun_out/scoring_r01b.txt 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:tcp_|xprep|recon|auc_kernel|deviation_kernel|stats_kernel|pack_rows" --csv --log-file gpurun_out/r01b_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench_b.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:train_tcp -s 3 -c 1 -o gpurun_out/r01b_tcp -f python tools/run_tcp.py 24 20 5 > gpurun_out/ncu_tcp_b.log 2>&1
-python tools/trace_tcp.py 1 32 62 > gpurun_out/trace_r01b_d116.txt 2>&1
-python tools/trace_tcp.py 1 45 98 big > gpurun_out/trace_r01b_d348.txt 2>&1
+python tools/trace_tcp.py 1 33 62 > gpurun_out/trace_r01b_d116.txt 2>&1
+python tools/trace_tcp.py 1 46 98 big > gpurun_out/trace_r01b_d348.txt 2>&1
