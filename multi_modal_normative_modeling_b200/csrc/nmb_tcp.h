@@ -78,6 +78,8 @@ struct alignas(16) Step {
   unsigned char commit_buf;         // accumulator barrier 0..3
   unsigned char commit2, commit2_buf;   // optional second commit of the same step (same encoding)
   unsigned char dep_grp;            // epilogue group whose counter `dep` refers to (0 / 1; 2 = both)
+  unsigned char a_hold;             // the A tile's ring slot is kept for the next step ...
+  unsigned char b_held;             // ... which reads it as its B operand (no tile of its own) and releases it
 };
 
 // Compact copy of the MMA-relevant fields of a Step.  The table travels in the KERNEL PARAMETERS (constant
@@ -102,7 +104,8 @@ inline MStep to_mstep(const Step& s) {
   m.b_kadv = (unsigned short)(s.b_kadv >> 4); m.b_lo = (unsigned short)(s.b_lo >> 4);
   m.ksteps = s.ksteps; m.n = s.n; m.tmem_col = s.tmem_col;
   m.mma_dep = (short)s.mma_dep; m.mma_dep_joint = (short)s.mma_dep_joint;
-  m.half = s.half; m.a_tile = s.a_bytes ? 1 : 0; m.a_mn = s.a_mn; m.b_mn = s.b_mn;
+  m.half = s.half; m.a_tile = (unsigned char)((s.a_bytes ? 1 : 0) | (s.a_hold ? 2 : 0)); m.a_mn = s.a_mn;
+  m.b_mn = (unsigned char)(s.b_mn | (s.b_held ? 2 : 0));      // a_tile bit 1: keep the A slot; b_mn bit 1: B = kept slot
   m.first = s.first; m.commit = s.commit; m.commit_buf = s.commit_buf; m.commit2 = s.commit2;
   return m;
 }
@@ -581,41 +584,44 @@ inline Program build_program(const ArchDesc& a) {
           act_ready[h] = push_epi(e);
         }
       }
-      // dgrad MMAs first (pre-update weights), K-chunks over the d/dx_recon blocks; acc[h] is committed by the
-      // last transposed-wgrad part of the half, and the EK_DGRAD epilogues (which overwrite ACT[h]) come last
-      for (int h = 0; h < 2; ++h) {
-        const int buf = accbuf(h);
-        for (int t = 0; t < lay.n_dxh_blk[m]; ++t) {
-          const WRef& w = w_out[m][t];
-          Step s = base_step(h);
-          set_b(s, SP_W, w.wp_off, 64, 0, w.cg, true);
-          set_a_kmajor(s, 0);
-          s.a_space = SP_STASH; s.a_off = lay.dxh_blk[m] + ((long long)h * lay.n_dxh_blk[m] + t) * 32768; s.a_bytes = 32768;
-          s.ksteps = 4; s.n = (unsigned short)(w.cg * 8); s.tmem_col = (unsigned short)(kAcc0 + 128 * buf);
-          s.first = t == 0;
-          if (t == 0) need(s, acc_free[buf]);
-          s.commit_buf = (unsigned char)buf;
-          P.steps.push_back(s);
-        }
-      }
-      // transposed wgrad, two 64-column blocks of D per item
+      // Per 64-column block t of d/dx_recon (one 32 KB stash tile) and half h: the data-gradient MMAs (tile = K-major
+      // A, weights of block t = MN-major B, accumulated over t in acc[h]) and the transposed weight-gradient MMAs
+      // (ACT[h]^T x the SAME tile as MN-major B) run back to back on one load of the tile: the first step keeps the
+      // tile's ring slot (a_hold), the second reads it (b_held) and releases it.  Blocks go in pairs (one weight-gradient
+      // accumulator = 128 output rows); every data-gradient MMA of a pair is issued before the pair's Adam item can
+      // start, so the weight planes it rewrites have been consumed.  acc[h] is committed by the last transposed part of
+      // the half: the EK_DGRAD epilogues, which overwrite ACT[h], come last.
       for (int t0 = 0; t0 < lay.n_dxh_blk[m]; t0 += 2) {
         const int wb = wacc_next; wacc_next ^= 1;
         const int nt = lay.n_dxh_blk[m] - t0 < 2 ? lay.n_dxh_blk[m] - t0 : 2;
         const bool last_item = t0 + 2 >= lay.n_dxh_blk[m];
         for (int h = 0; h < 2; ++h) {
+          const int buf = accbuf(h);
           for (int t = t0; t < t0 + nt; ++t) {
+            const WRef& w = w_out[m][t];
+            const long long tile = lay.dxh_blk[m] + ((long long)h * lay.n_dxh_blk[m] + t) * 32768;
             Step s = base_step(h);
-            set_b(s, SP_STASH, lay.dxh_blk[m] + ((long long)h * lay.n_dxh_blk[m] + t) * 32768, 128, 0, 8, true);
-            set_a_mnmajor(s);
-            s.ksteps = 8; s.n = 64; s.tmem_col = (unsigned short)(kWacc0 + 128 * wb + 64 * (t - t0));
-            s.first = h == 0;
-            if (t == t0) { need(s, act_ready[h]); need(s, acc_free[2 + wb]); }
-            const bool last = t == t0 + nt - 1;
-            s.commit = !last ? 0 : (h == 1 ? 1 : 2);
-            s.commit_buf = (unsigned char)(2 + wb);
-            if (last && last_item) { s.commit2 = 1; s.commit2_buf = (unsigned char)accbuf(h); }
+            set_b(s, SP_W, w.wp_off, 64, 0, w.cg, true);
+            set_a_kmajor(s, 0);
+            s.a_space = SP_STASH; s.a_off = tile; s.a_bytes = 32768; s.a_hold = 1;
+            s.ksteps = 4; s.n = (unsigned short)(w.cg * 8); s.tmem_col = (unsigned short)(kAcc0 + 128 * buf);
+            s.first = t == 0;
+            if (t == 0) need(s, acc_free[buf]);
+            s.commit_buf = (unsigned char)buf;
             P.steps.push_back(s);
+
+            Step g = base_step(h);
+            set_b(g, SP_NONE, 0, 128, 0, 8, true);
+            g.b_bytes = 0; g.b_held = 1;
+            set_a_mnmajor(g);
+            g.ksteps = 8; g.n = 64; g.tmem_col = (unsigned short)(kWacc0 + 128 * wb + 64 * (t - t0));
+            g.first = h == 0;
+            if (t == t0) { need(g, act_ready[h]); need(g, acc_free[2 + wb]); }
+            const bool last = t == t0 + nt - 1;
+            g.commit = !last ? 0 : (h == 1 ? 1 : 2);
+            g.commit_buf = (unsigned char)(2 + wb);
+            if (last && last_item) { g.commit2 = 1; g.commit2_buf = (unsigned char)accbuf(h); }
+            P.steps.push_back(g);
           }
         }
         Epi e = new_epi(EK_WGRAD_T, 2, 2 + wb, m);

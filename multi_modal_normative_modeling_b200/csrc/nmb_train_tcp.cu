@@ -149,7 +149,7 @@ __device__ void producer_role(const TrainLaunch& t, const ProgramDev& pg, const 
       for (int which = 0; which < 2; ++which) {
         const int space = which == 0 ? st.a_space : st.b_space;
         const uint32_t bytes = which == 0 ? st.a_bytes : st.b_bytes;
-        if (which == 0 && bytes == 0) continue;
+        if (bytes == 0) continue;          // A resident in ACT[half] / B = the tile the previous step kept
         const long long off = which == 0 ? st.a_off : st.b_off;
         const unsigned char* src;
         if (space == SP_W) src = mt.wplanes + off;
@@ -197,6 +197,7 @@ __device__ void mma_role(const LaunchP& L, int ai, const MemberDev& mb, unsigned
   const long long s0 = ctl->chunk_s0;
   const int i0 = ctl->chunk_i0, n_chunk = ctl->chunk_n;
   const int k0 = L.ms_off[ai], k1 = k0 + L.ms_cnt[ai];
+  uint32_t held_slot = 0;
   for (long long i = 0; i < n_chunk; ++i) {
     const StepVars sv = step_vars(mb, s0 + i, i, n_epis);
     const bool half1 = __any_sync(0xffffffffu, sv.rows_h[1] > 0);
@@ -211,7 +212,7 @@ __device__ void mma_role(const LaunchP& L, int ai, const MemberDev& mb, unsigned
       else if (st.mma_dep_joint < 0) wait_all(ctl->epi_done, sv.base + (uint32_t)(-st.mma_dep_joint));
       if (tr && (threadIdx.x & 31) == 0) g_trace[tb + 3 * (k - k0)] = gtime();
       uint32_t a_base, slot_a = kSlots;
-      if (st.a_tile) {
+      if (st.a_tile & 1) {
         slot_a = seq % kSlots;
         tc::mbar_wait(&ctl->full[slot_a], (seq / kSlots) & 1u);
         a_base = ring + slot_a * kSlotBytes;
@@ -219,12 +220,19 @@ __device__ void mma_role(const LaunchP& L, int ai, const MemberDev& mb, unsigned
       } else {
         a_base = act0 + st.half * kActBytes + st.a_start;
       }
-      const uint32_t slot_b = seq % kSlots;
-      tc::mbar_wait(&ctl->full[slot_b], (seq / kSlots) & 1u);
+      uint32_t slot_b;
+      if (st.b_mn & 2) {           // B = the tile the previous step kept (already landed): released after these MMAs
+        slot_b = held_slot;
+      } else {
+        slot_b = seq % kSlots;
+        tc::mbar_wait(&ctl->full[slot_b], (seq / kSlots) & 1u);
+        ++seq;
+      }
       const uint32_t b_base = ring + slot_b * kSlotBytes;
-      ++seq;
+      const bool keep_a = (st.a_tile & 2) != 0;
+      if (keep_a) held_slot = slot_a;
       tc::fence_after();
-      const uint32_t idesc = tc::make_idesc(st.n, st.a_mn, st.b_mn);
+      const uint32_t idesc = tc::make_idesc(st.n, st.a_mn, st.b_mn & 1);
       const uint32_t d = tmem + st.tmem_col;
       const uint64_t hi_a = ((uint64_t)st.a_sbo << 32) | (1ull << 46) | ((uint64_t)st.a_lbo << 16);
       const uint64_t hi_b = ((uint64_t)st.b_sbo << 32) | (1ull << 46) | ((uint64_t)st.b_lbo << 16);
@@ -240,7 +248,7 @@ __device__ void mma_role(const LaunchP& L, int ai, const MemberDev& mb, unsigned
           da += st.a_kadv; db += st.b_kadv;
         }
         tc::mma_commit(&ctl->empty[slot_b]);
-        if (slot_a != kSlots) tc::mma_commit(&ctl->empty[slot_a]);
+        if (slot_a != kSlots && !keep_a) tc::mma_commit(&ctl->empty[slot_a]);
         if (st.commit == 1 || (st.commit == 2 && !half1)) tc::mma_commit(&ctl->accbar[st.commit_buf]);
         if (st.commit2) tc::mma_commit(&ctl->accbar[st.half]);
         if (tr) g_trace[tb + 3 * (k - k0) + 2] = gtime();

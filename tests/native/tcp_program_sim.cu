@@ -15,7 +15,7 @@ int main(int argc, char** argv){
   std::vector<Tile> tiles; std::vector<int> first_tile(NS), n_tiles(NS);
   for (int k = 0; k < NS; ++k) { const auto& s = P.steps[k]; first_tile[k] = tiles.size();
     if (s.a_bytes) tiles.push_back({k, s.dep, s.dep_grp, false});
-    tiles.push_back({k, s.dep, s.dep_grp, s.b_space == tcp::SP_W}); n_tiles[k] = tiles.size() - first_tile[k]; }
+    if (s.b_bytes) tiles.push_back({k, s.dep, s.dep_grp, s.b_space == tcp::SP_W}); n_tiles[k] = tiles.size() - first_tile[k]; }
   auto owner = [&](const tcp::Epi& e, int g) {
     if (e.kind == tcp::EK_STEP_END || e.split_all) return g;
     if (e.kind == tcp::EK_WGRAD || e.kind == tcp::EK_WGRAD_T) return 2;
@@ -50,7 +50,7 @@ int main(int argc, char** argv){
         for (int g = 0; g < 3; ++g)
           if (owner(P.epis[prev], g) == g && ep[g] <= prev) { printf("HAZARD (seed %u): step %d overwrites accumulator %d before group %d finished item %d\n", seed, mi, b, g, prev); return -1; }
       }
-      consumed += n_tiles[mi];
+      consumed += n_tiles[mi] - (s.a_hold ? 1 : 0) + (s.b_held ? 1 : 0);      // a kept slot is released by the next step
       if (s.commit == 1) { commits[s.commit_buf]++; use_idx[s.commit_buf]++; }
       if (s.commit2) { commits[s.half]++; use_idx[s.half]++; }
       ++mi; return 1; };
