@@ -175,6 +175,7 @@ __host__ __device__ inline Epi from_epip(const EpiP& q) {
 struct WBlock {
   long long p_off; int p_ld, row0, rows_valid, cols_valid;
   long long wp_off; int R, cg;
+  int transposed;     // 1: planes block rows = INPUT index (R = round16(in + 1)), column groups = output rows (cg groups of 8)
 };
 
 // Adam master state of one linear layer inside the per-slot master buffer.  While a member is resident its
@@ -253,7 +254,7 @@ inline Program build_program(const ArchDesc& a) {
   struct WRef { long long wp_off; int R, cg, row0, rows; };
   auto wblock = [&](const LinDesc& w, int row0, int rows, int R) {
     WBlock b; b.p_off = w.off; b.p_ld = w.ld; b.row0 = row0; b.rows_valid = rows; b.cols_valid = w.in + 1;
-    b.R = R; b.cg = round16(w.in + 1) / 8; b.wp_off = wo;
+    b.R = R; b.cg = round16(w.in + 1) / 8; b.wp_off = wo; b.transposed = 0;
     wo += (long long)b.cg * 32 * R;
     P.wblocks.push_back(b);
     return WRef{b.wp_off, R, b.cg, row0, rows};
@@ -305,8 +306,16 @@ inline Program build_program(const ArchDesc& a) {
     w_head[m] = wblock(q.head, 0, q.head.out, round16(q.head.out));
     for (int l = 0; l < L; ++l) w_dec[m].push_back(wblock(q.dec[l], 0, q.dec[l].out, round16(q.dec[l].out)));
     if (fast_out) w_out[m].push_back(wblock(q.outl, 0, q.D, round16(q.D)));
-    for (int t = 0; t < lay.n_dxh_blk[m]; ++t)
-      w_out[m].push_back(wblock(q.outl, 64 * t, q.D - 64 * t < 64 ? q.D - 64 * t : 64, 64));
+    else {
+      // wide / multi-modality output layer: ONE block stored transposed (rows = input index, 8-column groups = output
+      // rows), so that the transposed weight-gradient epilogue (lane = input index) rewrites it with 16-byte stores.
+      // Any run of 8 groups (64 output rows) is a contiguous tile: MN-major B of the forward GEMM, K-major B of dgrad.
+      WBlock b; b.p_off = q.outl.off; b.p_ld = q.outl.ld; b.row0 = 0; b.rows_valid = q.D; b.cols_valid = q.outl.in + 1;
+      b.R = round16(q.outl.in + 1); b.cg = 8 * lay.n_dxh_blk[m]; b.wp_off = wo; b.transposed = 1;
+      wo += (long long)b.cg * 32 * b.R;
+      P.wblocks.push_back(b);
+      w_out[m].push_back(WRef{b.wp_off, b.R, b.cg, 0, q.D});
+    }
   }
   lay.zbuf = alloc((long long)256 * Z * 4);
   lay.dz = alloc((long long)256 * Z * 4);
@@ -495,9 +504,20 @@ inline Program build_program(const ArchDesc& a) {
     }
     for (int t = 0; t < lay.n_dxh_blk[m]; ++t) {
       for (int h = 0; h < 2; ++h) {
-        emit_fwd(h, w_out[m][t], SP_NONE, 0, 0, 0);
+        {   // x_recon columns 64 t .. 64 t + 63: ACT[h] (K-major) x 8 column groups of the transposed block (MN-major)
+          const WRef& w = w_out[m][0];
+          const int buf = accbuf(h);
+          Step s = base_step(h);
+          set_b(s, SP_W, w.wp_off, w.R, 8 * t, 8, true);
+          set_a_kmajor(s, 0);
+          s.ksteps = (unsigned short)(w.R / 16); s.n = 64; s.tmem_col = (unsigned short)(kAcc0 + 128 * buf);
+          s.first = 1;
+          need(s, acc_free[buf]); need(s, act_ready[h]);
+          s.commit = 1; s.commit_buf = (unsigned char)buf;
+          P.steps.push_back(s);
+        }
         Epi e = new_epi(EK_RECON, h, accbuf(h), m);
-        e.n_mma = 64; e.n_valid = w_out[m][t].rows; e.n_cols = 64; e.col0 = 64 * t;
+        e.n_mma = 64; e.n_valid = q.D - 64 * t < 64 ? q.D - 64 * t : 64; e.n_cols = 64; e.col0 = 64 * t;
         e.stash_off = lay.dxh_blk[m] + ((long long)h * lay.n_dxh_blk[m] + t) * 32768;
         e.last = t == lay.n_dxh_blk[m] - 1;
         const int id = push_epi(e);
@@ -598,13 +618,13 @@ inline Program build_program(const ArchDesc& a) {
         for (int h = 0; h < 2; ++h) {
           const int buf = accbuf(h);
           for (int t = t0; t < t0 + nt; ++t) {
-            const WRef& w = w_out[m][t];
+            const WRef& w = w_out[m][0];
             const long long tile = lay.dxh_blk[m] + ((long long)h * lay.n_dxh_blk[m] + t) * 32768;
             Step s = base_step(h);
-            set_b(s, SP_W, w.wp_off, 64, 0, w.cg, true);
+            set_b(s, SP_W, w.wp_off, w.R, 8 * t, 8, false);       // rows = input index (N), 8 groups = 64 output rows (K)
             set_a_kmajor(s, 0);
             s.a_space = SP_STASH; s.a_off = tile; s.a_bytes = 32768; s.a_hold = 1;
-            s.ksteps = 4; s.n = (unsigned short)(w.cg * 8); s.tmem_col = (unsigned short)(kAcc0 + 128 * buf);
+            s.ksteps = 4; s.n = (unsigned short)w.R; s.tmem_col = (unsigned short)(kAcc0 + 128 * buf);
             s.first = t == 0;
             if (t == 0) need(s, acc_free[buf]);
             s.commit_buf = (unsigned char)buf;
@@ -627,7 +647,7 @@ inline Program build_program(const ArchDesc& a) {
         Epi e = new_epi(EK_WGRAD_T, 2, 2 + wb, m);
         e.n_mma = 64 * nt; e.col0 = 64 * t0;
         e.p_off = q.outl.off; e.p_ld = q.outl.ld; e.p_rows = q.outl.out; e.p_cols = q.outl.in + 1;
-        e.wp_off = w_out[m][0].wp_off; e.wp_R = 64; e.src_cg = w_out[m][0].cg;
+        e.wp_off = w_out[m][0].wp_off; e.wp_R = w_out[m][0].R;
         e.mst_off = mst[q.outl.off].mst_off; e.mst_R = mst[q.outl.off].R;
         acc_free[2 + wb] = push_epi(e);
       }

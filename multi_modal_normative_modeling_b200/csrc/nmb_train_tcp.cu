@@ -341,6 +341,22 @@ __device__ void build_weight_planes(const ProgramDev& pg, const MemberDev& mb, c
   for (int b = 0; b < pg.n_wblocks; ++b) {
     const WBlock wb = pg.wblocks[b];
     if (p_off >= 0 && wb.p_off != p_off) continue;
+    if (wb.transposed) {            // rows = input index i, groups of 8 output rows
+      unsigned char* dstT = mt.wplanes + wb.wp_off;
+      for (int u = tid; u < wb.R * wb.cg; u += nthr) {
+        const int i = u % wb.R, og = u / wb.R;
+        float x[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          x[j] = (8 * og + j < wb.rows_valid && i < wb.cols_valid) ? P[wb.p_off + (long long)(8 * og + j) * wb.p_ld + i] : 0.f;
+        uint4 h, l;
+        tc::split8(x, h, l);
+        unsigned char* p = dstT + (long long)og * 32 * wb.R + i * 16;
+        *reinterpret_cast<uint4*>(p) = h;
+        *reinterpret_cast<uint4*>(p + 16 * wb.R) = l;
+      }
+      continue;
+    }
     const int units = wb.R * wb.cg;
     unsigned char* dst = mt.wplanes + wb.wp_off;
     for (int u = tid; u < units; u += nthr) {
@@ -857,8 +873,10 @@ __device__ __forceinline__ void epi_wgrad_t(EpiCtx& c, const Epi& e) {
   const bool vi = i < e.p_cols;
   const int p_ld = e.p_ld, p_rows = e.p_rows, n_mma = e.n_mma, col0 = e.col0;
   const long long R4 = (long long)e.mst_R * 4;
-  unsigned char* wp = c.mt->wplanes + e.wp_off + (long long)(i >> 3) * 2048 + (i & 7) * 2;
-  const long long blk_bytes = (long long)e.src_cg * 2048;     // one 64-row planes block
+  // the layer's planes are stored transposed (rows = input index): this lane's 8 output rows are one 16-byte element
+  unsigned char* wp = c.mt->wplanes + e.wp_off + i * 16;
+  const long long grp_bytes = 32LL * e.wp_R;
+  const int lo_off = 16 * e.wp_R;
   const bool adam = !(c.flags & NMB_TRAIN_NO_ADAM), wg = c.flags & NMB_TRAIN_WRITE_GRADS;
   const long long colbase = e.p_off + i;
   const long long m0 = e.mst_off + (long long)i * 4 + (long long)((col0 >> 2) + 2 * c.cpart) * R4;
@@ -907,21 +925,15 @@ __device__ __forceinline__ void epi_wgrad_t(EpiCtx& c, const Epi& e) {
           st_stream4(pm + R4, mb4); st_stream4(pv + R4, vb);
           st_stream4(pp + R4, make_float4(x[4], x[5], x[6], x[7]));
         }
-        // planes of W[o][i]: K-major 64-row blocks, this lane owns column i -> 2-byte elements, 8 rows per chunk
-        unsigned char* pb0 = wp + (long long)(o0 >> 6) * blk_bytes + (o0 & 63) * 16;     // chunks never straddle a block
+        if (o0 + 8 > p_rows) {
 #pragma unroll
-        for (int j = 0; j < 8; j += 2) {
-          uint32_t hi, lo;
-          tc::split2(x[j], x[j + 1], hi, lo);
-          if (o0 + j < p_rows) {
-            *reinterpret_cast<unsigned short*>(pb0 + j * 16) = (unsigned short)(hi & 0xFFFFu);
-            *reinterpret_cast<unsigned short*>(pb0 + j * 16 + 1024) = (unsigned short)(lo & 0xFFFFu);
-          }
-          if (o0 + j + 1 < p_rows) {
-            *reinterpret_cast<unsigned short*>(pb0 + (j + 1) * 16) = (unsigned short)(hi >> 16);
-            *reinterpret_cast<unsigned short*>(pb0 + (j + 1) * 16 + 1024) = (unsigned short)(lo >> 16);
-          }
+          for (int j = 0; j < 8; ++j) x[j] = (o0 + j < p_rows) ? x[j] : 0.f;
         }
+        uint4 hh, ll;
+        tc::split8(x, hh, ll);
+        unsigned char* pb0 = wp + (long long)(o0 >> 3) * grp_bytes;
+        *reinterpret_cast<uint4*>(pb0) = hh;
+        *reinterpret_cast<uint4*>(pb0 + lo_off) = ll;
       }
     }
     pp += mstride; pm += mstride; pv += mstride; ta += tstride;
@@ -1476,8 +1488,24 @@ __global__ void __launch_bounds__(256) tcp_move_kernel(const PrepArgs a, const i
           // thread = (row, 8-column group); consecutive rows -> 512 contiguous bytes per warp store
           for (int b = 0; b < pg.n_wblocks; ++b) {
             const WBlock wb = pg.wblocks[b];
-            if (wb.p_off != ml.p_off || r0 < wb.row0 || r0 >= wb.row0 + wb.R) continue;
+            if (wb.p_off != ml.p_off) continue;
             unsigned char* dst = a.mtc[mi].wplanes + wb.wp_off;
+            if (wb.transposed) {      // thread = (input index, group of 8 output rows): 512 contiguous bytes per warp store
+              for (int u = tid; u < 128 * 4; u += 256) {
+                const int il = u & 127, ogl = u >> 7, i = c0 + il, og = (r0 >> 3) + ogl;
+                if (i >= wb.R || og >= wb.cg) continue;
+                float x[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) x[j] = (8 * ogl + j < nr && il < nc) ? T[8 * ogl + j][il] : 0.f;
+                uint4 h, l;
+                tc::split8(x, h, l);
+                unsigned char* p = dst + (long long)og * 32 * wb.R + i * 16;
+                *reinterpret_cast<uint4*>(p) = h;
+                *reinterpret_cast<uint4*>(p + 16 * wb.R) = l;
+              }
+              continue;
+            }
+            if (r0 < wb.row0 || r0 >= wb.row0 + wb.R) continue;
             for (int u = tid; u < 32 * 16; u += 256) {
               const int r = u & 31, gl = u >> 5, g = (c0 >> 3) + gl, rb = r0 - wb.row0 + r;
               if (g >= wb.cg || rb >= wb.R) continue;
