@@ -1034,34 +1034,61 @@ __device__ void epi_head_latent(EpiCtx& c, const Epi& e, const float* eps_src) {
 
 // ---- one modality, Z <= 16: d/dz accumulator -> latent backward -> d[mu | logvar] planes in ACT[h] ------------
 __device__ void epi_dz_latent_bwd(EpiCtx& c, const Epi& e) {
-  
   const ArchDesc& a = *c.a;
   const int h = e.half, Z = a.Z, rows = c.rows_of(h);
   const bool vr = c.row < rows;
   const int gb = 128 * h + c.row;
   const float* S = c.scratch;
   const float inv_rows = 1.f / c.rows;
-  float dz[16], out[32];
+  const long long s_mub = a.s_mub, s_lvb = a.s_lvb, s_eps = a.s_eps;
+  float dz[16], dmu[16], dlv[16];
   tc::tmem_ld16(taddr(c, e.tmem_col), dz);
-#pragma unroll
-  for (int j = 0; j < 32; ++j) out[j] = 0.f;
+  // phase 1: every global load and all arithmetic, statically indexed registers only
 #pragma unroll
   for (int z = 0; z < 16; ++z) {
+    dmu[z] = 0.f; dlv[z] = 0.f;
     if (z < Z && vr) {
       const int gi = gb * Z + z;
-      const float mub = S[a.s_mub + gi], lvb = S[a.s_lvb + gi], eps = S[a.s_eps + gi];
+      const float mub = S[s_mub + gi], lvb = S[s_lvb + gi], eps = S[s_eps + gi];
       const float sd = expf(0.5f * lvb);
-      out[z] = dz[z] + mub * inv_rows;                                                   // d/dmu  (M = 1)
-      out[Z + z] = dz[z] * eps * sd * 0.5f + (expf(lvb) - 1.f) * 0.5f * inv_rows;       // d/dlogvar
+      dmu[z] = dz[z] + mub * inv_rows;                                                   // d/dmu  (M = 1)
+      dlv[z] = dz[z] * eps * sd * 0.5f + (expf(lvb) - 1.f) * 0.5f * inv_rows;           // d/dlogvar
     }
   }
-  unsigned char* act = c.smem + h * kActBytes;
+  // phase 2: planes of [d/dmu (Z) | d/dlogvar (Z) | 0] in ACT[h].  d/dmu sits at static columns; d/dlogvar starts at the
+  // run-time column Z, so its BF16 hi / lo elements are placed with 2-byte shared-memory stores over a zero fill
+  // (same thread, same row: program order).
+  unsigned char* act = c.smem + h * kActBytes + c.row * 16;
   const int cg = round16(2 * Z) / 8;
-  for (int g = 0; g < cg; ++g) {
+  {
     float x[8];
+    uint4 hh, ll;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) x[j] = out[8 * g + j];
-    put_planes(act, g, c.row, x);
+    for (int j = 0; j < 8; ++j) x[j] = dmu[j];
+    tc::split8(x, hh, ll);
+    *reinterpret_cast<uint4*>(act) = hh; *reinterpret_cast<uint4*>(act + 2048) = ll;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = dmu[8 + j];
+    tc::split8(x, hh, ll);
+    if (cg > 1) { *reinterpret_cast<uint4*>(act + 4096) = hh; *reinterpret_cast<uint4*>(act + 4096 + 2048) = ll; }
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    for (int g = 2; g < cg; ++g) { *reinterpret_cast<uint4*>(act + g * 4096) = zero; *reinterpret_cast<uint4*>(act + g * 4096 + 2048) = zero; }
+  }
+#pragma unroll
+  for (int z = 0; z < 16; z += 2) {
+    if (z < Z) {
+      uint32_t hi, lo;
+      tc::split2(dlv[z], dlv[z + 1], hi, lo);
+      const int c0 = Z + z, c1 = Z + z + 1;
+      unsigned char* p0 = act + (c0 >> 3) * 4096 + (c0 & 7) * 2;
+      *reinterpret_cast<unsigned short*>(p0) = (unsigned short)(hi & 0xFFFFu);
+      *reinterpret_cast<unsigned short*>(p0 + 2048) = (unsigned short)(lo & 0xFFFFu);
+      if (z + 1 < Z) {
+        unsigned char* p1 = act + (c1 >> 3) * 4096 + (c1 & 7) * 2;
+        *reinterpret_cast<unsigned short*>(p1) = (unsigned short)(hi >> 16);
+        *reinterpret_cast<unsigned short*>(p1 + 2048) = (unsigned short)(lo >> 16);
+      }
+    }
   }
 }
 
