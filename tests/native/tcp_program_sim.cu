@@ -10,6 +10,23 @@ int main(int argc, char** argv){
   auto P = tcp::build_program(d);
   const int NS = P.steps.size(), NE = P.epis.size();
   printf("steps %d epis %d\n", NS, NE);
+  // the compact item table that travels in the kernel parameters must reproduce every field the kernel reads
+  for (int k = 0; k < NE; ++k) {
+    const tcp::Epi& e = P.epis[k];
+    if (!tcp::epip_fits(e)) { printf("item %d does not fit the compact form\n", k); return 5; }
+    const tcp::Epi r = tcp::from_epip(tcp::to_epip(e));
+    const bool same = r.kind == e.kind && r.half == e.half && r.buf == e.buf && r.mod == e.mod && r.n_mma == e.n_mma &&
+                      r.n_valid == e.n_valid && r.n_cols == e.n_cols && r.tmem_col == e.tmem_col && r.col0 == e.col0 &&
+                      r.to_act == e.to_act && r.stash_off == e.stash_off && r.src_off == e.src_off && r.src_cg == e.src_cg &&
+                      r.p_off == e.p_off && r.p_ld == e.p_ld && r.p_rows == e.p_rows && r.p_cols == e.p_cols &&
+                      r.wp_off == e.wp_off && r.wp_R == e.wp_R && r.mst_off == e.mst_off && r.mst_R == e.mst_R &&
+                      r.row0 == e.row0 && r.last == e.last && r.split_all == e.split_all && r.wait_optim == e.wait_optim;
+    if (!same) { printf("item %d: compact form loses a field\n", k); return 6; }
+  }
+  // a step that reads the tile kept by its predecessor must directly follow a step that keeps one, in the same half
+  for (int k = 0; k < NS; ++k)
+    if (P.steps[k].b_held && (k == 0 || !P.steps[k - 1].a_hold || P.steps[k - 1].half != P.steps[k].half)) {
+      printf("step %d reads a kept tile nobody kept\n", k); return 7; }
   // tile list
   struct Tile { int step; int dep; int grp; bool w; };
   std::vector<Tile> tiles; std::vector<int> first_tile(NS), n_tiles(NS);
