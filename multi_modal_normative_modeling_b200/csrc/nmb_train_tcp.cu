@@ -998,8 +998,8 @@ __device__ void epi_head_latent(EpiCtx& c, const Epi& e, const float* eps_src) {
       const float m_ = mu[z], l_ = lv[z], eps = zz[z];
       S[s_mub + e0 + z] = m_; S[s_lvb + e0 + z] = l_;
       if (eps_src) S[s_eps + e0 + z] = eps;
-      zz[z] = m_ + eps * expf(0.5f * l_);
-      kl += -0.5f * (1.f + l_ - m_ * m_ - expf(l_));
+      zz[z] = m_ + eps * __expf(0.5f * l_);
+      kl += -0.5f * (1.f + l_ - m_ * m_ - __expf(l_));
     }
   }
   c.kl_acc += kl;
@@ -1050,9 +1050,9 @@ __device__ void epi_dz_latent_bwd(EpiCtx& c, const Epi& e) {
     if (z < Z && vr) {
       const int gi = gb * Z + z;
       const float mub = S[s_mub + gi], lvb = S[s_lvb + gi], eps = S[s_eps + gi];
-      const float sd = expf(0.5f * lvb);
+      const float sd = __expf(0.5f * lvb);
       dmu[z] = dz[z] + mub * inv_rows;                                                   // d/dmu  (M = 1)
-      dlv[z] = dz[z] * eps * sd * 0.5f + (expf(lvb) - 1.f) * 0.5f * inv_rows;           // d/dlogvar
+      dlv[z] = dz[z] * eps * sd * 0.5f + (__expf(lvb) - 1.f) * 0.5f * inv_rows;           // d/dlogvar
     }
   }
   // phase 2: planes of [d/dmu (Z) | d/dlogvar (Z) | 0] in ACT[h].  d/dmu sits at static columns; d/dlogvar starts at the
