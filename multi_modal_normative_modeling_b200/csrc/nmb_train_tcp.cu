@@ -144,12 +144,14 @@ __device__ void producer_role(const TrainLaunch& t, const ProgramDev& pg, const 
         if (st.dep_grp < 2) wait_epi(&ctl->epi_done[st.dep_grp], sv.base + (uint32_t)st.dep);
         else wait_all(ctl->epi_done, sv.base + (uint32_t)st.dep);
       }
-      if (st.b_space == SP_W) wait_all(ctl->epi_done, sv.base);   // weight planes: every Adam item of the previous step
       TRACE(tr, tb + 2 * k);
       for (int which = 0; which < 2; ++which) {
         const int space = which == 0 ? st.a_space : st.b_space;
         const uint32_t bytes = which == 0 ? st.a_bytes : st.b_bytes;
         if (bytes == 0) continue;          // A resident in ACT[half] / B = the tile the previous step kept
+        // weight planes: every Adam item of the previous step (dataset tiles do not wait: the first x tile of a step
+        // is in flight while the previous step ends)
+        if (space == SP_W) wait_all(ctl->epi_done, sv.base);
         const long long off = which == 0 ? st.a_off : st.b_off;
         const unsigned char* src;
         if (space == SP_W) src = mt.wplanes + off;
