@@ -363,6 +363,9 @@ inline Program build_program(const ArchDesc& a) {
     else { s.b_lbo = 32 * R; s.b_sbo = 128; s.b_kadv = 64 * R; }
   };
   auto tile_groups = [](int R) { int g = 1024 / R; return g > 16 ? 16 : (g < 2 ? 2 : g & ~1); };
+  // One modality: a stashed hidden activation of 9 .. 16 column groups is stored as two 64-row sub-blocks (the
+  // weight gradient that reads it is then split over K, see emit_wgrad_part); `cols` = layer width + 1.
+  auto is64 = [&](int cols) { const int cg = round16(cols) / 8; return M == 1 && cg > 8 && cg <= 16; };
 
   // forward-type group: acc[h][0..N) = sum_k A[.,k] B[n,k]; A from ACT[h] or ring tiles (a_space/a_base)
   auto emit_fwd = [&](int h, const WRef& w, int a_space, long long a_base, int a_dep, int x_mod) {
@@ -408,8 +411,28 @@ inline Program build_program(const ArchDesc& a) {
   // acc_commit: the part also commits acc[h] on its last step -- the preceding dgrad group of the same half
   // left it open so that the epilogue overwriting ACT[h] cannot start before these MMAs have read ACT[h].
   auto emit_wgrad_part = [&](int h, int wb, int b_space, long long b_base, int g_first, int g_count, int x_mod,
-                             bool acc_commit) {
+                             bool acc_commit, int blk64_cg) {
     const int b_dep = b_space == SP_STASH ? ready[b_base] : 0;
+    if (blk64_cg) {
+      // B block stored as two 64-row sub-blocks (all column groups contiguous, <= 32 KB each): the GEMM is split over K
+      // (batch rows) instead of N, so that the MN-major A operand (ACT[h]^T) is read once per pass, not once per N chunk
+      for (int kh = 0; kh < 2; ++kh) {
+        Step s = base_step(h);
+        s.b_space = (unsigned char)b_space; s.b_off = b_base + (long long)kh * blk64_cg * 2048; s.b_bytes = (unsigned)blk64_cg * 2048;
+        s.b_mn = 1; s.b_lo = 1024; s.b_sbo = 2048; s.b_lbo = 128; s.b_kadv = 256;
+        set_a_mnmajor(s); s.a_start = (unsigned)kh * 1024;
+        s.dep = b_dep;
+        s.ksteps = 4; s.n = (unsigned short)(g_count * 8); s.tmem_col = (unsigned short)(kWacc0 + 128 * wb);
+        s.first = h == 0 && kh == 0;
+        if (kh == 0) { need(s, act_ready[h]); need(s, acc_free[2 + wb]); }
+        const bool last = kh == 1;
+        s.commit = !last ? 0 : (h == 1 ? 1 : 2);
+        s.commit_buf = (unsigned char)(2 + wb);
+        if (last && acc_commit) { s.commit2 = 1; s.commit2_buf = (unsigned char)accbuf(h); }
+        P.steps.push_back(s);
+      }
+      return;
+    }
     for (int g0 = 0; g0 < g_count; g0 += 8) {
       const int ng = g_count - g0 < 8 ? g_count - g0 : 8;
       Step s = base_step(h);
@@ -443,6 +466,7 @@ inline Program build_program(const ArchDesc& a) {
         Epi e = new_epi(EK_HIDDEN, h, accbuf(h), m);
         e.n_mma = w_enc[m][l].R; e.n_valid = q.enc[l].out; e.n_cols = round16(q.enc[l].out + 1);
         e.to_act = 1; e.stash_off = s_h[m][l * 2 + h];
+        e.src_cg = is64(q.enc[l].out + 1) ? e.n_cols / 8 : 0;
         const int id = push_epi(e);
         act_ready[h] = id; acc_free[accbuf(h)] = id;
       }
@@ -487,6 +511,7 @@ inline Program build_program(const ArchDesc& a) {
         Epi e = new_epi(EK_HIDDEN, h, accbuf(h), m);
         e.n_mma = w_dec[m][l].R; e.n_valid = q.dec[l].out; e.n_cols = round16(q.dec[l].out + 1);
         e.to_act = 1; e.stash_off = s_k[m][l * 2 + h];
+        e.src_cg = is64(q.dec[l].out + 1) ? e.n_cols / 8 : 0;
         const int id = push_epi(e);
         act_ready[h] = id; acc_free[accbuf(h)] = id;
       }
@@ -554,8 +579,9 @@ inline Program build_program(const ArchDesc& a) {
   //   guard_act: no dgrad, but an epilogue-only item of the same half overwrites ACT[h] next (EK_COPY of the next
   //   modality): the wgrad part commits acc[h] and that item waits for it.
   auto layer_backward = [&](int m, const LinDesc& w, const WRef& wr, int b_space, const long long in_base[2],
-                            int dg_kind, int n_need, int x_mod, bool guard_act) {
+                            int dg_kind, int n_need, int x_mod, bool guard_act, bool blk64) {
     const int in_cg = round16(w.in + 1) / 8;
+    const int b64 = blk64 ? in_cg : 0;
     const int n_items = (in_cg + 15) / 16;
     for (int it0 = 0; it0 < n_items; it0 += 2) {
       const int it1 = it0 + 2 < n_items ? it0 + 2 : n_items;
@@ -566,12 +592,12 @@ inline Program build_program(const ArchDesc& a) {
         int wb = wb0;
         for (int it = it0; it < it1; ++it, wb ^= 1) {
           const int gf = it * 16, gc = in_cg - gf < 16 ? in_cg - gf : 16;
-          emit_wgrad_part(h, wb, b_space, in_base[h], gf, gc, x_mod, (dg_kind || guard_act) && last_pair && it == it1 - 1);
+          emit_wgrad_part(h, wb, b_space, in_base[h], gf, gc, x_mod, (dg_kind || guard_act) && last_pair && it == it1 - 1, b64);
         }
         if (dg_kind && last_pair) {
           Epi e = new_epi(dg_kind == 1 ? EK_DGRAD : (fused_latent ? EK_DZ_LATENT_BWD : EK_DZ), h, accbuf(h), m);
           e.n_mma = round16(n_need); e.n_valid = n_need;
-          if (dg_kind == 1) { e.n_cols = round16(n_need); e.to_act = 1; e.src_off = in_base[h]; }
+          if (dg_kind == 1) { e.n_cols = round16(n_need); e.to_act = 1; e.src_off = in_base[h]; e.src_cg = blk64 ? in_cg : 0; }
           else if (fused_latent) e.to_act = 1;
           const int id = push_epi(e);
           act_ready[h] = id; acc_free[accbuf(h)] = id;
@@ -595,7 +621,7 @@ inline Program build_program(const ArchDesc& a) {
     const long long k_last[2] = {s_k[m][(L - 1) * 2 + 0], s_k[m][(L - 1) * 2 + 1]};
     if (lay.n_dxh_blk[m] == 0) {
       // decoder_mean_layer as a regular layer: ACT[h] holds d/dx_recon (written by EK_RECON)
-      layer_backward(m, q.outl, w_out[m][0], SP_STASH, k_last, 1, q.outl.in, 0, false);
+      layer_backward(m, q.outl, w_out[m][0], SP_STASH, k_last, 1, q.outl.in, 0, false, is64(q.outl.in + 1));
     } else {
       if (M > 1) {   // ACT[h] <- last decoder hidden activation of this modality (transposed wgrad A operand)
         for (int h = 0; h < 2; ++h) {
@@ -656,6 +682,7 @@ inline Program build_program(const ArchDesc& a) {
         Epi e = new_epi(EK_DGRAD, h, buf, m);
         e.n_mma = round16(q.outl.in + 1); e.n_valid = q.outl.in; e.n_cols = round16(q.outl.in);
         e.to_act = 1; e.src_off = k_last[h];
+        e.src_cg = is64(q.outl.in + 1) ? round16(q.outl.in + 1) / 8 : 0;
         const int id = push_epi(e);
         act_ready[h] = id; acc_free[buf] = id;
       }
@@ -664,7 +691,8 @@ inline Program build_program(const ArchDesc& a) {
     for (int l = L - 1; l >= 0; --l) {
       const long long in_base[2] = {l == 0 ? s_g0[m * 2 + 0] : s_k[m][(l - 1) * 2 + 0],
                                     l == 0 ? s_g0[m * 2 + 1] : s_k[m][(l - 1) * 2 + 1]};
-      layer_backward(m, q.dec[l], w_dec[m][l], SP_STASH, in_base, l > 0 ? 1 : 2, l > 0 ? q.dec[l].in : Z, 0, false);
+      layer_backward(m, q.dec[l], w_dec[m][l], SP_STASH, in_base, l > 0 ? 1 : 2, l > 0 ? q.dec[l].in : Z, 0, false,
+                     l > 0 && is64(q.dec[l].in + 1));
     }
   }
   for (int h = 0; h < 2 && !fused_latent; ++h) {
@@ -689,11 +717,11 @@ inline Program build_program(const ArchDesc& a) {
       const WRef& wr = is_head ? w_head[m] : w_enc[m][l];
       if (!is_head && l == 0) {
         const long long xb[2] = {0, 0};
-        layer_backward(m, w, wr, SP_X, xb, 0, 0, m, m + 1 < M);
+        layer_backward(m, w, wr, SP_X, xb, 0, 0, m, m + 1 < M, false);
       } else {
         const int li = (is_head ? L : l) - 1;
         const long long in_base[2] = {s_h[m][li * 2 + 0], s_h[m][li * 2 + 1]};
-        layer_backward(m, w, wr, SP_STASH, in_base, 1, w.in, 0, false);
+        layer_backward(m, w, wr, SP_STASH, in_base, 1, w.in, 0, false, is64(w.in + 1));
       }
     }
   }

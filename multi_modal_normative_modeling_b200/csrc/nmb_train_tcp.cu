@@ -386,7 +386,11 @@ __device__ __forceinline__ void epi_hidden(EpiCtx& c, const Epi& e) {
   const int rows = c.rows_of(h);
   const bool vr = c.row < rows;
   unsigned char* act = c.smem + h * kActBytes + c.row * 16;
-  unsigned char* st = c.stash + e.stash_off + c.row * 16;
+  // stash block: one 128-row block (group chunk 4 KB = hi 2 KB + lo 2 KB) or, src_cg > 0, two 64-row sub-blocks of
+  // src_cg groups (group chunk 2 KB = hi 1 KB + lo 1 KB): the weight gradient that reads it is split over K
+  const int b64 = e.src_cg;
+  unsigned char* st = c.stash + e.stash_off + (b64 ? (long long)(c.row >> 6) * b64 * 2048 + (c.row & 63) * 16 : (long long)c.row * 16);
+  const int st_g = b64 ? 2048 : 4096, st_lo = b64 ? 1024 : 2048;
   const float slope = c.a->non_linear ? kSlope : 1.f;        // leaky-relu(x) = max(x, slope * x)
   const int n_cols = e.n_cols, n_mma = e.n_mma, n_valid = e.n_valid, tcol = e.tmem_col;
   for (int ch = c.cpart; ch * 16 < n_cols; ch += c.parts) {
@@ -418,8 +422,8 @@ __device__ __forceinline__ void epi_hidden(EpiCtx& c, const Epi& e) {
       const long long off = (long long)(2 * ch + q) * 4096;
       *reinterpret_cast<uint4*>(act + off) = hh;
       *reinterpret_cast<uint4*>(act + off + 2048) = ll;
-      *reinterpret_cast<uint4*>(st + off) = hh;
-      *reinterpret_cast<uint4*>(st + off + 2048) = ll;
+      *reinterpret_cast<uint4*>(st + (long long)(2 * ch + q) * st_g) = hh;
+      *reinterpret_cast<uint4*>(st + (long long)(2 * ch + q) * st_g + st_lo) = ll;
     }
   }
 }
@@ -667,21 +671,23 @@ __device__ __forceinline__ void epi_dgrad(EpiCtx& c, const Epi& e) {
   const int rows = c.rows_of(h);
   const bool vr = c.row < rows;
   unsigned char* act = c.smem + h * kActBytes;
-  const unsigned char* sg = c.stash + e.src_off + c.row * 16;
+  const int b64 = e.src_cg;        // layout of the stashed activation, see epi_hidden
+  const unsigned char* sg = c.stash + e.src_off + (b64 ? (long long)(c.row >> 6) * b64 * 2048 + (c.row & 63) * 16 : (long long)c.row * 16);
+  const long long sg_g = b64 ? 2048 : 4096;
   const int nl = c.a->non_linear;
   const int n_cols = e.n_cols, n_mma = e.n_mma, n_valid = e.n_valid, tcol = e.tmem_col;
   // the sign source of chunk k + 1 (hi plane of the stored activation) is in flight while chunk k is processed
   uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0;
   if (nl && c.cpart * 16 < n_cols) {
-    n0 = *reinterpret_cast<const uint4*>(sg + (long long)(2 * c.cpart) * 4096);
-    n1 = *reinterpret_cast<const uint4*>(sg + (long long)(2 * c.cpart + 1) * 4096);
+    n0 = *reinterpret_cast<const uint4*>(sg + (long long)(2 * c.cpart) * sg_g);
+    n1 = *reinterpret_cast<const uint4*>(sg + (long long)(2 * c.cpart + 1) * sg_g);
   }
   for (int ch = c.cpart; ch * 16 < n_cols; ch += c.parts) {
     const int col = ch * 16;
     const uint4 s0 = n0, s1 = n1;
     if (nl && (ch + c.parts) * 16 < n_cols) {
-      n0 = *reinterpret_cast<const uint4*>(sg + (long long)(2 * (ch + c.parts)) * 4096);
-      n1 = *reinterpret_cast<const uint4*>(sg + (long long)(2 * (ch + c.parts) + 1) * 4096);
+      n0 = *reinterpret_cast<const uint4*>(sg + (long long)(2 * (ch + c.parts)) * sg_g);
+      n1 = *reinterpret_cast<const uint4*>(sg + (long long)(2 * (ch + c.parts) + 1) * sg_g);
     }
     float v[16];
     if (col < n_mma) tc::tmem_ld16(taddr(c, tcol + col), v);
