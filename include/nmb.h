@@ -77,11 +77,13 @@ typedef struct {
   int32_t batch;                /* 256 in the reference (train script :116); no shuffle, last batch partial */
   uint64_t seed;                /* Philox key of the in-kernel eps stream */
   float lr, beta1, beta2, adam_eps; /* torch.optim.Adam defaults 1e-4, .9, .999, 1e-8 (cVAE.py:1111-1116) */
-  const float* lr_steps;        /* optional [>= total steps] per-step LR (nmmlp cyclic schedule :363-381) */
+  const float* lr_steps;        /* optional [n_lr_steps] per-step LR (nmmlp cyclic schedule :363-381) */
   float* params;                /* [n_params] packed, see NmbSlot */
   float* adam_m;                /* [n_params] exp_avg    */
   float* adam_v;                /* [n_params] exp_avg_sq */
   float* grads;                 /* [n_params] or NULL; written when NMB_TRAIN_WRITE_GRADS */
+  int64_t n_lr_steps;           /* entries of lr_steps; a train call that would step past it FAILS (no silent read
+                                   beyond the schedule).  Ignored when lr_steps is NULL. */
 } NmbMember;
 
 typedef struct NmbEnsemble NmbEnsemble;
@@ -137,6 +139,13 @@ enum {
 int nmb_ensemble_train(NmbEnsemble* ens, int64_t n_steps, const float* eps_override,
                        float* loss_out, uint32_t flags, void* stream);
 
+/* Whole epochs for members with DIFFERENT steps-per-epoch (folds of unequal size, e.g. after the healthy-control
+ * filter of multimodal_kfold_cvae_nmmlp.py:314): member i runs exactly n_epochs * ceil(n_rows_i / batch_i) steps --
+ * the `for epoch ... for batch` nest of the train script :177-199 -- in the same single launch.
+ *   loss_out : NULL or [n_members][n_epochs * max_i steps_per_epoch_i][3]; member i fills its first
+ *              n_epochs * steps_per_epoch_i rows, the rest is left untouched. */
+int nmb_ensemble_train_epochs(NmbEnsemble* ens, int64_t n_epochs, float* loss_out, uint32_t flags, void* stream);
+
 /* Stand-alone Adam update over a packed buffer: optimizer1.step() (torch.optim.Adam defaults,
  * cVAE.py:1111-1116) for the per-step nn.Module API, where forward/backward and step() are
  * separate calls.  t = 1-based step count.  Entries with zero gradient and zero state do not move,
@@ -152,6 +161,8 @@ int nmb_ensemble_peek(NmbEnsemble* ens, int32_t member, float* mu, float* logvar
                       void* stream);
 
 enum { NMB_RECON_MEAN = 0, NMB_RECON_SAMPLE = 1,
+       NMB_RECON_GIVEN_Z = 2 /* decoders only: eps[i] holds z itself [n_rows[i]][latent] -- Decoder.forward /
+                                cVAE.decode (cVAE.py:197-206, 426-428, 1135-1136); mu / logvar are not produced */,
        NMB_RECON_FP32 = 16 /* OR into `mode`: FP32 FFMA engine instead of the default tcgen05 (BF16x3) engine */ };
 /* Test-time reconstruction for every member on its own rows:
  *   mode MEAN   : decode(mu)                       -- cVAE.pred_recon, cVAE.py:549-555
@@ -185,6 +196,16 @@ int nmb_deviation(int32_t n_seg, const float* const* x, const int32_t* ldx,
                   const float* const* xhat, const float* const* stats, const int32_t* n_rows,
                   const int32_t* d, float* const* dev_roi, float* const* z,
                   float* const* dev_subj, void* stream);
+
+/* Latent-space normative deviation, the reference's own z-score (utils_vae.py:155-161):
+ *   z[i][k]  = (mu[i][k] - mean_t mu_train[t][k]) / sqrt(var_t mu_train[t][k] + exp(logvar[i][k]))   (np.var, ddof = 0)
+ *   dev[i]   = sum_k |z[i][k]| / latent                                       (latent_deviation :155-157)
+ * mu_train[s]: [n_train[s]][latent[s]] latent means of the reference (healthy-control training) rows; mu / logvar[s]:
+ * [n_rows[s]][latent[s]] of the scored rows (pred_latent returns exp(logvar), cVAE.py:540-547).
+ * out_z[s] ([n_rows][latent], separate_latent_deviation) and out_dev[s] ([n_rows]) may each be NULL. */
+int nmb_latent_deviation(int32_t n_seg, const float* const* mu_train, const int32_t* n_train,
+                         const float* const* mu, const float* const* logvar, const int32_t* n_rows,
+                         const int32_t* latent, float* const* out_z, float* const* out_dev, void* stream);
 
 /* ROC-AUC of every column of `scores[s]` ([n_rows][n_cols], row stride n_cols) against
  * binary labels[s] (uint8, 1 = patient): exact pair counting with tie half-credit

@@ -12,7 +12,7 @@ COMBINE = {"poe": 0, "gpoe": 1, "moe": 2, "mopoe": 3}
 LOSS = {"gauss_ll": 0, "neg_mse": 1}
 SLOT_ENC, SLOT_ENC_MEAN, SLOT_ENC_LOGVAR, SLOT_DEC, SLOT_DEC_MEAN, SLOT_LOGVAR_OUT, SLOT_ALPHA = range(7)
 TRAIN_NO_ADAM, TRAIN_WRITE_GRADS, TRAIN_KEEP_ACTS, TRAIN_FP32, TRAIN_TC_SIMPLE = 1, 2, 4, 8, 16
-RECON_MEAN, RECON_SAMPLE, RECON_FP32 = 0, 1, 16
+RECON_MEAN, RECON_SAMPLE, RECON_GIVEN_Z, RECON_FP32 = 0, 1, 2, 16
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libnmb.so")
 
@@ -32,7 +32,7 @@ class NmbMember(C.Structure):
     _fields_ = [("arch", NmbArch), ("xc", C.c_void_p * NMB_MAX_MOD), ("n_rows", C.c_int32), ("batch", C.c_int32),
                 ("seed", C.c_uint64), ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float),
                 ("adam_eps", C.c_float), ("lr_steps", C.c_void_p), ("params", C.c_void_p),
-                ("adam_m", C.c_void_p), ("adam_v", C.c_void_p), ("grads", C.c_void_p)]
+                ("adam_m", C.c_void_p), ("adam_v", C.c_void_p), ("grads", C.c_void_p), ("n_lr_steps", C.c_int64)]
 
 
 _PROTOS = {
@@ -49,6 +49,7 @@ _PROTOS = {
     "nmb_ensemble_engine": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_int32)]),
     "nmb_ensemble_steps_done": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]),
     "nmb_ensemble_train": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
+    "nmb_ensemble_train_epochs": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_uint32, C.c_void_p]),
     "nmb_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_float,
                                 C.c_float, C.c_float, C.c_float, C.c_void_p]),
     "nmb_ensemble_peek": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p),
@@ -62,6 +63,9 @@ _PROTOS = {
     "nmb_deviation": (C.c_int, [C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.POINTER(C.c_void_p),
                                 C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                 C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p]),
+    "nmb_latent_deviation": (C.c_int, [C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.POINTER(C.c_void_p),
+                                       C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                       C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p]),
     "nmb_auc": (C.c_int, [C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int32),
                           C.POINTER(C.c_int32), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p]),
     "nmb_mean_rows": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),

@@ -99,12 +99,16 @@ class _FusedStep(torch.autograd.Function):
             if g is not None and bool((g != 0).any()):
                 raise RuntimeError("the fused cVAE step only supports backward through losses['total'] "
                                    "(the reference's training loop, train script :198)")
-        scale = 1.0 if g_total is None else g_total.reshape(())
+        if g_total is None or bool((g_total.reshape(()) == 1).item()):
+            return (None, None) + tuple(ctx.grads)           # the views of the packed gradient buffer themselves
+        scale = g_total.reshape(())
         return (None, None) + tuple(None if g is None else g * scale for g in ctx.grads)
 
 
 class _FusedAdam(optim.Adam):
-    """``torch.optim.Adam`` surface (param_groups, zero_grad, state) whose step() is nmb_adam_step."""
+    """``torch.optim.Adam`` surface (param_groups, zero_grad, state, state_dict) whose step() is the
+    nmb_adam_step kernel.  exp_avg / exp_avg_sq live in module-owned packed buffers (they survive changes of the
+    minibatch size, ``.to(device)`` and ``torch.save``); ``state[p]`` exposes them as views."""
 
     def __init__(self, params, lr, owner):
         super().__init__(params, lr=lr)
@@ -114,19 +118,40 @@ class _FusedAdam(optim.Adam):
     def step(self, closure=None):
         self._owner._adam_step(self.param_groups[0])
 
+    def load_state_dict(self, state_dict):
+        """Restores step / exp_avg / exp_avg_sq INTO the packed buffers (the views in ``state`` stay linked)."""
+        own = self._owner
+        own._moments(own._require_cuda())
+        params = [p for g in self.param_groups for p in g["params"]]
+        for idx, st in state_dict.get("state", {}).items():
+            p = params[int(idx)]
+            if p in self.state and "exp_avg" in self.state[p]:
+                self.state[p]["exp_avg"].copy_(st["exp_avg"])
+                self.state[p]["exp_avg_sq"].copy_(st["exp_avg_sq"])
+                object.__setattr__(own, "_adam_t", int(st["step"]))
+        for g_new, g in zip(state_dict.get("param_groups", []), self.param_groups):
+            for k, v in g_new.items():
+                if k != "params":
+                    g[k] = v
+
 
 class _FusedBase(nn.Module):
-    """Shared engine: a one-member EnsembleTrainer holding packed copies of the parameters."""
+    """Shared engine plumbing of the two drop-in modules.
 
-    _combine_default = "poe"
+    Per-step training API: cached one-member EnsembleTrainers keyed by (combine, minibatch rows) -- a run with a
+    ragged last batch alternates between two engines, nothing is rebuilt per step -- with the Adam moments kept in
+    module-owned packed buffers.  Inference API (pred_recon / pred_latent / encode / decode): one cached engine per
+    combine rule; rows are passed per call."""
+
     _loss_kind = "gauss_ll"
-
-    def _names(self):
-        raise NotImplementedError
+    _ENGINE_KEYS = ("_engines", "_pending", "_last", "_views_cache")
 
     def _trainable(self):
         """(name in packed layout, Parameter) in optimizer1 order."""
         raise NotImplementedError
+
+    def _trainable_named(self):
+        return self._trainable()
 
     def _require_cuda(self):
         p = next(self.parameters())
@@ -134,90 +159,200 @@ class _FusedBase(nn.Module):
             raise RuntimeError("this cVAE runs only on CUDA (libnmb has no CPU fallback): call model.to('cuda')")
         return p.device
 
-    def _engine_for(self, xs, cs, combine):
-        dev = self._require_cuda()
-        xc = [pack_rows(x.to(dev), c.to(dev)) for x, c in zip(xs, cs)]
-        rows = xc[0].shape[0]
-        if rows > 256:
-            raise ValueError("a minibatch has at most 256 rows (train script :116)")
-        key = (combine.lower(), rows, str(dev))
-        eng = getattr(self, "_eng", None)
-        if eng is None or self._eng_key != key:
-            if eng is not None:
-                eng.close()
-            # the engine reads minibatches from its own persistent row buffers
-            bufs = [torch.empty_like(t) for t in xc]
-            spec = MemberSpec(self._dims, self._hidden, self.latent_dim, self.c_dim, bufs, combine=combine,
-                              loss_kind=self._loss_kind, non_linear=self._non_linear, batch=rows,
-                              lr=self.learning_rate)
-            eng = EnsembleTrainer([spec], device=dev, keep_grads=True)
-            object.__setattr__(self, "_eng", eng)
-            object.__setattr__(self, "_eng_key", key)
-            object.__setattr__(self, "_eng_xc", bufs)
-        for dst, src in zip(self._eng_xc, xc):
-            dst.copy_(src)
-        eng.load_state_dict(0, self._packed_state())
+    # ---- engines -------------------------------------------------------------------------------------------
+    def _cache(self):
+        c = self.__dict__.get("_engines")
+        if c is None:
+            c = {}
+            object.__setattr__(self, "_engines", c)
+        return c
+
+    def _make_engine(self, dev, dims, combine, rows, keep_grads, names=None):
+        bufs = [torch.zeros((rows, _lib.packed_row_stride(int(d), self.c_dim)), dtype=torch.float32, device=dev)
+                for d in dims]
+        spec = MemberSpec(dims, self._hidden, self.latent_dim, self.c_dim, bufs, combine=combine,
+                          loss_kind=self._loss_kind, non_linear=self._non_linear, batch=rows, lr=self.learning_rate)
+        eng = EnsembleTrainer([spec], device=dev, keep_grads=keep_grads)
+        eng._rows_buf = bufs
         return eng
 
-    def _packed_state(self):
-        return {k: p.detach() for k, p in self._trainable_named()}
+    def _load_weights(self, eng, named=None, rename=None):
+        """Current module parameters -> the engine's packed buffer (one multi-tensor copy)."""
+        views = eng.__dict__.setdefault("_pviews", eng._views(0, eng.params))
+        dst, src = [], []
+        for name, p in (named or self._trainable_named()):
+            k = rename(name) if rename else name
+            if k is None:
+                continue
+            dst.append(views[k]); src.append(p.detach().reshape(views[k].shape))
+        with torch.no_grad():
+            torch._foreach_copy_(dst, src)
 
+    def _train_engine(self, xs, cs, combine):
+        dev = self._require_cuda()
+        rows = int(xs[0].shape[0])
+        if rows > 256 or rows < 1:
+            raise ValueError("a minibatch has 1..256 rows (train script :116)")
+        key = ("train", combine.lower(), rows, str(dev))
+        eng = self._cache().get(key)
+        if eng is None:
+            eng = self._cache()[key] = self._make_engine(dev, self._dims, combine, rows, keep_grads=True)
+        for dst, x, c in zip(eng._rows_buf, xs, cs):
+            pack_rows(x.to(dev), c.to(dev), out=dst)
+        self._load_weights(eng)
+        return eng
+
+    def _infer_engine(self, combine):
+        dev = self._require_cuda()
+        key = ("infer", combine.lower(), str(dev))
+        eng = self._cache().get(key)
+        if eng is None:
+            eng = self._cache()[key] = self._make_engine(dev, self._dims, combine, 1, keep_grads=False)
+        self._load_weights(eng)
+        return eng
+
+    def close(self):
+        """Free every cached engine (they are also freed with the module)."""
+        for eng in self._cache().values():
+            eng.close()
+        self._cache().clear()
+
+    # ---- one fused forward + loss + backward launch ------------------------------------------------------------
     def _launch_step(self):
         eng, eps = self._pending
         eng.grads.zero_()
         losses = eng.train_steps(1, eps=eps[None, None], record_losses=True,
                                  flags=_lib.TRAIN_NO_ADAM | _lib.TRAIN_WRITE_GRADS | _lib.TRAIN_KEEP_ACTS)
         mu, lv, xr = eng.peek(0)
-        g = eng.state_dict(0, "grads")
-        grads = []
-        for name, p in self._trainable_named():
-            grads.append(g[name].reshape(p.shape))
+        gviews = eng.__dict__.setdefault("_gviews", eng._views(0, eng.grads))
+        grads = [gviews[name].view(p.shape) for name, p in self._trainable_named()]       # views, nothing is copied
         lo = losses[0, 0]
         return [lo[0].reshape(1), lo[1].reshape(()), lo[2].reshape(1), mu, lv] + list(xr), grads
 
     def _fused_forward(self, xs, cs, combine):
-        eng = self._engine_for(xs, cs, combine)
+        eng = self._train_engine(xs, cs, combine)
         rows = xs[0].shape[0]
-        # the reference draws eps with randn_like(mu) from the global generator (cVAE.py:1132)
+        # the reference draws eps with randn_like(mu) from the global generator (cVAE.py:420, 1132)
         eps = torch.randn((rows, self.latent_dim), device=xs[0].device if xs[0].is_cuda else eng.device,
                           dtype=torch.float32)
         object.__setattr__(self, "_pending", (eng, eps.to(eng.device)))
         params = [p for _, p in self._trainable_named()]
-        outs = _FusedStep.apply(self, 0, *params)
-        return outs
+        return _FusedStep.apply(self, 0, *params)
+
+    def _remember(self, fwd_rtn, losses, key):
+        object.__setattr__(self, "_last", (fwd_rtn[key], losses))
+
+    def _losses_of(self, fwd_rtn, key):
+        last = self.__dict__.get("_last")
+        if last is None:
+            raise RuntimeError("loss_function called before forward")
+        if not isinstance(fwd_rtn, dict) or fwd_rtn.get(key) is not last[0]:
+            raise ValueError("fwd_rtn is not the result of this module's LAST forward pass: the fused kernel computes "
+                             "the losses together with the forward pass, so only that pass can be scored")
+        return dict(last[1])
+
+    # ---- optimizer1.step() --------------------------------------------------------------------------------------
+    def _moments(self, dev):
+        """Module-owned packed exp_avg / exp_avg_sq (layout of nmb_arch_slots) and their per-parameter views."""
+        m = self.__dict__.get("_adam_m")
+        if m is None:
+            arch = _lib.make_arch(self._dims, self._hidden, self.latent_dim, self.c_dim, "poe", self._loss_kind,
+                                  self._non_linear)
+            n = _lib.arch_param_count(arch)
+            object.__setattr__(self, "_adam_m", torch.zeros(n, dtype=torch.float32, device=dev))
+            object.__setattr__(self, "_adam_v", torch.zeros(n, dtype=torch.float32, device=dev))
+            object.__setattr__(self, "_adam_t", 0)
+        elif m.device != dev:                                  # the module was moved / unpickled on another device
+            object.__setattr__(self, "_adam_m", self._adam_m.to(dev))
+            object.__setattr__(self, "_adam_v", self._adam_v.to(dev))
+            self.__dict__.pop("_views_cache", None)
+        return self._adam_m, self._adam_v
 
     def _adam_step(self, group):
-        eng = getattr(self, "_eng", None)
-        if eng is None:
+        last = self.__dict__.get("_pending")
+        if last is None:
             raise RuntimeError("optimizer1.step() called before any forward pass")
+        eng = last[0]
         named = list(self._trainable_named())
-        # gradients as the user left them (zero_grad / backward), packed into the engine layout
-        eng.grads.zero_()
-        gviews = eng._views(0, eng.grads)
-        pviews = eng._views(0, eng.params)
+        m, v = self._moments(eng.device)
+        pviews = eng.__dict__.setdefault("_pviews", eng._views(0, eng.params))
+        gviews = eng.__dict__.setdefault("_gviews", eng._views(0, eng.grads))
+        # gradients as the user left them (zero_grad / backward).  backward() hands out views of eng.grads, so in the
+        # reference loop nothing is copied here; parameters without a gradient do not move (torch skips grad=None).
         for name, p in named:
-            pviews[name].copy_(p.detach().reshape(pviews[name].shape))
-            if p.grad is not None:
-                gviews[name].copy_(p.grad.reshape(gviews[name].shape))
-        t = getattr(self, "_adam_t", 0) + 1
+            gv = gviews[name]
+            if p.grad is None:
+                gv.zero_()
+            elif p.grad.data_ptr() != gv.data_ptr():
+                gv.copy_(p.grad.reshape(gv.shape))
+        self._load_weights(eng, named)
+        t = self._adam_t + 1
         object.__setattr__(self, "_adam_t", t)
         b1, b2 = group["betas"]
         with torch.cuda.device(eng.device):
-            _lib.check(eng.lib.nmb_adam_step(eng.params.data_ptr(), eng.grads.data_ptr(), eng.adam_m.data_ptr(),
-                                             eng.adam_v.data_ptr(), eng.total_params, t, float(group["lr"]),
-                                             float(b1), float(b2), float(group["eps"]), _stream_ptr(eng.device)),
-                       "nmb_adam_step")
+            _lib.check(eng.lib.nmb_adam_step(eng.params.data_ptr(), eng.grads.data_ptr(), m.data_ptr(), v.data_ptr(),
+                                             eng.total_params, t, float(group["lr"]), float(b1), float(b2),
+                                             float(group["eps"]), _stream_ptr(eng.device)), "nmb_adam_step")
+        torch._foreach_copy_([p.data for _, p in named], [pviews[name].reshape(p.shape) for name, p in named])
+        # torch.optim.Adam-shaped state (views of the packed moments), so state_dict() is meaningful
+        vc = self.__dict__.get("_views_cache")
+        if vc is None:
+            vc = (eng._views(0, m), eng._views(0, v))
+            object.__setattr__(self, "_views_cache", vc)
+        st = self.optimizer1.state
         for name, p in named:
-            p.copy_(pviews[name].reshape(p.shape))
-
-    def _trainable_named(self):
-        return self._trainable()
+            st[p] = {"step": torch.tensor(float(t)), "exp_avg": vc[0][name].view(p.shape),
+                     "exp_avg_sq": vc[1][name].view(p.shape)}
 
     def __getstate__(self):      # torch.save(model): engines are not picklable and are rebuilt lazily
         d = self.__dict__.copy()
-        for k in ("_eng", "_eng_key", "_eng_xc", "_pending"):
+        for k in self._ENGINE_KEYS:
             d.pop(k, None)
         return d
+
+    def __setstate__(self, state):
+        """Also accepts a module pickled by the REFERENCE (``cVAE.cVAE`` / ``cVAE.cVAE_multimodal`` through the root
+        ``cVAE.py`` shim): the private fields of the drop-in are derived from the reference's public attributes."""
+        self.__dict__.update(state)
+        if "_dims" not in self.__dict__:
+            dims = self.__dict__.get("input_dim_list")
+            self._dims = [int(d) for d in dims[: self.modalities]] if dims is not None else [int(self.input_dim)]
+            self._hidden = [int(h) for h in list(self.hidden_dim)[:-1]]
+            mods = self._modules
+            enc = mods["encoder_list"][0] if "encoder_list" in mods else mods["encoder"]
+            self._non_linear = bool(getattr(enc, "non_linear", True))
+            opt = self.__dict__.get("optimizer1")
+            if opt is not None and not isinstance(opt, _FusedAdam):       # the reference's torch.optim.Adam
+                lr = opt.param_groups[0]["lr"]
+                self.__dict__["optimizer1"] = _FusedAdam([p for _, p in self._trainable_named()], lr=lr, owner=self)
+
+
+def _as_float_cuda(a, dev):
+    a = getattr(a, "values", a)
+    return torch.as_tensor(np.asarray(a) if not torch.is_tensor(a) else a).to(device=dev, dtype=torch.float32)
+
+
+def fuse_latent(mus, variances, combine, alphas=None):
+    """``combine_latent`` (cVAE.py:1144-1164) with ProductOfExperts (:993-998), MixtureOfExperts (:1007-1011) and
+    MoPoE (:1072-1083) as plain tensor ops on the caller's device (the training and scoring kernels carry their own
+    fused implementation, csrc/nmb_fusion.cuh; this is the stand-alone method of the reference's API).
+    mus, variances: [M, B, Z]."""
+    kind = combine.lower()
+    m = mus.shape[0]
+    if kind == "poe":
+        t = 1.0 / variances
+        return torch.sum(mus * t, dim=0) / torch.sum(t, dim=0), 1.0 / torch.sum(t, dim=0)
+    if kind == "gpoe":
+        a = torch.softmax(torch.stack([p for p in alphas]), dim=0).reshape(m, 1, 1)
+        return (torch.sum(mus * a / variances, dim=0) / torch.sum(a / variances, dim=0),
+                1 / torch.sum(a / variances, dim=0))
+    if kind == "moe":
+        return torch.sum(mus, dim=0) / m, torch.sum(variances, dim=0) / m
+    if kind == "mopoe":
+        t = 1.0 / variances
+        p_mu, p_var = torch.sum(mus * t, dim=0) / torch.sum(t, dim=0), 1.0 / torch.sum(t, dim=0)
+        return (torch.sum(mus, dim=0) + p_mu) / (m + 1), (torch.sum(variances, dim=0) + p_var) / (m + 1)
+    raise ValueError("No such combination method")
 
 
 class cVAE(_FusedBase):
@@ -235,6 +370,9 @@ class cVAE(_FusedBase):
         self.discriminator = Discriminator(input_dim, self.hidden_dim, c_dim, non_linear)
         self.optimizer1 = _FusedAdam(list(self.encoder.parameters()) + list(self.decoder.parameters()),
                                      lr=learning_rate, owner=self)
+        # cVAE.py:412-413: the (never stepped) optimisers of the adversarial pieces, kept for attribute parity
+        self.optimizer2 = optim.Adam(list(self.discriminator.parameters()), lr=learning_rate)
+        self.optimizer3 = optim.Adam(list(self.encoder.parameters()), lr=learning_rate)
 
     def _trainable(self):
         for k, p in self.encoder.named_parameters():
@@ -242,21 +380,45 @@ class cVAE(_FusedBase):
         for k, p in self.decoder.named_parameters():
             yield "decoder_list.0." + k, p
 
-    def _packed_state(self):
-        sd = super()._packed_state()
-        sd["alpha_m_list.0"] = torch.zeros(1)
-        return sd
-
+    # ---- the training-loop surface (cVAE.py:435-443, 491-504) ------------------------------------------
     def forward(self, x, c):
         self.zero_grad()
         total, kl, ll, mu, logvar, xr = self._fused_forward([x], [c], "poe")
         scale = self.decoder.logvar_out.detach().exp().pow(0.5)
-        object.__setattr__(self, "_last_losses", {"total": total, "kl": kl, "ll": ll})
-        return {"x_recon": Normal(loc=xr, scale=scale), "mu": mu, "logvar": logvar}
+        fwd = {"x_recon": Normal(loc=xr, scale=scale), "mu": mu, "logvar": logvar}
+        self._remember(fwd, {"total": total, "kl": kl, "ll": ll}, "mu")
+        return fwd
 
     def loss_function(self, x, fwd_rtn):
-        """{'total','kl','ll'} of the forward pass that produced fwd_rtn (cVAE.py:491-504)."""
-        return dict(self._last_losses)
+        """{'total','kl','ll'} of the forward pass that produced fwd_rtn (cVAE.py:491-504); any other fwd_rtn is
+        refused with ValueError."""
+        return self._losses_of(fwd_rtn, "mu")
+
+    # ---- pieces (cVAE.py:415-433): inference-time calls into the kernels, no autograd graph -----------------
+    def _packed(self, x, c, dev):
+        c_t = _as_float_cuda(c, dev)
+        x_t = _as_float_cuda(x, dev) if x is not None else torch.zeros((c_t.shape[0], self.input_dim), device=dev)
+        return [pack_rows(x_t, c_t)]
+
+    def encode(self, x, c):
+        """(mu, logvar) of Encoder.forward (cVAE.py:415-416)."""
+        dev = self._require_cuda()
+        _, mu, lv = self._infer_engine("poe").reconstruct([self._packed(x, c, dev)], mode="mean", want_latent=True,
+                                                           want_xhat=False)
+        return mu[0], lv[0]
+
+    def reparameterise(self, mu, logvar):
+        """cVAE.py:418-421; eps from the global torch generator (randn_like), like the reference."""
+        std = torch.exp(0.5 * logvar)
+        eps = torch.randn_like(mu)
+        return mu + eps * std
+
+    def decode(self, z, c):
+        """Decoder.forward (cVAE.py:426-427): Normal(decoder_mean_layer(...), exp(logvar_out)^0.5)."""
+        dev = self._require_cuda()
+        xhat, _, _ = self._infer_engine("poe").reconstruct([self._packed(None, c, dev)], mode="decode",
+                                                            eps=[_as_float_cuda(z, dev)])
+        return Normal(loc=xhat[0][0], scale=self.decoder.logvar_out.detach().exp().pow(0.5))
 
     def calc_kl(self, mu, logvar):
         return -0.5 * torch.sum(1 + logvar - mu.pow(2) - logvar.exp(), dim=1).mean(0)
@@ -264,33 +426,28 @@ class cVAE(_FusedBase):
     def calc_ll(self, x, x_recon):
         return compute_ll(x, x_recon)
 
-    def _recon(self, x, c, mode):
+    def _recon(self, x, c, mode, want_xhat=True):
         dev = self._require_cuda()
-        xc = [pack_rows(torch.as_tensor(np.asarray(x), dtype=torch.float32).to(dev),
-                        torch.as_tensor(np.asarray(c)).to(dev))]
-        sd = self._packed_state()
-        eng = EnsembleTrainer([MemberSpec(self._dims, self._hidden, self.latent_dim, self.c_dim, xc,
-                                          non_linear=self._non_linear, state_dict=sd)], device=dev)
-        out = eng.reconstruct([xc], mode=mode, want_latent=True)
+        out = self._infer_engine("poe").reconstruct([self._packed(x, c, dev)], mode=mode, want_latent=True,
+                                                     want_xhat=want_xhat)
         torch.cuda.synchronize(dev)
-        eng.close()
         return out
 
     def pred_latent(self, x, c, DEVICE=None):
         """(mu, exp(logvar)) as numpy (cVAE.py:540-547)."""
-        x = x.to_numpy() if hasattr(x, "to_numpy") else x
-        _, mu, lv = self._recon(x, c, "mean")
+        _, mu, lv = self._recon(x, c, "mean", want_xhat=False)
         return mu[0].cpu().numpy(), lv[0].exp().cpu().numpy()
 
     def pred_recon(self, x, c, DEVICE=None):
         """Decode the latent MEAN (cVAE.py:549-555)."""
-        x = x.to_numpy() if hasattr(x, "to_numpy") else x
         xhat, _, _ = self._recon(x, c, "mean")
         return xhat[0][0].cpu().numpy()
 
 
 class cVAE_multimodal(_FusedBase):
     """M encoders + M decoders with latent fusion (cVAE.py:1087-1211)."""
+
+    _rng_order = "cvae"          # alphas, encoders, decoders (cVAE.py:1107-1109)
 
     def __init__(self, input_dim_list, hidden_dim, latent_dim, c_dim, learning_rate=0.0001, modalities=3,
                  non_linear=False):
@@ -300,17 +457,24 @@ class cVAE_multimodal(_FusedBase):
         self.latent_dim, self.c_dim, self.modalities, self.learning_rate = latent_dim, c_dim, modalities, learning_rate
         self._dims = [int(d) for d in input_dim_list[:modalities]]
         self._hidden, self._non_linear = list(hidden_dim), bool(non_linear)
-        # RNG order of cVAE.py:1107-1109: alphas, encoders, decoders
-        self.alpha_m_list = nn.ParameterList(
-            [nn.Parameter(torch.randn(1, requires_grad=True)) for _ in range(modalities)])
+        if self._rng_order == "cvae":
+            self.alpha_m_list = nn.ParameterList(
+                [nn.Parameter(torch.randn(1, requires_grad=True)) for _ in range(modalities)])
         self.encoder_list = nn.ModuleList(
             [Encoder(input_dim_list[i], self.hidden_dim, c_dim, non_linear) for i in range(modalities)])
         self.decoder_list = nn.ModuleList(
             [Decoder(input_dim_list[i], self.hidden_dim, c_dim, non_linear) for i in range(modalities)])
+        if self._rng_order != "cvae":
+            self.alpha_m_list = nn.ParameterList(
+                [nn.Parameter(torch.randn(1, requires_grad=True)) for _ in range(modalities)])
+        self._extra_init()
         self.optimizer1 = _FusedAdam(
             [p for m in self.encoder_list for p in m.parameters()]
             + [p for m in self.decoder_list for p in m.parameters()]
             + list(self.alpha_m_list.parameters()), lr=learning_rate, owner=self)
+
+    def _extra_init(self):
+        pass
 
     def _trainable(self):
         for i, m in enumerate(self.encoder_list):
@@ -322,6 +486,7 @@ class cVAE_multimodal(_FusedBase):
         for i, p in enumerate(self.alpha_m_list):
             yield f"alpha_m_list.{i}", p
 
+    # ---- the training-loop surface (cVAE.py:1166-1196) --------------------------------------------------
     def forward_multimodal(self, xes, cs, combine):
         self.zero_grad()
         _lib.make_arch(self._dims, self._hidden, self.latent_dim, self.c_dim, combine)   # ValueError if unknown
@@ -329,12 +494,69 @@ class cVAE_multimodal(_FusedBase):
         total, kl, ll, mu, logvar = outs[:5]
         x_recons = [Normal(loc=outs[5 + i], scale=self.decoder_list[i].logvar_out.detach().exp().pow(0.5))
                     for i in range(self.modalities)]
-        object.__setattr__(self, "_last_losses", {"total": total, "kl": kl, "ll": ll})
-        return {"x_recons": x_recons, "mu_multimodal": mu, "logvar_multimodal": logvar}
+        fwd = {"x_recons": x_recons, "mu_multimodal": mu, "logvar_multimodal": logvar}
+        self._remember(fwd, {"total": total, "kl": kl, "ll": ll}, "mu_multimodal")
+        return fwd
 
-    def loss_function_multimodal(self, xes, fwd_rtn):
-        """sum_m (kl - ll_m) of the forward pass that produced fwd_rtn (cVAE.py:1187-1196)."""
-        return dict(self._last_losses)
+    def loss_function_multimodal(self, xes, fwd_rtn, labels=None):
+        """sum_m (kl - ll_m) of the forward pass that produced fwd_rtn (cVAE.py:1187-1196); any other fwd_rtn is
+        refused with ValueError.  `labels` is accepted (and ignored) for the nmmlp class, whose signature has it."""
+        return self._losses_of(fwd_rtn, "mu_multimodal")
+
+    # ---- pieces (cVAE.py:1127-1164): inference-time calls into the kernels, no autograd graph ------------------
+    def _modality_engine(self, m):
+        """One-modality engine holding encoder m / decoder m (for encode / decode of a single modality)."""
+        dev = self._require_cuda()
+        key = ("mod", m, str(dev))
+        eng = self._cache().get(key)
+        if eng is None:
+            eng = self._cache()[key] = self._make_engine(dev, [self._dims[m]], "poe", 1, keep_grads=False)
+        pre_e, pre_d = f"encoder_list.{m}.", f"decoder_list.{m}."
+
+        def rename(name):
+            if name.startswith(pre_e):
+                return "encoder_list.0." + name[len(pre_e):]
+            if name.startswith(pre_d):
+                return "decoder_list.0." + name[len(pre_d):]
+            return None
+        self._load_weights(eng, rename=rename)
+        return eng, dev
+
+    def encode(self, x, c, m):
+        """(mu, logvar) of encoder m (cVAE.py:1127-1128)."""
+        eng, dev = self._modality_engine(m)
+        xc = [pack_rows(_as_float_cuda(x, dev), _as_float_cuda(c, dev))]
+        _, mu, lv = eng.reconstruct([xc], mode="mean", want_latent=True, want_xhat=False)
+        return mu[0], lv[0]
+
+    def reparameterise(self, mu, logvar):
+        """cVAE.py:1130-1133."""
+        std = torch.exp(0.5 * logvar)
+        eps = torch.randn_like(mu)
+        return mu + eps * std
+
+    def decode(self, z, c, m):
+        """Normal of decoder m (cVAE.py:1135-1136)."""
+        eng, dev = self._modality_engine(m)
+        c_t = _as_float_cuda(c, dev)
+        xc = [pack_rows(torch.zeros((c_t.shape[0], self._dims[m]), device=dev), c_t)]
+        xhat, _, _ = eng.reconstruct([xc], mode="decode", eps=[_as_float_cuda(z, dev)])
+        return Normal(loc=xhat[0][0], scale=self.decoder_list[m].logvar_out.detach().exp().pow(0.5))
+
+    def product_of_experts(self, mus, variances):
+        return fuse_latent(mus, variances, "poe")
+
+    def mixture_of_experts(self, mus, variances):
+        return fuse_latent(mus, variances, "moe")
+
+    def mixture_of_product_of_experts(self, mus, variances):
+        return fuse_latent(mus, variances, "mopoe")
+
+    def combine_latent(self, mus, variances, combine):
+        """cVAE.py:1144-1164 (case-insensitive; ValueError('No such combination method') otherwise)."""
+        if self.modalities == 1 and self._rng_order == "cvae":
+            return mus[0], variances[0]                      # :1145-1146
+        return fuse_latent(mus, variances, combine, list(self.alpha_m_list))
 
     def calc_kl(self, mu, logvar):
         return -0.5 * torch.sum(1 + logvar - mu.pow(2) - logvar.exp(), dim=1).mean(0)
@@ -345,15 +567,11 @@ class cVAE_multimodal(_FusedBase):
     def pred_recon(self, xes, c, DEVICE=None, combine="poe"):
         """Test-time reconstruction; z is SAMPLED with torch.randn like the reference (cVAE.py:1198-1208)."""
         dev = self._require_cuda()
-        c_t = torch.as_tensor(np.asarray(c)).to(dev)
-        xc = [pack_rows(torch.as_tensor(np.asarray(getattr(x, "values", x)), dtype=torch.float32).to(dev), c_t)
-              for x in xes[: self.modalities]]
-        eng = EnsembleTrainer([MemberSpec(self._dims, self._hidden, self.latent_dim, self.c_dim, xc, combine=combine,
-                                          non_linear=self._non_linear, state_dict=self._packed_state())], device=dev)
+        c_t = _as_float_cuda(c, dev)
+        xc = [pack_rows(_as_float_cuda(x, dev), c_t) for x in xes[: self.modalities]]
         eps = torch.randn((xc[0].shape[0], self.latent_dim), dtype=torch.float32)   # CPU generator, like :1207
-        xhat, _, _ = eng.reconstruct([xc], mode="sample", eps=[eps.to(dev)])
+        xhat, _, _ = self._infer_engine(combine).reconstruct([xc], mode="sample", eps=[eps.to(dev)])
         torch.cuda.synchronize(dev)
-        eng.close()
         return [t.cpu().numpy() for t in xhat[0]]
 
     def reconstruction_deviation_multimodal(self, xes, x_preds):
@@ -368,5 +586,34 @@ class cVAE_multimodal(_FusedBase):
         model = cls(list(s.input_dims), list(s.hidden), s.latent, s.c_dim, learning_rate=s.lr,
                     modalities=len(s.input_dims), non_linear=s.non_linear)
         sd = trainer.state_dict(i)
-        model.load_state_dict({k: v.cpu() for k, v in sd.items()})
+        model.load_state_dict({k: v.cpu() for k, v in sd.items()}, strict=False)
         return model.to(trainer.device)
+
+
+class cVAE_multimodal_endtoend(cVAE_multimodal):
+    """The model class defined inside multimodal_kfold_cvae_nmmlp.py (:39-245): same encoders / decoders / fusion,
+    reconstruction term -MSE(mean) (:124-127), torch-RNG order encoders -> decoders -> alphas -> MLP (:57-83).  The MLP
+    "diagnosis" head is constructed (it consumes RNG and appears in the state_dict) but, as in the reference, never
+    called and not in optimizer1 (:92-98)."""
+
+    _rng_order = "nmmlp"
+    _loss_kind = "neg_mse"
+
+    def _extra_init(self):
+        self.total_input_size = sum(self._dims)
+        self.mlp = nn.Sequential(nn.Linear(self.total_input_size, 128), nn.ReLU(), nn.Linear(128, 64), nn.ReLU(),
+                                 nn.Linear(64, 1), nn.Sigmoid())
+        self.criterion = nn.BCELoss()
+
+    def calc_ll(self, x, x_recon):
+        return -nn.MSELoss(reduction="mean")(x_recon.loc, x)
+
+    def pred_recon(self, xes, c, DEVICE=None, combine="poe"):
+        """nmmlp :212-233: like cVAE_multimodal.pred_recon but eps is drawn on the model's device (randn_like)."""
+        dev = self._require_cuda()
+        c_t = _as_float_cuda(c, dev)
+        xc = [pack_rows(_as_float_cuda(x, dev), c_t) for x in xes[: self.modalities]]
+        eps = torch.randn((xc[0].shape[0], self.latent_dim), dtype=torch.float32, device=dev)
+        xhat, _, _ = self._infer_engine(combine).reconstruct([xc], mode="sample", eps=[eps])
+        torch.cuda.synchronize(dev)
+        return [t.cpu().numpy() for t in xhat[0]]

@@ -11,7 +11,15 @@ families per fold, concatenated copies under ``deviation/supervised_cvae/<R>/<P>
 
 Extra flags (not in the reference): ``--ensemble-seeds`` (train several seeds per fold in the same
 launch; seed 0 is the one written to ``cVAE_model.pkl``), ``--nmmlp`` (the -MSE / healthy-only /
-cyclic-LR variant of multimodal_kfold_cvae_nmmlp.py).
+cyclic-LR variant of multimodal_kfold_cvae_nmmlp.py; the program with the reference's positional
+``action`` is ``nmmlp_main``).
+
+Deliberate deviations from the reference scripts (all documented in DESIGN.md):
+* deviations in the CSV files come from the fp32 deviation kernel on the packed fp32 rows; the reference
+  subtracts its fp32 prediction from the float64 scaled frame on the host (test script :112-141), so values agree
+  to ~1e-7 relative, not bit for bit;
+* members of one run whose folds have different row counts train exactly ``epochs`` passes over their own rows
+  (nmb_ensemble_train_epochs), like the per-fold loops of the reference.
 """
 from __future__ import annotations
 
@@ -26,7 +34,7 @@ import torch
 from sklearn.preprocessing import RobustScaler
 
 from . import scoring
-from .cVAE import cVAE_multimodal
+from .cVAE import cVAE_multimodal, cVAE_multimodal_endtoend
 from .ensemble import EnsembleTrainer, MemberSpec, pack_rows
 from .pipeline import covariate_onehots
 from .utils import generate_kfold_ids, get_column_name, get_datasets_name, get_hc_label, load_dataset
@@ -106,65 +114,68 @@ def train_main(args, root=None):
     if args.model != "cVAE_multimodal":
         raise ValueError(f"Model '{args.model}' is not recognized. Available models are: cVAE_multimodal")
     dev = _device()
+    nmmlp = bool(getattr(args, "nmmlp", False))
+    n_seeds = int(getattr(args, "ensemble_seeds", 1))
+    model_cls = cVAE_multimodal_endtoend if nmmlp else cVAE_multimodal
     participants_path, kfold_dir, model_dir = _paths(root, args.dataset_resourse)
     np.random.seed(42)                                       # train script :41-44
     rn.seed(42)
     names = get_datasets_name(args.dataset_resourse, args.procedure)
     ids_df = pd.read_csv(participants_path)
     hc_label = get_hc_label(args.dataset_resourse)
-    label = hc_label if args.training_class == "nm" else 0
-    generate_kfold_ids(ids_df[ids_df["DIA"] == label], ids_df[ids_df["DIA"] != label],
+    label = hc_label if getattr(args, "training_class", "nm") == "nm" else 0
+    # train script :53-66 splits training class vs everyone else; nmmlp :296-299 HC vs DIA == 0
+    other = ids_df[ids_df["DIA"] == 0] if nmmlp else ids_df[ids_df["DIA"] != label]
+    generate_kfold_ids(ids_df[ids_df["DIA"] == label], other,
                        oversample_percentage=args.oversample_percentage, n_splits=args.n_splits, kfold_dir=kfold_dir)
     h_dim, z_dim = list(args.hz_para_list[:-1]), int(args.hz_para_list[-1])
-    specs, dims = [], None
+    dims = [len(get_column_name(args.dataset_resourse, n)) for n in names]
+    specs = []
     for fold in range(args.n_splits):
         (model_dir / f"{fold:03d}").mkdir(exist_ok=True)
-        xc, n_samples = [], None
+        xs, c, n_samples = [], None, None
         for name, (tr, _) in _fold_frames(root, args, fold, names, kfold_dir, participants_path).items():
-            if args.nmmlp:
+            if nmmlp:
                 tr = tr.loc[tr["DIA"] == hc_label]                       # nmmlp :314
             x = RobustScaler().fit_transform(tr[get_column_name(args.dataset_resourse, name)].values)
-            c = covariate_onehots(tr)
-            xc.append(pack_rows(torch.from_numpy(x.astype(np.float32)).to(dev), torch.from_numpy(c).to(dev)))
+            c = covariate_onehots(tr)                         # every modality feeds its own frame's one-hots (:126)
+            xs.append(pack_rows(torch.from_numpy(x.astype(np.float32)).to(dev), torch.from_numpy(c).to(dev)))
             n_samples = x.shape[0]
-        dims = [int(t.shape[1]) for t in xc]
-        dims = [len(get_column_name(args.dataset_resourse, n)) for n in names]
         spe = -(-n_samples // 256)
         lr_steps = None
-        if args.nmmlp:
+        if nmmlp:
             lr_steps = torch.from_numpy(cyclic_lr_schedule(args.epochs * spe, n_samples)).to(dev)
-        for s in range(args.ensemble_seeds):
-            torch.manual_seed(42 + s)                         # train script :119 (seed 42 for member 0)
-            init = cVAE_multimodal(dims, h_dim, z_dim, 29, learning_rate=0.0001, modalities=len(names),
-                                   non_linear=True).state_dict()
-            specs.append(MemberSpec(dims, h_dim, z_dim, 29, xc, combine=args.combine,
-                                    loss_kind="neg_mse" if args.nmmlp else "gauss_ll", batch=256,
-                                    seed=(42 + s) * 1000003 + fold, lr=0.0001, lr_steps=lr_steps,
-                                    state_dict={k: v.detach().clone() for k, v in init.items()}, tag=(fold, s)))
+        for s_ in range(n_seeds):
+            torch.manual_seed(42 + s_)                        # train script :119 (seed 42 for member 0)
+            init = model_cls(dims, h_dim, z_dim, 29, learning_rate=0.0001, modalities=len(names),
+                             non_linear=True).state_dict()
+            specs.append(MemberSpec(dims, h_dim, z_dim, 29, xs, combine=args.combine,
+                                    loss_kind="neg_mse" if nmmlp else "gauss_ll", batch=256,
+                                    seed=(42 + s_) * 1000003 + fold, lr=0.0001, lr_steps=lr_steps,
+                                    state_dict={k: v.detach().clone() for k, v in init.items() if not k.startswith("mlp.")},
+                                    tag=(fold, s_)))
     print("train model")
     trainer = EnsembleTrainer(specs, device=dev)
     spe = trainer.steps_per_epoch
-    if len(set(spe)) == 1:
-        losses = trainer.train_steps(args.epochs * spe[0], record_losses=True).cpu().numpy()
-    else:                                                     # folds with different row counts
-        losses = None
-        for e in range(args.epochs):
-            trainer.train_steps(max(spe))
+    # every member takes exactly `epochs` passes over its OWN rows, whatever its fold size (one launch)
+    losses = trainer.train_epochs(args.epochs, record_losses=True).cpu().numpy()
     torch.cuda.synchronize(dev)
+    logs = []
     for i, s in enumerate(specs):
         fold, seed = s.tag
         fold_dir = model_dir / f"{fold:03d}"
-        if losses is not None:
-            log = losses[i, :: spe[i]]                        # batch 0 of every epoch (train script :201)
-            pd.DataFrame(log, columns=["total", "kl", "ll"]).to_csv(fold_dir / f"losses_seed{seed}.csv", index=False)
-            if seed == 0:
-                for e in (0, len(log) - 1):
-                    print("Train Epoch:%d Train batch: 0 total: %.3f, kl: %.3f, ll: %.3f" % (e, *log[e]))
+        log = losses[i, : args.epochs * spe[i] : spe[i]]       # batch 0 of every epoch (train script :201)
+        logs.append(log)
+        pd.DataFrame(log, columns=["total", "kl", "ll"]).to_csv(fold_dir / f"losses_seed{seed}.csv", index=False)
         if seed == 0:
-            torch.save(cVAE_multimodal.from_ensemble(trainer, i).cpu(), fold_dir / "cVAE_model.pkl")
+            for e in (0, len(log) - 1):
+                print("Train Epoch:%d Train batch: 0 total: %.3f, kl: %.3f, ll: %.3f" % (e, *log[e]))
+            model = model_cls.from_ensemble(trainer, i).cpu()
+            model.close()
+            torch.save(model, fold_dir / "cVAE_model.pkl")
             print("file saved at ", fold_dir / "cVAE_model.pkl")
     trainer.close()
-    return losses
+    return np.stack(logs)
 
 
 def test_main(args, root=None):
@@ -179,6 +190,7 @@ def test_main(args, root=None):
     names = get_datasets_name(args.dataset_resourse, args.procedure)
     if args.combine is None:
         raise ValueError(f"Unknown procedure: {args.procedure}")
+    nmmlp = bool(getattr(args, "nmmlp", False))
     specs, test_xc, test_frames, test_x64 = [], [], [], []
     for fold in range(args.n_splits):
         fold_dir = model_dir / f"{fold:03d}"
@@ -187,16 +199,25 @@ def test_main(args, root=None):
             raise FileNotFoundError(f"{path}: train the model first")
         model = torch.load(path, weights_only=False)
         xcs, frames, x64 = [], [], []
+        hc_only = bool(getattr(args, "nmmlp", False))
+        hc_label = get_hc_label(args.dataset_resourse)
+        c = None
         for name, (tr, te) in _fold_frames(root, args, fold, names, kfold_dir, participants_path).items():
             cols = get_column_name(args.dataset_resourse, name)
+            if hc_only:
+                tr = tr.loc[tr["DIA"] == hc_label]             # nmmlp :455
             scaler = RobustScaler().fit(tr[cols].values)       # fitted on TRAIN (test script :83-90)
-            x = scaler.transform(te[cols].values)
+            x64.append(scaler.transform(te[cols].values))
             c = covariate_onehots(te)                          # from the TEST set's own ranks (:93-97)
-            xcs.append(pack_rows(torch.from_numpy(x.astype(np.float32)).to(dev), torch.from_numpy(c).to(dev)))
-            frames.append(te); x64.append(x)
+            frames.append(te)
+        # every modality is decoded with the LAST modality's one-hots, like the reference (test script :102, :109)
+        c_dev = torch.from_numpy(c).to(dev)
+        xcs = [pack_rows(torch.from_numpy(x.astype(np.float32)).to(dev), c_dev) for x in x64]
         dims = [len(get_column_name(args.dataset_resourse, n)) for n in names]
         specs.append(MemberSpec(dims, list(args.hz_para_list[:-1]), int(args.hz_para_list[-1]), 29, xcs,
-                                combine=args.combine, state_dict=model.state_dict(), seed=4242 + fold))
+                                combine=args.combine, loss_kind="neg_mse" if nmmlp else "gauss_ll",
+                                state_dict={k: v for k, v in model.state_dict().items() if not k.startswith("mlp.")},
+                                seed=4242 + fold))
         test_xc.append(xcs); test_frames.append(frames); test_x64.append(x64)
     trainer = EnsembleTrainer(specs, device=dev)
     xhat, _, _ = trainer.reconstruct(test_xc, mode="sample")   # z sampled at test time (cVAE.py:1207)
@@ -232,6 +253,18 @@ def test_main(args, root=None):
         d.mkdir(exist_ok=True, parents=True)
         for key, parts in all_frames[name].items():
             pd.concat(parts, ignore_index=True).to_csv(d / f"{key}_{name}.csv", index=False)
+    if nmmlp:
+        # nmmlp :515-523: "diagnosis" = modality-averaged per-subject deviation (nmb_mean_rows), HC = 0 / other = 1
+        hc_label = get_hc_label(args.dataset_resourse)
+        k = 0
+        for fold in range(args.n_splits):
+            m = len(names)
+            diag = scoring.mean_rows(subj[k:k + m]).cpu().numpy().astype(np.float64)
+            k += m
+            te = test_frames[fold][0]
+            pd.DataFrame({"participant_id": te["participant_id"].values, "Diagnosis": diag,
+                          "True_Label": (te["DIA"].to_numpy() != hc_label).astype(int)}).to_csv(
+                model_dir / f"{fold:03d}" / "diagnosis_results.csv", index=False)
     trainer.close()
 
 
@@ -273,7 +306,10 @@ def analysis_main(args, root=None):
             keep = (dia == hc_label) | (dia == disease_label)
             if keep.sum() == 0 or (dia[keep] == hc_label).all() or (dia[keep] == disease_label).all():
                 continue
-            rows.append(classification_performance(err[keep], (dia[keep] == disease_label), dev))
+            labels = dia[keep] == disease_label
+            if getattr(args, "training_class", "nm") != "nm":
+                labels = ~labels                                  # trained on the disease class (group analysis :114-117)
+            rows.append(classification_performance(err[keep], labels, dev))
         if not rows:
             continue
         r = np.array(rows, dtype=np.float64)
@@ -293,3 +329,54 @@ def analysis_main(args, root=None):
         pd.DataFrame({"ROC-AUC": r[:, 0]}).to_csv(comp / "auc_rocs.csv", index=False)
         summary.append((hc_label, disease_label, r.mean(axis=0), r.std(axis=0)))
     return summary
+
+
+def nmmlp_analyze(args, root=None):
+    """``analyze`` of multimodal_kfold_cvae_nmmlp.py:537-643: per-fold ROC metrics of diagnosis_results.csv and their
+    mean +- std, appended to outputs/analysis_results/performance_metrics.txt."""
+    root = Path(root or Path.cwd())
+    dev = _device()
+    _, kfold_dir, model_dir = _paths(root, args.dataset_resourse)
+    rows = []
+    for fold in range(args.n_splits):
+        path = model_dir / f"{fold:03d}" / "diagnosis_results.csv"
+        if not path.exists():
+            print(f"Diagnosis results not found for fold {fold}. Please run the test function first.")
+            continue
+        df = pd.read_csv(path)
+        rows.append(classification_performance(df["Diagnosis"].values, df["True_Label"].values, dev))
+        print("Fold %d:\nROC AUC: %.4f\nAccuracy: %.4f\nSensitivity (Recall): %.4f\nSpecificity: %.4f\n" % (fold, *rows[-1][:4]))
+    r = np.array(rows, dtype=np.float64)
+    names = ("ROC AUC", "Accuracy", "Sensitivity", "Specificity", "Significance Ratio")
+    out_dir = root / "outputs" / "analysis_results"
+    out_dir.mkdir(exist_ok=True, parents=True)
+    lines = ["Overall Performance:"] + ["Mean %s: %.4f \u00b1 %.4f" % (n, r[:, j].mean(), r[:, j].std()) for j, n in enumerate(names)]
+    print("\n".join(lines))
+    with open(out_dir / "performance_metrics.txt", "a") as f:
+        f.write("\n".join(lines) + "\n")
+    return r
+
+
+def nmmlp_main(argv=None, root=None):
+    """multimodal_kfold_cvae_nmmlp.py:646-677: positional action in {train, test, analyze, all} + the common flags."""
+    p = argparse.ArgumentParser(description="Train, Test, and Analyze the model.")
+    p.add_argument("action", choices=["train", "test", "analyze", "all"])
+    p.add_argument("-R", "--dataset_resourse", type=str, default="ADNI")
+    p.add_argument("-H", "--hz_para_list", nargs="+", type=int, default=[110, 110, 10])
+    p.add_argument("-C", "--combine", type=str)
+    p.add_argument("-P", "--procedure", type=str, default="SE-MoE")
+    p.add_argument("-E", "--epochs", type=int, default=200)
+    p.add_argument("-K", "--n_splits", type=int, default=5)
+    p.add_argument("-O", "--oversample_percentage", type=float, default=1)
+    args = p.parse_args(argv)
+    if args.combine is None:
+        args.combine = args.procedure.split("-")[1]
+    args.nmmlp, args.model, args.training_class, args.ensemble_seeds = True, "cVAE_multimodal", "nm", 1
+    out = {}
+    if args.action in ("train", "all"):
+        out["losses"] = train_main(args, root)
+    if args.action in ("test", "all"):
+        test_main(args, root)
+    if args.action in ("analyze", "all"):
+        out["metrics"] = nmmlp_analyze(args, root)
+    return out

@@ -133,6 +133,8 @@ struct NmbEnsemble {
   std::vector<tcp::EpiP> epis_p;             // compact epilogue item tables (kernel parameters) where they fit
   std::vector<int> ep_off, ep_cnt;
   int max_mlayers = 1;                       // layers with Adam master state, over all architectures
+  std::vector<long long> steps_host;         // host mirror of MemberDev.steps_done (every step goes through this API)
+  std::vector<long long> n_lr_steps;         // length of each member's lr_steps schedule (0 = none)
 };
 
 namespace {
@@ -336,7 +338,9 @@ int nmb_ensemble_create(NmbEnsemble** out, int32_t device, const NmbMember* memb
     md.lr_steps = mm.lr_steps; md.seed = mm.seed;
     md.lr = mm.lr; md.beta1 = mm.beta1; md.beta2 = mm.beta2; md.adam_eps = mm.adam_eps;
     md.steps_done = 0; md.last_rows = 0; md.last_slot = -1; md.launch_base = 0;
+    if (mm.lr_steps && mm.n_lr_steps < 1) { delete e; return fail("lr_steps given without n_lr_steps"); }
     e->members_host.push_back(md); e->arch_idx.push_back(ai);
+    e->steps_host.push_back(0); e->n_lr_steps.push_back(mm.lr_steps ? (long long)mm.n_lr_steps : 0);
   }
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, device));
@@ -401,18 +405,33 @@ int nmb_ensemble_steps_done(NmbEnsemble* e, int64_t* steps, void* stream) {
   return 0;
 }
 
-int nmb_ensemble_train(NmbEnsemble* e, int64_t n_steps, const float* eps_override, float* loss_out, uint32_t flags,
-                       void* stream) {
+static int train_common(NmbEnsemble* e, int64_t n, int n_is_epochs, const float* eps_override, float* loss_out,
+                        uint32_t flags, void* stream) {
   if (!e) return fail("null ensemble");
-  if (n_steps < 0) return fail("negative n_steps");
+  if (n < 0) return fail(n_is_epochs ? "negative n_epochs" : "negative n_steps");
   if ((flags & NMB_TRAIN_WRITE_GRADS)) {
     for (const MemberDev& m : e->members_host) if (!m.grads) return fail("NMB_TRAIN_WRITE_GRADS needs NmbMember.grads");
   }
   for (const MemberDev& m : e->members_host) if (m.n_rows < 1) return fail("member without training rows");
-  CU(cudaSetDevice(e->device));
   TrainLaunch t;
   t.members = e->members_dev; t.archs = e->archs_dev; t.n_members = e->n_members;
-  t.n_steps = n_steps; t.eps_override = eps_override; t.loss_out = loss_out; t.flags = flags;
+  t.n_steps = n; t.eps_override = eps_override; t.loss_out = loss_out; t.flags = flags;
+  t.n_is_epochs = n_is_epochs; t.stride_steps = n;
+  long long max_steps = 0;
+  for (int i = 0; i < e->n_members; ++i) {
+    const long long ns = member_steps(t, e->members_host[i]);
+    if (ns > max_steps) max_steps = ns;
+    // a per-step learning-rate schedule must cover every step of this call (the kernels index it by global step)
+    if (e->n_lr_steps[i] > 0 && e->steps_host[i] + ns > e->n_lr_steps[i]) {
+      char buf[160];
+      std::snprintf(buf, sizeof(buf), "member %d: lr_steps has %lld entries but this call would reach step %lld",
+                    i, e->n_lr_steps[i], e->steps_host[i] + ns);
+      return fail(buf);
+    }
+  }
+  t.stride_steps = max_steps;
+  if (max_steps == 0) return 0;
+  CU(cudaSetDevice(e->device));
   t.scratch = e->scratch; t.slot_floats = e->slot_floats; t.n_slots = e->n_slots; t.work_counter = e->work_counter; t.order = e->order_dev;
   if (e->tcp_ok && !(flags & (NMB_TRAIN_FP32 | NMB_TRAIN_TC_SIMPLE))) {
     // dataset rows may have been re-packed since the last call: refresh their planes (cheap, streaming)
@@ -424,7 +443,17 @@ int nmb_ensemble_train(NmbEnsemble* e, int64_t n_steps, const float* eps_overrid
   } else {
     CU(launch_train(t, (cudaStream_t)stream));
   }
+  for (int i = 0; i < e->n_members; ++i) e->steps_host[i] += member_steps(t, e->members_host[i]);
   return 0;
+}
+
+int nmb_ensemble_train(NmbEnsemble* e, int64_t n_steps, const float* eps_override, float* loss_out, uint32_t flags,
+                       void* stream) {
+  return train_common(e, n_steps, 0, eps_override, loss_out, flags, stream);
+}
+
+int nmb_ensemble_train_epochs(NmbEnsemble* e, int64_t n_epochs, float* loss_out, uint32_t flags, void* stream) {
+  return train_common(e, n_epochs, 1, nullptr, loss_out, flags, stream);
 }
 
 int nmb_ensemble_peek(NmbEnsemble* e, int32_t member, float* mu, float* logvar, float* const* x_recon, int32_t* rows,
@@ -460,7 +489,11 @@ int nmb_ensemble_reconstruct(NmbEnsemble* e, const float* const* xc, const int32
   if (!e || !xc || !n_rows || !xhat) return fail("null argument");
   const int fp32 = (mode & NMB_RECON_FP32) ? 1 : 0;
   mode &= ~NMB_RECON_FP32;
-  if (mode != NMB_RECON_MEAN && mode != NMB_RECON_SAMPLE) return fail("bad mode");
+  if (mode != NMB_RECON_MEAN && mode != NMB_RECON_SAMPLE && mode != NMB_RECON_GIVEN_Z) return fail("bad mode");
+  if (mode == NMB_RECON_GIVEN_Z) {
+    if (!eps) return fail("NMB_RECON_GIVEN_Z needs z in eps[]");
+    for (int i = 0; i < e->n_members; ++i) if (n_rows[i] > 0 && !eps[i]) return fail("NMB_RECON_GIVEN_Z: null z entry");
+  }
   cudaStream_t st = (cudaStream_t)stream;
   CU(cudaSetDevice(e->device));
   std::vector<ReconItem> items;
@@ -555,6 +588,36 @@ int nmb_deviation(int32_t n_seg, const float* const* x, const int32_t* ldx, cons
   t.z = z ? b.at<float*>(oz) : nullptr;
   t.dev_subj = dev_subj ? b.at<float*>(oj) : nullptr;
   launch_deviation(t, n_seg, mr, st);
+  CU(cudaGetLastError());
+  CU(b.release(st));
+  return 0;
+}
+
+int nmb_latent_deviation(int32_t n_seg, const float* const* mu_train, const int32_t* n_train, const float* const* mu,
+                         const float* const* logvar, const int32_t* n_rows, const int32_t* latent,
+                         float* const* out_z, float* const* out_dev, void* stream) {
+  if (n_seg < 0 || (n_seg && (!mu_train || !n_train || !mu || !logvar || !n_rows || !latent))) return fail("bad argument");
+  if (n_seg == 0) return 0;
+  int max_rows = 0;
+  for (int i = 0; i < n_seg; ++i) {
+    if (latent[i] < 1 || latent[i] > 128) return fail("latent must be in 1..128");
+    if (n_train[i] < 1 || n_rows[i] < 0) return fail("bad segment size");
+    if (!mu_train[i] || (n_rows[i] > 0 && (!mu[i] || !logvar[i]))) return fail("null segment pointer");
+    if (n_rows[i] > max_rows) max_rows = n_rows[i];
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  Blob b;
+  LatentTable t; std::memset(&t, 0, sizeof(t));
+  const size_t o0 = b.add(mu_train, sizeof(void*) * n_seg), o1 = b.add(n_train, sizeof(int) * n_seg);
+  const size_t o2 = b.add(mu, sizeof(void*) * n_seg), o3 = b.add(logvar, sizeof(void*) * n_seg);
+  const size_t o4 = b.add(n_rows, sizeof(int) * n_seg), o5 = b.add(latent, sizeof(int) * n_seg);
+  const size_t o6 = out_z ? b.add(out_z, sizeof(void*) * n_seg) : 0;
+  const size_t o7 = out_dev ? b.add(out_dev, sizeof(void*) * n_seg) : 0;
+  CU(b.upload(st));
+  t.mu_train = b.at<const float*>(o0); t.n_train = b.at<int>(o1); t.mu = b.at<const float*>(o2);
+  t.logvar = b.at<const float*>(o3); t.n_rows = b.at<int>(o4); t.latent = b.at<int>(o5);
+  t.out_z = out_z ? b.at<float*>(o6) : nullptr; t.out_dev = out_dev ? b.at<float*>(o7) : nullptr;
+  launch_latent_deviation(t, n_seg, max_rows, st);
   CU(cudaGetLastError());
   CU(b.release(st));
   return 0;

@@ -11,6 +11,19 @@
 
 namespace nmb {
 
+// SMs of the current device (queried once per device; grids are sized in multiples of it)
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
 // ---- pack rows: [x | c | 1 | 0] ------------------------------------------------------------
 __global__ void pack_rows_kernel(const float* __restrict__ x, const float* __restrict__ c, long long n_rows,
                                  int d, int c_dim, int ldx, float* __restrict__ out) {
@@ -31,7 +44,7 @@ void launch_pack_rows(const float* x, const float* c, long long n_rows, int d, i
                       cudaStream_t st) {
   const long long total = n_rows * ldx;
   if (total == 0) return;
-  const int blocks = (int)min((total + 255) / 256, (long long)148 * 16);
+  const int blocks = (int)min((total + 255) / 256, (long long)sm_count() * 16);
   pack_rows_kernel<<<blocks, 256, 0, st>>>(x, c, n_rows, d, c_dim, ldx, out);
 }
 
@@ -134,7 +147,7 @@ __global__ void __launch_bounds__(256) deviation_kernel(SegTable t) {
 void launch_deviation(const SegTable& t, int n_seg, int max_rows, cudaStream_t st) {
   if (n_seg == 0 || max_rows == 0) return;
   int bx = (max_rows + 7) / 8;
-  const int cap = max(1, (148 * 8) / n_seg);   // ~8 CTAs per SM over all segments
+  const int cap = max(1, (sm_count() * 8) / n_seg);   // ~8 CTAs per SM over all segments
   if (bx > cap) bx = cap;
   dim3 grid(bx, n_seg);
   deviation_kernel<<<grid, 256, 0, st>>>(t);
@@ -232,6 +245,77 @@ void launch_auc(const AucTable& t, int n_seg, int max_cols, cudaStream_t st) {
   auc_kernel<<<grid, 256, kAucChunk * sizeof(float), st>>>(t);
 }
 
+// ---- latent-space normative deviation (utils_vae.py:155-161) --------------------------------------------------
+// grid = (row slices, n_seg).  Every CTA first reduces the reference rows of its segment to per-dimension mean and
+// population variance (fp64 accumulation, fixed combine order; the [n_train][Z] table is tiny and L2-resident, so the
+// row slices of one segment recompute it instead of synchronising), then streams its slice of the scored rows.
+constexpr int kLatMaxZ = 128;
+__global__ void __launch_bounds__(256) latent_deviation_kernel(LatentTable t) {
+  __shared__ double s_sum[256], s_sq[256];
+  __shared__ float s_mean[kLatMaxZ], s_var[kLatMaxZ];
+  const int s = blockIdx.y;
+  const int Z = t.latent[s], nt = t.n_train[s], n = t.n_rows[s];
+  const float* mt = t.mu_train[s];
+  // thread = (row group rg, dimension k): 256 / Zp row groups, Zp = Z rounded up to a power of two <= 128
+  int zp = 1;
+  while (zp < Z) zp <<= 1;
+  const int k = threadIdx.x % zp, rg = threadIdx.x / zp, n_rg = 256 / zp;
+  double sum = 0.0, sq = 0.0;
+  if (k < Z)
+    for (int i = rg; i < nt; i += n_rg) { const double v = (double)mt[(long long)i * Z + k]; sum += v; sq += v * v; }
+  s_sum[threadIdx.x] = sum; s_sq[threadIdx.x] = sq;
+  __syncthreads();
+  if (rg == 0 && k < Z) {
+    double a = 0.0, b = 0.0;
+    for (int g = 0; g < n_rg; ++g) { a += s_sum[g * zp + k]; b += s_sq[g * zp + k]; }
+    const double mean = nt > 0 ? a / nt : 0.0;
+    double var = nt > 0 ? b / nt - mean * mean : 0.0;
+    if (var < 0.0) var = 0.0;
+    s_mean[k] = (float)mean; s_var[k] = (float)var;
+  }
+  __syncthreads();
+  const float* mu = t.mu[s];
+  const float* lv = t.logvar[s];
+  float* oz = t.out_z ? t.out_z[s] : nullptr;
+  float* od = t.out_dev ? t.out_dev[s] : nullptr;
+  // one row per group of zp threads (zp <= 32: sub-warp shuffle reduction; larger: shared memory).  The loop is
+  // uniform over the CTA (row index guarded inside), so the barriers of the wide case are never divergent.
+  __shared__ float s_row[8];
+  for (int base = blockIdx.x * n_rg; base < n; base += gridDim.x * n_rg) {
+    const int i = base + rg;
+    float a = 0.f;
+    if (i < n && k < Z) {
+      const float zz = (mu[(long long)i * Z + k] - s_mean[k]) / sqrtf(s_var[k] + expf(lv[(long long)i * Z + k]));
+      if (oz) oz[(long long)i * Z + k] = zz;
+      a = fabsf(zz);
+    }
+    if (zp <= 32) {
+      for (int o = zp >> 1; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      if (od && i < n && k == 0) od[i] = a / Z;
+    } else {
+      a = warp_sum(a);
+      if ((threadIdx.x & 31) == 0) s_row[threadIdx.x >> 5] = a;
+      __syncthreads();
+      if (od && i < n && k == 0) {
+        float tot = 0.f;
+        for (int w = 0; w < zp / 32; ++w) tot += s_row[rg * (zp / 32) + w];
+        od[i] = tot / Z;
+      }
+      __syncthreads();
+    }
+  }
+}
+
+void launch_latent_deviation(const LatentTable& t, int n_seg, int max_rows, cudaStream_t st) {
+  if (n_seg == 0) return;
+  int bx = (max_rows + 255) / 256;
+  const int cap = max(1, (sm_count() * 4) / n_seg);
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  dim3 grid(bx, n_seg);
+  latent_deviation_kernel<<<grid, 256, 0, st>>>(t);
+}
+
 // ---- misc -----------------------------------------------------------------------------------
 __global__ void mean_rows_kernel(PtrTable16 src, int k, long long n, float* out) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
@@ -244,7 +328,7 @@ __global__ void mean_rows_kernel(PtrTable16 src, int k, long long n, float* out)
 
 void launch_mean_rows(const PtrTable16& src, int k, long long n, float* out, cudaStream_t st) {
   if (n == 0) return;
-  const int blocks = (int)min((n + 255) / 256, (long long)148 * 8);
+  const int blocks = (int)min((n + 255) / 256, (long long)sm_count() * 8);
   mean_rows_kernel<<<blocks, 256, 0, st>>>(src, k, n, out);
 }
 
@@ -262,7 +346,7 @@ __global__ void adam_kernel(float* p, const float* g, float* m, float* v, long l
 void launch_adam(float* p, const float* g, float* m, float* v, long long n, float step_size, float bc2_sqrt,
                  float b1, float b2, float eps, cudaStream_t st) {
   if (n == 0) return;
-  const int blocks = (int)min((n + 255) / 256, (long long)148 * 8);
+  const int blocks = (int)min((n + 255) / 256, (long long)sm_count() * 8);
   adam_kernel<<<blocks, 256, 0, st>>>(p, g, m, v, n, step_size, bc2_sqrt, b1, b2, eps);
 }
 
@@ -281,7 +365,7 @@ void launch_philox(unsigned long long seed, unsigned long long step, uint32_t st
                    cudaStream_t st) {
   if (n == 0) return;
   const long long groups = (n + 3) / 4;
-  const int blocks = (int)min((groups + 255) / 256, (long long)148 * 8);
+  const int blocks = (int)min((groups + 255) / 256, (long long)sm_count() * 8);
   philox_kernel<<<blocks, 256, 0, st>>>(seed, step, stream_id, n, out);
 }
 

@@ -36,6 +36,12 @@ void launch_pack_rows(const float* x, const float* c, long long n_rows, int d, i
 void launch_stats(const SegTable& t, int n_seg, int max_d, cudaStream_t st);
 void launch_deviation(const SegTable& t, int n_seg, int max_rows, cudaStream_t st);
 void launch_auc(const AucTable& t, int n_seg, int max_cols, cudaStream_t st);
+struct LatentTable {
+  const float* const* mu_train; const int* n_train; const float* const* mu; const float* const* logvar;
+  const int* n_rows; const int* latent; float* const* out_z; float* const* out_dev;
+};
+void launch_latent_deviation(const LatentTable& t, int n_seg, int max_rows, cudaStream_t st);
+int sm_count();
 void launch_mean_rows(const PtrTable16& src, int k, long long n, float* out, cudaStream_t st);
 void launch_adam(float* p, const float* g, float* m, float* v, long long n, float step_size, float bc2_sqrt,
                  float b1, float b2, float eps, cudaStream_t st);
@@ -46,9 +52,15 @@ void launch_philox(unsigned long long seed, unsigned long long step, uint32_t st
 struct TrainLaunch {
   MemberDev* members; const ArchDesc* archs; int n_members;
   long long n_steps; const float* eps_override; float* loss_out; unsigned flags;
+  int n_is_epochs;          // 1: member i runs n_steps * steps_per_epoch_i steps (nmb_ensemble_train_epochs)
+  long long stride_steps;   // rows per member of eps_override / loss_out
   float* scratch; long long slot_floats; int n_slots; int* work_counter;
   const int* order;   // members sorted by decreasing cost (longest-processing-time-first dealing)
 };
+// minibatch steps member `mb` takes in this launch
+__host__ __device__ inline long long member_steps(const TrainLaunch& t, const MemberDev& mb) {
+  return t.n_is_epochs ? t.n_steps * (long long)((mb.n_rows + mb.batch - 1) / mb.batch) : t.n_steps;
+}
 cudaError_t launch_train(const TrainLaunch& t, cudaStream_t st);
 cudaError_t launch_debug_tc_gemm(const float* A, int lda, int a_kmajor, const float* B, int ldb, int b_kmajor,
                                  float* C, int ldc, int M, int N, int K, cudaStream_t st);

@@ -290,7 +290,8 @@ __device__ void encoders_forward(const StepCtx& c, const float* const* xc) {
 
 // Fusion + reparameterisation + KL.  Writes fused mu/logvar, eps, and the decoder inputs
 // [z | c | 1] of every modality.  Returns sum over elements of the KL integrand (all threads).
-//   eps_mode: 0 = Philox(stream_id), 1 = injected (eps_src [rows][Z]), 2 = zero (decode the mean)
+//   eps_mode: 0 = Philox(stream_id), 1 = injected (eps_src [rows][Z]), 2 = zero (decode the mean),
+//             3 = z itself is given in eps_src (decoders only; the heads are not read)
 __device__ float latent_forward(const StepCtx& c, const float* const* xc, int eps_mode,
                                 const float* eps_src, uint32_t stream_id, unsigned long long eps_step) {
   const ArchDesc& a = *c.a;
@@ -307,6 +308,12 @@ __device__ float latent_forward(const StepCtx& c, const float* const* xc, int ep
       const int e = g * 4 + j;
       if (e >= n) break;
       const int b = e / Z, z = e - b * Z;
+      if (eps_mode == 3) {
+        const float zz = eps_src[e];
+        S[a.s_mub + e] = zz; S[a.s_lvb + e] = 0.f; S[a.s_eps + e] = 0.f;
+        for (int m = 0; m < M; ++m) S[a.mod[m].s_g0 + (long long)b * a.mod[m].ld_g0 + z] = zz;
+        continue;
+      }
       float mu[NMB_MAX_MOD], lv[NMB_MAX_MOD];
       for (int m = 0; m < M; ++m) {
         const float* h = S + a.mod[m].s_mulv + (long long)b * a.mod[m].ld_mulv;
@@ -526,7 +533,8 @@ __device__ __forceinline__ void train_body(const TrainLaunch& t, float* smem_f, 
     const int spe = (mb.n_rows + mb.batch - 1) / mb.batch;   // steps per epoch
     const long long s0 = mb.steps_done;
     int rows = 0;
-    for (long long i = 0; i < t.n_steps; ++i) {
+    const long long ns = member_steps(t, mb);
+    for (long long i = 0; i < ns; ++i) {
       const long long s = s0 + i;
       const int pos = (int)(s % spe);
       c.step = s;
@@ -537,13 +545,13 @@ __device__ __forceinline__ void train_body(const TrainLaunch& t, float* smem_f, 
       c.step_size = (float)((double)lr / (1.0 - pow((double)mb.beta1, tt)));
       c.bc2_sqrt = (float)sqrt(1.0 - pow((double)mb.beta2, tt));
       const float* eps = t.eps_override
-          ? t.eps_override + ((long long)mi * t.n_steps + i) * mb.batch * a.Z : nullptr;
-      float* lo = t.loss_out ? t.loss_out + ((long long)mi * t.n_steps + i) * 3 : nullptr;
+          ? t.eps_override + ((long long)mi * t.stride_steps + i) * mb.batch * a.Z : nullptr;
+      float* lo = t.loss_out ? t.loss_out + ((long long)mi * t.stride_steps + i) * 3 : nullptr;
       train_step<TC>(c, eps, lo);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-      mb.steps_done = s0 + t.n_steps;
+      mb.steps_done = s0 + ns;
       mb.last_rows = rows;
       mb.last_slot = blockIdx.x;
     }
@@ -611,17 +619,17 @@ __device__ __forceinline__ void recon_body(const ReconLaunch& t, float* smem_f, 
     c.rows = item.rows; c.row0 = item.row0; c.step = 0;
     const float* const* xc = t.xc + (long long)item.member * NMB_MAX_MOD;
     prepare_slot(c);
-    encoders_forward<TC>(c, xc);
-    const float* eps = (t.mode == NMB_RECON_SAMPLE && t.eps && t.eps[item.member])
+    if (t.mode != NMB_RECON_GIVEN_Z) encoders_forward<TC>(c, xc);
+    const float* eps = (t.mode != NMB_RECON_MEAN && t.eps && t.eps[item.member])
         ? t.eps[item.member] + (long long)item.row0 * a.Z : nullptr;
-    const int eps_mode = t.mode == NMB_RECON_MEAN ? 2 : (eps ? 1 : 0);
+    const int eps_mode = t.mode == NMB_RECON_GIVEN_Z ? 3 : (t.mode == NMB_RECON_MEAN ? 2 : (eps ? 1 : 0));
     // Philox test stream: counter "step" = row tile index so that tiles draw disjoint numbers
     latent_forward(c, xc, eps_mode, eps, 1u, (unsigned long long)(item.row0 / kMaxBatch));
-    if (t.mu && t.mu[item.member]) {
+    if (t.mode != NMB_RECON_GIVEN_Z && t.mu && t.mu[item.member]) {
       float* mu = t.mu[item.member] + (long long)item.row0 * a.Z;
       for (int e = threadIdx.x; e < item.rows * a.Z; e += kThreads) mu[e] = c.scratch[a.s_mub + e];
     }
-    if (t.logvar && t.logvar[item.member]) {
+    if (t.mode != NMB_RECON_GIVEN_Z && t.logvar && t.logvar[item.member]) {
       float* lv = t.logvar[item.member] + (long long)item.row0 * a.Z;
       for (int e = threadIdx.x; e < item.rows * a.Z; e += kThreads) lv[e] = c.scratch[a.s_lvb + e];
     }

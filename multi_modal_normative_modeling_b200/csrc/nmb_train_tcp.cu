@@ -61,12 +61,16 @@ __device__ __forceinline__ void st_release(volatile uint32_t* p, uint32_t v) {
 #define NMB_POLL_NS 100
 #endif
 constexpr unsigned kPollSleepNs = NMB_POLL_NS;
+// Watchdog of every bounded spin, in SM clock cycles (0 = never trap).  Set per process from NMB_TCP_SPIN_BUDGET
+// (configure_tcp): tools that stretch time by orders of magnitude -- compute-sanitizer, ncu replay, a debugger -- must
+// be able to switch it off, because a trap leaves a sticky context error.  Read only on the slow path.
+__device__ long long g_spin_budget = 8000000000LL;
 __device__ __forceinline__ void wait_epi(const volatile uint32_t* p, uint32_t need) {
   if (ld_acquire(p) < need) {
     const long long t0 = clock64();
     while (ld_acquire(p) < need) {
       __nanosleep(kPollSleepNs);
-      if (clock64() - t0 > 4000000000LL) __trap();
+      if (g_spin_budget > 0 && clock64() - t0 > g_spin_budget) __trap();
     }
   }
 }
@@ -1197,8 +1201,8 @@ __device__ void epilogue_role(const LaunchP& L, int ai, int mi, EpiCtx& c, uint3
       c.step_size = (float)((double)lr / (1.0 - pow((double)mb.beta1, tt)));
       c.inv_bc2 = (float)(1.0 / sqrt(1.0 - pow((double)mb.beta2, tt)));
     }
-    const float* eps = t.eps_override ? t.eps_override + ((long long)mi * t.n_steps + i0 + i) * mb.batch * c.a->Z : nullptr;
-    float* lo = t.loss_out ? t.loss_out + ((long long)mi * t.n_steps + i0 + i) * 3 : nullptr;
+    const float* eps = t.eps_override ? t.eps_override + ((long long)mi * t.stride_steps + i0 + i) * mb.batch * c.a->Z : nullptr;
+    float* lo = t.loss_out ? t.loss_out + ((long long)mi * t.stride_steps + i0 + i) * 3 : nullptr;
     for (int k = 0; k < n_epis; ++k) {
       Epi e;
       if (in_params) e = from_epip(L.epis_p[ep0 + k]);
@@ -1315,7 +1319,8 @@ __global__ void __launch_bounds__(kThreadsP, 1) train_tcp_kernel(const __grid_co
         const int chunk = it / t.n_members;
         mi = dynamic ? t.order[it - chunk * t.n_members] : it;
         MemberDev& m = t.members[mi];
-        const long long i0 = t.n_steps * chunk / L.n_chunks, i1 = t.n_steps * (chunk + 1) / L.n_chunks;
+        const long long ns = member_steps(t, m);
+        const long long i0 = ns * chunk / L.n_chunks, i1 = ns * (chunk + 1) / L.n_chunks;
         const long long need = m.launch_base + i0;
         if (chunk > 0) {
           const long long t0 = clock64();
@@ -1324,7 +1329,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) train_tcp_kernel(const __grid_co
             asm volatile("ld.acquire.gpu.global.s64 %0, [%1];" : "=l"(have) : "l"(&m.steps_done) : "memory");
             if (have >= need) break;
             __nanosleep(200);
-            if (clock64() - t0 > 8000000000LL) __trap();
+            if (g_spin_budget > 0 && clock64() - t0 > g_spin_budget) __trap();
           }
         }
         ctl->chunk_i0 = (int)i0; ctl->chunk_n = (int)(i1 - i0); ctl->chunk_s0 = need;
@@ -1442,7 +1447,19 @@ cudaError_t set_tcp_trace(unsigned long long* buf, int step) {
 }
 
 cudaError_t configure_tcp() {
-  return cudaFuncSetAttribute(tcp::train_tcp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tcp::kSmemBytes);
+  if (const char* u = getenv("NMB_TCP_SPIN_BUDGET")) {
+    const long long v = atoll(u);
+    cudaError_t e = cudaMemcpyToSymbol(tcp::g_spin_budget, &v, sizeof(v));
+    if (e != cudaSuccess) return e;
+  }
+  // Forward progress of chunked work items relies on every CTA of the grid being co-resident (a chunk spins on its
+  // predecessor, which may sit on another SM): the grid is capped at the SM count and needs one CTA per SM to fit.
+  int per_sm = 0;
+  cudaError_t e = cudaFuncSetAttribute(tcp::train_tcp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tcp::kSmemBytes);
+  if (e != cudaSuccess) return e;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tcp::train_tcp_kernel, tcp::kThreadsP, tcp::kSmemBytes);
+  if (e != cudaSuccess) return e;
+  return per_sm >= 1 ? cudaSuccess : cudaErrorLaunchOutOfResources;
 }
 
 cudaError_t launch_xprep(const void* items_dev, int n_items, int max_blocks, cudaStream_t st) {
@@ -1601,7 +1618,8 @@ cudaError_t launch_train_tcp(const TrainLaunch& t, const tcp::ProgramDev* progs,
   // more members than SMs: deal chunks of >= 4 steps, so that the launch does not end on a few whole members
   int n_chunks = 1;
   if (t.n_members > n_sm) {
-    n_chunks = (int)(t.n_steps / 4 < 8 ? t.n_steps / 4 : 8);
+    const long long ns_min = t.n_is_epochs ? t.n_steps : t.n_steps;      // epochs mode: every member has >= n_steps steps
+    n_chunks = (int)(ns_min / 4 < 8 ? ns_min / 4 : 8);
     if (n_chunks < 1) n_chunks = 1;
     if (const char* u = getenv("NMB_TCP_CHUNKS")) { const int v = atoi(u); if (v >= 1 && v <= t.n_steps) n_chunks = v; }   // dev knob
   }

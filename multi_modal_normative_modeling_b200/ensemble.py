@@ -133,6 +133,7 @@ class EnsembleTrainer:
                 lr = s.lr_steps.to(device=dev, dtype=torch.float32).contiguous()
                 self._keep.append(lr)
                 m.lr_steps = lr.data_ptr()
+                m.n_lr_steps = int(lr.numel())
             off = self.offsets[i] * 4
             m.params = self.params.data_ptr() + off
             m.adam_m = self.adam_m.data_ptr() + off
@@ -241,11 +242,27 @@ class EnsembleTrainer:
         _lib.check(self.lib.nmb_ensemble_engine(self.handle, int(flags), C.byref(out)), "nmb_ensemble_engine")
         return {2: "tcgen05-pipelined", 1: "tcgen05-generic", 0: "fp32"}[out.value]
 
-    def train_epochs(self, epochs: int, **kw):
-        spe = set(self.steps_per_epoch)
-        if len(spe) != 1:
-            raise ValueError("members have different steps per epoch; use train_steps")
-        return self.train_steps(epochs * spe.pop(), **kw)
+    def train_epochs(self, epochs: int, record_losses: bool = False, flags: int = 0) -> Optional[torch.Tensor]:
+        """`epochs` passes over EVERY member's own rows in one launch: member i takes epochs * steps_per_epoch[i]
+        steps (the ``for epoch / for batch`` nest of the train script :177-199), also when the folds have different
+        row counts.  Returns [n_members, epochs * max(steps_per_epoch), 3] when record_losses (member i fills its
+        first epochs * steps_per_epoch[i] rows; the rest is NaN)."""
+        losses = None
+        if record_losses:
+            losses = torch.full((self.n, epochs * max(self.steps_per_epoch), 3), float("nan"), dtype=torch.float32,
+                                device=self.device)
+        if (flags & _lib.TRAIN_WRITE_GRADS) and self.grads is None:
+            raise RuntimeError("TRAIN_WRITE_GRADS needs keep_grads=True")
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.nmb_ensemble_train_epochs(self.handle, int(epochs),
+                                                          losses.data_ptr() if losses is not None else None,
+                                                          int(flags), _stream_ptr(self.device)),
+                       "nmb_ensemble_train_epochs")
+        if self._engine_cached(int(flags)) == "tcgen05-pipelined":
+            self.gpu_launches += 3 if (int(flags) & _lib.TRAIN_NO_ADAM) else 4
+        else:
+            self.gpu_launches += 1
+        return losses
 
     def steps_done(self) -> np.ndarray:
         out = (C.c_int64 * self.n)()
@@ -270,11 +287,19 @@ class EnsembleTrainer:
 
     # ---- test-time reconstruction ----------------------------------------------------------
     def reconstruct(self, xc: Sequence[Sequence[torch.Tensor]], mode: str = "sample",
-                    eps: Optional[Sequence[Optional[torch.Tensor]]] = None, want_latent: bool = False):
+                    eps: Optional[Sequence[Optional[torch.Tensor]]] = None, want_latent: bool = False,
+                    want_xhat: bool = True):
         """pred_recon for every member on its own rows (packed, per modality).
 
         mode 'mean' = cVAE.pred_recon (cVAE.py:549-555); 'sample' = cVAE_multimodal.pred_recon
-        (cVAE.py:1198-1208; eps injectable).  Returns (xhat[i][m], mu[i], logvar[i])."""
+        (cVAE.py:1198-1208; eps injectable); 'decode' = decoders only on a given z passed in `eps`
+        (Decoder.forward, cVAE.py:197-206; the covariates are read from the packed rows).
+        want_xhat=False with want_latent=True = encoders + fusion only (pred_latent, cVAE.py:540-547).
+        Returns (xhat[i][m], mu[i], logvar[i])."""
+        if mode not in ("mean", "sample", "decode"):
+            raise ValueError("mode must be 'mean', 'sample' or 'decode'")
+        if mode == "decode" and (eps is None or want_latent):
+            raise ValueError("mode='decode' needs z in eps and produces no latent")
         if len(xc) != self.n:
             raise ValueError("one row-set per member")
         tbl, rows, outs, out_tbl = [], [], [], []
@@ -289,8 +314,8 @@ class EnsembleTrainer:
                     ldx = _lib.packed_row_stride(int(s.input_dims[k]), s.c_dim)
                     if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.shape == (n_i, ldx)):
                         raise ValueError("reconstruct needs packed CUDA float32 rows from pack_rows()")
-                    o = torch.empty((n_i, int(s.input_dims[k])), dtype=torch.float32, device=self.device)
-                    tbl.append(t.data_ptr()); out_tbl.append(o.data_ptr()); row_out.append(o)
+                    o = torch.empty((n_i, int(s.input_dims[k])), dtype=torch.float32, device=self.device) if want_xhat else None
+                    tbl.append(t.data_ptr()); out_tbl.append(o.data_ptr() if want_xhat else None); row_out.append(o)
                 else:
                     tbl.append(None); out_tbl.append(None)
             outs.append(row_out)
@@ -311,7 +336,8 @@ class EnsembleTrainer:
         with torch.cuda.device(self.device):
             _lib.check(self.lib.nmb_ensemble_reconstruct(
                 self.handle, _lib.ptr_table(tbl), _lib.int_table(rows),
-                _lib.RECON_MEAN if mode == "mean" else _lib.RECON_SAMPLE, eps_tbl, _lib.ptr_table(out_tbl),
+                {"mean": _lib.RECON_MEAN, "sample": _lib.RECON_SAMPLE, "decode": _lib.RECON_GIVEN_Z}[mode], eps_tbl,
+                _lib.ptr_table(out_tbl),
                 _lib.ptr_table([t.data_ptr() for t in mus]) if want_latent else None,
                 _lib.ptr_table([t.data_ptr() for t in lvs]) if want_latent else None,
                 _stream_ptr(self.device)), "nmb_ensemble_reconstruct")

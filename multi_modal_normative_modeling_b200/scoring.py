@@ -75,6 +75,30 @@ def deviation(x: Sequence[torch.Tensor], xhat: Sequence[torch.Tensor],
     return roi, z, subj
 
 
+def latent_deviation(mu_train: Sequence[torch.Tensor], mu: Sequence[torch.Tensor], logvar: Sequence[torch.Tensor],
+                     want_separate: bool = True):
+    """The reference's latent-space normative deviation (utils_vae.py:155-161) per segment:
+    ``separate_latent_deviation`` z[s] [N, Z] and ``latent_deviation`` dev[s] [N].
+    mu_train[s]: latent means of the reference (healthy-control training) rows; mu / logvar[s]: the scored rows
+    (var_sample = exp(logvar), what ``pred_latent`` returns)."""
+    dev = _dev(mu)
+    f = lambda ts: [t.to(device=dev, dtype=torch.float32).contiguous() for t in ts]
+    mt, m, lv = f(mu_train), f(mu), f(logvar)
+    for a, b, c in zip(mt, m, lv):
+        if a.dim() != 2 or b.dim() != 2 or a.shape[1] != b.shape[1] or b.shape != c.shape:
+            raise ValueError("mu_train [Nt, Z], mu [N, Z], logvar [N, Z] required")
+    z = [torch.empty_like(t) for t in m] if want_separate else None
+    out = [torch.empty((t.shape[0],), dtype=torch.float32, device=dev) for t in m]
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().nmb_latent_deviation(
+            len(m), _lib.ptr_table([t.data_ptr() for t in mt]), _lib.int_table([t.shape[0] for t in mt]),
+            _lib.ptr_table([t.data_ptr() for t in m]), _lib.ptr_table([t.data_ptr() for t in lv]),
+            _lib.int_table([t.shape[0] for t in m]), _lib.int_table([t.shape[1] for t in m]),
+            _lib.ptr_table([t.data_ptr() for t in z]) if z is not None else None,
+            _lib.ptr_table([t.data_ptr() for t in out]), _stream_ptr(dev)), "nmb_latent_deviation")
+    return z, out
+
+
 def auc(scores: Sequence[torch.Tensor], labels: Sequence[torch.Tensor], want_pairs: bool = False):
     """ROC-AUC of every column of scores[s] ([N, K] or [N]) vs labels[s] (1 = patient).
 

@@ -167,18 +167,26 @@ class OracleCVAEMultimodal(nn.Module):
     """``cVAE_multimodal`` (cVAE.py:1087-1211).  loss_kind: 'gauss_ll' | 'neg_mse'."""
 
     def __init__(self, input_dim_list, hidden_dim, latent_dim, c_dim, learning_rate=1e-4,
-                 modalities=3, non_linear=False, loss_kind="gauss_ll"):
+                 modalities=3, non_linear=False, loss_kind="gauss_ll", rng_order="cvae"):
         super().__init__()
         hd = list(hidden_dim) + [latent_dim]
         self.modalities = modalities
         self.loss_kind = loss_kind
-        # RNG order: alphas, then encoders, then decoders (cVAE.py:1107-1109)
-        self.alpha_m_list = nn.ParameterList(
-            [nn.Parameter(torch.randn(1)) for _ in range(modalities)])
+        # RNG order: alphas, then encoders, then decoders (cVAE.py:1107-1109).  The class inside
+        # multimodal_kfold_cvae_nmmlp.py (:57-83) draws encoders, decoders, alphas and then its (unused) MLP.
+        if rng_order == "cvae":
+            self.alpha_m_list = nn.ParameterList(
+                [nn.Parameter(torch.randn(1)) for _ in range(modalities)])
         self.encoder_list = nn.ModuleList(
             [OracleEncoder(input_dim_list[i], hd, c_dim, non_linear) for i in range(modalities)])
         self.decoder_list = nn.ModuleList(
             [OracleDecoder(input_dim_list[i], hd, c_dim, non_linear) for i in range(modalities)])
+        if rng_order != "cvae":
+            self.alpha_m_list = nn.ParameterList(
+                [nn.Parameter(torch.randn(1)) for _ in range(modalities)])
+            _burn_linear(sum(input_dim_list[:modalities]), 128)
+            _burn_linear(128, 64)
+            _burn_linear(64, 1)
         self.optimizer1 = torch.optim.Adam(
             [p for e in self.encoder_list for p in e.parameters()]
             + [p for d in self.decoder_list for p in d.parameters()]

@@ -143,6 +143,264 @@ def ref_single_case(ref, name, d, hidden, z, c_dim, b, seed, n_age):
     print(name, "ok")
 
 
+
+def _loop_batches(n, b):
+    """DataLoader(batch_size=b, shuffle=False) without drop_last (train script :128-131)."""
+    return [(r0, min(b, n - r0)) for r0 in range(0, n, b)]
+
+
+def ref_loop_case(ref, name, dims, hidden, z, c_dim, n, b, combine, epochs, seed, n_age, lean=0,
+                  model_cls=None, shared=None):
+    """Full-size cases: N rows, batch b with a partial last batch, `epochs` passes of the reference loop
+    body (train script :177-199) with injected eps.  Records per-step losses, step-0 activations, autograd
+    gradients of the first full batch ("grad/") and of the ragged batch on the INITIAL weights ("gradr/"),
+    post-Adam parameters, pred_recon over all rows.
+
+    lean: 0 = everything; 1 = no ragged gradients / dev_roi; 2 = only losses, latents and step-0 gradients
+    (the inputs and initial weights are those of the case named `shared`: same seed, same draws)."""
+    m = len(dims)
+    rng = np.random.RandomState(seed)
+    torch.manual_seed(seed)
+    cls = model_cls or ref.cVAE_multimodal
+    nmmlp = model_cls is not None
+    model = cls(input_dim_list=list(dims), hidden_dim=list(hidden), latent_dim=z, c_dim=c_dim,
+                learning_rate=1e-4, modalities=m, non_linear=True)
+    next_draw = torch.randn(4).numpy().copy()
+    out = {"dims": np.array(dims), "hidden": np.array(hidden), "z": z, "c_dim": c_dim, "combine": combine,
+           "seed": seed, "next_draw": next_draw, "n": n, "batch": b, "epochs": epochs}
+    if shared:
+        out["shared"] = shared
+    init = sd_np(model)
+    xs = [rng.randn(n, d).astype(np.float32) for d in dims]
+    c = onehot_cov(rng, n, c_dim, n_age)
+    batches = _loop_batches(n, b)
+    steps = epochs * len(batches)
+    eps = rng.randn(steps, b, z).astype(np.float32)
+    if lean < 2:
+        for k, v in init.items():
+            if not k.startswith("mlp."):
+                out["init/" + k] = v
+        out["c"] = c
+        for i, x in enumerate(xs):
+            out[f"x{i}"] = x
+    out["eps"] = eps
+    xt = [torch.from_numpy(x) for x in xs]
+    ct = torch.from_numpy(c).long() if not nmmlp else torch.from_numpy(c)
+
+    def fwd_loss(r0, rows, e):
+        xb = [x[r0:r0 + rows] for x in xt]
+        cb = [ct[r0:r0 + rows] for _ in dims]
+        with injected_eps([torch.from_numpy(e[:rows])]):
+            fwd = model.forward_multimodal(xb, cb, combine)
+        loss = model.loss_function_multimodal(xb, fwd, None) if nmmlp else model.loss_function_multimodal(xb, fwd)
+        return fwd, loss
+
+    # gradient of the ragged batch on the initial weights (no Adam step before it)
+    if len(batches) > 1:
+        r0, rows = batches[-1]
+        fwd, loss = fwd_loss(r0, rows, eps[len(batches) - 1])
+        model.optimizer1.zero_grad()
+        loss["total"].backward()
+        out["lossr"] = np.array([float(loss["total"]), float(loss["kl"]), float(loss["ll"])])
+        out["ragged_step"] = len(batches) - 1
+        if lean == 0:
+            for k, p in model.named_parameters():
+                if p.grad is not None and not k.startswith("mlp."):
+                    out["gradr/" + k] = p.grad.detach().numpy().copy()
+        model.optimizer1.zero_grad()
+    losses = []
+    s = 0
+    # Knife-edge units of step 0: a hidden pre-activation within rounding distance of zero takes the leaky-relu slope
+    # 1 or 0.01 depending on the summation order of the fp32 dot product, so the reference's own gradient row of that
+    # unit is decided by rounding noise.  Their indices are recorded; parity tests skip exactly those rows.
+    pre, hooks = {}, []
+    for pname, mod in model.named_modules():
+        if isinstance(mod, torch.nn.Linear) and (".encoder_layers." in pname or ".decoder_layers." in pname):
+            def _keep(_m, _i, o, pname=pname):      # must return None: a returned value would replace the output
+                pre.setdefault(pname, o.detach().clone())
+            hooks.append(mod.register_forward_hook(_keep))
+    for _ in range(epochs):
+        for r0, rows in batches:
+            fwd, loss = fwd_loss(r0, rows, eps[s])
+            model.optimizer1.zero_grad()
+            loss["total"].backward()
+            if s == 0:
+                for h_ in hooks:
+                    h_.remove()
+                for pname, a_ in pre.items():
+                    units = torch.nonzero(a_.abs().min(0).values < 2e-6 * a_.abs().max()).flatten().numpy()
+                    if units.size:
+                        out["knife/" + pname] = units.astype(np.int64)
+                out["mu"] = fwd["mu_multimodal"].detach().numpy().copy()
+                out["logvar"] = fwd["logvar_multimodal"].detach().numpy().copy()
+                if lean < 2:
+                    for i in range(m):
+                        out[f"xrecon{i}"] = fwd["x_recons"][i].loc.detach().numpy().copy()
+                for k, p in model.named_parameters():
+                    if p.grad is not None and not k.startswith("mlp."):
+                        out["grad/" + k] = p.grad.detach().numpy().copy()
+            model.optimizer1.step()
+            losses.append([float(loss["total"]), float(loss["kl"]), float(loss["ll"])])
+            s += 1
+    out["losses"] = np.array(losses, dtype=np.float64)
+    if lean < 2:
+        for k, v in sd_np(model).items():
+            if not k.startswith("mlp."):
+                out["final/" + k] = v
+        eps_t = rng.randn(n, z).astype(np.float32)
+        dfs = [pd.DataFrame(x.astype(np.float64)) for x in xs]
+        with injected_eps([torch.from_numpy(eps_t)]):
+            preds = model.pred_recon(dfs, c, torch.device("cpu"), combine)
+        devs = model.reconstruction_deviation_multimodal(dfs, preds)
+        out["eps_test"] = eps_t
+        for i in range(m):
+            out[f"pred{i}"] = preds[i]
+            out[f"dev{i}"] = np.asarray(devs[i], dtype=np.float64)
+            if lean == 0:
+                out[f"dev_roi{i}"] = ((dfs[i] - preds[i]) ** 2).to_numpy()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, "ok", losses[0], "steps", steps)
+
+
+def nmmlp_class(ref):
+    """The model class defined INSIDE multimodal_kfold_cvae_nmmlp.py (:39-233).  The script itself cannot be
+    imported (tensorflow / nilearn), so the class statement is cut out of the unmodified source with `ast` and
+    executed against the reference's own Encoder / Decoder / expert classes."""
+    import ast
+    src = open(os.path.join(REF, "multimodal_kfold_cvae_nmmlp.py")).read()
+    tree = ast.parse(src)
+    node = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "cVAE_multimodal_endtoend"][0]
+    ns = {"nn": torch.nn, "optim": torch.optim, "torch": torch, "np": np, "Encoder": ref.Encoder,
+          "Decoder": ref.Decoder, "ProductOfExperts": ref.ProductOfExperts,
+          "MixtureOfExperts": ref.MixtureOfExperts, "MoPoE": ref.MoPoE}
+    exec(compile(ast.Module(body=[node], type_ignores=[]), "multimodal_kfold_cvae_nmmlp.py", "exec"), ns)
+    return ns["cVAE_multimodal_endtoend"]
+
+
+def nmmlp_lr_case():
+    """The cyclic learning-rate lines of multimodal_kfold_cvae_nmmlp.py:357-381, executed verbatim."""
+    src = open(os.path.join(REF, "multimodal_kfold_cvae_nmmlp.py")).read().splitlines()
+    pick = lambda key: [l.strip() for l in src if l.strip().startswith(key)][0]
+    setup = [pick("gamma ="), pick("scale_fn ="), pick("base_lr ="), pick("max_lr ="), pick("step_size =")]
+    body = [pick("cycle ="), pick("x_lr ="), pick("clr =")]
+    out = {}
+    for n_samples, epochs in ((560, 30), (800, 200), (257, 7), (1000, 3)):
+        ns = {"np": np, "n_samples": n_samples, "batch_size": 256}
+        for l in setup:
+            exec(l, ns)
+        spe = -(-n_samples // 256)
+        lrs = []
+        for gs in range(1, epochs * spe + 1):
+            ns["global_step"] = gs
+            for l in body:
+                exec(l, ns)
+            lrs.append(ns["clr"])
+        out[f"lr/{n_samples}/{epochs}"] = np.array(lrs, dtype=np.float64)
+    np.savez_compressed(os.path.join(OUT, "nmmlp_lr.npz"), **out)
+    print("nmmlp_lr ok")
+
+
+def pieces_case(ref):
+    """encode / decode / combine_latent of the reference classes called directly (cVAE.py:415-428, 1127-1164)."""
+    rng = np.random.RandomState(60)
+    torch.manual_seed(60)
+    dims, hidden, z, c_dim, b = [13, 6, 21], [11, 9], 4, 7, 10
+    model = ref.cVAE_multimodal(list(dims), list(hidden), z, c_dim, modalities=3, non_linear=True)
+    out = {"dims": np.array(dims), "hidden": np.array(hidden), "z": z, "c_dim": c_dim}
+    for k, v in sd_np(model).items():
+        out["init/" + k] = v
+    c = onehot_cov(rng, b, c_dim, 5)
+    zz = rng.randn(b, z).astype(np.float32)
+    out["c"], out["zin"] = c, zz
+    ct = torch.from_numpy(c)
+    mus, lvs = [], []
+    with torch.no_grad():
+        for m_, d in enumerate(dims):
+            x = rng.randn(b, d).astype(np.float32)
+            out[f"x{m_}"] = x
+            mu, lv = model.encode(torch.from_numpy(x), ct, m_)
+            out[f"enc_mu{m_}"], out[f"enc_lv{m_}"] = mu.numpy(), lv.numpy()
+            out[f"dec{m_}"] = model.decode(torch.from_numpy(zz), ct, m_).loc.numpy()
+            out[f"dec_scale{m_}"] = model.decode(torch.from_numpy(zz), ct, m_).scale.numpy()
+            mus.append(mu); lvs.append(lv)
+        mus, var = torch.stack(mus), torch.exp(torch.stack(lvs))
+        for comb in ("PoE", "gPoE", "MoE", "MoPoE"):
+            mu_c, var_c = model.combine_latent(mus, var, comb)
+            out[f"comb_mu/{comb}"], out[f"comb_var/{comb}"] = mu_c.numpy(), var_c.numpy()
+    # the single-modality class
+    torch.manual_seed(61)
+    single = ref.cVAE(13, list(hidden), z, c_dim, non_linear=True)
+    for k, v in sd_np(single).items():
+        out["sinit/" + k] = v
+    with torch.no_grad():
+        mu, lv = single.encode(torch.from_numpy(out["x0"]), ct)
+        out["s_enc_mu"], out["s_enc_lv"] = mu.numpy(), lv.numpy()
+        out["s_dec"] = single.decode(torch.from_numpy(zz), ct).loc.numpy()
+    np.savez_compressed(os.path.join(OUT, "pieces_M3.npz"), **out)
+    print("pieces ok")
+
+
+def latent_case():
+    """latent_deviation / separate_latent_deviation (utils_vae.py:155-161).  utils_vae cannot be imported
+    (matplotlib / statsmodels), so the two function definitions are cut out of the unmodified source and executed."""
+    import ast
+    src = open(os.path.join(REF, "utils_vae.py")).read()
+    tree = ast.parse(src)
+    nodes = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in ("latent_deviation", "separate_latent_deviation")]
+    ns = {"np": np}
+    exec(compile(ast.Module(body=nodes, type_ignores=[]), "utils_vae.py", "exec"), ns)
+    rng = np.random.RandomState(62)
+    out = {}
+    for tag, (nt, n, z) in {"a": (560, 200, 10), "b": (37, 5, 32), "c": (300, 1000, 3), "d": (64, 40, 100)}.items():
+        mu_train = (rng.randn(nt, z) * rng.rand(z) * 2 + rng.randn(z)).astype(np.float32)
+        mu = (rng.randn(n, z) * 1.5).astype(np.float32)
+        logvar = (rng.randn(n, z) * 0.7 - 1).astype(np.float32)
+        var = np.exp(logvar.astype(np.float64))                   # pred_latent returns exp(logvar) (cVAE.py:546)
+        out[f"{tag}/mu_train"], out[f"{tag}/mu"], out[f"{tag}/logvar"] = mu_train, mu, logvar
+        out[f"{tag}/sep"] = ns["separate_latent_deviation"](mu_train.astype(np.float64), mu.astype(np.float64), var)
+        out[f"{tag}/dev"] = ns["latent_deviation"](mu_train.astype(np.float64), mu.astype(np.float64), var)
+    np.savez_compressed(os.path.join(OUT, "latent_deviation.npz"), **out)
+    print("latent_deviation ok")
+
+
+def ref_pickle_case(ref):
+    """``torch.save(model)`` of the reference's classes (train script :211-212): must load into the drop-in classes
+    through the root cVAE.py shim."""
+    torch.manual_seed(63)
+    m = ref.cVAE_multimodal([13, 6], [12], 5, 7, learning_rate=3e-4, modalities=2, non_linear=True)
+    torch.save(m, os.path.join(OUT, "ref_cVAE_multimodal.pkl"))
+    torch.manual_seed(64)
+    torch.save(ref.cVAE(13, [12, 8], 5, 7, non_linear=True), os.path.join(OUT, "ref_cVAE.pkl"))
+    print("ref pickles ok")
+
+
+def round2_cases(ref):
+    """Every BASELINE config at full size."""
+    # cfg1 (D=150) / cfg2 + cfg4 early fusion (D=348) / cfg5 (D=1000): one modality, B=256 + ragged 32-row batch
+    ref_loop_case(ref, "mm_M1_D150_full", [150], [110, 110], 10, 29, 288, 256, "gPoE", 2, 43, 27)
+    ref_loop_case(ref, "mm_M1_D348_full", [348], [110, 110], 10, 29, 288, 256, "gPoE", 2, 44, 27)
+    ref_loop_case(ref, "mm_M1_D1000_full", [1000], [110, 110], 10, 29, 288, 256, "gPoE", 2, 45, 27, lean=1)
+    # cfg3: four encoders / decoders with latent fusion at full size, every fusion op
+    ref_loop_case(ref, "mm_M4_full_gpoe", [116, 116, 116, 348], [110, 110], 10, 29, 288, 256, "gPoE", 2, 46, 27, lean=1)
+    for comb in ("PoE", "MoE", "MoPoE"):
+        ref_loop_case(ref, "mm_M4_full_" + comb.lower(), [116, 116, 116, 348], [110, 110], 10, 29, 288, 256, comb, 2,
+                      46, 27, lean=2, shared="mm_M4_full_gpoe")
+    # latent > 16 (unfused latent items), half 1 ragged (160 = 128 + 32), 4 hidden layers, hidden > 127 (generic engine)
+    ref_loop_case(ref, "mm_M1_Z32", [116], [110, 64], 32, 29, 416, 256, "poe", 2, 47, 27)
+    ref_loop_case(ref, "mm_M1_L4", [64], [96, 64, 48, 32], 8, 29, 160, 128, "poe", 2, 48, 27)
+    ref_loop_case(ref, "mm_M1_wide", [116], [256, 128], 32, 29, 80, 64, "poe", 2, 49, 27, lean=1)
+    # the nmmlp variant: -MSE reconstruction term, encoders -> decoders -> alphas RNG order
+    cls = nmmlp_class(ref)
+    ref_loop_case(ref, "nmmlp_M3_full", [116, 116, 116], [110, 110], 10, 29, 288, 256, "gPoE", 2, 50, 27, lean=1,
+                  model_cls=cls)
+    ref_loop_case(ref, "nmmlp_M2_small", [13, 6], [12], 5, 7, 14, 10, "MoPoE", 2, 51, 5, model_cls=cls)
+    nmmlp_lr_case()
+    ref_single_case(ref, "cvae_D150_full", 150, [110, 110], 10, 29, 256, 52, 27)
+    pieces_case(ref)
+    latent_case()
+    ref_pickle_case(ref)
+
+
 def host_case():
     """Third-party call sites of the host path (sklearn / pandas / numpy legacy RNG)."""
     from sklearn.metrics import auc, roc_curve
@@ -241,6 +499,13 @@ def main():
     sys.path.insert(0, REF)
     import cVAE as ref  # noqa: N813  (the unmodified reference module)
 
+    if "--round2b" in sys.argv:
+        pieces_case(ref); latent_case(); ref_pickle_case(ref)
+        return
+    if "--round2" in sys.argv:      # only the cases added in round 2 (the others regenerate bit-identically)
+        round2_cases(ref)
+        return
+
     # full-size single modality (cfg1 real AAL width) and the cVAE class
     ref_multimodal_case(ref, "mm_M1_D116_full", [116], [110, 110], 10, 29, 256, "gPoE", 3, 42, 27)
     ref_single_case(ref, "cvae_D116_full", 116, [110, 110], 10, 29, 256, 42, 27)
@@ -253,6 +518,7 @@ def main():
     host_case()
     merge_case()
     stored_deviation_case()
+    round2_cases(ref)
 
 
 if __name__ == "__main__":

@@ -1,0 +1,194 @@
+"""GPU tests of the drop-in boundary beyond the training loop: encode / decode / reparameterise / combine_latent of
+both classes against calls recorded from the reference (tests/golden/pieces_M3.npz), the per-step API over a RAGGED
+epoch (Adam moments must survive the change of minibatch size), the nmmlp program end to end, the latent-space
+normative deviation kernel, classification metrics against the sklearn recordings, whole-epoch training of members
+with different fold sizes."""
+import argparse
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+import torch
+
+from helpers import load, loop_batches, relerr, sub
+
+pytestmark = pytest.mark.gpu
+REL = 1e-4
+
+
+def test_pieces_encode_decode_combine_vs_reference(golden_dir):
+    from multi_modal_normative_modeling_b200.cVAE import cVAE, cVAE_multimodal
+    g = load(golden_dir, "pieces_M3")
+    dims = [int(d) for d in g["dims"]]
+    model = cVAE_multimodal(dims, [int(h) for h in g["hidden"]], int(g["z"]), int(g["c_dim"]), modalities=3, non_linear=True)
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in sub(g, "init/").items()})
+    model.to("cuda")
+    c = torch.from_numpy(g["c"]).cuda()
+    z = torch.from_numpy(g["zin"]).cuda()
+    mus, lvs = [], []
+    for m in range(3):
+        mu, lv = model.encode(torch.from_numpy(g[f"x{m}"]).cuda(), c, m)
+        assert relerr(mu.cpu().numpy(), g[f"enc_mu{m}"]) < REL and relerr(lv.cpu().numpy(), g[f"enc_lv{m}"]) < REL
+        d = model.decode(z, c, m)
+        assert relerr(d.loc.cpu().numpy(), g[f"dec{m}"]) < REL
+        assert relerr(d.scale.cpu().numpy(), g[f"dec_scale{m}"]) < 1e-6
+        mus.append(mu); lvs.append(lv)
+    mus, var = torch.stack(mus), torch.exp(torch.stack(lvs))
+    for comb in ("PoE", "gPoE", "MoE", "MoPoE", "mopoe", "GPOE"):
+        key = {"mopoe": "MoPoE", "GPOE": "gPoE"}.get(comb, comb)
+        mu_c, var_c = model.combine_latent(mus, var, comb)
+        assert relerr(mu_c.detach().cpu().numpy(), g[f"comb_mu/{key}"]) < REL
+        assert relerr(var_c.detach().cpu().numpy(), g[f"comb_var/{key}"]) < REL
+    with pytest.raises(ValueError, match="No such combination method"):
+        model.combine_latent(mus, var, "concat")
+    torch.manual_seed(5)
+    e = torch.randn_like(mus[0])
+    torch.manual_seed(5)
+    assert torch.allclose(model.reparameterise(mus[0], lvs[0]), mus[0] + e * torch.exp(0.5 * lvs[0]))
+    single = cVAE(13, [int(h) for h in g["hidden"]], int(g["z"]), int(g["c_dim"]), non_linear=True)
+    single.load_state_dict({k: torch.from_numpy(v) for k, v in sub(g, "sinit/").items()})
+    single.to("cuda")
+    mu, lv = single.encode(torch.from_numpy(g["x0"]).cuda(), c)
+    assert relerr(mu.cpu().numpy(), g["s_enc_mu"]) < REL and relerr(lv.cpu().numpy(), g["s_enc_lv"]) < REL
+    assert relerr(single.decode(z, c).loc.cpu().numpy(), g["s_dec"]) < REL
+    model.close(); single.close()
+
+
+@pytest.mark.parametrize("name", ["nmmlp_M2_small", "mm_M1_L4"])
+def test_module_per_step_api_over_a_ragged_epoch(golden_dir, name):
+    """The reference's loop body on the drop-in module over full AND partial batches: the Adam moments live in the
+    module (not in a per-batch-size engine), so the trajectory matches the reference's recording."""
+    from multi_modal_normative_modeling_b200.cVAE import cVAE_multimodal, cVAE_multimodal_endtoend
+    g = load(golden_dir, name)
+    nmmlp = name.startswith("nmmlp")
+    dims = [int(d) for d in g["dims"]]
+    torch.manual_seed(int(g["seed"]))
+    cls = cVAE_multimodal_endtoend if nmmlp else cVAE_multimodal
+    model = cls(dims, [int(h) for h in g["hidden"]], int(g["z"]), int(g["c_dim"]), learning_rate=1e-4,
+                modalities=len(dims), non_linear=True).to("cuda")
+    xs = [torch.from_numpy(g[f"x{i}"]).cuda() for i in range(len(dims))]
+    c = torch.from_numpy(g["c"]).cuda()
+    n, b, epochs = int(g["n"]), int(g["batch"]), int(g["epochs"])
+    real_randn = torch.randn
+    losses, s = [], 0
+    for _ in range(epochs):
+        for r0, rows in loop_batches(n, b):
+            torch.randn = lambda *a, **k: torch.from_numpy(g["eps"][s][:rows]).to(k.get("device", "cpu"))
+            try:
+                fwd = model.forward_multimodal([x[r0:r0 + rows] for x in xs], [c[r0:r0 + rows]] * len(dims), str(g["combine"]))
+            finally:
+                torch.randn = real_randn
+            loss = model.loss_function_multimodal(xs, fwd, None) if nmmlp else model.loss_function_multimodal(xs, fwd)
+            model.optimizer1.zero_grad()
+            loss["total"].backward()
+            model.optimizer1.step()
+            losses.append([float(loss["total"]), float(loss["kl"]), float(loss["ll"])])
+            s += 1
+    assert np.allclose(np.array(losses), g["losses"], rtol=REL), (losses, g["losses"])
+    init = sub(g, "init/")
+    for k, v in sub(g, "final/").items():
+        got = model.state_dict()[k].cpu().numpy()
+        assert relerr(got, v) < 1e-5, k
+        d_ref = v - init[k]
+        if np.abs(d_ref).max() > 0:          # the UPDATE: a reset of the Adam moments would show up as a 3x-lr spike
+            dev = np.sort(np.abs((got - init[k]) - d_ref).ravel() / np.abs(d_ref).max())
+            assert dev[-max(2, dev.size // 1000) - 1] < 2e-3, k
+    st = model.optimizer1.state_dict()["state"]
+    assert len(st) > 0 and int(next(iter(st.values()))["step"]) == len(losses)
+    assert len(model._cache()) == 2                      # one engine per minibatch size, none rebuilt
+    with pytest.raises(ValueError):
+        model.loss_function_multimodal(xs, {"mu_multimodal": fwd["mu_multimodal"].clone()})
+    model.close()
+
+
+def test_train_epochs_with_unequal_fold_sizes_and_lr_schedule_bounds():
+    """Members with DIFFERENT steps per epoch in one launch: each takes exactly epochs x its own steps (ADVICE r1:
+    over-training + out-of-bounds lr_steps read); a schedule shorter than the requested steps is refused."""
+    from multi_modal_normative_modeling_b200 import EnsembleTrainer, MemberSpec, pack_rows
+    from oracle import cvae_torch
+    rng = np.random.RandomState(4)
+    d, c_dim, z, batch, epochs = 12, 5, 3, 8, 3
+    specs, refs = [], []
+    for k, n in enumerate((23, 8, 17, 40)):
+        x = rng.randn(n, d).astype(np.float32)
+        c = np.zeros((n, c_dim), np.float32); c[np.arange(n), rng.randint(0, c_dim, n)] = 1
+        spe = -(-n // batch)
+        lr = (1e-4 * (1 + 0.3 * np.cos(np.arange(epochs * spe)))).astype(np.float32)
+        torch.manual_seed(20 + k)
+        model = cvae_torch.OracleCVAEMultimodal([d], [10, 7], z, c_dim, 1e-4, 1, True)
+        sd = {a: b.detach().clone() for a, b in model.state_dict().items()}
+        specs.append(MemberSpec([d], [10, 7], z, c_dim, [pack_rows(torch.from_numpy(x).cuda(), torch.from_numpy(c).cuda())],
+                                batch=batch, seed=100 + k, state_dict=sd, lr_steps=torch.from_numpy(lr).cuda()))
+        refs.append((model, x, c, lr, spe))
+    for flags in (0, 8, 16):                      # pipelined, FP32, generic engines
+        tr = EnsembleTrainer(specs)
+        losses = tr.train_epochs(epochs, record_losses=True, flags=flags).cpu().numpy()
+        done = tr.steps_done()
+        for k, (model, x, c, lr, spe) in enumerate(refs):
+            assert int(done[k]) == epochs * spe, (k, done)
+            assert np.isfinite(losses[k, :epochs * spe]).all() and np.isnan(losses[k, epochs * spe:]).all()
+        # the in-kernel eps stream is seeded per member: replay it through the oracle loop
+        from multi_modal_normative_modeling_b200 import scoring
+        k = 0
+        model, x, c, lr, spe = refs[k]
+        torch.manual_seed(20 + k)
+        model = cvae_torch.OracleCVAEMultimodal([d], [10, 7], z, c_dim, 1e-4, 1, True)
+        log = cvae_torch.reference_train_loop(
+            model, [torch.from_numpy(x)], [torch.from_numpy(c).long()], "poe", epochs, batch,
+            eps_fn=lambda s, rows: scoring.philox_normal(100 + k, s, batch * z, 0).view(batch, z)[:rows].cpu(),
+            lr_fn=lambda step: float(lr[step - 1]))
+        assert np.allclose(losses[k, :epochs * spe], log, rtol=2e-4, atol=1e-5)
+        with pytest.raises(RuntimeError, match="lr_steps"):
+            tr.train_epochs(1)                    # the schedules are exhausted
+        with pytest.raises(RuntimeError, match="lr_steps"):
+            tr.train_steps(1)
+        tr.close()
+
+
+def test_latent_deviation_kernel_vs_reference(golden_dir):
+    from multi_modal_normative_modeling_b200 import scoring
+    g = load(golden_dir, "latent_deviation")
+    tags = "abcd"
+    z, dev = scoring.latent_deviation([torch.from_numpy(g[f"{t}/mu_train"]).cuda() for t in tags],
+                                      [torch.from_numpy(g[f"{t}/mu"]).cuda() for t in tags],
+                                      [torch.from_numpy(g[f"{t}/logvar"]).cuda() for t in tags])
+    torch.cuda.synchronize()
+    for i, t in enumerate(tags):
+        assert relerr(z[i].cpu().numpy(), g[f"{t}/sep"]) < 1e-5, t
+        assert relerr(dev[i].cpu().numpy(), g[f"{t}/dev"]) < 1e-5, t
+
+
+def test_classification_performance_vs_sklearn_recordings(golden_dir):
+    """cli.classification_performance (GPU pair-count AUC + Youden threshold) vs the values recorded from sklearn at
+    the reference's call sites (group analysis :105-157)."""
+    from multi_modal_normative_modeling_b200 import cli
+    g = load(golden_dir, "host_callsites")
+    for tag in ("a", "b"):
+        auc, acc, sens, spec, ratio = cli.classification_performance(g[f"roc/{tag}/scores"], g[f"roc/{tag}/labels"],
+                                                                      torch.device("cuda", 0))
+        assert abs(auc - float(g[f"roc/{tag}/auc"])) < 1e-12
+        assert acc == float(g[f"roc/{tag}/acc"]) and sens == float(g[f"roc/{tag}/sens"]) and spec == float(g[f"roc/{tag}/spec"])
+        assert abs(ratio - auc / (1 - auc)) < 1e-12
+
+
+def test_nmmlp_program_end_to_end(tmp_path):
+    """multimodal_kfold_cvae_nmmlp.py all: HC-only training rows, -MSE term, cyclic LR, diagnosis files, metrics."""
+    from multi_modal_normative_modeling_b200 import cli, synthetic
+    synthetic.write_dataset(str(tmp_path), "HCPimage", n=300, seed=5)
+    out = cli.nmmlp_main(["all", "-R", "HCPimage", "-H", "32", "24", "6", "-P", "SE-gPoE", "-E", "4", "-K", "3"], root=tmp_path)
+    assert out["losses"].shape == (3, 4, 3) and np.isfinite(out["losses"]).all()
+    assert (out["losses"][:, :, 2] <= 0).all()                      # ll = -MSE
+    md = tmp_path / "outputs" / "kfold_analysis" / "supervised_cvae"
+    m = torch.load(md / "000" / "cVAE_model.pkl", weights_only=False)
+    assert type(m).__name__ == "cVAE_multimodal_endtoend" and any(k.startswith("mlp.") for k in m.state_dict())
+    diag = pd.read_csv(md / "001" / "diagnosis_results.csv")
+    assert list(diag.columns) == ["participant_id", "Diagnosis", "True_Label"] and set(diag["True_Label"]) <= {0, 1}
+    errs = [pd.read_csv(md / "001" / n / f"reconstruction_error_{n}.csv")["Reconstruction error"].to_numpy()
+            for n in ("T1w_sMRI", "T2w_sMRI", "fMRI")]
+    assert np.allclose(diag["Diagnosis"].to_numpy(), np.mean(errs, axis=0), rtol=1e-5)
+    assert out["metrics"].shape == (3, 5) and (out["metrics"][:, 0] >= 0).all() and (out["metrics"][:, 0] <= 1).all()
+    assert (tmp_path / "outputs" / "analysis_results" / "performance_metrics.txt").exists()
+    # the training rows were healthy controls only: the schedule length = epochs * ceil(n_hc_rows / 256)
+    tr_ids = pd.read_csv(tmp_path / "outputs" / "kfold_analysis" / "train_ids_000.csv")
+    assert len(tr_ids) > 0

@@ -1,0 +1,146 @@
+"""Pin the oracle against the full-size vectors recorded from the UNMODIFIED reference in round 2
+(oracle/make_golden.py::round2_cases): every BASELINE config shape (D=150 / 348 / 1000, four modalities
+116/116/116/348 with every fusion op), latent 32, four hidden layers, hidden > 127, a ragged last batch, the
+model class and the cyclic learning-rate lines of multimodal_kfold_cvae_nmmlp.py."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import LOOP_CASES, drop_knife_rows, is_nmmlp, load, loop_batches, sub
+from oracle import cvae_numpy, cvae_torch
+
+
+def build(g, name):
+    dims = [int(d) for d in g["dims"]]
+    torch.manual_seed(int(g["seed"]))
+    model = cvae_torch.OracleCVAEMultimodal(dims, [int(h) for h in g["hidden"]], int(g["z"]), int(g["c_dim"]), 1e-4,
+                                            len(dims), non_linear=True,
+                                            loss_kind="neg_mse" if is_nmmlp(name) else "gauss_ll",
+                                            rng_order="nmmlp" if is_nmmlp(name) else "cvae")
+    return model, dims
+
+
+@pytest.mark.parametrize("name", LOOP_CASES)
+def test_seed_exact_init(golden_dir, name):
+    g = load(golden_dir, name)
+    model, _ = build(g, name)
+    assert np.array_equal(torch.randn(4).numpy(), g["next_draw"])       # generator state after construction
+    init = sub(g, "init/")
+    sd = model.state_dict()
+    assert set(sd) == set(init)
+    for k, v in init.items():
+        assert np.array_equal(sd[k].numpy(), v), k
+
+
+@pytest.mark.parametrize("name", LOOP_CASES)
+def test_torch_port_loop(golden_dir, name):
+    """The restated loop body (oracle/cvae_torch.py) over full and partial batches == the reference's."""
+    g = load(golden_dir, name)
+    model, dims = build(g, name)
+    n, b, epochs = int(g["n"]), int(g["batch"]), int(g["epochs"])
+    xs = [torch.from_numpy(g[f"x{i}"]) for i in range(len(dims))]
+    cs = [torch.from_numpy(g["c"]).long() for _ in dims]
+    comb = str(g["combine"])
+    eps = torch.from_numpy(g["eps"])
+    if "lossr" in g:
+        r0, rows = loop_batches(n, b)[-1]
+        out = model.step_losses([x[r0:r0 + rows] for x in xs], [c[r0:r0 + rows] for c in cs], comb,
+                                eps[int(g["ragged_step"])][:rows])
+        np.testing.assert_allclose([float(out["total"]), float(out["kl"]), float(out["ll"])], g["lossr"], rtol=1e-5)
+        model.optimizer1.zero_grad()
+        out["total"].backward()
+        for k, v in sub(g, "gradr/").items():
+            np.testing.assert_allclose(dict(model.named_parameters())[k].grad.numpy(), v, rtol=1e-4,
+                                       atol=1e-6 * np.abs(v).max(), err_msg=k)
+        model.optimizer1.zero_grad()
+    log = cvae_torch.reference_train_loop(model, xs, cs, comb, epochs, b, eps_fn=lambda s, rows: eps[s][:rows])
+    np.testing.assert_allclose(log, g["losses"], rtol=1e-5)
+    for k, v in sub(g, "final/").items():
+        np.testing.assert_allclose(model.state_dict()[k].numpy(), v, rtol=1e-5, atol=1e-7, err_msg=k)
+
+
+@pytest.mark.parametrize("name", [c for c in LOOP_CASES if "D1000" not in c])
+def test_numpy_math_fp64(golden_dir, name):
+    """The hand-derived formulas the CUDA kernels implement vs the reference's autograd, first full batch."""
+    g = load(golden_dir, name)
+    dims = [int(d) for d in g["dims"]]
+    b = int(g["batch"])
+    p = {k: v.astype(np.float64) for k, v in sub(g, "init/").items()}
+    xs = [g[f"x{i}"][:b].astype(np.float64) for i in range(len(dims))]
+    cs = [g["c"][:b].astype(np.float64) for _ in dims]
+    losses, outs, grads = cvae_numpy.step(p, xs, cs, g["eps"][0].astype(np.float64), str(g["combine"]),
+                                          loss_kind="neg_mse" if is_nmmlp(name) else "gauss_ll")
+    np.testing.assert_allclose([losses["total"], losses["kl"], losses["ll"]], g["losses"][0], rtol=3e-6)
+    np.testing.assert_allclose(outs["mu"], g["mu"], rtol=1e-4, atol=2e-6)
+    for k, v in sub(g, "grad/").items():
+        got, want = drop_knife_rows(g, k, grads[k], v)
+        assert np.abs(got - want).max() / (np.abs(v).max() + 1e-12) < 1e-4, k
+
+
+def test_cyclic_lr_vs_reference_lines(golden_dir):
+    """oracle.cvae_torch.cyclic_lr AND the product's cli.cyclic_lr_schedule vs the reference's own lines
+    (multimodal_kfold_cvae_nmmlp.py:357-381, executed verbatim by make_golden.py)."""
+    from multi_modal_normative_modeling_b200 import cli
+    g = load(golden_dir, "nmmlp_lr")
+    for key, want in g.items():
+        _, n_samples, epochs = key.split("/")
+        n_samples, epochs = int(n_samples), int(epochs)
+        got = np.array([cvae_torch.cyclic_lr(s, n_samples) for s in range(1, len(want) + 1)])
+        np.testing.assert_allclose(got, want, rtol=1e-14)
+        sched = cli.cyclic_lr_schedule(len(want), n_samples)
+        assert sched.dtype == np.float32
+        np.testing.assert_allclose(sched, want.astype(np.float32), rtol=1e-7)
+
+
+def test_single_modality_cvae_class_d150(golden_dir):
+    g = load(golden_dir, "cvae_D150_full")
+    torch.manual_seed(int(g["seed"]))
+    model = cvae_torch.OracleCVAE(int(g["d"]), [int(h) for h in g["hidden"]], int(g["z"]), int(g["c_dim"]),
+                                  non_linear=True)
+    assert np.array_equal(torch.randn(4).numpy(), g["next_draw"])
+    x, c = torch.from_numpy(g["x"]), torch.from_numpy(g["c"]).long()
+    out = model.step_losses(x, c, torch.from_numpy(g["eps"]))
+    np.testing.assert_allclose([float(out["total"]), float(out["kl"]), float(out["ll"])], g["losses"], rtol=1e-5)
+
+
+def test_latent_deviation_oracle_vs_reference_functions(golden_dir):
+    """oracle.deviation.latent_* == the reference's own functions (utils_vae.py:155-161, executed by make_golden)."""
+    from oracle import deviation
+    g = load(golden_dir, "latent_deviation")
+    for tag in "abcd":
+        mt, mu, lv = (g[f"{tag}/{k}"].astype(np.float64) for k in ("mu_train", "mu", "logvar"))
+        np.testing.assert_allclose(deviation.latent_zscores(mt, mu, np.exp(lv)), g[f"{tag}/sep"], rtol=1e-13)
+        np.testing.assert_allclose(deviation.latent_deviation(mt, mu, np.exp(lv)), g[f"{tag}/dev"], rtol=1e-13)
+
+
+def test_product_classes_seed_exact_and_load_reference_pickles(golden_dir):
+    """Host side of the drop-in boundary (no GPU): the nmmlp class draws in the reference's order
+    (encoders -> decoders -> alphas -> MLP); a cVAE_model.pkl written by the REFERENCE unpickles into the drop-in
+    classes through the root cVAE.py shim with identical weights."""
+    import os
+    import sys
+    from multi_modal_normative_modeling_b200.cVAE import cVAE, cVAE_multimodal, cVAE_multimodal_endtoend
+    for name in ("nmmlp_M2_small", "nmmlp_M3_full"):
+        g = load(golden_dir, name)
+        dims = [int(d) for d in g["dims"]]
+        torch.manual_seed(int(g["seed"]))
+        m = cVAE_multimodal_endtoend(dims, [int(h) for h in g["hidden"]], int(g["z"]), int(g["c_dim"]),
+                                     modalities=len(dims), non_linear=True)
+        assert np.array_equal(torch.randn(4).numpy(), g["next_draw"])
+        for k, v in sub(g, "init/").items():
+            assert np.array_equal(m.state_dict()[k].numpy(), v), k
+        assert any(k.startswith("mlp.") for k in m.state_dict())
+        assert not any(p is q for p in m.mlp.parameters() for q in m.optimizer1.param_groups[0]["params"])
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    assert root in sys.path
+    sys.modules.pop("cVAE", None)
+    m = torch.load(os.path.join(golden_dir, "ref_cVAE_multimodal.pkl"), weights_only=False)
+    assert type(m) is cVAE_multimodal and m._dims == [13, 6] and m._hidden == [12] and m._non_linear
+    assert m.optimizer1.param_groups[0]["lr"] == 3e-4 and len(m.optimizer1.param_groups[0]["params"]) == 2 * 6 + 2 * 5 + 2
+    torch.manual_seed(63)
+    fresh = cVAE_multimodal([13, 6], [12], 5, 7, modalities=2, non_linear=True)
+    for (k, a), b in zip(fresh.state_dict().items(), m.state_dict().values()):
+        assert torch.equal(a, b), k
+    s = torch.load(os.path.join(golden_dir, "ref_cVAE.pkl"), weights_only=False)
+    assert type(s) is cVAE and s._dims == [13] and s._hidden == [12, 8]
+    assert hasattr(s, "optimizer2") and hasattr(s, "optimizer3")
