@@ -328,8 +328,9 @@ class _FusedBase(nn.Module):
 
 
 def _as_float_cuda(a, dev):
-    a = getattr(a, "values", a)
-    return torch.as_tensor(np.asarray(a) if not torch.is_tensor(a) else a).to(device=dev, dtype=torch.float32)
+    if not torch.is_tensor(a):
+        a = torch.as_tensor(np.asarray(getattr(a, "values", a)))      # DataFrame / ndarray / list
+    return a.detach().to(device=dev, dtype=torch.float32)
 
 
 def fuse_latent(mus, variances, combine, alphas=None):

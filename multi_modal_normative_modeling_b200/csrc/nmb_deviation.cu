@@ -154,15 +154,32 @@ void launch_deviation(const SegTable& t, int n_seg, int max_rows, cudaStream_t s
 }
 
 // ---- ROC-AUC by exact pair counting ------------------------------------------------------------
-// CTA = (column, segment).  Negatives are sorted in shared memory (bitonic, chunked when they do
-// not fit); every positive is binary-searched: U2 += 2*#(neg < s) + #(neg == s).  Integer
-// arithmetic -> bit-exact against oracle/deviation.py:auc_pairs.
-constexpr int kAucChunk = 8192;   // negatives per sorted chunk (32 KB)
+// CTA = (group of 8 adjacent columns, segment); warp w owns column 8 g + w.  The score table is row-major, so the 8
+// columns of a row are 32 contiguous bytes = one DRAM sector: tiles of rows are read with every byte of every sector
+// used (a CTA per column with stride n_cols used 4 of 32) and transposed into shared memory.  Per column the
+// negatives of a tile are sorted (warp-level bitonic network in shared memory, +inf sentinels for the non-negatives)
+// and every positive of every tile is binary-searched in them:  U2 += 2 #(neg < s) + #(neg == s).  Integer
+// arithmetic -> bit-exact against oracle/deviation.py:auc_pairs (== sklearn roc_curve + auc).
+constexpr int kAucCols = 8;       // columns per CTA = warps per CTA
+constexpr int kAucTile = 1024;    // rows per tile (2 x 32 KB of shared memory)
 
-__device__ inline void bitonic_sort(float* v, int n_pow2) {
+// rows [r0, r0 + m) x columns [c0, c0 + 8) of a row-major table -> dst[col][row]; `pad` fills columns / rows beyond
+// the table.  A warp reads 4 rows x 8 columns per instruction (4 full sectors).
+__device__ __forceinline__ void auc_load_tile(const float* __restrict__ sc, int n_cols, int c0, int r0, int m, int p2,
+                                              const uint8_t* __restrict__ lab, bool negatives_only, float* dst) {
+  const int cj = threadIdx.x & 7;
+  const bool col_ok = c0 + cj < n_cols;
+  for (int i = threadIdx.x >> 3; i < p2; i += 32) {
+    float v = __int_as_float(0x7f800000);                       // +inf sorts behind every real negative
+    if (i < m && col_ok && (!negatives_only || lab[r0 + i] == 0)) v = sc[(long long)(r0 + i) * n_cols + c0 + cj];
+    dst[cj * kAucTile + i] = v;
+  }
+}
+
+__device__ __forceinline__ void warp_bitonic_sort(float* v, int n_pow2, int lane) {
   for (int k = 2; k <= n_pow2; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
+      for (int i = lane; i < n_pow2; i += 32) {
         const int p = i ^ j;
         if (p > i) {
           const float a = v[i], b = v[p];
@@ -170,79 +187,88 @@ __device__ inline void bitonic_sort(float* v, int n_pow2) {
           if ((a > b) == up) { v[i] = b; v[p] = a; }
         }
       }
-      __syncthreads();
+      __syncwarp();
     }
   }
 }
 
 __global__ void __launch_bounds__(256) auc_kernel(AucTable t) {
-  extern __shared__ float neg[];
-  __shared__ unsigned long long s_part[8];
+  extern __shared__ float auc_smem[];
+  float* negs = auc_smem;                                  // [8][kAucTile] sorted negatives of the current tile
+  float* vals = auc_smem + kAucCols * kAucTile;             // [8][kAucTile] raw scores of the current positive tile
   __shared__ int s_cnt[8];
   const int s = blockIdx.y;
   const int n_cols = t.n_cols[s];
-  const int col = blockIdx.x;
-  if (col >= n_cols) return;
-  const float* sc = t.scores[s] + col;
+  const int c0 = blockIdx.x * kAucCols;
+  if (c0 >= n_cols) return;
+  const float* sc = t.scores[s];
   const uint8_t* lab = t.labels[s];
   const int n = t.n_rows[s];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const bool single = n <= kAucTile;                         // the usual case: one tile holds every row
   unsigned long long u2 = 0;
   int n_neg_total = 0;
-  for (int r0 = 0; r0 < n; r0 += kAucChunk) {
-    const int m = min(kAucChunk, n - r0);
-    int p2 = 1;
+  for (int r0 = 0; r0 < n; r0 += kAucTile) {
+    const int m = min(kAucTile, n - r0);
+    int p2 = 32;
     while (p2 < m) p2 <<= 1;
-    // non-negatives and the pow2 tail become +inf sentinels that sort behind every real negative
     int cnt = 0;
-    for (int i = threadIdx.x; i < p2; i += blockDim.x) {
-      const bool is_neg = i < m && lab[r0 + i] == 0;
-      neg[i] = is_neg ? sc[(long long)(r0 + i) * n_cols] : __int_as_float(0x7f800000);
-      cnt += is_neg;
-    }
+    for (int i = threadIdx.x; i < m; i += 256) cnt += lab[r0 + i] == 0;
     for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    __syncthreads();                                         // previous tile fully consumed (negs, s_cnt)
     if (lane == 0) s_cnt[w] = cnt;
+    auc_load_tile(sc, n_cols, c0, r0, m, p2, lab, true, negs);
+    if (single) auc_load_tile(sc, n_cols, c0, 0, n, p2, lab, false, vals);
     __syncthreads();
     int n_neg = 0;
-    for (int k = 0; k < nw; ++k) n_neg += s_cnt[k];
-    bitonic_sort(neg, p2);
-    if (n_neg > 0) {
-      for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        if (lab[i] == 0) continue;
-        const float v = sc[(long long)i * n_cols];
+    for (int k = 0; k < 8; ++k) n_neg += s_cnt[k];
+    n_neg_total += n_neg;
+    float* mine = negs + w * kAucTile;
+    const bool active = c0 + w < n_cols;                      // warp-uniform; barriers below stay CTA-uniform
+    if (active && n_neg > 0) warp_bitonic_sort(mine, p2, lane);
+    if (n_neg == 0) continue;                                 // CTA-uniform
+    for (int q0 = 0; q0 < n; q0 += kAucTile) {                // positives of every tile against this tile's negatives
+      const int mq = min(kAucTile, n - q0);
+      if (!single) {
+        __syncthreads();
+        auc_load_tile(sc, n_cols, c0, q0, mq, mq, lab, false, vals);
+        __syncthreads();
+      }
+      if (!active) continue;
+      const float* pv = vals + w * kAucTile;
+      for (int i = lane; i < mq; i += 32) {
+        if (lab[q0 + i] == 0) continue;
+        const float v = pv[i];
         int lo = 0, hi = n_neg;
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (neg[mid] < v) lo = mid + 1; else hi = mid; }
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (mine[mid] < v) lo = mid + 1; else hi = mid; }
         const int less = lo;
         hi = n_neg;
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (neg[mid] <= v) lo = mid + 1; else hi = mid; }
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (mine[mid] <= v) lo = mid + 1; else hi = mid; }
         u2 += 2ull * less + (unsigned long long)(lo - less);
       }
     }
-    n_neg_total += n_neg;
-    __syncthreads();   // everyone is done with this chunk before it is overwritten
   }
+  if (c0 + w >= n_cols) return;
   int n_pos = 0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) n_pos += lab[i] != 0;
+  for (int i = lane; i < n; i += 32) n_pos += lab[i] != 0;
   for (int o = 16; o > 0; o >>= 1) {
     u2 += __shfl_xor_sync(0xffffffffu, u2, o);
     n_pos += __shfl_xor_sync(0xffffffffu, n_pos, o);
   }
-  if (lane == 0) { s_part[w] = u2; s_cnt[w] = n_pos; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned long long tot = 0;
-    int npos = 0;
-    for (int k = 0; k < nw; ++k) { tot += s_part[k]; npos += s_cnt[k]; }
-    if (t.out_u2 && t.out_u2[s]) t.out_u2[s][col] = tot;
-    t.out_auc[s][col] = (npos > 0 && n_neg_total > 0)
-        ? (double)tot / (2.0 * (double)npos * (double)n_neg_total) : nan("");
+  if (lane == 0) {
+    const int col = c0 + w;
+    if (t.out_u2 && t.out_u2[s]) t.out_u2[s][col] = u2;
+    t.out_auc[s][col] = (n_pos > 0 && n_neg_total > 0)
+        ? (double)u2 / (2.0 * (double)n_pos * (double)n_neg_total) : nan("");
   }
 }
 
 void launch_auc(const AucTable& t, int n_seg, int max_cols, cudaStream_t st) {
   if (n_seg == 0 || max_cols == 0) return;
-  dim3 grid(max_cols, n_seg);
-  auc_kernel<<<grid, 256, kAucChunk * sizeof(float), st>>>(t);
+  const int smem = 2 * kAucCols * kAucTile * (int)sizeof(float);
+  cudaFuncSetAttribute(auc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  dim3 grid((max_cols + kAucCols - 1) / kAucCols, n_seg);
+  auc_kernel<<<grid, 256, smem, st>>>(t);
 }
 
 // ---- latent-space normative deviation (utils_vae.py:155-161) --------------------------------------------------

