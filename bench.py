@@ -5,17 +5,19 @@ models) & deviation subjects/s at 1/2/4/8 B200 vs CPU).
     python bench.py --gpus N --steps K --warmup W            # this framework (CUDA, libnmb.so)
     python bench.py --impl reference --steps K --warmup W    # the reference's PyTorch CPU path
 
-Workload (config.workload = "cfg4"): 5 folds x {T1w, T2w, fMRI (D=116), early fusion (D=348)} x 24
-seeds = 480 independent cVAEs per GPU (weak scaling: every rank trains its own 480-member
-ensemble with distinct seeds), hidden [110,110], latent 10, C=29, batch 256, 800 bootstrap rows
-per fold, synthetic HCP-shaped data, reference-exact random initialisation.
-One "step" = `--epochs-per-step` epochs (default 5 = 20 minibatch steps) of EVERY member in ONE
-fused kernel launch (forward + loss + backward + Adam).  `value` counts training samples only;
-deviation scoring is timed separately and reported under "deviation".
+Workload (config.workload = "cfg4", BASELINE configs[3]): ONE ensemble of 5 folds x {T1w, T2w, fMRI (D=116), early
+fusion (D=348)} x 24 seeds = 480 independent cVAEs, hidden [110,110], latent 10, C=29, batch 256, 800 bootstrap rows
+per fold, synthetic HCP-shaped data, reference-exact random initialisation.  With N > 1 the SAME 480 members are
+sharded over the N ranks (strong scaling, `scaling: "strong"`; no collective while training, one all-gather of the
+per-member deviation records); the weak-scaling figure (480 members on every rank) is reported under extra.weak.
+One "step" = `--epochs-per-step` epochs (default 5 = 20 minibatch steps) of EVERY member in ONE fused kernel launch
+(forward + loss + backward + Adam).  `value` counts training samples only; deviation scoring is timed separately and
+reported under "deviation".
 """
 from __future__ import annotations
 
 import argparse
+import importlib.util
 import json
 import os
 import sys
@@ -35,77 +37,167 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--seeds", type=int, default=24, help="seeds per (fold, modality): 24 -> 480 members per GPU")
+    ap.add_argument("--seeds", type=int, default=24, help="seeds per (fold, modality): 24 -> 480 members")
     ap.add_argument("--epochs-per-step", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-deviation", action="store_true")
+    ap.add_argument("--no-weak", action="store_true", help="N > 1: skip the extra weak-scaling measurement")
+    ap.add_argument("--no-module-step", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the bounded CPU sample")
     return ap.parse_args()
 
 
-def config(args, extra=None):
-    c = {"workload": "cfg4: 5 folds x 4 modalities (D=116,116,116,348) x %d seeds = %d cVAEs per GPU"
-                     % (args.seeds, 20 * args.seeds),
-         "hidden": [110, 110], "latent": 10, "c_dim": 29, "batch": 256, "n_train": 800, "n_test": 200,
-         "epochs_per_step": args.epochs_per_step, "members_per_gpu": 20 * args.seeds,
-         "parallelism": "member-sharded, no gradient collective",
-         "l2": "working set (params+Adam+scratch > 600 MB) exceeds the 126 MB L2"}
-    if extra:
-        c.update(extra)
-    return c
+def config(args):
+    """Identical for both arms (the driver compares them)."""
+    return {"workload": "cfg4: 5 folds x 4 modalities (D=116,116,116,348) x %d seeds = %d cVAEs, one ensemble"
+                        % (args.seeds, 20 * args.seeds),
+            "hidden": [110, 110], "latent": 10, "c_dim": 29, "batch": 256, "n_train": 800, "n_test": 200,
+            "epochs_per_step": args.epochs_per_step, "members": 20 * args.seeds,
+            "parallelism": "member-sharded over the ranks, no gradient collective",
+            "l2": "working set (params+Adam+scratch > 600 MB) exceeds the 126 MB L2"}
 
 
 # ---------------------------------------------------------------------------------------------
-# CPU baseline: the reference's eager PyTorch loop, restated in oracle/cvae_torch.py (the reference
-# is Python and cannot travel to the GPU box; kind = "port").
-def cpu_reference_sample(hw, epochs, budget_s, threads=None):
-    """Reference training loop on the host for fold 0 x all 4 modalities (keeps the 3:1 D=116 : D=348 mix).
-    With a finite `budget_s` the number of epochs is calibrated so that the sample takes about that long."""
+# CPU arm: the reference's eager PyTorch loop on the host cores.
+def find_reference():
+    """The UNMODIFIED reference module (its cVAE.py) when it has been installed next to this file
+    (tools/install_reference.sh -> baseline/_ref) or NMB_REFERENCE points at a checkout; else None and the restated
+    port oracle/cvae_torch.py is timed.  Never reads /root/reference."""
+    for base in (os.environ.get("NMB_REFERENCE"), os.path.join(ROOT, "baseline", "_ref")):
+        if not base:
+            continue
+        path = os.path.join(base, "cVAE.py")
+        if os.path.exists(path):
+            try:
+                spec = importlib.util.spec_from_file_location("nmb_reference_cVAE", path)
+                mod = importlib.util.module_from_spec(spec)
+                spec.loader.exec_module(mod)
+                return mod
+            except Exception as e:          # missing dependency of the reference: fall back to the port, say why
+                sys.stderr.write("reference at %s does not import (%s): timing the port\n" % (path, e))
+    return None
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def _cpu_models(hw, ref):
+    """(name, model, x, c) of fold 0 x all 4 modalities (keeps the 3:1 D=116 : D=348 mix), reference-initialised."""
     import torch
     from oracle import cvae_torch
-    threads = threads or os.cpu_count() or 1
-    torch.set_num_threads(threads)
+    out = []
     fold = hw.folds[0]
-
-    def one_pass(n_epochs):
-        samples, t_total = 0, 0.0
-        for name in hw.names:
-            d = hw.dims[name]
-            torch.manual_seed(42)
+    for name in hw.names:
+        d = hw.dims[name]
+        torch.manual_seed(42)
+        if ref is not None:
+            model = ref.cVAE_multimodal(input_dim_list=[d], hidden_dim=list(hw.hidden), latent_dim=hw.latent, c_dim=hw.c_dim,
+                                        learning_rate=1e-4, modalities=1, non_linear=True)
+        else:
             model = cvae_torch.OracleCVAEMultimodal([d], list(hw.hidden), hw.latent, hw.c_dim, 1e-4, 1, True)
-            x = torch.from_numpy(fold.train_x[name])
-            c = torch.from_numpy(fold.train_c).long()          # int64 one-hots (utils_vae.py:24)
-            t0 = time.perf_counter()
-            cvae_torch.reference_train_loop(model, [x], [c], "gPoE", n_epochs, hw.batch)
-            t_total += time.perf_counter() - t0
-            samples += x.shape[0] * n_epochs
-        return samples, t_total
+        out.append((name, model, torch.from_numpy(fold.train_x[name]), torch.from_numpy(fold.train_c).long()))
+    return out
 
+
+def _reference_loop(model, x, c, combine, epochs, batch):
+    """Loop body of multimodal_kfold_train_cvae_supervised.py:177-199 on the unmodified reference classes (tensor
+    slices instead of its DataLoader: slightly cheaper per step than the reference, i.e. conservative for the GPU arm)."""
+    n = x.shape[0]
+    for _ in range(epochs):
+        for lo in range(0, n, batch):
+            xb, cb = [x[lo:lo + batch]], [c[lo:lo + batch]]
+            fwd = model.forward_multimodal(xb, cb, combine)
+            loss = model.loss_function_multimodal(xb, fwd)
+            model.optimizer1.zero_grad()
+            loss["total"].backward()
+            model.optimizer1.step()
+
+
+def cpu_train_pass(hw, epochs, threads, ref):
+    import torch
+    from oracle import cvae_torch
+    torch.set_num_threads(threads)
+    samples, t_total = 0, 0.0
+    for name, model, x, c in _cpu_models(hw, ref):
+        t0 = time.perf_counter()
+        if ref is not None:
+            _reference_loop(model, x, c, "gPoE", epochs, hw.batch)
+        else:
+            cvae_torch.reference_train_loop(model, [x], [c], "gPoE", epochs, hw.batch)
+        t_total += time.perf_counter() - t0
+        samples += x.shape[0] * epochs
+    return samples, t_total
+
+
+def cpu_reference_sample(hw, epochs, budget_s, threads, ref):
+    """Reference training loop on the host, one process using `threads` intra-op threads.  With a finite `budget_s`
+    the number of epochs is calibrated so that the sample takes about that long."""
     if budget_s < 1e8:
-        s0, t0 = one_pass(2)                                   # calibration (also warms the thread pool)
+        s0, t0 = cpu_train_pass(hw, 2, threads, ref)          # calibration (also warms the thread pool)
         epochs = max(epochs, int(budget_s / max(t0 / 2, 1e-6)))
-    samples, t_total = one_pass(epochs)
-    return samples / t_total, threads, len(hw.names), t_total, epochs
+    samples, t_total = cpu_train_pass(hw, epochs, threads, ref)
+    return samples / t_total, t_total, epochs
 
 
-def cpu_deviation_sample(hw, threads):
+def _proc_worker(q, epochs, use_ref):
+    import torch
+    torch.set_num_threads(1)
+    from multi_modal_normative_modeling_b200 import workloads
+    hw = workloads.build_host_workload()
+    ref = find_reference() if use_ref else None
+    cpu_train_pass(hw, 1, 1, ref)                              # warm-up
+    q.put(("ready", 0, 0.0))
+    t0 = time.perf_counter()
+    samples, _ = cpu_train_pass(hw, epochs, 1, ref)
+    q.put(("done", samples, time.perf_counter() - t0))
+
+
+def cpu_process_parallel_sample(epochs, procs, use_ref):
+    """`procs` independent single-thread processes, each training the same bounded sample (the reference grid of
+    commands_list*.sh is process-parallel: one model per process).  Aggregate samples/s = sum of samples / slowest."""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_proc_worker, args=(q, epochs, use_ref)) for _ in range(procs)]
+    for p in ps:
+        p.start()
+    total, slowest, done = 0, 0.0, 0
+    while done < procs:
+        tag, s, dt = q.get(timeout=900)
+        if tag == "done":
+            total += s; slowest = max(slowest, dt); done += 1
+    for p in ps:
+        p.join()
+    return total / slowest, slowest
+
+
+def cpu_deviation_sample(hw, threads, ref):
     """pred_recon + deviation + roc/auc on the host for one fold x 4 modalities (subjects/s)."""
     import numpy as np
+    import pandas as pd
     import torch
-    from oracle import cvae_torch, deviation as odev
+    from oracle import deviation as odev
     torch.set_num_threads(threads)
     fold = hw.folds[0]
     labels = (fold.test_df["DIA"].to_numpy() != hw.hc_label).astype(np.int64)
     n, t_total = 0, 0.0
-    for name in hw.names:
+    for name, model, xt, ct in _cpu_models(hw, ref):
         d = hw.dims[name]
-        torch.manual_seed(42)
-        model = cvae_torch.OracleCVAEMultimodal([d], list(hw.hidden), hw.latent, hw.c_dim, 1e-4, 1, True)
-        x = torch.from_numpy(fold.test_x[name]); c = torch.from_numpy(fold.test_c).long()
-        xt = torch.from_numpy(fold.train_x[name]); ct = torch.from_numpy(fold.train_c).long()
+        x, c = torch.from_numpy(fold.test_x[name]), torch.from_numpy(fold.test_c).long()
         t0 = time.perf_counter()
-        pred = model.pred_recon([x], c, "gPoE")[0].numpy()
-        pred_tr = model.pred_recon([xt], ct, "gPoE")[0].numpy()
+        if ref is not None:
+            pred = model.pred_recon([pd.DataFrame(fold.test_x[name])], fold.test_c, torch.device("cpu"), "gPoE")[0]
+            pred_tr = model.pred_recon([pd.DataFrame(fold.train_x[name])], fold.train_c, torch.device("cpu"), "gPoE")[0]
+        else:
+            pred = model.pred_recon([x], c, "gPoE")[0].numpy()
+            pred_tr = model.pred_recon([xt], ct, "gPoE")[0].numpy()
         roi = odev.recon_deviation_roi(fold.test_x64[name], pred)
         subj = odev.recon_deviation(fold.test_x64[name], pred)
         mean, std = odev.normative_stats(odev.recon_deviation_roi(fold.train_x[name], pred_tr))
@@ -117,29 +209,59 @@ def cpu_deviation_sample(hw, threads):
     return n / t_total
 
 
+def cpu_baseline_block(hw, args, ref):
+    threads = os.cpu_count() or 1
+    kind = "reference" if ref is not None else "port"
+    what = ("unmodified reference classes (baseline/_ref/cVAE.py) through the loop of the train script :177-199"
+            if ref is not None else "oracle/cvae_torch.py eager PyTorch loop (restated port)")
+    rate, dt, ep = cpu_reference_sample(hw, 5, args.cpu_seconds / 2, threads, ref)
+    block = {"value": rate, "unit": UNIT, "cores": threads, "kind": kind, "cpu_model": cpu_model(),
+             "sample": "fold 0 x 4 modalities (3 x D=116 + D=348) x %d epochs, %.1f s, one process with %d intra-op "
+                       "threads; %s" % (ep, dt, threads, what)}
+    try:
+        ep_p = max(1, ep // 4)            # a single-thread process is a few times slower per epoch than all cores
+        prate, pdt = cpu_process_parallel_sample(ep_p, threads, ref is not None)
+        block["process_parallel"] = {"value": prate, "unit": UNIT, "processes": threads, "threads_per_process": 1,
+                                     "sample": "%d single-thread processes x (fold 0 x 4 modalities x %d epochs), %.1f s"
+                                               % (threads, ep_p, pdt)}
+        if prate > block["value"]:          # the stronger of the two CPU arrangements is the baseline
+            block["one_process_all_cores"] = {"value": rate, "unit": UNIT}
+            block["value"] = prate
+            block["sample"] = block["process_parallel"]["sample"] + "; " + what
+    except Exception as e:
+        block["process_parallel"] = {"error": "%s: %s" % (type(e).__name__, e)}
+    block["deviation_subjects_per_s"] = cpu_deviation_sample(hw, threads, ref)
+    return block
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from multi_modal_normative_modeling_b200 import workloads
     hw = workloads.build_host_workload()
+    ref = find_reference()
     threads = os.cpu_count() or 1
     # each step = a bounded sample (1 fold x 4 modalities x epochs_per_step epochs = 16k samples)
     for _ in range(args.warmup):
-        cpu_reference_sample(hw, 1, 1e9, threads)
+        cpu_train_pass(hw, 1, threads, ref)
     t0 = time.perf_counter()
     samples = 0
     for _ in range(args.steps):
-        rate, _, models, dt, _ = cpu_reference_sample(hw, args.epochs_per_step, 1e9, threads)
-        samples += rate * dt
+        s, _ = cpu_train_pass(hw, args.epochs_per_step, threads, ref)
+        samples += s
     el = time.perf_counter() - t0
     value = samples / el
-    sample = "1 fold x 4 modalities x %d epochs per step, oracle/cvae_torch.py eager loop" % args.epochs_per_step
+    kind = "reference" if ref is not None else "port"
+    sample = ("1 fold x 4 modalities x %d epochs per step, one process with %d intra-op threads, %s"
+              % (args.epochs_per_step, threads,
+                 "unmodified reference classes from baseline/_ref" if ref is not None else "oracle/cvae_torch.py eager loop"))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / max(args.steps, 1),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config(args),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config(args),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample,
+                             "cpu_model": cpu_model()},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -184,12 +306,39 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(s)}
 
 
+def module_step_ms(dev, steps=20):
+    """Per-step drop-in API (cVAE_multimodal.forward_multimodal -> loss -> backward -> optimizer1.step(), the
+    reference's own loop body) on one D=116 model, B=256: milliseconds per step, host-timed around a synchronize."""
+    import torch
+    from multi_modal_normative_modeling_b200.cVAE import cVAE_multimodal
+    torch.manual_seed(0)
+    model = cVAE_multimodal([116], [110, 110], 10, 29, learning_rate=1e-4, modalities=1, non_linear=True).to(dev)
+    x = torch.randn(256, 116, device=dev)
+    c = torch.zeros(256, 29, device=dev); c[:, 0] = 1; c[:, 27] = 1
+    def one():
+        fwd = model.forward_multimodal([x], [c], "gPoE")
+        loss = model.loss_function_multimodal([x], fwd)
+        model.optimizer1.zero_grad()
+        loss["total"].backward()
+        model.optimizer1.step()
+    for _ in range(5):
+        one()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    torch.cuda.synchronize(dev)
+    ms = 1e3 * (time.perf_counter() - t0) / steps
+    model.close()
+    return ms
+
+
 def run_b200(args):
     import numpy as np
     import torch
     import torch.distributed as dist
-    from multi_modal_normative_modeling_b200 import EnsembleTrainer, pack_rows, scoring, workloads
-    from multi_modal_normative_modeling_b200 import distributed as nd
+    from multi_modal_normative_modeling_b200 import pack_rows, workloads
+    from multi_modal_normative_modeling_b200.runner import EnsembleRunner
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -202,45 +351,58 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
 
     hw = workloads.build_host_workload()
-    wl = workloads.to_device(hw, dev, n_seeds=args.seeds, seed0=rank * args.seeds, pin=True)
-    tr = EnsembleTrainer(wl.specs, device=dev)
+    run = EnsembleRunner(hw, args.seeds, dev, pin=True)          # ONE ensemble; this rank owns len(run.owned) members
+    wl, tr = run.wl, run.trainer
     spe = tr.steps_per_epoch[0]
     n_steps = args.epochs_per_step * spe
-    samples_per_step = wl.samples_per_epoch * args.epochs_per_step
-    flops_per_step = wl.flops_per_epoch * args.epochs_per_step
+    n_tr_rows = {name: hw.folds[0].train_x[name].shape[0] for name in hw.names}
+    total_samples_per_step = sum(hw.folds[f].train_x[name].shape[0] for f, name, _ in run.grid) * args.epochs_per_step
+    total_flops_per_step = sum(hw.folds[f].train_x[name].shape[0] *
+                               workloads.train_flops_per_sample(hw.dims[name], hw.c_dim, hw.hidden, hw.latent)
+                               for f, name, _ in run.grid) * args.epochs_per_step
+    local_flops_per_step = wl.flops_per_epoch * args.epochs_per_step
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t[0])
+        return ms
+
+    def timed_train(trainer, steps, warmup):
+        for _ in range(max(warmup, 3)):
+            trainer.train_steps(n_steps)
+        barrier()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for a, b in ev:
+            a.record()
+            trainer.train_steps(n_steps)
+            b.record()
+        t1.record()
+        barrier()
+        return t0.elapsed_time(t1), float(np.mean([a.elapsed_time(b) for a, b in ev]))
+
     # ---- device-resident throughput (`value`) ------------------------------------------------
     sampler = ClockSampler(local_rank)
     sampler.start()
+    sampler.ready.wait(5.0)
     for _ in range(max(args.warmup, 3)):
         tr.train_steps(n_steps)
-    sampler.ready.wait(5.0)
     barrier()
     sampler.armed = True
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     launches0 = tr.gpu_launches
-    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_start.record()
-    for a, b in ev:
-        a.record()
-        tr.train_steps(n_steps)
-        b.record()
-    t_end.record()
-    barrier()
+    elapsed_local, kernel_ms = timed_train(tr, args.steps, 0)
     sampler.armed = False                       # re-armed for the end-to-end timed region below
-    elapsed_ms = t_start.elapsed_time(t_end)
-    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
-    launches = tr.gpu_launches - launches0
-    if world > 1:
-        t = torch.tensor([elapsed_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t[0])
-    value = world * samples_per_step * args.steps / (elapsed_ms * 1e-3)
+    launches = tr.gpu_launches - launches0 - 3 * 4          # timed_train ran 3 more warm-up calls first
+    elapsed_ms = max_over_ranks(elapsed_local)
+    value = total_samples_per_step * args.steps / (elapsed_ms * 1e-3)
 
     # ---- end-to-end through the public API with HOST buffers ----------------------------------
     keys = list(wl.host_buffers)
@@ -297,110 +459,142 @@ def run_b200(args):
     barrier()
     sampler.stop_flag = True
     sampler.join()
-    e2e_ms = e0.elapsed_time(e1)
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    e2e_value = total_samples_per_step * args.steps / (e2e_ms * 1e-3)
+    h2d_all, d2h_all = h2d, loss_host.numel() * 4
     if world > 1:
-        t = torch.tensor([e2e_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t[0])
-    e2e_value = world * samples_per_step * args.steps / (e2e_ms * 1e-3)
+        t = torch.tensor([h2d, d2h_all], device=dev, dtype=torch.float64)
+        dist.all_reduce(t)
+        h2d_all, d2h_all = int(t[0]), int(t[1])
     final_loss = float(loss_host[:, -1, 0].mean())
 
     # ---- deviation scoring: reconstruct -> normative stats -> deviation/z -> AUC -> all-gather --
     deviation = None
     if not args.no_deviation:
-        scorer = scoring.DeviationScorer(tr, [s.xc for s in wl.specs], wl.test_xc, wl.train_hc_mask, wl.test_labels)
+        scorer = run.scorer
 
         def dev_step():
-            # 6 libnmb launches (2 x reconstruct, stats, deviation / z, 2 x AUC), then one fixed-size record per
-            # member {subject AUC | per-ROI mean | std | AUC} and the all-gather (NCCL over NVLink when N > 1)
-            scorer.run()
-            rec = scorer.member_records()
-            owned = list(range(rank * tr.n, (rank + 1) * tr.n))
-            table = nd.gather_member_tables(rec, owned, world * tr.n)
-            return table, scorer.auc_subj
+            # 6 libnmb launches (2 x reconstruct, stats, deviation / z, 2 x AUC), then one fixed-size record per member
+            # {subject AUC | per-ROI mean | std | AUC | per-subject deviation} and the all-gather (NCCL over NVLink, N > 1)
+            return run.score()
         for _ in range(max(args.warmup, 5)):
-            dev_step()
+            gs = dev_step()
         barrier()
         reps = max(5, min(args.steps, 10))
         dev_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
         for a, b in dev_ev:
             a.record()
-            table, subj_auc = dev_step()
+            gs = dev_step()
             b.record()
         barrier()
+        fold_auc = run.fold_auc(gs)
         # per-pass device time, median over the passes (max over ranks): a pass is a handful of short launches, so a
         # single host hiccup (first process on a fresh box: lazy module loading, clock ramp) would otherwise dominate
         pass_ms = sorted(a.elapsed_time(b) for a, b in dev_ev)
-        dms = pass_ms[len(pass_ms) // 2] * reps
-        dev_worst = pass_ms[-1]
-        if world > 1:
-            t = torch.tensor([dms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dms = float(t[0])
-        # algorithmic bytes of the streaming deviation kernel: read x (ldx) + xhat, write roi + z + subj
-        dev_bytes = sum(t[0].shape[0] * (4 * (3 * s.input_dims[0] + t[0].shape[1]) + 4)
-                        for t, s in zip(wl.test_xc, wl.specs))
-        deviation = {"value": world * wl.test_subjects * reps / (dms * 1e-3), "unit": "subjects/s",
-                     "ms_per_pass": dms / reps, "ms_worst_pass": dev_worst, "timing": "median pass of %d, CUDA events" % reps,
-                     "subjects_per_pass": world * wl.test_subjects,
-                     "mean_subject_auc": float(subj_auc.mean()),
-                     "gathered_table": list(table.shape), "launches_per_pass": 6,
-                     "streaming_kernel_algorithmic_bytes": dev_bytes}
+        dms = max_over_ranks(pass_ms[len(pass_ms) // 2])
+        # the streaming deviation kernel alone (the HBM-bound kernel the north star names): algorithmic bytes =
+        # read x (ldx floats) + xhat (D), write roi + z (2 D) + subject score, per test row -- timed with CUDA events
+        dev_bytes = sum(t[0].shape[0] * (4 * (3 * s.input_dims[0] + t[0].shape[1]) + 4) for t, s in zip(wl.test_xc, wl.specs))
+        for _ in range(3):
+            scorer.run_deviation_only()
+        torch.cuda.synchronize(dev)
+        kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(20)]
+        for a, b in kev:
+            a.record()
+            scorer.run_deviation_only()
+            b.record()
+        torch.cuda.synchronize(dev)
+        k_ms = sorted(a.elapsed_time(b) for a, b in kev)[10]
+        n_test_total = sum(run.n_test_all)
+        deviation = {"value": n_test_total / (dms * 1e-3), "unit": "subjects/s",
+                     "ms_per_pass": dms, "ms_worst_pass": pass_ms[-1], "timing": "median pass of %d, CUDA events, max over ranks" % reps,
+                     "subjects_per_pass": n_test_total, "reconstruction": "z sampled (cVAE.py:1207), like the reference's test script",
+                     "mean_subject_auc": float(gs.subject_auc().mean()),
+                     "mean_fold_auc_modalities_averaged": float(np.mean(list(fold_auc.values()))),
+                     "gathered_table": list(gs.table.shape), "launches_per_pass": 6}
 
-    if rank == 0:
+    if True:
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
+        hbm_peak = peaks.get("hbm_gbs") or 6500.0
+        if deviation is not None:
+            ach = dev_bytes / (k_ms * 1e-3) / 1e9
+            deviation["roofline"] = {"bound": "hbm", "kernel": "nmb::deviation_kernel", "achieved": ach, "peak": hbm_peak,
+                                     "unit": "GB/s", "frac": ach / hbm_peak, "kernel_ms": k_ms,
+                                     "algorithmic_bytes_per_launch": dev_bytes, "timing": "median of 20 launches, CUDA events, this rank",
+                                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.5 TB/s",
+                                     "whole_pass_GBps": dev_bytes / (dms * 1e-3) / 1e9}
+
+    # ---- extras: weak scaling (N > 1) and the per-step module API ---------------------------------------------
+    extra = {"engine": tr.engine(), "final_mean_total_loss": final_loss, "members_this_rank": tr.n}
+    if world > 1 and not args.no_weak:
+        wlw = workloads.to_device(hw, dev, n_seeds=args.seeds, seed0=1000 + rank * args.seeds)
+        from multi_modal_normative_modeling_b200 import EnsembleTrainer
+        trw = EnsembleTrainer(wlw.specs, device=dev)
+        w_ms, _ = timed_train(trw, max(3, args.steps // 2), args.warmup)
+        w_ms = max_over_ranks(w_ms)
+        extra["weak"] = {"value": world * wlw.samples_per_epoch * args.epochs_per_step * max(3, args.steps // 2) / (w_ms * 1e-3),
+                         "unit": UNIT, "members_per_gpu": trw.n, "ms_per_step": w_ms / max(3, args.steps // 2),
+                         "note": "every rank trains its own 480-member ensemble (distinct seeds): the round-1 headline"}
+        trw.close()
+    if rank == 0 and not args.no_module_step:
+        try:
+            extra["module_step_ms"] = module_step_ms(dev)
+            extra["module_step_note"] = ("per-step drop-in API, one D=116 model, B=256: forward_multimodal -> loss -> "
+                                         "backward -> optimizer1.step(); host-timed, 20 steps")
+        except Exception as e:
+            extra["module_step_ms"] = None
+            extra["module_step_error"] = "%s: %s" % (type(e).__name__, e)
+
+    if rank == 0:
         peak_tf = peaks.get("bf16_tflops_sustained") or 1400.0
         peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained"
-        achieved = flops_per_step / (kernel_ms * 1e-3) / 1e12
+        achieved = local_flops_per_step / (kernel_ms * 1e-3) / 1e12
         clocks = sampler.summary()
-        traffic = None
+        traffic, traffic_note = None, None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "train_kernel_traffic.json"))).get("dram_bytes_per_launch")
+            tj = json.load(open(os.path.join(ROOT, "profiles", "train_kernel_traffic.json")))
+            traffic, traffic_note = tj.get("dram_bytes_per_launch"), tj.get("note")
         except Exception:
             pass
         engine = tr.engine()
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "bf16x3->f32" if engine != "fp32" else "f32",
-                "data": "synthetic",
-                "config": config(args, {"final_mean_total_loss": final_loss, "engine": engine}),
+                "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
+                "dtype": "bf16x3->f32" if engine != "fp32" else "f32",
+                "data": "synthetic", "config": config(args), "extra": extra,
                 "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                             "frac": achieved / peak_tf, "traffic": traffic,
+                             "frac": achieved / peak_tf, "traffic": traffic if world == 1 else None,
                              "kernel": "nmb::tcp::train_tcp_kernel" if engine == "tcgen05-pipelined" else "nmb::train_kernel",
-                             "kernel_ms": kernel_ms, "algorithmic_flops_per_launch": flops_per_step,
-                             "peak_source": peak_src,
-                             "kernel_ms_note": "CUDA events bracket the four launches of a training call (xprep, state "
+                             "kernel_ms": kernel_ms, "algorithmic_flops_per_launch": local_flops_per_step,
+                             "peak_source": peak_src, "traffic_note": traffic_note,
+                             "kernel_ms_note": "CUDA events bracket the four launches of a training call on rank 0 (xprep, state "
                                                "conversion in, persistent kernel, state conversion out); the persistent kernel is "
-                                               "0.92 of it (profiles/r01b_launch_list_summary.txt)",
-                             "hbm": None if not traffic else {
+                                               "~0.92 of it (profiles/*launch_list_summary.txt)",
+                             "hbm": None if not (traffic and world == 1) else {
                                  "achieved_GBps": traffic / (kernel_ms * 1e-3) / 1e9, "peak_GBps": peaks.get("hbm_gbs"),
                                  "frac": (traffic / (kernel_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]) if peaks.get("hbm_gbs") else None,
                                  "note": "measured DRAM bytes per launch (ncu, profiles/train_kernel_traffic.json) over the "
                                          "live launch time: the kernel is latency-bound between its two roofs"},
-                             "note": "achieved = algorithmic (FP32-equivalent) FLOPs; every product is executed as 3 BF16 "
-                                     "tcgen05 passes (hi*hi, lo*hi, hi*lo, FP32 accumulate) to meet the 1e-4 parity bar, so "
-                                     "the tensor pipe executes 3x these FLOPs: executed_frac = %.4f of the measured peak"
-                                     % (3 * achieved / peak_tf),
+                             "note": "achieved = algorithmic (FP32-equivalent) FLOPs of rank 0's members; every product is "
+                                     "executed as 3 BF16 tcgen05 passes (hi*hi, lo*hi, hi*lo, FP32 accumulate) to meet the "
+                                     "1e-4 parity bar, so the tensor pipe executes 3x these FLOPs: executed_frac = %.4f of "
+                                     "the measured peak" % (3 * achieved / peak_tf),
                              "executed_tensor_frac": 3 * achieved / peak_tf},
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                        "d2h_bytes_per_step": loss_host.numel() * 4, "ms_per_step": e2e_ms / args.steps},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_all,
+                        "d2h_bytes_per_step": d2h_all, "ms_per_step": e2e_ms / args.steps},
                 "gpu_launches": launches, "clocks": clocks}
         if deviation:
             line["deviation"] = deviation
-        if not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
-            rate, cores, models, dt, ep = cpu_reference_sample(hw, 5, args.cpu_seconds, threads)
-            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": "fold 0 x %d modalities (3 x D=116 + D=348) x %d epochs, %.1f s, "
-                                              "oracle/cvae_torch.py eager PyTorch loop" % (models, ep, dt),
-                                    "deviation_subjects_per_s": cpu_deviation_sample(hw, threads)}
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline_block(hw, args, find_reference())
         print(json.dumps(line))
-    tr.close()
+    run.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -222,6 +222,14 @@ class DeviationScorer:
         self.tr.gpu_launches += self.launches_per_run
         return self
 
+    def run_deviation_only(self):
+        """Just the streaming deviation / z-score kernel on the current reconstructions (for timing it alone)."""
+        with torch.cuda.device(self.dev):
+            _lib.check(self.lib.nmb_deviation(self.n_seg, self.s_x_te, self.s_ldx, self.s_hat_te, self.s_stats, self.s_nte,
+                                              self.s_d, self.s_roi, self.s_z, self.s_subj, _stream_ptr(self.dev)), "nmb_deviation")
+        self.tr.gpu_launches += 1
+        return self
+
     # ---- views of segment s ----------------------------------------------------------------
     def seg_stats(self, s):
         return self.stats[int(self.o_stats[s]):int(self.o_stats[s]) + 2 * self.seg_d[s]].view(2, self.seg_d[s])
@@ -238,12 +246,14 @@ class DeviationScorer:
     def seg_auc_roi(self, s):
         return self.auc_roi[int(self.o_auc[s]):int(self.o_auc[s]) + self.seg_d[s]]
 
-    def member_records(self) -> torch.Tensor:
+    def member_records(self, d_max: int = None) -> torch.Tensor:
         """Fixed-size float64 record per segment {subject AUC | per-ROI mean | per-ROI std | per-ROI AUC}, padded
-        to the widest segment -- the payload of the multi-GPU all-gather (distributed.gather_member_tables)."""
+        to the widest segment (or `d_max`, the widest of the WHOLE ensemble when it is sharded over ranks) -- the
+        payload of the multi-GPU all-gather (distributed.gather_member_tables)."""
         import numpy as np
-        if not hasattr(self, "_rec_idx"):
-            dmax = max(self.seg_d)
+        if not hasattr(self, "_rec_idx") or self._rec_dmax != d_max:
+            dmax = max(max(self.seg_d), d_max or 0)
+            self._rec_dmax = d_max
             w = 1 + 3 * dmax
             src_s, dst_s, src_a, dst_a = [], [], [], []
             for s, d in enumerate(self.seg_d):
