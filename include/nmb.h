@@ -163,7 +163,9 @@ int nmb_ensemble_peek(NmbEnsemble* ens, int32_t member, float* mu, float* logvar
 enum { NMB_RECON_MEAN = 0, NMB_RECON_SAMPLE = 1,
        NMB_RECON_GIVEN_Z = 2 /* decoders only: eps[i] holds z itself [n_rows[i]][latent] -- Decoder.forward /
                                 cVAE.decode (cVAE.py:197-206, 426-428, 1135-1136); mu / logvar are not produced */,
-       NMB_RECON_FP32 = 16 /* OR into `mode`: FP32 FFMA engine instead of the default tcgen05 (BF16x3) engine */ };
+       NMB_RECON_FP32 = 16 /* OR into `mode`: FP32 FFMA engine instead of the default tcgen05 (BF16x3) engine */,
+       NMB_RECON_TC_SIMPLE = 32 /* OR into `mode`: generic tcgen05 engine instead of the pipelined forward-only program
+                                   (the default wherever the pipelined training kernel covers the architecture) */ };
 /* Test-time reconstruction for every member on its own rows:
  *   mode MEAN   : decode(mu)                       -- cVAE.pred_recon, cVAE.py:549-555
  *   mode SAMPLE : decode(mu + eps*exp(logvar/2))   -- cVAE_multimodal.pred_recon, cVAE.py:1198-1208

@@ -133,6 +133,15 @@ struct NmbEnsemble {
   std::vector<tcp::EpiP> epis_p;             // compact epilogue item tables (kernel parameters) where they fit
   std::vector<int> ep_off, ep_cnt;
   int max_mlayers = 1;                       // layers with Adam master state, over all architectures
+  // forward-only programs of the same architectures (nmb_ensemble_reconstruct on the pipelined kernel)
+  tcp::ProgramDev* progs_fwd_dev = nullptr;
+  std::vector<tcp::MStep> msteps_fwd;
+  std::vector<int> msf_off, msf_cnt;
+  std::vector<tcp::EpiP> epis_fwd;
+  std::vector<int> epf_off, epf_cnt;
+  bool fwd_ok = false;
+  unsigned char* recon_buf = nullptr;        // grow-only planes of the rows being reconstructed
+  size_t recon_buf_bytes = 0;
   std::vector<long long> steps_host;         // host mirror of MemberDev.steps_done (every step goes through this API)
   std::vector<long long> n_lr_steps;         // length of each member's lr_steps schedule (0 = none)
 };
@@ -238,6 +247,29 @@ int setup_tcp(NmbEnsemble* e) {
   }
   CU(upload(mtc.data(), sizeof(tcp::MemberTc) * mtc.size(), &p));
   e->mtc_dev = (tcp::MemberTc*)p;
+  {   // forward-only programs (same planes / stash layout): every table must fit the kernel parameters
+    std::vector<tcp::ProgramDev> pf(progs.size());
+    bool ok = true;
+    for (size_t i = 0; i < progs.size(); ++i) {
+      tcp::Program F = tcp::build_program(e->archs[i], true);
+      e->msf_off.push_back((int)e->msteps_fwd.size()); e->msf_cnt.push_back((int)F.steps.size());
+      for (const tcp::Step& s : F.steps) e->msteps_fwd.push_back(tcp::to_mstep(s));
+      bool fits = e->epis_fwd.size() + F.epis.size() <= (size_t)tcp::kMaxParamEpis;
+      for (const tcp::Epi& ep : F.epis) fits = fits && tcp::epip_fits(ep);
+      e->epf_off.push_back((int)e->epis_fwd.size()); e->epf_cnt.push_back(fits ? (int)F.epis.size() : 0);
+      if (fits) for (const tcp::Epi& ep : F.epis) e->epis_fwd.push_back(tcp::to_epip(ep));
+      void *ds, *de;
+      CU(upload(F.steps.data(), sizeof(tcp::Step) * F.steps.size(), &ds));
+      CU(upload(F.epis.data(), sizeof(tcp::Epi) * F.epis.size(), &de));
+      pf[i] = pd[i];
+      pf[i].steps = (const tcp::Step*)ds; pf[i].epis = (const tcp::Epi*)de;
+      pf[i].n_steps = (int)F.steps.size(); pf[i].n_epis = (int)F.epis.size();
+    }
+    if (e->msteps_fwd.size() > (size_t)tcp::kMaxParamSteps) ok = false;
+    CU(upload(pf.data(), sizeof(tcp::ProgramDev) * pf.size(), &p));
+    e->progs_fwd_dev = (tcp::ProgramDev*)p;
+    e->fwd_ok = ok;
+  }
   CU(upload(items.data(), sizeof(tcp::XPrepItem) * items.size(), &p));
   e->xprep_dev = (tcp::XPrepItem*)p;
   e->n_xprep = (int)items.size();
@@ -379,6 +411,7 @@ int nmb_ensemble_destroy(NmbEnsemble* e) {
   cudaSetDevice(e->device);
   cudaFree(e->members_dev); cudaFree(e->archs_dev); cudaFree(e->scratch); cudaFree(e->work_counter); cudaFree(e->order_dev);
   for (void* p : e->tcp_allocs) cudaFree(p);
+  cudaFree(e->recon_buf);
   delete e;
   return 0;
 }
@@ -488,7 +521,8 @@ int nmb_ensemble_reconstruct(NmbEnsemble* e, const float* const* xc, const int32
                              void* stream) {
   if (!e || !xc || !n_rows || !xhat) return fail("null argument");
   const int fp32 = (mode & NMB_RECON_FP32) ? 1 : 0;
-  mode &= ~NMB_RECON_FP32;
+  const int tc_simple = (mode & NMB_RECON_TC_SIMPLE) ? 1 : 0;
+  mode &= ~(NMB_RECON_FP32 | NMB_RECON_TC_SIMPLE);
   if (mode != NMB_RECON_MEAN && mode != NMB_RECON_SAMPLE && mode != NMB_RECON_GIVEN_Z) return fail("bad mode");
   if (mode == NMB_RECON_GIVEN_Z) {
     if (!eps) return fail("NMB_RECON_GIVEN_Z needs z in eps[]");
@@ -508,6 +542,91 @@ int nmb_ensemble_reconstruct(NmbEnsemble* e, const float* const* xc, const int32
     }
   }
   if (items.empty()) return 0;
+  if (e->tcp_ok && e->fwd_ok && !fp32 && !tc_simple && mode != NMB_RECON_GIVEN_Z) {
+    // ---- pipelined forward-only program (the training kernel's operand pipeline, forward half) ----
+    struct Key { const float* xc; int n_rows, ldx, k_valid, z, c; size_t x_off, c_off; };
+    std::vector<Key> keys;
+    std::vector<tcp::XPrepItem> xitems;
+    std::vector<tcp::ReconTc> rtc(n);
+    size_t need = 0;
+    int max_blocks = 1;
+    auto carve = [&](size_t bytes) { size_t o = need; need += (bytes + 1023) & ~size_t(1023); return o; };
+    for (int i = 0; i < n; ++i) {
+      const ArchDesc& a = e->archs[e->arch_idx[i]];
+      tcp::ReconTc& r = rtc[i];
+      std::memset(&r, 0, sizeof(r));
+      r.n_rows = n_rows[i];
+      r.mu = mu ? mu[i] : nullptr; r.logvar = logvar ? logvar[i] : nullptr;
+      r.eps = (eps && mode == NMB_RECON_SAMPLE) ? eps[i] : nullptr;
+      if (n_rows[i] == 0) continue;
+      const int tiles = (n_rows[i] + kMaxBatch - 1) / kMaxBatch;
+      for (int m = 0; m < a.M; ++m) {
+        const ModDesc& q = a.mod[m];
+        const float* src = xc[i * NMB_MAX_MOD + m];
+        Key k{src, n_rows[i], q.ldx, q.D + a.C + 1, a.Z, a.C, 0, 0};
+        int found = -1;
+        for (size_t j = 0; j < keys.size(); ++j)
+          if (keys[j].xc == k.xc && keys[j].n_rows == k.n_rows && keys[j].ldx == k.ldx && keys[j].k_valid == k.k_valid &&
+              keys[j].z == k.z && keys[j].c == k.c) { found = (int)j; break; }
+        if (found < 0) {
+          const int cg = tcp::round16(k.k_valid) / 8, c_cg = tcp::round16(a.Z + a.C + 1) / 8;
+          const long long blocks = 2LL * tiles;
+          k.x_off = carve((size_t)(blocks * cg * 4096)); k.c_off = carve((size_t)(blocks * c_cg * 4096));
+          keys.push_back(k);
+          tcp::XPrepItem it{src, nullptr, nullptr, nullptr, k.n_rows, kMaxBatch, k.ldx, k.k_valid, cg, 2, q.D, a.C, a.Z, c_cg,
+                            (q.D + 3) / 4};
+          xitems.push_back(it);
+          if ((int)blocks > max_blocks) max_blocks = (int)blocks;
+          found = (int)keys.size() - 1;
+        }
+        r.xc[m] = src; r.xhat[m] = xhat[i * NMB_MAX_MOD + m];
+        r.xplanes[m] = reinterpret_cast<const unsigned char*>(keys[found].x_off);     // offsets, rebased below
+        r.cplanes[m] = reinterpret_cast<const unsigned char*>(keys[found].c_off);
+      }
+    }
+    if (need > e->recon_buf_bytes) {          // grow-only scratch for the planes (synchronising, first call / larger call only)
+      CU(cudaStreamSynchronize(st));
+      if (e->recon_buf) CU(cudaFree(e->recon_buf));
+      e->recon_buf = nullptr; e->recon_buf_bytes = 0;
+      void* nb = nullptr;
+      CU(cudaMalloc(&nb, need));
+      e->recon_buf = (unsigned char*)nb; e->recon_buf_bytes = need;
+    }
+    for (size_t j = 0; j < keys.size(); ++j) { xitems[j].out = e->recon_buf + keys[j].x_off; xitems[j].cplanes = e->recon_buf + keys[j].c_off; }
+    for (int i = 0; i < n; ++i)
+      for (int m = 0; m < NMB_MAX_MOD; ++m) {
+        if (!rtc[i].xc[m]) continue;
+        rtc[i].xplanes[m] = e->recon_buf + reinterpret_cast<size_t>(rtc[i].xplanes[m]);
+        rtc[i].cplanes[m] = e->recon_buf + reinterpret_cast<size_t>(rtc[i].cplanes[m]);
+      }
+    // work items: (member, <= 2 tiles), most expensive architectures first (dynamic dealing keeps the tail short)
+    std::vector<int> order(n);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
+      return e->archs[e->arch_idx[x]].n_params > e->archs[e->arch_idx[y]].n_params; });
+    std::vector<tcp::ReconWork> work;
+    for (int i : order) {
+      const int tiles = (n_rows[i] + kMaxBatch - 1) / kMaxBatch;
+      for (int t0 = 0; t0 < tiles; t0 += 2) work.push_back(tcp::ReconWork{i, t0, tiles - t0 < 2 ? tiles - t0 : 2});
+    }
+    Blob b;
+    const size_t o_x = b.add(xitems.data(), sizeof(tcp::XPrepItem) * xitems.size());
+    const size_t o_r = b.add(rtc.data(), sizeof(tcp::ReconTc) * rtc.size());
+    const size_t o_w = b.add(work.data(), sizeof(tcp::ReconWork) * work.size());
+    CU(b.upload(st));
+    CU(launch_xprep(b.at<tcp::XPrepItem>(o_x), (int)xitems.size(), max_blocks, st));
+    TrainLaunch t;
+    std::memset(&t, 0, sizeof(t));
+    t.members = e->members_dev; t.archs = e->archs_dev; t.n_members = e->n_members;
+    t.scratch = e->scratch; t.slot_floats = e->slot_floats; t.n_slots = e->n_slots; t.work_counter = e->work_counter;
+    t.order = e->order_dev;
+    CU(launch_recon_tcp(t, e->progs_fwd_dev, e->progs_dev, e->mtc_dev, e->stash, e->stash_bytes, e->msteps_fwd.data(),
+                        e->msf_off.data(), e->msf_cnt.data(), (int)e->msf_off.size(), e->epis_fwd.data(), e->epf_off.data(),
+                        e->epf_cnt.data(), e->max_mlayers, mode == NMB_RECON_MEAN ? 1 : 2, b.at<tcp::ReconTc>(o_r),
+                        b.at<tcp::ReconWork>(o_w), (int)work.size(), e->n_sm, st));
+    CU(b.release(st));
+    return 0;
+  }
   Blob b;
   const size_t o_items = b.add(items.data(), sizeof(ReconItem) * items.size());
   const size_t o_xc = b.add(xc, sizeof(void*) * (size_t)n * NMB_MAX_MOD);

@@ -194,9 +194,10 @@ __device__ __forceinline__ void warp_bitonic_sort(float* v, int n_pow2, int lane
 
 __global__ void __launch_bounds__(256) auc_kernel(AucTable t) {
   extern __shared__ float auc_smem[];
-  float* negs = auc_smem;                                  // [8][kAucTile] sorted negatives of the current tile
+  float* negs = auc_smem;                                  // [8][kAucTile] negatives of the current tile (sorted / compacted)
   float* vals = auc_smem + kAucCols * kAucTile;             // [8][kAucTile] raw scores of the current positive tile
   __shared__ int s_cnt[8];
+  __shared__ unsigned short s_idx[kAucTile];                // single-tile path: negatives first, positives from the back
   const int s = blockIdx.y;
   const int n_cols = t.n_cols[s];
   const int c0 = blockIdx.x * kAucCols;
@@ -205,56 +206,91 @@ __global__ void __launch_bounds__(256) auc_kernel(AucTable t) {
   const uint8_t* lab = t.labels[s];
   const int n = t.n_rows[s];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const bool single = n <= kAucTile;                         // the usual case: one tile holds every row
+  const bool active = c0 + w < n_cols;                        // warp-uniform; barriers below stay CTA-uniform
   unsigned long long u2 = 0;
-  int n_neg_total = 0;
-  for (int r0 = 0; r0 < n; r0 += kAucTile) {
-    const int m = min(kAucTile, n - r0);
-    int p2 = 32;
-    while (p2 < m) p2 <<= 1;
-    int cnt = 0;
-    for (int i = threadIdx.x; i < m; i += 256) cnt += lab[r0 + i] == 0;
-    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-    __syncthreads();                                         // previous tile fully consumed (negs, s_cnt)
-    if (lane == 0) s_cnt[w] = cnt;
-    auc_load_tile(sc, n_cols, c0, r0, m, p2, lab, true, negs);
-    if (single) auc_load_tile(sc, n_cols, c0, 0, n, p2, lab, false, vals);
+  int n_neg_total = 0, n_pos = 0;
+  if (n <= kAucTile) {
+    // ---- the usual case (a fold's test set): one tile holds every row.  No sort: the labels are shared by the 8
+    // columns, so warp 0 compacts the row indices once (negatives from the front, positives from the back), every warp
+    // gathers its column's negatives into a dense array and counts, for each of its positives, the negatives below /
+    // equal by a broadcast scan (n_pos * n_neg / 32 steps per lane; cheaper than sorting for n <= 1024).
+    auc_load_tile(sc, n_cols, c0, 0, n, n, lab, false, vals);
+    if (w == 0) {
+      int nn = 0, np = 0;
+      for (int i0 = 0; i0 < n; i0 += 32) {
+        const int i = i0 + lane;
+        const bool is_neg = i < n && lab[i] == 0, is_pos = i < n && lab[i] != 0;
+        const unsigned bn = __ballot_sync(0xffffffffu, is_neg), bp = __ballot_sync(0xffffffffu, is_pos);
+        const unsigned below = (1u << lane) - 1u;
+        if (is_neg) s_idx[nn + __popc(bn & below)] = (unsigned short)i;
+        if (is_pos) s_idx[n - 1 - (np + __popc(bp & below))] = (unsigned short)i;
+        nn += __popc(bn); np += __popc(bp);
+      }
+      if (lane == 0) { s_cnt[0] = nn; s_cnt[1] = np; }
+    }
     __syncthreads();
-    int n_neg = 0;
-    for (int k = 0; k < 8; ++k) n_neg += s_cnt[k];
-    n_neg_total += n_neg;
+    const int n_neg = s_cnt[0];
+    n_pos = s_cnt[1];
+    n_neg_total = n_neg;
+    if (!active) return;
+    const float* pv = vals + w * kAucTile;
     float* mine = negs + w * kAucTile;
-    const bool active = c0 + w < n_cols;                      // warp-uniform; barriers below stay CTA-uniform
-    if (active && n_neg > 0) warp_bitonic_sort(mine, p2, lane);
-    if (n_neg == 0) continue;                                 // CTA-uniform
-    for (int q0 = 0; q0 < n; q0 += kAucTile) {                // positives of every tile against this tile's negatives
-      const int mq = min(kAucTile, n - q0);
-      if (!single) {
+    for (int q = lane; q < n_neg; q += 32) mine[q] = pv[s_idx[q]];
+    __syncwarp();
+    for (int p = lane; p < n_pos; p += 32) {
+      const float v = pv[s_idx[n - 1 - p]];
+      int less = 0, eq = 0;
+#pragma unroll 4
+      for (int q = 0; q < n_neg; ++q) {
+        const float u = mine[q];                             // same address in every lane: one broadcast read
+        less += u < v; eq += u == v;
+      }
+      u2 += 2ull * (unsigned long long)less + (unsigned long long)eq;
+    }
+  } else {
+    // ---- large tables: tiles of kAucTile rows; the negatives of a tile are sorted and the positives of every tile are
+    // binary-searched in them
+    for (int r0 = 0; r0 < n; r0 += kAucTile) {
+      const int m = min(kAucTile, n - r0);
+      int p2 = 32;
+      while (p2 < m) p2 <<= 1;
+      int cnt = 0;
+      for (int i = threadIdx.x; i < m; i += 256) cnt += lab[r0 + i] == 0;
+      for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+      __syncthreads();                                         // previous tile fully consumed (negs, s_cnt)
+      if (lane == 0) s_cnt[w] = cnt;
+      auc_load_tile(sc, n_cols, c0, r0, m, p2, lab, true, negs);
+      __syncthreads();
+      int n_neg = 0;
+      for (int k = 0; k < 8; ++k) n_neg += s_cnt[k];
+      n_neg_total += n_neg;
+      float* mine = negs + w * kAucTile;
+      if (active && n_neg > 0) warp_bitonic_sort(mine, p2, lane);
+      if (n_neg == 0) continue;                                 // CTA-uniform
+      for (int q0 = 0; q0 < n; q0 += kAucTile) {                // positives of every tile against this tile's negatives
+        const int mq = min(kAucTile, n - q0);
         __syncthreads();
         auc_load_tile(sc, n_cols, c0, q0, mq, mq, lab, false, vals);
         __syncthreads();
-      }
-      if (!active) continue;
-      const float* pv = vals + w * kAucTile;
-      for (int i = lane; i < mq; i += 32) {
-        if (lab[q0 + i] == 0) continue;
-        const float v = pv[i];
-        int lo = 0, hi = n_neg;
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (mine[mid] < v) lo = mid + 1; else hi = mid; }
-        const int less = lo;
-        hi = n_neg;
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (mine[mid] <= v) lo = mid + 1; else hi = mid; }
-        u2 += 2ull * less + (unsigned long long)(lo - less);
+        if (!active) continue;
+        const float* pv = vals + w * kAucTile;
+        for (int i = lane; i < mq; i += 32) {
+          if (lab[q0 + i] == 0) continue;
+          const float v = pv[i];
+          int lo = 0, hi = n_neg;
+          while (lo < hi) { const int mid = (lo + hi) >> 1; if (mine[mid] < v) lo = mid + 1; else hi = mid; }
+          const int less = lo;
+          hi = n_neg;
+          while (lo < hi) { const int mid = (lo + hi) >> 1; if (mine[mid] <= v) lo = mid + 1; else hi = mid; }
+          u2 += 2ull * less + (unsigned long long)(lo - less);
+        }
       }
     }
+    if (!active) return;
+    for (int i = lane; i < n; i += 32) n_pos += lab[i] != 0;
+    for (int o = 16; o > 0; o >>= 1) n_pos += __shfl_xor_sync(0xffffffffu, n_pos, o);
   }
-  if (c0 + w >= n_cols) return;
-  int n_pos = 0;
-  for (int i = lane; i < n; i += 32) n_pos += lab[i] != 0;
-  for (int o = 16; o > 0; o >>= 1) {
-    u2 += __shfl_xor_sync(0xffffffffu, u2, o);
-    n_pos += __shfl_xor_sync(0xffffffffu, n_pos, o);
-  }
+  for (int o = 16; o > 0; o >>= 1) u2 += __shfl_xor_sync(0xffffffffu, u2, o);
   if (lane == 0) {
     const int col = c0 + w;
     if (t.out_u2 && t.out_u2[s]) t.out_u2[s][col] = u2;

@@ -80,6 +80,12 @@ cudaError_t configure_kernels();
 cudaError_t configure_tcp();
 cudaError_t set_tcp_trace(unsigned long long* buf, int step);
 cudaError_t launch_xprep(const void* items_dev, int n_items, int max_blocks, cudaStream_t st);
+cudaError_t launch_recon_tcp(const TrainLaunch& t, const tcp::ProgramDev* progs, const tcp::ProgramDev* train_progs,
+                             const tcp::MemberTc* mtc, unsigned char* stash, long long stash_bytes,
+                             const tcp::MStep* msteps, const int* ms_off, const int* ms_cnt, int n_archs,
+                             const tcp::EpiP* epis_p, const int* ep_off, const int* ep_cnt, int max_mlayers,
+                             int recon_mode, const tcp::ReconTc* rtc, const tcp::ReconWork* rwork, int n_rwork,
+                             int n_sm, cudaStream_t st);
 cudaError_t launch_train_tcp(const TrainLaunch& t, const tcp::ProgramDev* progs, const tcp::MemberTc* mtc,
                              unsigned char* stash, long long stash_bytes, float* master, long long master_floats,
                              const tcp::MStep* msteps, const int* ms_off, const int* ms_cnt, int n_archs,

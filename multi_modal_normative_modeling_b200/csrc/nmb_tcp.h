@@ -57,7 +57,8 @@ enum EpiKind : int {
   EK_STEP_END,        // loss reduction, alpha (gPoE) update; publishes the new weight planes to the TMA proxy
   EK_FENCE,           // publishes every stash block written so far to the TMA proxy (start of the backward pass)
   EK_HEAD_LATENT,     // one modality, Z <= 16: head accumulator -> reparameterisation -> [z | c | 1] planes, in registers
-  EK_DZ_LATENT_BWD    // one modality, Z <= 16: d/dz accumulator -> d[mu | logvar] planes, in registers
+  EK_DZ_LATENT_BWD,   // one modality, Z <= 16: d/dz accumulator -> d[mu | logvar] planes, in registers
+  EK_XHAT             // forward-only program (pred_recon): x_recon tile -> fp32 rows of the caller's output
 };
 
 // One ring tile (+ optional A tile) and the MMAs issued on it.
@@ -229,6 +230,18 @@ struct MemberTc {            // per member
   int n_half;                                  // halves per minibatch = ceil(batch / 128)
 };
 
+// Per-member arguments of a forward-only (reconstruction) launch: rows to reconstruct and where the results go.
+struct ReconTc {
+  const unsigned char* xplanes[NMB_MAX_MOD];   // [tile][half] canonical blocks of the rows (xprep_kernel, batch 256)
+  const unsigned char* cplanes[NMB_MAX_MOD];   // decoder-input templates of the rows
+  const float* xc[NMB_MAX_MOD];                // the packed fp32 rows themselves (covariates of the unfused latent path)
+  float* xhat[NMB_MAX_MOD];                    // out [n_rows][D_m] or NULL
+  float* mu; float* logvar;                    // out [n_rows][Z] or NULL
+  const float* eps;                            // injected draws [n_rows][Z] or NULL (Philox stream 1)
+  int n_rows;
+};
+struct ReconWork { int member, tile0, n_tiles; };   // tiles of 256 rows
+
 // One dataset (packed fp32 rows of one modality) to be re-tiled into 128-row blocks per (minibatch, half).
 struct XPrepItem {
   const float* xc; unsigned char* out; unsigned char* cplanes; float* xlm;
@@ -238,7 +251,9 @@ struct XPrepItem {
 __host__ __device__ inline int round16(int v) { return (v + 15) & ~15; }
 
 // ---- host: build the step program of one architecture ------------------------------------------
-inline Program build_program(const ArchDesc& a) {
+// fwd_only: the forward half only, ending in EK_XHAT items (same weight-plane and stash layout as the training program,
+// so both programs run on the same per-member planes); nothing is stashed for a backward pass.
+inline Program build_program(const ArchDesc& a, bool fwd_only = false) {
   Program P;
   const int M = a.M, L = a.L, Z = a.Z, C = a.C;
   if (2 * Z > 128 || Z + C + 1 > 128) return P;
@@ -465,7 +480,7 @@ inline Program build_program(const ArchDesc& a) {
         else emit_fwd(h, w_enc[m][l], SP_NONE, 0, 0, 0);
         Epi e = new_epi(EK_HIDDEN, h, accbuf(h), m);
         e.n_mma = w_enc[m][l].R; e.n_valid = q.enc[l].out; e.n_cols = round16(q.enc[l].out + 1);
-        e.to_act = 1; e.stash_off = s_h[m][l * 2 + h];
+        e.to_act = 1; e.stash_off = fwd_only ? -1 : s_h[m][l * 2 + h];
         e.src_cg = is64(q.enc[l].out + 1) ? e.n_cols / 8 : 0;
         const int id = push_epi(e);
         act_ready[h] = id; acc_free[accbuf(h)] = id;
@@ -510,7 +525,7 @@ inline Program build_program(const ArchDesc& a) {
         emit_fwd(h, w_dec[m][l], SP_NONE, 0, 0, 0);
         Epi e = new_epi(EK_HIDDEN, h, accbuf(h), m);
         e.n_mma = w_dec[m][l].R; e.n_valid = q.dec[l].out; e.n_cols = round16(q.dec[l].out + 1);
-        e.to_act = 1; e.stash_off = s_k[m][l * 2 + h];
+        e.to_act = 1; e.stash_off = fwd_only ? -1 : s_k[m][l * 2 + h];
         e.src_cg = is64(q.dec[l].out + 1) ? e.n_cols / 8 : 0;
         const int id = push_epi(e);
         act_ready[h] = id; acc_free[accbuf(h)] = id;
@@ -519,10 +534,10 @@ inline Program build_program(const ArchDesc& a) {
     if (lay.n_dxh_blk[m] == 0) {          // fast path: one tile, d/dx_recon planes land in ACT[h]
       for (int h = 0; h < 2; ++h) {
         emit_fwd(h, w_out[m][0], SP_NONE, 0, 0, 0);
-        Epi e = new_epi(EK_RECON, h, accbuf(h), m);
+        Epi e = new_epi(fwd_only ? EK_XHAT : EK_RECON, h, accbuf(h), m);
         e.n_mma = w_out[m][0].R; e.n_valid = q.D; e.n_cols = round16(q.D); e.col0 = 0;
-        e.to_act = 1; e.last = 1;
-        e.src_cg = (M == 1) ? 1 : 0;       // one modality: last forward item of the half, it publishes the stash early
+        e.to_act = fwd_only ? 0 : 1; e.last = 1;
+        e.src_cg = (M == 1 && !fwd_only) ? 1 : 0;   // one modality: last forward item of the half, it publishes the stash early
         const int id = push_epi(e);
         act_ready[h] = id; acc_free[accbuf(h)] = id;
       }
@@ -541,9 +556,9 @@ inline Program build_program(const ArchDesc& a) {
           s.commit = 1; s.commit_buf = (unsigned char)buf;
           P.steps.push_back(s);
         }
-        Epi e = new_epi(EK_RECON, h, accbuf(h), m);
+        Epi e = new_epi(fwd_only ? EK_XHAT : EK_RECON, h, accbuf(h), m);
         e.n_mma = 64; e.n_valid = q.D - 64 * t < 64 ? q.D - 64 * t : 64; e.n_cols = 64; e.col0 = 64 * t;
-        e.stash_off = lay.dxh_blk[m] + ((long long)h * lay.n_dxh_blk[m] + t) * 32768;
+        e.stash_off = fwd_only ? -1 : lay.dxh_blk[m] + ((long long)h * lay.n_dxh_blk[m] + t) * 32768;
         e.last = t == lay.n_dxh_blk[m] - 1;
         const int id = push_epi(e);
         acc_free[accbuf(h)] = id;
@@ -552,6 +567,11 @@ inline Program build_program(const ArchDesc& a) {
     }
   }
 
+  if (fwd_only) {
+    push_epi(new_epi(EK_STEP_END, 2, -1, 0));
+    for (Step& s : P.steps) s.dep_grp = 2;
+    return P;
+  }
   // ================= backward =================
   // Generic-proxy stores to the stash become visible to the TMA (async proxy) at the per-half EK_FENCE item:
   // every stash-sourced tile of half h waits for it (all of them are consumed in the backward pass).

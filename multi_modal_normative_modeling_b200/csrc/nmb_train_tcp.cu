@@ -35,6 +35,10 @@ __device__ __forceinline__ unsigned long long gtime() {
 #define TR3() do { } while (0)
 #endif
 
+// Rows walked by the current work item: the member's training rows (minibatch `batch`) or, in a reconstruction launch,
+// the caller's rows in tiles of 256.  Lives in shared memory (Ctrl), read per step: no role keeps it in registers.
+struct RowSet { int n_rows, batch, n_half; };
+
 struct Ctrl {
   uint64_t full[kSlots], empty[kSlots], accbar[4];
   uint32_t tmem;
@@ -42,6 +46,7 @@ struct Ctrl {
   int member;
   int chunk_i0, chunk_n;                 // launch-relative first step and step count of the current work item
   long long chunk_s0;                    // member-global index of its first step
+  RowSet rs;                             // rows of the current work item
   float red[40];
 };
 
@@ -97,12 +102,12 @@ struct StepVars {           // per minibatch step, identical in every role
   int rows, rows_h[2], row0, pos;
   uint32_t base;            // epi_done value when every item of the previous step has finished
 };
-__device__ __forceinline__ StepVars step_vars(const MemberDev& mb, long long s, long long i, int n_epis) {
+__device__ __forceinline__ StepVars step_vars(const RowSet& rs, long long s, long long i, int n_epis) {
   StepVars v;
-  const int spe = (mb.n_rows + mb.batch - 1) / mb.batch;
+  const int spe = (rs.n_rows + rs.batch - 1) / rs.batch;
   v.pos = (int)(s % spe);
-  v.row0 = v.pos * mb.batch;
-  v.rows = min(mb.batch, mb.n_rows - v.row0);
+  v.row0 = v.pos * rs.batch;
+  v.rows = min(rs.batch, rs.n_rows - v.row0);
   v.rows_h[0] = min(v.rows, 128);
   v.rows_h[1] = v.rows - v.rows_h[0];
   v.base = 1u + (uint32_t)i * (uint32_t)n_epis;
@@ -127,7 +132,8 @@ __device__ __forceinline__ PStep load_pstep(const Step* steps, int k) {
   return p;
 }
 
-__device__ void producer_role(const TrainLaunch& t, const ProgramDev& pg, const MemberDev& mb, const MemberTc& mt,
+__device__ void producer_role(const TrainLaunch& t, const ProgramDev& pg, const RowSet& rs, const MemberTc& mt,
+                              const unsigned char* const* xplanes, bool recon,
                               const unsigned char* stash, unsigned char* smem, Ctrl* ctl, uint32_t& seq) {
   unsigned char* ring = smem + kSmemRing;
   const Step* __restrict__ steps = pg.steps;
@@ -137,7 +143,7 @@ __device__ void producer_role(const TrainLaunch& t, const ProgramDev& pg, const 
   fence_async_all();          // weight planes may have been written by another SM (previous work item of this member)
   PStep nxt = load_pstep(steps, 0);
   for (long long i = 0; i < n_chunk; ++i) {
-    const StepVars sv = step_vars(mb, s0 + i, i, pg.n_epis);
+    const StepVars sv = step_vars(rs, s0 + i, i, pg.n_epis);
     const bool tr = g_trace && blockIdx.x == 0 && i0 + i == g_trace_step;
     const int tb = 3 * pg.n_epis + 3 * pg.n_steps;
     for (int k = 0; k < n_steps; ++k) {
@@ -155,12 +161,13 @@ __device__ void producer_role(const TrainLaunch& t, const ProgramDev& pg, const 
         if (bytes == 0) continue;          // A resident in ACT[half] / B = the tile the previous step kept
         // weight planes: every Adam item of the previous step (dataset tiles do not wait: the first x tile of a step
         // is in flight while the previous step ends)
-        if (space == SP_W) wait_all(ctl->epi_done, sv.base);
+        // (a reconstruction launch never rewrites the planes: its weight tiles run ahead of the previous tile's items)
+        if (space == SP_W && !recon) wait_all(ctl->epi_done, sv.base);
         const long long off = which == 0 ? st.a_off : st.b_off;
         const unsigned char* src;
         if (space == SP_W) src = mt.wplanes + off;
         else if (space == SP_STASH) src = stash + off;
-        else src = mt.xplanes[st.x_mod] + ((long long)(sv.pos * mt.n_half + st.half) * pg.lay.x_cg[st.x_mod]) * 4096 + off;
+        else src = xplanes[st.x_mod] + ((long long)(sv.pos * rs.n_half + st.half) * pg.lay.x_cg[st.x_mod]) * 4096 + off;
         const uint32_t slot = seq % kSlots, use = seq / kSlots;
         tc::mbar_wait(&ctl->empty[slot], (use & 1u) ^ 1u);
         expect_tx(&ctl->full[slot], bytes);
@@ -182,6 +189,9 @@ struct LaunchP {
   long long master_floats;
   int ms_off[kMaxParamArchs], ms_cnt[kMaxParamArchs];   // slice of msteps per architecture
   int n_chunks;             // a member's steps of this launch are dealt as n_chunks work items (consecutive step ranges)
+  // forward-only (reconstruction) launch: recon_mode 1 = decode the mean, 2 = sampled z; work items = tile ranges
+  int recon_mode; int n_rwork;
+  const ReconTc* rtc; const ReconWork* rwork;
   int ep_off[kMaxParamArchs], ep_cnt[kMaxParamArchs];   // slice of epis_p per architecture; cnt 0 = global-memory table
   MStep msteps[kMaxParamSteps];
   EpiP epis_p[kMaxParamEpis];
@@ -196,7 +206,7 @@ __device__ __forceinline__ bool elect_one() {
 // ------------------------------------------------------------------------------------------------
 // MMA issuer: 3 BF16 passes per K = 16 step.  The WHOLE warp walks the step table (kernel parameters ->
 // uniform loads); one elected lane issues, so descriptors never leave the uniform datapath.
-__device__ void mma_role(const LaunchP& L, int ai, const MemberDev& mb, unsigned char* smem, Ctrl* ctl, uint32_t tmem,
+__device__ void mma_role(const LaunchP& L, int ai, const RowSet& rs, unsigned char* smem, Ctrl* ctl, uint32_t tmem,
                          uint32_t& seq, int n_epis) {
   const uint32_t ring = tc::smem_u32(smem + kSmemRing);
   const uint32_t act0 = tc::smem_u32(smem);
@@ -205,7 +215,7 @@ __device__ void mma_role(const LaunchP& L, int ai, const MemberDev& mb, unsigned
   const int k0 = L.ms_off[ai], k1 = k0 + L.ms_cnt[ai];
   uint32_t held_slot = 0;
   for (long long i = 0; i < n_chunk; ++i) {
-    const StepVars sv = step_vars(mb, s0 + i, i, n_epis);
+    const StepVars sv = step_vars(rs, s0 + i, i, n_epis);
     const bool half1 = __any_sync(0xffffffffu, sv.rows_h[1] > 0);
     wait_all(ctl->epi_done, sv.base);
     const bool tr = g_trace && blockIdx.x == 0 && i0 + i == g_trace_step;
@@ -282,6 +292,13 @@ struct EpiCtx {
   float step_size, inv_bc2, b1, b2, aeps;
   float kl_acc, ll_acc;
   float* dw_acc;            // [NMB_MAX_MOD] gPoE alpha-gradient partials (local array of the role)
+  int recon;                // 0 = training step; 1 = reconstruction, decode the mean; 2 = reconstruction, sampled z
+  const ReconTc* rt;        // rows and outputs of a reconstruction launch
+  // row source of the current work item: the member's training rows, or the rows of a reconstruction launch (looked up
+  // on demand: in the training instantiation `recon` is the constant 0 and nothing extra stays live in registers)
+  __device__ __forceinline__ const float* xc_rows(int m) const { return recon ? rt->xc[m] : mb->xc[m]; }
+  __device__ __forceinline__ const unsigned char* cplanes0() const { return recon ? rt->cplanes[0] : mt->cplanes[0]; }
+  __device__ __forceinline__ int n_half() const { return recon ? 2 : mt->n_half; }
 #ifdef NMB_TCP_FINE_TRACE
   unsigned long long* tr_ptr;
 #endif
@@ -393,7 +410,8 @@ __device__ __forceinline__ void epi_hidden(EpiCtx& c, const Epi& e) {
   // stash block: one 128-row block (group chunk 4 KB = hi 2 KB + lo 2 KB) or, src_cg > 0, two 64-row sub-blocks of
   // src_cg groups (group chunk 2 KB = hi 1 KB + lo 1 KB): the weight gradient that reads it is split over K
   const int b64 = e.src_cg;
-  unsigned char* st = c.stash + e.stash_off + (b64 ? (long long)(c.row >> 6) * b64 * 2048 + (c.row & 63) * 16 : (long long)c.row * 16);
+  const bool keep = e.stash_off >= 0;             // forward-only program: nothing is stashed for a backward pass
+  unsigned char* st = c.stash + (keep ? e.stash_off : 0) + (b64 ? (long long)(c.row >> 6) * b64 * 2048 + (c.row & 63) * 16 : (long long)c.row * 16);
   const int st_g = b64 ? 2048 : 4096, st_lo = b64 ? 1024 : 2048;
   const float slope = c.a->non_linear ? kSlope : 1.f;        // leaky-relu(x) = max(x, slope * x)
   const int n_cols = e.n_cols, n_mma = e.n_mma, n_valid = e.n_valid, tcol = e.tmem_col;
@@ -426,8 +444,10 @@ __device__ __forceinline__ void epi_hidden(EpiCtx& c, const Epi& e) {
       const long long off = (long long)(2 * ch + q) * 4096;
       *reinterpret_cast<uint4*>(act + off) = hh;
       *reinterpret_cast<uint4*>(act + off + 2048) = ll;
-      *reinterpret_cast<uint4*>(st + (long long)(2 * ch + q) * st_g) = hh;
-      *reinterpret_cast<uint4*>(st + (long long)(2 * ch + q) * st_g + st_lo) = ll;
+      if (keep) {
+        *reinterpret_cast<uint4*>(st + (long long)(2 * ch + q) * st_g) = hh;
+        *reinterpret_cast<uint4*>(st + (long long)(2 * ch + q) * st_g + st_lo) = ll;
+      }
     }
   }
 }
@@ -460,9 +480,13 @@ __device__ void epi_latent(EpiCtx& c, const Epi& e, const float* eps_src) {
   if (M > 1 && a.combine == NMB_COMBINE_GPOE) softmax_alpha(c.mb->params + a.alpha_off, M, w);
   const int n = rows * Z;
   const int g_base = (128 * h * Z) / 4;
+  // reconstruction: Philox stream 1, counter = tile index (the draws of nmb_ensemble_reconstruct's generic engine)
+  float* out_mu = (c.recon && c.rt->mu) ? c.rt->mu + (long long)c.row0 * Z : nullptr;
+  float* out_lv = (c.recon && c.rt->logvar) ? c.rt->logvar + (long long)c.row0 * Z : nullptr;
   for (int g = c.tid; g * 4 < n; g += c.nthr) {
     float nrm[4] = {0.f, 0.f, 0.f, 0.f};
-    if (!eps_src) philox_normal4(c.mb->seed, (unsigned long long)c.step, 0u, (uint32_t)(g_base + g), nrm);
+    if (!eps_src && c.recon != 1)
+      philox_normal4(c.mb->seed, (unsigned long long)c.step, c.recon ? 1u : 0u, (uint32_t)(g_base + g), nrm);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int el = g * 4 + j;
@@ -481,8 +505,10 @@ __device__ void epi_latent(EpiCtx& c, const Epi& e, const float* eps_src) {
         }
         f = fuse_forward(mu, lv, M, a.combine, w);
       }
-      const float eps = eps_src ? eps_src[gb * Z + z] : nrm[j];
+      const float eps = c.recon == 1 ? 0.f : (eps_src ? eps_src[gb * Z + z] : nrm[j]);
       S[a.s_mub + gb * Z + z] = f.mu; S[a.s_lvb + gb * Z + z] = f.lv; S[a.s_eps + gb * Z + z] = eps;
+      if (out_mu) out_mu[gb * Z + z] = f.mu;
+      if (out_lv) out_lv[gb * Z + z] = f.lv;
       zbuf[gb * Z + z] = f.mu + eps * expf(0.5f * f.lv);
       c.kl_acc += -0.5f * (1.f + f.lv - f.mu * f.mu - expf(f.lv));
     }
@@ -492,7 +518,7 @@ __device__ void epi_latent(EpiCtx& c, const Epi& e, const float* eps_src) {
   for (int m = 0; m < M; ++m) {
     const ModDesc& q = a.mod[m];
     unsigned char* st = c.stash + lay.g0[m][h];
-    const float* xc = c.mb->xc[m] + (long long)(c.row0 + 128 * h) * q.ldx + q.D;
+    const float* xc = c.xc_rows(m) + (long long)(c.row0 + 128 * h) * q.ldx + q.D;
     const int ldx = q.ldx, C = a.C;
     for (int u = c.tid; u < 128 * cg; u += c.nthr) {
       const int r = u & 127, g = u >> 7;
@@ -648,6 +674,33 @@ __device__ __forceinline__ void epi_recon(EpiCtx& c, const Epi& e) {
   }
 #undef NMB_LOAD_X
   c.ll_acc += ll * (gauss ? -0.5f * inv_rows : -inv_rows_d);
+}
+
+// Forward-only program: x_recon tile (accumulator rows = the 128 rows of this half) -> fp32 rows of the caller's
+// [n_rows][D] output (pred_recon, cVAE.py:549-555 / 1198-1208).  Each thread owns one row: 64 contiguous bytes per chunk.
+__device__ __forceinline__ void epi_xhat(EpiCtx& c, const Epi& e) {
+  const ModDesc& q = c.a->mod[e.mod];
+  const int h = e.half, D = q.D;
+  const bool vr = c.row < c.rows_of(h);
+  float* out = c.rt->xhat[e.mod];
+  const int n_valid = e.n_valid, n_cols = e.n_cols, tcol = e.tmem_col;
+  float* dst = out ? out + (long long)(c.row0 + 128 * h + c.row) * D + e.col0 : nullptr;
+  const bool vec = out && ((reinterpret_cast<unsigned long long>(dst) & 15ull) == 0ull);
+  for (int ch = c.cpart; ch * 16 < n_cols; ch += c.parts) {
+    const int col = ch * 16;
+    if (col >= n_valid) break;
+    float v[16];
+    __syncwarp();
+    tc::tmem_ld16(taddr(c, tcol + col), v);
+    if (!vr || !out) continue;
+    if (vec && col + 16 <= n_valid) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + col + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) if (col + j < n_valid) dst[col + j] = v[j];
+    }
+  }
 }
 
 // logvar_out: gradient from the per-warp partial sums of r^2 e^{-lam} (both halves complete), Adam, refreshed
@@ -963,20 +1016,20 @@ __device__ __forceinline__ float bf16pair_hi(uint32_t w) { return __uint_as_floa
 __device__ void epi_head_latent_pre(EpiCtx& c, const Epi& e, const float* eps_src) {
   {   // this row's decoder-input template planes start their way to L1 while the head GEMM finishes (no registers held)
     const Layout& lay = c.pg->lay;
-    const unsigned char* tp = c.mt->cplanes[0] + (long long)(c.pos * c.mt->n_half + e.half) * lay.c_cg * 4096 + c.row * 16;
+    const unsigned char* tp = c.cplanes0() + (long long)(c.pos * c.n_half() + e.half) * lay.c_cg * 4096 + c.row * 16;
     for (int g = 0; g < lay.c_cg; ++g) {
       asm volatile("prefetch.global.L1 [%0];" ::"l"(tp + (long long)g * 4096));
       asm volatile("prefetch.global.L1 [%0];" ::"l"(tp + (long long)g * 4096 + 2048));
     }
   }
-  if (eps_src) return;
+  if (eps_src || c.recon == 1) return;
   const ArchDesc& a = *c.a;
   const int h = e.half, Z = a.Z, n = c.rows_of(h) * Z;
   float* eps = c.scratch + a.s_eps + 128 * h * Z;
   const int g_base = (128 * h * Z) / 4;
   for (int g = c.tid; g * 4 < n; g += c.nthr) {
     float nrm[4];
-    philox_normal4(c.mb->seed, (unsigned long long)c.step, 0u, (uint32_t)(g_base + g), nrm);
+    philox_normal4(c.mb->seed, (unsigned long long)c.step, c.recon ? 1u : 0u, (uint32_t)(g_base + g), nrm);
 #pragma unroll
     for (int j = 0; j < 4; ++j) if (g * 4 + j < n) eps[g * 4 + j] = nrm[j];
   }
@@ -997,13 +1050,24 @@ __device__ void epi_head_latent(EpiCtx& c, const Epi& e, const float* eps_src) {
   // all draws of the row first (a store to the scratch array could alias a later load: the compiler keeps program
   // order, which exposed one L2 round trip per latent element); zz[] holds eps until the arithmetic
 #pragma unroll
-  for (int z = 0; z < 16; ++z) zz[z] = (z < Z && vr) ? epsrow[z] : 0.f;
+  for (int z = 0; z < 16; ++z) zz[z] = (z < Z && vr && c.recon != 1) ? epsrow[z] : 0.f;    // mean decode: eps = 0
   TR3();
   tc::tmem_ld16(taddr(c, e.tmem_col), mu);            // columns 0 .. 15: mu[0 .. Z)
   tc::tmem_ld16(taddr(c, e.tmem_col + Z), lv);        // columns Z .. Z + 15: logvar[0 .. Z)
   TR3();
   float kl = 0.f;
   const long long s_mub = a.s_mub, s_lvb = a.s_lvb, s_eps = a.s_eps;
+  if (c.recon) {            // pred_latent outputs of a reconstruction launch (rows of this tile)
+    float* om = c.rt->mu ? c.rt->mu + ((long long)c.row0 * Z + e0) : nullptr;
+    float* ol = c.rt->logvar ? c.rt->logvar + ((long long)c.row0 * Z + e0) : nullptr;
+#pragma unroll
+    for (int z = 0; z < 16; ++z) {
+      if (z < Z && vr) {
+        if (om) om[z] = mu[z];
+        if (ol) ol[z] = lv[z];
+      }
+    }
+  }
 #pragma unroll
   for (int z = 0; z < 16; ++z) {
     if (z < Z && vr) {
@@ -1017,7 +1081,7 @@ __device__ void epi_head_latent(EpiCtx& c, const Epi& e, const float* eps_src) {
   c.kl_acc += kl;
   TR3();
   // [z | c | 1]: the covariate part comes from the dataset's template block (coalesced 16-byte reads)
-  const unsigned char* tp = c.mt->cplanes[0] + (long long)(c.pos * c.mt->n_half + h) * lay.c_cg * 4096 + c.row * 16;
+  const unsigned char* tp = c.cplanes0() + (long long)(c.pos * c.n_half() + h) * lay.c_cg * 4096 + c.row * 16;
   unsigned char* act = c.smem + h * kActBytes + c.row * 16;
   unsigned char* st = c.stash + lay.g0[0][h] + c.row * 16;
   const int zg = (Z + 7) >> 3;                          // groups that contain z columns (<= 2)
@@ -1124,6 +1188,7 @@ __device__ __forceinline__ void prefetch_adam_state(const EpiCtx& c, const Epi& 
 __device__ void epi_step_end(EpiCtx& c, float* loss_out) {
   const ArchDesc& a = *c.a;
   const int M = a.M;
+  if (c.recon) { c.kl_acc = 0.f; c.ll_acc = 0.f; return; }
   // both loss sums in one pass over the barrier pair (red[] holds 12 + 12 partials)
   float kl, ll;
   {
@@ -1166,7 +1231,7 @@ __device__ __forceinline__ void set_workers(EpiCtx& c, bool all) {
 // data gradients: two independent dependency chains whose latencies overlap) and the optimiser group, which
 // consumes the weight-gradient accumulators (Adam + new weight planes) off both chains.  Every group walks the
 // item list and executes its own items; EK_STEP_END is the only rendezvous.
-__device__ void epilogue_role(const LaunchP& L, int ai, int mi, EpiCtx& c, uint32_t& acc_par) {
+__device__ void epilogue_role(const LaunchP& L, int ai, int mi, EpiCtx& c, const RowSet& rs, uint32_t& acc_par) {
   const TrainLaunch& t = L.t;
   const ProgramDev& pg = *c.pg;
   MemberDev& mb = *c.mb;
@@ -1175,7 +1240,7 @@ __device__ void epilogue_role(const LaunchP& L, int ai, int mi, EpiCtx& c, uint3
   for (int m = 0; m < NMB_MAX_MOD; ++m) dw_acc[m] = 0.f;
   c.dw_acc = dw_acc;
   set_workers(c, true);
-  build_iv_table(c);          // weight planes and the lane-major master state were prepared by tcp_prepare_kernel
+  if (!c.recon) build_iv_table(c);   // weight planes and the lane-major master state were prepared by tcp_prepare_kernel
   __threadfence();
   fence_async_all();
   bar_n(4, kEpiWarps * 32);
@@ -1192,17 +1257,22 @@ __device__ void epilogue_role(const LaunchP& L, int ai, int mi, EpiCtx& c, uint3
   const bool pub = (c.warp % kGroupWarps) == 0 && c.lane == 0;     // the thread that publishes its group's counter
   for (long long i = 0; i < n_chunk; ++i) {
     const long long s = s0 + i;
-    const StepVars sv = step_vars(mb, s, i, n_epis);
+    const StepVars sv = step_vars(rs, s, i, n_epis);
     c.rows = sv.rows; c.rows_h0 = sv.rows_h[0]; c.rows_h1 = sv.rows_h[1]; c.row0 = sv.row0; c.pos = sv.pos;
     c.step = s;
-    {
+    const float* eps = nullptr;
+    float* lo = nullptr;
+    if (c.recon) {           // s = tile index; injected draws [n_rows][Z] of the caller, rows of this tile
+      if (c.recon == 2 && c.rt->eps) eps = c.rt->eps + (long long)sv.row0 * c.a->Z;
+      c.step_size = 0.f; c.inv_bc2 = 1.f;
+    } else {
       const double tt = (double)(s + 1);
       const float lr = mb.lr_steps ? mb.lr_steps[s] : mb.lr;
       c.step_size = (float)((double)lr / (1.0 - pow((double)mb.beta1, tt)));
       c.inv_bc2 = (float)(1.0 / sqrt(1.0 - pow((double)mb.beta2, tt)));
+      eps = t.eps_override ? t.eps_override + ((long long)mi * t.stride_steps + i0 + i) * mb.batch * c.a->Z : nullptr;
+      lo = t.loss_out ? t.loss_out + ((long long)mi * t.stride_steps + i0 + i) * 3 : nullptr;
     }
-    const float* eps = t.eps_override ? t.eps_override + ((long long)mi * t.stride_steps + i0 + i) * mb.batch * c.a->Z : nullptr;
-    float* lo = t.loss_out ? t.loss_out + ((long long)mi * t.stride_steps + i0 + i) * 3 : nullptr;
     for (int k = 0; k < n_epis; ++k) {
       Epi e;
       if (in_params) e = from_epip(L.epis_p[ep0 + k]);
@@ -1275,7 +1345,8 @@ __device__ void epilogue_role(const LaunchP& L, int ai, int mi, EpiCtx& c, uint3
         case EK_LAM: epi_lam(c, e); break;
         case EK_HEAD_LATENT: epi_head_latent(c, e, eps); fence = 1; break;
         case EK_DZ_LATENT_BWD: epi_dz_latent_bwd(c, e); fence = 1; break;
-        default: epi_step_end(c, lo); fence = 2; break;
+        case EK_XHAT: epi_xhat(c, e); break;
+        default: epi_step_end(c, lo); fence = c.recon ? 0 : 2; break;
       }
       if (e.buf >= 0) tc::fence_before();
       if (fence == 1) fence_async_smem();
@@ -1287,6 +1358,9 @@ __device__ void epilogue_role(const LaunchP& L, int ai, int mi, EpiCtx& c, uint3
   }
 }
 
+// RECON = false: the training kernel (recon_mode is the compile-time constant 0 in every role);
+// RECON = true: the forward-only instantiation used by nmb_ensemble_reconstruct.
+template <bool RECON>
 __global__ void __launch_bounds__(kThreadsP, 1) train_tcp_kernel(const __grid_constant__ LaunchP L) {
   extern __shared__ __align__(1024) unsigned char smem[];
   Ctrl* ctl = reinterpret_cast<Ctrl*>(smem + kSmemCtrl);
@@ -1306,7 +1380,8 @@ __global__ void __launch_bounds__(kThreadsP, 1) train_tcp_kernel(const __grid_co
   // Work items = (member, chunk of consecutive minibatch steps), dealt longest-member-first, all chunks 0 before
   // all chunks 1 ...  A chunk waits (thread 0, acquire) until the member's previous chunk -- possibly on another
   // SM -- has published its last step: finer items than whole members keep the tail of the launch short.
-  const int n_items = t.n_members * L.n_chunks;
+  constexpr bool recon = RECON;
+  const int n_items = recon ? L.n_rwork : t.n_members * L.n_chunks;
   const bool dynamic = (int)gridDim.x < n_items;
   bool first = true;
   for (;;) {
@@ -1315,7 +1390,11 @@ __global__ void __launch_bounds__(kThreadsP, 1) train_tcp_kernel(const __grid_co
       if (dynamic) it = atomicAdd(t.work_counter, 1);
       else if (first) it = blockIdx.x;
       int mi = t.n_members;
-      if (it < n_items) {
+      if (it < n_items && recon) {          // forward-only launch: (member, range of 256-row tiles), no cross-item order
+        const ReconWork rw = L.rwork[it];
+        mi = rw.member;
+        ctl->chunk_i0 = rw.tile0; ctl->chunk_n = rw.n_tiles; ctl->chunk_s0 = rw.tile0;
+      } else if (it < n_items) {
         const int chunk = it / t.n_members;
         mi = dynamic ? t.order[it - chunk * t.n_members] : it;
         MemberDev& m = t.members[mi];
@@ -1335,6 +1414,10 @@ __global__ void __launch_bounds__(kThreadsP, 1) train_tcp_kernel(const __grid_co
         ctl->chunk_i0 = (int)i0; ctl->chunk_n = (int)(i1 - i0); ctl->chunk_s0 = need;
       }
       ctl->member = mi;
+      if (mi < t.n_members) {
+        if (recon) { ctl->rs.n_rows = L.rtc[mi].n_rows; ctl->rs.batch = 256; ctl->rs.n_half = 2; }
+        else { ctl->rs.n_rows = t.members[mi].n_rows; ctl->rs.batch = t.members[mi].batch; ctl->rs.n_half = L.mtc[mi].n_half; }
+      }
       for (int g = 0; g < kGroups; ++g) ctl->epi_done[g] = 0;
     }
     first = false;
@@ -1344,26 +1427,29 @@ __global__ void __launch_bounds__(kThreadsP, 1) train_tcp_kernel(const __grid_co
     MemberDev& mb = t.members[mi];
     const ProgramDev& pg = L.progs[mb.arch_idx];
     const MemberTc& mt = L.mtc[mi];
+    const ReconTc* rt = recon ? L.rtc + mi : nullptr;
+    const RowSet& rs = ctl->rs;
     if (ctl->chunk_n > 0) {
       if (warp < kEpiWarps) {
         EpiCtx c;
         c.a = &t.archs[mb.arch_idx]; c.pg = &pg; c.mb = &mb; c.mt = &mt;
+        c.recon = recon ? L.recon_mode : 0; c.rt = rt;
         c.smem = smem; c.stash = stash; c.scratch = t.scratch + (long long)blockIdx.x * t.slot_floats; c.ctl = ctl;
         c.mst_p = L.master + (long long)mi * 3 * L.master_floats;        // per member, persistent across work items
         c.mst_m = c.mst_p + L.master_floats; c.mst_v = c.mst_m + L.master_floats;
         c.tmem = tmem; c.warp = warp; c.lane = lane; c.row = ((warp & 3) << 5) + lane;
         c.grp = warp / kGroupWarps; c.flags = t.flags;
         c.b1 = mb.beta1; c.b2 = mb.beta2; c.aeps = mb.adam_eps;
-        epilogue_role(L, mb.arch_idx, mi, c, acc_par);
+        epilogue_role(L, mb.arch_idx, mi, c, rs, acc_par);
       } else if (warp == kEpiWarps) {
         const int ai = __shfl_sync(0xffffffffu, mb.arch_idx, 0);
-        mma_role(L, ai, mb, smem, ctl, tmem, seq, pg.n_epis);
+        mma_role(L, ai, rs, smem, ctl, tmem, seq, pg.n_epis);
       } else {
-        if (lane == 0) producer_role(t, pg, mb, mt, stash, smem, ctl, seq);
+        if (lane == 0) producer_role(t, pg, rs, mt, recon ? rt->xplanes : mt.xplanes, recon, stash, smem, ctl, seq);
       }
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && !recon) {
       const int spe = (mb.n_rows + mb.batch - 1) / mb.batch;
       const long long done = ctl->chunk_s0 + ctl->chunk_n;
       if (ctl->chunk_n > 0) {
@@ -1422,7 +1508,8 @@ __global__ void __launch_bounds__(256) xprep_kernel(const XPrepItem* items, int 
         }
         put_planes(cb, g, r, v);
       }
-      // ROI targets, lane-major fp32
+      // ROI targets, lane-major fp32 (training only)
+      if (!x.xlm) continue;
       float* xb = x.xlm + (long long)b * x.quads * 512;
       for (int u = threadIdx.x; u < 128 * x.quads; u += 256) {
         const int r = u & 127, qd = u >> 7;
@@ -1455,9 +1542,10 @@ cudaError_t configure_tcp() {
   // Forward progress of chunked work items relies on every CTA of the grid being co-resident (a chunk spins on its
   // predecessor, which may sit on another SM): the grid is capped at the SM count and needs one CTA per SM to fit.
   int per_sm = 0;
-  cudaError_t e = cudaFuncSetAttribute(tcp::train_tcp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tcp::kSmemBytes);
+  cudaError_t e = cudaFuncSetAttribute(tcp::train_tcp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcp::kSmemBytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(tcp::train_tcp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcp::kSmemBytes);
   if (e != cudaSuccess) return e;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tcp::train_tcp_kernel, tcp::kThreadsP, tcp::kSmemBytes);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tcp::train_tcp_kernel<false>, tcp::kThreadsP, tcp::kSmemBytes);
   if (e != cudaSuccess) return e;
   return per_sm >= 1 ? cudaSuccess : cudaErrorLaunchOutOfResources;
 }
@@ -1609,6 +1697,40 @@ __global__ void __launch_bounds__(256) tcp_move_kernel(const PrepArgs a, const i
 }
 }  // namespace tcp
 
+// Forward-only (reconstruction) launch of the pipelined kernel: `progs` / tables are those of the forward-only programs.
+cudaError_t launch_recon_tcp(const TrainLaunch& t, const tcp::ProgramDev* progs, const tcp::ProgramDev* train_progs,
+                             const tcp::MemberTc* mtc, unsigned char* stash, long long stash_bytes,
+                             const tcp::MStep* msteps, const int* ms_off, const int* ms_cnt, int n_archs,
+                             const tcp::EpiP* epis_p, const int* ep_off, const int* ep_cnt, int max_mlayers,
+                             int recon_mode, const tcp::ReconTc* rtc, const tcp::ReconWork* rwork, int n_rwork,
+                             int n_sm, cudaStream_t st) {
+  if (n_rwork <= 0) return cudaSuccess;
+  const int grid = n_rwork < n_sm ? n_rwork : n_sm;
+  if (grid < n_rwork) {
+    cudaError_t e = cudaMemsetAsync(t.work_counter, 0, sizeof(int), st);
+    if (e != cudaSuccess) return e;
+  }
+  // the caller may have changed the parameters since the last call: rebuild the BF16 planes (layout of the TRAINING
+  // program, shared by both programs) from the fp32 parameters
+  tcp::PrepArgs pa{t.members, train_progs, mtc, nullptr, 0, t.n_members, 0};
+  const dim3 pgrid((unsigned)t.n_members, (unsigned)max_mlayers);
+  tcp::tcp_move_kernel<<<pgrid, 256, 0, st>>>(pa, 1);
+  tcp::LaunchP L;
+  L.n_chunks = 1;
+  L.t = t; L.progs = progs; L.mtc = mtc; L.stash = stash; L.stash_bytes = stash_bytes;
+  L.master = nullptr; L.master_floats = 0;
+  L.recon_mode = recon_mode; L.n_rwork = n_rwork; L.rtc = rtc; L.rwork = rwork;
+  for (int a = 0; a < n_archs; ++a) { L.ms_off[a] = ms_off[a]; L.ms_cnt[a] = ms_cnt[a]; L.ep_off[a] = ep_off[a]; L.ep_cnt[a] = ep_cnt[a]; }
+  {
+    int n_ep = 0;
+    for (int a = 0; a < n_archs; ++a) if (ep_cnt[a] > 0 && ep_off[a] + ep_cnt[a] > n_ep) n_ep = ep_off[a] + ep_cnt[a];
+    if (n_ep > 0) std::memcpy(L.epis_p, epis_p, sizeof(tcp::EpiP) * (size_t)n_ep);
+  }
+  std::memcpy(L.msteps, msteps, sizeof(tcp::MStep) * (size_t)(ms_off[n_archs - 1] + ms_cnt[n_archs - 1]));
+  tcp::train_tcp_kernel<true><<<grid, tcp::kThreadsP, tcp::kSmemBytes, st>>>(L);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_train_tcp(const TrainLaunch& t, const tcp::ProgramDev* progs, const tcp::MemberTc* mtc,
                              unsigned char* stash, long long stash_bytes, float* master, long long master_floats,
                              const tcp::MStep* msteps, const int* ms_off, const int* ms_cnt, int n_archs,
@@ -1636,6 +1758,7 @@ cudaError_t launch_train_tcp(const TrainLaunch& t, const tcp::ProgramDev* progs,
   L.n_chunks = n_chunks;
   L.t = t; L.progs = progs; L.mtc = mtc; L.stash = stash; L.stash_bytes = stash_bytes;
   L.master = master; L.master_floats = master_floats;
+  L.recon_mode = 0; L.n_rwork = 0; L.rtc = nullptr; L.rwork = nullptr;
   for (int a = 0; a < n_archs; ++a) { L.ms_off[a] = ms_off[a]; L.ms_cnt[a] = ms_cnt[a]; L.ep_off[a] = ep_off[a]; L.ep_cnt[a] = ep_cnt[a]; }
   {
     int n_ep = 0;
@@ -1643,7 +1766,7 @@ cudaError_t launch_train_tcp(const TrainLaunch& t, const tcp::ProgramDev* progs,
     if (n_ep > 0) std::memcpy(L.epis_p, epis_p, sizeof(tcp::EpiP) * (size_t)n_ep);
   }
   std::memcpy(L.msteps, msteps, sizeof(tcp::MStep) * (size_t)(ms_off[n_archs - 1] + ms_cnt[n_archs - 1]));
-  tcp::train_tcp_kernel<<<grid, tcp::kThreadsP, tcp::kSmemBytes, st>>>(L);
+  tcp::train_tcp_kernel<false><<<grid, tcp::kThreadsP, tcp::kSmemBytes, st>>>(L);
   if (pa.adam) tcp::tcp_move_kernel<<<pgrid, 256, 0, st>>>(pa, 0);
   return cudaGetLastError();
 }

@@ -288,14 +288,17 @@ class EnsembleTrainer:
     # ---- test-time reconstruction ----------------------------------------------------------
     def reconstruct(self, xc: Sequence[Sequence[torch.Tensor]], mode: str = "sample",
                     eps: Optional[Sequence[Optional[torch.Tensor]]] = None, want_latent: bool = False,
-                    want_xhat: bool = True):
+                    want_xhat: bool = True, engine: str = "default"):
         """pred_recon for every member on its own rows (packed, per modality).
 
         mode 'mean' = cVAE.pred_recon (cVAE.py:549-555); 'sample' = cVAE_multimodal.pred_recon
         (cVAE.py:1198-1208; eps injectable); 'decode' = decoders only on a given z passed in `eps`
         (Decoder.forward, cVAE.py:197-206; the covariates are read from the packed rows).
         want_xhat=False with want_latent=True = encoders + fusion only (pred_latent, cVAE.py:540-547).
+        engine: "default" = the pipelined forward-only program where the architecture allows it, "tcs" = generic
+        tcgen05 engine, "fp32" = FFMA engine.
         Returns (xhat[i][m], mu[i], logvar[i])."""
+        eng_bits = {"default": 0, "tcs": _lib.RECON_TC_SIMPLE, "fp32": _lib.RECON_FP32}[engine]
         if mode not in ("mean", "sample", "decode"):
             raise ValueError("mode must be 'mean', 'sample' or 'decode'")
         if mode == "decode" and (eps is None or want_latent):
@@ -336,7 +339,7 @@ class EnsembleTrainer:
         with torch.cuda.device(self.device):
             _lib.check(self.lib.nmb_ensemble_reconstruct(
                 self.handle, _lib.ptr_table(tbl), _lib.int_table(rows),
-                {"mean": _lib.RECON_MEAN, "sample": _lib.RECON_SAMPLE, "decode": _lib.RECON_GIVEN_Z}[mode], eps_tbl,
+                {"mean": _lib.RECON_MEAN, "sample": _lib.RECON_SAMPLE, "decode": _lib.RECON_GIVEN_Z}[mode] | eng_bits, eps_tbl,
                 _lib.ptr_table(out_tbl),
                 _lib.ptr_table([t.data_ptr() for t in mus]) if want_latent else None,
                 _lib.ptr_table([t.data_ptr() for t in lvs]) if want_latent else None,

@@ -7,7 +7,8 @@ int main(int argc, char** argv){
   for (int m = 0; m < a.n_mod; ++m) a.input_dims[m] = atoi(argv[1]);
   a.n_hidden=2; a.hidden[0]=110; a.hidden[1]=110; a.latent=10; a.c_dim=29; a.non_linear=1; a.combine = 1;
   ArchDesc d; const char* err; if(build_arch(a,&d,&err)){printf("err %s\n",err);return 1;}
-  auto P = tcp::build_program(d);
+  const bool fwd = argc > 3 && argv[3][0] == 'f';      // forward-only (reconstruction) program
+  auto P = tcp::build_program(d, fwd);
   const int NS = P.steps.size(), NE = P.epis.size();
   printf("steps %d epis %d\n", NS, NE);
   // the compact item table that travels in the kernel parameters must reproduce every field the kernel reads

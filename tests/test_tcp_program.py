@@ -24,7 +24,10 @@ def sim(tmp_path_factory):
 
 
 @pytest.mark.parametrize("args", [["116"], ["348"], ["116", "3"], ["20"], ["348", "2"], ["1000"], ["7", "4"],
-                                  ["128"], ["129"], ["64", "2"], ["3"]])
+                                  ["128"], ["129"], ["64", "2"], ["3"],
+                                  # forward-only (reconstruction) programs of the same architectures
+                                  ["116", "1", "fwd"], ["348", "1", "fwd"], ["116", "3", "fwd"], ["348", "2", "fwd"],
+                                  ["1000", "1", "fwd"], ["7", "4", "fwd"], ["129", "1", "fwd"]])
 def test_step_program_drains_without_deadlock(sim, args):
     r = subprocess.run([sim] + args, capture_output=True, text=True)
     assert r.returncode == 0 and "OK all done" in r.stdout, r.stdout + r.stderr
