@@ -48,8 +48,19 @@ struct Blob {
     int device = 0;
     cudaError_t e = cudaGetDevice(&device);
     if (e != cudaSuccess) return e;
+    // 64-bit words at a time (tables of a 480-member reconstruct call are ~300 KB: a byte-wise hash cost 0.3 ms per call)
     unsigned long long h = 1469598103934665603ull ^ (unsigned long long)device;
-    for (unsigned char c : host) { h ^= c; h *= 1099511628211ull; }
+    {
+      const size_t nw = host.size() / 8;
+      const unsigned char* pb = host.data();
+      for (size_t i = 0; i < nw; ++i) {
+        unsigned long long w;
+        std::memcpy(&w, pb + 8 * i, 8);
+        h = (h ^ w) * 0x9E3779B97F4A7C15ull;
+        h ^= h >> 29;
+      }
+      for (size_t i = nw * 8; i < host.size(); ++i) { h ^= pb[i]; h *= 1099511628211ull; }
+    }
     {
       std::lock_guard<std::mutex> lock(g_blob_mu);
       for (BlobCacheEntry& c : g_blob_cache)

@@ -27,11 +27,13 @@ def shard_members(n_members: int, rank: int, world_size: int, cost: Sequence[flo
     return sorted(order[rank::world_size])
 
 
-def gather_member_tables(local: torch.Tensor, owned: Sequence[int], n_members: int) -> torch.Tensor:
+def gather_member_tables(local: torch.Tensor, owned: Sequence[int], n_members: int,
+                         collective: bool = True) -> torch.Tensor:
     """local: [len(owned), W] records of this rank's members -> [n_members, W] on every rank.
-    Shards may differ in length by one; they are padded to the longest for the collective."""
+    Shards may differ in length by one; they are padded to the longest for the collective.
+    collective=False: the caller owns every member (no exchange even inside a distributed run)."""
     rank, ws = world()
-    if ws == 1:
+    if ws == 1 or not collective:
         out = torch.empty((n_members, local.shape[1]), dtype=local.dtype, device=local.device)
         out[torch.as_tensor(list(owned), device=local.device, dtype=torch.long)] = local
         return out

@@ -59,8 +59,10 @@ class EnsembleRunner:
     """Train + score one (fold x modality x seed) ensemble, sharded over torch.distributed ranks."""
 
     def __init__(self, hw: workloads.HostWorkload, n_seeds: int, device, seed0: int = 0, pin: bool = False,
-                 score_mode: str = "sample"):
-        self.rank, self.world = nd.world()
+                 score_mode: str = "sample", rank: int = None, world: int = None):
+        """rank / world default to the torch.distributed group; world=1 (explicit) = the whole ensemble on this
+        GPU with no collective (also inside a distributed run: the unsharded reference of the N=1 vs N>1 test)."""
+        self.rank, self.world = nd.world() if world is None else (int(rank or 0), int(world))
         self.hw, self.n_seeds, self.device = hw, n_seeds, torch.device(device)
         self.grid = [(f, name, seed0 + s) for f in range(len(hw.folds)) for name in hw.names for s in range(n_seeds)]
         cost = [workloads.train_flops_per_sample(hw.dims[name], hw.c_dim, hw.hidden, hw.latent) for _, name, _ in self.grid]
@@ -101,7 +103,7 @@ class EnsembleRunner:
 
     def score(self) -> GatheredScores:
         self.scorer.run()
-        table = nd.gather_member_tables(self.local_records(), self.owned, len(self.grid))
+        table = nd.gather_member_tables(self.local_records(), self.owned, len(self.grid), collective=self.world > 1)
         return GatheredScores(table=table, d_max=self.d_max, n_test_max=self.n_test_max, grid=self.grid)
 
     def fold_auc(self, gs: GatheredScores):

@@ -191,7 +191,22 @@ def _rank_main(rank, world, port, n_members, out_dir):
     owned = nd.shard_members(n_members, rank, world, cost)
     local = torch.tensor([[float(i), float(i) * 0.5, float(cost[i])] for i in owned], dtype=torch.float64)
     table = nd.gather_member_tables(local, owned, n_members)
-    torch.save({"owned": owned, "table": table}, os.path.join(out_dir, f"rank{rank}.pt"))
+    # the runner's record layout {subject AUC | 3 x d_max ROI stats | per-subject deviation (padded)} and the
+    # modality averaging that follows the gather (group analysis :212-215)
+    from multi_modal_normative_modeling_b200.runner import GatheredScores, fold_seed_average
+    names = ["a", "b", "c", "d"]
+    grid = [(i // 8, names[(i // 2) % 4], i % 2) for i in range(n_members)] if n_members % 8 == 0 else None
+    avg = None
+    if grid is not None:
+        d_max, n_test_max = 3, 5
+        rec = torch.full((len(owned), 1 + 3 * d_max + n_test_max), float("nan"), dtype=torch.float64)
+        for k, i in enumerate(owned):
+            rec[k, 0] = i
+            rec[k, 1 + 3 * d_max:1 + 3 * d_max + 4] = torch.arange(4, dtype=torch.float64) + 10.0 * i
+        full = nd.gather_member_tables(rec, owned, n_members)
+        gs = GatheredScores(table=full, d_max=d_max, n_test_max=n_test_max, grid=grid)
+        avg = {k: v for k, v in fold_seed_average(gs, [4] * n_members).items()}
+    torch.save({"owned": owned, "table": table, "avg": avg}, os.path.join(out_dir, f"rank{rank}.pt"))
     dist.destroy_process_group()
 
 
@@ -211,3 +226,9 @@ def test_member_sharding_and_all_gather_gloo(tmp_path, n_members):
     assert torch.equal(r0["table"], r1["table"])
     assert torch.equal(r0["table"][:, 0], torch.arange(n_members, dtype=torch.float64))
     assert torch.equal(r0["table"][:, 1], torch.arange(n_members, dtype=torch.float64) * 0.5)
+    if n_members == 480:          # modalities of one (fold, seed) live on different ranks; their mean is exact after the gather
+        assert set(r0["avg"]) == {(f, s) for f in range(60) for s in range(2)}
+        for (f, s), v in r0["avg"].items():
+            members = [8 * f + 2 * m + s for m in range(4)]
+            want = torch.arange(4, dtype=torch.float64) + 10.0 * sum(members) / 4
+            assert torch.allclose(v, want) and torch.equal(v, r1["avg"][(f, s)])
