@@ -136,6 +136,37 @@ def cpu_train_pass(hw, epochs, threads, ref):
     return samples, t_total
 
 
+def cpu_deviation_sample(hw, threads, ref):
+    """pred_recon + deviation + roc/auc on the host for one fold x 4 modalities (subjects/s)."""
+    import numpy as np
+    import pandas as pd
+    import torch
+    from oracle import deviation as odev
+    torch.set_num_threads(threads)
+    fold = hw.folds[0]
+    labels = (fold.test_df["DIA"].to_numpy() != hw.hc_label).astype(np.int64)
+    n, t_total = 0, 0.0
+    for name, model, xt, ct in _cpu_models(hw, ref):
+        d = hw.dims[name]
+        x, c = torch.from_numpy(fold.test_x[name]), torch.from_numpy(fold.test_c).long()
+        t0 = time.perf_counter()
+        if ref is not None:
+            pred = model.pred_recon([pd.DataFrame(fold.test_x[name])], fold.test_c, torch.device("cpu"), "gPoE")[0]
+            pred_tr = model.pred_recon([pd.DataFrame(fold.train_x[name])], fold.train_c, torch.device("cpu"), "gPoE")[0]
+        else:
+            pred = model.pred_recon([x], c, "gPoE")[0].numpy()
+            pred_tr = model.pred_recon([xt], ct, "gPoE")[0].numpy()
+        roi = odev.recon_deviation_roi(fold.test_x64[name], pred)
+        subj = odev.recon_deviation(fold.test_x64[name], pred)
+        mean, std = odev.normative_stats(odev.recon_deviation_roi(fold.train_x[name], pred_tr))
+        z = odev.zscores(roi, mean, std)
+        _ = [odev.auc(z[:, j], labels) for j in range(d)]
+        _ = odev.auc(subj, labels)
+        t_total += time.perf_counter() - t0
+        n += x.shape[0]
+    return n / t_total
+
+
 def _cpu_worker(q, barrier, threads, use_ref, passes, epochs, what):
     """Child process of the CPU arm.  CUDA is hidden BEFORE torch is imported: the reference module pins
     ``cuda:1`` at import when a GPU is visible (cVAE.py:17), and the CPU arm must not touch the GPU anyway."""
@@ -169,12 +200,26 @@ def cpu_parallel(procs, threads, use_ref, passes, epochs, what="train"):
         p.start()
     times = []
     if what == "train":
-        for _ in range(passes):
-            barrier.wait(900)
-            t0 = time.perf_counter()
-            barrier.wait(900)
-            times.append(time.perf_counter() - t0)
-    outs = [q.get(timeout=900) for _ in range(procs)]
+        try:
+            for _ in range(passes):
+                barrier.wait(300)
+                t0 = time.perf_counter()
+                barrier.wait(600)
+                times.append(time.perf_counter() - t0)
+        except Exception:
+            for p in ps:
+                p.kill()
+            raise RuntimeError("CPU-baseline workers did not reach the barrier (a worker died?)")
+    outs = []
+    deadline = time.time() + 600
+    while len(outs) < procs:                                   # never sit on a dead child
+        try:
+            outs.append(q.get(timeout=2))
+        except Exception:
+            if time.time() > deadline or not any(p.is_alive() for p in ps):
+                for p in ps:
+                    p.kill()
+                raise RuntimeError("CPU-baseline worker died or timed out (%d of %d results)" % (len(outs), procs))
     for p in ps:
         p.join()
     return sum(o[1] for o in outs), times, outs[0][2]
@@ -555,7 +600,10 @@ def run_b200(args):
         if deviation:
             line["deviation"] = deviation
         if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_baseline_block(args)
+            try:
+                line["cpu_baseline"] = cpu_baseline_block(args)
+            except Exception as e:          # the GPU numbers are not held hostage by the CPU leg
+                line["cpu_baseline"] = {"error": "%s: %s" % (type(e).__name__, e)}
         print(json.dumps(line))
     run.close()
     if world > 1:
