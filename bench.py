@@ -550,6 +550,25 @@ def run_b200(args):
                          "unit": UNIT, "members_per_gpu": trw.n, "ms_per_step": w_ms / max(3, args.steps // 2),
                          "note": "every rank trains its own 480-member ensemble (distinct seeds): the round-1 headline"}
         trw.close()
+    if rank == 0:
+        # the fold prologue (RobustScaler, covariate bins, bootstrap gather, packing) of all 20 (fold, modality) datasets:
+        # host pandas / sklearn path vs the GPU-resident prologue on the raw float64 tables already in HBM
+        try:
+            from multi_modal_normative_modeling_b200 import pipeline, prologue
+            t0 = time.perf_counter()
+            pipeline.prepare_folds(hw.subjects, hw.features, hw.columns, hc_label=hw.hc_label, n_splits=hw.n_splits)
+            host_ms = 1e3 * (time.perf_counter() - t0)
+            raw = prologue.upload_raw(hw.subjects, hw.features, hw.columns, dev)
+            prologue.prepare_folds_gpu(hw.subjects, hw.features, hw.columns, hw.hc_label, dev, n_splits=hw.n_splits, raw=raw)
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            prologue.prepare_folds_gpu(hw.subjects, hw.features, hw.columns, hw.hc_label, dev, n_splits=hw.n_splits, raw=raw)
+            torch.cuda.synchronize(dev)
+            extra["prologue"] = {"host_pandas_sklearn_ms": host_ms, "gpu_ms": 1e3 * (time.perf_counter() - t0),
+                                 "note": "5 folds x 4 modalities: scaler fit + transform, age / sex rank bins, bootstrap "
+                                         "gather, row packing; GPU figure includes the host-side row-position bookkeeping"}
+        except Exception as e:
+            extra["prologue"] = {"error": "%s: %s" % (type(e).__name__, e)}
     if rank == 0 and not args.no_module_step:
         try:
             extra["module_step_ms"] = module_step_ms(dev)

@@ -108,6 +108,24 @@ int nmb_packed_row_stride(int32_t d, int32_t c_dim, int32_t* ldx);
 int nmb_pack_rows(const float* x, const float* c, int64_t n_rows, int32_t d, int32_t c_dim,
                   float* out, void* stream);
 
+/* ---- preprocessing prologue of a fold, resident on the GPU ------------------------------------------
+ * x: the raw float64 feature table of one modality [n_all][ld] in HBM; idx: row positions of the fold's train or test
+ * rows (host-computed: bootstrap + merge order are integer work on the legacy numpy RNG, utils.py:73-168), or NULL for
+ * rows 0..n-1.  float64 arithmetic, results bit-identical to the host calls they replace. */
+
+/* RobustScaler().fit (train script :101-102): center[j] = np.nanmedian, scale[j] = q75 - q25 (np.nanpercentile, linear),
+ * zeros -> 1.  n <= 8192 rows (shared-memory sort); center / scale: device float64 [d]. */
+int nmb_robust_fit(const double* x, int64_t ld, int32_t d, const int32_t* idx, int32_t n, double* center, double* scale,
+                   void* stream);
+/* v.rank(method='first') -> pd.qcut(q) bin per selected row (train script :105-114).  edges: device float64 [q + 1], the
+ * bin edges pandas computes for n ranks (they depend on n only; the host passes pandas' own values).  bins: int32 [n]. */
+int nmb_rank_bins(const double* v, const int32_t* idx, int32_t n, const double* edges, int32_t q, int32_t* bins, void* stream);
+/* One pass: gather rows, (x - center) / scale in float64 -> fp32, np.eye(n_age)[age_bin] | np.eye(n_sex)[sex_bin], the
+ * constant-1 column, zero padding: the packed rows of nmb_pack_rows ([n][roundup4(d + n_age + n_sex + 1)]). */
+int nmb_pack_rows_scaled(const double* x, int64_t ld, int32_t d, const int32_t* idx, int64_t n, const double* center,
+                         const double* scale, const int32_t* age_bin, int32_t n_age, const int32_t* sex_bin, int32_t n_sex,
+                         float* out, void* stream);
+
 /* ---- ensemble ---------------------------------------------------------------------- */
 int nmb_ensemble_create(NmbEnsemble** out, int32_t device, const NmbMember* members /*host*/,
                         int32_t n_members);

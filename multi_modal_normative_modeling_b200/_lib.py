@@ -43,6 +43,10 @@ _PROTOS = {
     "nmb_arch_slots": (C.c_int, [C.POINTER(NmbArch), C.POINTER(NmbSlot), C.c_int32, C.POINTER(C.c_int32)]),
     "nmb_packed_row_stride": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
     "nmb_pack_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "nmb_robust_fit": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nmb_rank_bins": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "nmb_pack_rows_scaled": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "nmb_ensemble_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.POINTER(NmbMember), C.c_int32]),
     "nmb_ensemble_destroy": (C.c_int, [C.c_void_p]),
     "nmb_ensemble_size": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),

@@ -350,6 +350,31 @@ int nmb_pack_rows(const float* x, const float* c, int64_t n_rows, int32_t d, int
   return 0;
 }
 
+int nmb_robust_fit(const double* x, int64_t ld, int32_t d, const int32_t* idx, int32_t n, double* center, double* scale,
+                   void* stream) {
+  if (!x || !center || !scale || d < 1 || n < 1 || ld < d) return fail("bad argument");
+  if (n > prologue_max_rows()) return fail("nmb_robust_fit: at most 8192 rows per fold (shared-memory sort)");
+  CU(launch_robust_fit(x, ld, d, idx, n, center, scale, (cudaStream_t)stream));
+  return 0;
+}
+
+int nmb_rank_bins(const double* v, const int32_t* idx, int32_t n, const double* edges, int32_t q, int32_t* bins, void* stream) {
+  if (!v || !edges || !bins || n < 1 || q < 1) return fail("bad argument");
+  if (n > prologue_max_rows()) return fail("nmb_rank_bins: at most 8192 rows per fold");
+  CU(launch_rank_bins(v, idx, n, edges, q, bins, (cudaStream_t)stream));
+  return 0;
+}
+
+int nmb_pack_rows_scaled(const double* x, int64_t ld, int32_t d, const int32_t* idx, int64_t n, const double* center,
+                         const double* scale, const int32_t* age_bin, int32_t n_age, const int32_t* sex_bin, int32_t n_sex,
+                         float* out, void* stream) {
+  if (!x || !center || !scale || !out || d < 1 || n < 0 || n_age < 0 || n_sex < 0 || (n_age && !age_bin) || (n_sex && !sex_bin))
+    return fail("bad argument");
+  CU(launch_pack_scaled(x, ld, d, idx, n, center, scale, age_bin, n_age, sex_bin, n_sex, round4(d + n_age + n_sex + 1), out,
+                        (cudaStream_t)stream));
+  return 0;
+}
+
 int nmb_ensemble_create(NmbEnsemble** out, int32_t device, const NmbMember* members, int32_t n_members) {
   if (!out || !members || n_members < 1) return fail("bad argument");
   int count = 0;

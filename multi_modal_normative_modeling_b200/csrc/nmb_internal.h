@@ -42,6 +42,14 @@ struct LatentTable {
 };
 void launch_latent_deviation(const LatentTable& t, int n_seg, int max_rows, cudaStream_t st);
 int sm_count();
+// nmb_prologue.cu
+int prologue_max_rows();
+cudaError_t launch_robust_fit(const double* x, long long ld, int d, const int* idx, int n, double* center, double* scale,
+                              cudaStream_t st);
+cudaError_t launch_rank_bins(const double* v, const int* idx, int n, const double* edges, int q, int* bins, cudaStream_t st);
+cudaError_t launch_pack_scaled(const double* x, long long ld, int d, const int* idx, long long n, const double* center,
+                               const double* scale, const int* age_bin, int n_age, const int* sex_bin, int n_sex, int ldx,
+                               float* out, cudaStream_t st);
 void launch_mean_rows(const PtrTable16& src, int k, long long n, float* out, cudaStream_t st);
 void launch_adam(float* p, const float* g, float* m, float* v, long long n, float step_size, float bc2_sqrt,
                  float b1, float b2, float eps, cudaStream_t st);

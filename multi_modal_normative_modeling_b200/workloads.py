@@ -51,6 +51,11 @@ class HostWorkload:
     latent: int = 10
     c_dim: int = 29
     batch: int = 256
+    # the raw frames the folds were cut from (what pd.read_csv returns): input of the GPU prologue
+    subjects: pd.DataFrame = None
+    features: Dict[str, pd.DataFrame] = None
+    columns: Dict[str, List[str]] = None
+    n_splits: int = 5
 
 
 def build_host_workload(n_subjects: int = 1000, d: int = 116, n_splits: int = 5, early_fusion: bool = True,
@@ -71,7 +76,8 @@ def build_host_workload(n_subjects: int = 1000, d: int = 116, n_splits: int = 5,
         columns[EARLY] = [c for c in fused.columns if c != "IID"]
     folds = pipeline.prepare_folds(subjects, feats, columns, hc_label=1, n_splits=n_splits)
     return HostWorkload(folds=folds, names=list(feats), dims={k: len(v) for k, v in columns.items()},
-                        hidden=tuple(hidden), latent=latent)
+                        hidden=tuple(hidden), latent=latent, subjects=subjects, features=feats, columns=columns,
+                        n_splits=n_splits)
 
 
 def init_state_dict(d: int, hidden, latent: int, c_dim: int, seed: int):
@@ -98,10 +104,16 @@ class DeviceWorkload:
 
 
 def to_device(hw: HostWorkload, device, n_seeds: int = 24, seed0: int = 0, members: Sequence[int] = None,
-              pin: bool = False) -> DeviceWorkload:
+              pin: bool = False, gpu_prologue: bool = False) -> DeviceWorkload:
     """Upload datasets once, create one MemberSpec per (fold, modality, seed).  `members` optionally
-    restricts to a subset of the global member list (multi-GPU sharding)."""
+    restricts to a subset of the global member list (multi-GPU sharding).  gpu_prologue: the packed rows are built on
+    the device from the raw float64 tables (prologue.prepare_folds_gpu: RobustScaler, covariate bins, gather, packing)
+    instead of being packed from the host pipeline's arrays; the results are bit-identical."""
     from .ensemble import MemberSpec, pack_rows
+    gfolds = None
+    if gpu_prologue:
+        from . import prologue
+        gfolds = prologue.prepare_folds_gpu(hw.subjects, hw.features, hw.columns, hw.hc_label, device, n_splits=hw.n_splits)
     grid = [(f, name, s) for f in range(len(hw.folds)) for name in hw.names for s in range(n_seeds)]
     if members is not None:
         grid = [grid[i] for i in members]
@@ -116,8 +128,11 @@ def to_device(hw: HostWorkload, device, n_seeds: int = 24, seed0: int = 0, membe
             if pin:
                 x, c = x.pin_memory(), c.pin_memory()
                 wl.host_buffers[key] = (x, c)
-            wl.packed[key] = pack_rows(x.to(device, non_blocking=True), c.to(device, non_blocking=True))
-            tests[key] = pack_rows(torch.from_numpy(fd.test_x[name]).to(device), torch.from_numpy(fd.test_c).to(device))
+            if gfolds is not None:
+                wl.packed[key], tests[key] = gfolds[f].train[name], gfolds[f].test[name]
+            else:
+                wl.packed[key] = pack_rows(x.to(device, non_blocking=True), c.to(device, non_blocking=True))
+                tests[key] = pack_rows(torch.from_numpy(fd.test_x[name]).to(device), torch.from_numpy(fd.test_c).to(device))
             labels[key] = torch.from_numpy((fd.test_df["DIA"].to_numpy() != hw.hc_label).astype(np.uint8)).to(device)
             masks[key] = torch.from_numpy((fd.train_df["DIA"].to_numpy() == hw.hc_label).astype(np.uint8)).to(device)
         d = hw.dims[name]
