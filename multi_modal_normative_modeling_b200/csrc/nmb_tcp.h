@@ -18,6 +18,7 @@
 // an MN-major operand (MN index = c, K index = r: SBO = 32R, LBO = 128), so activations, output
 // gradients and weights are each stored once and used by forward, dgrad and wgrad.
 #pragma once
+#include <cstdlib>
 #include <map>
 #include <vector>
 
@@ -81,6 +82,12 @@ struct alignas(16) Step {
   unsigned char dep_grp;            // epilogue group whose counter `dep` refers to (0 / 1; 2 = both)
   unsigned char a_hold;             // the A tile's ring slot is kept for the next step ...
   unsigned char b_held;             // ... which reads it as its B operand (no tile of its own) and releases it
+  unsigned char b2;                 // two-part step: the FIRST ring tile (a_space / a_off / a_bytes) is B of part 1 (k_first
+                                    // K steps), the second tile B of part 2 (the rest); A stays resident in ACT[half]
+  unsigned char k_first;            // K steps of part 1
+  unsigned char p2_new;             // part 2 is a new N chunk (A restarts at a_start, accumulator columns tmem2, width n2,
+                                    // overwrite like part 1) instead of the continuation of part 1 along K
+  unsigned short n2, tmem2;
 };
 
 // Compact copy of the MMA-relevant fields of a Step.  The table travels in the KERNEL PARAMETERS (constant
@@ -92,8 +99,10 @@ struct MStep {
   unsigned short ksteps, n, tmem_col;
   short mma_dep, mma_dep_joint;
   unsigned char half, a_tile, a_mn, b_mn, first, commit, commit_buf, commit2;   // commit2_buf = accumulator of `half`
+  unsigned char k_first, p2_new;                      // two-part steps (a_tile bit 2), see Step
+  unsigned short n2, tmem2;
 };
-constexpr int kMaxParamSteps = 448;                   // 40 B each: 17.9 KB of the 32 KB parameter space
+constexpr int kMaxParamSteps = 400;                   // 44 B each: 17.6 KB of the 32 KB parameter space
 constexpr int kMaxParamArchs = 8;
 
 inline MStep to_mstep(const Step& s) {
@@ -105,9 +114,10 @@ inline MStep to_mstep(const Step& s) {
   m.b_kadv = (unsigned short)(s.b_kadv >> 4); m.b_lo = (unsigned short)(s.b_lo >> 4);
   m.ksteps = s.ksteps; m.n = s.n; m.tmem_col = s.tmem_col;
   m.mma_dep = (short)s.mma_dep; m.mma_dep_joint = (short)s.mma_dep_joint;
-  m.half = s.half; m.a_tile = (unsigned char)((s.a_bytes ? 1 : 0) | (s.a_hold ? 2 : 0)); m.a_mn = s.a_mn;
+  m.half = s.half; m.a_tile = (unsigned char)((s.b2 ? 4 : (s.a_bytes ? 1 : 0)) | (s.a_hold ? 2 : 0)); m.a_mn = s.a_mn;
   m.b_mn = (unsigned char)(s.b_mn | (s.b_held ? 2 : 0));      // a_tile bit 1: keep the A slot; b_mn bit 1: B = kept slot
   m.first = s.first; m.commit = s.commit; m.commit_buf = s.commit_buf; m.commit2 = s.commit2;
+  m.k_first = s.b2 ? (s.k_first ? s.k_first : (unsigned char)(s.ksteps / 2)) : 0; m.p2_new = s.p2_new; m.n2 = s.n2; m.tmem2 = s.tmem2;
   return m;
 }
 
@@ -261,6 +271,11 @@ inline Program build_program(const ArchDesc& a, bool fwd_only = false) {
   P.eligible = true;
   Layout& lay = P.lay;
   lay = Layout{};
+  // dev knob NMB_TCP_MERGE (bit mask, default 7): two-part MMA steps for 1 = the K-split weight gradients, 2 = the
+  // two-tile forward layers, 4 = the two-chunk data gradients; 0 = one MMA step per ring tile everywhere
+  const char* mk_env = getenv("NMB_TCP_MERGE");
+  const int merge_mask = mk_env ? atoi(mk_env) : 7;
+  const bool merge_k = (merge_mask & 1) != 0, merge_fwd = (merge_mask & 2) != 0, merge_dg = (merge_mask & 4) != 0;
 
   // ---- stash + planes layout ----
   long long so = 0, wo = 0;
@@ -386,6 +401,21 @@ inline Program build_program(const ArchDesc& a, bool fwd_only = false) {
   auto emit_fwd = [&](int h, const WRef& w, int a_space, long long a_base, int a_dep, int x_mod) {
     const int buf = accbuf(h);
     const int tg = tile_groups(w.R) > 8 && a_space != SP_NONE ? 8 : tile_groups(w.R);
+    if (merge_fwd && a_space == SP_NONE && w.cg > tg && w.cg <= 2 * tg) {
+      // both K tiles of the weight block in ONE MMA step (A resident in ACT[h], continuing along K)
+      Step s = base_step(h);
+      set_b(s, SP_W, w.wp_off, w.R, tg, w.cg - tg, false);                       // part 2: groups tg .. cg
+      s.b2 = 1; s.k_first = (unsigned char)(tg / 2);
+      s.a_space = SP_W; s.a_off = w.wp_off; s.a_bytes = (unsigned)(tg * 32 * w.R);   // part 1: groups 0 .. tg
+      set_a_kmajor(s, 0);
+      s.dep = a_dep;
+      s.ksteps = (unsigned short)(w.cg / 2); s.n = (unsigned short)w.R; s.tmem_col = (unsigned short)(kAcc0 + 128 * buf);
+      s.first = 1;
+      need(s, acc_free[buf]); need(s, act_ready[h]);
+      s.commit = 1; s.commit_buf = (unsigned char)buf;
+      P.steps.push_back(s);
+      return;
+    }
     for (int g0 = 0, j = 0; g0 < w.cg; g0 += tg, ++j) {
       const int ng = w.cg - g0 < tg ? w.cg - g0 : tg;
       Step s = base_step(h);
@@ -409,6 +439,22 @@ inline Program build_program(const ArchDesc& a, bool fwd_only = false) {
     const int buf = accbuf(h);
     const int tg = tile_groups(w.R);
     const int cg = (round16(n_need) / 8) < w.cg ? round16(n_need) / 8 : w.cg;
+    if (merge_dg && cg > tg && cg <= 2 * tg && 2 * (w.R / 16) < 256) {
+      // both N chunks in ONE MMA step: part 1 -> columns 0 .. 8 tg, part 2 (new N chunk, A restarts) -> the rest
+      Step s = base_step(h);
+      set_b(s, SP_W, w.wp_off, w.R, tg, cg - tg, true);                           // part 2
+      s.b2 = 1; s.k_first = (unsigned char)(w.R / 16); s.p2_new = 1;
+      s.a_space = SP_W; s.a_off = w.wp_off; s.a_bytes = (unsigned)(tg * 32 * w.R);   // part 1: groups 0 .. tg
+      set_a_kmajor(s, 0);
+      s.ksteps = (unsigned short)(2 * (w.R / 16)); s.n = (unsigned short)(tg * 8);
+      s.tmem_col = (unsigned short)(kAcc0 + 128 * buf);
+      s.n2 = (unsigned short)((cg - tg) * 8); s.tmem2 = (unsigned short)(kAcc0 + 128 * buf + tg * 8);
+      s.first = 1;
+      need(s, act_ready[h]); need(s, acc_free[buf]);
+      s.commit = commit ? 1 : 0; s.commit_buf = (unsigned char)buf;
+      P.steps.push_back(s);
+      return;
+    }
     for (int g0 = 0, j = 0; g0 < cg; g0 += tg, ++j) {
       const int ng = cg - g0 < tg ? cg - g0 : tg;
       Step s = base_step(h);
@@ -428,6 +474,25 @@ inline Program build_program(const ArchDesc& a, bool fwd_only = false) {
   auto emit_wgrad_part = [&](int h, int wb, int b_space, long long b_base, int g_first, int g_count, int x_mod,
                              bool acc_commit, int blk64_cg) {
     const int b_dep = b_space == SP_STASH ? ready[b_base] : 0;
+    if (blk64_cg && merge_k) {
+      // both 64-row sub-blocks of B in ONE MMA step (two ring tiles, 8 K steps): the backward pass is bound by the
+      // per-step cost of the MMA issuer, and this saves one step per (layer, half)
+      Step s = base_step(h);
+      s.b2 = 1;
+      s.a_space = (unsigned char)b_space; s.a_off = b_base; s.a_bytes = (unsigned)blk64_cg * 2048;
+      s.b_space = (unsigned char)b_space; s.b_off = b_base + (long long)blk64_cg * 2048; s.b_bytes = (unsigned)blk64_cg * 2048;
+      s.b_mn = 1; s.b_lo = 1024; s.b_sbo = 2048; s.b_lbo = 128; s.b_kadv = 256;
+      set_a_mnmajor(s); s.a_start = 0;
+      s.dep = b_dep;
+      s.ksteps = 8; s.n = (unsigned short)(g_count * 8); s.tmem_col = (unsigned short)(kWacc0 + 128 * wb);
+      s.first = h == 0;
+      need(s, act_ready[h]); need(s, acc_free[2 + wb]);
+      s.commit = h == 1 ? 1 : 2;
+      s.commit_buf = (unsigned char)(2 + wb);
+      if (acc_commit) { s.commit2 = 1; s.commit2_buf = (unsigned char)accbuf(h); }
+      P.steps.push_back(s);
+      return;
+    }
     if (blk64_cg) {
       // B block stored as two 64-row sub-blocks (all column groups contiguous, <= 32 KB each): the GEMM is split over K
       // (batch rows) instead of N, so that the MN-major A operand (ACT[h]^T) is read once per pass, not once per N chunk
@@ -467,6 +532,7 @@ inline Program build_program(const ArchDesc& a, bool fwd_only = false) {
   };
 
   int wacc_next = 0;
+  (void)merge_k;
   const bool fused_latent = M == 1 && Z <= 16;     // head -> latent and d/dz -> latent backward stay in registers
   const int nl = a.non_linear;
   (void)nl;

@@ -227,8 +227,13 @@ __device__ void mma_role(const LaunchP& L, int ai, const RowSet& rs, unsigned ch
       if (st.mma_dep_joint > 0) wait_epi(&ctl->epi_done[2], sv.base + (uint32_t)st.mma_dep_joint);
       else if (st.mma_dep_joint < 0) wait_all(ctl->epi_done, sv.base + (uint32_t)(-st.mma_dep_joint));
       if (tr && (threadIdx.x & 31) == 0) g_trace[tb + 3 * (k - k0)] = gtime();
-      uint32_t a_base, slot_a = kSlots;
-      if (st.a_tile & 1) {
+      uint32_t a_base, slot_a = kSlots, slot_b0 = kSlots;
+      if (st.a_tile & 4) {         // first K half of B (the step's first ring tile); A stays resident in ACT[half]
+        slot_b0 = seq % kSlots;
+        tc::mbar_wait(&ctl->full[slot_b0], (seq / kSlots) & 1u);
+        ++seq;
+        a_base = act0 + st.half * kActBytes + st.a_start;
+      } else if (st.a_tile & 1) {
         slot_a = seq % kSlots;
         tc::mbar_wait(&ctl->full[slot_a], (seq / kSlots) & 1u);
         a_base = ring + slot_a * kSlotBytes;
@@ -256,6 +261,31 @@ __device__ void mma_role(const LaunchP& L, int ai, const RowSet& rs, unsigned ch
       if (elect_one()) {
         if (tr) g_trace[tb + 3 * (k - k0) + 1] = gtime();
         uint32_t acc = st.first ? 0u : 1u;
+        if (slot_b0 != kSlots) {       // two-part step: k_first K steps on the first B tile, the rest on the second
+          uint64_t db0 = hi_b | (((ring + slot_b0 * kSlotBytes) & 0x3FFFFu) >> 4);
+          const int k1 = st.k_first;
+          for (int ks = 0; ks < k1; ++ks) {
+            tc::mma_bf16(d, da, db0, idesc, acc);
+            tc::mma_bf16(d, da + st.a_lo, db0, idesc, 1u);
+            tc::mma_bf16(d, da, db0 + st.b_lo, idesc, 1u);
+            acc = 1u;
+            da += st.a_kadv; db0 += st.b_kadv;
+          }
+          tc::mma_commit(&ctl->empty[slot_b0]);
+          uint32_t d2 = d, idesc2 = idesc;
+          if (st.p2_new) {             // a new N chunk: A from the start again, its own accumulator columns and width
+            da = hi_a | ((a_base & 0x3FFFFu) >> 4);
+            d2 = tmem + st.tmem2; idesc2 = tc::make_idesc(st.n2, st.a_mn, st.b_mn & 1);
+            acc = st.first ? 0u : 1u;
+          }
+          for (int ks = k1; ks < st.ksteps; ++ks) {
+            tc::mma_bf16(d2, da, db, idesc2, acc);
+            tc::mma_bf16(d2, da + st.a_lo, db, idesc2, 1u);
+            tc::mma_bf16(d2, da, db + st.b_lo, idesc2, 1u);
+            acc = 1u;
+            da += st.a_kadv; db += st.b_kadv;
+          }
+        } else
         for (int ks = 0; ks < st.ksteps; ++ks) {
           tc::mma_bf16(d, da, db, idesc, acc);
           tc::mma_bf16(d, da + st.a_lo, db, idesc, 1u);
@@ -296,9 +326,11 @@ struct EpiCtx {
   const ReconTc* rt;        // rows and outputs of a reconstruction launch
   // row source of the current work item: the member's training rows, or the rows of a reconstruction launch (looked up
   // on demand: in the training instantiation `recon` is the constant 0 and nothing extra stays live in registers)
-  __device__ __forceinline__ const float* xc_rows(int m) const { return recon ? rt->xc[m] : mb->xc[m]; }
-  __device__ __forceinline__ const unsigned char* cplanes0() const { return recon ? rt->cplanes[0] : mt->cplanes[0]; }
-  __device__ __forceinline__ int n_half() const { return recon ? 2 : mt->n_half; }
+  template <bool R> __device__ __forceinline__ const float* xc_rows(int m) const { return R ? rt->xc[m] : mb->xc[m]; }
+  template <bool R> __device__ __forceinline__ const unsigned char* cplanes0() const { return R ? rt->cplanes[0] : mt->cplanes[0]; }
+  template <bool R> __device__ __forceinline__ int n_half() const { return R ? 2 : mt->n_half; }
+  // reconstruction mode as a compile-time 0 in the training instantiation
+  template <bool R> __device__ __forceinline__ int rmode() const { return R ? recon : 0; }
 #ifdef NMB_TCP_FINE_TRACE
   unsigned long long* tr_ptr;
 #endif
@@ -317,8 +349,27 @@ __device__ __forceinline__ void put_planes(unsigned char* blk, int g, int row, c
 // Adam master state is a pure stream (read once, written once per step, re-read a whole step later): keep it from
 // displacing the weight planes and the backward stash in L2.
 // (.cg: the previous work item of the member may have run on another SM -- never trust this SM's L1 for it)
+#ifdef NMB_ADAM_EVICT_FIRST
+// variant: explicit L2 evict-first policy on the Adam stream (dev A/B build)
+__device__ __forceinline__ uint64_t evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ float4 ld_stream4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(evict_first_policy()) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_stream4(float* p, const float4& v) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;"
+               ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(evict_first_policy()) : "memory");
+}
+#else
 __device__ __forceinline__ float4 ld_stream4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void st_stream4(float* p, const float4& v) { __stcs(reinterpret_cast<float4*>(p), v); }
+#endif
 
 // torch.optim.Adam element update; sqrt / reciprocal on the SFU (2 ulp, far inside the parity budget)
 __device__ __forceinline__ float adam_update(const EpiCtx& c, float& m1, float& v1, float p0, float g) {
@@ -402,6 +453,7 @@ __device__ void build_weight_planes(const ProgramDev& pg, const MemberDev& mb, c
   }
 }
 
+template <bool RECON>
 __device__ __forceinline__ void epi_hidden(EpiCtx& c, const Epi& e) {
   const int h = e.half;
   const int rows = c.rows_of(h);
@@ -410,8 +462,8 @@ __device__ __forceinline__ void epi_hidden(EpiCtx& c, const Epi& e) {
   // stash block: one 128-row block (group chunk 4 KB = hi 2 KB + lo 2 KB) or, src_cg > 0, two 64-row sub-blocks of
   // src_cg groups (group chunk 2 KB = hi 1 KB + lo 1 KB): the weight gradient that reads it is split over K
   const int b64 = e.src_cg;
-  const bool keep = e.stash_off >= 0;             // forward-only program: nothing is stashed for a backward pass
-  unsigned char* st = c.stash + (keep ? e.stash_off : 0) + (b64 ? (long long)(c.row >> 6) * b64 * 2048 + (c.row & 63) * 16 : (long long)c.row * 16);
+  constexpr bool keep = !RECON;                   // forward-only program: nothing is stashed for a backward pass
+  unsigned char* st = c.stash + (keep ? e.stash_off : 0LL) + (b64 ? (long long)(c.row >> 6) * b64 * 2048 + (c.row & 63) * 16 : (long long)c.row * 16);
   const int st_g = b64 ? 2048 : 4096, st_lo = b64 ? 1024 : 2048;
   const float slope = c.a->non_linear ? kSlope : 1.f;        // leaky-relu(x) = max(x, slope * x)
   const int n_cols = e.n_cols, n_mma = e.n_mma, n_valid = e.n_valid, tcol = e.tmem_col;
@@ -470,7 +522,9 @@ __device__ __forceinline__ void epi_head(EpiCtx& c, const Epi& e) {
 }
 
 // fusion + reparameterisation + KL for half h; builds decoder inputs [z | c | 1] (cVAE.py:1130-1164, 199)
+template <bool RECON>
 __device__ void epi_latent(EpiCtx& c, const Epi& e, const float* eps_src) {
+  const int rmode = c.template rmode<RECON>();
   const ArchDesc& a = *c.a;
   const Layout& lay = c.pg->lay;
   const int h = e.half, Z = a.Z, M = a.M, rows = c.rows_of(h);
@@ -481,12 +535,12 @@ __device__ void epi_latent(EpiCtx& c, const Epi& e, const float* eps_src) {
   const int n = rows * Z;
   const int g_base = (128 * h * Z) / 4;
   // reconstruction: Philox stream 1, counter = tile index (the draws of nmb_ensemble_reconstruct's generic engine)
-  float* out_mu = (c.recon && c.rt->mu) ? c.rt->mu + (long long)c.row0 * Z : nullptr;
-  float* out_lv = (c.recon && c.rt->logvar) ? c.rt->logvar + (long long)c.row0 * Z : nullptr;
+  float* out_mu = (rmode && c.rt->mu) ? c.rt->mu + (long long)c.row0 * Z : nullptr;
+  float* out_lv = (rmode && c.rt->logvar) ? c.rt->logvar + (long long)c.row0 * Z : nullptr;
   for (int g = c.tid; g * 4 < n; g += c.nthr) {
     float nrm[4] = {0.f, 0.f, 0.f, 0.f};
-    if (!eps_src && c.recon != 1)
-      philox_normal4(c.mb->seed, (unsigned long long)c.step, c.recon ? 1u : 0u, (uint32_t)(g_base + g), nrm);
+    if (!eps_src && rmode != 1)
+      philox_normal4(c.mb->seed, (unsigned long long)c.step, rmode ? 1u : 0u, (uint32_t)(g_base + g), nrm);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int el = g * 4 + j;
@@ -505,7 +559,7 @@ __device__ void epi_latent(EpiCtx& c, const Epi& e, const float* eps_src) {
         }
         f = fuse_forward(mu, lv, M, a.combine, w);
       }
-      const float eps = c.recon == 1 ? 0.f : (eps_src ? eps_src[gb * Z + z] : nrm[j]);
+      const float eps = rmode == 1 ? 0.f : (eps_src ? eps_src[gb * Z + z] : nrm[j]);
       S[a.s_mub + gb * Z + z] = f.mu; S[a.s_lvb + gb * Z + z] = f.lv; S[a.s_eps + gb * Z + z] = eps;
       if (out_mu) out_mu[gb * Z + z] = f.mu;
       if (out_lv) out_lv[gb * Z + z] = f.lv;
@@ -518,7 +572,7 @@ __device__ void epi_latent(EpiCtx& c, const Epi& e, const float* eps_src) {
   for (int m = 0; m < M; ++m) {
     const ModDesc& q = a.mod[m];
     unsigned char* st = c.stash + lay.g0[m][h];
-    const float* xc = c.xc_rows(m) + (long long)(c.row0 + 128 * h) * q.ldx + q.D;
+    const float* xc = c.template xc_rows<RECON>(m) + (long long)(c.row0 + 128 * h) * q.ldx + q.D;
     const int ldx = q.ldx, C = a.C;
     for (int u = c.tid; u < 128 * cg; u += c.nthr) {
       const int r = u & 127, g = u >> 7;
@@ -1013,30 +1067,34 @@ __device__ __forceinline__ float bf16pair_hi(uint32_t w) { return __uint_as_floa
 
 // Pre-phase (before the accumulator barrier is waited on, so it overlaps the head GEMM): the Philox draws of this
 // half, spread over the whole group, written to the eps array the backward pass reads anyway.
+template <bool RECON>
 __device__ void epi_head_latent_pre(EpiCtx& c, const Epi& e, const float* eps_src) {
+  const int rmode = c.template rmode<RECON>();
   {   // this row's decoder-input template planes start their way to L1 while the head GEMM finishes (no registers held)
     const Layout& lay = c.pg->lay;
-    const unsigned char* tp = c.cplanes0() + (long long)(c.pos * c.n_half() + e.half) * lay.c_cg * 4096 + c.row * 16;
+    const unsigned char* tp = c.template cplanes0<RECON>() + (long long)(c.pos * c.template n_half<RECON>() + e.half) * lay.c_cg * 4096 + c.row * 16;
     for (int g = 0; g < lay.c_cg; ++g) {
       asm volatile("prefetch.global.L1 [%0];" ::"l"(tp + (long long)g * 4096));
       asm volatile("prefetch.global.L1 [%0];" ::"l"(tp + (long long)g * 4096 + 2048));
     }
   }
-  if (eps_src || c.recon == 1) return;
+  if (eps_src || rmode == 1) return;
   const ArchDesc& a = *c.a;
   const int h = e.half, Z = a.Z, n = c.rows_of(h) * Z;
   float* eps = c.scratch + a.s_eps + 128 * h * Z;
   const int g_base = (128 * h * Z) / 4;
   for (int g = c.tid; g * 4 < n; g += c.nthr) {
     float nrm[4];
-    philox_normal4(c.mb->seed, (unsigned long long)c.step, c.recon ? 1u : 0u, (uint32_t)(g_base + g), nrm);
+    philox_normal4(c.mb->seed, (unsigned long long)c.step, rmode ? 1u : 0u, (uint32_t)(g_base + g), nrm);
 #pragma unroll
     for (int j = 0; j < 4; ++j) if (g * 4 + j < n) eps[g * 4 + j] = nrm[j];
   }
   bar_n(c.bar_id, c.bar_nthr);
 }
 
+template <bool RECON>
 __device__ void epi_head_latent(EpiCtx& c, const Epi& e, const float* eps_src) {
+  const int rmode = c.template rmode<RECON>();
   
   const ArchDesc& a = *c.a;
   const Layout& lay = c.pg->lay;
@@ -1050,14 +1108,14 @@ __device__ void epi_head_latent(EpiCtx& c, const Epi& e, const float* eps_src) {
   // all draws of the row first (a store to the scratch array could alias a later load: the compiler keeps program
   // order, which exposed one L2 round trip per latent element); zz[] holds eps until the arithmetic
 #pragma unroll
-  for (int z = 0; z < 16; ++z) zz[z] = (z < Z && vr && c.recon != 1) ? epsrow[z] : 0.f;    // mean decode: eps = 0
+  for (int z = 0; z < 16; ++z) zz[z] = (z < Z && vr && rmode != 1) ? epsrow[z] : 0.f;    // mean decode: eps = 0
   TR3();
   tc::tmem_ld16(taddr(c, e.tmem_col), mu);            // columns 0 .. 15: mu[0 .. Z)
   tc::tmem_ld16(taddr(c, e.tmem_col + Z), lv);        // columns Z .. Z + 15: logvar[0 .. Z)
   TR3();
   float kl = 0.f;
   const long long s_mub = a.s_mub, s_lvb = a.s_lvb, s_eps = a.s_eps;
-  if (c.recon) {            // pred_latent outputs of a reconstruction launch (rows of this tile)
+  if (rmode) {            // pred_latent outputs of a reconstruction launch (rows of this tile)
     float* om = c.rt->mu ? c.rt->mu + ((long long)c.row0 * Z + e0) : nullptr;
     float* ol = c.rt->logvar ? c.rt->logvar + ((long long)c.row0 * Z + e0) : nullptr;
 #pragma unroll
@@ -1081,7 +1139,7 @@ __device__ void epi_head_latent(EpiCtx& c, const Epi& e, const float* eps_src) {
   c.kl_acc += kl;
   TR3();
   // [z | c | 1]: the covariate part comes from the dataset's template block (coalesced 16-byte reads)
-  const unsigned char* tp = c.cplanes0() + (long long)(c.pos * c.n_half() + h) * lay.c_cg * 4096 + c.row * 16;
+  const unsigned char* tp = c.template cplanes0<RECON>() + (long long)(c.pos * c.template n_half<RECON>() + h) * lay.c_cg * 4096 + c.row * 16;
   unsigned char* act = c.smem + h * kActBytes + c.row * 16;
   unsigned char* st = c.stash + lay.g0[0][h] + c.row * 16;
   const int zg = (Z + 7) >> 3;                          // groups that contain z columns (<= 2)
@@ -1185,10 +1243,12 @@ __device__ __forceinline__ void prefetch_adam_state(const EpiCtx& c, const Epi& 
   }
 }
 
+template <bool RECON>
 __device__ void epi_step_end(EpiCtx& c, float* loss_out) {
+  const int rmode = c.template rmode<RECON>();
   const ArchDesc& a = *c.a;
   const int M = a.M;
-  if (c.recon) { c.kl_acc = 0.f; c.ll_acc = 0.f; return; }
+  if (rmode) { c.kl_acc = 0.f; c.ll_acc = 0.f; return; }
   // both loss sums in one pass over the barrier pair (red[] holds 12 + 12 partials)
   float kl, ll;
   {
@@ -1231,7 +1291,9 @@ __device__ __forceinline__ void set_workers(EpiCtx& c, bool all) {
 // data gradients: two independent dependency chains whose latencies overlap) and the optimiser group, which
 // consumes the weight-gradient accumulators (Adam + new weight planes) off both chains.  Every group walks the
 // item list and executes its own items; EK_STEP_END is the only rendezvous.
+template <bool RECON>
 __device__ void epilogue_role(const LaunchP& L, int ai, int mi, EpiCtx& c, const RowSet& rs, uint32_t& acc_par) {
+  const int rmode = c.template rmode<RECON>();
   const TrainLaunch& t = L.t;
   const ProgramDev& pg = *c.pg;
   MemberDev& mb = *c.mb;
@@ -1240,7 +1302,7 @@ __device__ void epilogue_role(const LaunchP& L, int ai, int mi, EpiCtx& c, const
   for (int m = 0; m < NMB_MAX_MOD; ++m) dw_acc[m] = 0.f;
   c.dw_acc = dw_acc;
   set_workers(c, true);
-  if (!c.recon) build_iv_table(c);   // weight planes and the lane-major master state were prepared by tcp_prepare_kernel
+  if (!rmode) build_iv_table(c);   // weight planes and the lane-major master state were prepared by tcp_prepare_kernel
   __threadfence();
   fence_async_all();
   bar_n(4, kEpiWarps * 32);
@@ -1262,8 +1324,8 @@ __device__ void epilogue_role(const LaunchP& L, int ai, int mi, EpiCtx& c, const
     c.step = s;
     const float* eps = nullptr;
     float* lo = nullptr;
-    if (c.recon) {           // s = tile index; injected draws [n_rows][Z] of the caller, rows of this tile
-      if (c.recon == 2 && c.rt->eps) eps = c.rt->eps + (long long)sv.row0 * c.a->Z;
+    if (rmode) {           // s = tile index; injected draws [n_rows][Z] of the caller, rows of this tile
+      if (rmode == 2 && c.rt->eps) eps = c.rt->eps + (long long)sv.row0 * c.a->Z;
       c.step_size = 0.f; c.inv_bc2 = 1.f;
     } else {
       const double tt = (double)(s + 1);
@@ -1301,7 +1363,7 @@ __device__ void epilogue_role(const LaunchP& L, int ai, int mi, EpiCtx& c, const
         if (c.rows_h1 > 0) wait_epi(&c.ctl->epi_done[1], sv.base + (uint32_t)e.n_cols);
       }
       if (all) bar_n(4, kEpiWarps * 32);           // every group has finished everything before this item
-      if (e.kind == EK_HEAD_LATENT) epi_head_latent_pre(c, e, eps);
+      if (e.kind == EK_HEAD_LATENT) epi_head_latent_pre<RECON>(c, e, eps);
       // every stash block of this half's forward pass has been written by now and this item writes none: the
       // generic -> async proxy publication (MEMBAR.GPU + proxy fence) runs while the group waits for its accumulator
       if (e.kind == EK_RECON && e.src_cg) { __threadfence(); fence_async_all(); }
@@ -1331,9 +1393,9 @@ __device__ void epilogue_role(const LaunchP& L, int ai, int mi, EpiCtx& c, const
       // (stash blocks, weight planes) only at EK_FENCE / EK_STEP_END, so the stores drain in the background
       int fence = 0;              // 1 = shared memory, 2 = everything
       switch (e.kind) {
-        case EK_HIDDEN: epi_hidden(c, e); fence = 1; break;
+        case EK_HIDDEN: epi_hidden<RECON>(c, e); fence = 1; break;
         case EK_HEAD: epi_head(c, e); break;
-        case EK_LATENT: epi_latent(c, e, eps); fence = 1; break;
+        case EK_LATENT: epi_latent<RECON>(c, e, eps); fence = 1; break;
         case EK_COPY: epi_copy(c, e); fence = 1; break;
         case EK_RECON: epi_recon(c, e); fence = e.to_act ? 1 : 0; break;
         case EK_DGRAD: epi_dgrad(c, e); fence = 1; break;
@@ -1343,10 +1405,10 @@ __device__ void epilogue_role(const LaunchP& L, int ai, int mi, EpiCtx& c, const
         case EK_WGRAD_T: epi_wgrad_t(c, e); break;
         case EK_FENCE: fence = e.src_cg ? 0 : 2; break;      // src_cg: already published before the last forward item
         case EK_LAM: epi_lam(c, e); break;
-        case EK_HEAD_LATENT: epi_head_latent(c, e, eps); fence = 1; break;
+        case EK_HEAD_LATENT: epi_head_latent<RECON>(c, e, eps); fence = 1; break;
         case EK_DZ_LATENT_BWD: epi_dz_latent_bwd(c, e); fence = 1; break;
-        case EK_XHAT: epi_xhat(c, e); break;
-        default: epi_step_end(c, lo); fence = c.recon ? 0 : 2; break;
+        case EK_XHAT: if (RECON) epi_xhat(c, e); break;
+        default: epi_step_end<RECON>(c, lo); fence = rmode ? 0 : 2; break;
       }
       if (e.buf >= 0) tc::fence_before();
       if (fence == 1) fence_async_smem();
@@ -1440,7 +1502,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) train_tcp_kernel(const __grid_co
         c.tmem = tmem; c.warp = warp; c.lane = lane; c.row = ((warp & 3) << 5) + lane;
         c.grp = warp / kGroupWarps; c.flags = t.flags;
         c.b1 = mb.beta1; c.b2 = mb.beta2; c.aeps = mb.adam_eps;
-        epilogue_role(L, mb.arch_idx, mi, c, rs, acc_par);
+        epilogue_role<RECON>(L, mb.arch_idx, mi, c, rs, acc_par);
       } else if (warp == kEpiWarps) {
         const int ai = __shfl_sync(0xffffffffu, mb.arch_idx, 0);
         mma_role(L, ai, rs, smem, ctl, tmem, seq, pg.n_epis);
