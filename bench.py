@@ -585,8 +585,16 @@ def run_b200(args):
         clocks = sampler.summary()
         traffic, traffic_note = None, None
         try:
+            import hashlib
             tj = json.load(open(os.path.join(ROOT, "profiles", "train_kernel_traffic.json")))
-            traffic, traffic_note = tj.get("dram_bytes_per_launch"), tj.get("note")
+            csrc = os.path.join(ROOT, "multi_modal_normative_modeling_b200", "csrc")
+            have = hashlib.sha256(b"".join(open(os.path.join(csrc, f), "rb").read()
+                                           for f in ("nmb_train_tcp.cu", "nmb_tcp.h"))).hexdigest()
+            if tj.get("kernel_source_sha256") == have:
+                traffic = tj.get("dram_bytes_per_launch")
+                traffic_note = "ncu --set full capture of this kernel source (" + str(tj.get("capture")) + ")"
+            else:       # a capture of another kernel revision says nothing about this one
+                traffic_note = "profiles/train_kernel_traffic.json was captured for a different kernel source: not reported"
         except Exception:
             pass
         engine = tr.engine()

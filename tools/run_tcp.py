@@ -2,7 +2,8 @@
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from multi_modal_normative_modeling_b200 import EnsembleTrainer, workloads
+from multi_modal_normative_modeling_b200 import EnsembleTrainer, workloads, _lib
+if os.environ.get("NMB_LIB"): _lib.LIB_PATH = os.path.abspath(os.environ["NMB_LIB"])   # A/B against another build
 
 seeds = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 8
