@@ -143,8 +143,13 @@ enum {
   NMB_TRAIN_KEEP_ACTS = 4,   /* keep x_recon in scratch instead of overwriting it with its gradient */
   NMB_TRAIN_FP32 = 8,        /* run every dense stage on the FP32 FFMA engine (bit-stable trajectories) instead of
                                 the default tcgen05 engine (error-compensated BF16x3 products, FP32 accumulate) */
-  NMB_TRAIN_TC_SIMPLE = 16   /* tcgen05 engine without the operand pipeline (the generic engine that also serves
+  NMB_TRAIN_TC_SIMPLE = 16,  /* tcgen05 engine without the operand pipeline (the generic engine that also serves
                                 architectures the pipelined kernel does not cover, e.g. hidden width > 127) */
+  NMB_TRAIN_RESIDENT = 32    /* pipelined engine: leave parameters and Adam moments in the kernel's lane-major master
+                                layout after the call (no conversion back, none in at the next call).  NmbMember.params /
+                                adam_m / adam_v are then STALE until nmb_ensemble_sync (logvar_out and the gPoE alphas
+                                are always current); every libnmb call that reads them syncs by itself.  For runs that
+                                call train repeatedly (per-epoch logging): saves two state conversions per call. */
 };
 /* The fused hot loop: for every member, n_steps minibatch steps of
  *   forward_multimodal -> loss_function_multimodal -> zero_grad -> backward -> optimizer1.step()
@@ -163,6 +168,12 @@ int nmb_ensemble_train(NmbEnsemble* ens, int64_t n_steps, const float* eps_overr
  *   loss_out : NULL or [n_members][n_epochs * max_i steps_per_epoch_i][3]; member i fills its first
  *              n_epochs * steps_per_epoch_i rows, the rest is left untouched. */
 int nmb_ensemble_train_epochs(NmbEnsemble* ens, int64_t n_epochs, float* loss_out, uint32_t flags, void* stream);
+
+/* After NMB_TRAIN_RESIDENT calls: bring NmbMember.params / adam_m / adam_v up to date (no-op otherwise). */
+int nmb_ensemble_sync(NmbEnsemble* ens, void* stream);
+/* The caller is about to WRITE NmbMember.params / adam_m / adam_v (e.g. load new weights): syncs, then drops the resident
+ * copy so that the next train call reads the caller's buffers again. */
+int nmb_ensemble_invalidate(NmbEnsemble* ens, void* stream);
 
 /* Stand-alone Adam update over a packed buffer: optimizer1.step() (torch.optim.Adam defaults,
  * cVAE.py:1111-1116) for the per-step nn.Module API, where forward/backward and step() are

@@ -11,7 +11,7 @@ NMB_MAX_HIDDEN = 4
 COMBINE = {"poe": 0, "gpoe": 1, "moe": 2, "mopoe": 3}
 LOSS = {"gauss_ll": 0, "neg_mse": 1}
 SLOT_ENC, SLOT_ENC_MEAN, SLOT_ENC_LOGVAR, SLOT_DEC, SLOT_DEC_MEAN, SLOT_LOGVAR_OUT, SLOT_ALPHA = range(7)
-TRAIN_NO_ADAM, TRAIN_WRITE_GRADS, TRAIN_KEEP_ACTS, TRAIN_FP32, TRAIN_TC_SIMPLE = 1, 2, 4, 8, 16
+TRAIN_NO_ADAM, TRAIN_WRITE_GRADS, TRAIN_KEEP_ACTS, TRAIN_FP32, TRAIN_TC_SIMPLE, TRAIN_RESIDENT = 1, 2, 4, 8, 16, 32
 RECON_MEAN, RECON_SAMPLE, RECON_GIVEN_Z, RECON_FP32, RECON_TC_SIMPLE = 0, 1, 2, 16, 32
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libnmb.so")
@@ -53,6 +53,8 @@ _PROTOS = {
     "nmb_ensemble_engine": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_int32)]),
     "nmb_ensemble_steps_done": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]),
     "nmb_ensemble_train": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
+    "nmb_ensemble_sync": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "nmb_ensemble_invalidate": (C.c_int, [C.c_void_p, C.c_void_p]),
     "nmb_ensemble_train_epochs": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_uint32, C.c_void_p]),
     "nmb_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_float,
                                 C.c_float, C.c_float, C.c_float, C.c_void_p]),

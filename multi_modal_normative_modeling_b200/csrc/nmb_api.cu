@@ -153,6 +153,9 @@ struct NmbEnsemble {
   bool fwd_ok = false;
   unsigned char* recon_buf = nullptr;        // grow-only planes of the rows being reconstructed
   size_t recon_buf_bytes = 0;
+  // NMB_TRAIN_RESIDENT: the lane-major master state (and the weight planes) stay authoritative between calls
+  bool master_valid = false;                 // master holds the current p, m, v
+  bool caller_stale = false;                 // ... and the caller's row-major buffers have not been refreshed from it
   std::vector<long long> steps_host;         // host mirror of MemberDev.steps_done (every step goes through this API)
   std::vector<long long> n_lr_steps;         // length of each member's lr_steps schedule (0 = none)
 };
@@ -474,6 +477,15 @@ int nmb_ensemble_steps_done(NmbEnsemble* e, int64_t* steps, void* stream) {
   return 0;
 }
 
+// Caller-layout buffers up to date (before anything reads them: another engine, reconstruct, the caller itself).
+static int ensure_synced(NmbEnsemble* e, cudaStream_t st) {
+  if (e->caller_stale) {
+    CU(launch_tcp_scatter(e->members_dev, e->n_members, e->progs_dev, e->mtc_dev, e->master, e->master_floats, e->max_mlayers, st));
+    e->caller_stale = false;
+  }
+  return 0;
+}
+
 static int train_common(NmbEnsemble* e, int64_t n, int n_is_epochs, const float* eps_override, float* loss_out,
                         uint32_t flags, void* stream) {
   if (!e) return fail("null ensemble");
@@ -505,14 +517,35 @@ static int train_common(NmbEnsemble* e, int64_t n, int n_is_epochs, const float*
   if (e->tcp_ok && !(flags & (NMB_TRAIN_FP32 | NMB_TRAIN_TC_SIMPLE))) {
     // dataset rows may have been re-packed since the last call: refresh their planes (cheap, streaming)
     CU(launch_xprep(e->xprep_dev, e->n_xprep, e->xprep_max_blocks, (cudaStream_t)stream));
+    const bool adam = !(flags & NMB_TRAIN_NO_ADAM);
+    const bool resident = adam && (flags & NMB_TRAIN_RESIDENT);
+    if (!adam) { if (int rc = ensure_synced(e, (cudaStream_t)stream)) return rc; e->master_valid = false; }   // planes from the caller's params
+    const bool gather_in = !adam || !e->master_valid;
     CU(launch_train_tcp(t, e->progs_dev, e->mtc_dev, e->stash, e->stash_bytes, e->master, e->master_floats,
                         e->msteps.data(), e->ms_off.data(), e->ms_cnt.data(), (int)e->ms_off.size(),
                         e->epis_p.data(), e->ep_off.data(), e->ep_cnt.data(), e->max_mlayers, e->n_sm,
-                        (cudaStream_t)stream));
+                        gather_in, !resident, (cudaStream_t)stream));
+    if (adam) { e->master_valid = resident; e->caller_stale = resident; }
   } else {
+    if (int rc = ensure_synced(e, (cudaStream_t)stream)) return rc;
+    e->master_valid = false;
     CU(launch_train(t, (cudaStream_t)stream));
   }
   for (int i = 0; i < e->n_members; ++i) e->steps_host[i] += member_steps(t, e->members_host[i]);
+  return 0;
+}
+
+int nmb_ensemble_sync(NmbEnsemble* e, void* stream) {
+  if (!e) return fail("null ensemble");
+  CU(cudaSetDevice(e->device));
+  return ensure_synced(e, (cudaStream_t)stream);
+}
+
+int nmb_ensemble_invalidate(NmbEnsemble* e, void* stream) {
+  if (!e) return fail("null ensemble");
+  CU(cudaSetDevice(e->device));
+  if (int rc = ensure_synced(e, (cudaStream_t)stream)) return rc;      // nothing the caller has not seen may be dropped
+  e->master_valid = false;
   return 0;
 }
 
@@ -566,6 +599,7 @@ int nmb_ensemble_reconstruct(NmbEnsemble* e, const float* const* xc, const int32
   }
   cudaStream_t st = (cudaStream_t)stream;
   CU(cudaSetDevice(e->device));
+  if (int rc = ensure_synced(e, st)) return rc;       // the planes / generic engines read the caller-layout parameters
   std::vector<ReconItem> items;
   const int n = e->n_members;
   for (int i = 0; i < n; ++i) {

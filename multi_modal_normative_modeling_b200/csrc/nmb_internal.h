@@ -98,6 +98,8 @@ cudaError_t launch_train_tcp(const TrainLaunch& t, const tcp::ProgramDev* progs,
                              unsigned char* stash, long long stash_bytes, float* master, long long master_floats,
                              const tcp::MStep* msteps, const int* ms_off, const int* ms_cnt, int n_archs,
                              const tcp::EpiP* epis_p, const int* ep_off, const int* ep_cnt,
-                             int max_mlayers, int n_sm, cudaStream_t st);
+                             int max_mlayers, int n_sm, bool gather_in, bool scatter_out, cudaStream_t st);
+cudaError_t launch_tcp_scatter(MemberDev* members, int n_members, const tcp::ProgramDev* progs, const tcp::MemberTc* mtc,
+                               float* master, long long master_floats, int max_mlayers, cudaStream_t st);
 
 }  // namespace nmb

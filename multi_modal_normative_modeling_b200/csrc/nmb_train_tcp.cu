@@ -1793,11 +1793,30 @@ cudaError_t launch_recon_tcp(const TrainLaunch& t, const tcp::ProgramDev* progs,
   return cudaGetLastError();
 }
 
+namespace tcp {
+// resident state: the only per-launch bookkeeping of the state-conversion pass that is still needed
+__global__ void tcp_launch_base_kernel(MemberDev* members, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) members[i].launch_base = members[i].steps_done;
+}
+}  // namespace tcp
+
+// master state (lane-major p, m, v of every member) -> the caller's row-major buffers
+cudaError_t launch_tcp_scatter(MemberDev* members, int n_members, const tcp::ProgramDev* progs, const tcp::MemberTc* mtc,
+                               float* master, long long master_floats, int max_mlayers, cudaStream_t st) {
+  tcp::PrepArgs pa{members, progs, mtc, master, master_floats, n_members, 1};
+  const dim3 pgrid((unsigned)n_members, (unsigned)max_mlayers);
+  tcp::tcp_move_kernel<<<pgrid, 256, 0, st>>>(pa, 0);
+  return cudaGetLastError();
+}
+
+// gather_in: convert the caller's buffers to the master layout (and build the weight planes) before the launch;
+// scatter_out: convert back after it.  Both false = the state stays resident between consecutive calls.
 cudaError_t launch_train_tcp(const TrainLaunch& t, const tcp::ProgramDev* progs, const tcp::MemberTc* mtc,
                              unsigned char* stash, long long stash_bytes, float* master, long long master_floats,
                              const tcp::MStep* msteps, const int* ms_off, const int* ms_cnt, int n_archs,
                              const tcp::EpiP* epis_p, const int* ep_off, const int* ep_cnt,
-                             int max_mlayers, int n_sm, cudaStream_t st) {
+                             int max_mlayers, int n_sm, bool gather_in, bool scatter_out, cudaStream_t st) {
   if (t.n_members <= 0 || t.n_steps <= 0) return cudaSuccess;
   // more members than SMs: deal chunks of >= 4 steps, so that the launch does not end on a few whole members
   int n_chunks = 1;
@@ -1815,7 +1834,8 @@ cudaError_t launch_train_tcp(const TrainLaunch& t, const tcp::ProgramDev* progs,
   }
   tcp::PrepArgs pa{t.members, progs, mtc, master, master_floats, t.n_members, (t.flags & NMB_TRAIN_NO_ADAM) ? 0 : 1};
   const dim3 pgrid((unsigned)t.n_members, (unsigned)max_mlayers);
-  tcp::tcp_move_kernel<<<pgrid, 256, 0, st>>>(pa, 1);
+  if (gather_in) tcp::tcp_move_kernel<<<pgrid, 256, 0, st>>>(pa, 1);
+  else tcp::tcp_launch_base_kernel<<<(t.n_members + 255) / 256, 256, 0, st>>>(t.members, t.n_members);
   tcp::LaunchP L;
   L.n_chunks = n_chunks;
   L.t = t; L.progs = progs; L.mtc = mtc; L.stash = stash; L.stash_bytes = stash_bytes;
@@ -1829,7 +1849,7 @@ cudaError_t launch_train_tcp(const TrainLaunch& t, const tcp::ProgramDev* progs,
   }
   std::memcpy(L.msteps, msteps, sizeof(tcp::MStep) * (size_t)(ms_off[n_archs - 1] + ms_cnt[n_archs - 1]));
   tcp::train_tcp_kernel<false><<<grid, tcp::kThreadsP, tcp::kSmemBytes, st>>>(L);
-  if (pa.adam) tcp::tcp_move_kernel<<<pgrid, 256, 0, st>>>(pa, 0);
+  if (pa.adam && scatter_out) tcp::tcp_move_kernel<<<pgrid, 256, 0, st>>>(pa, 0);
   return cudaGetLastError();
 }
 

@@ -180,8 +180,19 @@ class EnsembleTrainer:
                 out[name + ".bias"] = mat[:, s.cols]
         return out
 
+    def sync(self):
+        """After ``train_steps(..., resident=True)``: refresh ``params`` / ``adam_m`` / ``adam_v`` from the kernel's
+        resident master state (no-op otherwise).  state_dict / load_state_dict / reconstruct do it themselves; call it
+        before reading the packed tensors directly."""
+        if getattr(self, "handle", None):
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.nmb_ensemble_sync(self.handle, _stream_ptr(self.device)), "nmb_ensemble_sync")
+
     def load_state_dict(self, i: int, sd: Dict[str, torch.Tensor]):
         """Copy reference-named tensors (cVAE_multimodal or cVAE naming) into member i."""
+        if getattr(self, "handle", None):       # the kernel's resident copy (if any) is dropped: the caller's buffers rule
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.nmb_ensemble_invalidate(self.handle, _stream_ptr(self.device)), "nmb_ensemble_invalidate")
         views = self._views(i, self.params)
         sd = _normalise_names(sd)
         with torch.no_grad():
@@ -191,6 +202,7 @@ class EnsembleTrainer:
                 v.copy_(torch.as_tensor(sd[k]).to(device=self.device, dtype=torch.float32).reshape(v.shape))
 
     def state_dict(self, i: int, which: str = "params") -> Dict[str, torch.Tensor]:
+        self.sync()
         flat = {"params": self.params, "grads": self.grads, "adam_m": self.adam_m, "adam_v": self.adam_v}[which]
         if flat is None:
             raise RuntimeError("ensemble was created without keep_grads=True")
@@ -198,8 +210,11 @@ class EnsembleTrainer:
 
     # ---- training -----------------------------------------------------------------------
     def train_steps(self, n_steps: int, eps: Optional[torch.Tensor] = None, record_losses: bool = False,
-                    flags: int = 0) -> Optional[torch.Tensor]:
+                    flags: int = 0, resident: bool = False) -> Optional[torch.Tensor]:
         """n_steps minibatch steps for EVERY member in one launch.
+
+        resident=True (pipelined engine): parameters and Adam moments stay in the kernel's layout between calls (two
+        state-conversion launches less per call); the packed tensors are refreshed by ``sync()``.
 
         eps: optional injected draws [n_members, n_steps, batch, latent] (per-step parity);
         returns [n_members, n_steps, 3] (total, kl, ll) when record_losses."""
@@ -217,6 +232,8 @@ class EnsembleTrainer:
             eps_ptr = eps.data_ptr()
         if (flags & _lib.TRAIN_WRITE_GRADS) and self.grads is None:
             raise RuntimeError("TRAIN_WRITE_GRADS needs keep_grads=True")
+        if resident:
+            flags = int(flags) | _lib.TRAIN_RESIDENT
         with torch.cuda.device(self.device):
             _lib.check(self.lib.nmb_ensemble_train(self.handle, int(n_steps), eps_ptr,
                                                    losses.data_ptr() if losses is not None else None,
@@ -224,7 +241,7 @@ class EnsembleTrainer:
         # the pipelined engine launches xprep (dataset re-tiling), tcp_prepare (weight planes + lane-major Adam
         # state), the fused train kernel and, with Adam on, tcp_finish (state back to the caller's layout)
         if self._engine_cached(int(flags)) == "tcgen05-pipelined":
-            self.gpu_launches += 3 if (int(flags) & _lib.TRAIN_NO_ADAM) else 4
+            self.gpu_launches += 3 if (int(flags) & (_lib.TRAIN_NO_ADAM | _lib.TRAIN_RESIDENT)) else 4
         else:
             self.gpu_launches += 1
         return losses

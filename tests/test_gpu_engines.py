@@ -107,3 +107,43 @@ def test_pipelined_forward_only_reconstruct_equals_the_other_engines(dims, hidde
     ref = tr.reconstruct(rows, mode="mean", want_latent=True)
     assert all(torch.equal(xh[i][0], ref[0][i][0]) and torch.equal(mu[i], ref[1][i]) for i in range(len(rows)))
     tr.close()
+
+
+def test_resident_state_between_calls_equals_converting_every_call(workload):
+    """NMB_TRAIN_RESIDENT: parameters / Adam moments stay in the kernel's layout between calls.  Three resident calls +
+    sync == three ordinary calls == one call, bit for bit; state_dict / reconstruct / another engine sync by themselves;
+    load_state_dict drops the resident copy."""
+    from multi_modal_normative_modeling_b200 import EnsembleTrainer, _lib
+    hw, wl = workload
+    dev = torch.device("cuda", 0)
+    specs = wl.specs[::8]                                    # 20 members, both architectures
+    def fresh():
+        return EnsembleTrainer(specs, device=dev)
+    a, b, c = fresh(), fresh(), fresh()
+    a.train_steps(9)
+    for n in (2, 3, 4):
+        b.train_steps(n)
+        c.train_steps(n, resident=True)
+    assert not torch.equal(c.params, a.params)               # the packed tensors are stale until sync() ...
+    sd = c.state_dict(0)                                      # ... which state_dict does by itself
+    torch.cuda.synchronize()
+    assert torch.equal(a.params, b.params) and torch.equal(a.params, c.params)
+    assert torch.equal(a.adam_m, c.adam_m) and torch.equal(a.adam_v, c.adam_v)
+    assert torch.equal(sd["encoder_list.0.encoder_layers.0.weight"], a.state_dict(0)["encoder_list.0.encoder_layers.0.weight"])
+    # resident -> reconstruct (syncs) -> more resident steps -> FP32 engine (syncs) : same as the plain sequence
+    c.train_steps(2, resident=True)
+    xa, _, _ = c.reconstruct([s.xc for s in specs], mode="mean")
+    c.train_steps(2, resident=True)
+    c.train_steps(1, flags=_lib.TRAIN_FP32)
+    a.train_steps(2)
+    xb, _, _ = a.reconstruct([s.xc for s in specs], mode="mean")
+    a.train_steps(2)
+    a.train_steps(1, flags=_lib.TRAIN_FP32)
+    torch.cuda.synchronize()
+    assert torch.equal(xa[3][0], xb[3][0]) and torch.equal(a.params, c.params)
+    # new weights while a resident copy exists: the caller's buffers win
+    c.train_steps(2, resident=True)
+    c.load_state_dict(0, a.state_dict(0))
+    c.sync(); torch.cuda.synchronize()
+    assert torch.equal(c.state_dict(0)["decoder_list.0.decoder_mean_layer.bias"], a.state_dict(0)["decoder_list.0.decoder_mean_layer.bias"])
+    a.close(); b.close(); c.close()

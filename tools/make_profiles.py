@@ -80,6 +80,28 @@ json.dump({"kernel": "nmb::tcp::train_tcp_kernel", "kernel_source_sha256": src_h
            "capture": "profiles/r02_tcp_ncu_summary.txt (ncu --set full, 480 members x 20 minibatch steps = one bench step)",
            "dram_bytes_read_per_launch": rd * 1e9, "dram_bytes_write_per_launch": wr * 1e9,
            "dram_bytes_per_launch": (rd + wr) * 1e9, "gpu_time_ms_under_ncu": t}, open("profiles/train_kernel_traffic.json", "w"), indent=1)
+# the forward-only (reconstruction) instantiation of the same kernel and the scoring breakdown
+if os.path.exists(G + "/r02_recon.ncu-rep"):
+    for page in ("raw", "source"):
+        with open("%s/r02_recon_%s.csv" % (G, "raw" if page == "raw" else "src"), "w") as f:
+            subprocess.run(["ncu", "-i", G + "/r02_recon.ncu-rep", "--page", page, "--csv"], stdout=f, stderr=subprocess.DEVNULL, check=True)
+    rbody = subprocess.run([sys.executable, "profiles/ncu_summary.py", G + "/r02_recon_raw.csv", G + "/r02_recon_src.csv"],
+                           capture_output=True, text=True, check=True).stdout
+    rr = list(csv.reader(open(G + "/r02_recon_raw.csv")))
+    rd_ = dict(zip(rr[0], rr[2]))
+    rextra = "\n-- tensor pipe / memory\n"
+    for k in ["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
+              "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "launch__grid_size"]:
+        if k in rd_:
+            rextra += "   %s = %s\n" % (k, rd_[k])
+    open("profiles/r02_recon_ncu_summary.txt", "w").write(
+        "ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k regex:train_tcp_kernelILb1 -s 4 -c 1 : "
+        "python tools/time_scoring.py\n(nmb::tcp::train_tcp_kernel<true>: the forward-only program of nmb_ensemble_reconstruct, one launch "
+        "over the training rows of the 480 cfg4 members = 1 920 tiles of 256 rows dealt as 960 work items)\n" + rbody + rextra)
+if os.path.exists(G + "/scoring_r02.txt"):
+    open("profiles/r02_scoring_breakdown.txt", "w").write(
+        "tools/time_scoring.py (cfg4, 480 members: 384 000 training rows + 96 000 test rows per pass; CUDA events, 10 repetitions)\n" +
+        "".join(l for l in open(G + "/scoring_r02.txt") if " gpu " in l))
 print(reading)
 print("share %.3f  value %.1f M samples/s  e2e %.1f M  deviation %.1f M subjects/s" %
       (share, bench["value"] / 1e6, bench["e2e"]["value"] / 1e6, bench["deviation"]["value"] / 1e6))
