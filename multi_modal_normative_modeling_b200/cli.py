@@ -173,6 +173,9 @@ def train_main(args, root=None):
             model = model_cls.from_ensemble(trainer, i).cpu()
             model.close()
             torch.save(model, fold_dir / "cVAE_model.pkl")
+            # the same weights as a plain state_dict with the reference's parameter names: loadable by the reference's
+            # own cVAE.cVAE_multimodal(...).load_state_dict (the pickle above names this package's class)
+            torch.save({k: v.detach().cpu() for k, v in model.state_dict().items()}, fold_dir / "cVAE_state_dict.pt")
             print("file saved at ", fold_dir / "cVAE_model.pkl")
     trainer.close()
     return np.stack(logs)

@@ -197,3 +197,98 @@ def test_deviation_scorer_equals_the_per_call_api():
     assert torch.equal(rec[3, 1:117], sc.seg_stats(3)[0].double()) and torch.equal(rec[:, 0], sc.auc_subj)
     assert torch.equal(rec[0, 1 + 2 * 116:1 + 2 * 116 + 17], sc.seg_auc_roi(0)) and float(rec[0, 1 + 17:1 + 116].abs().max()) == 0
     tr.close()
+
+
+def _kfold_auc_vs_oracle(dims_names, combine, early_fusion, production_rng, d=116, n_subjects=400, epochs=6):
+    """5-fold train + deviation scoring of ONE configuration on the GPU and with the CPU oracle (same initial weights,
+    same eps draws): per-fold AUC of the modality-averaged per-subject deviation (group analysis :212-215) and per-ROI
+    z-score AUCs must agree within |dAUC| <= 0.01 (north_star).  production_rng: the kernels draw eps themselves (Philox
+    stream of oracle/philox.py) instead of taking injected draws; the oracle replays that stream."""
+    from oracle import cvae_torch, deviation as odev, philox
+    from multi_modal_normative_modeling_b200 import EnsembleTrainer, MemberSpec, pack_rows, scoring, workloads
+    hw = workloads.build_host_workload(n_subjects=n_subjects, d=d, n_splits=5, early_fusion=early_fusion, hidden=(110, 110))
+    names = [n for n in hw.names if n in dims_names] if dims_names else [workloads.EARLY]
+    dims = [hw.dims[n] for n in names]
+    M, z, batch = len(names), 10, 256
+    dev = torch.device("cuda", 0)
+    rng = np.random.RandomState(1)
+    specs, oracle_out, eps_all, eps_test_all, test_xc = [], [], [], [], []
+    for f, fd in enumerate(hw.folds):
+        xs = [fd.train_x[n] for n in names]
+        c = fd.train_c
+        n_tr, n_te = xs[0].shape[0], fd.test_x[names[0]].shape[0]
+        spe = -(-n_tr // batch)
+        seed = 5000 + f
+        torch.manual_seed(42)
+        model = cvae_torch.OracleCVAEMultimodal(dims, [110, 110], z, 29, 1e-4, M, True)
+        sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+        if production_rng:
+            eps = np.stack([philox.normals(seed, s, batch * z, 0).reshape(batch, z) for s in range(epochs * spe)])
+            tiles = -(-n_te // 256)
+            eps_test = np.concatenate([philox.normals(seed, t, 256 * z, 1).reshape(256, z) for t in range(tiles)])[:n_te]
+        else:
+            eps = rng.randn(epochs * spe, batch, z).astype(np.float32)
+            eps_test = rng.randn(n_te, z).astype(np.float32)
+        cvae_torch.reference_train_loop(model, [torch.from_numpy(x) for x in xs], [torch.from_numpy(c).long()] * M, combine,
+                                        epochs, batch, eps_fn=lambda s, rows, e=eps: torch.from_numpy(e[s][:rows]))
+        ct = torch.from_numpy(fd.test_c).long()
+        preds = model.pred_recon([torch.from_numpy(fd.test_x[n]) for n in names], ct, combine, torch.from_numpy(eps_test))
+        preds_tr = model.pred_recon([torch.from_numpy(x) for x in xs], torch.from_numpy(c).long(), combine,
+                                    torch.zeros(n_tr, z))
+        hc = fd.train_df["DIA"].to_numpy() == 1
+        labels = (fd.test_df["DIA"].to_numpy() != 1).astype(np.uint8)
+        subj, zs = [], []
+        for m, n in enumerate(names):
+            p, ptr = preds[m].numpy(), preds_tr[m].numpy()
+            mean, std = odev.normative_stats(odev.recon_deviation_roi(xs[m], ptr)[hc])
+            subj.append(odev.recon_deviation(fd.test_x64[n], p))
+            zs.append(odev.zscores(odev.recon_deviation_roi(fd.test_x64[n], p), mean, std))
+        oracle_out.append(dict(subj=np.mean(subj, axis=0), z=zs, labels=labels, hc=hc))
+        cd = torch.from_numpy(c).to(dev)
+        xc = [pack_rows(torch.from_numpy(x).to(dev), cd) for x in xs]
+        specs.append(MemberSpec(dims, [110, 110], z, 29, xc, combine=combine, batch=batch, seed=seed, state_dict=sd))
+        ctd = torch.from_numpy(fd.test_c).to(dev)
+        test_xc.append([pack_rows(torch.from_numpy(fd.test_x[n]).to(dev), ctd) for n in names])
+        eps_all.append(eps); eps_test_all.append(eps_test)
+    tr = EnsembleTrainer(specs, device=dev)
+    assert tr.engine() == "tcgen05-pipelined"
+    n_steps = eps_all[0].shape[0]
+    if production_rng:
+        tr.train_steps(n_steps)
+        xhat, _, _ = tr.reconstruct(test_xc, mode="sample")
+    else:
+        tr.train_steps(n_steps, eps=torch.from_numpy(np.stack(eps_all)).to(dev))
+        xhat, _, _ = tr.reconstruct(test_xc, mode="sample", eps=[torch.from_numpy(e).to(dev) for e in eps_test_all])
+    xhat_tr, _, _ = tr.reconstruct([s.xc for s in specs], mode="mean")
+    for f, o in enumerate(oracle_out):
+        mask = torch.from_numpy(o["hc"].astype(np.uint8)).to(dev)
+        lab = torch.from_numpy(o["labels"]).to(dev)
+        stats = scoring.normative_stats(specs[f].xc, xhat_tr[f], [mask] * M)
+        _, zg, subj = scoring.deviation(test_xc[f], xhat[f], stats)
+        avg = scoring.mean_rows(subj)                                   # modality averaging on the GPU
+        got = float(scoring.auc([avg], [lab])[0][0])
+        want = odev.auc(o["subj"], o["labels"])
+        assert abs(got - want) <= 0.01, (f, got, want)
+        assert relerr(avg.cpu().numpy(), o["subj"]) < 2e-3
+        roi_auc = scoring.auc(zg, [lab] * M)
+        for m in range(M):
+            for col in range(0, dims[m], 17):
+                assert abs(float(roi_auc[m][col]) - odev.auc(o["z"][m][:, col], o["labels"])) <= 0.01, (f, m, col)
+    tr.close()
+
+
+def test_cfg2_early_fusion_kfold_auc_vs_oracle():
+    """BASELINE configs[1]: early_fusion_modalities (concatenated T1w + T2w + fMRI, D = 348), 5 folds."""
+    _kfold_auc_vs_oracle(None, "gPoE", early_fusion=True, production_rng=False)
+
+
+def test_cfg3_multimodal_fusion_kfold_auc_vs_oracle():
+    """BASELINE configs[2]: per-modality encoders / decoders with latent fusion (gPoE, three modalities) and the group
+    analysis' modality-averaged deviation AUC."""
+    _kfold_auc_vs_oracle(("T1w_sMRI", "T2w_sMRI", "fMRI"), "gPoE", early_fusion=False, production_rng=False)
+
+
+def test_cfg1_production_philox_draws_kfold_auc_vs_oracle():
+    """The production path end to end: in-kernel Philox eps for training and for the sampled test-time z, against the
+    oracle replaying the documented stream (oracle/philox.py)."""
+    _kfold_auc_vs_oracle(("T1w_sMRI",), "poe", early_fusion=False, production_rng=True, d=150)
