@@ -143,6 +143,7 @@ struct NmbEnsemble {
   std::vector<int> ms_off, ms_cnt;
   std::vector<tcp::EpiP> epis_p;             // compact epilogue item tables (kernel parameters) where they fit
   std::vector<int> ep_off, ep_cnt;
+  std::vector<unsigned char> ep_first, epf_first;     // [arch][4]: first own item per epilogue group (train / forward-only)
   int max_mlayers = 1;                       // layers with Adam master state, over all architectures
   // forward-only programs of the same architectures (nmb_ensemble_reconstruct on the pipelined kernel)
   tcp::ProgramDev* progs_fwd_dev = nullptr;
@@ -178,7 +179,14 @@ int setup_tcp(NmbEnsemble* e) {
     bool fits = e->epis_p.size() + P.epis.size() <= (size_t)tcp::kMaxParamEpis;
     for (const tcp::Epi& ep : P.epis) fits = fits && tcp::epip_fits(ep);
     e->ep_off.push_back((int)e->epis_p.size()); e->ep_cnt.push_back(fits ? (int)P.epis.size() : 0);
-    if (fits) for (const tcp::Epi& ep : P.epis) e->epis_p.push_back(tcp::to_epip(ep));
+    unsigned char first[3] = {255, 255, 255}, flip0[3] = {0, 0, 0};
+    if (fits) {
+      const size_t off = e->epis_p.size();
+      for (const tcp::Epi& ep : P.epis) e->epis_p.push_back(tcp::to_epip(ep));
+      tcp::link_group_items(P.epis, e->epis_p.data() + off, first, flip0);
+    }
+    for (int g = 0; g < 3; ++g) e->ep_first.push_back(first[g]);
+    e->ep_first.push_back(0);
   }
   auto dev_alloc = [&](size_t bytes, void** out) {
     cudaError_t ce = cudaMalloc(out, bytes ? bytes : 16);
@@ -271,7 +279,14 @@ int setup_tcp(NmbEnsemble* e) {
       bool fits = e->epis_fwd.size() + F.epis.size() <= (size_t)tcp::kMaxParamEpis;
       for (const tcp::Epi& ep : F.epis) fits = fits && tcp::epip_fits(ep);
       e->epf_off.push_back((int)e->epis_fwd.size()); e->epf_cnt.push_back(fits ? (int)F.epis.size() : 0);
-      if (fits) for (const tcp::Epi& ep : F.epis) e->epis_fwd.push_back(tcp::to_epip(ep));
+      unsigned char first[3] = {255, 255, 255}, flip0[3] = {0, 0, 0};
+      if (fits) {
+        const size_t off = e->epis_fwd.size();
+        for (const tcp::Epi& ep : F.epis) e->epis_fwd.push_back(tcp::to_epip(ep));
+        tcp::link_group_items(F.epis, e->epis_fwd.data() + off, first, flip0);
+      }
+      for (int g = 0; g < 3; ++g) e->epf_first.push_back(first[g]);
+      e->epf_first.push_back(0);
       void *ds, *de;
       CU(upload(F.steps.data(), sizeof(tcp::Step) * F.steps.size(), &ds));
       CU(upload(F.epis.data(), sizeof(tcp::Epi) * F.epis.size(), &de));
@@ -523,7 +538,7 @@ static int train_common(NmbEnsemble* e, int64_t n, int n_is_epochs, const float*
     const bool gather_in = !adam || !e->master_valid;
     CU(launch_train_tcp(t, e->progs_dev, e->mtc_dev, e->stash, e->stash_bytes, e->master, e->master_floats,
                         e->msteps.data(), e->ms_off.data(), e->ms_cnt.data(), (int)e->ms_off.size(),
-                        e->epis_p.data(), e->ep_off.data(), e->ep_cnt.data(), e->max_mlayers, e->n_sm,
+                        e->epis_p.data(), e->ep_off.data(), e->ep_cnt.data(), e->ep_first.data(), e->max_mlayers, e->n_sm,
                         gather_in, !resident, (cudaStream_t)stream));
     if (adam) { e->master_valid = resident; e->caller_stale = resident; }
   } else {
@@ -692,7 +707,7 @@ int nmb_ensemble_reconstruct(NmbEnsemble* e, const float* const* xc, const int32
     t.order = e->order_dev;
     CU(launch_recon_tcp(t, e->progs_fwd_dev, e->progs_dev, e->mtc_dev, e->stash, e->stash_bytes, e->msteps_fwd.data(),
                         e->msf_off.data(), e->msf_cnt.data(), (int)e->msf_off.size(), e->epis_fwd.data(), e->epf_off.data(),
-                        e->epf_cnt.data(), e->max_mlayers, mode == NMB_RECON_MEAN ? 1 : 2, b.at<tcp::ReconTc>(o_r),
+                        e->epf_cnt.data(), e->epf_first.data(), e->max_mlayers, mode == NMB_RECON_MEAN ? 1 : 2, b.at<tcp::ReconTc>(o_r),
                         b.at<tcp::ReconWork>(o_w), (int)work.size(), e->n_sm, st));
     CU(b.release(st));
     return 0;

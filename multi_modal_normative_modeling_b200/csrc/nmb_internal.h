@@ -91,13 +91,13 @@ cudaError_t launch_xprep(const void* items_dev, int n_items, int max_blocks, cud
 cudaError_t launch_recon_tcp(const TrainLaunch& t, const tcp::ProgramDev* progs, const tcp::ProgramDev* train_progs,
                              const tcp::MemberTc* mtc, unsigned char* stash, long long stash_bytes,
                              const tcp::MStep* msteps, const int* ms_off, const int* ms_cnt, int n_archs,
-                             const tcp::EpiP* epis_p, const int* ep_off, const int* ep_cnt, int max_mlayers,
-                             int recon_mode, const tcp::ReconTc* rtc, const tcp::ReconWork* rwork, int n_rwork,
+                             const tcp::EpiP* epis_p, const int* ep_off, const int* ep_cnt, const unsigned char* ep_first,
+                             int max_mlayers, int recon_mode, const tcp::ReconTc* rtc, const tcp::ReconWork* rwork, int n_rwork,
                              int n_sm, cudaStream_t st);
 cudaError_t launch_train_tcp(const TrainLaunch& t, const tcp::ProgramDev* progs, const tcp::MemberTc* mtc,
                              unsigned char* stash, long long stash_bytes, float* master, long long master_floats,
                              const tcp::MStep* msteps, const int* ms_off, const int* ms_cnt, int n_archs,
-                             const tcp::EpiP* epis_p, const int* ep_off, const int* ep_cnt,
+                             const tcp::EpiP* epis_p, const int* ep_off, const int* ep_cnt, const unsigned char* ep_first,
                              int max_mlayers, int n_sm, bool gather_in, bool scatter_out, cudaStream_t st);
 cudaError_t launch_tcp_scatter(MemberDev* members, int n_members, const tcp::ProgramDev* progs, const tcp::MemberTc* mtc,
                                float* master, long long master_floats, int max_mlayers, cudaStream_t st);

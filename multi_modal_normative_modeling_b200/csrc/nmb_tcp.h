@@ -149,10 +149,44 @@ struct alignas(16) EpiP {
   unsigned short n_mma, n_valid, n_cols, tmem_col, col0, src_cg, p_ld, p_rows, p_cols, wp_R, mst_R, row0, wait_optim;
   signed char kind, half, buf, mod;
   unsigned char to_act, last, split_all, pad_;
-  int pad2_[2];
+  // Per epilogue group g: the next item the group executes after this one (255 = none) and, for THIS item, the
+  // weight-gradient accumulator barriers (bit 0 = wacc[0], bit 1 = wacc[1]) whose phase the group must flip before it,
+  // because it skipped optimiser-only items that consumed them.  Lets a group jump from own item to own item instead of
+  // decoding every item of the other groups on its critical path.
+  unsigned char next_own[3], flip_before[3];
+  unsigned char pad3_[2];
 };
 static_assert(sizeof(EpiP) == 64, "EpiP must stay 64 bytes");
 constexpr int kMaxParamEpis = 160;                    // 10 KB
+
+// which group(s) execute an item (all rows of the minibatch present)
+inline bool epi_owned_by(const Epi& e, int g) {
+  if (e.kind == EK_STEP_END || e.split_all) return true;
+  if (e.kind == EK_WGRAD || e.kind == EK_WGRAD_T) return g == 2;
+  return e.half == g;
+}
+// fill next_own / flip_before of a program's compact items; first_own[g] = the group's first item
+inline void link_group_items(const std::vector<Epi>& epis, EpiP* out, unsigned char first_own[3], unsigned char first_flip[3]) {
+  const int n = (int)epis.size();
+  for (int g = 0; g < 3; ++g) {
+    int prev = -1;
+    unsigned flip = 0;
+    first_own[g] = 255; first_flip[g] = 0;
+    for (int k = 0; k < n; ++k) {
+      const Epi& e = epis[k];
+      if (!epi_owned_by(e, g)) {
+        if ((e.kind == EK_WGRAD || e.kind == EK_WGRAD_T) && e.buf >= 2) flip ^= 1u << (e.buf - 2);
+        continue;
+      }
+      if (prev < 0) { first_own[g] = (unsigned char)k; first_flip[g] = (unsigned char)flip; }
+      else out[prev].next_own[g] = (unsigned char)k;
+      out[k].flip_before[g] = (unsigned char)flip;
+      out[k].next_own[g] = 255;
+      flip = 0;
+      prev = k;
+    }
+  }
+}
 
 inline bool epip_fits(const Epi& e) {
   return e.stash_off < (1LL << 31) && e.src_off < (1LL << 31) && e.p_off < (1LL << 31) && e.wp_off < (1LL << 31) &&
@@ -276,6 +310,7 @@ inline Program build_program(const ArchDesc& a, bool fwd_only = false) {
   const char* mk_env = getenv("NMB_TCP_MERGE");
   const int merge_mask = mk_env ? atoi(mk_env) : 7;
   const bool merge_k = (merge_mask & 1) != 0, merge_fwd = (merge_mask & 2) != 0, merge_dg = (merge_mask & 4) != 0;
+  const bool split_recon = (merge_mask & 8) != 0;   // 8: x_recon tiles alternate between two accumulator halves (measured: no gain, off)
 
   // ---- stash + planes layout ----
   long long so = 0, wo = 0;
@@ -366,7 +401,9 @@ inline Program build_program(const ArchDesc& a, bool fwd_only = false) {
   };
   auto new_epi = [&](int kind, int half, int buf, int mod) {
     Epi e{}; e.kind = kind; e.half = half; e.buf = buf; e.mod = mod; e.stash_off = -1; e.src_off = -1;
-    e.tmem_col = buf < 0 ? 0 : (buf < 2 ? kAcc0 + 128 * buf : kWacc0 + 128 * (buf - 2));
+    // accumulator barriers: 0 / 1 = acc[h], 2 / 3 = wacc[b], 4 / 5 = the upper 64 columns of acc[h] used as a second
+    // x_recon tile buffer (the tiles of the wide output layer alternate between the two halves of acc[h])
+    e.tmem_col = buf < 0 ? 0 : (buf < 2 ? kAcc0 + 128 * buf : (buf < 4 ? kWacc0 + 128 * (buf - 2) : kAcc0 + 128 * (buf - 4) + 64));
     return e;
   };
   // MMA-issue dependencies: items of the step's own half go to that group's counter, joint items to both
@@ -608,26 +645,33 @@ inline Program build_program(const ArchDesc& a, bool fwd_only = false) {
         act_ready[h] = id; acc_free[accbuf(h)] = id;
       }
     }
+    // Wide output layer: x_recon in tiles of 64 columns.  Consecutive tiles of a half alternate between the two 64-column
+    // halves of acc[h] (each with its own barrier), so the MMAs of tile t + 1 run while the epilogue of tile t -- the
+    // longest item of the forward pass -- is still reading tile t.
+    int sub_free[2][2] = {{acc_free[0], acc_free[0]}, {acc_free[1], acc_free[1]}};
     for (int t = 0; t < lay.n_dxh_blk[m]; ++t) {
       for (int h = 0; h < 2; ++h) {
+        const int sb = split_recon ? (t & 1) : 0;
+        const int bufid = sb ? 4 + h : accbuf(h);
         {   // x_recon columns 64 t .. 64 t + 63: ACT[h] (K-major) x 8 column groups of the transposed block (MN-major)
           const WRef& w = w_out[m][0];
-          const int buf = accbuf(h);
           Step s = base_step(h);
           set_b(s, SP_W, w.wp_off, w.R, 8 * t, 8, true);
           set_a_kmajor(s, 0);
-          s.ksteps = (unsigned short)(w.R / 16); s.n = 64; s.tmem_col = (unsigned short)(kAcc0 + 128 * buf);
+          s.ksteps = (unsigned short)(w.R / 16); s.n = 64; s.tmem_col = (unsigned short)(kAcc0 + 128 * h + 64 * sb);
           s.first = 1;
-          need(s, acc_free[buf]); need(s, act_ready[h]);
-          s.commit = 1; s.commit_buf = (unsigned char)buf;
+          need(s, sub_free[h][sb]); need(s, act_ready[h]);
+          s.commit = 1; s.commit_buf = (unsigned char)bufid;
           P.steps.push_back(s);
         }
-        Epi e = new_epi(fwd_only ? EK_XHAT : EK_RECON, h, accbuf(h), m);
+        Epi e = new_epi(fwd_only ? EK_XHAT : EK_RECON, h, bufid, m);
         e.n_mma = 64; e.n_valid = q.D - 64 * t < 64 ? q.D - 64 * t : 64; e.n_cols = 64; e.col0 = 64 * t;
         e.stash_off = fwd_only ? -1 : lay.dxh_blk[m] + ((long long)h * lay.n_dxh_blk[m] + t) * 32768;
         e.last = t == lay.n_dxh_blk[m] - 1;
         const int id = push_epi(e);
         acc_free[accbuf(h)] = id;
+        sub_free[h][sb] = id;
+        if (!split_recon) sub_free[h][1] = id;
         dxh_ready[m * 2 + h] = id;
       }
     }

@@ -40,7 +40,7 @@ __device__ __forceinline__ unsigned long long gtime() {
 struct RowSet { int n_rows, batch, n_half; };
 
 struct Ctrl {
-  uint64_t full[kSlots], empty[kSlots], accbar[4];
+  uint64_t full[kSlots], empty[kSlots], accbar[6];      // accbar: acc[0], acc[1], wacc[0], wacc[1], upper halves of acc[0], acc[1]
   uint32_t tmem;
   volatile uint32_t epi_done[kGroups];   // per epilogue group: items finished (1 + step * n_epis + index + 1)
   int member;
@@ -193,6 +193,8 @@ struct LaunchP {
   int recon_mode; int n_rwork;
   const ReconTc* rtc; const ReconWork* rwork;
   int ep_off[kMaxParamArchs], ep_cnt[kMaxParamArchs];   // slice of epis_p per architecture; cnt 0 = global-memory table
+  unsigned char ep_first[kMaxParamArchs][4];            // first own item of epilogue group g (see EpiP::next_own)
+  int jump;                                             // 0: dev knob NMB_TCP_JUMP=0, every group walks the whole item list
   MStep msteps[kMaxParamSteps];
   EpiP epis_p[kMaxParamEpis];
 };
@@ -349,27 +351,8 @@ __device__ __forceinline__ void put_planes(unsigned char* blk, int g, int row, c
 // Adam master state is a pure stream (read once, written once per step, re-read a whole step later): keep it from
 // displacing the weight planes and the backward stash in L2.
 // (.cg: the previous work item of the member may have run on another SM -- never trust this SM's L1 for it)
-#ifdef NMB_ADAM_EVICT_FIRST
-// variant: explicit L2 evict-first policy on the Adam stream (dev A/B build)
-__device__ __forceinline__ uint64_t evict_first_policy() {
-  uint64_t pol;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-  return pol;
-}
-__device__ __forceinline__ float4 ld_stream4(const float* p) {
-  float4 v;
-  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(evict_first_policy()) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_stream4(float* p, const float4& v) {
-  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;"
-               ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(evict_first_policy()) : "memory");
-}
-#else
 __device__ __forceinline__ float4 ld_stream4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void st_stream4(float* p, const float4& v) { __stcs(reinterpret_cast<float4*>(p), v); }
-#endif
 
 // torch.optim.Adam element update; sqrt / reciprocal on the SFU (2 ulp, far inside the parity budget)
 __device__ __forceinline__ float adam_update(const EpiCtx& c, float& m1, float& v1, float p0, float g) {
@@ -1335,19 +1318,34 @@ __device__ void epilogue_role(const LaunchP& L, int ai, int mi, EpiCtx& c, const
       eps = t.eps_override ? t.eps_override + ((long long)mi * t.stride_steps + i0 + i) * mb.batch * c.a->Z : nullptr;
       lo = t.loss_out ? t.loss_out + ((long long)mi * t.stride_steps + i0 + i) * 3 : nullptr;
     }
-    for (int k = 0; k < n_epis; ++k) {
+    // Full minibatch + compact table: every group jumps from own item to own item (host-linked list); otherwise it
+    // walks the whole list and skips what it does not own.
+    const bool jump = in_params && c.rows_h1 > 0 && L.jump;
+    const bool tr_step = g_trace && blockIdx.x == 0 && i0 + i == g_trace_step;     // one global read per step, not per item
+    for (int k = jump ? (int)L.ep_first[ai][c.grp] : 0; k < n_epis; ) {
       Epi e;
-      if (in_params) e = from_epip(L.epis_p[ep0 + k]);
-      else {
+      int k_next = k + 1;
+      if (in_params) {
+        const EpiP& q = L.epis_p[ep0 + k];
+        if (jump) {
+          acc_par ^= (uint32_t)q.flip_before[c.grp] << 2;
+          k_next = q.next_own[c.grp] == 255 ? n_epis : (int)q.next_own[c.grp];
+        }
+        e = from_epip(q);
+      } else {
         e = epis[k];
         if (c.lane == 0 && k + 2 < n_epis) asm volatile("prefetch.global.L1 [%0];" ::"l"(epis + k + 2));
       }
+      const int k_cur = k;
+      k = k_next;
       const bool all = e.kind == EK_STEP_END;
       const bool optim = e.kind == EK_WGRAD || e.kind == EK_WGRAD_T;
-      const int owner = (all || e.split_all) ? c.grp : (optim ? 2 : e.half);
-      if (owner != c.grp || (e.half == 1 && c.rows_h1 == 0)) {
-        if (optim) acc_par ^= 1u << e.buf;       // keep this group's view of the accumulator barrier phases in step
-        continue;
+      if (!jump) {
+        const int owner = (all || e.split_all) ? c.grp : (optim ? 2 : e.half);
+        if (owner != c.grp || (e.half == 1 && c.rows_h1 == 0)) {
+          if (optim) acc_par ^= 1u << e.buf;       // keep this group's view of the accumulator barrier phases in step
+          continue;
+        }
       }
       set_workers(c, all);
       if (e.split_all) {
@@ -1355,9 +1353,18 @@ __device__ void epilogue_role(const LaunchP& L, int ai, int mi, EpiCtx& c, const
         // an idle activation group may be far ahead of the optimiser: mbarrier parity only disambiguates one phase
         if (c.grp != 2 && e.wait_optim) wait_epi(&c.ctl->epi_done[2], sv.base + (uint32_t)e.wait_optim);
       }
-      const bool tr = g_trace && blockIdx.x == 0 && i0 + i == g_trace_step && pub && (!all || c.grp == 0);
+      const bool tr = tr_step && pub && (!all || c.grp == 0);
+#ifdef NMB_TCP_FINE_TRACE
+      // loop-level cycle stamps of group 0's publishing thread: [decoded | before accumulator wait | after it | item done |
+      // fenced | group barrier | published]
+      unsigned long long* lp = (tr && c.grp == 0) ? g_trace + 2048 + 512 + 8 * k_cur : nullptr;
+#define LPS(j) do { if (lp) lp[j] = (unsigned long long)clock64(); } while (0)
+#else
+#define LPS(j) do { } while (0)
+#endif
+      LPS(0);
       const int tbase = c.grp == 0 ? 0 : 3 * n_epis * c.grp + 5 * pg.n_steps;   // groups 1, 2 stamp after the MMA / producer records
-      if (tr) g_trace[tbase + 3 * k] = gtime();
+      if (tr) g_trace[tbase + 3 * k_cur] = gtime();
       if (e.kind == EK_LAM) {        // both halves' reconstruction items (and their stash fences) are behind these counters
         wait_epi(&c.ctl->epi_done[0], sv.base + (uint32_t)e.n_valid);
         if (c.rows_h1 > 0) wait_epi(&c.ctl->epi_done[1], sv.base + (uint32_t)e.n_cols);
@@ -1376,12 +1383,14 @@ __device__ void epilogue_role(const LaunchP& L, int ai, int mi, EpiCtx& c, const
         asm volatile("prefetch.global.L1 [%0];" ::"l"(c.stash + lay.ivtab[e.mod] + (long long)e.col0 * 4));
       }
       if (optim) prefetch_adam_state(c, e);
+      LPS(1);
       if (e.buf >= 0) {
         tc::mbar_wait(&c.ctl->accbar[e.buf], (acc_par >> e.buf) & 1u);
         acc_par ^= 1u << e.buf;
         tc::fence_after();
       }
-      if (tr) g_trace[tbase + 3 * k + 1] = gtime();
+      LPS(2);
+      if (tr) g_trace[tbase + 3 * k_cur + 1] = gtime();
 #ifdef NMB_TCP_FINE_TRACE
       c.tr_ptr = nullptr;
       if (tr && c.grp == 0 && e.half == 0) {
@@ -1410,12 +1419,16 @@ __device__ void epilogue_role(const LaunchP& L, int ai, int mi, EpiCtx& c, const
         case EK_XHAT: if (RECON) epi_xhat(c, e); break;
         default: epi_step_end<RECON>(c, lo); fence = rmode ? 0 : 2; break;
       }
+      LPS(3);
       if (e.buf >= 0) tc::fence_before();
       if (fence == 1) fence_async_smem();
       else if (fence == 2) { __threadfence(); fence_async_all(); }
+      LPS(4);
       bar_n(1 + c.grp, kGroupThreads);
-      if (pub) st_release(&c.ctl->epi_done[c.grp], sv.base + (uint32_t)k + 1u);
-      if (tr) g_trace[tbase + 3 * k + 2] = gtime();
+      LPS(5);
+      if (pub) st_release(&c.ctl->epi_done[c.grp], sv.base + (uint32_t)k_cur + 1u);
+      LPS(6);
+      if (tr) g_trace[tbase + 3 * k_cur + 2] = gtime();
     }
   }
 }
@@ -1430,7 +1443,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) train_tcp_kernel(const __grid_co
   const TrainLaunch& t = L.t;
   if (threadIdx.x == 0) {
     for (int i = 0; i < kSlots; ++i) { tc::mbar_init(&ctl->full[i], 1); tc::mbar_init(&ctl->empty[i], 1); }
-    for (int i = 0; i < 4; ++i) tc::mbar_init(&ctl->accbar[i], 1);
+    for (int i = 0; i < 6; ++i) tc::mbar_init(&ctl->accbar[i], 1);
   }
   if (warp == kEpiWarps) tc::tmem_alloc(&ctl->tmem, 512);
   tc::fence_before();
@@ -1763,8 +1776,8 @@ __global__ void __launch_bounds__(256) tcp_move_kernel(const PrepArgs a, const i
 cudaError_t launch_recon_tcp(const TrainLaunch& t, const tcp::ProgramDev* progs, const tcp::ProgramDev* train_progs,
                              const tcp::MemberTc* mtc, unsigned char* stash, long long stash_bytes,
                              const tcp::MStep* msteps, const int* ms_off, const int* ms_cnt, int n_archs,
-                             const tcp::EpiP* epis_p, const int* ep_off, const int* ep_cnt, int max_mlayers,
-                             int recon_mode, const tcp::ReconTc* rtc, const tcp::ReconWork* rwork, int n_rwork,
+                             const tcp::EpiP* epis_p, const int* ep_off, const int* ep_cnt, const unsigned char* ep_first,
+                             int max_mlayers, int recon_mode, const tcp::ReconTc* rtc, const tcp::ReconWork* rwork, int n_rwork,
                              int n_sm, cudaStream_t st) {
   if (n_rwork <= 0) return cudaSuccess;
   const int grid = n_rwork < n_sm ? n_rwork : n_sm;
@@ -1782,7 +1795,11 @@ cudaError_t launch_recon_tcp(const TrainLaunch& t, const tcp::ProgramDev* progs,
   L.t = t; L.progs = progs; L.mtc = mtc; L.stash = stash; L.stash_bytes = stash_bytes;
   L.master = nullptr; L.master_floats = 0;
   L.recon_mode = recon_mode; L.n_rwork = n_rwork; L.rtc = rtc; L.rwork = rwork;
-  for (int a = 0; a < n_archs; ++a) { L.ms_off[a] = ms_off[a]; L.ms_cnt[a] = ms_cnt[a]; L.ep_off[a] = ep_off[a]; L.ep_cnt[a] = ep_cnt[a]; }
+  for (int a = 0; a < n_archs; ++a) {
+    L.ms_off[a] = ms_off[a]; L.ms_cnt[a] = ms_cnt[a]; L.ep_off[a] = ep_off[a]; L.ep_cnt[a] = ep_cnt[a];
+    for (int g = 0; g < 4; ++g) L.ep_first[a][g] = ep_first[4 * a + g];
+  }
+  { const char* u = getenv("NMB_TCP_JUMP"); L.jump = !(u && u[0] == '0'); }
   {
     int n_ep = 0;
     for (int a = 0; a < n_archs; ++a) if (ep_cnt[a] > 0 && ep_off[a] + ep_cnt[a] > n_ep) n_ep = ep_off[a] + ep_cnt[a];
@@ -1815,7 +1832,7 @@ cudaError_t launch_tcp_scatter(MemberDev* members, int n_members, const tcp::Pro
 cudaError_t launch_train_tcp(const TrainLaunch& t, const tcp::ProgramDev* progs, const tcp::MemberTc* mtc,
                              unsigned char* stash, long long stash_bytes, float* master, long long master_floats,
                              const tcp::MStep* msteps, const int* ms_off, const int* ms_cnt, int n_archs,
-                             const tcp::EpiP* epis_p, const int* ep_off, const int* ep_cnt,
+                             const tcp::EpiP* epis_p, const int* ep_off, const int* ep_cnt, const unsigned char* ep_first,
                              int max_mlayers, int n_sm, bool gather_in, bool scatter_out, cudaStream_t st) {
   if (t.n_members <= 0 || t.n_steps <= 0) return cudaSuccess;
   // more members than SMs: deal chunks of >= 4 steps, so that the launch does not end on a few whole members
@@ -1841,7 +1858,11 @@ cudaError_t launch_train_tcp(const TrainLaunch& t, const tcp::ProgramDev* progs,
   L.t = t; L.progs = progs; L.mtc = mtc; L.stash = stash; L.stash_bytes = stash_bytes;
   L.master = master; L.master_floats = master_floats;
   L.recon_mode = 0; L.n_rwork = 0; L.rtc = nullptr; L.rwork = nullptr;
-  for (int a = 0; a < n_archs; ++a) { L.ms_off[a] = ms_off[a]; L.ms_cnt[a] = ms_cnt[a]; L.ep_off[a] = ep_off[a]; L.ep_cnt[a] = ep_cnt[a]; }
+  for (int a = 0; a < n_archs; ++a) {
+    L.ms_off[a] = ms_off[a]; L.ms_cnt[a] = ms_cnt[a]; L.ep_off[a] = ep_off[a]; L.ep_cnt[a] = ep_cnt[a];
+    for (int g = 0; g < 4; ++g) L.ep_first[a][g] = ep_first[4 * a + g];
+  }
+  { const char* u = getenv("NMB_TCP_JUMP"); L.jump = !(u && u[0] == '0'); }
   {
     int n_ep = 0;
     for (int a = 0; a < n_archs; ++a) if (ep_cnt[a] > 0 && ep_off[a] + ep_cnt[a] > n_ep) n_ep = ep_off[a] + ep_cnt[a];

@@ -41,15 +41,15 @@ int main(int argc, char** argv){
   };
   // accumulator hazard check: the MMAs of use #u of an accumulator buffer may only be issued when every group that
   // owns the epilogue item of use #u-1 has finished reading it
-  std::vector<int> uses[4];
+  std::vector<int> uses[6];
   for (int k = 0; k < NE; ++k) if (P.epis[k].buf >= 0) uses[P.epis[k].buf].push_back(k);
   // Randomised interleaving: each trial advances one randomly chosen role by one unit at a time, so that any
   // ordering the hardware could produce between the roles is sampled (300 seeds).
   for (unsigned seed = 1; seed <= 300; ++seed) {
     unsigned rng = seed * 2654435761u;
     auto rnd = [&]() { rng ^= rng << 13; rng ^= rng >> 17; rng ^= rng << 5; return rng; };
-    int issued = 0, consumed = 0, mi = 0; int epi_done[3] = {0, 0, 0}; int commits[4] = {0,0,0,0}; int waited[3][4] = {{0}};
-    int ep[3] = {0, 0, 0}; int use_idx[4] = {0, 0, 0, 0};
+    int issued = 0, consumed = 0, mi = 0; int epi_done[3] = {0, 0, 0}; int commits[6] = {0,0,0,0,0,0}; int waited[3][6] = {{0}};
+    int ep[3] = {0, 0, 0}; int use_idx[6] = {0, 0, 0, 0, 0, 0};
     auto step_producer = [&]() {
       if (!(issued < (int)tiles.size() && issued - consumed < 3)) return false;
       const Tile& t = tiles[issued];
@@ -62,7 +62,8 @@ int main(int argc, char** argv){
       if (s.mma_dep_joint > 0 && epi_done[2] < s.mma_dep_joint) return 0;
       if (s.mma_dep_joint < 0 && (epi_done[0] < -s.mma_dep_joint || epi_done[1] < -s.mma_dep_joint || epi_done[2] < -s.mma_dep_joint)) return 0;
       if (issued < first_tile[mi] + n_tiles[mi]) return 0;
-      const int b = s.tmem_col / 128, u = use_idx[b];
+      // accumulator buffer id: the committing step names it (4 / 5 = upper halves of acc[h]); partial steps by column
+      const int b = s.commit == 1 ? s.commit_buf : s.tmem_col / 128, u = use_idx[b];
       if (u > 0) {
         const int prev = uses[b][u - 1];
         for (int g = 0; g < 3; ++g)

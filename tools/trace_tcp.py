@@ -57,3 +57,13 @@ def fine(name, off, n, per):
         print("   " + " ".join("%6d" % x for x in d[i:i + per]))
 fine("head->latent item, half 0: [tmem ld | z math + scratch stores | per plane group: template load, split, 4 stores ...]", 2048, 64, 12)
 fine("reconstruction item, half 0, per chunk: [ld issue | column sums of previous chunk | ld wait | math | planes | loop + prefetch]", 2048 + 64, 256, 5)
+
+# loop-level stamps of group 0 (fine-trace builds): per item [decoded | before acc wait | after acc wait | item done | fenced | barrier | published]
+lv = b[2048 + 512:2048 + 512 + 8 * E].reshape(E, 8)
+if (lv > 0).any():
+    print("group 0 item loop, SM cycles: item | prep | acc-wait | work | fence | bar | publish | -> next item decoded")
+    prev_end = None
+    rows = [(k, lv[k]) for k in range(E) if lv[k][0] > 0]
+    for n, (k, r) in enumerate(rows):
+        nxt = rows[n + 1][1][0] - r[6] if n + 1 < len(rows) else 0
+        print("  E%02d %6d %6d %6d %6d %6d %6d | %6d" % (k + 1, r[1] - r[0], r[2] - r[1], r[3] - r[2], r[4] - r[3], r[5] - r[4], r[6] - r[5], nxt))
