@@ -3,6 +3,6 @@
 set -x
 L=multi_modal_normative_modeling_b200/lib
 python tools/time_subsets.py quick
-NMB_LIB=$L/libnmb_L.so python tools/time_subsets.py quick
+NMB_LIB=$L/libnmb_W.so python tools/time_subsets.py quick
 python tools/time_subsets.py quick
-NMB_LIB=$L/libnmb_L.so python tools/time_subsets.py quick
+NMB_LIB=$L/libnmb_W.so python tools/time_subsets.py quick
