@@ -292,3 +292,48 @@ def test_cfg1_production_philox_draws_kfold_auc_vs_oracle():
     """The production path end to end: in-kernel Philox eps for training and for the sampled test-time z, against the
     oracle replaying the documented stream (oracle/philox.py)."""
     _kfold_auc_vs_oracle(("T1w_sMRI",), "poe", early_fusion=False, production_rng=True, d=150)
+
+
+def test_cfg5_scale_stress_properties():
+    """BASELINE configs[4] at FULL size (100 000 subjects x 1 000 features, 5 folds -> 80 000 training rows, 313
+    minibatches per epoch): too large for the CPU oracle, so parity is checked through size-independent properties --
+    the pipelined kernel against the FP32 engine on the same rows and draws (per-step losses), bit-determinism of a
+    whole epoch, the pipelined forward-only reconstruction against the generic engine on all 20 000 test rows, and
+    the multi-tile AUC path (20 000 rows > one 1 024-row tile) against exact pair counting on the host."""
+    from oracle import deviation as odev
+    from multi_modal_normative_modeling_b200 import EnsembleTrainer, MemberSpec, _lib, pack_rows, scoring
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    n_tr, n_te, d, c_dim, z = 80000, 20000, 1000, 29, 10
+
+    def rows(n):
+        x = torch.randn(n, d, device=dev, generator=g)
+        c = torch.zeros(n, c_dim, device=dev)
+        c[torch.arange(n, device=dev), torch.randint(0, 27, (n,), device=dev, generator=g)] = 1
+        c[torch.arange(n, device=dev), 27 + torch.randint(0, 2, (n,), device=dev, generator=g)] = 1
+        return pack_rows(x, c)
+    train, test = rows(n_tr), rows(n_te)
+    from multi_modal_normative_modeling_b200 import workloads
+    sd = workloads.init_state_dict(d, (110, 110), z, c_dim, 42)
+    mk = lambda: EnsembleTrainer([MemberSpec([d], [110, 110], z, c_dim, [train], seed=9, state_dict=sd),
+                                  MemberSpec([d], [110, 110], z, c_dim, [train], seed=10, state_dict=sd)], device=dev)
+    a, b, f = mk(), mk(), mk()
+    assert a.engine() == "tcgen05-pipelined" and a.steps_per_epoch == [313, 313]
+    la = a.train_steps(313, record_losses=True)                   # one full epoch incl. the ragged 128-row last batch
+    lb = b.train_steps(313, record_losses=True)
+    lf = f.train_steps(12, record_losses=True, flags=_lib.TRAIN_FP32)
+    torch.cuda.synchronize()
+    assert torch.equal(la, lb) and torch.equal(a.params, b.params)            # bit-deterministic
+    assert torch.isfinite(la).all() and float(la[:, -20:, 0].mean()) < float(la[:, :20, 0].mean())   # it trains
+    assert np.allclose(la[:, :12].cpu().numpy(), lf.cpu().numpy(), rtol=1e-4)   # same trajectory as the FP32 engine
+    xa, mua, _ = a.reconstruct([[test], [test]], mode="mean", want_latent=True)
+    xg, mug, _ = a.reconstruct([[test], [test]], mode="mean", want_latent=True, engine="tcs")
+    torch.cuda.synchronize()
+    assert float((xa[0][0] - xg[0][0]).abs().max()) < 2e-5 * max(1.0, float(xg[0][0].abs().max()))
+    assert float((mua[1] - mug[1]).abs().max()) < 2e-5 * max(1.0, float(mug[1].abs().max()))
+    _, _, subj = scoring.deviation([test], [xa[0][0]], want_roi=False)
+    lab = (torch.rand(n_te, device=dev, generator=g) < 0.3).to(torch.uint8)
+    auc, u2 = scoring.auc(subj, [lab], want_pairs=True)
+    want, n1, n0 = odev.auc_pairs(subj[0].cpu().numpy(), lab.cpu().numpy())
+    assert int(u2[0][0]) == want and float(auc[0][0]) == want / (2.0 * n1 * n0)
+    a.close(); b.close(); f.close()
