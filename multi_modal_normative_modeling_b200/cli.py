@@ -36,10 +36,31 @@ from sklearn.preprocessing import RobustScaler
 from . import scoring
 from .cVAE import cVAE_multimodal, cVAE_multimodal_endtoend
 from .ensemble import EnsembleTrainer, MemberSpec, pack_rows
+from . import prologue
 from .pipeline import covariate_onehots
 from .utils import generate_kfold_ids, get_column_name, get_datasets_name, get_hc_label, load_dataset
 
 MODEL_NAME = "supervised_cvae"
+
+# wall-clock seconds per phase of the programs (tools/time_cli.py reads it): where a CSV -> AUC run spends its time
+TIMINGS = {}
+
+
+class _phase:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        import time
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        self.t0 = time.perf_counter()
+
+    def __exit__(self, *exc):
+        import time
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        TIMINGS[self.name] = TIMINGS.get(self.name, 0.0) + time.perf_counter() - self.t0
 
 
 def add_common_args(p: argparse.ArgumentParser, train: bool):
@@ -58,6 +79,9 @@ def add_common_args(p: argparse.ArgumentParser, train: bool):
         p.add_argument("-TrainingClass", "--training_class", dest="training_class", default="nm", type=str)
         p.add_argument("--ensemble-seeds", dest="ensemble_seeds", type=int, default=1)
         p.add_argument("--nmmlp", action="store_true")
+    p.add_argument("--host-prologue", dest="host_prologue", action="store_true",
+                   help="RobustScaler / covariate bins / packing with sklearn + pandas on the host instead of the "
+                        "GPU prologue (bit-identical results)")
     return p
 
 
@@ -134,13 +158,20 @@ def train_main(args, root=None):
     for fold in range(args.n_splits):
         (model_dir / f"{fold:03d}").mkdir(exist_ok=True)
         xs, c, n_samples = [], None, None
-        for name, (tr, _) in _fold_frames(root, args, fold, names, kfold_dir, participants_path).items():
+        with _phase("train: read csv + merge (pandas)"):
+            fold_frames = _fold_frames(root, args, fold, names, kfold_dir, participants_path)
+        for name, (tr, _) in fold_frames.items():
             if nmmlp:
                 tr = tr.loc[tr["DIA"] == hc_label]                       # nmmlp :314
-            x = RobustScaler().fit_transform(tr[get_column_name(args.dataset_resourse, name)].values)
-            c = covariate_onehots(tr)                         # every modality feeds its own frame's one-hots (:126)
-            xs.append(pack_rows(torch.from_numpy(x.astype(np.float32)).to(dev), torch.from_numpy(c).to(dev)))
-            n_samples = x.shape[0]
+            cols = get_column_name(args.dataset_resourse, name)
+            n_samples = len(tr)
+            with _phase("train: scaler + covariate bins + packing"):
+                if getattr(args, "host_prologue", False) or n_samples > prologue.MAX_ROWS:
+                    x = RobustScaler().fit_transform(tr[cols].values)
+                    c = covariate_onehots(tr)                 # every modality feeds its own frame's one-hots (:126)
+                    xs.append(pack_rows(torch.from_numpy(x.astype(np.float32)).to(dev), torch.from_numpy(c).to(dev)))
+                else:                                         # GPU prologue: scaler fit + transform, rank bins, packing
+                    xs.append(prologue.frame_to_packed(tr, None, cols, dev)[0])
         spe = -(-n_samples // 256)
         lr_steps = None
         if nmmlp:
@@ -155,10 +186,12 @@ def train_main(args, root=None):
                                     state_dict={k: v.detach().clone() for k, v in init.items() if not k.startswith("mlp.")},
                                     tag=(fold, s_)))
     print("train model")
-    trainer = EnsembleTrainer(specs, device=dev)
+    with _phase("train: ensemble create"):
+        trainer = EnsembleTrainer(specs, device=dev)
     spe = trainer.steps_per_epoch
     # every member takes exactly `epochs` passes over its OWN rows, whatever its fold size (one launch)
-    losses = trainer.train_epochs(args.epochs, record_losses=True).cpu().numpy()
+    with _phase("train: fused training launch (all folds x seeds x epochs)"):
+        losses = trainer.train_epochs(args.epochs, record_losses=True).cpu().numpy()
     torch.cuda.synchronize(dev)
     logs = []
     for i, s in enumerate(specs):
@@ -209,13 +242,25 @@ def test_main(args, root=None):
             cols = get_column_name(args.dataset_resourse, name)
             if hc_only:
                 tr = tr.loc[tr["DIA"] == hc_label]             # nmmlp :455
-            scaler = RobustScaler().fit(tr[cols].values)       # fitted on TRAIN (test script :83-90)
-            x64.append(scaler.transform(te[cols].values))
-            c = covariate_onehots(te)                          # from the TEST set's own ranks (:93-97)
             frames.append(te)
-        # every modality is decoded with the LAST modality's one-hots, like the reference (test script :102, :109)
-        c_dev = torch.from_numpy(c).to(dev)
-        xcs = [pack_rows(torch.from_numpy(x.astype(np.float32)).to(dev), c_dev) for x in x64]
+            if getattr(args, "host_prologue", False) or max(len(tr), len(te)) > prologue.MAX_ROWS:
+                scaler = RobustScaler().fit(tr[cols].values)   # fitted on TRAIN (test script :83-90)
+                x64.append(scaler.transform(te[cols].values))
+                c = covariate_onehots(te)                      # from the TEST set's own ranks (:93-97)
+            else:                                              # GPU prologue (fit on train, applied to test)
+                _, pte, xte64, _ = prologue.frame_to_packed(tr, te, cols, dev)
+                x64.append(xte64.cpu().numpy())
+                xcs.append(pte)
+        if not xcs:
+            # every modality is decoded with the LAST modality's one-hots, like the reference (test script :102, :109)
+            c_dev = torch.from_numpy(c).to(dev)
+            xcs = [pack_rows(torch.from_numpy(x.astype(np.float32)).to(dev), c_dev) for x in x64]
+        else:
+            # (all modalities hold the same subjects in the same order, so every frame's covariate bins are the last one's;
+            #  the last modality's covariate columns are copied into the others to mirror the reference literally)
+            widths = [len(get_column_name(args.dataset_resourse, n)) for n in names]
+            for m_, d_ in enumerate(widths[:-1]):
+                xcs[m_][:, d_:d_ + 29] = xcs[-1][:, widths[-1]:widths[-1] + 29]
         dims = [len(get_column_name(args.dataset_resourse, n)) for n in names]
         specs.append(MemberSpec(dims, list(args.hz_para_list[:-1]), int(args.hz_para_list[-1]), 29, xcs,
                                 combine=args.combine, loss_kind="neg_mse" if nmmlp else "gauss_ll",

@@ -63,36 +63,65 @@ def _dev_i32(a, dev):
     return torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(dev)
 
 
-def robust_fit(x: torch.Tensor, idx: torch.Tensor):
-    """(center, scale) float64 [D] of rows idx of x -- RobustScaler().fit (nmb_robust_fit)."""
+def _ptr_n(idx, n_all):
+    return (idx.data_ptr(), idx.numel()) if idx is not None else (None, n_all)
+
+
+def robust_fit(x: torch.Tensor, idx: torch.Tensor = None):
+    """(center, scale) float64 [D] of rows idx of x (all rows if None) -- RobustScaler().fit (nmb_robust_fit)."""
     d = x.shape[1]
     center = torch.empty(d, dtype=torch.float64, device=x.device)
     scale = torch.empty(d, dtype=torch.float64, device=x.device)
+    ip, n = _ptr_n(idx, x.shape[0])
     with torch.cuda.device(x.device):
-        _lib.check(_lib.load().nmb_robust_fit(x.data_ptr(), x.stride(0), d, idx.data_ptr(), idx.numel(), center.data_ptr(),
+        _lib.check(_lib.load().nmb_robust_fit(x.data_ptr(), x.stride(0), d, ip, n, center.data_ptr(),
                                               scale.data_ptr(), _stream_ptr(x.device)), "nmb_robust_fit")
     return center, scale
 
 
 def rank_bins(v: torch.Tensor, idx: torch.Tensor, q: int) -> torch.Tensor:
     """``pd.qcut(v[idx].rank(method='first'), q, labels=False)`` as int32 [len(idx)] (nmb_rank_bins)."""
-    n = idx.numel()
+    ip, n = _ptr_n(idx, v.shape[0])
     edges = torch.from_numpy(qcut_edges(n, q)).to(v.device)
     bins = torch.empty(n, dtype=torch.int32, device=v.device)
     with torch.cuda.device(v.device):
-        _lib.check(_lib.load().nmb_rank_bins(v.data_ptr(), idx.data_ptr(), n, edges.data_ptr(), q, bins.data_ptr(),
+        _lib.check(_lib.load().nmb_rank_bins(v.data_ptr(), ip, n, edges.data_ptr(), q, bins.data_ptr(),
                                              _stream_ptr(v.device)), "nmb_rank_bins")
     return bins
 
 
 def pack_scaled(x, idx, center, scale, age_bin, sex_bin) -> torch.Tensor:
-    d, n = x.shape[1], idx.numel()
+    d = x.shape[1]
+    ip, n = _ptr_n(idx, x.shape[0])
     out = torch.empty((n, _lib.packed_row_stride(d, N_AGE_BINS + N_SEX_BINS)), dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
-        _lib.check(_lib.load().nmb_pack_rows_scaled(x.data_ptr(), x.stride(0), d, idx.data_ptr(), n, center.data_ptr(),
+        _lib.check(_lib.load().nmb_pack_rows_scaled(x.data_ptr(), x.stride(0), d, ip, n, center.data_ptr(),
                                                     scale.data_ptr(), age_bin.data_ptr(), N_AGE_BINS, sex_bin.data_ptr(),
                                                     N_SEX_BINS, out.data_ptr(), _stream_ptr(x.device)), "nmb_pack_rows_scaled")
     return out
+
+
+MAX_ROWS = 8192       # rows per fold the shared-memory sort of nmb_robust_fit / nmb_rank_bins holds
+
+
+def frame_to_packed(train_df: pd.DataFrame, test_df, cols, device, center_scale=None):
+    """The CLI flavour: the fold's frames come out of ``load_dataset`` (CSV + merges stay pandas: the file contract);
+    everything after that -- RobustScaler fit on train / transform, covariate bins from each frame's own ranks,
+    packing -- runs on the device.  Returns (packed_train, packed_test or None, scaled_test_float64 or None,
+    (center, scale)).  test_df may be None."""
+    dev = torch.device(device)
+    up = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
+
+    def bins(df):
+        return (rank_bins(up(df["AGE"].to_numpy()), None, N_AGE_BINS), rank_bins(up(df["PTGENDER"].to_numpy()), None, N_SEX_BINS))
+    xtr = up(train_df[cols].to_numpy())
+    center, scale = center_scale or robust_fit(xtr)
+    ptr = pack_scaled(xtr, None, center, scale, *bins(train_df))
+    if test_df is None:
+        return ptr, None, None, (center, scale)
+    xte = up(test_df[cols].to_numpy())
+    pte = pack_scaled(xte, None, center, scale, *bins(test_df))
+    return ptr, pte, ((xte - center) / scale), (center, scale)
 
 
 def upload_raw(subjects: pd.DataFrame, features: Dict[str, pd.DataFrame], columns: Dict[str, List[str]], device):
