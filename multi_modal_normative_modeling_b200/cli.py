@@ -79,6 +79,8 @@ def add_common_args(p: argparse.ArgumentParser, train: bool):
         p.add_argument("-TrainingClass", "--training_class", dest="training_class", default="nm", type=str)
         p.add_argument("--ensemble-seeds", dest="ensemble_seeds", type=int, default=1)
         p.add_argument("--nmmlp", action="store_true")
+    p.add_argument("--fast-csv", dest="fast_csv", action="store_true",
+                   help="write the deviation CSV families with Arrow's CSV writer instead of DataFrame.to_csv")
     p.add_argument("--host-prologue", dest="host_prologue", action="store_true",
                    help="RobustScaler / covariate bins / packing with sklearn + pandas on the host instead of the "
                         "GPU prologue (bit-identical results)")
@@ -98,6 +100,19 @@ def fill_defaults(args):
     if getattr(args, "epochs", 0) is None:
         args.epochs = 200
     return args
+
+
+def write_csv(df: pd.DataFrame, path, fast: bool = False):
+    """The per-modality CSV families of the test program (test script :116-178).  fast=True: Arrow's multithreaded CSV
+    writer (same columns, header and row order; every float written with all the digits of its shortest round-trip
+    representation, in positional instead of scientific notation) -- 6x faster than ``DataFrame.to_csv``, which is what
+    the test program spends its time in.  Default: pandas, byte-identical to what the reference writes."""
+    if fast:
+        import pyarrow as pa
+        import pyarrow.csv as pc
+        pc.write_csv(pa.Table.from_pandas(df, preserve_index=False), str(path), pc.WriteOptions(quoting_style="needed"))
+    else:
+        df.to_csv(path, index=False)
 
 
 def _paths(root: Path, resource: str):
@@ -227,6 +242,7 @@ def test_main(args, root=None):
     if args.combine is None:
         raise ValueError(f"Unknown procedure: {args.procedure}")
     nmmlp = bool(getattr(args, "nmmlp", False))
+    fast_csv = bool(getattr(args, "fast_csv", False))
     specs, test_xc, test_frames, test_x64 = [], [], [], []
     for fold in range(args.n_splits):
         fold_dir = model_dir / f"{fold:03d}"
@@ -293,14 +309,14 @@ def test_main(args, root=None):
                 columns=dict(zip(cols, map(str, range(1, len(cols) + 1)))))
             for key, body in tables.items():
                 df = pd.concat([cov.reset_index(drop=True), body], axis=1)
-                df.to_csv(out_dir / f"{key}_{name}.csv", index=False)
+                write_csv(df, out_dir / f"{key}_{name}.csv", fast_csv)
                 all_frames[name][key].append(df)
             k += 1
     for name in names:
         d = deviation_dir / name
         d.mkdir(exist_ok=True, parents=True)
         for key, parts in all_frames[name].items():
-            pd.concat(parts, ignore_index=True).to_csv(d / f"{key}_{name}.csv", index=False)
+            write_csv(pd.concat(parts, ignore_index=True), d / f"{key}_{name}.csv", fast_csv)
     if nmmlp:
         # nmmlp :515-523: "diagnosis" = modality-averaged per-subject deviation (nmb_mean_rows), HC = 0 / other = 1
         hc_label = get_hc_label(args.dataset_resourse)

@@ -232,3 +232,22 @@ def test_member_sharding_and_all_gather_gloo(tmp_path, n_members):
             members = [8 * f + 2 * m + s for m in range(4)]
             want = torch.arange(4, dtype=torch.float64) + 10.0 * sum(members) / 4
             assert torch.allclose(v, want) and torch.equal(v, r1["avg"][(f, s)])
+
+
+def test_fast_csv_writer_keeps_the_file_contract(tmp_path):
+    """cli.write_csv(fast=True) (Arrow) vs DataFrame.to_csv: same header, rows and dtypes; every value parses back to the
+    written float exactly with a round-trip parser (pandas' default fast parser may differ from it by one ulp on a few
+    long literals -- for either file)."""
+    import pandas as pd
+    from multi_modal_normative_modeling_b200 import cli
+    rng = np.random.RandomState(0)
+    df = pd.DataFrame(rng.randn(300, 20).astype(np.float32).astype(np.float64) ** 2, columns=[f"ROI {i}, left" for i in range(20)])
+    df.insert(0, "participant_id", [f"sub-{i:04d}" for i in range(300)])
+    df.insert(1, "DIA", rng.randint(0, 2, 300))
+    cli.write_csv(df, tmp_path / "a.csv", fast=False)
+    cli.write_csv(df, tmp_path / "b.csv", fast=True)
+    a = pd.read_csv(tmp_path / "a.csv", float_precision="round_trip")
+    b = pd.read_csv(tmp_path / "b.csv", float_precision="round_trip")
+    assert list(a.columns) == list(b.columns) == list(df.columns)
+    assert a.equals(b) and a.dtypes.equals(b.dtypes)
+    assert np.array_equal(b.iloc[:, 2:].to_numpy(), df.iloc[:, 2:].to_numpy())
