@@ -615,8 +615,8 @@ def run_b200(args):
                              "kernel_ms": kernel_ms, "algorithmic_flops_per_launch": local_flops_per_step,
                              "peak_source": peak_src, "traffic_note": traffic_note,
                              "kernel_ms_note": "CUDA events bracket the four launches of a training call on rank 0 (xprep, state "
-                                               "conversion in, persistent kernel, state conversion out); the persistent kernel is "
-                                               "~0.92 of it (profiles/*launch_list_summary.txt)",
+                                               "conversion in, persistent kernel, state conversion out; with resident state the conversions run once "
+                                               "per job); the persistent kernel is ~0.96 of it (profiles/r02_launch_list_summary.txt)",
                              "hbm": None if not (traffic and world == 1) else {
                                  "achieved_GBps": traffic / (kernel_ms * 1e-3) / 1e9, "peak_GBps": peaks.get("hbm_gbs"),
                                  "frac": (traffic / (kernel_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]) if peaks.get("hbm_gbs") else None,

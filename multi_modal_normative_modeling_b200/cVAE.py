@@ -144,7 +144,7 @@ class _FusedBase(nn.Module):
     combine rule; rows are passed per call."""
 
     _loss_kind = "gauss_ll"
-    _ENGINE_KEYS = ("_engines", "_pending", "_last", "_views_cache")
+    _ENGINE_KEYS = ("_engines", "_pending", "_last", "_views_cache", "_step_tensor")
 
     def _trainable(self):
         """(name in packed layout, Parameter) in optimizer1 order."""
@@ -300,9 +300,14 @@ class _FusedBase(nn.Module):
             vc = (eng._views(0, m), eng._views(0, v))
             object.__setattr__(self, "_views_cache", vc)
         st = self.optimizer1.state
-        for name, p in named:
-            st[p] = {"step": torch.tensor(float(t)), "exp_avg": vc[0][name].view(p.shape),
-                     "exp_avg_sq": vc[1][name].view(p.shape)}
+        step_t = self.__dict__.get("_step_tensor")
+        if step_t is None or len(st) != len(named):          # built once; afterwards only the shared step counter moves
+            step_t = torch.tensor(float(t))
+            object.__setattr__(self, "_step_tensor", step_t)
+            for name, p in named:
+                st[p] = {"step": step_t, "exp_avg": vc[0][name].view(p.shape), "exp_avg_sq": vc[1][name].view(p.shape)}
+        else:
+            step_t.fill_(float(t))
 
     def __getstate__(self):      # torch.save(model): engines are not picklable and are rebuilt lazily
         d = self.__dict__.copy()

@@ -580,9 +580,19 @@ int nmb_ensemble_peek(NmbEnsemble* e, int32_t member, float* mu, float* logvar, 
   cudaStream_t st = (cudaStream_t)stream;
   CU(cudaSetDevice(e->device));
   MemberDev md;
-  CU(cudaMemcpyAsync(&md, e->members_dev + member, sizeof(MemberDev), cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
-  if (md.last_slot < 0) return fail("member has not run a step yet");
+  if (e->n_members <= e->n_sm) {
+    // one CTA per member, dealt statically by every engine: the scratch slot is the member index and the rows of the last
+    // step follow from the host's step count -- no device round trip, the call stays asynchronous on the stream
+    if (e->steps_host[member] < 1) return fail("member has not run a step yet");
+    const MemberDev& h = e->members_host[member];
+    const long long spe = (h.n_rows + h.batch - 1) / h.batch, pos = (e->steps_host[member] - 1) % spe;
+    md.last_slot = member;
+    md.last_rows = (int)std::min<long long>(h.batch, h.n_rows - pos * h.batch);
+  } else {
+    CU(cudaMemcpyAsync(&md, e->members_dev + member, sizeof(MemberDev), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (md.last_slot < 0) return fail("member has not run a step yet");
+  }
   const ArchDesc& a = e->archs[e->arch_idx[member]];
   const float* S = e->scratch + (long long)md.last_slot * e->slot_floats;
   if (rows) *rows = md.last_rows;
