@@ -194,7 +194,11 @@ enum { NMB_RECON_MEAN = 0, NMB_RECON_SAMPLE = 1,
                                 cVAE.decode (cVAE.py:197-206, 426-428, 1135-1136); mu / logvar are not produced */,
        NMB_RECON_FP32 = 16 /* OR into `mode`: FP32 FFMA engine instead of the default tcgen05 (BF16x3) engine */,
        NMB_RECON_TC_SIMPLE = 32 /* OR into `mode`: generic tcgen05 engine instead of the pipelined forward-only program
-                                   (the default wherever the pipelined training kernel covers the architecture) */ };
+                                   (the default wherever the pipelined training kernel covers the architecture) */,
+       NMB_RECON_KEEP_PLANES = 64 /* OR into `mode`: the caller has not written NmbMember.params since the last
+                                   nmb_ensemble_train* call, so the BF16 weight planes the training kernel left behind are
+                                   current and are not rebuilt (honoured only if that call ran the pipelined engine and
+                                   nothing invalidated the ensemble since) */ };
 /* Test-time reconstruction for every member on its own rows:
  *   mode MEAN   : decode(mu)                       -- cVAE.pred_recon, cVAE.py:549-555
  *   mode SAMPLE : decode(mu + eps*exp(logvar/2))   -- cVAE_multimodal.pred_recon, cVAE.py:1198-1208

@@ -12,7 +12,7 @@ COMBINE = {"poe": 0, "gpoe": 1, "moe": 2, "mopoe": 3}
 LOSS = {"gauss_ll": 0, "neg_mse": 1}
 SLOT_ENC, SLOT_ENC_MEAN, SLOT_ENC_LOGVAR, SLOT_DEC, SLOT_DEC_MEAN, SLOT_LOGVAR_OUT, SLOT_ALPHA = range(7)
 TRAIN_NO_ADAM, TRAIN_WRITE_GRADS, TRAIN_KEEP_ACTS, TRAIN_FP32, TRAIN_TC_SIMPLE, TRAIN_RESIDENT = 1, 2, 4, 8, 16, 32
-RECON_MEAN, RECON_SAMPLE, RECON_GIVEN_Z, RECON_FP32, RECON_TC_SIMPLE = 0, 1, 2, 16, 32
+RECON_MEAN, RECON_SAMPLE, RECON_GIVEN_Z, RECON_FP32, RECON_TC_SIMPLE, RECON_KEEP_PLANES = 0, 1, 2, 16, 32, 64
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libnmb.so")
 

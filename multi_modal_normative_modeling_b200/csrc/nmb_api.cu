@@ -157,6 +157,7 @@ struct NmbEnsemble {
   // NMB_TRAIN_RESIDENT: the lane-major master state (and the weight planes) stay authoritative between calls
   bool master_valid = false;                 // master holds the current p, m, v
   bool caller_stale = false;                 // ... and the caller's row-major buffers have not been refreshed from it
+  bool planes_valid = false;                 // the BF16 weight planes match the parameters (left by the last pipelined train call)
   std::vector<long long> steps_host;         // host mirror of MemberDev.steps_done (every step goes through this API)
   std::vector<long long> n_lr_steps;         // length of each member's lr_steps schedule (0 = none)
 };
@@ -541,9 +542,11 @@ static int train_common(NmbEnsemble* e, int64_t n, int n_is_epochs, const float*
                         e->epis_p.data(), e->ep_off.data(), e->ep_cnt.data(), e->ep_first.data(), e->max_mlayers, e->n_sm,
                         gather_in, !resident, (cudaStream_t)stream));
     if (adam) { e->master_valid = resident; e->caller_stale = resident; }
+    e->planes_valid = true;
   } else {
     if (int rc = ensure_synced(e, (cudaStream_t)stream)) return rc;
     e->master_valid = false;
+    e->planes_valid = false;
     CU(launch_train(t, (cudaStream_t)stream));
   }
   for (int i = 0; i < e->n_members; ++i) e->steps_host[i] += member_steps(t, e->members_host[i]);
@@ -561,6 +564,7 @@ int nmb_ensemble_invalidate(NmbEnsemble* e, void* stream) {
   CU(cudaSetDevice(e->device));
   if (int rc = ensure_synced(e, (cudaStream_t)stream)) return rc;      // nothing the caller has not seen may be dropped
   e->master_valid = false;
+  e->planes_valid = false;
   return 0;
 }
 
@@ -616,7 +620,8 @@ int nmb_ensemble_reconstruct(NmbEnsemble* e, const float* const* xc, const int32
   if (!e || !xc || !n_rows || !xhat) return fail("null argument");
   const int fp32 = (mode & NMB_RECON_FP32) ? 1 : 0;
   const int tc_simple = (mode & NMB_RECON_TC_SIMPLE) ? 1 : 0;
-  mode &= ~(NMB_RECON_FP32 | NMB_RECON_TC_SIMPLE);
+  const bool keep_planes = (mode & NMB_RECON_KEEP_PLANES) && e && e->planes_valid;
+  mode &= ~(NMB_RECON_FP32 | NMB_RECON_TC_SIMPLE | NMB_RECON_KEEP_PLANES);
   if (mode != NMB_RECON_MEAN && mode != NMB_RECON_SAMPLE && mode != NMB_RECON_GIVEN_Z) return fail("bad mode");
   if (mode == NMB_RECON_GIVEN_Z) {
     if (!eps) return fail("NMB_RECON_GIVEN_Z needs z in eps[]");
@@ -717,7 +722,7 @@ int nmb_ensemble_reconstruct(NmbEnsemble* e, const float* const* xc, const int32
     t.order = e->order_dev;
     CU(launch_recon_tcp(t, e->progs_fwd_dev, e->progs_dev, e->mtc_dev, e->stash, e->stash_bytes, e->msteps_fwd.data(),
                         e->msf_off.data(), e->msf_cnt.data(), (int)e->msf_off.size(), e->epis_fwd.data(), e->epf_off.data(),
-                        e->epf_cnt.data(), e->epf_first.data(), e->max_mlayers, mode == NMB_RECON_MEAN ? 1 : 2, b.at<tcp::ReconTc>(o_r),
+                        e->epf_cnt.data(), e->epf_first.data(), keep_planes ? 0 : e->max_mlayers, mode == NMB_RECON_MEAN ? 1 : 2, b.at<tcp::ReconTc>(o_r),
                         b.at<tcp::ReconWork>(o_w), (int)work.size(), e->n_sm, st));
     CU(b.release(st));
     return 0;

@@ -1786,10 +1786,12 @@ cudaError_t launch_recon_tcp(const TrainLaunch& t, const tcp::ProgramDev* progs,
     if (e != cudaSuccess) return e;
   }
   // the caller may have changed the parameters since the last call: rebuild the BF16 planes (layout of the TRAINING
-  // program, shared by both programs) from the fp32 parameters
-  tcp::PrepArgs pa{t.members, train_progs, mtc, nullptr, 0, t.n_members, 0};
-  const dim3 pgrid((unsigned)t.n_members, (unsigned)max_mlayers);
-  tcp::tcp_move_kernel<<<pgrid, 256, 0, st>>>(pa, 1);
+  // program, shared by both programs) from the fp32 parameters (max_mlayers == 0: the caller vouches for the planes)
+  if (max_mlayers > 0) {
+    tcp::PrepArgs pa{t.members, train_progs, mtc, nullptr, 0, t.n_members, 0};
+    const dim3 pgrid((unsigned)t.n_members, (unsigned)max_mlayers);
+    tcp::tcp_move_kernel<<<pgrid, 256, 0, st>>>(pa, 1);
+  }
   tcp::LaunchP L;
   L.n_chunks = 1;
   L.t = t; L.progs = progs; L.mtc = mtc; L.stash = stash; L.stash_bytes = stash_bytes;

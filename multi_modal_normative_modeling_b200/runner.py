@@ -72,7 +72,8 @@ class EnsembleRunner:
         # the reference's test script decodes a SAMPLED z (cVAE_multimodal.pred_recon, cVAE.py:1198-1208) for the test
         # rows; the normative statistics of the training rows use the same mode
         self.scorer = scoring.DeviationScorer(self.trainer, [s.xc for s in self.wl.specs], self.wl.test_xc,
-                                              self.wl.train_hc_mask, self.wl.test_labels, mode=score_mode)
+                                              self.wl.train_hc_mask, self.wl.test_labels, mode=score_mode,
+                                              params_untouched=True)      # the runner owns the trainer: nobody writes its tensors
         self.n_test_all = [hw.folds[f].test_x[name].shape[0] for f, name, _ in self.grid]
         self.d_max = max(hw.dims.values())
         self.n_test_max = max(self.n_test_all)

@@ -149,11 +149,15 @@ class DeviationScorer:
     ROI z-score and of the subject score -- six libnmb launches, no per-member Python work.
     Segments are (member, modality) pairs in member-major order."""
 
-    def __init__(self, trainer, train_xc, test_xc, train_hc_mask, test_labels, mode: str = "mean"):
+    def __init__(self, trainer, train_xc, test_xc, train_hc_mask, test_labels, mode: str = "mean",
+                 params_untouched: bool = False):
+        """params_untouched: the caller promises not to write the trainer's packed parameter tensors between training
+        and scoring, so the weight planes the training kernel left behind are reused (NMB_RECON_KEEP_PLANES) instead of
+        being rebuilt for each of the two reconstruction launches."""
         self.tr = trainer
         self.lib = _lib.load()
         self.dev = trainer.device
-        self.mode = _lib.RECON_MEAN if mode == "mean" else _lib.RECON_SAMPLE
+        self.mode = (_lib.RECON_MEAN if mode == "mean" else _lib.RECON_SAMPLE) | (_lib.RECON_KEEP_PLANES if params_untouched else 0)
         n = trainer.n
         dev = self.dev
         self._keep = [train_xc, test_xc, train_hc_mask, test_labels]

@@ -147,3 +147,29 @@ def test_resident_state_between_calls_equals_converting_every_call(workload):
     c.sync(); torch.cuda.synchronize()
     assert torch.equal(c.state_dict(0)["decoder_list.0.decoder_mean_layer.bias"], a.state_dict(0)["decoder_list.0.decoder_mean_layer.bias"])
     a.close(); b.close(); c.close()
+
+
+def test_reconstruct_reusing_the_training_kernels_weight_planes(workload):
+    """NMB_RECON_KEEP_PLANES: after a pipelined training call the planes are current, so skipping their rebuild gives
+    the same bits; after the parameters were replaced (load_state_dict -> invalidate) the flag is ignored."""
+    from multi_modal_normative_modeling_b200 import EnsembleTrainer, scoring
+    hw, wl = workload
+    dev = torch.device("cuda", 0)
+    idx = list(range(0, len(wl.specs), 8))
+    specs = [wl.specs[i] for i in idx]
+    tr = EnsembleTrainer(specs, device=dev)
+    tr.train_steps(6, resident=True)
+    args = ([s.xc for s in specs], [wl.test_xc[i] for i in idx], [wl.train_hc_mask[i] for i in idx], [wl.test_labels[i] for i in idx])
+    a = scoring.DeviationScorer(tr, *args, mode="sample").run()
+    b = scoring.DeviationScorer(tr, *args, mode="sample", params_untouched=True).run()
+    torch.cuda.synchronize()
+    assert torch.equal(a.xhat_test, b.xhat_test) and torch.equal(a.z, b.z) and torch.equal(a.auc_roi, b.auc_roi)
+    other = EnsembleTrainer(specs, device=dev)
+    other.train_steps(2)
+    for i in range(len(specs)):
+        tr.load_state_dict(i, other.state_dict(i))          # new weights: the kept planes are stale and must not be used
+    c = scoring.DeviationScorer(tr, *args, mode="sample", params_untouched=True).run()
+    d = scoring.DeviationScorer(other, *args, mode="sample").run()
+    torch.cuda.synchronize()
+    assert torch.equal(c.xhat_test, d.xhat_test) and not torch.equal(c.xhat_test, a.xhat_test)
+    tr.close(); other.close()

@@ -10,7 +10,7 @@ hw = workloads.build_host_workload()
 wl = workloads.to_device(hw, dev, n_seeds=24)
 tr = EnsembleTrainer(wl.specs, device=dev)
 tr.train_steps(8)
-sc = scoring.DeviationScorer(tr, [s.xc for s in wl.specs], wl.test_xc, wl.train_hc_mask, wl.test_labels)
+sc = scoring.DeviationScorer(tr, [s.xc for s in wl.specs], wl.test_xc, wl.train_hc_mask, wl.test_labels, mode="sample", params_untouched=True)
 for _ in range(3):
     sc.run(); sc.member_records()
 torch.cuda.synchronize()
