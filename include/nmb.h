@@ -211,6 +211,14 @@ int nmb_ensemble_reconstruct(NmbEnsemble* ens, const float* const* xc, const int
                              int32_t mode, const float* const* eps, float* const* xhat,
                              float* const* mu, float* const* logvar, void* stream);
 
+/* The same for `n_sets` row sets per member in ONE launch (e.g. the training rows for the normative statistics and the
+ * test rows of the test script, :83-113): entry (s, i) of every table sits at index s * n_members + i, for xc / xhat at
+ * (s * n_members + i) * NMB_MAX_MOD + m.  Results are identical to n_sets separate calls; one work queue instead of
+ * n_sets keeps the tail of the launch short. */
+int nmb_ensemble_reconstruct_sets(NmbEnsemble* ens, int32_t n_sets, const float* const* xc, const int32_t* n_rows,
+                                  int32_t mode, const float* const* eps, float* const* xhat, float* const* mu,
+                                  float* const* logvar, void* stream);
+
 /* ---- deviation scoring (streaming, HBM-bound) --------------------------------------- */
 /* Batched over `n_seg` independent (member, modality) segments; tables are HOST arrays of
  * device pointers / sizes. x rows have stride ldx (packed rows) -- only the first d columns

@@ -614,10 +614,13 @@ int nmb_ensemble_peek(NmbEnsemble* e, int32_t member, float* mu, float* logvar, 
   return 0;
 }
 
-int nmb_ensemble_reconstruct(NmbEnsemble* e, const float* const* xc, const int32_t* n_rows, int32_t mode,
-                             const float* const* eps, float* const* xhat, float* const* mu, float* const* logvar,
-                             void* stream) {
-  if (!e || !xc || !n_rows || !xhat) return fail("null argument");
+// n_sets row sets per member in one launch: entry (s, i) of every table sits at s * n_members + i (xc / xhat:
+// (s * n_members + i) * NMB_MAX_MOD + m)
+static int reconstruct_sets(NmbEnsemble* e, int n_sets, const float* const* xc, const int32_t* n_rows, int32_t mode,
+                            const float* const* eps, float* const* xhat, float* const* mu, float* const* logvar,
+                            void* stream) {
+  if (!e || !xc || !n_rows || !xhat || n_sets < 1) return fail("null argument");
+  const int32_t mode_in = mode;
   const int fp32 = (mode & NMB_RECON_FP32) ? 1 : 0;
   const int tc_simple = (mode & NMB_RECON_TC_SIMPLE) ? 1 : 0;
   const bool keep_planes = (mode & NMB_RECON_KEEP_PLANES) && e && e->planes_valid;
@@ -625,24 +628,35 @@ int nmb_ensemble_reconstruct(NmbEnsemble* e, const float* const* xc, const int32
   if (mode != NMB_RECON_MEAN && mode != NMB_RECON_SAMPLE && mode != NMB_RECON_GIVEN_Z) return fail("bad mode");
   if (mode == NMB_RECON_GIVEN_Z) {
     if (!eps) return fail("NMB_RECON_GIVEN_Z needs z in eps[]");
-    for (int i = 0; i < e->n_members; ++i) if (n_rows[i] > 0 && !eps[i]) return fail("NMB_RECON_GIVEN_Z: null z entry");
+    for (int i = 0; i < n_sets * e->n_members; ++i) if (n_rows[i] > 0 && !eps[i]) return fail("NMB_RECON_GIVEN_Z: null z entry");
   }
   cudaStream_t st = (cudaStream_t)stream;
   CU(cudaSetDevice(e->device));
   if (int rc = ensure_synced(e, st)) return rc;       // the planes / generic engines read the caller-layout parameters
   std::vector<ReconItem> items;
-  const int n = e->n_members;
+  const int nm = e->n_members;
+  const int n = n_sets * nm;                       // row sets x members; member of entry i = i % nm
   for (int i = 0; i < n; ++i) {
     if (n_rows[i] < 0) return fail("negative n_rows");
-    const ArchDesc& a = e->archs[e->arch_idx[i]];
+    const ArchDesc& a = e->archs[e->arch_idx[i % nm]];
     for (int m = 0; m < a.M; ++m) if (n_rows[i] > 0 && !xc[i * NMB_MAX_MOD + m]) return fail("null xc entry");
     for (int r = 0; r < n_rows[i]; r += kMaxBatch) {
-      ReconItem it; it.member = i; it.row0 = r; it.rows = n_rows[i] - r < kMaxBatch ? n_rows[i] - r : kMaxBatch;
+      ReconItem it; it.member = i % nm; it.row0 = r; it.rows = n_rows[i] - r < kMaxBatch ? n_rows[i] - r : kMaxBatch;
       items.push_back(it);
     }
   }
   if (items.empty()) return 0;
-  if (e->tcp_ok && e->fwd_ok && !fp32 && !tc_simple && mode != NMB_RECON_GIVEN_Z) {
+  const bool use_tcp = e->tcp_ok && e->fwd_ok && !fp32 && !tc_simple && mode != NMB_RECON_GIVEN_Z;
+  if (!use_tcp && n_sets > 1) {           // the generic engines take one row set per launch
+    for (int s = 0; s < n_sets; ++s) {
+      const size_t o = (size_t)s * nm;
+      if (int rc = reconstruct_sets(e, 1, xc + o * NMB_MAX_MOD, n_rows + o, mode_in, eps ? eps + o : nullptr,
+                                    xhat + o * NMB_MAX_MOD, mu ? mu + o : nullptr, logvar ? logvar + o : nullptr, stream))
+        return rc;
+    }
+    return 0;
+  }
+  if (use_tcp) {
     // ---- pipelined forward-only program (the training kernel's operand pipeline, forward half) ----
     struct Key { const float* xc; int n_rows, ldx, k_valid, z, c; size_t x_off, c_off; };
     std::vector<Key> keys;
@@ -652,7 +666,7 @@ int nmb_ensemble_reconstruct(NmbEnsemble* e, const float* const* xc, const int32
     int max_blocks = 1;
     auto carve = [&](size_t bytes) { size_t o = need; need += (bytes + 1023) & ~size_t(1023); return o; };
     for (int i = 0; i < n; ++i) {
-      const ArchDesc& a = e->archs[e->arch_idx[i]];
+      const ArchDesc& a = e->archs[e->arch_idx[i % nm]];
       tcp::ReconTc& r = rtc[i];
       std::memset(&r, 0, sizeof(r));
       r.n_rows = n_rows[i];
@@ -703,11 +717,11 @@ int nmb_ensemble_reconstruct(NmbEnsemble* e, const float* const* xc, const int32
     std::vector<int> order(n);
     std::iota(order.begin(), order.end(), 0);
     std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
-      return e->archs[e->arch_idx[x]].n_params > e->archs[e->arch_idx[y]].n_params; });
+      return e->archs[e->arch_idx[x % nm]].n_params > e->archs[e->arch_idx[y % nm]].n_params; });
     std::vector<tcp::ReconWork> work;
     for (int i : order) {
       const int tiles = (n_rows[i] + kMaxBatch - 1) / kMaxBatch;
-      for (int t0 = 0; t0 < tiles; t0 += 2) work.push_back(tcp::ReconWork{i, t0, tiles - t0 < 2 ? tiles - t0 : 2});
+      for (int t0 = 0; t0 < tiles; t0 += 2) work.push_back(tcp::ReconWork{i % nm, t0, tiles - t0 < 2 ? tiles - t0 : 2, i});
     }
     Blob b;
     const size_t o_x = b.add(xitems.data(), sizeof(tcp::XPrepItem) * xitems.size());
@@ -746,6 +760,18 @@ int nmb_ensemble_reconstruct(NmbEnsemble* e, const float* const* xc, const int32
   CU(launch_recon(t, st));
   CU(b.release(st));
   return 0;
+}
+
+int nmb_ensemble_reconstruct(NmbEnsemble* e, const float* const* xc, const int32_t* n_rows, int32_t mode,
+                             const float* const* eps, float* const* xhat, float* const* mu, float* const* logvar,
+                             void* stream) {
+  return reconstruct_sets(e, 1, xc, n_rows, mode, eps, xhat, mu, logvar, stream);
+}
+
+int nmb_ensemble_reconstruct_sets(NmbEnsemble* e, int32_t n_sets, const float* const* xc, const int32_t* n_rows, int32_t mode,
+                                  const float* const* eps, float* const* xhat, float* const* mu, float* const* logvar,
+                                  void* stream) {
+  return reconstruct_sets(e, n_sets, xc, n_rows, mode, eps, xhat, mu, logvar, stream);
 }
 
 static int seg_common(int32_t n_seg, const int32_t* n_rows, const int32_t* d, int* max_rows, int* max_d) {

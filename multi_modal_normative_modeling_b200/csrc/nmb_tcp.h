@@ -284,7 +284,7 @@ struct ReconTc {
   const float* eps;                            // injected draws [n_rows][Z] or NULL (Philox stream 1)
   int n_rows;
 };
-struct ReconWork { int member, tile0, n_tiles; };   // tiles of 256 rows
+struct ReconWork { int member, tile0, n_tiles, rt; };   // tiles of 256 rows; rt = index of the row set's ReconTc
 
 // One dataset (packed fp32 rows of one modality) to be re-tiled into 128-row blocks per (minibatch, half).
 struct XPrepItem {

@@ -47,6 +47,7 @@ struct Ctrl {
   int chunk_i0, chunk_n;                 // launch-relative first step and step count of the current work item
   long long chunk_s0;                    // member-global index of its first step
   RowSet rs;                             // rows of the current work item
+  int rt_idx;                            // reconstruction launch: index of the work item's row set (ReconTc)
   float red[40];
 };
 
@@ -1468,7 +1469,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) train_tcp_kernel(const __grid_co
       if (it < n_items && recon) {          // forward-only launch: (member, range of 256-row tiles), no cross-item order
         const ReconWork rw = L.rwork[it];
         mi = rw.member;
-        ctl->chunk_i0 = rw.tile0; ctl->chunk_n = rw.n_tiles; ctl->chunk_s0 = rw.tile0;
+        ctl->chunk_i0 = rw.tile0; ctl->chunk_n = rw.n_tiles; ctl->chunk_s0 = rw.tile0; ctl->rt_idx = rw.rt;
       } else if (it < n_items) {
         const int chunk = it / t.n_members;
         mi = dynamic ? t.order[it - chunk * t.n_members] : it;
@@ -1490,7 +1491,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) train_tcp_kernel(const __grid_co
       }
       ctl->member = mi;
       if (mi < t.n_members) {
-        if (recon) { ctl->rs.n_rows = L.rtc[mi].n_rows; ctl->rs.batch = 256; ctl->rs.n_half = 2; }
+        if (recon) { ctl->rs.n_rows = L.rtc[ctl->rt_idx].n_rows; ctl->rs.batch = 256; ctl->rs.n_half = 2; }
         else { ctl->rs.n_rows = t.members[mi].n_rows; ctl->rs.batch = t.members[mi].batch; ctl->rs.n_half = L.mtc[mi].n_half; }
       }
       for (int g = 0; g < kGroups; ++g) ctl->epi_done[g] = 0;
@@ -1502,7 +1503,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) train_tcp_kernel(const __grid_co
     MemberDev& mb = t.members[mi];
     const ProgramDev& pg = L.progs[mb.arch_idx];
     const MemberTc& mt = L.mtc[mi];
-    const ReconTc* rt = recon ? L.rtc + mi : nullptr;
+    const ReconTc* rt = recon ? L.rtc + ctl->rt_idx : nullptr;
     const RowSet& rs = ctl->rs;
     if (ctl->chunk_n > 0) {
       if (warp < kEpiWarps) {

@@ -194,6 +194,10 @@ class DeviationScorer:
         self.t_xc_te, self.t_hat_te = member_table(test_xc, self.xhat_test, self.o_hat_te)
         self.t_rows_tr = _lib.int_table([int(train_xc[i][0].shape[0]) for i in range(n)])
         self.t_rows_te = _lib.int_table([int(test_xc[i][0].shape[0]) for i in range(n)])
+        # both row sets in one launch (nmb_ensemble_reconstruct_sets): tables of set 0 (training rows) then set 1 (test rows)
+        cat = lambda a, b: _lib.ptr_table([a[i] for i in range(n * M)] + [b[i] for i in range(n * M)])
+        self.t_xc_both, self.t_hat_both = cat(self.t_xc_tr, self.t_xc_te), cat(self.t_hat_tr, self.t_hat_te)
+        self.t_rows_both = _lib.int_table([int(train_xc[i][0].shape[0]) for i in range(n)] + [int(test_xc[i][0].shape[0]) for i in range(n)])
         seg = range(self.n_seg)
         ptrs = lambda base, offsets, size: _lib.ptr_table([base.data_ptr() + size * int(offsets[s]) for s in seg])
         flat = lambda xc: [xc[i][k] for i, sp in enumerate(trainer.specs) for k in range(len(sp.input_dims))]
@@ -207,15 +211,13 @@ class DeviationScorer:
         self.s_lab = _lib.ptr_table([labels[seg_member[s]].data_ptr() for s in seg])
         self.s_ldx, self.s_d = _lib.int_table(seg_ldx), _lib.int_table(seg_d)
         self.s_ntr, self.s_nte, self.s_one = _lib.int_table(n_tr), _lib.int_table(n_te), _lib.int_table([1] * self.n_seg)
-        self.launches_per_run = 6
+        self.launches_per_run = 5
 
     def run(self):
         lib, st = self.lib, _stream_ptr(self.dev)
         with torch.cuda.device(self.dev):
-            _lib.check(lib.nmb_ensemble_reconstruct(self.tr.handle, self.t_xc_tr, self.t_rows_tr, self.mode, None,
-                                                    self.t_hat_tr, None, None, st), "nmb_ensemble_reconstruct")
-            _lib.check(lib.nmb_ensemble_reconstruct(self.tr.handle, self.t_xc_te, self.t_rows_te, self.mode, None,
-                                                    self.t_hat_te, None, None, st), "nmb_ensemble_reconstruct")
+            _lib.check(lib.nmb_ensemble_reconstruct_sets(self.tr.handle, 2, self.t_xc_both, self.t_rows_both, self.mode, None,
+                                                         self.t_hat_both, None, None, st), "nmb_ensemble_reconstruct_sets")
             _lib.check(lib.nmb_normative_stats(self.n_seg, self.s_x_tr, self.s_ldx, self.s_hat_tr, self.s_mask, self.s_ntr,
                                                self.s_d, self.s_stats, st), "nmb_normative_stats")
             _lib.check(lib.nmb_deviation(self.n_seg, self.s_x_te, self.s_ldx, self.s_hat_te, self.s_stats, self.s_nte,

@@ -27,6 +27,7 @@ owned = list(range(tr.n))
 print("gather           gpu %.3f ms  host-issue %.3f ms  wall %.3f ms" % timed(lambda: nd.gather_member_tables(rec, owned, tr.n)))
 lib, st = sc.lib, torch.cuda.current_stream().cuda_stream
 calls = {
+ "reconstruct both": lambda: lib.nmb_ensemble_reconstruct_sets(tr.handle, 2, sc.t_xc_both, sc.t_rows_both, sc.mode, None, sc.t_hat_both, None, None, st),
  "reconstruct train": lambda: lib.nmb_ensemble_reconstruct(tr.handle, sc.t_xc_tr, sc.t_rows_tr, sc.mode, None, sc.t_hat_tr, None, None, st),
  "reconstruct test": lambda: lib.nmb_ensemble_reconstruct(tr.handle, sc.t_xc_te, sc.t_rows_te, sc.mode, None, sc.t_hat_te, None, None, st),
  "stats": lambda: lib.nmb_normative_stats(sc.n_seg, sc.s_x_tr, sc.s_ldx, sc.s_hat_tr, sc.s_mask, sc.s_ntr, sc.s_d, sc.s_stats, st),
