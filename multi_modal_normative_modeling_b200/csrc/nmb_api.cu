@@ -885,7 +885,7 @@ int nmb_auc(int32_t n_seg, const float* const* scores, const uint8_t* const* lab
   t.scores = b.at<const float*>(os); t.labels = b.at<const uint8_t*>(ol);
   t.n_rows = b.at<int>(on); t.n_cols = b.at<int>(oc); t.out_auc = b.at<double*>(oa);
   t.out_u2 = out_u2 ? b.at<unsigned long long*>(ou) : nullptr;
-  launch_auc(t, n_seg, mc, st);
+  launch_auc(t, n_seg, mc, mr, st);
   CU(cudaGetLastError());
   CU(b.release(st));
   return 0;

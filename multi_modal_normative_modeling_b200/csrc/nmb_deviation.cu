@@ -166,13 +166,13 @@ constexpr int kAucTile = 1024;    // rows per tile (2 x 32 KB of shared memory)
 // rows [r0, r0 + m) x columns [c0, c0 + 8) of a row-major table -> dst[col][row]; `pad` fills columns / rows beyond
 // the table.  A warp reads 4 rows x 8 columns per instruction (4 full sectors).
 __device__ __forceinline__ void auc_load_tile(const float* __restrict__ sc, int n_cols, int c0, int r0, int m, int p2,
-                                              const uint8_t* __restrict__ lab, bool negatives_only, float* dst) {
+                                              const uint8_t* __restrict__ lab, bool negatives_only, float* dst, int stride) {
   const int cj = threadIdx.x & 7;
   const bool col_ok = c0 + cj < n_cols;
   for (int i = threadIdx.x >> 3; i < p2; i += 32) {
     float v = __int_as_float(0x7f800000);                       // +inf sorts behind every real negative
     if (i < m && col_ok && (!negatives_only || lab[r0 + i] == 0)) v = sc[(long long)(r0 + i) * n_cols + c0 + cj];
-    dst[cj * kAucTile + i] = v;
+    dst[cj * stride + i] = v;
   }
 }
 
@@ -192,10 +192,12 @@ __device__ __forceinline__ void warp_bitonic_sort(float* v, int n_pow2, int lane
   }
 }
 
-__global__ void __launch_bounds__(256) auc_kernel(AucTable t) {
+// stride = rows per column array in shared memory: the launch sizes it to the largest segment (<= kAucTile), so that the
+// usual 200-row test sets need 13 KB per CTA instead of 64 KB and five times as many CTAs are resident.
+__global__ void __launch_bounds__(256) auc_kernel(AucTable t, int stride) {
   extern __shared__ float auc_smem[];
-  float* negs = auc_smem;                                  // [8][kAucTile] negatives of the current tile (sorted / compacted)
-  float* vals = auc_smem + kAucCols * kAucTile;             // [8][kAucTile] raw scores of the current positive tile
+  float* negs = auc_smem;                                  // [8][stride] negatives of the current tile (sorted / compacted)
+  float* vals = auc_smem + kAucCols * stride;               // [8][stride] raw scores of the current positive tile
   __shared__ int s_cnt[8];
   __shared__ unsigned short s_idx[kAucTile];                // single-tile path: negatives first, positives from the back
   const int s = blockIdx.y;
@@ -214,7 +216,7 @@ __global__ void __launch_bounds__(256) auc_kernel(AucTable t) {
     // columns, so warp 0 compacts the row indices once (negatives from the front, positives from the back), every warp
     // gathers its column's negatives into a dense array and counts, for each of its positives, the negatives below /
     // equal by a broadcast scan (n_pos * n_neg / 32 steps per lane; cheaper than sorting for n <= 1024).
-    auc_load_tile(sc, n_cols, c0, 0, n, n, lab, false, vals);
+    auc_load_tile(sc, n_cols, c0, 0, n, n, lab, false, vals, stride);
     if (w == 0) {
       int nn = 0, np = 0;
       for (int i0 = 0; i0 < n; i0 += 32) {
@@ -233,8 +235,8 @@ __global__ void __launch_bounds__(256) auc_kernel(AucTable t) {
     n_pos = s_cnt[1];
     n_neg_total = n_neg;
     if (!active) return;
-    const float* pv = vals + w * kAucTile;
-    float* mine = negs + w * kAucTile;
+    const float* pv = vals + w * stride;
+    float* mine = negs + w * stride;
     for (int q = lane; q < n_neg; q += 32) mine[q] = pv[s_idx[q]];
     __syncwarp();
     for (int p = lane; p < n_pos; p += 32) {
@@ -259,21 +261,21 @@ __global__ void __launch_bounds__(256) auc_kernel(AucTable t) {
       for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
       __syncthreads();                                         // previous tile fully consumed (negs, s_cnt)
       if (lane == 0) s_cnt[w] = cnt;
-      auc_load_tile(sc, n_cols, c0, r0, m, p2, lab, true, negs);
+      auc_load_tile(sc, n_cols, c0, r0, m, p2, lab, true, negs, stride);
       __syncthreads();
       int n_neg = 0;
       for (int k = 0; k < 8; ++k) n_neg += s_cnt[k];
       n_neg_total += n_neg;
-      float* mine = negs + w * kAucTile;
+      float* mine = negs + w * stride;
       if (active && n_neg > 0) warp_bitonic_sort(mine, p2, lane);
       if (n_neg == 0) continue;                                 // CTA-uniform
       for (int q0 = 0; q0 < n; q0 += kAucTile) {                // positives of every tile against this tile's negatives
         const int mq = min(kAucTile, n - q0);
         __syncthreads();
-        auc_load_tile(sc, n_cols, c0, q0, mq, mq, lab, false, vals);
+        auc_load_tile(sc, n_cols, c0, q0, mq, mq, lab, false, vals, stride);
         __syncthreads();
         if (!active) continue;
-        const float* pv = vals + w * kAucTile;
+        const float* pv = vals + w * stride;
         for (int i = lane; i < mq; i += 32) {
           if (lab[q0 + i] == 0) continue;
           const float v = pv[i];
@@ -299,12 +301,14 @@ __global__ void __launch_bounds__(256) auc_kernel(AucTable t) {
   }
 }
 
-void launch_auc(const AucTable& t, int n_seg, int max_cols, cudaStream_t st) {
+void launch_auc(const AucTable& t, int n_seg, int max_cols, int max_rows, cudaStream_t st) {
   if (n_seg == 0 || max_cols == 0) return;
-  const int smem = 2 * kAucCols * kAucTile * (int)sizeof(float);
-  cudaFuncSetAttribute(auc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  int stride = kAucTile;                          // multi-tile path: full tiles (power-of-two sort width <= kAucTile)
+  if (max_rows <= kAucTile) stride = max_rows < 32 ? 32 : ((max_rows + 31) & ~31);
+  const int smem = 2 * kAucCols * stride * (int)sizeof(float);
+  cudaFuncSetAttribute(auc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kAucCols * kAucTile * (int)sizeof(float));
   dim3 grid((max_cols + kAucCols - 1) / kAucCols, n_seg);
-  auc_kernel<<<grid, 256, smem, st>>>(t);
+  auc_kernel<<<grid, 256, smem, st>>>(t, stride);
 }
 
 // ---- latent-space normative deviation (utils_vae.py:155-161) --------------------------------------------------

@@ -35,7 +35,7 @@ void launch_pack_rows(const float* x, const float* c, long long n_rows, int d, i
                       cudaStream_t st);
 void launch_stats(const SegTable& t, int n_seg, int max_d, cudaStream_t st);
 void launch_deviation(const SegTable& t, int n_seg, int max_rows, cudaStream_t st);
-void launch_auc(const AucTable& t, int n_seg, int max_cols, cudaStream_t st);
+void launch_auc(const AucTable& t, int n_seg, int max_cols, int max_rows, cudaStream_t st);
 struct LatentTable {
   const float* const* mu_train; const int* n_train; const float* const* mu; const float* const* logvar;
   const int* n_rows; const int* latent; float* const* out_z; float* const* out_dev;
