@@ -126,6 +126,15 @@ int nmb_pack_rows_scaled(const double* x, int64_t ld, int32_t d, const int32_t* 
                          const double* scale, const int32_t* age_bin, int32_t n_age, const int32_t* sex_bin, int32_t n_sex,
                          float* out, void* stream);
 
+/* ---- on-disk contract writer (f2) ---------------------------------------------------- */
+/* One table of the test program's CSV families (multimodal_kfold_test_cvae_supervised.py:116-178, DataFrame.to_csv(index=
+ * False)): `header` line, then per row `row_prefix[r]` (the leading cells already joined with ',', or NULL) followed by
+ * n_cols numbers of the HOST block `body` (float32 or float64, row stride ld), printed exactly as pandas prints a float
+ * column (shortest round-trip digits, numpy's positional / scientific rule, nan -> empty).  Byte-identical files; rows are
+ * formatted by `threads` host threads (0 = all cores). */
+int nmb_csv_write(const char* path, const char* header, const char* const* row_prefix, const void* body, int32_t body_is_f64,
+                  int64_t n_rows, int32_t n_cols, int64_t ld, int32_t threads);
+
 /* ---- ensemble ---------------------------------------------------------------------- */
 int nmb_ensemble_create(NmbEnsemble** out, int32_t device, const NmbMember* members /*host*/,
                         int32_t n_members);

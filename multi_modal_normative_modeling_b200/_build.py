@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libnmb.so")
-SOURCES = ["nmb_train.cu", "nmb_train_tcp.cu", "nmb_deviation.cu", "nmb_prologue.cu", "nmb_api.cu"]
+SOURCES = ["nmb_train.cu", "nmb_train_tcp.cu", "nmb_deviation.cu", "nmb_prologue.cu", "nmb_csv.cu", "nmb_api.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 

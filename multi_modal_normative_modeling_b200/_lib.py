@@ -47,6 +47,8 @@ _PROTOS = {
     "nmb_rank_bins": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "nmb_pack_rows_scaled": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "nmb_csv_write": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(C.c_char_p), C.c_void_p, C.c_int32, C.c_int64, C.c_int32,
+                                C.c_int64, C.c_int32]),
     "nmb_ensemble_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.POINTER(NmbMember), C.c_int32]),
     "nmb_ensemble_destroy": (C.c_int, [C.c_void_p]),
     "nmb_ensemble_size": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),

@@ -102,17 +102,38 @@ def fill_defaults(args):
     return args
 
 
-def write_csv(df: pd.DataFrame, path, fast: bool = False):
-    """The per-modality CSV families of the test program (test script :116-178).  fast=True: Arrow's multithreaded CSV
-    writer (same columns, header and row order; every float written with all the digits of its shortest round-trip
-    representation, in positional instead of scientific notation) -- 6x faster than ``DataFrame.to_csv``, which is what
-    the test program spends its time in.  Default: pandas, byte-identical to what the reference writes."""
+def write_csv(df: pd.DataFrame, path, fast: bool = False, native: bool = True):
+    """The per-modality CSV families of the test program (test script :116-178), ``df.to_csv(path, index=False)``.
+    Default: libnmb's writer (``nmb_csv_write``) -- the trailing block of float columns is formatted natively (threads
+    over rows, numpy's shortest-repr rules), the few leading columns and the header by pandas itself; the file is
+    byte-identical to what the reference writes (tests/test_host_cpu.py) at a fraction of ``DataFrame.to_csv``'s time,
+    which is what the test program spends most of its wall time in.  native=False: pandas.  fast=True: Arrow's CSV writer
+    (same cells, but positional instead of scientific notation -- not byte-identical; kept for comparison)."""
     if fast:
         import pyarrow as pa
         import pyarrow.csv as pc
         pc.write_csv(pa.Table.from_pandas(df, preserve_index=False), str(path), pc.WriteOptions(quoting_style="needed"))
-    else:
+        return
+    dts = list(df.dtypes)
+    k = len(dts)
+    while k > 0 and dts[k - 1] == dts[-1] and dts[-1] in (np.dtype("float32"), np.dtype("float64")):
+        k -= 1
+    if not native or k == len(dts) or len(df) == 0 or not df.columns.is_unique:
         df.to_csv(path, index=False)
+        return
+    import ctypes as C
+    from . import _lib
+    body = np.ascontiguousarray(df.iloc[:, k:].to_numpy())
+    header = df.iloc[:0].to_csv(index=False).rstrip("\r\n").encode()
+    prefix = None
+    if k:
+        lines = df.iloc[:, :k].to_csv(index=False, header=False).split("\n")[:len(df)]
+        if len(lines) != len(df) or any("\r" in ln or '"' in ln for ln in lines):      # embedded newlines / quoted cells
+            df.to_csv(path, index=False)
+            return
+        prefix = (C.c_char_p * len(df))(*[ln.encode() for ln in lines])
+    _lib.check(_lib.load().nmb_csv_write(os.fspath(path).encode(), header, prefix, body.ctypes.data,
+                                         int(body.dtype == np.float64), body.shape[0], body.shape[1], body.shape[1], 0))
 
 
 def _paths(root: Path, resource: str):

@@ -394,6 +394,14 @@ int nmb_pack_rows_scaled(const double* x, int64_t ld, int32_t d, const int32_t* 
   return 0;
 }
 
+int nmb_csv_write(const char* path, const char* header, const char* const* row_prefix, const void* body, int32_t body_is_f64,
+                  int64_t n_rows, int32_t n_cols, int64_t ld, int32_t threads) {
+  if (!path || n_rows < 0 || n_cols < 0 || (n_cols && n_rows && !body) || ld < n_cols) return fail("bad argument");
+  std::string err;
+  if (csv_write(path, header, row_prefix, body, body_is_f64, n_rows, n_cols, ld, threads, err)) return fail(err);
+  return 0;
+}
+
 int nmb_ensemble_create(NmbEnsemble** out, int32_t device, const NmbMember* members, int32_t n_members) {
   if (!out || !members || n_members < 1) return fail("bad argument");
   int count = 0;

@@ -1,5 +1,6 @@
 // Internal (non-ABI) declarations shared by the translation units of libnmb.
 #pragma once
+#include <string>
 #include "nmb_common.cuh"
 #include "nmb_tcp.h"
 
@@ -101,5 +102,9 @@ cudaError_t launch_train_tcp(const TrainLaunch& t, const tcp::ProgramDev* progs,
                              int max_mlayers, int n_sm, bool gather_in, bool scatter_out, cudaStream_t st);
 cudaError_t launch_tcp_scatter(MemberDev* members, int n_members, const tcp::ProgramDev* progs, const tcp::MemberTc* mtc,
                                float* master, long long master_floats, int max_mlayers, cudaStream_t st);
+
+// nmb_csv.cu: host-side table writer (f2)
+int csv_write(const char* path, const char* header, const char* const* prefix, const void* body, int is_f64, long long n_rows,
+              int n_cols, long long ld, int threads, std::string& err);
 
 }  // namespace nmb

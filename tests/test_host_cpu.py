@@ -251,3 +251,43 @@ def test_fast_csv_writer_keeps_the_file_contract(tmp_path):
     assert list(a.columns) == list(b.columns) == list(df.columns)
     assert a.equals(b) and a.dtypes.equals(b.dtypes)
     assert np.array_equal(b.iloc[:, 2:].to_numpy(), df.iloc[:, 2:].to_numpy())
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_native_csv_writer_is_byte_identical_to_pandas(tmp_path, dtype):
+    """f2: cli.write_csv's default (libnmb ``nmb_csv_write``) against ``DataFrame.to_csv(index=False)`` -- the call the
+    reference's test program writes every table with (multimodal_kfold_test_cvae_supervised.py:116-178).  Random bit
+    patterns (every exponent, denormals), the notation thresholds from both sides, signed zeros, nan / inf, integral
+    values; string, int and float leading columns; column names that need quoting."""
+    import pandas as pd
+    from multi_modal_normative_modeling_b200 import cli
+    rng = np.random.RandomState(1)
+    n, d = 1500, 24
+    it = np.uint64 if dtype == np.float64 else np.uint32
+    bits = rng.randint(0, 2 ** 32, (n, d), dtype=np.uint64)
+    if dtype == np.float64:
+        bits = (bits << np.uint64(32)) | rng.randint(0, 2 ** 32, (n, d), dtype=np.uint64)
+    x = bits.astype(it).view(dtype).copy()
+    x[: n // 2] = (rng.randn(n // 2, d) * 10.0 ** rng.randint(-8, 9, (n // 2, d))).astype(dtype)   # the usual range
+    edge = []
+    for t in (1e-4, 1e6, 1e16, 1e-5, 1e15, 1e5, 1.0, 1e22, 2.0 ** 53, 2.0 ** 24):
+        v = dtype(t)
+        edge += [v, np.nextafter(v, dtype(0)), np.nextafter(v, dtype(np.inf)), -v]
+    edge += [0.0, -0.0, np.nan, np.inf, -np.inf, 5e-324, 1e-45, np.finfo(dtype).max, np.finfo(dtype).tiny, 100.0, 1 / 3, 0.1]
+    edge = np.asarray(edge, dtype=dtype)
+    x[n // 2, :] = np.resize(edge, d); x[n // 2 + 1, :] = np.resize(edge[d:], d); x[n // 2 + 2, :] = np.resize(edge[2 * d:], d)
+    body = pd.DataFrame(x, columns=[f"ROI {i}, left" if i % 2 else f"roi{i}" for i in range(d)])
+    cov = pd.DataFrame({"participant_id": [f"sub-{i:04d}" for i in range(n)], "DIA": rng.randint(0, 4, n),
+                        "AGE": np.where(rng.rand(n) < 0.02, np.nan, rng.uniform(50, 90, n).round(1)), "PTGENDER": rng.randint(1, 3, n)})
+    for name, df in (("full", pd.concat([cov, body], axis=1)), ("body", body), ("few", pd.concat([cov, body], axis=1).iloc[:7]),
+                     ("one", pd.concat([cov, body.iloc[:, :1]], axis=1))):
+        df.to_csv(tmp_path / "ref.csv", index=False)
+        cli.write_csv(df, tmp_path / "new.csv")
+        assert (tmp_path / "new.csv").read_bytes() == (tmp_path / "ref.csv").read_bytes(), name
+    # tables the native path does not take (no trailing float block, quoted cells) still come out as pandas writes them
+    odd = cov.copy()
+    odd.loc[3, "participant_id"] = 'a,"b'
+    for df in (cov, pd.concat([odd, body], axis=1)):
+        df.to_csv(tmp_path / "ref.csv", index=False)
+        cli.write_csv(df, tmp_path / "new.csv")
+        assert (tmp_path / "new.csv").read_bytes() == (tmp_path / "ref.csv").read_bytes()
