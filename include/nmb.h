@@ -29,12 +29,17 @@ extern "C" {
 
 #define NMB_MAX_MOD 16    /* modalities per model (HCP uses 12 + early fusion) */
 #define NMB_MAX_HIDDEN 4  /* hidden layers per encoder/decoder (hz_para_list up to "1024 512 256 32") */
+#define NMB_MAX_HEAD 3    /* hidden layers of a supervised head (the regressor has 2: 128, 64) */
 
 /* combine_latent kinds, cVAE.py:1144-1164 (case-insensitive strings in the reference) */
 enum { NMB_COMBINE_POE = 0, NMB_COMBINE_GPOE = 1, NMB_COMBINE_MOE = 2, NMB_COMBINE_MOPOE = 3 };
 /* reconstruction term: Gaussian log-likelihood with learned logvar_out (cVAE.py:14-15,193-206)
  * or -MSE(mean) (multimodal_kfold_cvae_nmmlp.py:124-127) */
 enum { NMB_LOSS_GAUSS_LL = 0, NMB_LOSS_NEG_MSE = 1 };
+/* supervised head on top of the multimodal cVAE.  NMB_HEAD_REGRESSION = cVAE_multimodal_regression
+ * (cVAE.py:2211-2347): regressor MLP Linear(sum D, h0) ReLU ... Linear(h_last, 1) on the concatenated residuals
+ * x_m - x_recon_m.loc (:2321-2325), loss total += head_weight * MSE(fi_pred, true_fi) (:2334-2347). */
+enum { NMB_HEAD_NONE = 0, NMB_HEAD_REGRESSION = 1 };
 
 /* Architecture of one ensemble member = the constructor arguments of
  * cVAE_multimodal(input_dim_list, hidden_dim, latent_dim, c_dim, ..., modalities, non_linear)
@@ -49,6 +54,10 @@ typedef struct {
   int32_t combine;    /* NMB_COMBINE_* */
   int32_t loss_kind;  /* NMB_LOSS_* */
   int32_t non_linear; /* leaky_relu(0.01) after hidden layers (cVAE.py:166-167) */
+  int32_t head_kind;  /* NMB_HEAD_*; members with a head run on the generic engines */
+  int32_t n_head_hidden;
+  int32_t head_hidden[NMB_MAX_HEAD]; /* 128, 64 (cVAE.py:2248-2255) */
+  float head_weight;  /* lambda_reg (cVAE.py:2334; the trainer passes 1.0) */
 } NmbArch;
 
 /* One tensor of the reference's state_dict inside the packed per-model parameter buffer.
@@ -56,7 +65,8 @@ typedef struct {
  * row n = { weight[n][0..in-1], bias[n], 0... }.  The mean and logvar heads are stacked
  * (rows 0..Z-1 = enc_mean_layer, Z..2Z-1 = enc_logvar_layer). */
 enum { NMB_SLOT_ENC = 0, NMB_SLOT_ENC_MEAN = 1, NMB_SLOT_ENC_LOGVAR = 2, NMB_SLOT_DEC = 3,
-       NMB_SLOT_DEC_MEAN = 4, NMB_SLOT_LOGVAR_OUT = 5, NMB_SLOT_ALPHA = 6 };
+       NMB_SLOT_DEC_MEAN = 4, NMB_SLOT_LOGVAR_OUT = 5, NMB_SLOT_ALPHA = 6,
+       NMB_SLOT_HEAD = 7 /* layer l of the head = regressor.{2l} (cVAE.py:2248-2255); modality 0 */ };
 typedef struct {
   int32_t kind;      /* NMB_SLOT_* */
   int32_t modality;
@@ -84,6 +94,12 @@ typedef struct {
   float* grads;                 /* [n_params] or NULL; written when NMB_TRAIN_WRITE_GRADS */
   int64_t n_lr_steps;           /* entries of lr_steps; a train call that would step past it FAILS (no silent read
                                    beyond the schedule).  Ignored when lr_steps is NULL. */
+  const float* y;               /* head target per training row [n_rows] (FI, ..._regression.py:86-87); NULL without a head */
+  const int32_t* row_order;     /* optional [n_order_epochs][n_mod][n_rows]: the dataset row each modality's loader yields
+                                   at position i of that epoch -- DataLoader(shuffle=True) draws one permutation PER
+                                   MODALITY per epoch (..._regression.py:94, 122); the target follows modality 0 (:125).
+                                   NULL = rows in order (shuffle=False).  Generic engines only. */
+  int64_t n_order_epochs;       /* epochs row_order covers; training past it FAILS */
 } NmbMember;
 
 typedef struct NmbEnsemble NmbEnsemble;
@@ -154,6 +170,8 @@ enum {
                                 the default tcgen05 engine (error-compensated BF16x3 products, FP32 accumulate) */
   NMB_TRAIN_TC_SIMPLE = 16,  /* tcgen05 engine without the operand pipeline (the generic engine that also serves
                                 architectures the pipelined kernel does not cover, e.g. hidden width > 127) */
+  NMB_TRAIN_LOSS4 = 64,      /* loss_out rows hold 4 values: (total, kl, ll, head loss) -- losses['regression'] of
+                                cVAE_multimodal_regression (cVAE.py:2343-2345); 0 for members without a head */
   NMB_TRAIN_RESIDENT = 32    /* pipelined engine: leave parameters and Adam moments in the kernel's lane-major master
                                 layout after the call (no conversion back, none in at the next call).  NmbMember.params /
                                 adam_m / adam_v are then STALE until nmb_ensemble_sync (logvar_out and the gPoE alphas
@@ -219,6 +237,14 @@ enum { NMB_RECON_MEAN = 0, NMB_RECON_SAMPLE = 1,
 int nmb_ensemble_reconstruct(NmbEnsemble* ens, const float* const* xc, const int32_t* n_rows,
                              int32_t mode, const float* const* eps, float* const* xhat,
                              float* const* mu, float* const* logvar, void* stream);
+
+/* Members with a supervised head (NMB_HEAD_REGRESSION): the head's prediction for every row of xc -- `fi_pred` of
+ * cVAE_multimodal_regression.forward_multimodal (cVAE.py:2309-2332): encode, fuse, z = mu + eps*std (mode SAMPLE: the
+ * reference samples at test time too, ..._regression.py:146-152; eps[i] injected or Philox), decode, residuals,
+ * regressor.  out[i]: [n_rows[i]] (NULL entries / members without a head are skipped); xhat: optional table as in
+ * nmb_ensemble_reconstruct (may be NULL). */
+int nmb_ensemble_head_predict(NmbEnsemble* ens, const float* const* xc, const int32_t* n_rows, int32_t mode,
+                              const float* const* eps, float* const* xhat, float* const* out, void* stream);
 
 /* The same for `n_sets` row sets per member in ONE launch (e.g. the training rows for the normative statistics and the
  * test rows of the test script, :83-113): entry (s, i) of every table sits at index s * n_members + i, for xc / xhat at

@@ -7,11 +7,13 @@ import os
 
 NMB_MAX_MOD = 16
 NMB_MAX_HIDDEN = 4
+NMB_MAX_HEAD = 3
 
 COMBINE = {"poe": 0, "gpoe": 1, "moe": 2, "mopoe": 3}
 LOSS = {"gauss_ll": 0, "neg_mse": 1}
-SLOT_ENC, SLOT_ENC_MEAN, SLOT_ENC_LOGVAR, SLOT_DEC, SLOT_DEC_MEAN, SLOT_LOGVAR_OUT, SLOT_ALPHA = range(7)
-TRAIN_NO_ADAM, TRAIN_WRITE_GRADS, TRAIN_KEEP_ACTS, TRAIN_FP32, TRAIN_TC_SIMPLE, TRAIN_RESIDENT = 1, 2, 4, 8, 16, 32
+HEAD = {None: 0, "none": 0, "regression": 1}
+SLOT_ENC, SLOT_ENC_MEAN, SLOT_ENC_LOGVAR, SLOT_DEC, SLOT_DEC_MEAN, SLOT_LOGVAR_OUT, SLOT_ALPHA, SLOT_HEAD = range(8)
+TRAIN_NO_ADAM, TRAIN_WRITE_GRADS, TRAIN_KEEP_ACTS, TRAIN_FP32, TRAIN_TC_SIMPLE, TRAIN_RESIDENT, TRAIN_LOSS4 = 1, 2, 4, 8, 16, 32, 64
 RECON_MEAN, RECON_SAMPLE, RECON_GIVEN_Z, RECON_FP32, RECON_TC_SIMPLE, RECON_KEEP_PLANES = 0, 1, 2, 16, 32, 64
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libnmb.so")
@@ -20,7 +22,9 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libn
 class NmbArch(C.Structure):
     _fields_ = [("n_mod", C.c_int32), ("input_dims", C.c_int32 * NMB_MAX_MOD), ("n_hidden", C.c_int32),
                 ("hidden", C.c_int32 * NMB_MAX_HIDDEN), ("latent", C.c_int32), ("c_dim", C.c_int32),
-                ("combine", C.c_int32), ("loss_kind", C.c_int32), ("non_linear", C.c_int32)]
+                ("combine", C.c_int32), ("loss_kind", C.c_int32), ("non_linear", C.c_int32),
+                ("head_kind", C.c_int32), ("n_head_hidden", C.c_int32), ("head_hidden", C.c_int32 * NMB_MAX_HEAD),
+                ("head_weight", C.c_float)]
 
 
 class NmbSlot(C.Structure):
@@ -32,7 +36,8 @@ class NmbMember(C.Structure):
     _fields_ = [("arch", NmbArch), ("xc", C.c_void_p * NMB_MAX_MOD), ("n_rows", C.c_int32), ("batch", C.c_int32),
                 ("seed", C.c_uint64), ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float),
                 ("adam_eps", C.c_float), ("lr_steps", C.c_void_p), ("params", C.c_void_p),
-                ("adam_m", C.c_void_p), ("adam_v", C.c_void_p), ("grads", C.c_void_p), ("n_lr_steps", C.c_int64)]
+                ("adam_m", C.c_void_p), ("adam_v", C.c_void_p), ("grads", C.c_void_p), ("n_lr_steps", C.c_int64),
+                ("y", C.c_void_p), ("row_order", C.c_void_p), ("n_order_epochs", C.c_int64)]
 
 
 _PROTOS = {
@@ -65,6 +70,8 @@ _PROTOS = {
     "nmb_ensemble_reconstruct": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_int32,
                                            C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                            C.POINTER(C.c_void_p), C.c_void_p]),
+    "nmb_ensemble_head_predict": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_int32,
+                                            C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p]),
     "nmb_ensemble_reconstruct_sets": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_int32,
                                                 C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                                 C.POINTER(C.c_void_p), C.c_void_p]),
@@ -127,7 +134,8 @@ def int_table(vals):
     return (C.c_int32 * max(len(vals), 1))(*[int(v) for v in vals])
 
 
-def make_arch(input_dims, hidden, latent, c_dim, combine="poe", loss_kind="gauss_ll", non_linear=True) -> NmbArch:
+def make_arch(input_dims, hidden, latent, c_dim, combine="poe", loss_kind="gauss_ll", non_linear=True,
+              head=None, head_hidden=(128, 64), head_weight=1.0) -> NmbArch:
     if isinstance(combine, str):
         key = combine.lower()
         if key not in COMBINE:
@@ -148,6 +156,14 @@ def make_arch(input_dims, hidden, latent, c_dim, combine="poe", loss_kind="gauss
         a.hidden[i] = int(h)
     a.latent, a.c_dim = int(latent), int(c_dim)
     a.combine, a.loss_kind, a.non_linear = int(combine), int(loss_kind), int(bool(non_linear))
+    a.head_kind = HEAD[head.lower() if isinstance(head, str) else head]
+    if a.head_kind:
+        if not 1 <= len(head_hidden) <= NMB_MAX_HEAD:
+            raise ValueError(f"1..{NMB_MAX_HEAD} hidden layers in a supervised head")
+        a.n_head_hidden = len(head_hidden)
+        for i, h in enumerate(head_hidden):
+            a.head_hidden[i] = int(h)
+        a.head_weight = float(head_weight)
     return a
 
 

@@ -108,6 +108,10 @@ NmbArch canonical(const NmbArch& a) {   // zero the unused tails so memcmp is me
   c.combine = a.combine; c.loss_kind = a.loss_kind; c.non_linear = a.non_linear ? 1 : 0;
   for (int i = 0; i < a.n_mod && i < NMB_MAX_MOD; ++i) c.input_dims[i] = a.input_dims[i];
   for (int i = 0; i < a.n_hidden && i < NMB_MAX_HIDDEN; ++i) c.hidden[i] = a.hidden[i];
+  if (a.head_kind) {
+    c.head_kind = a.head_kind; c.n_head_hidden = a.n_head_hidden; c.head_weight = a.head_weight;
+    for (int i = 0; i < a.n_head_hidden && i < NMB_MAX_HEAD; ++i) c.head_hidden[i] = a.head_hidden[i];
+  }
   return c;
 }
 
@@ -160,6 +164,7 @@ struct NmbEnsemble {
   bool planes_valid = false;                 // the BF16 weight planes match the parameters (left by the last pipelined train call)
   std::vector<long long> steps_host;         // host mirror of MemberDev.steps_done (every step goes through this API)
   std::vector<long long> n_lr_steps;         // length of each member's lr_steps schedule (0 = none)
+  std::vector<long long> n_order_epochs;     // epochs each member's row_order covers (0 = none)
 };
 
 namespace {
@@ -357,6 +362,8 @@ int nmb_arch_slots(const NmbArch* arch, NmbSlot* slots, int32_t max_slots, int32
     for (int l = 0; l < d.L; ++l) push(NMB_SLOT_DEC, m, l, q.dec[l].out, q.dec[l].in, q.dec[l].ld, q.dec[l].off);
     push(NMB_SLOT_DEC_MEAN, m, 0, q.outl.out, q.outl.in, q.outl.ld, q.outl.off);
   }
+  if (d.head_kind)
+    for (int l = 0; l <= d.HL; ++l) push(NMB_SLOT_HEAD, 0, l, d.hd[l].out, d.hd[l].in, d.hd[l].ld, d.hd[l].off);
   *n_slots = (int32_t)v.size();
   if (slots) for (int i = 0; i < (int)v.size() && i < max_slots; ++i) slots[i] = v[i];
   return 0;
@@ -431,11 +438,16 @@ int nmb_ensemble_create(NmbEnsemble** out, int32_t device, const NmbMember* memb
     for (int m = 0; m < d.M; ++m) md.xc[m] = mm.xc[m];
     md.params = mm.params; md.adam_m = mm.adam_m; md.adam_v = mm.adam_v; md.grads = mm.grads;
     md.lr_steps = mm.lr_steps; md.seed = mm.seed;
+    md.y = mm.y; md.row_order = mm.row_order;
+    if (d.head_kind && !mm.y && mm.n_rows > 0) { delete e; return fail("a member with a supervised head needs targets (NmbMember.y)"); }
+    if (mm.row_order && !d.head_kind) { delete e; return fail("row_order is supported for members with a supervised head only"); }
+    if (mm.row_order && mm.n_order_epochs < 1) { delete e; return fail("row_order given without n_order_epochs"); }
     md.lr = mm.lr; md.beta1 = mm.beta1; md.beta2 = mm.beta2; md.adam_eps = mm.adam_eps;
     md.steps_done = 0; md.last_rows = 0; md.last_slot = -1; md.launch_base = 0;
     if (mm.lr_steps && mm.n_lr_steps < 1) { delete e; return fail("lr_steps given without n_lr_steps"); }
     e->members_host.push_back(md); e->arch_idx.push_back(ai);
     e->steps_host.push_back(0); e->n_lr_steps.push_back(mm.lr_steps ? (long long)mm.n_lr_steps : 0);
+    e->n_order_epochs.push_back(mm.row_order ? (long long)mm.n_order_epochs : 0);
   }
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, device));
@@ -533,7 +545,19 @@ static int train_common(NmbEnsemble* e, int64_t n, int n_is_epochs, const float*
                     i, e->n_lr_steps[i], e->steps_host[i] + ns);
       return fail(buf);
     }
+    if (e->n_order_epochs[i] > 0) {        // the per-epoch permutations must cover every step of this call
+      const MemberDev& m = e->members_host[i];
+      const long long spe = (m.n_rows + m.batch - 1) / m.batch;
+      if (e->steps_host[i] + ns > e->n_order_epochs[i] * spe) {
+        char buf[160];
+        std::snprintf(buf, sizeof(buf), "member %d: row_order covers %lld epochs but this call would reach step %lld",
+                      i, e->n_order_epochs[i], e->steps_host[i] + ns);
+        return fail(buf);
+      }
+    }
   }
+  if ((flags & NMB_TRAIN_LOSS4) && e->tcp_ok && !(flags & (NMB_TRAIN_FP32 | NMB_TRAIN_TC_SIMPLE)))
+    return fail("NMB_TRAIN_LOSS4 is a generic-engine option (members with a supervised head)");
   t.stride_steps = max_steps;
   if (max_steps == 0) return 0;
   CU(cudaSetDevice(e->device));
@@ -626,7 +650,7 @@ int nmb_ensemble_peek(NmbEnsemble* e, int32_t member, float* mu, float* logvar, 
 // (s * n_members + i) * NMB_MAX_MOD + m)
 static int reconstruct_sets(NmbEnsemble* e, int n_sets, const float* const* xc, const int32_t* n_rows, int32_t mode,
                             const float* const* eps, float* const* xhat, float* const* mu, float* const* logvar,
-                            void* stream) {
+                            void* stream, float* const* head_out = nullptr) {
   if (!e || !xc || !n_rows || !xhat || n_sets < 1) return fail("null argument");
   const int32_t mode_in = mode;
   const int fp32 = (mode & NMB_RECON_FP32) ? 1 : 0;
@@ -756,6 +780,7 @@ static int reconstruct_sets(NmbEnsemble* e, int n_sets, const float* const* xc, 
   const size_t o_eps = eps ? b.add(eps, sizeof(void*) * n) : 0;
   const size_t o_mu = mu ? b.add(mu, sizeof(void*) * n) : 0;
   const size_t o_lv = logvar ? b.add(logvar, sizeof(void*) * n) : 0;
+  const size_t o_ho = head_out ? b.add(head_out, sizeof(void*) * n) : 0;
   CU(b.upload(st));
   ReconLaunch t;
   t.members = e->members_dev; t.archs = e->archs_dev;
@@ -764,6 +789,7 @@ static int reconstruct_sets(NmbEnsemble* e, int n_sets, const float* const* xc, 
   t.eps = eps ? b.at<const float*>(o_eps) : nullptr;
   t.mu = mu ? b.at<float*>(o_mu) : nullptr;
   t.logvar = logvar ? b.at<float*>(o_lv) : nullptr;
+  t.head_out = head_out ? b.at<float*>(o_ho) : nullptr;
   t.mode = mode; t.scratch = e->scratch; t.slot_floats = e->slot_floats; t.n_slots = e->n_slots; t.fp32 = fp32;
   CU(launch_recon(t, st));
   CU(b.release(st));
@@ -774,6 +800,17 @@ int nmb_ensemble_reconstruct(NmbEnsemble* e, const float* const* xc, const int32
                              const float* const* eps, float* const* xhat, float* const* mu, float* const* logvar,
                              void* stream) {
   return reconstruct_sets(e, 1, xc, n_rows, mode, eps, xhat, mu, logvar, stream);
+}
+
+int nmb_ensemble_head_predict(NmbEnsemble* e, const float* const* xc, const int32_t* n_rows, int32_t mode,
+                              const float* const* eps, float* const* xhat, float* const* out, void* stream) {
+  if (!e || !out) return fail("null argument");
+  if (e->tcp_ok) return fail("nmb_ensemble_head_predict: no member of this ensemble has a supervised head");
+  if ((mode & ~(NMB_RECON_FP32 | NMB_RECON_TC_SIMPLE | NMB_RECON_KEEP_PLANES)) == NMB_RECON_GIVEN_Z)
+    return fail("nmb_ensemble_head_predict: the head needs the encoders (MEAN or SAMPLE)");
+  std::vector<float*> none;
+  if (!xhat) { none.assign((size_t)e->n_members * NMB_MAX_MOD, nullptr); xhat = none.data(); }
+  return reconstruct_sets(e, 1, xc, n_rows, mode, eps, xhat, nullptr, nullptr, stream, out);
 }
 
 int nmb_ensemble_reconstruct_sets(NmbEnsemble* e, int32_t n_sets, const float* const* xc, const int32_t* n_rows, int32_t mode,

@@ -33,6 +33,8 @@ struct ModDesc {
   long long s_g0;                 int ld_g0;                  // decoder input [z | c | 1]
   long long s_xh;                 int ld_xh;                  // d(total)/d(x_recon)
   long long s_xr;                                             // x_recon kept for nmb_ensemble_peek
+  long long s_in;                                             // staged minibatch rows (members with row_order)
+  int r_off;                                                  // first column of this modality in the head's residual row
 };
 
 struct ArchDesc {
@@ -43,6 +45,14 @@ struct ArchDesc {
   long long n_params;
   long long s_mub, s_lvb, s_eps, s_dz;   // fused mu, fused logvar, eps, d(total)/dz   [B][Z]
   long long s_ga, s_gb; int ld_g;        // gradient ping-pong buffers [B][ld_g]
+  // supervised head (NMB_HEAD_REGRESSION): linears hd[0..HL], input = residual row [x_m - x_recon_m ... | 1]
+  int head_kind, HL, sumD;
+  float head_weight;
+  int head_w[NMB_MAX_HEAD];
+  LinDesc hd[NMB_MAX_HEAD + 1];
+  long long s_R, s_dR; int ld_R;                              // residual rows and their gradient
+  long long s_hh[NMB_MAX_HEAD]; int ld_hh[NMB_MAX_HEAD];      // head hidden activations (post-ReLU | 1)
+  long long s_pred, s_dpred;                                  // [B][4]: prediction, d(total)/d(prediction)
   long long scratch_floats;
 };
 
@@ -53,6 +63,8 @@ struct MemberDev {
   const float* xc[NMB_MAX_MOD];
   float* params; float* adam_m; float* adam_v; float* grads;
   const float* lr_steps;
+  const float* y;           // head targets [n_rows]
+  const int* row_order;     // [epochs][M][n_rows] or NULL
   unsigned long long seed;
   float lr, beta1, beta2, adam_eps;
   long long steps_done;     // mutable: minibatch steps taken so far
@@ -69,6 +81,8 @@ inline int build_arch(const NmbArch& a, ArchDesc* d, const char** err) {
   if (a.latent < 1 || a.c_dim < 0) return fail("bad latent / c_dim");
   if (a.combine < 0 || a.combine > NMB_COMBINE_MOPOE) return fail("No such combination method");
   if (a.loss_kind < 0 || a.loss_kind > NMB_LOSS_NEG_MSE) return fail("bad loss_kind");
+  if (a.head_kind != NMB_HEAD_NONE && a.head_kind != NMB_HEAD_REGRESSION) return fail("bad head_kind");
+  if (a.head_kind && (a.n_head_hidden < 1 || a.n_head_hidden > NMB_MAX_HEAD)) return fail("n_head_hidden out of range (1..3)");
   *d = ArchDesc{};
   d->M = a.n_mod; d->L = a.n_hidden; d->Z = a.latent; d->C = a.c_dim;
   d->combine = a.combine; d->loss_kind = a.loss_kind; d->non_linear = a.non_linear;
@@ -105,6 +119,22 @@ inline int build_arch(const NmbArch& a, ArchDesc* d, const char** err) {
     q.ld_xh = round4(q.D); q.s_xh = buf(q.ld_xh); q.s_xr = buf(q.ld_xh);
   }
   d->alpha_off = off; off += round4(d->M);
+  d->head_kind = a.head_kind; d->HL = 0; d->sumD = 0; d->head_weight = a.head_weight;
+  if (a.head_kind) {     // appended after alpha: the packed layout of a head-less model is a prefix of this one
+    d->HL = a.n_head_hidden;
+    for (int m = 0; m < d->M; ++m) { d->mod[m].r_off = d->sumD; d->sumD += d->mod[m].D; d->mod[m].s_in = buf(d->mod[m].ldx); }
+    for (int l = 0; l <= d->HL; ++l) {
+      if (l < d->HL) {
+        if (a.head_hidden[l] < 1) return fail("bad head width");
+        d->head_w[l] = a.head_hidden[l];
+        if (d->head_w[l] > maxw) maxw = d->head_w[l];
+      }
+      d->hd[l] = lin(l == 0 ? d->sumD : d->head_w[l - 1], l == d->HL ? 1 : d->head_w[l]);
+    }
+    d->ld_R = round4(d->sumD + 1); d->s_R = buf(d->ld_R); d->s_dR = buf(d->ld_R);
+    for (int l = 0; l < d->HL; ++l) { d->ld_hh[l] = round4(d->head_w[l] + 1); d->s_hh[l] = buf(d->ld_hh[l]); }
+    d->s_pred = buf(4); d->s_dpred = buf(4);
+  }
   d->n_params = off;
   d->s_mub = buf(Z); d->s_lvb = buf(Z); d->s_eps = buf(Z); d->s_dz = buf(Z);
   d->ld_g = round4(maxw);

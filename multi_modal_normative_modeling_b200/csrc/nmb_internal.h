@@ -81,6 +81,7 @@ struct ReconLaunch {
   const float* const* xc; const float* const* eps; float* const* xhat; float* const* mu; float* const* logvar;
   int mode; float* scratch; long long slot_floats; int n_slots;
   int fp32;   // FP32 FFMA engine instead of tcgen05
+  float* const* head_out;   // optional per member: head predictions [n_rows] (members with a head)
 };
 cudaError_t launch_recon(const ReconLaunch& t, cudaStream_t st);
 cudaError_t configure_kernels();

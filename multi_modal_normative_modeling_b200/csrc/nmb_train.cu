@@ -27,6 +27,8 @@ struct StepCtx {
   tc::Ctx* tc;      // tensor-core engine context (null for the FP32 engine)
   float* red;       // reduction scratch (>= 16 floats)
   int rows, row0;
+  const float* const* xin;   // per modality: base such that xin[m] + row0 * ldx is the minibatch (mb.xc, or staged rows)
+  const int* yidx;           // head targets: y[yidx ? yidx[row0 + b] : row0 + b]
   long long step;   // global 0-based step index of this member
   unsigned flags;
   // Adam scalars of this step
@@ -43,13 +45,15 @@ struct EpiHidden {     // h = leaky_relu(a) (bias already inside a via the ones 
     float* d = dst + (long long)m * ld + nb;
 #pragma unroll
     for (int j = 0; j < TN; ++j)
-      if (nb + 16 * j < N) d[16 * j] = (nl && v[j] <= 0.f) ? kSlope * v[j] : v[j];
+      if (nb + 16 * j < N) d[16 * j] = (nl && v[j] <= 0.f) ? slope() * v[j] : v[j];
   }
+  __device__ __forceinline__ float slope() const { return nl == 2 ? 0.f : kSlope; }   // nl: 1 = leaky_relu, 2 = ReLU (head)
   // tensor-core engine: v = C[m][n0 .. n0+16), first nvalid entries inside N
   __device__ __forceinline__ void rowc(int m, int n0, int nvalid, const float (&v)[16]) {
     float o[16];
+    const float sl = slope();
 #pragma unroll
-    for (int j = 0; j < 16; ++j) o[j] = (nl && v[j] <= 0.f) ? kSlope * v[j] : v[j];
+    for (int j = 0; j < 16; ++j) o[j] = (nl && v[j] <= 0.f) ? sl * v[j] : v[j];
     store16(dst + (long long)m * ld + n0, nvalid, o);
   }
 };
@@ -143,13 +147,14 @@ struct EpiDgrad {      // d_pre = d_act * leaky_relu'(pre), sign recovered from 
     float* d = dst + (long long)m * ld + nb;
 #pragma unroll
     for (int j = 0; j < TN; ++j)
-      if (nb + 16 * j < N) d[16 * j] = h[j] <= 0.f ? kSlope * v[j] : v[j];
+      if (nb + 16 * j < N) d[16 * j] = h[j] <= 0.f ? (nl == 2 ? 0.f : kSlope) * v[j] : v[j];
   }
   __device__ __forceinline__ void rowc(int m, int n0, int nvalid, const float (&v)[16]) {
     float h[16], o[16];
     if (nl) load16(act + (long long)m * ld_act + n0, nvalid, 1.f, h);
+    const float sl = nl == 2 ? 0.f : kSlope;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) o[j] = (nl && h[j] <= 0.f) ? kSlope * v[j] : v[j];
+    for (int j = 0; j < 16; ++j) o[j] = (nl && h[j] <= 0.f) ? sl * v[j] : v[j];
     store16(dst + (long long)m * ld + n0, nvalid, o);
   }
 };
@@ -265,6 +270,12 @@ __device__ void prepare_slot(const StepCtx& c) {
       c.scratch[q.s_g0 + (long long)b * q.ld_g0 + a.Z + a.C] = 1.f;
     }
   }
+  if (a.head_kind) {
+    for (int b = threadIdx.x; b < kMaxBatch; b += kThreads) {
+      c.scratch[a.s_R + (long long)b * a.ld_R + a.sumD] = 1.f;
+      for (int l = 0; l < a.HL; ++l) c.scratch[a.s_hh[l] + (long long)b * a.ld_hh[l] + a.head_w[l]] = 1.f;
+    }
+  }
   __syncthreads();
 }
 
@@ -357,6 +368,98 @@ __device__ Opnd decoder_hidden(const StepCtx& c, int m) {
   return A;
 }
 
+// ---- supervised head (NMB_HEAD_REGRESSION, cVAE_multimodal_regression, cVAE.py:2211-2347) ---------------------
+// Residual rows R = [x_0 - x_recon_0 | x_1 - x_recon_1 | ... | 1] from the targets and the kept reconstructions (:2321-2323).
+__device__ void head_residuals(const StepCtx& c) {
+  const ArchDesc& a = *c.a;
+  float* S = c.scratch;
+  for (int m = 0; m < a.M; ++m) {
+    const ModDesc& q = a.mod[m];
+    const float* x = c.xin[m] + (long long)c.row0 * q.ldx;
+    const float* xr = S + q.s_xr;
+    float* R = S + a.s_R + q.r_off;
+    for (int e = threadIdx.x; e < c.rows * q.D; e += kThreads) {
+      const int b = e / q.D, n = e - b * q.D;
+      R[(long long)b * a.ld_R + n] = x[(long long)b * q.ldx + n] - xr[(long long)b * q.ld_xh + n];
+    }
+  }
+  __syncthreads();
+}
+
+// regressor(R): Linear -> ReLU -> ... -> Linear(., 1) (:2248-2255); the prediction lands in s_pred[b * 4]
+template <bool TC>
+__device__ void head_forward(const StepCtx& c) {
+  const ArchDesc& a = *c.a;
+  float* S = c.scratch;
+  const float* P = c.mb->params;
+  Opnd A{S + a.s_R, a.ld_R, 1};
+  for (int l = 0; l < a.HL; ++l) {
+    const LinDesc& w = a.hd[l];
+    EpiHidden e{S + a.s_hh[l], a.ld_hh[l], 2};
+    mm<TC>(c, c.rows, w.out, w.in + 1, A, Opnd{P + w.off, w.ld, 1}, e);
+    A = Opnd{S + a.s_hh[l], a.ld_hh[l], 1};
+  }
+  const LinDesc& w = a.hd[a.HL];
+  EpiStore e{S + a.s_pred, 4};
+  mm<TC>(c, c.rows, 1, w.in + 1, A, Opnd{P + w.off, w.ld, 1}, e);
+}
+
+// Forward + MSE (:2343) + backward + Adam of the head; leaves d(total)/dR in s_dR (head_fold).  Returns the
+// regression loss (all threads).
+template <bool TC>
+__device__ float head_step(const StepCtx& c, const AdamCfg& ad) {
+  const ArchDesc& a = *c.a;
+  float* S = c.scratch;
+  const float* P = c.mb->params;
+  const int rows = c.rows;
+  head_residuals(c);
+  head_forward<TC>(c);
+  float acc = 0.f;
+  const float gsc = a.head_weight * 2.f / rows;
+  for (int b = threadIdx.x; b < rows; b += kThreads) {
+    const float yb = c.mb->y[c.yidx ? c.yidx[c.row0 + b] : c.row0 + b];
+    const float r = S[a.s_pred + 4 * b] - yb;
+    acc += r * r;
+    S[a.s_dpred + 4 * b] = gsc * r;
+  }
+  const float loss = block_sum(acc, c.red) / rows;
+  float* gbuf[2] = {S + a.s_ga, S + a.s_gb};
+  const float* dy = S + a.s_dpred; int ld_dy = 4;
+  int cur = 0;
+  for (int l = a.HL; l >= 0; --l) {
+    const LinDesc& w = a.hd[l];
+    const float* in_act = l == 0 ? S + a.s_R : S + a.s_hh[l - 1];
+    const int ld_in = l == 0 ? a.ld_R : a.ld_hh[l - 1];
+    if (l > 0) {
+      EpiDgrad eg{gbuf[cur], a.ld_g, in_act, ld_in, 2};
+      mm<TC>(c, rows, w.in, w.out, Opnd{dy, ld_dy, 1}, Opnd{P + w.off, w.ld, 0}, eg);
+    } else {
+      EpiStore es{S + a.s_dR, a.ld_R};
+      mm<TC>(c, rows, w.in, w.out, Opnd{dy, ld_dy, 1}, Opnd{P + w.off, w.ld, 0}, es);
+    }
+    EpiWgradAdam ew{ad, w.off, w.ld};
+    mm<TC>(c, w.out, w.in + 1, rows, Opnd{dy, ld_dy, 0}, Opnd{in_act, ld_in, 0}, ew);
+    if (l > 0) { dy = gbuf[cur]; ld_dy = a.ld_g; cur ^= 1; }
+  }
+  __syncthreads();
+  return loss;
+}
+
+// d(total)/d(x_recon_m) += -d(total)/dR (R = x - x_recon).  After the logvar_out gradient, which recovers the residuals
+// from the likelihood part of s_xh.
+__device__ void head_fold(const StepCtx& c, int m) {
+  const ArchDesc& a = *c.a;
+  const ModDesc& q = a.mod[m];
+  float* dxh = c.scratch + q.s_xh;
+  const float* dR = c.scratch + a.s_dR + q.r_off;
+  __syncthreads();
+  for (int e = threadIdx.x; e < c.rows * q.D; e += kThreads) {
+    const int b = e / q.D, n = e - b * q.D;
+    dxh[(long long)b * q.ld_xh + n] -= dR[(long long)b * a.ld_R + n];
+  }
+  __syncthreads();
+}
+
 // ---- one training step ---------------------------------------------------------------------
 template <bool TC>
 __device__ void train_step(StepCtx& c, const float* eps_src, float* loss_out) {
@@ -369,29 +472,31 @@ __device__ void train_step(StepCtx& c, const float* eps_src, float* loss_out) {
   const int gauss = a.loss_kind == NMB_LOSS_GAUSS_LL;
 
   // ---------------- forward ----------------
-  encoders_forward<TC>(c, mb.xc);
-  float kl = latent_forward(c, mb.xc, eps_src ? 1 : 0, eps_src, 0u, (unsigned long long)c.step);
+  encoders_forward<TC>(c, c.xin);
+  float kl = latent_forward(c, c.xin, eps_src ? 1 : 0, eps_src, 0u, (unsigned long long)c.step);
   kl = block_sum(kl, c.red) * inv_rows;
   float ll_sum = 0.f;
   for (int m = 0; m < M; ++m) {
     const ModDesc& q = a.mod[m];
     Opnd A = decoder_hidden<TC>(c, m);
     EpiRecon e;
-    e.x = mb.xc[m] + (long long)c.row0 * q.ldx; e.ldx = q.ldx;
+    e.x = c.xin[m] + (long long)c.row0 * q.ldx; e.ldx = q.ldx;
     e.lam = P + q.lam_off;
     e.dxh = S + q.s_xh; e.ld = q.ld_xh;
-    e.keep = (c.flags & NMB_TRAIN_KEEP_ACTS) ? S + q.s_xr : nullptr;
+    e.keep = ((c.flags & NMB_TRAIN_KEEP_ACTS) || a.head_kind) ? S + q.s_xr : nullptr;
     e.inv_rows = inv_rows; e.inv_rows_d = inv_rows / q.D; e.gauss = gauss; e.ll_acc = 0.f;
     mm<TC>(c, rows, q.D, q.outl.in + 1, A, Opnd{P + q.outl.off, q.outl.ld, 1}, e);
     const float s = block_sum(e.ll_acc, c.red);
     ll_sum += gauss ? s * inv_rows : s * inv_rows / q.D;
   }
-  if (loss_out && threadIdx.x == 0) {
-    loss_out[0] = M * kl - ll_sum; loss_out[1] = M * kl; loss_out[2] = ll_sum;   // cVAE.py:1187-1196
-  }
-
   // ---------------- backward + Adam ----------------
   const AdamCfg ad = make_adam(c);
+  float head_loss = 0.f;
+  if (a.head_kind) head_loss = head_step<TC>(c, ad);
+  if (loss_out && threadIdx.x == 0) {
+    loss_out[0] = M * kl - ll_sum + a.head_weight * head_loss; loss_out[1] = M * kl; loss_out[2] = ll_sum;   // cVAE.py:1187-1196
+    if (c.flags & NMB_TRAIN_LOSS4) loss_out[3] = head_loss;                                                // cVAE.py:2343-2345
+  }
   float* gbuf[2] = {S + a.s_ga, S + a.s_gb};
   for (int m = 0; m < M; ++m) {
     const ModDesc& q = a.mod[m];
@@ -414,6 +519,7 @@ __device__ void train_step(StepCtx& c, const float* eps_src, float* loss_out) {
         ad.apply(q.lam_off + n, acc * inv_rows);
       }
     }
+    if (a.head_kind) head_fold(c, m);
     int cur = 0;
     // decoder_mean_layer
     {
@@ -493,7 +599,7 @@ __device__ void train_step(StepCtx& c, const float* eps_src, float* loss_out) {
     for (int l = L - 1; l >= 0; --l) {
       const LinDesc& w = q.enc[l];
       const float* dy = gbuf[cur];
-      const float* in_act = l == 0 ? mb.xc[m] + (long long)c.row0 * q.ldx : S + q.s_h[l - 1];
+      const float* in_act = l == 0 ? c.xin[m] + (long long)c.row0 * q.ldx : S + q.s_h[l - 1];
       const int ld_in = l == 0 ? q.ldx : q.ld_h[l - 1];
       if (l > 0) {
         EpiDgrad eg{gbuf[cur ^ 1], a.ld_g, in_act, ld_in, a.non_linear};
@@ -504,6 +610,28 @@ __device__ void train_step(StepCtx& c, const float* eps_src, float* loss_out) {
       cur ^= 1;
     }
   }
+}
+
+// Members trained through shuffling loaders: copy the minibatch rows each modality's permutation selects into the
+// staging buffers and point xin at them (xin[m] + row0 * ldx = staged row 0).
+__device__ void stage_rows(StepCtx& c, long long epoch, const float** xin) {
+  const ArchDesc& a = *c.a;
+  const MemberDev& mb = *c.mb;
+  __syncthreads();
+  for (int m = 0; m < a.M; ++m) {
+    const ModDesc& q = a.mod[m];
+    const int* ord = mb.row_order + (epoch * a.M + m) * (long long)mb.n_rows + c.row0;
+    float* dst = c.scratch + q.s_in;
+    const int w4 = q.ldx / 4;
+    for (int e = threadIdx.x; e < c.rows * w4; e += kThreads) {
+      const int b = e / w4, j = e - b * w4;
+      reinterpret_cast<float4*>(dst + (long long)b * q.ldx)[j] =
+          reinterpret_cast<const float4*>(mb.xc[m] + (long long)ord[b] * q.ldx)[j];
+    }
+    if (threadIdx.x == 0) xin[m] = dst - (long long)c.row0 * q.ldx;
+  }
+  c.yidx = mb.row_order + epoch * a.M * (long long)mb.n_rows;       // the target follows modality 0's loader
+  __syncthreads();
 }
 
 // ---- kernels -------------------------------------------------------------------------------
@@ -530,6 +658,10 @@ __device__ __forceinline__ void train_body(const TrainLaunch& t, float* smem_f, 
     c.scratch = t.scratch + (long long)blockIdx.x * t.slot_floats;
     c.b1 = mb.beta1; c.b2 = mb.beta2; c.aeps = mb.adam_eps;
     prepare_slot(c);
+    __shared__ const float* s_xin[NMB_MAX_MOD];
+    if (threadIdx.x < NMB_MAX_MOD) s_xin[threadIdx.x] = mb.xc[threadIdx.x];
+    c.xin = s_xin; c.yidx = nullptr;
+    __syncthreads();
     const int spe = (mb.n_rows + mb.batch - 1) / mb.batch;   // steps per epoch
     const long long s0 = mb.steps_done;
     int rows = 0;
@@ -540,13 +672,14 @@ __device__ __forceinline__ void train_body(const TrainLaunch& t, float* smem_f, 
       c.step = s;
       c.row0 = pos * mb.batch;
       c.rows = rows = min(mb.batch, mb.n_rows - c.row0);
+      if (mb.row_order) stage_rows(c, s / spe, s_xin);      // this epoch's per-modality permutations
       const double tt = (double)(s + 1);
       const float lr = mb.lr_steps ? mb.lr_steps[s] : mb.lr;
       c.step_size = (float)((double)lr / (1.0 - pow((double)mb.beta1, tt)));
       c.bc2_sqrt = (float)sqrt(1.0 - pow((double)mb.beta2, tt));
       const float* eps = t.eps_override
           ? t.eps_override + ((long long)mi * t.stride_steps + i) * mb.batch * a.Z : nullptr;
-      float* lo = t.loss_out ? t.loss_out + ((long long)mi * t.stride_steps + i) * 3 : nullptr;
+      float* lo = t.loss_out ? t.loss_out + ((long long)mi * t.stride_steps + i) * ((t.flags & NMB_TRAIN_LOSS4) ? 4 : 3) : nullptr;
       train_step<TC>(c, eps, lo);
     }
     __syncthreads();
@@ -618,6 +751,8 @@ __device__ __forceinline__ void recon_body(const ReconLaunch& t, float* smem_f, 
     c.scratch = t.scratch + (long long)blockIdx.x * t.slot_floats;
     c.rows = item.rows; c.row0 = item.row0; c.step = 0;
     const float* const* xc = t.xc + (long long)item.member * NMB_MAX_MOD;
+    c.xin = xc; c.yidx = nullptr;
+    float* head_out = (a.head_kind && t.head_out) ? t.head_out[item.member] : nullptr;
     prepare_slot(c);
     if (t.mode != NMB_RECON_GIVEN_Z) encoders_forward<TC>(c, xc);
     const float* eps = (t.mode != NMB_RECON_MEAN && t.eps && t.eps[item.member])
@@ -637,9 +772,27 @@ __device__ __forceinline__ void recon_body(const ReconLaunch& t, float* smem_f, 
       const ModDesc& q = a.mod[m];
       Opnd A = decoder_hidden<TC>(c, m);
       float* out = t.xhat[(long long)item.member * NMB_MAX_MOD + m];
+      if (head_out) {      // the head reads the reconstructions from scratch
+        EpiStore e{c.scratch + q.s_xr, q.ld_xh};
+        mm<TC>(c, item.rows, q.D, q.outl.in + 1, A, Opnd{mb.params + q.outl.off, q.outl.ld, 1}, e);
+        __syncthreads();
+        if (out)
+          for (int e2 = threadIdx.x; e2 < item.rows * q.D; e2 += kThreads) {
+            const int b = e2 / q.D, n = e2 - b * q.D;
+            out[(long long)(item.row0 + b) * q.D + n] = c.scratch[q.s_xr + (long long)b * q.ld_xh + n];
+          }
+        continue;
+      }
       if (!out) continue;
       EpiStore e{out + (long long)item.row0 * q.D, q.D};
       mm<TC>(c, item.rows, q.D, q.outl.in + 1, A, Opnd{mb.params + q.outl.off, q.outl.ld, 1}, e);
+    }
+    if (head_out) {        // fi_pred = regressor(cat(x_m - x_recon_m.loc)) (cVAE.py:2321-2325)
+      __syncthreads();
+      head_residuals(c);
+      head_forward<TC>(c);
+      __syncthreads();
+      for (int b = threadIdx.x; b < item.rows; b += kThreads) head_out[item.row0 + b] = c.scratch[a.s_pred + 4 * b];
     }
     __syncthreads();
   }

@@ -23,6 +23,7 @@ _SLOT_NAMES = {
     _lib.SLOT_ENC_LOGVAR: "encoder_list.{m}.enc_logvar_layer",
     _lib.SLOT_DEC: "decoder_list.{m}.decoder_layers.{l}",
     _lib.SLOT_DEC_MEAN: "decoder_list.{m}.decoder_mean_layer",
+    _lib.SLOT_HEAD: "regressor.{l2}",        # nn.Sequential(Linear, ReLU, Linear, ReLU, Linear): linears at 0, 2, 4
 }
 
 
@@ -68,6 +69,12 @@ class MemberSpec:
     adam_eps: float = 1e-8
     lr_steps: Optional[torch.Tensor] = None   # per-step LR (float32 CUDA) for the nmmlp cyclic schedule
     state_dict: Optional[Dict[str, torch.Tensor]] = None   # initial weights, reference names
+    # supervised head (f3): "regression" = cVAE_multimodal_regression (cVAE.py:2211-2347)
+    head: Optional[str] = None
+    head_hidden: Sequence[int] = (128, 64)
+    head_weight: float = 1.0               # lambda_reg
+    y: Optional[torch.Tensor] = None       # head target per training row (float32 CUDA [N])
+    row_order: Optional[torch.Tensor] = None   # int32 CUDA [epochs, n_mod, N]: per-epoch, per-modality loader permutations
     tag: object = None                     # caller bookkeeping, e.g. (fold, modality, seed)
     _arch: object = field(default=None, repr=False)
 
@@ -91,9 +98,10 @@ class EnsembleTrainer:
         total = 0
         for s in self.specs:
             key = (tuple(s.input_dims), tuple(s.hidden), s.latent, s.c_dim, s.combine.lower(), s.loss_kind,
-                   bool(s.non_linear))
+                   bool(s.non_linear), s.head, tuple(s.head_hidden) if s.head else (), float(s.head_weight) if s.head else 0.0)
             if key not in cache:
-                arch = _lib.make_arch(s.input_dims, s.hidden, s.latent, s.c_dim, s.combine, s.loss_kind, s.non_linear)
+                arch = _lib.make_arch(s.input_dims, s.hidden, s.latent, s.c_dim, s.combine, s.loss_kind, s.non_linear,
+                                      head=s.head, head_hidden=s.head_hidden, head_weight=s.head_weight)
                 cache[key] = (arch, _lib.arch_slots(arch), _lib.arch_param_count(arch))
             arch, slots, npar = cache[key]
             s._arch = arch
@@ -134,6 +142,21 @@ class EnsembleTrainer:
                 self._keep.append(lr)
                 m.lr_steps = lr.data_ptr()
                 m.n_lr_steps = int(lr.numel())
+            if s.head:
+                if s.y is None:
+                    raise ValueError(f"member {i}: a supervised head needs targets y")
+                y = s.y.to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
+                if y.numel() != n_rows:
+                    raise ValueError("one target per training row")
+                self._keep.append(y)
+                m.y = y.data_ptr()
+            if s.row_order is not None:
+                ro = s.row_order.to(device=dev, dtype=torch.int32).contiguous()
+                if ro.dim() != 3 or ro.shape[1] != len(s.input_dims) or ro.shape[2] != n_rows:
+                    raise ValueError("row_order must be [epochs, n_mod, n_rows]")
+                self._keep.append(ro)
+                m.row_order = ro.data_ptr()
+                m.n_order_epochs = int(ro.shape[0])
             off = self.offsets[i] * 4
             m.params = self.params.data_ptr() + off
             m.adam_m = self.adam_m.data_ptr() + off
@@ -174,7 +197,7 @@ class EnsembleTrainer:
             elif s.kind == _lib.SLOT_LOGVAR_OUT:
                 out[f"decoder_list.{s.modality}.logvar_out"] = flat[base + s.offset: base + s.offset + s.cols].view(1, s.cols)
             else:
-                name = _SLOT_NAMES[s.kind].format(m=s.modality, l=s.layer)
+                name = _SLOT_NAMES[s.kind].format(m=s.modality, l=s.layer, l2=2 * s.layer)
                 mat = seg.view(s.rows, s.ld)
                 out[name + ".weight"] = mat[:, : s.cols]
                 out[name + ".bias"] = mat[:, s.cols]
@@ -217,10 +240,12 @@ class EnsembleTrainer:
         state-conversion launches less per call); the packed tensors are refreshed by ``sync()``.
 
         eps: optional injected draws [n_members, n_steps, batch, latent] (per-step parity);
-        returns [n_members, n_steps, 3] (total, kl, ll) when record_losses."""
+        returns [n_members, n_steps, 3] (total, kl, ll) when record_losses -- [.., 4] with the head loss
+        (losses['regression']) last when flags has TRAIN_LOSS4."""
         losses = None
         if record_losses:
-            losses = torch.zeros((self.n, n_steps, 3), dtype=torch.float32, device=self.device)
+            losses = torch.zeros((self.n, n_steps, 4 if (int(flags) & _lib.TRAIN_LOSS4) else 3), dtype=torch.float32,
+                                 device=self.device)
         eps_ptr = None
         if eps is not None:
             b, z = int(self._members[0].batch), int(self.specs[0].latent)
@@ -266,8 +291,8 @@ class EnsembleTrainer:
         first epochs * steps_per_epoch[i] rows; the rest is NaN)."""
         losses = None
         if record_losses:
-            losses = torch.full((self.n, epochs * max(self.steps_per_epoch), 3), float("nan"), dtype=torch.float32,
-                                device=self.device)
+            losses = torch.full((self.n, epochs * max(self.steps_per_epoch), 4 if (int(flags) & _lib.TRAIN_LOSS4) else 3),
+                                float("nan"), dtype=torch.float32, device=self.device)
         if (flags & _lib.TRAIN_WRITE_GRADS) and self.grads is None:
             raise RuntimeError("TRAIN_WRITE_GRADS needs keep_grads=True")
         with torch.cuda.device(self.device):
@@ -365,6 +390,40 @@ class EnsembleTrainer:
         return outs, (mus if want_latent else None), (lvs if want_latent else None)
 
 
+def head_predict(trainer: "EnsembleTrainer", xc, mode: str = "sample", eps=None, engine: str = "tcs", want_xhat: bool = False):
+    """``fi_pred`` of cVAE_multimodal_regression.forward_multimodal (cVAE.py:2309-2332) for every member on its own packed
+    rows: [n_rows_i] per member (and the reconstructions when want_xhat).  mode / eps as in ``reconstruct``."""
+    self = trainer
+    eng_bits = {"tcs": _lib.RECON_TC_SIMPLE, "fp32": _lib.RECON_FP32}[engine]
+    tbl, rows, outs, xh_tbl, xhs = [], [], [], [], []
+    for i, s in enumerate(self.specs):
+        n_i = int(xc[i][0].shape[0])
+        rows.append(n_i)
+        outs.append(torch.empty(n_i, dtype=torch.float32, device=self.device) if s.head else None)
+        row = []
+        for k in range(_lib.NMB_MAX_MOD):
+            if k < len(s.input_dims):
+                tbl.append(xc[i][k].data_ptr())
+                o = torch.empty((n_i, int(s.input_dims[k])), dtype=torch.float32, device=self.device) if want_xhat else None
+                xh_tbl.append(o.data_ptr() if want_xhat else None); row.append(o)
+            else:
+                tbl.append(None); xh_tbl.append(None)
+        xhs.append(row)
+    eps_keep = None
+    if eps is not None:
+        eps_keep = [None if e is None else e.to(device=self.device, dtype=torch.float32).contiguous() for e in eps]
+    with torch.cuda.device(self.device):
+        _lib.check(self.lib.nmb_ensemble_head_predict(
+            self.handle, _lib.ptr_table(tbl), _lib.int_table(rows),
+            {"mean": _lib.RECON_MEAN, "sample": _lib.RECON_SAMPLE}[mode] | eng_bits,
+            _lib.ptr_table([e.data_ptr() if e is not None else None for e in eps_keep]) if eps_keep is not None else None,
+            _lib.ptr_table(xh_tbl) if want_xhat else None,
+            _lib.ptr_table([o.data_ptr() if o is not None else None for o in outs]), _stream_ptr(self.device)),
+            "nmb_ensemble_head_predict")
+    self.gpu_launches += 1
+    return (outs, xhs) if want_xhat else outs
+
+
 def _normalise_names(sd):
     """Accept single-modality ``cVAE`` names (encoder.* / decoder.*, cVAE.py:408-409) as modality 0."""
     out = {}
@@ -377,3 +436,6 @@ def _normalise_names(sd):
     if "alpha_m_list.0" not in out:
         out["alpha_m_list.0"] = torch.zeros(1)
     return out
+
+
+EnsembleTrainer.head_predict = head_predict

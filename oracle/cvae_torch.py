@@ -263,3 +263,61 @@ def cyclic_lr(step, n_samples, batch_size=256, base_lr=1e-6, max_lr=5e-5, gamma=
     cycle = np.floor(1 + step / (2 * step_size))
     x_lr = np.abs(step / step_size - 2 * cycle + 1)
     return float(base_lr + (max_lr - base_lr) * max(0, 1 - x_lr) * gamma ** cycle)
+
+
+class OracleCVAERegression(OracleCVAEMultimodal):
+    """``cVAE_multimodal_regression`` (cVAE.py:2211-2347): the multimodal cVAE plus an MLP on the concatenated
+    residuals x_m - x_recon_m.loc that predicts a scalar target (FI).  RNG order of the constructor: encoders,
+    decoders, alphas, regressor (:2231-2255); Adam over encoders, decoders, regressor, alphas (:2260-2266)."""
+
+    def __init__(self, input_dim_list, hidden_dim, latent_dim, c_dim, learning_rate=1e-4, modalities=3, non_linear=False,
+                 head_hidden=(128, 64)):
+        nn.Module.__init__(self)
+        hd = list(hidden_dim) + [latent_dim]
+        self.modalities = modalities
+        self.loss_kind = "gauss_ll"
+        self.encoder_list = nn.ModuleList(
+            [OracleEncoder(input_dim_list[i], hd, c_dim, non_linear) for i in range(modalities)])
+        self.decoder_list = nn.ModuleList(
+            [OracleDecoder(input_dim_list[i], hd, c_dim, non_linear) for i in range(modalities)])
+        self.alpha_m_list = nn.ParameterList([nn.Parameter(torch.randn(1)) for _ in range(modalities)])
+        widths = [sum(input_dim_list[:modalities])] + list(head_hidden)
+        layers = []
+        for a, b in zip(widths[:-1], widths[1:]):
+            layers += [nn.Linear(a, b), nn.ReLU()]
+        layers.append(nn.Linear(widths[-1], 1))
+        self.regressor = nn.Sequential(*layers)
+        self.optimizer1 = torch.optim.Adam(
+            list(self.encoder_list.parameters()) + list(self.decoder_list.parameters())
+            + list(self.regressor.parameters()) + list(self.alpha_m_list.parameters()), lr=learning_rate)
+
+    def step_losses(self, xs, cs, combine, eps=None, true_fi=None, lambda_reg=1.0):
+        """forward_multimodal (:2309-2332) + loss_function_multimodal (:2334-2347)."""
+        out = super().step_losses(xs, cs, combine, eps)
+        resid = torch.cat([xs[i] - out["x_recons"][i] for i in range(self.modalities)], dim=1)
+        out["fi_pred"] = self.regressor(resid)
+        if true_fi is not None:
+            out["regression"] = torch.mean((out["fi_pred"].squeeze() - true_fi.squeeze()) ** 2)      # nn.MSELoss
+            out["total"] = out["total"] + lambda_reg * out["regression"]
+        return out
+
+
+def regression_train_loop(model, xs, cs, fi, order, combine, batch_size, eps_steps):
+    """Loop body of multimodal_kfold_train_cvae_supervised_regression.py:119-131 with the shuffling loaders made
+    explicit: order[epoch][m] is the permutation modality m's DataLoader(shuffle=True) yields in that epoch (one
+    independent permutation per modality, :94); the target comes from modality 0's loader (:125).
+    Returns per-step (total, kl, ll, regression)."""
+    n = xs[0].shape[0]
+    log, step = [], 0
+    for ep in range(order.shape[0]):
+        for lo in range(0, n, batch_size):
+            idx = [torch.as_tensor(order[ep, m, lo:lo + batch_size], dtype=torch.long) for m in range(model.modalities)]
+            xb = [xs[m][idx[m]] for m in range(model.modalities)]
+            cb = [cs[idx[m]] for m in range(model.modalities)]
+            out = model.step_losses(xb, cb, combine, torch.as_tensor(eps_steps[step][: xb[0].shape[0]]), fi[idx[0]])
+            model.optimizer1.zero_grad()
+            out["total"].backward()
+            model.optimizer1.step()
+            log.append((float(out["total"]), float(out["kl"]), float(out["ll"]), float(out["regression"])))
+            step += 1
+    return np.asarray(log, dtype=np.float64)

@@ -157,7 +157,8 @@ def _knife_scan(model, run):
     executed by run(): {layer name: sorted unit indices}."""
     pre, hooks = {}, []
     for pname, mod in model.named_modules():
-        if isinstance(mod, torch.nn.Linear) and (".encoder_layers." in pname or ".decoder_layers." in pname):
+        if isinstance(mod, torch.nn.Linear) and (".encoder_layers." in pname or ".decoder_layers." in pname
+                                                 or pname in ("regressor.0", "regressor.2")):
             def _keep(_m, _i, o, pname=pname):      # must return None: a returned value would replace the output
                 pre.setdefault(pname, []).append(o.detach().clone())
             hooks.append(mod.register_forward_hook(_keep))
@@ -556,6 +557,96 @@ def stored_deviation_case():
     print("stored_deviation ok")
 
 
+def _regression_inputs(ref, dims, hidden, z, n, b, epochs, seed, n_test):
+    m = len(dims)
+    rng = np.random.RandomState(seed)
+    torch.manual_seed(seed)
+    model = ref.cVAE_multimodal_regression(input_dim_list=list(dims), hidden_dim=list(hidden), latent_dim=z, c_dim=2,
+                                           learning_rate=1e-4, modalities=m, non_linear=True)
+    xs = [rng.randn(n, d).astype(np.float32) for d in dims]
+    # raw covariates like the trainer's train_dataset_df[['AGE', 'PTGENDER']] (..._regression.py:83), unscaled
+    c = np.stack([rng.uniform(22, 36, n).round(0), rng.randint(1, 3, n)], 1).astype(np.float32)
+    fi = (rng.randn(n, 1) * 4 + 17).astype(np.float32)            # fluid-intelligence-like target (:86)
+    # DataLoader(shuffle=True): an independent permutation per modality loader and epoch (:94, :122)
+    order = np.stack([np.stack([rng.permutation(n) for _ in range(m)]) for _ in range(epochs)]).astype(np.int32)
+    steps = epochs * len(_loop_batches(n, b))
+    eps = rng.randn(steps, b, z).astype(np.float32)
+    xt = [rng.randn(n_test, d).astype(np.float32) for d in dims]
+    ct = np.stack([rng.uniform(22, 36, n_test).round(0), rng.randint(1, 3, n_test)], 1).astype(np.float32)
+    eps_t = rng.randn(n_test, z).astype(np.float32)
+    return model, xs, c, fi, order, eps, xt, ct, eps_t
+
+
+def ref_regression_case(ref, name, dims, hidden, z, n, b, combine, epochs, seed, n_test=70, tries=300):
+    """f3: the UNMODIFIED cVAE_multimodal_regression (cVAE.py:2211-2347) through the loop body of
+    multimodal_kfold_train_cvae_supervised_regression.py:119-131 -- per-modality shuffled loaders (recorded as `order`),
+    injected eps -- then the evaluation pass of :137-152.  Per-step losses (total, kl, ll, regression), step-0
+    gradients, post-Adam parameters, test fi_pred and reconstructions."""
+    m = len(dims)
+    batches = _loop_batches(n, b)
+
+    def fwd_loss(model, xs_t, c_t, fi_t, order, eps, s):
+        ep, k = divmod(s, len(batches))
+        r0, rows = batches[k]
+        idx = [torch.from_numpy(order[ep, i, r0:r0 + rows].astype(np.int64)) for i in range(m)]
+        xb = [xs_t[i][idx[i]] for i in range(m)]
+        cb = [c_t[idx[i]] for i in range(m)]
+        with injected_eps([torch.from_numpy(eps[s][:rows])]):
+            fwd = model.forward_multimodal(xb, cb, combine)
+        return fwd, model.loss_function_multimodal(xb, fwd, fi_t[idx[0]], lambda_reg=1.0)
+
+    best = None
+    for t in range(tries):          # a seed without knife-edge units in the recorded gradient step (see clean_seed)
+        sd = seed + 1000 * t
+        model, xs, c, fi, order, eps, _, _, _ = _regression_inputs(ref, dims, hidden, z, n, b, epochs, sd, n_test)
+        xs_t, c_t, fi_t = [torch.from_numpy(x) for x in xs], torch.from_numpy(c), torch.from_numpy(fi)
+        kn = _knife_scan(model, lambda: fwd_loss(model, xs_t, c_t, fi_t, order, eps, 0))
+        score = sum(len(v) for v in kn.values())
+        if best is None or score < best[0]:
+            best = (score, sd)
+        if score == 0:
+            break
+    seed = best[1]
+    print("  seed", seed, "knife edges:", best[0])
+    model, xs, c, fi, order, eps, xt, ct, eps_t = _regression_inputs(ref, dims, hidden, z, n, b, epochs, seed, n_test)
+    xs_t, c_t, fi_t = [torch.from_numpy(x) for x in xs], torch.from_numpy(c), torch.from_numpy(fi)
+    out = {"dims": np.array(dims), "hidden": np.array(hidden), "z": z, "c_dim": 2, "combine": combine, "seed": seed,
+           "n": n, "batch": b, "epochs": epochs, "c": c, "fi": fi, "order": order, "eps": eps}
+    for k, v in sd_np(model).items():
+        out["init/" + k] = v
+    for i, x in enumerate(xs):
+        out[f"x{i}"] = x
+    for pname, units in _knife_scan(model, lambda: fwd_loss(model, xs_t, c_t, fi_t, order, eps, 0)).items():
+        out["knife/" + pname] = units
+    model.train()
+    losses = []
+    for s_ in range(epochs * len(batches)):
+        fwd, loss = fwd_loss(model, xs_t, c_t, fi_t, order, eps, s_)
+        model.optimizer1.zero_grad()
+        loss["total"].backward()
+        if s_ == 0:
+            out["mu"] = fwd["mu_multimodal"].detach().numpy().copy()
+            out["fi_pred0"] = fwd["fi_pred"].detach().numpy().copy()
+            for k, p in model.named_parameters():
+                if p.grad is not None:
+                    out["grad/" + k] = p.grad.detach().numpy().copy()
+        model.optimizer1.step()
+        losses.append([float(loss["total"]), float(loss["kl"]), float(loss["ll"]), float(loss["regression"])])
+    out["losses"] = np.array(losses, dtype=np.float64)
+    for k, v in sd_np(model).items():
+        out["final/" + k] = v
+    model.eval()
+    with torch.no_grad(), injected_eps([torch.from_numpy(eps_t)]):
+        fwd = model.forward_multimodal([torch.from_numpy(x) for x in xt], [torch.from_numpy(ct) for _ in dims], combine)
+    out["ct"] = ct; out["eps_test"] = eps_t
+    out["fi_pred_test"] = fwd["fi_pred"].numpy().copy()
+    for i in range(m):
+        out[f"xt{i}"] = xt[i]
+        out[f"pred{i}"] = fwd["x_recons"][i].loc.numpy().copy()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, "ok", losses[0], "->", losses[-1])
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     sys.path.insert(0, REF)
@@ -567,6 +658,10 @@ def main():
             sd = clean_seed(mm, [116, 116, 116, 348], [110, 110], 10, 29, 288, 256, 2, 46, 27, [comb])
             ref_loop_case(ref, "mm_M4_full_" + comb.lower(), [116, 116, 116, 348], [110, 110], 10, 29, 288, 256, comb, 2,
                           sd, 27, lean=lean)
+        return
+    if "--f3" in sys.argv:
+        ref_regression_case(ref, "reg_M3_full_gpoe", [116, 116, 116], [110, 110], 10, 300, 128, "gpoe", 2, 7)
+        ref_regression_case(ref, "reg_M2_small_poe", [13, 6], [11, 9], 4, 23, 10, "poe", 3, 8, n_test=9)
         return
     if "--round2b" in sys.argv:
         pieces_case(ref); latent_case(); ref_pickle_case(ref)

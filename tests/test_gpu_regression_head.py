@@ -1,0 +1,112 @@
+"""f3: the supervised regression head -- ``cVAE_multimodal_regression`` (cVAE.py:2211-2347) trained like
+multimodal_kfold_train_cvae_supervised_regression.py:119-131 (per-modality shuffling loaders, target from modality 0)
+and evaluated like :137-152 -- through the C ABI on both generic engines, against vectors recorded from the unmodified
+reference (oracle/make_golden.py --f3).  Tolerance 1e-4 relative per step (north_star); Adam trajectories by
+helpers.assert_update_close."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import assert_grads_close, assert_update_close, load, relerr, sub
+
+pytestmark = pytest.mark.gpu
+REL = 1e-4
+CASES = ["reg_M3_full_gpoe", "reg_M2_small_poe"]
+ENGINES = ["tcs", "fp32"]
+
+
+def engine_flags(engine):
+    from multi_modal_normative_modeling_b200 import _lib
+    return {"tcs": _lib.TRAIN_TC_SIMPLE, "fp32": _lib.TRAIN_FP32}[engine]
+
+
+def make_trainer(g, sd_prefix="init/", keep_grads=True, order=True):
+    from multi_modal_normative_modeling_b200 import EnsembleTrainer, MemberSpec, pack_rows
+    dims = [int(d) for d in g["dims"]]
+    c = torch.from_numpy(g["c"]).cuda()
+    xc = [pack_rows(torch.from_numpy(g[f"x{i}"]).cuda(), c) for i in range(len(dims))]
+    sd = {k: torch.from_numpy(v) for k, v in sub(g, sd_prefix).items()}
+    spec = MemberSpec(input_dims=dims, hidden=[int(h) for h in g["hidden"]], latent=int(g["z"]), c_dim=2, xc=xc,
+                      combine=str(g["combine"]), batch=int(g["batch"]), seed=5, state_dict=sd, head="regression",
+                      y=torch.from_numpy(g["fi"]).cuda(), row_order=torch.from_numpy(g["order"]).cuda() if order else None)
+    return EnsembleTrainer([spec], keep_grads=keep_grads)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("name", CASES)
+def test_regression_step_vs_reference(golden_dir, name, engine):
+    from multi_modal_normative_modeling_b200 import _lib
+    g = load(golden_dir, name)
+    tr = make_trainer(g)
+    assert tr.engine() == "tcgen05-generic"          # members with a head never take the pipelined kernel
+    flags = engine_flags(engine) | _lib.TRAIN_NO_ADAM | _lib.TRAIN_WRITE_GRADS | _lib.TRAIN_KEEP_ACTS | _lib.TRAIN_LOSS4
+    losses = tr.train_steps(1, eps=torch.from_numpy(g["eps"][:1]).cuda()[None], record_losses=True, flags=flags)
+    torch.cuda.synchronize()
+    got = losses[0, 0].cpu().numpy()
+    assert got.shape == (4,)
+    assert np.allclose(got, g["losses"][0], rtol=REL), (got, g["losses"][0])      # total, kl, ll, regression
+    mu, _, _ = tr.peek(0)
+    assert relerr(mu.cpu().numpy(), g["mu"]) < REL
+    grads = tr.state_dict(0, "grads")
+    assert {k for k in grads if k.startswith("regressor.")} == {f"regressor.{l}.{w}" for l in (0, 2, 4) for w in ("weight", "bias")}
+    assert_grads_close(g, "grad/", grads, REL, to_numpy=lambda t: t.cpu().numpy())
+    for k, v in sub(g, "init/").items():
+        assert np.array_equal(tr.state_dict(0)[k].cpu().numpy().reshape(v.shape), v), k
+    tr.close()
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("name", CASES)
+def test_regression_epochs_with_adam_vs_reference(golden_dir, name, engine):
+    from multi_modal_normative_modeling_b200 import _lib
+    g = load(golden_dir, name)
+    tr = make_trainer(g, keep_grads=False)
+    steps = g["eps"].shape[0]
+    losses = tr.train_steps(steps, eps=torch.from_numpy(g["eps"]).cuda()[None], record_losses=True,
+                            flags=engine_flags(engine) | _lib.TRAIN_LOSS4)
+    torch.cuda.synchronize()
+    got, want = losses[0].cpu().numpy().astype(np.float64), g["losses"]
+    for col, rel in ((0, REL), (2, REL), (3, 10 * REL), (1, 10 * REL)):      # kl / head loss after Adam steps: see helpers
+        assert np.allclose(got[:, col], want[:, col], rtol=rel), (col, got[:, col], want[:, col])
+    sd, init, g0 = tr.state_dict(0), sub(g, "init/"), sub(g, "grad/")
+    for k, v in sub(g, "final/").items():
+        assert_update_close(k, sd[k].cpu().numpy().reshape(v.shape), v, init[k], steps, 1e-4, engine == "fp32", g0.get(k))
+    # the per-epoch permutations cover exactly `epochs` epochs: one more step must be refused, not read out of bounds
+    with pytest.raises(RuntimeError, match="row_order covers"):
+        tr.train_steps(1, flags=engine_flags(engine))
+    tr.close()
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("name", CASES)
+def test_regression_predict_vs_reference(golden_dir, name, engine):
+    """Evaluation pass (..._regression.py:137-152): fi_pred and the reconstructions of the trained model."""
+    from multi_modal_normative_modeling_b200 import pack_rows
+    g = load(golden_dir, name)
+    tr = make_trainer(g, sd_prefix="final/", keep_grads=False)
+    dims = [int(d) for d in g["dims"]]
+    ct = torch.from_numpy(g["ct"]).cuda()
+    xt = [pack_rows(torch.from_numpy(g[f"xt{i}"]).cuda(), ct) for i in range(len(dims))]
+    pred, xh = tr.head_predict([xt], mode="sample", eps=[torch.from_numpy(g["eps_test"]).cuda()], engine=engine, want_xhat=True)
+    torch.cuda.synchronize()
+    for i in range(len(dims)):
+        assert relerr(xh[0][i].cpu().numpy(), g[f"pred{i}"]) < REL, i
+    assert relerr(pred[0].cpu().numpy(), g["fi_pred_test"].ravel()) < 2 * REL
+    only = tr.head_predict([xt], mode="sample", eps=[torch.from_numpy(g["eps_test"]).cuda()], engine=engine)
+    assert torch.equal(only[0], pred[0])
+    tr.close()
+
+
+def test_head_members_are_validated():
+    from multi_modal_normative_modeling_b200 import EnsembleTrainer, MemberSpec, pack_rows
+    x = torch.randn(20, 6, device="cuda"); c = torch.randn(20, 2, device="cuda")
+    xc = [pack_rows(x, c)]
+    with pytest.raises(ValueError, match="needs targets"):
+        EnsembleTrainer([MemberSpec([6], [5], 3, 2, xc, head="regression")])
+    with pytest.raises(RuntimeError, match="supervised head only"):
+        EnsembleTrainer([MemberSpec([6], [5], 3, 2, xc, row_order=torch.zeros((1, 1, 20), dtype=torch.int32, device="cuda"))])
+    tr = EnsembleTrainer([MemberSpec([6], [5], 3, 2, xc)])
+    with pytest.raises(RuntimeError, match="LOSS4"):
+        from multi_modal_normative_modeling_b200 import _lib
+        tr.train_steps(1, record_losses=True, flags=_lib.TRAIN_LOSS4)
+    tr.close()
