@@ -2,4 +2,5 @@
 ``cVAE.<Class>``, so a ``cVAE_model.pkl`` written by the reference resolves to the drop-in classes
 here when this directory is on ``sys.path`` (the multimodal_kfold_* programs run from it)."""
 from multi_modal_normative_modeling_b200.cVAE import (  # noqa: F401
-    DEVICE, Decoder, Discriminator, Encoder, cVAE, cVAE_multimodal, cVAE_multimodal_endtoend, compute_ll, fuse_latent)
+    DEVICE, Decoder, Discriminator, Encoder, cVAE, cVAE_multimodal, cVAE_multimodal_endtoend, cVAE_multimodal_regression,
+    compute_ll, fuse_latent)

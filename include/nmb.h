@@ -241,10 +241,11 @@ int nmb_ensemble_reconstruct(NmbEnsemble* ens, const float* const* xc, const int
 /* Members with a supervised head (NMB_HEAD_REGRESSION): the head's prediction for every row of xc -- `fi_pred` of
  * cVAE_multimodal_regression.forward_multimodal (cVAE.py:2309-2332): encode, fuse, z = mu + eps*std (mode SAMPLE: the
  * reference samples at test time too, ..._regression.py:146-152; eps[i] injected or Philox), decode, residuals,
- * regressor.  out[i]: [n_rows[i]] (NULL entries / members without a head are skipped); xhat: optional table as in
- * nmb_ensemble_reconstruct (may be NULL). */
+ * regressor.  out[i]: [n_rows[i]] (NULL entries / members without a head are skipped); xhat / mu / logvar: optional
+ * tables as in nmb_ensemble_reconstruct (may be NULL). */
 int nmb_ensemble_head_predict(NmbEnsemble* ens, const float* const* xc, const int32_t* n_rows, int32_t mode,
-                              const float* const* eps, float* const* xhat, float* const* out, void* stream);
+                              const float* const* eps, float* const* xhat, float* const* mu, float* const* logvar,
+                              float* const* out, void* stream);
 
 /* The same for `n_sets` row sets per member in ONE launch (e.g. the training rows for the normative statistics and the
  * test rows of the test script, :83-113): entry (s, i) of every table sits at index s * n_members + i, for xc / xhat at

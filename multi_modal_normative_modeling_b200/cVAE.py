@@ -144,7 +144,12 @@ class _FusedBase(nn.Module):
     combine rule; rows are passed per call."""
 
     _loss_kind = "gauss_ll"
-    _ENGINE_KEYS = ("_engines", "_pending", "_last", "_views_cache", "_step_tensor")
+    _head_kind = None            # "regression" for cVAE_multimodal_regression
+    _ENGINE_KEYS = ("_engines", "_pending", "_last", "_views_cache", "_step_tensor", "_pending_fwd")
+
+    def _head_kwargs(self):
+        """make_arch / MemberSpec keywords of the supervised head (none for the normative models)."""
+        return {}
 
     def _trainable(self):
         """(name in packed layout, Parameter) in optimizer1 order."""
@@ -167,13 +172,17 @@ class _FusedBase(nn.Module):
             object.__setattr__(self, "_engines", c)
         return c
 
-    def _make_engine(self, dev, dims, combine, rows, keep_grads, names=None):
+    def _make_engine(self, dev, dims, combine, rows, keep_grads, names=None, with_head=False):
         bufs = [torch.zeros((rows, _lib.packed_row_stride(int(d), self.c_dim)), dtype=torch.float32, device=dev)
                 for d in dims]
+        head = dict(self._head_kwargs()) if with_head else {}
+        y = torch.zeros(rows, dtype=torch.float32, device=dev) if head else None
         spec = MemberSpec(dims, self._hidden, self.latent_dim, self.c_dim, bufs, combine=combine,
-                          loss_kind=self._loss_kind, non_linear=self._non_linear, batch=rows, lr=self.learning_rate)
+                          loss_kind=self._loss_kind, non_linear=self._non_linear, batch=rows, lr=self.learning_rate,
+                          y=y, **head)
         eng = EnsembleTrainer([spec], device=dev, keep_grads=keep_grads)
         eng._rows_buf = bufs
+        eng._y_buf = y
         return eng
 
     def _load_weights(self, eng, named=None, rename=None):
@@ -182,7 +191,7 @@ class _FusedBase(nn.Module):
         dst, src = [], []
         for name, p in (named or self._trainable_named()):
             k = rename(name) if rename else name
-            if k is None:
+            if k is None or k not in views:           # e.g. the head's parameters in an engine built without the head
                 continue
             dst.append(views[k]); src.append(p.detach().reshape(views[k].shape))
         with torch.no_grad():
@@ -193,10 +202,11 @@ class _FusedBase(nn.Module):
         rows = int(xs[0].shape[0])
         if rows > 256 or rows < 1:
             raise ValueError("a minibatch has 1..256 rows (train script :116)")
-        key = ("train", combine.lower(), rows, str(dev))
+        key = ("train", combine.lower(), rows, str(dev)) + tuple(sorted(self._head_kwargs().items()))
         eng = self._cache().get(key)
         if eng is None:
-            eng = self._cache()[key] = self._make_engine(dev, self._dims, combine, rows, keep_grads=True)
+            eng = self._cache()[key] = self._make_engine(dev, self._dims, combine, rows, keep_grads=True,
+                                                         with_head=bool(self._head_kind))
         for dst, x, c in zip(eng._rows_buf, xs, cs):
             pack_rows(x.to(dev), c.to(dev), out=dst)
         self._load_weights(eng)
@@ -221,13 +231,15 @@ class _FusedBase(nn.Module):
     def _launch_step(self):
         eng, eps = self._pending
         eng.grads.zero_()
+        loss4 = _lib.TRAIN_LOSS4 if self._head_kind else 0
         losses = eng.train_steps(1, eps=eps[None, None], record_losses=True,
-                                 flags=_lib.TRAIN_NO_ADAM | _lib.TRAIN_WRITE_GRADS | _lib.TRAIN_KEEP_ACTS)
+                                 flags=_lib.TRAIN_NO_ADAM | _lib.TRAIN_WRITE_GRADS | _lib.TRAIN_KEEP_ACTS | loss4)
         mu, lv, xr = eng.peek(0)
         gviews = eng.__dict__.setdefault("_gviews", eng._views(0, eng.grads))
         grads = [gviews[name].view(p.shape) for name, p in self._trainable_named()]       # views, nothing is copied
         lo = losses[0, 0]
-        return [lo[0].reshape(1), lo[1].reshape(()), lo[2].reshape(1), mu, lv] + list(xr), grads
+        extra = [lo[3].reshape(())] if loss4 else []           # the head loss rides last (not differentiable by itself)
+        return [lo[0].reshape(1), lo[1].reshape(()), lo[2].reshape(1), mu, lv] + list(xr) + extra, grads
 
     def _fused_forward(self, xs, cs, combine):
         eng = self._train_engine(xs, cs, combine)
@@ -257,7 +269,7 @@ class _FusedBase(nn.Module):
         m = self.__dict__.get("_adam_m")
         if m is None:
             arch = _lib.make_arch(self._dims, self._hidden, self.latent_dim, self.c_dim, "poe", self._loss_kind,
-                                  self._non_linear)
+                                  self._non_linear, **self._head_kwargs())
             n = _lib.arch_param_count(arch)
             object.__setattr__(self, "_adam_m", torch.zeros(n, dtype=torch.float32, device=dev))
             object.__setattr__(self, "_adam_v", torch.zeros(n, dtype=torch.float32, device=dev))
@@ -560,7 +572,7 @@ class cVAE_multimodal(_FusedBase):
 
     def combine_latent(self, mus, variances, combine):
         """cVAE.py:1144-1164 (case-insensitive; ValueError('No such combination method') otherwise)."""
-        if self.modalities == 1 and self._rng_order == "cvae":
+        if self.modalities == 1 and self._rng_order != "nmmlp":
             return mus[0], variances[0]                      # :1145-1146
         return fuse_latent(mus, variances, combine, list(self.alpha_m_list))
 
@@ -623,3 +635,92 @@ class cVAE_multimodal_endtoend(cVAE_multimodal):
         xhat, _, _ = self._infer_engine(combine).reconstruct([xc], mode="sample", eps=[eps])
         torch.cuda.synchronize(dev)
         return [t.cpu().numpy() for t in xhat[0]]
+
+
+class cVAE_multimodal_regression(cVAE_multimodal):
+    """``cVAE_multimodal_regression`` (cVAE.py:2211-2347): the multimodal cVAE plus a regressor MLP
+    ``Linear(sum D, 128) ReLU Linear(128, 64) ReLU Linear(64, 1)`` on the concatenated residuals
+    ``x_m - x_recon_m.loc`` (:2321-2325), trained jointly: ``total = sum_m (kl - ll_m) + lambda_reg * MSE(fi_pred,
+    true_fi)`` (:2334-2347).  torch-RNG order of the constructor: encoders, decoders, alphas, regressor; Adam over
+    encoders, decoders, regressor, alphas (:2260-2266).
+
+    ``forward_multimodal`` runs the forward pass (encoders -> fusion -> z -> decoders -> residuals -> regressor) in one
+    launch; ``loss_function_multimodal(xes, fwd_rtn, true_fi)`` -- the first moment the target is known -- runs the fused
+    forward + losses + backward launch with the SAME eps draw, so ``losses['total'].backward()`` only hands out the
+    gradients.  Runs on libnmb's generic tcgen05 engine (members with a head are not served by the pipelined kernel)."""
+
+    _rng_order = "regression"
+    _head_kind = "regression"
+    _head_hidden = (128, 64)
+
+    def _extra_init(self):
+        widths = [sum(self._dims)] + list(self._head_hidden)
+        layers = []
+        for a, b in zip(widths[:-1], widths[1:]):
+            layers += [nn.Linear(a, b), nn.ReLU()]
+        layers.append(nn.Linear(widths[-1], 1))
+        self.regressor = nn.Sequential(*layers)
+        self.mse_loss = nn.MSELoss()
+        self._head_weight = 1.0
+
+    def __init__(self, input_dim_list, hidden_dim, latent_dim, c_dim, learning_rate=0.0001, modalities=3, non_linear=False):
+        super().__init__(input_dim_list, hidden_dim, latent_dim, c_dim, learning_rate, modalities, non_linear)
+        self.optimizer1 = _FusedAdam([p for _, p in self._trainable()], lr=learning_rate, owner=self)
+
+    def _head_kwargs(self):
+        return {"head": "regression", "head_hidden": tuple(self._head_hidden), "head_weight": float(self.__dict__.get("_head_weight", 1.0))}
+
+    def _trainable(self):       # optimizer1 order (:2260-2266)
+        for i, m in enumerate(self.encoder_list):
+            for k, p in m.named_parameters():
+                yield f"encoder_list.{i}.{k}", p
+        for i, m in enumerate(self.decoder_list):
+            for k, p in m.named_parameters():
+                yield f"decoder_list.{i}.{k}", p
+        for k, p in self.regressor.named_parameters():
+            yield f"regressor.{k}", p
+        for i, p in enumerate(self.alpha_m_list):
+            yield f"alpha_m_list.{i}", p
+
+    def forward_multimodal(self, xes, cs, combine):
+        self.zero_grad()
+        _lib.make_arch(self._dims, self._hidden, self.latent_dim, self.c_dim, combine)   # ValueError if unknown
+        xs, cs = list(xes), list(cs)
+        eng = self._train_engine(xs, cs, combine)
+        rows = xs[0].shape[0]
+        eps = torch.randn((rows, self.latent_dim), device=xs[0].device if xs[0].is_cuda else eng.device,
+                          dtype=torch.float32).to(eng.device)             # reparameterise (:2284-2287)
+        pred, xh, mu, lv = eng.head_predict([eng._rows_buf], mode="sample", eps=[eps], want_xhat=True, want_latent=True)
+        x_recons = [Normal(loc=xh[0][i], scale=self.decoder_list[i].logvar_out.detach().exp().pow(0.5))
+                    for i in range(self.modalities)]
+        fwd = {"x_recons": x_recons, "mu_multimodal": mu[0], "logvar_multimodal": lv[0], "fi_pred": pred[0].view(-1, 1)}
+        object.__setattr__(self, "_pending_fwd", (eng, eps, fwd, combine))
+        return fwd
+
+    def loss_function_multimodal(self, xes, fwd_rtn, true_fi, lambda_reg=1.0):
+        """{'total', 'kl', 'll', 'regression'} of the forward pass that produced fwd_rtn (:2334-2347)."""
+        last = self.__dict__.get("_pending_fwd")
+        if last is None:
+            raise RuntimeError("loss_function_multimodal called before forward_multimodal")
+        eng, eps, fwd, combine = last
+        if fwd_rtn is not fwd:
+            raise ValueError("fwd_rtn is not the result of this module's LAST forward pass: the fused kernel computes "
+                             "the losses together with the forward pass, so only that pass can be scored")
+        if float(lambda_reg) != float(self.__dict__.get("_head_weight", 1.0)):
+            # lambda_reg is part of the engine's architecture record: switch to (or build) the engine for this weight
+            # and hand it the rows forward_multimodal packed
+            self._head_weight = float(lambda_reg)
+            rows = eng._rows_buf
+            key = ("train", combine.lower(), int(rows[0].shape[0]), str(eng.device)) + tuple(sorted(self._head_kwargs().items()))
+            eng2 = self._cache().get(key)
+            if eng2 is None:
+                eng2 = self._cache()[key] = self._make_engine(eng.device, self._dims, combine, int(rows[0].shape[0]),
+                                                              keep_grads=True, with_head=True)
+            for dst, src in zip(eng2._rows_buf, rows):
+                dst.copy_(src)
+            self._load_weights(eng2)
+            eng = eng2
+        eng._y_buf.copy_(torch.as_tensor(true_fi).to(device=eng.device, dtype=torch.float32).reshape(-1))
+        object.__setattr__(self, "_pending", (eng, eps))
+        outs = _FusedStep.apply(self, 0, *[p for _, p in self._trainable_named()])
+        return {"total": outs[0], "kl": outs[1], "ll": outs[2], "regression": outs[-1]}

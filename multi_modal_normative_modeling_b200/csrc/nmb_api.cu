@@ -803,14 +803,15 @@ int nmb_ensemble_reconstruct(NmbEnsemble* e, const float* const* xc, const int32
 }
 
 int nmb_ensemble_head_predict(NmbEnsemble* e, const float* const* xc, const int32_t* n_rows, int32_t mode,
-                              const float* const* eps, float* const* xhat, float* const* out, void* stream) {
+                              const float* const* eps, float* const* xhat, float* const* mu, float* const* logvar,
+                              float* const* out, void* stream) {
   if (!e || !out) return fail("null argument");
   if (e->tcp_ok) return fail("nmb_ensemble_head_predict: no member of this ensemble has a supervised head");
   if ((mode & ~(NMB_RECON_FP32 | NMB_RECON_TC_SIMPLE | NMB_RECON_KEEP_PLANES)) == NMB_RECON_GIVEN_Z)
     return fail("nmb_ensemble_head_predict: the head needs the encoders (MEAN or SAMPLE)");
   std::vector<float*> none;
   if (!xhat) { none.assign((size_t)e->n_members * NMB_MAX_MOD, nullptr); xhat = none.data(); }
-  return reconstruct_sets(e, 1, xc, n_rows, mode, eps, xhat, nullptr, nullptr, stream, out);
+  return reconstruct_sets(e, 1, xc, n_rows, mode, eps, xhat, mu, logvar, stream, out);
 }
 
 int nmb_ensemble_reconstruct_sets(NmbEnsemble* e, int32_t n_sets, const float* const* xc, const int32_t* n_rows, int32_t mode,

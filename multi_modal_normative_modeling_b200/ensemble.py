@@ -390,12 +390,14 @@ class EnsembleTrainer:
         return outs, (mus if want_latent else None), (lvs if want_latent else None)
 
 
-def head_predict(trainer: "EnsembleTrainer", xc, mode: str = "sample", eps=None, engine: str = "tcs", want_xhat: bool = False):
+def head_predict(trainer: "EnsembleTrainer", xc, mode: str = "sample", eps=None, engine: str = "tcs", want_xhat: bool = False,
+                 want_latent: bool = False):
     """``fi_pred`` of cVAE_multimodal_regression.forward_multimodal (cVAE.py:2309-2332) for every member on its own packed
-    rows: [n_rows_i] per member (and the reconstructions when want_xhat).  mode / eps as in ``reconstruct``."""
+    rows: [n_rows_i] per member.  mode / eps as in ``reconstruct``.  Returns preds, then xhat[i][m] when want_xhat, then
+    (mu[i], logvar[i]) when want_latent."""
     self = trainer
     eng_bits = {"tcs": _lib.RECON_TC_SIMPLE, "fp32": _lib.RECON_FP32}[engine]
-    tbl, rows, outs, xh_tbl, xhs = [], [], [], [], []
+    tbl, rows, outs, xh_tbl, xhs, mus, lvs = [], [], [], [], [], [], []
     for i, s in enumerate(self.specs):
         n_i = int(xc[i][0].shape[0])
         rows.append(n_i)
@@ -409,6 +411,9 @@ def head_predict(trainer: "EnsembleTrainer", xc, mode: str = "sample", eps=None,
             else:
                 tbl.append(None); xh_tbl.append(None)
         xhs.append(row)
+        if want_latent:
+            mus.append(torch.empty((n_i, int(s.latent)), dtype=torch.float32, device=self.device))
+            lvs.append(torch.empty((n_i, int(s.latent)), dtype=torch.float32, device=self.device))
     eps_keep = None
     if eps is not None:
         eps_keep = [None if e is None else e.to(device=self.device, dtype=torch.float32).contiguous() for e in eps]
@@ -418,10 +423,13 @@ def head_predict(trainer: "EnsembleTrainer", xc, mode: str = "sample", eps=None,
             {"mean": _lib.RECON_MEAN, "sample": _lib.RECON_SAMPLE}[mode] | eng_bits,
             _lib.ptr_table([e.data_ptr() if e is not None else None for e in eps_keep]) if eps_keep is not None else None,
             _lib.ptr_table(xh_tbl) if want_xhat else None,
+            _lib.ptr_table([t.data_ptr() for t in mus]) if want_latent else None,
+            _lib.ptr_table([t.data_ptr() for t in lvs]) if want_latent else None,
             _lib.ptr_table([o.data_ptr() if o is not None else None for o in outs]), _stream_ptr(self.device)),
             "nmb_ensemble_head_predict")
     self.gpu_launches += 1
-    return (outs, xhs) if want_xhat else outs
+    res = (outs,) + ((xhs,) if want_xhat else ()) + ((mus, lvs) if want_latent else ())
+    return res if len(res) > 1 else outs
 
 
 def _normalise_names(sd):

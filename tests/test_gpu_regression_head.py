@@ -114,3 +114,102 @@ def test_head_members_are_validated():
         from multi_modal_normative_modeling_b200 import _lib
         tr.train_steps(1, record_losses=True, flags=_lib.TRAIN_LOSS4)
     tr.close()
+
+
+def test_dropin_regression_module_loop_vs_reference(golden_dir):
+    """Drop-in class through the reference's loop body (..._regression.py:119-131): forward_multimodal ->
+    loss_function_multimodal(xes, out, fi, lambda_reg=1.0) -> zero_grad -> backward -> optimizer1.step(), eps drawn by
+    torch (injected here through randn so that the recorded draws are used), against the reference's recording."""
+    from multi_modal_normative_modeling_b200.cVAE import cVAE_multimodal_regression
+    name = "reg_M2_small_poe"
+    g = load(golden_dir, name)
+    dims = [int(d) for d in g["dims"]]
+    torch.manual_seed(int(g["seed"]))
+    model = cVAE_multimodal_regression(dims, [int(h) for h in g["hidden"]], int(g["z"]), 2, learning_rate=1e-4,
+                                       modalities=len(dims), non_linear=True)
+    init = sub(g, "init/")
+    assert set(model.state_dict()) == set(init)
+    for k, v in model.state_dict().items():
+        assert np.array_equal(v.numpy(), init[k]), k           # seed-exact constructor
+    model.to("cuda")
+    xs = [torch.from_numpy(g[f"x{i}"]).cuda() for i in range(len(dims))]
+    c, fi = torch.from_numpy(g["c"]).cuda(), torch.from_numpy(g["fi"]).cuda()
+    n, b = int(g["n"]), int(g["batch"])
+    real_randn = torch.randn
+    s = 0
+    log = []
+    try:
+        for ep in range(int(g["epochs"])):
+            for r0 in range(0, n, b):
+                idx = [torch.from_numpy(g["order"][ep, m, r0:r0 + b].astype(np.int64)).cuda() for m in range(len(dims))]
+                rows = idx[0].numel()
+                torch.randn = lambda *a, **k: torch.from_numpy(g["eps"][s][:rows]).to(k.get("device", "cpu"))
+                out = model.forward_multimodal([xs[m][idx[m]] for m in range(len(dims))], [c[idx[m]] for m in range(len(dims))],
+                                               str(g["combine"]))
+                torch.randn = real_randn
+                losses = model.loss_function_multimodal([xs[m][idx[m]] for m in range(len(dims))], out, fi[idx[0]], lambda_reg=1.0)
+                if s == 0:
+                    assert relerr(out["fi_pred"].cpu().numpy(), g["fi_pred0"]) < REL
+                    assert relerr(out["mu_multimodal"].cpu().numpy(), g["mu"]) < REL
+                    with pytest.raises(ValueError, match="LAST forward"):
+                        model.loss_function_multimodal(xs, dict(out), fi[idx[0]])
+                model.optimizer1.zero_grad()
+                losses["total"].backward()
+                if s == 0:
+                    grads = {k: p.grad for k, p in model.named_parameters()}
+                    assert_grads_close(g, "grad/", grads, REL, to_numpy=lambda t: t.cpu().numpy())
+                model.optimizer1.step()
+                log.append([float(losses[k]) for k in ("total", "kl", "ll", "regression")])
+                s += 1
+    finally:
+        torch.randn = real_randn
+    got, want = np.asarray(log), g["losses"]
+    for col, rel in ((0, REL), (2, REL), (3, 10 * REL), (1, 10 * REL)):
+        assert np.allclose(got[:, col], want[:, col], rtol=rel), (col, got[:, col], want[:, col])
+    sd, g0 = model.state_dict(), sub(g, "grad/")
+    for k, v in sub(g, "final/").items():
+        assert_update_close(k, sd[k].cpu().numpy(), v, init[k], s, 1e-4, False, g0.get(k), q99_tc=5e-3)
+    model.close()
+
+
+def test_regression_program_end_to_end_vs_oracle(tmp_path):
+    """multimodal_kfold_train_cvae_supervised_regression.py on a synthetic HCPimage-shaped dataset: every fold in one
+    launch, production Philox eps.  Fold 0 is replayed through the oracle (same initial weights, the same loader
+    permutations, the documented Philox stream): per-step losses and test predictions."""
+    from multi_modal_normative_modeling_b200 import regression, synthetic
+    from oracle import cvae_torch, philox
+    synthetic.write_dataset(str(tmp_path), "HCPimage", n=150, seed=3)
+    args = regression.build_parser().parse_args(["-R", "HCPimage", "-P", "SE-gPoE", "-C", "gpoe", "-E", "2", "-K", "2",
+                                                 "--batch_size", "64", "-H", "110", "110", "10"])
+    dbg = {}
+    scores = regression.train_and_test(args, root=tmp_path, debug=dbg)
+    assert len(scores) == 2 and all(np.isfinite(list(s.values())).all() for s in scores)
+    out = tmp_path / "regression_outputs"
+    for f in range(2):
+        pred, true = np.load(out / f"fold_{f}_pred.npy"), np.load(out / f"fold_{f}_true.npy")
+        assert pred.shape == true.shape == (75, 1)
+        for name in ("T1w_sMRI", "T2w_sMRI", "fMRI"):
+            df = __import__("pandas").read_csv(out / f"deviation_fold_{f}_{name}_roiwise.csv")
+            assert df.shape == (150, 117) and list(df.columns[:2]) == ["IID", "ROI_0"] and (df.iloc[:, 1:].to_numpy() >= 0).all()
+    # ---- fold 0 through the oracle ----
+    fd = dbg["folds"][0]
+    dims, z, b = fd["dims"], 10, 64
+    model = cvae_torch.OracleCVAERegression(dims, [110, 110], z, 2, 1e-4, len(dims), non_linear=True)
+    model.load_state_dict(fd["init"])
+    xs = [torch.from_numpy(x[:, :d].copy()) for x, d in zip(fd["xc_train"], dims)]
+    c = torch.from_numpy(fd["xc_train"][0][:, dims[0]:dims[0] + 2].copy())
+    n = xs[0].shape[0]
+    spe = -(-n // b)
+    eps = np.stack([philox.normals(fd["seed"], s, b * z, 0).reshape(b, z) for s in range(2 * spe)])
+    log = cvae_torch.regression_train_loop(model, xs, c, torch.from_numpy(fd["fi"]), fd["order"], "gpoe", b, eps)
+    got = dbg["losses"][0][: 2 * spe].astype(np.float64)
+    assert np.allclose(got[:, 0], log[:, 0], rtol=5e-4), (got, log)
+    assert np.allclose(got[:, 3], log[:, 3], rtol=2e-3), (got, log)
+    xt = [torch.from_numpy(x[:, :d].copy()) for x, d in zip(fd["xc_test"], dims)]
+    ct = torch.from_numpy(fd["xc_test"][0][:, dims[0]:dims[0] + 2].copy())
+    eps_t = philox.normals(fd["seed"], 0, 256 * z, 1).reshape(256, z)[: xt[0].shape[0]]
+    model.eval()
+    with torch.no_grad():
+        ev = model.step_losses(xt, [ct] * len(dims), "gpoe", torch.from_numpy(eps_t))
+    want = ev["fi_pred"].numpy().ravel()
+    assert np.abs(dbg["preds"][0] - want).max() < 2e-3 * (np.abs(want).max() + 1.0), (dbg["preds"][0][:5], want[:5])
