@@ -81,6 +81,8 @@ def add_common_args(p: argparse.ArgumentParser, train: bool):
         p.add_argument("--nmmlp", action="store_true")
     p.add_argument("--fast-csv", dest="fast_csv", action="store_true",
                    help="write the deviation CSV families with Arrow's CSV writer instead of DataFrame.to_csv")
+    p.add_argument("--pandas-csv", dest="pandas_csv", action="store_true",
+                   help="write the CSV families with DataFrame.to_csv instead of libnmb's byte-identical writer")
     p.add_argument("--host-prologue", dest="host_prologue", action="store_true",
                    help="RobustScaler / covariate bins / packing with sklearn + pandas on the host instead of the "
                         "GPU prologue (bit-identical results)")
@@ -264,6 +266,7 @@ def test_main(args, root=None):
         raise ValueError(f"Unknown procedure: {args.procedure}")
     nmmlp = bool(getattr(args, "nmmlp", False))
     fast_csv = bool(getattr(args, "fast_csv", False))
+    native_csv = not bool(getattr(args, "pandas_csv", False))
     specs, test_xc, test_frames, test_x64 = [], [], [], []
     for fold in range(args.n_splits):
         fold_dir = model_dir / f"{fold:03d}"
@@ -330,14 +333,14 @@ def test_main(args, root=None):
                 columns=dict(zip(cols, map(str, range(1, len(cols) + 1)))))
             for key, body in tables.items():
                 df = pd.concat([cov.reset_index(drop=True), body], axis=1)
-                write_csv(df, out_dir / f"{key}_{name}.csv", fast_csv)
+                write_csv(df, out_dir / f"{key}_{name}.csv", fast_csv, native_csv)
                 all_frames[name][key].append(df)
             k += 1
     for name in names:
         d = deviation_dir / name
         d.mkdir(exist_ok=True, parents=True)
         for key, parts in all_frames[name].items():
-            write_csv(pd.concat(parts, ignore_index=True), d / f"{key}_{name}.csv", fast_csv)
+            write_csv(pd.concat(parts, ignore_index=True), d / f"{key}_{name}.csv", fast_csv, native_csv)
     if nmmlp:
         # nmmlp :515-523: "diagnosis" = modality-averaged per-subject deviation (nmb_mean_rows), HC = 0 / other = 1
         hc_label = get_hc_label(args.dataset_resourse)
