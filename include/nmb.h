@@ -38,8 +38,14 @@ enum { NMB_COMBINE_POE = 0, NMB_COMBINE_GPOE = 1, NMB_COMBINE_MOE = 2, NMB_COMBI
 enum { NMB_LOSS_GAUSS_LL = 0, NMB_LOSS_NEG_MSE = 1 };
 /* supervised head on top of the multimodal cVAE.  NMB_HEAD_REGRESSION = cVAE_multimodal_regression
  * (cVAE.py:2211-2347): regressor MLP Linear(sum D, h0) ReLU ... Linear(h_last, 1) on the concatenated residuals
- * x_m - x_recon_m.loc (:2321-2325), loss total += head_weight * MSE(fi_pred, true_fi) (:2334-2347). */
-enum { NMB_HEAD_NONE = 0, NMB_HEAD_REGRESSION = 1 };
+ * x_m - x_recon_m.loc (:2321-2325), loss total += head_weight * MSE(fi_pred, true_fi) (:2334-2347).
+ * NMB_HEAD_ENDTOEND = cVAE_multimodal_endtoend v2 (cVAE.py:2004-2207, driven by multimodal_kfold_cvae_nmpmcont.py): shared
+ * encoders, PoE fusion (:2081-2088), TWO decoder sets (health / disease), a classifier Linear -> BatchNorm1d -> ReLU ->
+ * Dropout ... -> Linear(., 2) on z (:2004-2018), loss = w_rec (rec_health + rec_disease) + w_kl kl + cross-entropy +
+ * w_con * contrastive hinge on the per-subject deviations of the two decoder sets (:2131-2196).  n_mod <= 8. */
+enum { NMB_HEAD_NONE = 0, NMB_HEAD_REGRESSION = 1, NMB_HEAD_ENDTOEND = 2 };
+/* indices into NmbArch.head_params for NMB_HEAD_ENDTOEND (loss_function defaults :2131: margin 1, 0.1, 0.1, 0.1; dropout .5) */
+enum { NMB_HP_MARGIN = 0, NMB_HP_W_CONTRASTIVE = 1, NMB_HP_W_KL = 2, NMB_HP_W_REC = 3, NMB_HP_DROPOUT = 4 };
 
 /* Architecture of one ensemble member = the constructor arguments of
  * cVAE_multimodal(input_dim_list, hidden_dim, latent_dim, c_dim, ..., modalities, non_linear)
@@ -58,6 +64,7 @@ typedef struct {
   int32_t n_head_hidden;
   int32_t head_hidden[NMB_MAX_HEAD]; /* 128, 64 (cVAE.py:2248-2255) */
   float head_weight;  /* lambda_reg (cVAE.py:2334; the trainer passes 1.0) */
+  float head_params[6]; /* NMB_HP_* (NMB_HEAD_ENDTOEND) */
 } NmbArch;
 
 /* One tensor of the reference's state_dict inside the packed per-model parameter buffer.
@@ -66,7 +73,11 @@ typedef struct {
  * (rows 0..Z-1 = enc_mean_layer, Z..2Z-1 = enc_logvar_layer). */
 enum { NMB_SLOT_ENC = 0, NMB_SLOT_ENC_MEAN = 1, NMB_SLOT_ENC_LOGVAR = 2, NMB_SLOT_DEC = 3,
        NMB_SLOT_DEC_MEAN = 4, NMB_SLOT_LOGVAR_OUT = 5, NMB_SLOT_ALPHA = 6,
-       NMB_SLOT_HEAD = 7 /* layer l of the head = regressor.{2l} (cVAE.py:2248-2255); modality 0 */ };
+       NMB_SLOT_HEAD = 7 /* layer l of the head = regressor.{2l} (cVAE.py:2248-2255) or classifier.classifier.{4l}
+                            (cVAE.py:2010-2015); modality 0 */,
+       NMB_SLOT_HEAD_BN = 8 /* BatchNorm1d after head layer l = classifier.classifier.{4l+1}: rows = 5 vectors of `cols`
+                               entries at stride ld: weight, bias, running_mean, running_var, [num_batches_tracked] */,
+       NMB_SLOT_DEC2 = 9, NMB_SLOT_DEC2_MEAN = 10, NMB_SLOT_LOGVAR_OUT2 = 11 /* the second (disease) decoder set */ };
 typedef struct {
   int32_t kind;      /* NMB_SLOT_* */
   int32_t modality;
@@ -100,6 +111,10 @@ typedef struct {
                                    MODALITY per epoch (..._regression.py:94, 122); the target follows modality 0 (:125).
                                    NULL = rows in order (shuffle=False).  Generic engines only. */
   int64_t n_order_epochs;       /* epochs row_order covers; training past it FAILS */
+  const float* drop_keep;       /* optional injected dropout keep flags (0 / 1) of the classifier, [n_drop_steps][batch][sum of
+                                   the head's hidden widths], step s reads entry s mod n_drop_steps (parity tests and the
+                                   per-step module API, where torch draws the masks); NULL = in-kernel Philox, stream 2 */
+  int64_t n_drop_steps;
 } NmbMember;
 
 typedef struct NmbEnsemble NmbEnsemble;
@@ -172,6 +187,9 @@ enum {
                                 architectures the pipelined kernel does not cover, e.g. hidden width > 127) */
   NMB_TRAIN_LOSS4 = 64,      /* loss_out rows hold 4 values: (total, kl, ll, head loss) -- losses['regression'] of
                                 cVAE_multimodal_regression (cVAE.py:2343-2345); 0 for members without a head */
+  NMB_TRAIN_LOSS8 = 128,     /* loss_out rows hold 8 values: (total, kl, ll = -(rec_health + rec_disease), cross-entropy,
+                                rec_health, rec_disease, contrastive, 0) -- the loss dict of cVAE.py:2186-2195 */
+  NMB_TRAIN_NO_STATS = 256,  /* do not update the BatchNorm running statistics (a repeated pass over the same minibatch) */
   NMB_TRAIN_RESIDENT = 32    /* pipelined engine: leave parameters and Adam moments in the kernel's lane-major master
                                 layout after the call (no conversion back, none in at the next call).  NmbMember.params /
                                 adam_m / adam_v are then STALE until nmb_ensemble_sync (logvar_out and the gPoE alphas
@@ -211,10 +229,15 @@ int nmb_adam_step(float* params, const float* grads, float* adam_m, float* adam_
 
 /* Activations of the LAST executed step of one member (debug / per-step parity):
  * mu, logvar: fused latent [rows][latent]; x_recon[m]: [rows][input_dims[m]] (needs
- * NMB_TRAIN_KEEP_ACTS).  Any pointer may be NULL.  rows = size of that step's minibatch. */
+ * NMB_TRAIN_KEEP_ACTS; 2 * n_mod entries for end-to-end members, health decoders first).  Any pointer may be NULL.
+ * rows = size of that step's minibatch. */
 int nmb_ensemble_peek(NmbEnsemble* ens, int32_t member, float* mu, float* logvar,
                       float* const* x_recon /*host array of device ptrs*/, int32_t* rows /*host*/,
                       void* stream);
+
+/* Members with a supervised head: the head's output of the last executed step, [rows][4] floats per row --
+ * regression: {fi_pred, -, -, -}; end-to-end: {logit 0, logit 1, -, -} (train-mode BatchNorm / dropout of that step). */
+int nmb_ensemble_peek_head(NmbEnsemble* ens, int32_t member, float* out4, void* stream);
 
 enum { NMB_RECON_MEAN = 0, NMB_RECON_SAMPLE = 1,
        NMB_RECON_GIVEN_Z = 2 /* decoders only: eps[i] holds z itself [n_rows[i]][latent] -- Decoder.forward /
@@ -242,7 +265,9 @@ int nmb_ensemble_reconstruct(NmbEnsemble* ens, const float* const* xc, const int
  * cVAE_multimodal_regression.forward_multimodal (cVAE.py:2309-2332): encode, fuse, z = mu + eps*std (mode SAMPLE: the
  * reference samples at test time too, ..._regression.py:146-152; eps[i] injected or Philox), decode, residuals,
  * regressor.  out[i]: [n_rows[i]] (NULL entries / members without a head are skipped); xhat / mu / logvar: optional
- * tables as in nmb_ensemble_reconstruct (may be NULL). */
+ * tables as in nmb_ensemble_reconstruct (may be NULL).
+ * NMB_HEAD_ENDTOEND members: out[i] = [n_rows[i]][2] logits of classifier(z) in EVAL mode (BatchNorm running statistics, no
+ * dropout) -- cVAE_multimodal_endtoend.predict (cVAE.py:2198-2203) with mode MEAN; xhat has 2 * n_mod entries per member. */
 int nmb_ensemble_head_predict(NmbEnsemble* ens, const float* const* xc, const int32_t* n_rows, int32_t mode,
                               const float* const* eps, float* const* xhat, float* const* mu, float* const* logvar,
                               float* const* out, void* stream);

@@ -11,9 +11,12 @@ NMB_MAX_HEAD = 3
 
 COMBINE = {"poe": 0, "gpoe": 1, "moe": 2, "mopoe": 3}
 LOSS = {"gauss_ll": 0, "neg_mse": 1}
-HEAD = {None: 0, "none": 0, "regression": 1}
-SLOT_ENC, SLOT_ENC_MEAN, SLOT_ENC_LOGVAR, SLOT_DEC, SLOT_DEC_MEAN, SLOT_LOGVAR_OUT, SLOT_ALPHA, SLOT_HEAD = range(8)
+HEAD = {None: 0, "none": 0, "regression": 1, "endtoend": 2}
+(SLOT_ENC, SLOT_ENC_MEAN, SLOT_ENC_LOGVAR, SLOT_DEC, SLOT_DEC_MEAN, SLOT_LOGVAR_OUT, SLOT_ALPHA, SLOT_HEAD, SLOT_HEAD_BN,
+ SLOT_DEC2, SLOT_DEC2_MEAN, SLOT_LOGVAR_OUT2) = range(12)
 TRAIN_NO_ADAM, TRAIN_WRITE_GRADS, TRAIN_KEEP_ACTS, TRAIN_FP32, TRAIN_TC_SIMPLE, TRAIN_RESIDENT, TRAIN_LOSS4 = 1, 2, 4, 8, 16, 32, 64
+TRAIN_LOSS8, TRAIN_NO_STATS = 128, 256
+HP_MARGIN, HP_W_CONTRASTIVE, HP_W_KL, HP_W_REC, HP_DROPOUT = range(5)
 RECON_MEAN, RECON_SAMPLE, RECON_GIVEN_Z, RECON_FP32, RECON_TC_SIMPLE, RECON_KEEP_PLANES = 0, 1, 2, 16, 32, 64
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libnmb.so")
@@ -24,7 +27,7 @@ class NmbArch(C.Structure):
                 ("hidden", C.c_int32 * NMB_MAX_HIDDEN), ("latent", C.c_int32), ("c_dim", C.c_int32),
                 ("combine", C.c_int32), ("loss_kind", C.c_int32), ("non_linear", C.c_int32),
                 ("head_kind", C.c_int32), ("n_head_hidden", C.c_int32), ("head_hidden", C.c_int32 * NMB_MAX_HEAD),
-                ("head_weight", C.c_float)]
+                ("head_weight", C.c_float), ("head_params", C.c_float * 6)]
 
 
 class NmbSlot(C.Structure):
@@ -37,7 +40,8 @@ class NmbMember(C.Structure):
                 ("seed", C.c_uint64), ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float),
                 ("adam_eps", C.c_float), ("lr_steps", C.c_void_p), ("params", C.c_void_p),
                 ("adam_m", C.c_void_p), ("adam_v", C.c_void_p), ("grads", C.c_void_p), ("n_lr_steps", C.c_int64),
-                ("y", C.c_void_p), ("row_order", C.c_void_p), ("n_order_epochs", C.c_int64)]
+                ("y", C.c_void_p), ("row_order", C.c_void_p), ("n_order_epochs", C.c_int64),
+                ("drop_keep", C.c_void_p), ("n_drop_steps", C.c_int64)]
 
 
 _PROTOS = {
@@ -67,6 +71,7 @@ _PROTOS = {
                                 C.c_float, C.c_float, C.c_float, C.c_void_p]),
     "nmb_ensemble_peek": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p),
                                     C.POINTER(C.c_int32), C.c_void_p]),
+    "nmb_ensemble_peek_head": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "nmb_ensemble_reconstruct": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_int32,
                                            C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                            C.POINTER(C.c_void_p), C.c_void_p]),
@@ -136,7 +141,7 @@ def int_table(vals):
 
 
 def make_arch(input_dims, hidden, latent, c_dim, combine="poe", loss_kind="gauss_ll", non_linear=True,
-              head=None, head_hidden=(128, 64), head_weight=1.0) -> NmbArch:
+              head=None, head_hidden=(128, 64), head_weight=1.0, head_params=None) -> NmbArch:
     if isinstance(combine, str):
         key = combine.lower()
         if key not in COMBINE:
@@ -165,6 +170,12 @@ def make_arch(input_dims, hidden, latent, c_dim, combine="poe", loss_kind="gauss
         for i, h in enumerate(head_hidden):
             a.head_hidden[i] = int(h)
         a.head_weight = float(head_weight)
+        if a.head_kind == HEAD["endtoend"]:
+            hp = dict(margin=1.0, w_contrastive=0.1, w_kl=0.1, w_rec=0.1, dropout=0.5)     # cVAE.py:2131, 2031
+            hp.update(head_params or {})
+            for i, k in enumerate(("margin", "w_contrastive", "w_kl", "w_rec", "dropout")):
+                a.head_params[i] = float(hp[k])
+            a.head_weight = 0.0
     return a
 
 

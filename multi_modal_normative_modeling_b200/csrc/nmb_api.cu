@@ -111,6 +111,7 @@ NmbArch canonical(const NmbArch& a) {   // zero the unused tails so memcmp is me
   if (a.head_kind) {
     c.head_kind = a.head_kind; c.n_head_hidden = a.n_head_hidden; c.head_weight = a.head_weight;
     for (int i = 0; i < a.n_head_hidden && i < NMB_MAX_HEAD; ++i) c.head_hidden[i] = a.head_hidden[i];
+    if (a.head_kind == NMB_HEAD_ENDTOEND) { for (int i = 0; i < 6; ++i) c.head_params[i] = a.head_params[i]; c.head_weight = 0.f; }
   }
   return c;
 }
@@ -349,7 +350,8 @@ int nmb_arch_slots(const NmbArch* arch, NmbSlot* slots, int32_t max_slots, int32
     NmbSlot s; s.kind = kind; s.modality = m; s.layer = layer; s.rows = rows; s.cols = cols; s.ld = ld; s.offset = off;
     v.push_back(s);
   };
-  for (int m = 0; m < d.M; ++m) push(NMB_SLOT_ALPHA, m, 0, 1, 1, 1, d.alpha_off + m);
+  if (d.head_kind != NMB_HEAD_ENDTOEND)      // (the end-to-end model has no alpha_m_list: plain PoE, cVAE.py:2081-2088)
+    for (int m = 0; m < d.M; ++m) push(NMB_SLOT_ALPHA, m, 0, 1, 1, 1, d.alpha_off + m);
   for (int m = 0; m < d.M; ++m) {
     const ModDesc& q = d.mod[m];
     for (int l = 0; l < d.L; ++l) push(NMB_SLOT_ENC, m, l, q.enc[l].out, q.enc[l].in, q.enc[l].ld, q.enc[l].off);
@@ -362,8 +364,16 @@ int nmb_arch_slots(const NmbArch* arch, NmbSlot* slots, int32_t max_slots, int32
     for (int l = 0; l < d.L; ++l) push(NMB_SLOT_DEC, m, l, q.dec[l].out, q.dec[l].in, q.dec[l].ld, q.dec[l].off);
     push(NMB_SLOT_DEC_MEAN, m, 0, q.outl.out, q.outl.in, q.outl.ld, q.outl.off);
   }
+  for (int m = d.M; m < d.MD; ++m) {         // second decoder set (decoder_list_disease)
+    const ModDesc& q = d.mod[m];
+    push(NMB_SLOT_LOGVAR_OUT2, m - d.M, 0, 1, q.D, round4(q.D), q.lam_off);
+    for (int l = 0; l < d.L; ++l) push(NMB_SLOT_DEC2, m - d.M, l, q.dec[l].out, q.dec[l].in, q.dec[l].ld, q.dec[l].off);
+    push(NMB_SLOT_DEC2_MEAN, m - d.M, 0, q.outl.out, q.outl.in, q.outl.ld, q.outl.off);
+  }
   if (d.head_kind)
     for (int l = 0; l <= d.HL; ++l) push(NMB_SLOT_HEAD, 0, l, d.hd[l].out, d.hd[l].in, d.hd[l].ld, d.hd[l].off);
+  if (d.head_kind == NMB_HEAD_ENDTOEND)
+    for (int l = 0; l < d.HL; ++l) push(NMB_SLOT_HEAD_BN, 0, l, 5, d.head_w[l], d.bn_ld[l], d.bn_off[l]);
   *n_slots = (int32_t)v.size();
   if (slots) for (int i = 0; i < (int)v.size() && i < max_slots; ++i) slots[i] = v[i];
   return 0;
@@ -439,6 +449,8 @@ int nmb_ensemble_create(NmbEnsemble** out, int32_t device, const NmbMember* memb
     md.params = mm.params; md.adam_m = mm.adam_m; md.adam_v = mm.adam_v; md.grads = mm.grads;
     md.lr_steps = mm.lr_steps; md.seed = mm.seed;
     md.y = mm.y; md.row_order = mm.row_order;
+    md.drop_keep = mm.drop_keep; md.n_drop_steps = mm.drop_keep ? (long long)mm.n_drop_steps : 0;
+    if (mm.drop_keep && (d.head_kind != NMB_HEAD_ENDTOEND || mm.n_drop_steps < 1)) { delete e; return fail("drop_keep needs an end-to-end head and n_drop_steps >= 1"); }
     if (d.head_kind && !mm.y && mm.n_rows > 0) { delete e; return fail("a member with a supervised head needs targets (NmbMember.y)"); }
     if (mm.row_order && !d.head_kind) { delete e; return fail("row_order is supported for members with a supervised head only"); }
     if (mm.row_order && mm.n_order_epochs < 1) { delete e; return fail("row_order given without n_order_epochs"); }
@@ -556,8 +568,8 @@ static int train_common(NmbEnsemble* e, int64_t n, int n_is_epochs, const float*
       }
     }
   }
-  if ((flags & NMB_TRAIN_LOSS4) && e->tcp_ok && !(flags & (NMB_TRAIN_FP32 | NMB_TRAIN_TC_SIMPLE)))
-    return fail("NMB_TRAIN_LOSS4 is a generic-engine option (members with a supervised head)");
+  if ((flags & (NMB_TRAIN_LOSS4 | NMB_TRAIN_LOSS8)) && e->tcp_ok && !(flags & (NMB_TRAIN_FP32 | NMB_TRAIN_TC_SIMPLE)))
+    return fail("NMB_TRAIN_LOSS4 / LOSS8 are generic-engine options (members with a supervised head)");
   t.stride_steps = max_steps;
   if (max_steps == 0) return 0;
   CU(cudaSetDevice(e->device));
@@ -609,13 +621,11 @@ int nmb_ensemble_train_epochs(NmbEnsemble* e, int64_t n_epochs, float* loss_out,
   return train_common(e, n_epochs, 1, nullptr, loss_out, flags, stream);
 }
 
-int nmb_ensemble_peek(NmbEnsemble* e, int32_t member, float* mu, float* logvar, float* const* x_recon, int32_t* rows,
-                      void* stream) {
+// scratch slot and minibatch rows of the last step of `member`
+static int peek_slot(NmbEnsemble* e, int32_t member, cudaStream_t st, MemberDev& md) {
   if (!e || member < 0 || member >= e->n_members) return fail("bad member");
   if (e->n_members > e->n_slots) return fail("peek needs n_members <= resident slots (debug API)");
-  cudaStream_t st = (cudaStream_t)stream;
   CU(cudaSetDevice(e->device));
-  MemberDev md;
   if (e->n_members <= e->n_sm) {
     // one CTA per member, dealt statically by every engine: the scratch slot is the member index and the rows of the last
     // step follow from the host's step count -- no device round trip, the call stays asynchronous on the stream
@@ -629,6 +639,25 @@ int nmb_ensemble_peek(NmbEnsemble* e, int32_t member, float* mu, float* logvar, 
     CU(cudaStreamSynchronize(st));
     if (md.last_slot < 0) return fail("member has not run a step yet");
   }
+  return 0;
+}
+
+int nmb_ensemble_peek_head(NmbEnsemble* e, int32_t member, float* out4, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  MemberDev md;
+  if (int rc = peek_slot(e, member, st, md)) return rc;
+  const ArchDesc& a = e->archs[e->arch_idx[member]];
+  if (!a.head_kind || !out4) return fail("nmb_ensemble_peek_head: member without a supervised head / null output");
+  const float* S = e->scratch + (long long)md.last_slot * e->slot_floats;
+  CU(cudaMemcpyAsync(out4, S + a.s_pred, sizeof(float) * 4 * (size_t)md.last_rows, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+int nmb_ensemble_peek(NmbEnsemble* e, int32_t member, float* mu, float* logvar, float* const* x_recon, int32_t* rows,
+                      void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  MemberDev md;
+  if (int rc = peek_slot(e, member, st, md)) return rc;
   const ArchDesc& a = e->archs[e->arch_idx[member]];
   const float* S = e->scratch + (long long)md.last_slot * e->slot_floats;
   if (rows) *rows = md.last_rows;
@@ -636,7 +665,7 @@ int nmb_ensemble_peek(NmbEnsemble* e, int32_t member, float* mu, float* logvar, 
   if (mu) CU(cudaMemcpyAsync(mu, S + a.s_mub, lat, cudaMemcpyDeviceToDevice, st));
   if (logvar) CU(cudaMemcpyAsync(logvar, S + a.s_lvb, lat, cudaMemcpyDeviceToDevice, st));
   if (x_recon) {
-    for (int m = 0; m < a.M; ++m) {
+    for (int m = 0; m < a.MD; ++m) {           // (end-to-end members: entries M .. 2M-1 = the disease decoders)
       if (!x_recon[m]) continue;
       const ModDesc& q = a.mod[m];
       CU(cudaMemcpy2DAsync(x_recon[m], sizeof(float) * q.D, S + q.s_xr, sizeof(float) * q.ld_xh, sizeof(float) * q.D,

@@ -39,6 +39,7 @@ struct ModDesc {
 
 struct ArchDesc {
   int M, L, Z, C, combine, loss_kind, non_linear;
+  int MD;                                // decoder sets: M, or 2 M with NMB_HEAD_ENDTOEND (mod[M + m] = disease decoder of m)
   int hidden[NMB_MAX_HIDDEN];
   ModDesc mod[NMB_MAX_MOD];
   long long alpha_off;
@@ -52,7 +53,16 @@ struct ArchDesc {
   LinDesc hd[NMB_MAX_HEAD + 1];
   long long s_R, s_dR; int ld_R;                              // residual rows and their gradient
   long long s_hh[NMB_MAX_HEAD]; int ld_hh[NMB_MAX_HEAD];      // head hidden activations (post-ReLU | 1)
-  long long s_pred, s_dpred;                                  // [B][4]: prediction, d(total)/d(prediction)
+  long long s_pred, s_dpred;                                  // [B][4]: prediction / logits, d(total)/d(.)
+  // NMB_HEAD_ENDTOEND: classifier on z with BatchNorm + dropout after every hidden layer
+  float hp[6];                                                // NMB_HP_*
+  long long bn_off[NMB_MAX_HEAD]; int bn_ld[NMB_MAX_HEAD];    // 5 vectors at stride bn_ld: gamma, beta, running mean / var, count
+  long long s_zc; int ld_zc;                                  // classifier input [z | 1]
+  long long s_xn[NMB_MAX_HEAD];                               // normalised pre-activations (ld_hh)
+  long long s_gate[NMB_MAX_HEAD];                             // relu gate x dropout scale (ld_hh)
+  long long s_bn[NMB_MAX_HEAD];                               // [2][bn_ld]: batch inverse std, scratch
+  long long s_dev;                                            // [B][4]: deviation health, disease, contrastive sign, label
+  int drop_w;                                                 // sum of the hidden widths (row length of drop_keep)
   long long scratch_floats;
 };
 
@@ -65,6 +75,8 @@ struct MemberDev {
   const float* lr_steps;
   const float* y;           // head targets [n_rows]
   const int* row_order;     // [epochs][M][n_rows] or NULL
+  const float* drop_keep;   // injected dropout keep flags or NULL
+  long long n_drop_steps;
   unsigned long long seed;
   float lr, beta1, beta2, adam_eps;
   long long steps_done;     // mutable: minibatch steps taken so far
@@ -81,7 +93,10 @@ inline int build_arch(const NmbArch& a, ArchDesc* d, const char** err) {
   if (a.latent < 1 || a.c_dim < 0) return fail("bad latent / c_dim");
   if (a.combine < 0 || a.combine > NMB_COMBINE_MOPOE) return fail("No such combination method");
   if (a.loss_kind < 0 || a.loss_kind > NMB_LOSS_NEG_MSE) return fail("bad loss_kind");
-  if (a.head_kind != NMB_HEAD_NONE && a.head_kind != NMB_HEAD_REGRESSION) return fail("bad head_kind");
+  if (a.head_kind < NMB_HEAD_NONE || a.head_kind > NMB_HEAD_ENDTOEND) return fail("bad head_kind");
+  if (a.head_kind == NMB_HEAD_ENDTOEND && 2 * a.n_mod > NMB_MAX_MOD) return fail("NMB_HEAD_ENDTOEND: at most 8 modalities");
+  if (a.head_kind == NMB_HEAD_ENDTOEND && !(a.head_params[NMB_HP_DROPOUT] >= 0.f && a.head_params[NMB_HP_DROPOUT] < 1.f))
+    return fail("dropout rate must be in [0, 1)");
   if (a.head_kind && (a.n_head_hidden < 1 || a.n_head_hidden > NMB_MAX_HEAD)) return fail("n_head_hidden out of range (1..3)");
   *d = ArchDesc{};
   d->M = a.n_mod; d->L = a.n_hidden; d->Z = a.latent; d->C = a.c_dim;
@@ -99,13 +114,16 @@ inline int build_arch(const NmbArch& a, ArchDesc* d, const char** err) {
   };
   auto buf = [&](int ld) { long long r = so; so += (long long)B * ld; return r; };
   int maxw = 2 * Z;
-  for (int m = 0; m < d->M; ++m) {
+  d->MD = a.head_kind == NMB_HEAD_ENDTOEND ? 2 * d->M : d->M;
+  for (int m = 0; m < d->MD; ++m) {
     ModDesc& q = d->mod[m];
-    q.D = a.input_dims[m];
+    q.D = a.input_dims[m % d->M];
     if (q.D < 1) return fail("bad input dim");
     q.ldx = round4(q.D + C + 1);
-    for (int l = 0; l < L; ++l) q.enc[l] = lin(l == 0 ? q.D + C : d->hidden[l - 1], d->hidden[l]);
-    q.head = lin(d->hidden[L - 1], 2 * Z);
+    if (m < d->M) {
+      for (int l = 0; l < L; ++l) q.enc[l] = lin(l == 0 ? q.D + C : d->hidden[l - 1], d->hidden[l]);
+      q.head = lin(d->hidden[L - 1], 2 * Z);
+    }
     for (int l = 0; l < L; ++l) q.dec[l] = lin(l == 0 ? Z + C : d->hidden[L - l], d->hidden[L - 1 - l]);
     q.outl = lin(d->hidden[0], q.D);
     q.lam_off = off; off += round4(q.D);
@@ -120,7 +138,27 @@ inline int build_arch(const NmbArch& a, ArchDesc* d, const char** err) {
   }
   d->alpha_off = off; off += round4(d->M);
   d->head_kind = a.head_kind; d->HL = 0; d->sumD = 0; d->head_weight = a.head_weight;
-  if (a.head_kind) {     // appended after alpha: the packed layout of a head-less model is a prefix of this one
+  if (a.head_kind == NMB_HEAD_ENDTOEND) {
+    d->HL = a.n_head_hidden;
+    for (int i = 0; i < 6; ++i) d->hp[i] = a.head_params[i];
+    d->ld_zc = round4(Z + 1); d->s_zc = buf(d->ld_zc);
+    for (int l = 0; l <= d->HL; ++l) {
+      if (l < d->HL) {
+        if (a.head_hidden[l] < 1) return fail("bad head width");
+        d->head_w[l] = a.head_hidden[l];
+        d->drop_w += d->head_w[l];
+        if (d->head_w[l] > maxw) maxw = d->head_w[l];
+      }
+      d->hd[l] = lin(l == 0 ? Z : d->head_w[l - 1], l == d->HL ? 2 : d->head_w[l]);
+      if (l < d->HL) {
+        d->bn_ld[l] = round4(d->head_w[l]); d->bn_off[l] = off; off += 5LL * d->bn_ld[l];
+        d->ld_hh[l] = round4(d->head_w[l] + 1);
+        d->s_hh[l] = buf(d->ld_hh[l]); d->s_xn[l] = buf(d->ld_hh[l]); d->s_gate[l] = buf(d->ld_hh[l]);
+        d->s_bn[l] = so; so += 2LL * d->bn_ld[l];
+      }
+    }
+    d->s_pred = buf(4); d->s_dpred = buf(4); d->s_dev = buf(4);
+  } else if (a.head_kind) {     // appended after alpha: the packed layout of a head-less model is a prefix of this one
     d->HL = a.n_head_hidden;
     for (int m = 0; m < d->M; ++m) { d->mod[m].r_off = d->sumD; d->sumD += d->mod[m].D; d->mod[m].s_in = buf(d->mod[m].ldx); }
     for (int l = 0; l <= d->HL; ++l) {

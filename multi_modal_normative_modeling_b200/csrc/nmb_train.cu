@@ -260,7 +260,7 @@ __device__ __forceinline__ void mm(const StepCtx& c, int M, int N, int K, Opnd A
 // columns and stale rows are never read (every GEMM operand load is bounds-guarded).
 __device__ void prepare_slot(const StepCtx& c) {
   const ArchDesc& a = *c.a;
-  for (int m = 0; m < a.M; ++m) {
+  for (int m = 0; m < a.MD; ++m) {
     const ModDesc& q = a.mod[m];
     for (int b = threadIdx.x; b < kMaxBatch; b += kThreads) {
       for (int l = 0; l < a.L; ++l) {
@@ -272,7 +272,8 @@ __device__ void prepare_slot(const StepCtx& c) {
   }
   if (a.head_kind) {
     for (int b = threadIdx.x; b < kMaxBatch; b += kThreads) {
-      c.scratch[a.s_R + (long long)b * a.ld_R + a.sumD] = 1.f;
+      if (a.head_kind == NMB_HEAD_REGRESSION) c.scratch[a.s_R + (long long)b * a.ld_R + a.sumD] = 1.f;
+      else c.scratch[a.s_zc + (long long)b * a.ld_zc + a.Z] = 1.f;
       for (int l = 0; l < a.HL; ++l) c.scratch[a.s_hh[l] + (long long)b * a.ld_hh[l] + a.head_w[l]] = 1.f;
     }
   }
@@ -322,7 +323,7 @@ __device__ float latent_forward(const StepCtx& c, const float* const* xc, int ep
       if (eps_mode == 3) {
         const float zz = eps_src[e];
         S[a.s_mub + e] = zz; S[a.s_lvb + e] = 0.f; S[a.s_eps + e] = 0.f;
-        for (int m = 0; m < M; ++m) S[a.mod[m].s_g0 + (long long)b * a.mod[m].ld_g0 + z] = zz;
+        for (int m = 0; m < a.MD; ++m) S[a.mod[m].s_g0 + (long long)b * a.mod[m].ld_g0 + z] = zz;
         continue;
       }
       float mu[NMB_MAX_MOD], lv[NMB_MAX_MOD];
@@ -334,14 +335,14 @@ __device__ float latent_forward(const StepCtx& c, const float* const* xc, int ep
       const float eps = eps_mode == 1 ? eps_src[e] : nrm[j];
       S[a.s_mub + e] = f.mu; S[a.s_lvb + e] = f.lv; S[a.s_eps + e] = eps;
       const float zz = f.mu + eps * expf(0.5f * f.lv);
-      for (int m = 0; m < M; ++m) S[a.mod[m].s_g0 + (long long)b * a.mod[m].ld_g0 + z] = zz;
+      for (int m = 0; m < a.MD; ++m) S[a.mod[m].s_g0 + (long long)b * a.mod[m].ld_g0 + z] = zz;
       kl += -0.5f * (1.f + f.lv - f.mu * f.mu - expf(f.lv));
     }
   }
   // covariates into the decoder inputs (Decoder.forward: cat((z, c)), cVAE.py:199)
-  for (int m = 0; m < M; ++m) {
+  for (int m = 0; m < a.MD; ++m) {
     const ModDesc& q = a.mod[m];
-    const float* src = xc[m] + (long long)c.row0 * q.ldx + q.D;
+    const float* src = xc[m % M] + (long long)c.row0 * q.ldx + q.D;
     float* dst = S + q.s_g0 + Z;
     for (int e = threadIdx.x; e < c.rows * a.C; e += kThreads) {
       const int b = e / a.C, j = e - b * a.C;
@@ -460,6 +461,388 @@ __device__ void head_fold(const StepCtx& c, int m) {
   __syncthreads();
 }
 
+__device__ void e2e_fold(const StepCtx& c, int m);
+
+// Backward of decoder set m (logvar_out, decoder_mean_layer, hidden layers down to dz) fused with Adam.
+//   lam_scale: weight of the reconstruction term in the total (1; w_rec for the end-to-end model)
+//   fold: fold another loss's d/d(x_recon) into s_xh after the logvar_out gradient (1 = regression head, 2 = contrastive)
+template <bool TC>
+__device__ void decoder_backward(const StepCtx& c, const AdamCfg& ad, int m, float lam_scale, bool dz_accumulate, int fold) {
+  const ArchDesc& a = *c.a;
+  float* S = c.scratch;
+  float* P = c.mb->params;
+  const int L = a.L, Z = a.Z, rows = c.rows;
+  const float inv_rows = 1.f / rows;
+  const int gauss = a.loss_kind == NMB_LOSS_GAUSS_LL;
+  float* gbuf[2] = {S + a.s_ga, S + a.s_gb};
+  {
+    const ModDesc& q = a.mod[m];
+    float* dxh = S + q.s_xh;
+    // logvar_out: d/d lam_n = sum_b 0.5 (1 - r^2/sigma^2) / B, with r/sigma^2 = -B * dxh
+    if (gauss) {
+      for (int n = threadIdx.x; n < q.D; n += kThreads) {
+        const float var = __expf(P[q.lam_off + n]);
+        const float* col = dxh + n;
+        float acc = 0.f;
+        int b = 0;
+        for (; b + 8 <= rows; b += 8) {
+          float t[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) t[u] = col[(long long)(b + u) * q.ld_xh];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) { const float w = t[u] * rows; acc += 0.5f * (1.f - w * w * var); }
+        }
+        for (; b < rows; ++b) { const float w = col[(long long)b * q.ld_xh] * rows; acc += 0.5f * (1.f - w * w * var); }
+        ad.apply(q.lam_off + n, lam_scale * acc * inv_rows);
+      }
+    }
+    if (fold == 1) head_fold(c, m);
+    else if (fold == 2) e2e_fold(c, m);
+    int cur = 0;
+    // decoder_mean_layer
+    {
+      const LinDesc& w = q.outl;
+      const float* act = S + q.s_k[L - 1]; const int ld_act = q.ld_k[L - 1];
+      EpiDgrad eg{gbuf[cur], a.ld_g, act, ld_act, a.non_linear};
+      mm<TC>(c, rows, w.in, w.out, Opnd{dxh, q.ld_xh, 1}, Opnd{P + w.off, w.ld, 0}, eg);
+      EpiWgradAdam ew{ad, w.off, w.ld};
+      mm<TC>(c, w.out, w.in + 1, rows, Opnd{dxh, q.ld_xh, 0}, Opnd{act, ld_act, 0}, ew);
+    }
+    for (int l = L - 1; l >= 0; --l) {
+      const LinDesc& w = q.dec[l];
+      const float* dy = gbuf[cur];
+      const float* in_act = l == 0 ? S + q.s_g0 : S + q.s_k[l - 1];
+      const int ld_in = l == 0 ? q.ld_g0 : q.ld_k[l - 1];
+      if (l > 0) {
+        EpiDgrad eg{gbuf[cur ^ 1], a.ld_g, in_act, ld_in, a.non_linear};
+        mm<TC>(c, rows, w.in, w.out, Opnd{dy, a.ld_g, 1}, Opnd{P + w.off, w.ld, 0}, eg);
+      } else {
+        EpiDz ez{S + a.s_dz, Z, dz_accumulate};
+        mm<TC>(c, rows, Z, w.out, Opnd{dy, a.ld_g, 1}, Opnd{P + w.off, w.ld, 0}, ez);
+      }
+      EpiWgradAdam ew{ad, w.off, w.ld};
+      mm<TC>(c, w.out, w.in + 1, rows, Opnd{dy, a.ld_g, 0}, Opnd{in_act, ld_in, 0}, ew);
+      cur ^= 1;
+    }
+  }
+}
+
+// klw: weight of the KL term in the total (M for sum_m (kl - ll_m); w_kl for the end-to-end model)
+__device__ void latent_backward(const StepCtx& c, const AdamCfg& ad, float klw) {
+  const ArchDesc& a = *c.a;
+  float* S = c.scratch;
+  float* P = c.mb->params;
+  const int M = a.M, Z = a.Z, rows = c.rows;
+  const float inv_rows = 1.f / rows;
+  // latent backward: d mu_bar = dz + M mu/B ; d lv_bar = dz eps s/2 + M (e^lv - 1)/(2B)
+  {
+    float w[NMB_MAX_MOD], dw_acc[NMB_MAX_MOD];
+    const bool gpoe = M > 1 && a.combine == NMB_COMBINE_GPOE;
+    if (gpoe) softmax_alpha(P + a.alpha_off, M, w);
+    for (int m = 0; m < M; ++m) dw_acc[m] = 0.f;
+    for (int e = threadIdx.x; e < rows * Z; e += kThreads) {
+      const int b = e / Z, z = e - b * Z;
+      const float mub = S[a.s_mub + e], lvb = S[a.s_lvb + e], eps = S[a.s_eps + e], dz = S[a.s_dz + e];
+      const float sd = expf(0.5f * lvb);
+      const float dmu_bar = dz + klw * mub * inv_rows;
+      const float dlv_bar = dz * eps * sd * 0.5f + klw * (expf(lvb) - 1.f) * 0.5f * inv_rows;
+      float mu[NMB_MAX_MOD], lv[NMB_MAX_MOD], dmu[NMB_MAX_MOD], dlv[NMB_MAX_MOD], dw[NMB_MAX_MOD];
+      for (int m = 0; m < M; ++m) {
+        const float* h = S + a.mod[m].s_mulv + (long long)b * a.mod[m].ld_mulv;
+        mu[m] = h[z]; lv[m] = h[Z + z];
+      }
+      fuse_backward(mu, lv, M, a.combine, w, dmu_bar, dlv_bar, dmu, dlv, gpoe ? dw : nullptr);
+      for (int m = 0; m < M; ++m) {
+        float* d = S + a.mod[m].s_dmulv + (long long)b * a.mod[m].ld_mulv;
+        d[z] = dmu[m]; d[Z + z] = dlv[m];
+        if (gpoe) dw_acc[m] += dw[m];
+      }
+    }
+    if (gpoe) {   // softmax backward + Adam on alpha_m (cVAE.py:1154)
+      float dw_tot[NMB_MAX_MOD];
+      for (int m = 0; m < M; ++m) dw_tot[m] = block_sum(dw_acc[m], c.red);
+      if (threadIdx.x == 0) {
+        float dot = 0.f;
+        for (int m = 0; m < M; ++m) dot += w[m] * dw_tot[m];
+        for (int m = 0; m < M; ++m) ad.apply(a.alpha_off + m, w[m] * (dw_tot[m] - dot));
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <bool TC>
+__device__ void encoder_backward(const StepCtx& c, const AdamCfg& ad, int m) {
+  const ArchDesc& a = *c.a;
+  float* S = c.scratch;
+  float* P = c.mb->params;
+  const int L = a.L, rows = c.rows;
+  float* gbuf[2] = {S + a.s_ga, S + a.s_gb};
+  {
+    const ModDesc& q = a.mod[m];
+    const float* dmulv = S + q.s_dmulv;
+    int cur = 0;
+    {
+      const LinDesc& w = q.head;
+      const float* act = S + q.s_h[L - 1]; const int ld_act = q.ld_h[L - 1];
+      EpiDgrad eg{gbuf[cur], a.ld_g, act, ld_act, a.non_linear};
+      mm<TC>(c, rows, w.in, w.out, Opnd{dmulv, q.ld_mulv, 1}, Opnd{P + w.off, w.ld, 0}, eg);
+      EpiWgradAdam ew{ad, w.off, w.ld};
+      mm<TC>(c, w.out, w.in + 1, rows, Opnd{dmulv, q.ld_mulv, 0}, Opnd{act, ld_act, 0}, ew);
+    }
+    for (int l = L - 1; l >= 0; --l) {
+      const LinDesc& w = q.enc[l];
+      const float* dy = gbuf[cur];
+      const float* in_act = l == 0 ? c.xin[m] + (long long)c.row0 * q.ldx : S + q.s_h[l - 1];
+      const int ld_in = l == 0 ? q.ldx : q.ld_h[l - 1];
+      if (l > 0) {
+        EpiDgrad eg{gbuf[cur ^ 1], a.ld_g, in_act, ld_in, a.non_linear};
+        mm<TC>(c, rows, w.in, w.out, Opnd{dy, a.ld_g, 1}, Opnd{P + w.off, w.ld, 0}, eg);
+      }
+      EpiWgradAdam ew{ad, w.off, w.ld};
+      mm<TC>(c, w.out, w.in + 1, rows, Opnd{dy, a.ld_g, 0}, Opnd{in_act, ld_in, 0}, ew);
+      cur ^= 1;
+    }
+  }
+}
+
+// ---- end-to-end supervised model (NMB_HEAD_ENDTOEND, cVAE_multimodal_endtoend v2, cVAE.py:2004-2207) -------------
+// Dropout keep flag of classifier unit (layer l, row b, unit j) at global step `step`: injected, or Philox stream 2.
+__device__ __forceinline__ float e2e_keep(const StepCtx& c, int l, int b, int j, int col0, float p) {
+  const MemberDev& mb = *c.mb;
+  const ArchDesc& a = *c.a;
+  if (p <= 0.f) return 1.f;
+  if (mb.drop_keep)
+    return mb.drop_keep[((c.step % mb.n_drop_steps) * mb.batch + b) * (long long)a.drop_w + col0 + j];
+  const uint32_t e = (uint32_t)(b * a.drop_w + col0 + j);
+  uint32_t w[4];
+  philox4x32_10(e >> 2, (uint32_t)c.step, (uint32_t)((unsigned long long)c.step >> 32), 2u, (uint32_t)mb.seed,
+                (uint32_t)(mb.seed >> 32), w);
+  const float u = ((float)(w[e & 3] >> 9) + 0.5f) * 1.1920928955078125e-07f;
+  return u >= p ? 1.f : 0.f;                       // bernoulli(1 - p)
+}
+
+// Classifier forward on [z | 1] (s_zc).  train: BatchNorm1d with batch statistics (+ running-statistics update,
+// momentum 0.1, unbiased variance -- torch defaults), ReLU, Dropout(p); eval: running statistics, no dropout.
+// Logits land in s_pred[b * 4 + {0, 1}].
+template <bool TC>
+__device__ void e2e_classifier_forward(const StepCtx& c, bool train) {
+  const ArchDesc& a = *c.a;
+  float* S = c.scratch;
+  float* P = c.mb->params;
+  const int rows = c.rows;
+  const float p = a.hp[NMB_HP_DROPOUT];
+  Opnd A{S + a.s_zc, a.ld_zc, 1};
+  int col0 = 0;
+  for (int l = 0; l < a.HL; ++l) {
+    const LinDesc& w = a.hd[l];
+    const int W = a.head_w[l], ld = a.ld_hh[l], bl = a.bn_ld[l];
+    EpiStore e{S + a.s_xn[l], ld};
+    mm<TC>(c, rows, w.out, w.in + 1, A, Opnd{P + w.off, w.ld, 1}, e);
+    __syncthreads();
+    float* bn = P + a.bn_off[l];                  // gamma | beta | running mean | running var | count
+    float* xn = S + a.s_xn[l];
+    float* istd = S + a.s_bn[l];
+    for (int j = threadIdx.x; j < W; j += kThreads) {
+      float mean, var;
+      if (train) {
+        float s1 = 0.f;
+        for (int b = 0; b < rows; ++b) s1 += xn[(long long)b * ld + j];
+        mean = s1 / rows;
+        float s2 = 0.f;
+        for (int b = 0; b < rows; ++b) { const float d = xn[(long long)b * ld + j] - mean; s2 += d * d; }
+        var = s2 / rows;                           // biased: what normalises the batch
+        if (!(c.flags & NMB_TRAIN_NO_STATS)) {
+          bn[2 * bl + j] = 0.9f * bn[2 * bl + j] + 0.1f * mean;
+          bn[3 * bl + j] = 0.9f * bn[3 * bl + j] + 0.1f * (rows > 1 ? s2 / (rows - 1) : var);
+          if (j == 0) bn[4 * bl] += 1.f;
+        }
+      } else {
+        mean = bn[2 * bl + j]; var = bn[3 * bl + j];
+      }
+      const float is = 1.f / sqrtf(var + 1e-5f);
+      istd[j] = is;
+      const float g = bn[j], be = bn[bl + j];
+      for (int b = 0; b < rows; ++b) {
+        const float v = (xn[(long long)b * ld + j] - mean) * is;
+        const float y = g * v + be;
+        float gate = y > 0.f ? 1.f : 0.f;
+        if (train && p > 0.f) gate *= e2e_keep(c, l, b, j, col0, p) / (1.f - p);
+        xn[(long long)b * ld + j] = v;
+        S[a.s_gate[l] + (long long)b * ld + j] = gate;
+        S[a.s_hh[l] + (long long)b * ld + j] = y * gate;
+      }
+    }
+    __syncthreads();
+    A = Opnd{S + a.s_hh[l], ld, 1};
+    col0 += W;
+  }
+  const LinDesc& w = a.hd[a.HL];
+  EpiStore e{S + a.s_pred, 4};
+  mm<TC>(c, rows, 2, w.in + 1, A, Opnd{P + w.off, w.ld, 1}, e);
+  __syncthreads();
+}
+
+__device__ void e2e_copy_z(const StepCtx& c) {
+  const ArchDesc& a = *c.a;
+  float* S = c.scratch;
+  const ModDesc& q = a.mod[0];
+  for (int e = threadIdx.x; e < c.rows * a.Z; e += kThreads) {
+    const int b = e / a.Z, z = e - b * a.Z;
+    S[a.s_zc + (long long)b * a.ld_zc + z] = S[q.s_g0 + (long long)b * q.ld_g0 + z];
+  }
+  __syncthreads();
+}
+
+// d(total)/d(x_recon) of decoder set m: w_rec x likelihood part (already in s_xh) + the contrastive hinge through the
+// per-subject deviation mean_m mean_d (x - x_recon)^2 (cVAE.py:2150-2172); s_dev[b][2] holds w_con * sign_b / B.
+__device__ void e2e_fold(const StepCtx& c, int m) {
+  const ArchDesc& a = *c.a;
+  const ModDesc& q = a.mod[m];
+  float* S = c.scratch;
+  float* dxh = S + q.s_xh;
+  const float* xr = S + q.s_xr;
+  const float* x = c.xin[m % a.M] + (long long)c.row0 * q.ldx;
+  const float grp = m < a.M ? 1.f : -1.f;               // health decoders enter the hinge with +, disease with -
+  const float k = 2.f / (q.D * a.M), w_rec = a.hp[NMB_HP_W_REC];
+  __syncthreads();
+  for (int e = threadIdx.x; e < c.rows * q.D; e += kThreads) {
+    const int b = e / q.D, n = e - b * q.D;
+    const float r = xr[(long long)b * q.ld_xh + n] - x[(long long)b * q.ldx + n];
+    dxh[(long long)b * q.ld_xh + n] = w_rec * dxh[(long long)b * q.ld_xh + n] + grp * S[a.s_dev + 4 * b + 2] * k * r;
+  }
+  __syncthreads();
+}
+
+template <bool TC>
+__device__ void train_step_e2e(StepCtx& c, const float* eps_src, float* loss_out) {
+  const ArchDesc& a = *c.a;
+  MemberDev& mb = *c.mb;
+  float* S = c.scratch;
+  float* P = mb.params;
+  const int M = a.M, rows = c.rows;
+  const float inv_rows = 1.f / rows;
+  const float margin = a.hp[NMB_HP_MARGIN], w_con = a.hp[NMB_HP_W_CONTRASTIVE], w_kl = a.hp[NMB_HP_W_KL],
+              w_rec = a.hp[NMB_HP_W_REC];
+
+  // ---------------- forward (cVAE.py:2108-2125) ----------------
+  encoders_forward<TC>(c, c.xin);
+  float kl = latent_forward(c, c.xin, eps_src ? 1 : 0, eps_src, 0u, (unsigned long long)c.step);
+  kl = block_sum(kl, c.red) * inv_rows;
+  float rec[2] = {0.f, 0.f};
+  for (int m = 0; m < a.MD; ++m) {
+    const ModDesc& q = a.mod[m];
+    Opnd A = decoder_hidden<TC>(c, m);
+    EpiRecon e;
+    e.x = c.xin[m % M] + (long long)c.row0 * q.ldx; e.ldx = q.ldx;
+    e.lam = P + q.lam_off;
+    e.dxh = S + q.s_xh; e.ld = q.ld_xh;
+    e.keep = S + q.s_xr;
+    e.inv_rows = inv_rows; e.inv_rows_d = inv_rows / q.D; e.gauss = 1; e.ll_acc = 0.f;
+    mm<TC>(c, rows, q.D, q.outl.in + 1, A, Opnd{P + q.outl.off, q.outl.ld, 1}, e);
+    rec[m < M ? 0 : 1] -= block_sum(e.ll_acc, c.red) * inv_rows;          // -log_prob(x).sum(1).mean() (:2131-2134)
+  }
+  __syncthreads();
+  // per-subject deviations of the two decoder sets and the contrastive hinge (:2150-2172); one warp per row
+  float con_acc = 0.f;
+  {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int b = warp; b < rows; b += kThreads / 32) {
+      float dv[2] = {0.f, 0.f};
+      for (int m = 0; m < a.MD; ++m) {
+        const ModDesc& q = a.mod[m];
+        const float* x = c.xin[m % M] + (long long)(c.row0 + b) * q.ldx;
+        const float* xr = S + q.s_xr + (long long)b * q.ld_xh;
+        float acc = 0.f;
+        for (int n = lane; n < q.D; n += 32) { const float r = x[n] - xr[n]; acc += r * r; }
+        dv[m < M ? 0 : 1] += warp_sum(acc) / q.D;
+      }
+      dv[0] /= M; dv[1] /= M;
+      const float yb = mb.y[c.yidx ? c.yidx[c.row0 + b] : c.row0 + b];      // 0 = healthy, 1 = disease
+      const float t = yb > 0.5f ? margin + dv[1] - dv[0] : margin + dv[0] - dv[1];
+      float sgn = 0.f;
+      if (t > 0.f) sgn = yb > 0.5f ? -1.f : 1.f;       // d hinge / d dev_health
+      if (lane == 0) {
+        S[a.s_dev + 4 * b + 0] = dv[0]; S[a.s_dev + 4 * b + 1] = dv[1];
+        S[a.s_dev + 4 * b + 2] = w_con * sgn * inv_rows; S[a.s_dev + 4 * b + 3] = yb;
+        con_acc += t > 0.f ? t : 0.f;
+      }
+    }
+  }
+  const float con = block_sum(con_acc, c.red) * inv_rows;
+  // classifier on z, cross-entropy (:2118, :2178)
+  e2e_copy_z(c);
+  e2e_classifier_forward<TC>(c, true);
+  float ce_acc = 0.f;
+  for (int b = threadIdx.x; b < rows; b += kThreads) {
+    const float l0 = S[a.s_pred + 4 * b], l1 = S[a.s_pred + 4 * b + 1];
+    const float mx = fmaxf(l0, l1);
+    const float e0 = expf(l0 - mx), e1 = expf(l1 - mx), den = e0 + e1;
+    const int y = S[a.s_dev + 4 * b + 3] > 0.5f;
+    ce_acc += -((y ? l1 : l0) - mx - logf(den));
+    S[a.s_dpred + 4 * b] = (e0 / den - (y ? 0.f : 1.f)) * inv_rows;
+    S[a.s_dpred + 4 * b + 1] = (e1 / den - (y ? 1.f : 0.f)) * inv_rows;
+  }
+  const float ce = block_sum(ce_acc, c.red) * inv_rows;
+  if (loss_out && threadIdx.x == 0) {
+    const float total = w_rec * (rec[0] + rec[1]) + w_kl * kl + ce + w_con * con;      // :2183
+    loss_out[0] = total; loss_out[1] = kl; loss_out[2] = -(rec[0] + rec[1]);
+    if (c.flags & (NMB_TRAIN_LOSS4 | NMB_TRAIN_LOSS8)) loss_out[3] = ce;
+    if (c.flags & NMB_TRAIN_LOSS8) { loss_out[4] = rec[0]; loss_out[5] = rec[1]; loss_out[6] = con; loss_out[7] = 0.f; }
+  }
+
+  // ---------------- backward + Adam ----------------
+  const AdamCfg ad = make_adam(c);
+  {   // classifier
+    float* gbuf[2] = {S + a.s_ga, S + a.s_gb};
+    const float* dy = S + a.s_dpred; int ld_dy = 4;
+    int cur = 0;
+    for (int l = a.HL; l >= 0; --l) {
+      const LinDesc& w = a.hd[l];
+      const float* in_act = l == 0 ? S + a.s_zc : S + a.s_hh[l - 1];
+      const int ld_in = l == 0 ? a.ld_zc : a.ld_hh[l - 1];
+      if (l > 0) {
+        EpiStore es{gbuf[cur], a.ld_g};
+        mm<TC>(c, rows, w.in, w.out, Opnd{dy, ld_dy, 1}, Opnd{P + w.off, w.ld, 0}, es);
+      } else {
+        EpiDz ez{S + a.s_dz, a.Z, 0};
+        mm<TC>(c, rows, a.Z, w.out, Opnd{dy, ld_dy, 1}, Opnd{P + w.off, w.ld, 0}, ez);
+      }
+      EpiWgradAdam ew{ad, w.off, w.ld};
+      mm<TC>(c, w.out, w.in + 1, rows, Opnd{dy, ld_dy, 0}, Opnd{in_act, ld_in, 0}, ew);
+      if (l > 0) {
+        // through Dropout, ReLU and BatchNorm of hidden layer l - 1: gbuf[cur] = d h  ->  d(pre-BN activations), in place
+        const int k = l - 1, W = a.head_w[k], ld = a.ld_hh[k], bl = a.bn_ld[k];
+        float* g = gbuf[cur];
+        const float* xn = S + a.s_xn[k];
+        const float* gate = S + a.s_gate[k];
+        const float* istd = S + a.s_bn[k];
+        __syncthreads();
+        for (int j = threadIdx.x; j < W; j += kThreads) {
+          float sg = 0.f, sgx = 0.f;
+          for (int b = 0; b < rows; ++b) {
+            const float d = g[(long long)b * a.ld_g + j] * gate[(long long)b * ld + j];
+            sg += d; sgx += d * xn[(long long)b * ld + j];
+          }
+          const float gam = P[a.bn_off[k] + j], is = istd[j];
+          for (int b = 0; b < rows; ++b) {
+            const float d = g[(long long)b * a.ld_g + j] * gate[(long long)b * ld + j];
+            g[(long long)b * a.ld_g + j] = gam * is * (d - sg * inv_rows - xn[(long long)b * ld + j] * sgx * inv_rows);
+          }
+          ad.apply(a.bn_off[k] + j, sgx);               // d gamma
+          ad.apply(a.bn_off[k] + bl + j, sg);           // d beta
+        }
+        __syncthreads();
+        dy = g; ld_dy = a.ld_g; cur ^= 1;
+      }
+    }
+    __syncthreads();
+  }
+  for (int m = 0; m < a.MD; ++m) decoder_backward<TC>(c, ad, m, w_rec, true, 2);     // dz accumulates onto the classifier's
+  latent_backward(c, ad, w_kl);
+  for (int m = 0; m < M; ++m) encoder_backward<TC>(c, ad, m);
+}
+
 // ---- one training step ---------------------------------------------------------------------
 template <bool TC>
 __device__ void train_step(StepCtx& c, const float* eps_src, float* loss_out) {
@@ -497,119 +880,9 @@ __device__ void train_step(StepCtx& c, const float* eps_src, float* loss_out) {
     loss_out[0] = M * kl - ll_sum + a.head_weight * head_loss; loss_out[1] = M * kl; loss_out[2] = ll_sum;   // cVAE.py:1187-1196
     if (c.flags & NMB_TRAIN_LOSS4) loss_out[3] = head_loss;                                                // cVAE.py:2343-2345
   }
-  float* gbuf[2] = {S + a.s_ga, S + a.s_gb};
-  for (int m = 0; m < M; ++m) {
-    const ModDesc& q = a.mod[m];
-    float* dxh = S + q.s_xh;
-    // logvar_out: d/d lam_n = sum_b 0.5 (1 - r^2/sigma^2) / B, with r/sigma^2 = -B * dxh
-    if (gauss) {
-      for (int n = threadIdx.x; n < q.D; n += kThreads) {
-        const float var = __expf(P[q.lam_off + n]);
-        const float* col = dxh + n;
-        float acc = 0.f;
-        int b = 0;
-        for (; b + 8 <= rows; b += 8) {
-          float t[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) t[u] = col[(long long)(b + u) * q.ld_xh];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) { const float w = t[u] * rows; acc += 0.5f * (1.f - w * w * var); }
-        }
-        for (; b < rows; ++b) { const float w = col[(long long)b * q.ld_xh] * rows; acc += 0.5f * (1.f - w * w * var); }
-        ad.apply(q.lam_off + n, acc * inv_rows);
-      }
-    }
-    if (a.head_kind) head_fold(c, m);
-    int cur = 0;
-    // decoder_mean_layer
-    {
-      const LinDesc& w = q.outl;
-      const float* act = S + q.s_k[L - 1]; const int ld_act = q.ld_k[L - 1];
-      EpiDgrad eg{gbuf[cur], a.ld_g, act, ld_act, a.non_linear};
-      mm<TC>(c, rows, w.in, w.out, Opnd{dxh, q.ld_xh, 1}, Opnd{P + w.off, w.ld, 0}, eg);
-      EpiWgradAdam ew{ad, w.off, w.ld};
-      mm<TC>(c, w.out, w.in + 1, rows, Opnd{dxh, q.ld_xh, 0}, Opnd{act, ld_act, 0}, ew);
-    }
-    for (int l = L - 1; l >= 0; --l) {
-      const LinDesc& w = q.dec[l];
-      const float* dy = gbuf[cur];
-      const float* in_act = l == 0 ? S + q.s_g0 : S + q.s_k[l - 1];
-      const int ld_in = l == 0 ? q.ld_g0 : q.ld_k[l - 1];
-      if (l > 0) {
-        EpiDgrad eg{gbuf[cur ^ 1], a.ld_g, in_act, ld_in, a.non_linear};
-        mm<TC>(c, rows, w.in, w.out, Opnd{dy, a.ld_g, 1}, Opnd{P + w.off, w.ld, 0}, eg);
-      } else {
-        EpiDz ez{S + a.s_dz, Z, m > 0};
-        mm<TC>(c, rows, Z, w.out, Opnd{dy, a.ld_g, 1}, Opnd{P + w.off, w.ld, 0}, ez);
-      }
-      EpiWgradAdam ew{ad, w.off, w.ld};
-      mm<TC>(c, w.out, w.in + 1, rows, Opnd{dy, a.ld_g, 0}, Opnd{in_act, ld_in, 0}, ew);
-      cur ^= 1;
-    }
-  }
-
-  // latent backward: d mu_bar = dz + M mu/B ; d lv_bar = dz eps s/2 + M (e^lv - 1)/(2B)
-  {
-    float w[NMB_MAX_MOD], dw_acc[NMB_MAX_MOD];
-    const bool gpoe = M > 1 && a.combine == NMB_COMBINE_GPOE;
-    if (gpoe) softmax_alpha(P + a.alpha_off, M, w);
-    for (int m = 0; m < M; ++m) dw_acc[m] = 0.f;
-    for (int e = threadIdx.x; e < rows * Z; e += kThreads) {
-      const int b = e / Z, z = e - b * Z;
-      const float mub = S[a.s_mub + e], lvb = S[a.s_lvb + e], eps = S[a.s_eps + e], dz = S[a.s_dz + e];
-      const float sd = expf(0.5f * lvb);
-      const float dmu_bar = dz + M * mub * inv_rows;
-      const float dlv_bar = dz * eps * sd * 0.5f + M * (expf(lvb) - 1.f) * 0.5f * inv_rows;
-      float mu[NMB_MAX_MOD], lv[NMB_MAX_MOD], dmu[NMB_MAX_MOD], dlv[NMB_MAX_MOD], dw[NMB_MAX_MOD];
-      for (int m = 0; m < M; ++m) {
-        const float* h = S + a.mod[m].s_mulv + (long long)b * a.mod[m].ld_mulv;
-        mu[m] = h[z]; lv[m] = h[Z + z];
-      }
-      fuse_backward(mu, lv, M, a.combine, w, dmu_bar, dlv_bar, dmu, dlv, gpoe ? dw : nullptr);
-      for (int m = 0; m < M; ++m) {
-        float* d = S + a.mod[m].s_dmulv + (long long)b * a.mod[m].ld_mulv;
-        d[z] = dmu[m]; d[Z + z] = dlv[m];
-        if (gpoe) dw_acc[m] += dw[m];
-      }
-    }
-    if (gpoe) {   // softmax backward + Adam on alpha_m (cVAE.py:1154)
-      float dw_tot[NMB_MAX_MOD];
-      for (int m = 0; m < M; ++m) dw_tot[m] = block_sum(dw_acc[m], c.red);
-      if (threadIdx.x == 0) {
-        float dot = 0.f;
-        for (int m = 0; m < M; ++m) dot += w[m] * dw_tot[m];
-        for (int m = 0; m < M; ++m) ad.apply(a.alpha_off + m, w[m] * (dw_tot[m] - dot));
-      }
-    }
-    __syncthreads();
-  }
-
-  for (int m = 0; m < M; ++m) {
-    const ModDesc& q = a.mod[m];
-    const float* dmulv = S + q.s_dmulv;
-    int cur = 0;
-    {
-      const LinDesc& w = q.head;
-      const float* act = S + q.s_h[L - 1]; const int ld_act = q.ld_h[L - 1];
-      EpiDgrad eg{gbuf[cur], a.ld_g, act, ld_act, a.non_linear};
-      mm<TC>(c, rows, w.in, w.out, Opnd{dmulv, q.ld_mulv, 1}, Opnd{P + w.off, w.ld, 0}, eg);
-      EpiWgradAdam ew{ad, w.off, w.ld};
-      mm<TC>(c, w.out, w.in + 1, rows, Opnd{dmulv, q.ld_mulv, 0}, Opnd{act, ld_act, 0}, ew);
-    }
-    for (int l = L - 1; l >= 0; --l) {
-      const LinDesc& w = q.enc[l];
-      const float* dy = gbuf[cur];
-      const float* in_act = l == 0 ? c.xin[m] + (long long)c.row0 * q.ldx : S + q.s_h[l - 1];
-      const int ld_in = l == 0 ? q.ldx : q.ld_h[l - 1];
-      if (l > 0) {
-        EpiDgrad eg{gbuf[cur ^ 1], a.ld_g, in_act, ld_in, a.non_linear};
-        mm<TC>(c, rows, w.in, w.out, Opnd{dy, a.ld_g, 1}, Opnd{P + w.off, w.ld, 0}, eg);
-      }
-      EpiWgradAdam ew{ad, w.off, w.ld};
-      mm<TC>(c, w.out, w.in + 1, rows, Opnd{dy, a.ld_g, 0}, Opnd{in_act, ld_in, 0}, ew);
-      cur ^= 1;
-    }
-  }
+  for (int m = 0; m < M; ++m) decoder_backward<TC>(c, ad, m, 1.f, m > 0, a.head_kind ? 1 : 0);
+  latent_backward(c, ad, (float)M);
+  for (int m = 0; m < M; ++m) encoder_backward<TC>(c, ad, m);
 }
 
 // Members trained through shuffling loaders: copy the minibatch rows each modality's permutation selects into the
@@ -679,8 +952,9 @@ __device__ __forceinline__ void train_body(const TrainLaunch& t, float* smem_f, 
       c.bc2_sqrt = (float)sqrt(1.0 - pow((double)mb.beta2, tt));
       const float* eps = t.eps_override
           ? t.eps_override + ((long long)mi * t.stride_steps + i) * mb.batch * a.Z : nullptr;
-      float* lo = t.loss_out ? t.loss_out + ((long long)mi * t.stride_steps + i) * ((t.flags & NMB_TRAIN_LOSS4) ? 4 : 3) : nullptr;
-      train_step<TC>(c, eps, lo);
+      float* lo = t.loss_out ? t.loss_out + ((long long)mi * t.stride_steps + i) * ((t.flags & NMB_TRAIN_LOSS8) ? 8 : (t.flags & NMB_TRAIN_LOSS4) ? 4 : 3) : nullptr;
+      if (a.head_kind == NMB_HEAD_ENDTOEND) train_step_e2e<TC>(c, eps, lo);
+      else train_step<TC>(c, eps, lo);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -760,6 +1034,15 @@ __device__ __forceinline__ void recon_body(const ReconLaunch& t, float* smem_f, 
     const int eps_mode = t.mode == NMB_RECON_GIVEN_Z ? 3 : (t.mode == NMB_RECON_MEAN ? 2 : (eps ? 1 : 0));
     // Philox test stream: counter "step" = row tile index so that tiles draw disjoint numbers
     latent_forward(c, xc, eps_mode, eps, 1u, (unsigned long long)(item.row0 / kMaxBatch));
+    if (head_out && a.head_kind == NMB_HEAD_ENDTOEND) {
+      // predict(): logits = classifier(z) in eval mode (running statistics, no dropout); the reference calls it on the
+      // fused mean (mode MEAN, cVAE.py:2198-2203).  Decoders run only if reconstructions were asked for.
+      e2e_copy_z(c);
+      e2e_classifier_forward<TC>(c, false);
+      for (int e2 = threadIdx.x; e2 < item.rows * 2; e2 += kThreads)
+        head_out[(long long)(item.row0 + (e2 >> 1)) * 2 + (e2 & 1)] = c.scratch[a.s_pred + 4 * (e2 >> 1) + (e2 & 1)];
+      head_out = nullptr;
+    }
     if (t.mode != NMB_RECON_GIVEN_Z && t.mu && t.mu[item.member]) {
       float* mu = t.mu[item.member] + (long long)item.row0 * a.Z;
       for (int e = threadIdx.x; e < item.rows * a.Z; e += kThreads) mu[e] = c.scratch[a.s_mub + e];
@@ -768,10 +1051,11 @@ __device__ __forceinline__ void recon_body(const ReconLaunch& t, float* smem_f, 
       float* lv = t.logvar[item.member] + (long long)item.row0 * a.Z;
       for (int e = threadIdx.x; e < item.rows * a.Z; e += kThreads) lv[e] = c.scratch[a.s_lvb + e];
     }
-    for (int m = 0; m < a.M; ++m) {
+    for (int m = 0; m < a.MD; ++m) {
       const ModDesc& q = a.mod[m];
-      Opnd A = decoder_hidden<TC>(c, m);
       float* out = t.xhat[(long long)item.member * NMB_MAX_MOD + m];
+      if (!out && !head_out) continue;
+      Opnd A = decoder_hidden<TC>(c, m);
       if (head_out) {      // the head reads the reconstructions from scratch
         EpiStore e{c.scratch + q.s_xr, q.ld_xh};
         mm<TC>(c, item.rows, q.D, q.outl.in + 1, A, Opnd{mb.params + q.outl.off, q.outl.ld, 1}, e);

@@ -25,6 +25,16 @@ _SLOT_NAMES = {
     _lib.SLOT_DEC_MEAN: "decoder_list.{m}.decoder_mean_layer",
     _lib.SLOT_HEAD: "regressor.{l2}",        # nn.Sequential(Linear, ReLU, Linear, ReLU, Linear): linears at 0, 2, 4
 }
+# cVAE_multimodal_endtoend v2 (cVAE.py:2042-2052, 2004-2018): two decoder sets, classifier Linear/BatchNorm/ReLU/Dropout blocks
+_SLOT_NAMES_E2E = dict(_SLOT_NAMES)
+_SLOT_NAMES_E2E.update({
+    _lib.SLOT_DEC: "decoder_list_health.{m}.decoder_layers.{l}",
+    _lib.SLOT_DEC_MEAN: "decoder_list_health.{m}.decoder_mean_layer",
+    _lib.SLOT_DEC2: "decoder_list_disease.{m}.decoder_layers.{l}",
+    _lib.SLOT_DEC2_MEAN: "decoder_list_disease.{m}.decoder_mean_layer",
+    _lib.SLOT_HEAD: "classifier.classifier.{l4}",
+})
+_BN_FIELDS = ("weight", "bias", "running_mean", "running_var", "num_batches_tracked")
 
 
 def _stream_ptr(device) -> int:
@@ -73,6 +83,8 @@ class MemberSpec:
     head: Optional[str] = None
     head_hidden: Sequence[int] = (128, 64)
     head_weight: float = 1.0               # lambda_reg
+    head_params: Optional[dict] = None     # "endtoend": margin, w_contrastive, w_kl, w_rec, dropout (cVAE.py:2131, 2031)
+    drop_keep: Optional[torch.Tensor] = None   # "endtoend": injected dropout keep flags [steps, batch, sum(head_hidden)]
     y: Optional[torch.Tensor] = None       # head target per training row (float32 CUDA [N])
     row_order: Optional[torch.Tensor] = None   # int32 CUDA [epochs, n_mod, N]: per-epoch, per-modality loader permutations
     tag: object = None                     # caller bookkeeping, e.g. (fold, modality, seed)
@@ -98,10 +110,12 @@ class EnsembleTrainer:
         total = 0
         for s in self.specs:
             key = (tuple(s.input_dims), tuple(s.hidden), s.latent, s.c_dim, s.combine.lower(), s.loss_kind,
-                   bool(s.non_linear), s.head, tuple(s.head_hidden) if s.head else (), float(s.head_weight) if s.head else 0.0)
+                   bool(s.non_linear), s.head, tuple(s.head_hidden) if s.head else (), float(s.head_weight) if s.head else 0.0,
+                   tuple(sorted((s.head_params or {}).items())))
             if key not in cache:
                 arch = _lib.make_arch(s.input_dims, s.hidden, s.latent, s.c_dim, s.combine, s.loss_kind, s.non_linear,
-                                      head=s.head, head_hidden=s.head_hidden, head_weight=s.head_weight)
+                                      head=s.head, head_hidden=s.head_hidden, head_weight=s.head_weight,
+                                      head_params=s.head_params)
                 cache[key] = (arch, _lib.arch_slots(arch), _lib.arch_param_count(arch))
             arch, slots, npar = cache[key]
             s._arch = arch
@@ -150,6 +164,13 @@ class EnsembleTrainer:
                     raise ValueError("one target per training row")
                 self._keep.append(y)
                 m.y = y.data_ptr()
+            if s.drop_keep is not None:
+                dk = s.drop_keep.to(device=dev, dtype=torch.float32).contiguous()
+                if dk.dim() != 3 or dk.shape[1] != int(s.batch) or dk.shape[2] != sum(int(h) for h in s.head_hidden):
+                    raise ValueError("drop_keep must be [steps, batch, sum(head_hidden)]")
+                self._keep.append(dk)
+                m.drop_keep = dk.data_ptr()
+                m.n_drop_steps = int(dk.shape[0])
             if s.row_order is not None:
                 ro = s.row_order.to(device=dev, dtype=torch.int32).contiguous()
                 if ro.dim() != 3 or ro.shape[1] != len(s.input_dims) or ro.shape[2] != n_rows:
@@ -190,14 +211,21 @@ class EnsembleTrainer:
         """Reference-named *views* into member i's slice of a packed buffer."""
         base = self.offsets[i]
         out = {}
+        e2e = self.specs[i].head == "endtoend"
+        names = _SLOT_NAMES_E2E if e2e else _SLOT_NAMES
         for s in self.slots[i]:
             seg = flat[base + s.offset: base + s.offset + s.rows * s.ld]
             if s.kind == _lib.SLOT_ALPHA:
                 out[f"alpha_m_list.{s.modality}"] = flat[base + s.offset: base + s.offset + 1]
-            elif s.kind == _lib.SLOT_LOGVAR_OUT:
-                out[f"decoder_list.{s.modality}.logvar_out"] = flat[base + s.offset: base + s.offset + s.cols].view(1, s.cols)
+            elif s.kind in (_lib.SLOT_LOGVAR_OUT, _lib.SLOT_LOGVAR_OUT2):
+                pre = "decoder_list" if not e2e else ("decoder_list_health" if s.kind == _lib.SLOT_LOGVAR_OUT else "decoder_list_disease")
+                out[f"{pre}.{s.modality}.logvar_out"] = flat[base + s.offset: base + s.offset + s.cols].view(1, s.cols)
+            elif s.kind == _lib.SLOT_HEAD_BN:
+                for r, f in enumerate(_BN_FIELDS):       # BatchNorm1d after head layer l: 5 vectors at stride ld
+                    o = base + s.offset + r * s.ld
+                    out[f"classifier.classifier.{4 * s.layer + 1}.{f}"] = flat[o: o + (s.cols if r < 4 else 1)].view(() if r == 4 else (s.cols,))
             else:
-                name = _SLOT_NAMES[s.kind].format(m=s.modality, l=s.layer, l2=2 * s.layer)
+                name = names[s.kind].format(m=s.modality, l=s.layer, l2=2 * s.layer, l4=4 * s.layer)
                 mat = seg.view(s.rows, s.ld)
                 out[name + ".weight"] = mat[:, : s.cols]
                 out[name + ".bias"] = mat[:, s.cols]
@@ -312,13 +340,25 @@ class EnsembleTrainer:
             _lib.check(self.lib.nmb_ensemble_steps_done(self.handle, out, _stream_ptr(self.device)))
         return np.array(out[:], dtype=np.int64)
 
+    def peek_head(self, i: int):
+        """Head output of the last step of member i: fi_pred [rows] (regression) or train-mode logits [rows, 2] (end-to-end)."""
+        b = int(self._members[i].batch)
+        out = torch.zeros((b, 4), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.nmb_ensemble_peek_head(self.handle, i, out.data_ptr(), _stream_ptr(self.device)),
+                       "nmb_ensemble_peek_head")
+        spe, done = self.steps_per_epoch[i], int(self.steps_done()[i])
+        rows = min(b, int(self._members[i].n_rows) - ((done - 1) % spe) * b)
+        return out[:rows, :2] if self.specs[i].head == "endtoend" else out[:rows, 0]
+
     def peek(self, i: int):
         """(mu, logvar, [x_recon...]) of the last step of member i (needs TRAIN_KEEP_ACTS for x_recon)."""
         s = self.specs[i]
         b, z = int(self._members[i].batch), int(s.latent)
         mu = torch.zeros((b, z), dtype=torch.float32, device=self.device)
         lv = torch.zeros_like(mu)
-        xr = [torch.zeros((b, int(d)), dtype=torch.float32, device=self.device) for d in s.input_dims]
+        xr = [torch.zeros((b, int(d)), dtype=torch.float32, device=self.device)
+              for d in list(s.input_dims) * (2 if s.head == "endtoend" else 1)]       # end-to-end: health sets, then disease sets
         rows = C.c_int32(0)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.nmb_ensemble_peek(self.handle, i, mu.data_ptr(), lv.data_ptr(),
@@ -401,15 +441,17 @@ def head_predict(trainer: "EnsembleTrainer", xc, mode: str = "sample", eps=None,
     for i, s in enumerate(self.specs):
         n_i = int(xc[i][0].shape[0])
         rows.append(n_i)
-        outs.append(torch.empty(n_i, dtype=torch.float32, device=self.device) if s.head else None)
+        e2e = s.head == "endtoend"
+        outs.append(torch.empty((n_i, 2) if e2e else (n_i,), dtype=torch.float32, device=self.device) if s.head else None)
         row = []
+        nm = len(s.input_dims)
         for k in range(_lib.NMB_MAX_MOD):
-            if k < len(s.input_dims):
-                tbl.append(xc[i][k].data_ptr())
-                o = torch.empty((n_i, int(s.input_dims[k])), dtype=torch.float32, device=self.device) if want_xhat else None
+            tbl.append(xc[i][k].data_ptr() if k < nm else None)
+            if k < nm * (2 if e2e else 1):            # end-to-end: health decoders, then disease decoders
+                o = torch.empty((n_i, int(s.input_dims[k % nm])), dtype=torch.float32, device=self.device) if want_xhat else None
                 xh_tbl.append(o.data_ptr() if want_xhat else None); row.append(o)
             else:
-                tbl.append(None); xh_tbl.append(None)
+                xh_tbl.append(None)
         xhs.append(row)
         if want_latent:
             mus.append(torch.empty((n_i, int(s.latent)), dtype=torch.float32, device=self.device))

@@ -321,3 +321,97 @@ def regression_train_loop(model, xs, cs, fi, order, combine, batch_size, eps_ste
             log.append((float(out["total"]), float(out["kl"]), float(out["ll"]), float(out["regression"])))
             step += 1
     return np.asarray(log, dtype=np.float64)
+
+
+class OracleCVAEEndToEnd(nn.Module):
+    """``cVAE_multimodal_endtoend`` v2 (cVAE.py:2021-2207) + ``Classifier`` (:2004-2018): shared encoders, plain PoE
+    fusion, a health and a disease decoder set, a classifier on z; loss = w_rec (rec_h + rec_d) + w_kl kl + CE +
+    w_con * hinge(margin +- (dev_h - dev_d)).  RNG order of the constructor: encoders, health decoders, disease decoders,
+    classifier (:2042-2052)."""
+
+    def __init__(self, input_dim_list, hidden_dim, latent_dim, c_dim, learning_rate=1e-4, modalities=3, non_linear=False,
+                 classifier_layers=(128, 64), dropout_rate=0.5):
+        super().__init__()
+        hd = list(hidden_dim) + [latent_dim]
+        self.modalities, self.dropout_rate = modalities, dropout_rate
+        self.encoder_list = nn.ModuleList(
+            [OracleEncoder(input_dim_list[i], hd, c_dim, non_linear) for i in range(modalities)])
+        self.decoder_list_health = nn.ModuleList(
+            [OracleDecoder(input_dim_list[i], hd, c_dim, non_linear) for i in range(modalities)])
+        self.decoder_list_disease = nn.ModuleList(
+            [OracleDecoder(input_dim_list[i], hd, c_dim, non_linear) for i in range(modalities)])
+        sizes = [latent_dim] + list(classifier_layers)
+        layers = []
+        for a, b in zip(sizes[:-1], sizes[1:]):
+            layers += [nn.Linear(a, b), nn.BatchNorm1d(b), nn.ReLU(), nn.Dropout(dropout_rate)]
+        layers.append(nn.Linear(sizes[-1], 2))
+        self.classifier = nn.Module()
+        self.classifier.classifier = nn.Sequential(*layers)
+        self.optimizer = torch.optim.Adam(self.parameters(), lr=learning_rate)
+
+    def classify(self, z, keep=None):
+        """keep: list of [rows, width] keep flags, one per Dropout (training mode); None = nn.Dropout's own draws."""
+        h, k = z, 0
+        for mod in self.classifier.classifier:
+            if isinstance(mod, nn.Dropout) and keep is not None and self.training and mod.p > 0:
+                h = h * keep[k] / (1.0 - mod.p)
+                k += 1
+            else:
+                h = mod(h)
+        return h
+
+    def latent(self, xs, cs):
+        enc = [self.encoder_list[i](xs[i], cs[i]) for i in range(self.modalities)]
+        mus, logvars = torch.stack([e[0] for e in enc]), torch.stack([e[1] for e in enc])
+        t = 1 / torch.exp(logvars)
+        return torch.sum(mus * t, dim=0) / torch.sum(t, dim=0), torch.log(1 / torch.sum(t, dim=0))      # :2081-2088
+
+    def step_losses(self, xs, cs, labels=None, eps=None, keep=None, margin=1.0, w_con=0.1, w_kl=0.1, w_rec=0.1):
+        mu, logvar = self.latent(xs, cs)
+        if eps is None:
+            eps = torch.randn_like(mu)
+        z = mu + eps * torch.exp(0.5 * logvar)
+        rh = [self.decoder_list_health[i](z, cs[i]) for i in range(self.modalities)]
+        rd = [self.decoder_list_disease[i](z, cs[i]) for i in range(self.modalities)]
+        out = {"mu": mu, "logvar": logvar, "logits": self.classify(z, keep),
+               "x_recons_health": [r[0] for r in rh], "x_recons_disease": [r[0] for r in rd]}
+        if labels is None:
+            return out
+        rec_h = sum(-gauss_ll(xs[i], rh[i][0], rh[i][1]) for i in range(self.modalities))
+        rec_d = sum(-gauss_ll(xs[i], rd[i][0], rd[i][1]) for i in range(self.modalities))
+        dev_h = torch.stack([((xs[i] - rh[i][0]) ** 2).mean(dim=1) for i in range(self.modalities)]).mean(dim=0)
+        dev_d = torch.stack([((xs[i] - rd[i][0]) ** 2).mean(dim=1) for i in range(self.modalities)]).mean(dim=0)
+        lab = labels.to(mu.dtype)
+        con = torch.mean((1 - lab) * torch.relu(margin + dev_h - dev_d) + lab * torch.relu(margin + dev_d - dev_h))
+        kl = -0.5 * torch.sum(1 + logvar - mu.pow(2) - logvar.exp(), dim=1).mean()
+        ce = torch.nn.functional.cross_entropy(out["logits"], labels)
+        out.update({"total": w_rec * (rec_h + rec_d) + w_kl * kl + ce + w_con * con, "kl": kl, "ce": ce, "rec_health": rec_h,
+                    "rec_disease": rec_d, "contrastive": con})
+        return out
+
+    def predict(self, xs, cs):
+        """:2198-2203: classifier(mu_combined), to be called in eval mode."""
+        with torch.no_grad():
+            return self.classify(self.latent(xs, cs)[0])
+
+
+def e2e_train_loop(model, xs, cs, labels, batch_size, epochs, eps_steps, keep_steps, widths, margin, w_con):
+    """Loop body of multimodal_kfold_cvae_nmpmcont.py:226-247 (shuffle=False, last batch partial; the cyclic learning rate
+    written to ``optimizer.lr`` never reaches Adam).  Returns per-step (total, kl, ce, rec_health, rec_disease, contrastive)."""
+    n = xs[0].shape[0]
+    log, step = [], 0
+    for _ in range(epochs):
+        for lo in range(0, n, batch_size):
+            xb = [x[lo:lo + batch_size] for x in xs]
+            cb = [cs[lo:lo + batch_size]] * model.modalities
+            rows = xb[0].shape[0]
+            keep, o = [], 0
+            for w in widths:
+                keep.append(torch.as_tensor(keep_steps[step][:rows, o:o + w])); o += w
+            out = model.step_losses(xb, cb, labels[lo:lo + batch_size], torch.as_tensor(eps_steps[step][:rows]), keep, margin, w_con)
+            model.optimizer.zero_grad()
+            out["total"].backward()
+            model.optimizer.step()
+            log.append([float(out[k].detach()) for k in ("total", "kl", "ce", "rec_health", "rec_disease", "contrastive")])
+            step += 1
+    return np.asarray(log, dtype=np.float64)

@@ -162,6 +162,10 @@ def _knife_scan(model, run):
             def _keep(_m, _i, o, pname=pname):      # must return None: a returned value would replace the output
                 pre.setdefault(pname, []).append(o.detach().clone())
             hooks.append(mod.register_forward_hook(_keep))
+        elif isinstance(mod, torch.nn.BatchNorm1d):         # the classifier's ReLU follows its BatchNorm
+            def _keep_bn(_m, _i, o, pname=pname):
+                pre.setdefault(pname, []).append(o.detach().clone())
+            hooks.append(mod.register_forward_hook(_keep_bn))
     with torch.no_grad():
         run()
     for h_ in hooks:
@@ -647,6 +651,132 @@ def ref_regression_case(ref, name, dims, hidden, z, n, b, combine, epochs, seed,
     print(name, "ok", losses[0], "->", losses[-1])
 
 
+@contextmanager
+def injected_dropout(keep_list):
+    """Make ``nn.Dropout`` (F.dropout) use our keep flags in order: out = x * keep / (1 - p) in training mode."""
+    import torch.nn.functional as F
+    real = F.dropout
+    it = iter(keep_list)
+
+    def fake(x, p=0.5, training=True, inplace=False):
+        if not training or p == 0.0:
+            return x
+        k = next(it)
+        assert tuple(k.shape) == tuple(x.shape), (k.shape, x.shape)
+        return x * k / (1.0 - p)
+
+    F.dropout = fake
+    try:
+        yield
+    finally:
+        F.dropout = real
+
+
+def _e2e_inputs(ref, dims, hidden, z, c_dim, n, b, layers, p, epochs, seed, n_age, n_test):
+    m = len(dims)
+    rng = np.random.RandomState(seed)
+    torch.manual_seed(seed)
+    model = ref.cVAE_multimodal_endtoend(input_dim_list=list(dims), hidden_dim=list(hidden), latent_dim=z, c_dim=c_dim,
+                                         modalities=m, non_linear=True, classifier_layers=list(layers), dropout_rate=p,
+                                         num_classes=2)
+    xs = [rng.randn(n, d).astype(np.float32) for d in dims]
+    c = onehot_cov(rng, n, c_dim, n_age)
+    labels = rng.randint(0, 2, n).astype(np.int64)
+    for x in xs:                                      # a class effect, so that the hinge and the classifier see signal
+        x[labels == 1, : max(1, x.shape[1] // 5)] += 0.8
+    steps = epochs * len(_loop_batches(n, b))
+    eps = rng.randn(steps, b, z).astype(np.float32)
+    keep = (rng.rand(steps, b, sum(layers)) >= p).astype(np.float32)
+    xt = [rng.randn(n_test, d).astype(np.float32) for d in dims]
+    ct = onehot_cov(rng, n_test, c_dim, n_age)
+    eps_t = rng.randn(n_test, z).astype(np.float32)
+    return model, xs, c, labels, eps, keep, xt, ct, eps_t
+
+
+def ref_e2e_case(ref, name, dims, hidden, z, c_dim, n, b, layers, p, epochs, seed, n_age, margin=1.0, w_con=1.0,
+                 n_test=70, tries=300):
+    """f3: the UNMODIFIED cVAE_multimodal_endtoend v2 (cVAE.py:2021-2207) through the loop body of
+    multimodal_kfold_cvae_nmpmcont.py:226-247 (loss_function(xs, fwd, labels, margin, weightcontrastive); weight_kl and
+    weight_rec stay at their 0.1 defaults; ``optimizer.lr = clr`` is a no-op so Adam runs at 1e-4), injected eps and
+    dropout keep flags; then ``predict`` in eval mode (:30-46) and an eval-mode forward."""
+    m = len(dims)
+    batches = _loop_batches(n, b)
+    widths = list(layers)
+
+    def fwd_loss(model, xs_t, c_t, lab_t, eps, keep, s):
+        r0, rows = batches[s % len(batches)]
+        xb = [x[r0:r0 + rows] for x in xs_t]
+        cb = [c_t[r0:r0 + rows] for _ in dims]
+        ks, o = [], 0
+        for w in widths:
+            ks.append(torch.from_numpy(keep[s][:rows, o:o + w])); o += w
+        with injected_eps([torch.from_numpy(eps[s][:rows])]), injected_dropout(ks):
+            fwd = model.forward(xb, cb)
+        return fwd, model.loss_function(xb, fwd, lab_t[r0:r0 + rows], margin, w_con)
+
+    best = None
+    for t in range(tries):
+        sd = seed + 1000 * t
+        model, xs, c, labels, eps, keep, _, _, _ = _e2e_inputs(ref, dims, hidden, z, c_dim, n, b, layers, p, epochs, sd, n_age, n_test)
+        model.train()
+        xs_t, c_t, lab_t = [torch.from_numpy(x) for x in xs], torch.from_numpy(c), torch.from_numpy(labels)
+        state = {k: v.clone() for k, v in model.state_dict().items()}
+        kn = _knife_scan(model, lambda: fwd_loss(model, xs_t, c_t, lab_t, eps, keep, 0))
+        model.load_state_dict(state)                  # the scan's forward moved the BatchNorm running statistics
+        score = sum(len(v) for v in kn.values())
+        if best is None or score < best[0]:
+            best = (score, sd)
+        if score == 0:
+            break
+    seed = best[1]
+    print("  seed", seed, "knife edges:", best[0])
+    model, xs, c, labels, eps, keep, xt, ct, eps_t = _e2e_inputs(ref, dims, hidden, z, c_dim, n, b, layers, p, epochs, seed, n_age, n_test)
+    model.train()
+    xs_t, c_t, lab_t = [torch.from_numpy(x) for x in xs], torch.from_numpy(c), torch.from_numpy(labels)
+    out = {"dims": np.array(dims), "hidden": np.array(hidden), "z": z, "c_dim": c_dim, "seed": seed, "n": n, "batch": b,
+           "epochs": epochs, "layers": np.array(layers), "dropout": p, "margin": margin, "w_con": w_con, "c": c,
+           "labels": labels, "eps": eps, "keep": keep}
+    for k, v in sd_np(model).items():
+        out["init/" + k] = v
+    for i, x in enumerate(xs):
+        out[f"x{i}"] = x
+    losses = []
+    keys = ["total_loss", "kl_loss", "classification_loss", "recon_loss_health", "recon_loss_disease", "contrastive_loss"]
+    for s_ in range(epochs * len(batches)):
+        fwd, loss = fwd_loss(model, xs_t, c_t, lab_t, eps, keep, s_)
+        model.optimizer.zero_grad()
+        loss["total_loss"].backward()
+        if s_ == 0:
+            out["mu"] = fwd["mu"].detach().numpy().copy()
+            out["logvar"] = fwd["logvar"].detach().numpy().copy()
+            out["logits0"] = fwd["logits"].detach().numpy().copy()
+            for i in range(m):
+                out[f"xh_health{i}"] = fwd["x_recons_health"][i].loc.detach().numpy().copy()
+                out[f"xh_disease{i}"] = fwd["x_recons_disease"][i].loc.detach().numpy().copy()
+            for k, pr in model.named_parameters():
+                if pr.grad is not None:
+                    out["grad/" + k] = pr.grad.detach().numpy().copy()
+        model.optimizer.step()
+        losses.append([float(loss[k].detach()) for k in keys])
+    out["losses"] = np.array(losses, dtype=np.float64)      # columns: total, kl, ce, rec_health, rec_disease, contrastive
+    for k, v in sd_np(model).items():
+        out["final/" + k] = v
+    model.eval()
+    xt_t, ct_t = [torch.from_numpy(x) for x in xt], torch.from_numpy(ct)
+    with torch.no_grad():
+        out["logits_test"] = model.predict(xt_t, [ct_t] * m).numpy().copy()
+        with injected_eps([torch.from_numpy(eps_t)]):
+            fwd = model.forward(xt_t, [ct_t] * m)
+    out["ct"] = ct; out["eps_test"] = eps_t
+    out["logits_test_sampled"] = fwd["logits"].numpy().copy()
+    for i in range(m):
+        out[f"xt{i}"] = xt[i]
+        out[f"pred_health{i}"] = fwd["x_recons_health"][i].loc.numpy().copy()
+        out[f"pred_disease{i}"] = fwd["x_recons_disease"][i].loc.numpy().copy()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, "ok", losses[0], "->", losses[-1])
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     sys.path.insert(0, REF)
@@ -658,6 +788,10 @@ def main():
             sd = clean_seed(mm, [116, 116, 116, 348], [110, 110], 10, 29, 288, 256, 2, 46, 27, [comb])
             ref_loop_case(ref, "mm_M4_full_" + comb.lower(), [116, 116, 116, 348], [110, 110], 10, 29, 288, 256, comb, 2,
                           sd, 27, lean=lean)
+        return
+    if "--f3e" in sys.argv:
+        ref_e2e_case(ref, "e2e_M3_full", [116, 116, 116], [110, 110], 10, 29, 300, 256, [128, 64, 32], 0.5, 2, 21, 27)
+        ref_e2e_case(ref, "e2e_M2_small", [13, 6], [11, 9], 4, 7, 23, 10, [12, 8], 0.25, 3, 22, 5, margin=0.5, w_con=0.3, n_test=9)
         return
     if "--f3" in sys.argv:
         ref_regression_case(ref, "reg_M3_full_gpoe", [116, 116, 116], [110, 110], 10, 300, 128, "gpoe", 2, 7)
