@@ -144,7 +144,8 @@ class _FusedBase(nn.Module):
     combine rule; rows are passed per call."""
 
     _loss_kind = "gauss_ll"
-    _head_kind = None            # "regression" for cVAE_multimodal_regression
+    _head_kind = None            # "regression" for cVAE_multimodal_regression, "endtoend" for e2e.cVAE_multimodal_endtoend
+    _opt_name = "optimizer1"     # attribute holding the fused Adam (the end-to-end class calls it `optimizer`)
     _ENGINE_KEYS = ("_engines", "_pending", "_last", "_views_cache", "_step_tensor", "_pending_fwd")
 
     def _head_kwargs(self):
@@ -194,8 +195,15 @@ class _FusedBase(nn.Module):
             if k is None or k not in views:           # e.g. the head's parameters in an engine built without the head
                 continue
             dst.append(views[k]); src.append(p.detach().reshape(views[k].shape))
+        for name, b in self._engine_buffers():              # e.g. BatchNorm running statistics (not parameters)
+            if name in views:
+                dst.append(views[name]); src.append(b.detach().to(torch.float32).reshape(views[name].shape))
         with torch.no_grad():
             torch._foreach_copy_(dst, src)
+
+    def _engine_buffers(self):
+        """(name in packed layout, buffer) pairs the engine reads AND updates (none for the normative models)."""
+        return ()
 
     def _train_engine(self, xs, cs, combine):
         dev = self._require_cuda()
@@ -311,7 +319,7 @@ class _FusedBase(nn.Module):
         if vc is None:
             vc = (eng._views(0, m), eng._views(0, v))
             object.__setattr__(self, "_views_cache", vc)
-        st = self.optimizer1.state
+        st = getattr(self, self._opt_name).state
         step_t = self.__dict__.get("_step_tensor")
         if step_t is None or len(st) != len(named):          # built once; afterwards only the shared step counter moves
             step_t = torch.tensor(float(t))

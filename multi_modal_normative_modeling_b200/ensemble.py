@@ -37,6 +37,11 @@ _SLOT_NAMES_E2E.update({
 _BN_FIELDS = ("weight", "bias", "running_mean", "running_var", "num_batches_tracked")
 
 
+def _loss_width(flags) -> int:
+    """Values per recorded step: 3 (total, kl, ll), 4 with TRAIN_LOSS4 (+ head loss), 8 with TRAIN_LOSS8 (end-to-end)."""
+    return 8 if (int(flags) & _lib.TRAIN_LOSS8) else 4 if (int(flags) & _lib.TRAIN_LOSS4) else 3
+
+
 def _stream_ptr(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
@@ -272,7 +277,7 @@ class EnsembleTrainer:
         (losses['regression']) last when flags has TRAIN_LOSS4."""
         losses = None
         if record_losses:
-            losses = torch.zeros((self.n, n_steps, 4 if (int(flags) & _lib.TRAIN_LOSS4) else 3), dtype=torch.float32,
+            losses = torch.zeros((self.n, n_steps, _loss_width(flags)), dtype=torch.float32,
                                  device=self.device)
         eps_ptr = None
         if eps is not None:
@@ -319,7 +324,7 @@ class EnsembleTrainer:
         first epochs * steps_per_epoch[i] rows; the rest is NaN)."""
         losses = None
         if record_losses:
-            losses = torch.full((self.n, epochs * max(self.steps_per_epoch), 4 if (int(flags) & _lib.TRAIN_LOSS4) else 3),
+            losses = torch.full((self.n, epochs * max(self.steps_per_epoch), _loss_width(flags)),
                                 float("nan"), dtype=torch.float32, device=self.device)
         if (flags & _lib.TRAIN_WRITE_GRADS) and self.grads is None:
             raise RuntimeError("TRAIN_WRITE_GRADS needs keep_grads=True")

@@ -40,6 +40,24 @@ def philox4x32_10(counter, key):
     return np.stack(c, axis=-1)
 
 
+def uniforms(seed: int, step: int, n_elems: int, stream: int = 2):
+    """u = ((w >> 9) + 0.5) * 2^-23 of element e = word (e & 3) of counter group e >> 2: the dropout stream (stream 2) of the
+    end-to-end classifier -- unit (row b, column j of the concatenated hidden layers) has e = b * sum(widths) + j and is
+    KEPT when u >= p."""
+    groups = (n_elems + 3) // 4
+    ctr = np.zeros((groups, 4), dtype=np.uint32)
+    ctr[:, 0] = np.arange(groups, dtype=np.uint32)
+    ctr[:, 1] = np.uint32(step & 0xFFFFFFFF)
+    ctr[:, 2] = np.uint32((step >> 32) & 0xFFFFFFFF)
+    ctr[:, 3] = np.uint32(stream)
+    key = np.zeros((groups, 2), dtype=np.uint32)
+    key[:, 0] = np.uint32(seed & 0xFFFFFFFF)
+    key[:, 1] = np.uint32((seed >> 32) & 0xFFFFFFFF)
+    w = philox4x32_10(ctr, key)
+    u = ((w >> np.uint32(9)).astype(np.float32) + np.float32(0.5)) * np.float32(2.0 ** -23)
+    return u.reshape(-1)[:n_elems]
+
+
 def normals(seed: int, step: int, n_elems: int, stream: int = 0):
     """The first n_elems eps values of minibatch `step` for Philox key `seed` (float32)."""
     groups = (n_elems + 3) // 4

@@ -107,7 +107,7 @@ def assert_losses_close(got, want, rel=1e-4):
     assert np.allclose(got[..., 1], want[..., 1], rtol=10 * rel), (got, want)
 
 
-def assert_update_close(name, got, final, init, steps, lr, exact_engine, g0=None, q99_tc=2e-3):
+def assert_update_close(name, got, final, init, steps, lr, exact_engine, g0=None, q99_tc=2e-3, mean_tc=1e-3):
     """Adam trajectory check on the UPDATE d = final - init (the parameter itself would pass trivially).
 
     Adam's normalised step lr * m_hat / sqrt(v_hat) is ~ lr * sign(.) in its first steps, so it is ill-conditioned
@@ -130,4 +130,4 @@ def assert_update_close(name, got, final, init, steps, lr, exact_engine, g0=None
     q99 = flat[min(flat.size - 1, int(np.ceil(0.99 * flat.size)))] if flat.size >= 200 else flat[max(0, flat.size - 3)]
     assert q99 < (2e-4 if exact_engine else q99_tc), (name, float(q99))
     if flat.size >= 200:
-        assert dev.mean() < 1e-3, (name, float(dev.mean()))
+        assert dev.mean() < (1e-3 if exact_engine else mean_tc), (name, float(dev.mean()))
