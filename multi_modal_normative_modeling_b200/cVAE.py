@@ -732,3 +732,35 @@ class cVAE_multimodal_regression(cVAE_multimodal):
         object.__setattr__(self, "_pending", (eng, eps))
         outs = _FusedStep.apply(self, 0, *[p for _, p in self._trainable_named()])
         return {"total": outs[0], "kl": outs[1], "ll": outs[2], "regression": outs[-1]}
+
+
+class mmJSD(cVAE_multimodal):
+    """The ``mmJSD`` baseline of the model zoo (cVAE.py:1354-1452; ``-Model mmJSD`` in the train script :141-148;
+    SURVEY 8 f4).  As written in the reference it is the multimodal cVAE with two fixed choices: ``forward_multimodal`` /
+    ``pred_recon`` IGNORE ``combine`` and always fuse with the class's own product of experts (:1400-1403), and the
+    Jensen-Shannon term is evaluated on M identical copies of the fused posterior (:1426) -- KL(p || p) -- so it is exactly 0
+    with zero gradient (recorded: tests/golden/mmjsd_M3.npz ``jsd0``).  Same parameters, same torch-RNG order (alphas,
+    encoders, decoders; the alphas never receive a gradient), same fused kernels."""
+
+    def forward_multimodal(self, xes, cs, combine=None):
+        return super().forward_multimodal(xes, cs, "poe")
+
+    def pred_recon(self, xes, c, DEVICE=None, combine=None):
+        return super().pred_recon(xes, c, DEVICE, "poe")
+
+    def combine_latent(self, mus, logvars):
+        """(mu, VARIANCE) of the product of the experts N(mus[m], exp(logvars[m])) (:1400-1403)."""
+        return fuse_latent(mus, torch.exp(logvars), "poe")
+
+    def reparameterize(self, mu, logvar):
+        return self.reparameterise(mu, logvar)
+
+    def multimodal_jsd(self, mus, logvars):
+        """Mean pairwise KL(N_i || N_j) over the M (M - 1) / 2 pairs (:1405-1412)."""
+        from torch.distributions import kl_divergence
+        jsd, n = 0, len(mus)
+        for i in range(n):
+            for j in range(i + 1, n):
+                jsd = jsd + kl_divergence(Normal(mus[i], torch.exp(0.5 * logvars[i])),
+                                          Normal(mus[j], torch.exp(0.5 * logvars[j]))).mean()
+        return jsd / (n * (n - 1) / 2)

@@ -777,6 +777,52 @@ def ref_e2e_case(ref, name, dims, hidden, z, c_dim, n, b, layers, p, epochs, see
     print(name, "ok", losses[0], "->", losses[-1])
 
 
+def ref_mmjsd_case(ref, name, dims, hidden, z, c_dim, n, b, epochs, seed, n_age):
+    """f4: the UNMODIFIED baseline ``mmJSD`` (cVAE.py:1354-1452) through the training loop body (train script :177-199,
+    model chosen with -Model mmJSD): it always fuses with its own PoE, whatever `combine` says, and its Jensen-Shannon term
+    is evaluated on M identical copies of the fused posterior, i.e. it is exactly zero with zero gradient."""
+    sd0 = clean_seed(ref.mmJSD, dims, hidden, z, c_dim, n, b, epochs, seed, n_age, ["moe"])
+    model, next_draw, rng, xs, c, eps = _build_case(ref.mmJSD, dims, hidden, z, c_dim, n, b, epochs, sd0, n_age)
+    out = {"dims": np.array(dims), "hidden": np.array(hidden), "z": z, "c_dim": c_dim, "seed": sd0, "next_draw": next_draw,
+           "n": n, "batch": b, "epochs": epochs, "c": c, "eps": eps, "combine": "moe"}
+    for k, v in sd_np(model).items():
+        out["init/" + k] = v
+    for i, x in enumerate(xs):
+        out[f"x{i}"] = x
+    xt, ct = [torch.from_numpy(x) for x in xs], torch.from_numpy(c).long()
+    losses, s_ = [], 0
+    for _ in range(epochs):
+        for r0, rows in _loop_batches(n, b):
+            xb, cb = [x[r0:r0 + rows] for x in xt], [ct[r0:r0 + rows] for _ in dims]
+            with injected_eps([torch.from_numpy(eps[s_][:rows])]):
+                fwd = model.forward_multimodal(xb, cb, "moe")          # the argument is ignored by mmJSD
+            loss = model.loss_function_multimodal(xb, fwd)
+            model.optimizer1.zero_grad()
+            loss["total"].backward()
+            if s_ == 0:
+                out["mu"] = fwd["mu_multimodal"].detach().numpy().copy()
+                out["jsd0"] = float(model.multimodal_jsd([fwd["mu_multimodal"]] * len(dims), [fwd["logvar_multimodal"]] * len(dims)))
+                for k, p_ in model.named_parameters():
+                    if p_.grad is not None:
+                        out["grad/" + k] = p_.grad.detach().numpy().copy()
+            model.optimizer1.step()
+            losses.append([float(loss["total"]), float(loss["kl"]), float(loss["ll"])])
+            s_ += 1
+    out["losses"] = np.array(losses, dtype=np.float64)
+    for k, v in sd_np(model).items():
+        out["final/" + k] = v
+    eps_t = rng.randn(n, z).astype(np.float32)
+    dfs = [pd.DataFrame(x.astype(np.float64)) for x in xs]
+    real = torch.randn_like
+    with injected_eps([torch.from_numpy(eps_t)]):
+        preds = model.pred_recon(dfs, c, torch.device("cpu"), "moe")
+    out["eps_test"] = eps_t
+    for i in range(len(dims)):
+        out[f"pred{i}"] = preds[i]
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, "ok", losses[0], "->", losses[-1], "jsd", out["jsd0"])
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     sys.path.insert(0, REF)
@@ -788,6 +834,9 @@ def main():
             sd = clean_seed(mm, [116, 116, 116, 348], [110, 110], 10, 29, 288, 256, 2, 46, 27, [comb])
             ref_loop_case(ref, "mm_M4_full_" + comb.lower(), [116, 116, 116, 348], [110, 110], 10, 29, 288, 256, comb, 2,
                           sd, 27, lean=lean)
+        return
+    if "--f4" in sys.argv:
+        ref_mmjsd_case(ref, "mmjsd_M3", [116, 58, 30], [110, 110], 10, 29, 150, 128, 2, 31, 27)
         return
     if "--f3e" in sys.argv:
         ref_e2e_case(ref, "e2e_M3_full", [116, 116, 116], [110, 110], 10, 29, 300, 256, [128, 64, 32], 0.5, 2, 21, 27)

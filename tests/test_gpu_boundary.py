@@ -187,3 +187,58 @@ def test_nmmlp_program_end_to_end(tmp_path):
     # the training rows were healthy controls only: the schedule length = epochs * ceil(n_hc_rows / 256)
     tr_ids = pd.read_csv(tmp_path / "outputs" / "kfold_analysis" / "train_ids_000.csv")
     assert len(tr_ids) > 0
+
+
+@pytest.mark.gpu
+def test_mmjsd_baseline_dropin_vs_reference(golden_dir):
+    """f4: drop-in ``mmJSD`` through the reference loop (fwd -> loss -> zero_grad -> backward -> optimizer1.step()) with
+    `combine="moe"` passed in -- and ignored, like the reference -- against the recording of the unmodified class."""
+    import cVAE as shim
+    from helpers import assert_update_close, load, relerr, sub
+    g = load(golden_dir, "mmjsd_M3")
+    dims = [int(d) for d in g["dims"]]
+    torch.manual_seed(int(g["seed"]))
+    model = shim.mmJSD(dims, [int(h) for h in g["hidden"]], int(g["z"]), int(g["c_dim"]), learning_rate=1e-4, modalities=len(dims),
+                       non_linear=True)
+    init = sub(g, "init/")
+    for k, v in model.state_dict().items():
+        assert np.array_equal(v.numpy(), init[k]), k
+    model.to("cuda")
+    xs = [torch.from_numpy(g[f"x{i}"]).cuda() for i in range(len(dims))]
+    c = torch.from_numpy(g["c"]).long().cuda()
+    n, b = int(g["n"]), int(g["batch"])
+    real = torch.randn
+    log, s = [], 0
+    try:
+        for _ in range(int(g["epochs"])):
+            for r0 in range(0, n, b):
+                rows = min(b, n - r0)
+                torch.randn = lambda *a, **k: torch.from_numpy(g["eps"][s][:rows]).to(k.get("device", "cpu"))
+                fwd = model.forward_multimodal([x[r0:r0 + rows] for x in xs], [c[r0:r0 + rows]] * len(dims), "moe")
+                torch.randn = real
+                loss = model.loss_function_multimodal([x[r0:r0 + rows] for x in xs], fwd)
+                if s == 0:
+                    assert relerr(fwd["mu_multimodal"].cpu().numpy(), g["mu"]) < 1e-4
+                    assert float(model.multimodal_jsd([fwd["mu_multimodal"]] * 3, [fwd["logvar_multimodal"]] * 3)) == 0.0
+                model.optimizer1.zero_grad()
+                loss["total"].backward()
+                model.optimizer1.step()
+                log.append([float(loss[k].detach()) for k in ("total", "kl", "ll")])
+                s += 1
+    finally:
+        torch.randn = real
+    got, want = np.asarray(log), g["losses"]
+    assert np.allclose(got[:, 0], want[:, 0], rtol=1e-4) and np.allclose(got[:, 2], want[:, 2], rtol=1e-4)
+    assert np.allclose(got[:, 1], want[:, 1], rtol=1e-3)
+    sd, g0 = model.state_dict(), sub(g, "grad/")
+    for k, v in sub(g, "final/").items():
+        assert_update_close(k, sd[k].cpu().numpy(), v, init[k], s, 1e-4, False, g0.get(k))
+    import pandas as pd
+    torch.randn = lambda *a, **k: torch.from_numpy(g["eps_test"])
+    try:
+        preds = model.pred_recon([pd.DataFrame(g[f"x{i}"].astype(np.float64)) for i in range(len(dims))], g["c"], None, "moe")
+    finally:
+        torch.randn = real
+    for i in range(len(dims)):
+        assert relerr(preds[i], g[f"pred{i}"]) < 2e-4, i
+    model.close()

@@ -148,3 +148,27 @@ def test_product_classes_seed_exact_and_load_reference_pickles(golden_dir):
     s = torch.load(os.path.join(golden_dir, "ref_cVAE.pkl"), weights_only=False)
     assert type(s) is cVAE and s._dims == [13] and s._hidden == [12, 8]
     assert hasattr(s, "optimizer2") and hasattr(s, "optimizer3")
+
+
+def test_mmjsd_baseline_is_the_poe_cvae(golden_dir):
+    """f4: the reference's ``mmJSD`` baseline (cVAE.py:1354-1452) recorded through the training loop == the oracle's
+    multimodal cVAE with PoE fusion: the `combine` argument is ignored and the Jensen-Shannon term is identically zero."""
+    g = load(golden_dir, "mmjsd_M3")
+    assert float(g["jsd0"]) == 0.0
+    dims = [int(d) for d in g["dims"]]
+    torch.manual_seed(int(g["seed"]))
+    model = cvae_torch.OracleCVAEMultimodal(dims, [int(h) for h in g["hidden"]], int(g["z"]), int(g["c_dim"]), 1e-4, len(dims),
+                                            non_linear=True)
+    assert np.array_equal(torch.randn(4).numpy(), g["next_draw"])
+    init = sub(g, "init/")
+    for k, v in model.state_dict().items():
+        assert np.array_equal(v.numpy(), init[k]), k
+    xs = [torch.from_numpy(g[f"x{i}"]) for i in range(len(dims))]
+    cs = [torch.from_numpy(g["c"]).long() for _ in dims]
+    eps = torch.from_numpy(g["eps"])
+    log = cvae_torch.reference_train_loop(model, xs, cs, "poe", int(g["epochs"]), int(g["batch"]), eps_fn=lambda s, rows: eps[s][:rows])
+    np.testing.assert_allclose(log, g["losses"], rtol=1e-5)
+    g0 = sub(g, "grad/")
+    assert not any(k.startswith("alpha_m_list") for k in g0)           # the alphas never receive a gradient
+    for k, v in sub(g, "final/").items():
+        assert_update_close(k, model.state_dict()[k].numpy(), v, init[k], len(log), 1e-4, False, g0.get(k))
