@@ -145,6 +145,8 @@ class _FusedBase(nn.Module):
 
     _loss_kind = "gauss_ll"
     _head_kind = None            # "regression" for cVAE_multimodal_regression, "endtoend" for e2e.cVAE_multimodal_endtoend
+    _engine_flags = 0            # OR-ed into the per-step launch: _lib.TRAIN_FP32 selects the FP32 FFMA engine (bit-stable
+                                 # trajectories; the default BF16x3 tensor-core engines meet the 1e-4 per-step bar)
     _opt_name = "optimizer1"     # attribute holding the fused Adam (the end-to-end class calls it `optimizer`)
     _ENGINE_KEYS = ("_engines", "_pending", "_last", "_views_cache", "_step_tensor", "_pending_fwd")
 
@@ -241,7 +243,8 @@ class _FusedBase(nn.Module):
         eng.grads.zero_()
         loss4 = _lib.TRAIN_LOSS4 if self._head_kind else 0
         losses = eng.train_steps(1, eps=eps[None, None], record_losses=True,
-                                 flags=_lib.TRAIN_NO_ADAM | _lib.TRAIN_WRITE_GRADS | _lib.TRAIN_KEEP_ACTS | loss4)
+                                 flags=_lib.TRAIN_NO_ADAM | _lib.TRAIN_WRITE_GRADS | _lib.TRAIN_KEEP_ACTS | loss4
+                                 | int(self._engine_flags))
         mu, lv, xr = eng.peek(0)
         gviews = eng.__dict__.setdefault("_gviews", eng._views(0, eng.grads))
         grads = [gviews[name].view(p.shape) for name, p in self._trainable_named()]       # views, nothing is copied
