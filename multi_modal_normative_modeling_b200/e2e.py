@@ -5,8 +5,8 @@ Model: shared encoders -> PoE -> z -> a health and a disease decoder set + a cla
 Dropout blocks) on z; loss = w_rec (rec_health + rec_disease) + w_kl kl + cross-entropy + w_con * contrastive hinge.
 The whole step -- both decoder sets, batch-statistics BatchNorm, dropout, the five loss terms, backward, Adam and the
 running-statistics update -- is ONE launch of libnmb's generic engines (``NMB_HEAD_ENDTOEND``); the program trains every
-fold in one launch.  It runs on the FP32 FFMA engine: the contrastive gradients of the two decoder sets cancel in dz, and
-the BF16x3 engine's 2^-16 product error then costs the encoder gradients two digits (tests/test_gpu_e2e_head.py).
+fold in one launch.  It runs on the FP32 FFMA engine (bit-stable trajectories: ReLU / BatchNorm / hinge decisions do not
+depend on BF16x3 rounding; the tensor-core engine meets the same 1e-4 per-step bar, tests/test_gpu_e2e_head.py).
 
 (This class is the one the reference's ``cVAE`` MODULE exports under this name.  The different class of the same name
 that multimodal_kfold_cvae_nmmlp.py defines locally lives in ``.cVAE``.)

@@ -236,9 +236,12 @@ def test_mmjsd_baseline_dropin_vs_reference(golden_dir, engine):
     assert np.allclose(got[:, 1], want[:, 1], rtol=1e-3)
     sd, g0 = model.state_dict(), sub(g, "grad/")
     for k, v in sub(g, "final/").items():
-        # FP32 engine: the trajectory of the reference to 2e-4 of the largest update on 99 % of the elements (measured 1e-5).
-        # Default engine (BF16x3, here the generic one: batch 128): the first-layer weights of the widest encoder lose
-        # accuracy in the 22-row ragged step (measured q99 3e-2 there, 4e-5 on every other tensor; tools/diag_traj.py)
+        # FP32 engine: the reference's trajectory to 2e-4 of the largest update on 99 % of the elements (measured 1e-5).
+        # Default engine (BF16x3; batch 128 -> the generic one): after the first Adam step one hidden unit of encoder 0 sits
+        # within rounding distance of the leaky-relu kink for one of the 22 samples of the ragged batch and takes the other
+        # branch (tools/diag_traj.py: that step's gradient agrees with the FP32 engine to 4e-5 in the median and differs by
+        # 6e-2 in ONE row of encoder 0 / layer 1, hence by a rank-one term in layer 0).  The fixture's knife-edge scan
+        # (oracle/make_golden.py::clean_seed) covers the initial weights only, so the looser bound applies here.
         assert_update_close(k, sd[k].cpu().numpy(), v, init[k], s, 1e-4, engine == "fp32", g0.get(k), q99_tc=6e-2, mean_tc=1e-2)
     import pandas as pd
     torch.randn = lambda *a, **k: torch.from_numpy(g["eps_test"])

@@ -54,3 +54,21 @@ for steps in (1, 2, 3, 4):
         print(steps, k, "vs fp32 engine: max %.2e; worst columns" % d.max(), np.argsort(-d.max(0))[:8], "col max", np.sort(d.max(0))[-8:].round(3),
               "worst rows", np.argsort(-d.max(1))[:5], "n elems > 1e-2:", int((d > 1e-2).sum()))
     tr.close(); trf.close()
+print("---- gradient of step 2 (ragged) at the weights after one FP32-engine Adam step: tcs vs fp32 engine")
+gs = {}
+for eng, fl in (("tcs", _lib.TRAIN_TC_SIMPLE), ("fp32", _lib.TRAIN_FP32)):
+    tr = mk(True)
+    tr.train_steps(1, eps=torch.from_numpy(g["eps"][:1]).cuda()[None], flags=_lib.TRAIN_FP32)
+    tr.grads.zero_()
+    tr.train_steps(1, eps=torch.from_numpy(g["eps"][1:2]).cuda()[None], flags=fl | _lib.TRAIN_NO_ADAM | _lib.TRAIN_WRITE_GRADS)
+    gs[eng] = {k: v.cpu().numpy() for k, v in tr.state_dict(0, "grads").items()}
+    m1 = {k: v.cpu().numpy() for k, v in tr.state_dict(0, "adam_m").items()}
+    tr.close()
+for k in ("encoder_list.0.encoder_layers.0.weight", "encoder_list.1.encoder_layers.0.weight", "encoder_list.0.encoder_layers.1.weight"):
+    a, b = gs["tcs"][k], gs["fp32"][k]
+    mx = np.abs(b).max()
+    rel = np.abs(a - b) / mx
+    # Adam after step 2: m = .9 m1 + .1 g2 with m1 = .1 g1: the update direction is sensitive where g2 ~ -.9 g1... look at it
+    mm = 0.9 * m1[k] + 0.1 * b
+    print(k, "grad max-norm rel err: max %.1e median %.1e | |g2|/max: median %.2e | frac of elements with |m2| < 1e-2 max|m2|: %.3f" % (
+        rel.max(), np.median(rel), np.median(np.abs(b)) / mx, (np.abs(mm) < 1e-2 * np.abs(mm).max()).mean()))
