@@ -490,7 +490,7 @@ def run_b200(args):
         scorer = run.scorer
 
         def dev_step():
-            # 5 libnmb calls (reconstruct of the training + test rows in one launch, stats, deviation / z, 2 x AUC), then one fixed-size record per member
+            # 6 libnmb calls (reconstruct of the training + test rows in one launch, stats, deviation / z, 2 x AUC, the records): one fixed-size record per member
             # {subject AUC | per-ROI mean | std | AUC | per-subject deviation} and the all-gather (NCCL over NVLink, N > 1)
             return run.score()
         for _ in range(max(args.warmup, 5)):
@@ -527,7 +527,7 @@ def run_b200(args):
                      "subjects_per_pass": n_test_total, "reconstruction": "z sampled (cVAE.py:1207), like the reference's test script",
                      "mean_subject_auc": float(gs.subject_auc().mean()),
                      "mean_fold_auc_modalities_averaged": float(np.mean(list(fold_auc.values()))),
-                     "gathered_table": list(gs.table.shape), "launches_per_pass": scorer.launches_per_run}
+                     "gathered_table": list(gs.table.shape), "launches_per_pass": scorer.launches_per_run + 1}      # + nmb_member_records
 
     if True:
         peaks = {}

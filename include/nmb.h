@@ -320,6 +320,16 @@ int nmb_auc(int32_t n_seg, const float* const* scores, const uint8_t* const* lab
             const int32_t* n_rows, const int32_t* n_cols, double* const* out_auc,
             unsigned long long* const* out_u2, void* stream);
 
+/* The one exchange step of the multi-GPU split: one fixed-size float64 record per (member, modality) segment
+ *   { subject AUC | per-ROI mean [d_max] | per-ROI std [d_max] | per-ROI AUC [d_max] | per-subject deviation [n_test_max] }
+ * (zero / NaN padded) assembled from the flat result buffers of nmb_normative_stats ([2][d] per segment at o_stats[s]),
+ * nmb_auc (per-ROI at o_auc[s], per-subject [n_seg]) and nmb_deviation (per-subject at o_subj[s]) -- the rows every rank
+ * all-gathers before modalities are averaged (group analysis :212-215).  ALL pointers are DEVICE pointers.
+ * out: [n_seg][1 + 3 d_max + n_test_max]. */
+int nmb_member_records(int32_t n_seg, const float* stats, const int64_t* o_stats, const double* auc_roi, const int64_t* o_auc,
+                       const double* auc_subj, const float* subj, const int64_t* o_subj, const int32_t* seg_d,
+                       const int32_t* n_test, int32_t d_max, int32_t n_test_max, double* out, void* stream);
+
 /* Mean of k score vectors (modality averaging, group analysis :212-215). */
 int nmb_mean_rows(const float* const* src /*host table*/, int32_t k, int64_t n, float* out,
                   void* stream);

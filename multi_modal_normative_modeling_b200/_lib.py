@@ -92,6 +92,8 @@ _PROTOS = {
                                        C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p]),
     "nmb_auc": (C.c_int, [C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int32),
                           C.POINTER(C.c_int32), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p]),
+    "nmb_member_records": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "nmb_mean_rows": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
     "nmb_philox_normal": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint32, C.c_int64, C.c_void_p, C.c_void_p]),
     "nmb_debug_tcp_trace": (C.c_int, [C.c_void_p, C.c_int32]),

@@ -966,6 +966,19 @@ int nmb_auc(int32_t n_seg, const float* const* scores, const uint8_t* const* lab
   return 0;
 }
 
+int nmb_member_records(int32_t n_seg, const float* stats, const int64_t* o_stats, const double* auc_roi, const int64_t* o_auc,
+                       const double* auc_subj, const float* subj, const int64_t* o_subj, const int32_t* seg_d,
+                       const int32_t* n_test, int32_t d_max, int32_t n_test_max, double* out, void* stream) {
+  if (n_seg < 0 || d_max < 1 || n_test_max < 0) return fail("bad argument");
+  if (n_seg && (!stats || !o_stats || !auc_roi || !o_auc || !auc_subj || !subj || !o_subj || !seg_d || !n_test || !out))
+    return fail("null argument");
+  static_assert(sizeof(long long) == sizeof(int64_t), "offset tables are 64-bit");
+  launch_member_records(stats, (const long long*)o_stats, auc_roi, (const long long*)o_auc, auc_subj, subj,
+                        (const long long*)o_subj, seg_d, n_test, n_seg, d_max, n_test_max, out, (cudaStream_t)stream);
+  CU(cudaGetLastError());
+  return 0;
+}
+
 int nmb_mean_rows(const float* const* src, int32_t k, int64_t n, float* out, void* stream) {
   if (!src || !out || k < 1 || k > 16 || n < 0) return fail("bad argument (k must be 1..16)");
   PtrTable16 t; std::memset(&t, 0, sizeof(t));

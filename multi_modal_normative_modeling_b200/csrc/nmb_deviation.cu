@@ -383,6 +383,38 @@ void launch_latent_deviation(const LatentTable& t, int n_seg, int max_rows, cuda
 }
 
 // ---- misc -----------------------------------------------------------------------------------
+// Fixed-size float64 record per segment {subject AUC | per-ROI mean | std | AUC (d_max each) | per-subject deviation
+// (n_test_max, NaN-padded)}: the payload of the multi-GPU all-gather, assembled in one pass from the
+// scorer's flat result buffers.  CTA = one segment.
+__global__ void __launch_bounds__(256) member_records_kernel(const float* __restrict__ stats, const long long* __restrict__ o_stats,
+                                                             const double* __restrict__ auc_roi, const long long* __restrict__ o_auc,
+                                                             const double* __restrict__ auc_subj, const float* __restrict__ subj,
+                                                             const long long* __restrict__ o_subj, const int* __restrict__ seg_d,
+                                                             const int* __restrict__ n_test, int d_max, int n_test_max,
+                                                             double* __restrict__ out) {
+  const int s = blockIdx.x, d = seg_d[s], n = n_test[s];
+  const long long w = 1 + 3LL * d_max + n_test_max;
+  double* row = out + (long long)s * w;
+  const float* st = stats + o_stats[s];
+  const double* au = auc_roi + o_auc[s];
+  const float* sj = subj + o_subj[s];
+  if (threadIdx.x == 0) row[0] = auc_subj[s];
+  for (int j = threadIdx.x; j < d_max; j += blockDim.x) {
+    row[1 + j] = j < d ? (double)st[j] : 0.0;
+    row[1 + d_max + j] = j < d ? (double)st[d + j] : 0.0;
+    row[1 + 2 * d_max + j] = j < d ? au[j] : 0.0;
+  }
+  const double nan = __longlong_as_double(0x7ff8000000000000LL);
+  for (int j = threadIdx.x; j < n_test_max; j += blockDim.x) row[1 + 3 * d_max + j] = j < n ? (double)sj[j] : nan;
+}
+
+void launch_member_records(const float* stats, const long long* o_stats, const double* auc_roi, const long long* o_auc,
+                           const double* auc_subj, const float* subj, const long long* o_subj, const int* seg_d, const int* n_test,
+                           int n_seg, int d_max, int n_test_max, double* out, cudaStream_t st) {
+  if (n_seg > 0) member_records_kernel<<<n_seg, 256, 0, st>>>(stats, o_stats, auc_roi, o_auc, auc_subj, subj, o_subj, seg_d, n_test,
+                                                               d_max, n_test_max, out);
+}
+
 __global__ void mean_rows_kernel(PtrTable16 src, int k, long long n, float* out) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {

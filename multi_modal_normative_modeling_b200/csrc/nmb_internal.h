@@ -52,6 +52,9 @@ cudaError_t launch_pack_scaled(const double* x, long long ld, int d, const int* 
                                const double* scale, const int* age_bin, int n_age, const int* sex_bin, int n_sex, int ldx,
                                float* out, cudaStream_t st);
 void launch_mean_rows(const PtrTable16& src, int k, long long n, float* out, cudaStream_t st);
+void launch_member_records(const float* stats, const long long* o_stats, const double* auc_roi, const long long* o_auc,
+                           const double* auc_subj, const float* subj, const long long* o_subj, const int* seg_d, const int* n_test,
+                           int n_seg, int d_max, int n_test_max, double* out, cudaStream_t st);
 void launch_adam(float* p, const float* g, float* m, float* v, long long n, float step_size, float bc2_sqrt,
                  float b1, float b2, float eps, cudaStream_t st);
 void launch_philox(unsigned long long seed, unsigned long long step, uint32_t stream_id, long long n, float* out,

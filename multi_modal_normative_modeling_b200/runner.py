@@ -88,19 +88,7 @@ class EnsembleRunner:
     # ---- scoring + the one exchange step ------------------------------------------------------------------------
     def local_records(self) -> torch.Tensor:
         """[len(owned), 1 + 3 d_max + n_test_max] float64 records of this rank's members (one segment per member)."""
-        sc = self.scorer
-        rec = sc.member_records(d_max=self.d_max)
-        dev = torch.full((sc.n_seg, self.n_test_max), float("nan"), dtype=torch.float64, device=self.device)
-        if not hasattr(self, "_subj_idx"):
-            src, dst = [], []
-            for s in range(sc.n_seg):
-                n = sc.n_test[s]
-                src.append(np.arange(n) + int(sc.o_subj[s])); dst.append(np.arange(n) + s * self.n_test_max)
-            t = lambda a: torch.from_numpy(np.concatenate(a).astype(np.int64)).to(self.device)
-            self._subj_idx = (t(src), t(dst))
-        src, dst = self._subj_idx
-        dev.view(-1).index_copy_(0, dst, sc.subj.index_select(0, src).double())
-        return torch.cat([rec, dev], dim=1)
+        return self.scorer.member_table(d_max=self.d_max, n_test_max=self.n_test_max)      # one launch
 
     def score(self) -> GatheredScores:
         self.scorer.run()

@@ -252,6 +252,25 @@ class DeviationScorer:
     def seg_auc_roi(self, s):
         return self.auc_roi[int(self.o_auc[s]):int(self.o_auc[s]) + self.seg_d[s]]
 
+    def member_table(self, d_max: int = None, n_test_max: int = None) -> torch.Tensor:
+        """[n_seg, 1 + 3 d_max + n_test_max] float64: ``member_records`` plus the per-subject deviations (NaN-padded), in
+        ONE launch (``nmb_member_records``) -- the rows a rank contributes to the all-gather."""
+        import numpy as np
+        dmax = max(max(self.seg_d), d_max or 0)
+        nmax = max(max(self.n_test), n_test_max or 0)
+        if not hasattr(self, "_tbl_dev"):
+            t64 = lambda a: torch.from_numpy(np.asarray(a[: self.n_seg], dtype=np.int64)).to(self.dev)
+            t32 = lambda a: torch.from_numpy(np.asarray(a, dtype=np.int32)).to(self.dev)
+            self._tbl_dev = (t64(self.o_stats), t64(self.o_auc), t64(self.o_subj), t32(self.seg_d), t32(self.n_test))
+        o_stats, o_auc, o_subj, seg_d, n_test = self._tbl_dev
+        out = torch.empty((self.n_seg, 1 + 3 * dmax + nmax), dtype=torch.float64, device=self.dev)
+        with torch.cuda.device(self.dev):
+            _lib.check(self.lib.nmb_member_records(self.n_seg, self.stats.data_ptr(), o_stats.data_ptr(), self.auc_roi.data_ptr(),
+                                                   o_auc.data_ptr(), self.auc_subj.data_ptr(), self.subj.data_ptr(), o_subj.data_ptr(),
+                                                   seg_d.data_ptr(), n_test.data_ptr(), dmax, nmax, out.data_ptr(),
+                                                   _stream_ptr(self.dev)), "nmb_member_records")
+        return out
+
     def member_records(self, d_max: int = None) -> torch.Tensor:
         """Fixed-size float64 record per segment {subject AUC | per-ROI mean | per-ROI std | per-ROI AUC}, padded
         to the widest segment (or `d_max`, the widest of the WHOLE ensemble when it is sharded over ranks) -- the

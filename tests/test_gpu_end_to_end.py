@@ -196,6 +196,14 @@ def test_deviation_scorer_equals_the_per_call_api():
     assert rec.shape == (sc.n_seg, 1 + 3 * 116)
     assert torch.equal(rec[3, 1:117], sc.seg_stats(3)[0].double()) and torch.equal(rec[:, 0], sc.auc_subj)
     assert torch.equal(rec[0, 1 + 2 * 116:1 + 2 * 116 + 17], sc.seg_auc_roi(0)) and float(rec[0, 1 + 17:1 + 116].abs().max()) == 0
+    # the all-gather payload in one launch (nmb_member_records): the same record + the NaN-padded per-subject deviations
+    nmax = max(sc.n_test) + 3
+    tbl = sc.member_table(d_max=120, n_test_max=nmax)
+    wide = sc.member_records(d_max=120)
+    assert tbl.shape == (sc.n_seg, 1 + 3 * 120 + nmax) and torch.equal(tbl[:, :1 + 3 * 120], wide)
+    for s_ in range(sc.n_seg):
+        n = sc.n_test[s_]
+        assert torch.equal(tbl[s_, 1 + 360:1 + 360 + n], sc.seg_subj(s_).double()) and bool(torch.isnan(tbl[s_, 1 + 360 + n:]).all())
     tr.close()
 
 
