@@ -604,29 +604,49 @@ def run_b200(args):
         except Exception:
             pass
         engine = tr.engine()
+        # Which roof binds: the optimiser state of 480 models (0.6 GB) cannot live on chip, so p / m / v stream
+        # through HBM every minibatch step -- 24 B per parameter and step -- and the arithmetic intensity of a step
+        # (algorithmic FLOPs / algorithmic bytes, ~40 FLOP/B for cfg4) is far below the ridge of the measured peaks
+        # (~220 FLOP/B): the kernel's roofline is HBM.  The tensor-pipe figures stay in `tensor`.
+        hbm_peak = peaks.get("hbm_gbs") or 6500.0
+        local_bytes_per_step = wl.bytes_per_epoch * args.epochs_per_step
+        ach_gbs = local_bytes_per_step / (kernel_ms * 1e-3) / 1e9
+        intensity = local_flops_per_step / local_bytes_per_step
+        ridge = peak_tf * 1e12 / (hbm_peak * 1e9)
+        tensor = {"achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "peak_source": peak_src,
+                  "algorithmic_flops_per_launch": local_flops_per_step, "executed_tensor_frac": 3 * achieved / peak_tf,
+                  "note": "algorithmic (FP32-equivalent) FLOPs of rank 0's members; every product is executed as 3 BF16 tcgen05 "
+                          "passes (hi*hi, lo*hi, hi*lo, FP32 accumulate) to meet the 1e-4 parity bar, so the tensor pipe "
+                          "executes 3x these FLOPs"}
+        hbm_bound = intensity < ridge
+        roofline = {"bound": "hbm" if hbm_bound else "tensor",
+                    "achieved": ach_gbs if hbm_bound else achieved, "peak": hbm_peak if hbm_bound else peak_tf,
+                    "unit": "GB/s" if hbm_bound else "TFLOP/s",
+                    "frac": ach_gbs / hbm_peak if hbm_bound else achieved / peak_tf,
+                    "traffic": traffic if world == 1 else None,
+                    "kernel": "nmb::tcp::train_tcp_kernel" if engine == "tcgen05-pipelined" else "nmb::train_kernel",
+                    "kernel_ms": kernel_ms,
+                    "algorithmic_bytes_per_launch": local_bytes_per_step, "algorithmic_flops_per_launch": local_flops_per_step,
+                    "arithmetic_intensity_flop_per_byte": intensity, "ridge_flop_per_byte": ridge,
+                    "bound_note": "SURVEY 8d: with the Adam state streamed from HBM every step the step is HBM-bound; algorithmic "
+                                  "bytes per model and step = 24 B x parameters (p, m, v read + written; 60 092 parameters at D=116, "
+                                  "111 596 at D=348) + 4 (D + C) B per training row (workloads.train_bytes_per_epoch)",
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.5 TB/s",
+                    "traffic_note": traffic_note,
+                    "measured_dram_GBps": (traffic / (kernel_ms * 1e-3) / 1e9) if (traffic and world == 1) else None,
+                    "traffic_over_algorithmic": (traffic / local_bytes_per_step) if (traffic and world == 1) else None,
+                    "kernel_ms_note": "CUDA events bracket the four launches of a training call on rank 0 (xprep, state "
+                                      "conversion in, persistent kernel, state conversion out; with resident state the conversions run "
+                                      "once per job); the persistent kernel is ~0.96 of it (profiles/r02_launch_list_summary.txt)",
+                    "tensor": tensor,
+                    "note": "the launch runs at a third of the HBM roof and a twentieth (a sixth, executed) of the tensor roof: it is "
+                            "bound by the dependent chain of its per-layer items (DESIGN.md 2.5), not by either pipe"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
                 "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
                 "dtype": "bf16x3->f32" if engine != "fp32" else "f32",
                 "data": "synthetic", "config": config(args), "extra": extra,
-                "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                             "frac": achieved / peak_tf, "traffic": traffic if world == 1 else None,
-                             "kernel": "nmb::tcp::train_tcp_kernel" if engine == "tcgen05-pipelined" else "nmb::train_kernel",
-                             "kernel_ms": kernel_ms, "algorithmic_flops_per_launch": local_flops_per_step,
-                             "peak_source": peak_src, "traffic_note": traffic_note,
-                             "kernel_ms_note": "CUDA events bracket the four launches of a training call on rank 0 (xprep, state "
-                                               "conversion in, persistent kernel, state conversion out; with resident state the conversions run once "
-                                               "per job); the persistent kernel is ~0.96 of it (profiles/r02_launch_list_summary.txt)",
-                             "hbm": None if not (traffic and world == 1) else {
-                                 "achieved_GBps": traffic / (kernel_ms * 1e-3) / 1e9, "peak_GBps": peaks.get("hbm_gbs"),
-                                 "frac": (traffic / (kernel_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]) if peaks.get("hbm_gbs") else None,
-                                 "note": "measured DRAM bytes per launch (ncu, profiles/train_kernel_traffic.json) over the "
-                                         "live launch time: the kernel is latency-bound between its two roofs"},
-                             "note": "achieved = algorithmic (FP32-equivalent) FLOPs of rank 0's members; every product is "
-                                     "executed as 3 BF16 tcgen05 passes (hi*hi, lo*hi, hi*lo, FP32 accumulate) to meet the "
-                                     "1e-4 parity bar, so the tensor pipe executes 3x these FLOPs: executed_frac = %.4f of "
-                                     "the measured peak" % (3 * achieved / peak_tf),
-                             "executed_tensor_frac": 3 * achieved / peak_tf},
+                "roofline": roofline,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_all,
                         "d2h_bytes_per_step": d2h_all, "ms_per_step": e2e_ms / args.steps},
                 "gpu_launches": launches, "clocks": clocks}

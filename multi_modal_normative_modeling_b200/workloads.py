@@ -33,6 +33,22 @@ def train_flops_per_sample(d: int, c: int = 29, hidden: Sequence[int] = (110, 11
     return 2 * (3 * mac - (d + c) * h[0] - c * h[-1])
 
 
+def train_param_count(d: int, c: int = 29, hidden: Sequence[int] = (110, 110), z: int = 10) -> int:
+    """Trainable scalars of one single-modality cVAE (weights + biases + logvar_out); D=116: 60 092."""
+    h = list(hidden)
+    enc = [(d + c, h[0])] + [(h[i - 1], h[i]) for i in range(1, len(h))] + [(h[-1], z), (h[-1], z)]
+    dec = [(z + c, h[-1])] + [(h[len(h) - i], h[len(h) - 1 - i]) for i in range(1, len(h))] + [(h[0], d)]
+    return sum(a * b + b for a, b in enc + dec) + d
+
+
+def train_bytes_per_epoch(n_rows: int, batch: int, d: int, c: int = 29, hidden: Sequence[int] = (110, 110), z: int = 10) -> int:
+    """Algorithmic HBM bytes of one epoch of one model when the optimiser state is NOT resident on chip:
+    per minibatch step 4 P (3 reads + 3 writes) for p, m, v (gradients stay on chip), plus every training row once,
+    4 (D + C) bytes."""
+    steps = -(-n_rows // batch)
+    return steps * 24 * train_param_count(d, c, hidden, z) + 4 * n_rows * (d + c)
+
+
 def forward_flops_per_sample(d: int, c: int = 29, hidden: Sequence[int] = (110, 110), z: int = 10) -> int:
     h = list(hidden)
     enc = [(d + c, h[0])] + [(h[i - 1], h[i]) for i in range(1, len(h))] + [(h[-1], 2 * z)]
@@ -99,6 +115,7 @@ class DeviceWorkload:
     host_buffers: dict = field(default_factory=dict)   # pinned (x, c) per (fold, modality) for the e2e leg
     packed: dict = field(default_factory=dict)         # (fold, modality) -> packed train tensor
     flops_per_epoch: float = 0.0
+    bytes_per_epoch: float = 0.0            # algorithmic HBM bytes with streamed optimiser state (train_bytes_per_epoch)
     samples_per_epoch: int = 0
     test_subjects: int = 0
 
@@ -146,5 +163,6 @@ def to_device(hw: HostWorkload, device, n_seeds: int = 24, seed0: int = 0, membe
         n_tr = fd.train_x[name].shape[0]
         wl.samples_per_epoch += n_tr
         wl.flops_per_epoch += n_tr * train_flops_per_sample(d, hw.c_dim, hw.hidden, hw.latent)
+        wl.bytes_per_epoch += train_bytes_per_epoch(n_tr, hw.batch, d, hw.c_dim, hw.hidden, hw.latent)
         wl.test_subjects += fd.test_x[name].shape[0]
     return wl
