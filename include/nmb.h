@@ -47,6 +47,16 @@ enum { NMB_HEAD_NONE = 0, NMB_HEAD_REGRESSION = 1, NMB_HEAD_ENDTOEND = 2 };
 /* indices into NmbArch.head_params for NMB_HEAD_ENDTOEND (loss_function defaults :2131: margin 1, 0.1, 0.1, 0.1; dropout .5) */
 enum { NMB_HP_MARGIN = 0, NMB_HP_W_CONTRASTIVE = 1, NMB_HP_W_KL = 2, NMB_HP_W_REC = 3, NMB_HP_DROPOUT = 4 };
 
+/* Model family.  NMB_FAMILY_DMVAE = the baselines built on VariationalEncoder / VariationalDecoder
+ * (cVAE.py:1454-1480): DMVAE (:1491-1618), mmVAEPlus (:1895-2002; the same code with beta = 0.05) and WeightedDMVAE
+ * (:1620-1752; learnable per-modality loss weights).  Encoder m: x -> fc1 ReLU -> fc2 ReLU -> (fc_mu, fc_logvar), NO
+ * covariates; the first s_dim latent dimensions of every modality are PRIVATE (passed on as their mean), the rest are
+ * shared (product of experts over the modalities, reparameterised); decoder m: [z_shared | mu_private_m] -> fc1 ReLU ->
+ * fc2 ReLU -> sigmoid(fc_out); loss = sum_m w_m (beta * kl_shared + 0.5 * sum_d (x - x_recon)^2 / B).  With the
+ * reference's defaults (s_dim = c_dim = 29 >= latent 10) there is no shared part and the model is M deterministic
+ * autoencoders.  Requires n_hidden == 2, c_dim == 0 (packed rows are [x | 1]), head_kind == 0. */
+enum { NMB_FAMILY_CVAE = 0, NMB_FAMILY_DMVAE = 1 };
+
 /* Architecture of one ensemble member = the constructor arguments of
  * cVAE_multimodal(input_dim_list, hidden_dim, latent_dim, c_dim, ..., modalities, non_linear)
  * (cVAE.py:1088-1116); the single-modality cVAE (cVAE.py:391-411) is n_mod == 1. */
@@ -65,6 +75,10 @@ typedef struct {
   int32_t head_hidden[NMB_MAX_HEAD]; /* 128, 64 (cVAE.py:2248-2255) */
   float head_weight;  /* lambda_reg (cVAE.py:2334; the trainer passes 1.0) */
   float head_params[6]; /* NMB_HP_* (NMB_HEAD_ENDTOEND) */
+  int32_t family;     /* NMB_FAMILY_* */
+  int32_t s_dim;      /* NMB_FAMILY_DMVAE: private latent dimensions per modality (the reference passes c_dim) */
+  int32_t weighted;   /* NMB_FAMILY_DMVAE: 1 = WeightedDMVAE (weights in the NMB_SLOT_ALPHA slots, total = kl - ll) */
+  float beta;         /* NMB_FAMILY_DMVAE: total = beta * kl - ll (1.0 DMVAE, 0.05 mmVAEPlus) */
 } NmbArch;
 
 /* One tensor of the reference's state_dict inside the packed per-model parameter buffer.

@@ -27,7 +27,8 @@ class NmbArch(C.Structure):
                 ("hidden", C.c_int32 * NMB_MAX_HIDDEN), ("latent", C.c_int32), ("c_dim", C.c_int32),
                 ("combine", C.c_int32), ("loss_kind", C.c_int32), ("non_linear", C.c_int32),
                 ("head_kind", C.c_int32), ("n_head_hidden", C.c_int32), ("head_hidden", C.c_int32 * NMB_MAX_HEAD),
-                ("head_weight", C.c_float), ("head_params", C.c_float * 6)]
+                ("head_weight", C.c_float), ("head_params", C.c_float * 6),
+                ("family", C.c_int32), ("s_dim", C.c_int32), ("weighted", C.c_int32), ("beta", C.c_float)]
 
 
 class NmbSlot(C.Structure):
@@ -143,7 +144,8 @@ def int_table(vals):
 
 
 def make_arch(input_dims, hidden, latent, c_dim, combine="poe", loss_kind="gauss_ll", non_linear=True,
-              head=None, head_hidden=(128, 64), head_weight=1.0, head_params=None) -> NmbArch:
+              head=None, head_hidden=(128, 64), head_weight=1.0, head_params=None,
+              family=None, s_dim=0, weighted=False, beta=1.0) -> NmbArch:
     if isinstance(combine, str):
         key = combine.lower()
         if key not in COMBINE:
@@ -178,6 +180,10 @@ def make_arch(input_dims, hidden, latent, c_dim, combine="poe", loss_kind="gauss
             for i, k in enumerate(("margin", "w_contrastive", "w_kl", "w_rec", "dropout")):
                 a.head_params[i] = float(hp[k])
             a.head_weight = 0.0
+    if family in ("dmvae", 1):         # DMVAE / mmVAEPlus / WeightedDMVAE (cVAE.py:1491-1752, 1895-2002)
+        a.family, a.s_dim, a.weighted, a.beta = 1, int(s_dim), int(bool(weighted)), float(beta)
+    elif family not in (None, "cvae", 0):
+        raise ValueError("unknown model family")
     return a
 
 

@@ -113,6 +113,7 @@ NmbArch canonical(const NmbArch& a) {   // zero the unused tails so memcmp is me
     for (int i = 0; i < a.n_head_hidden && i < NMB_MAX_HEAD; ++i) c.head_hidden[i] = a.head_hidden[i];
     if (a.head_kind == NMB_HEAD_ENDTOEND) { for (int i = 0; i < 6; ++i) c.head_params[i] = a.head_params[i]; c.head_weight = 0.f; }
   }
+  if (a.family) { c.family = a.family; c.s_dim = a.s_dim; c.weighted = a.weighted ? 1 : 0; c.beta = a.beta; c.combine = 0; c.loss_kind = 0; c.non_linear = 1; }
   return c;
 }
 
@@ -350,7 +351,9 @@ int nmb_arch_slots(const NmbArch* arch, NmbSlot* slots, int32_t max_slots, int32
     NmbSlot s; s.kind = kind; s.modality = m; s.layer = layer; s.rows = rows; s.cols = cols; s.ld = ld; s.offset = off;
     v.push_back(s);
   };
-  if (d.head_kind != NMB_HEAD_ENDTOEND)      // (the end-to-end model has no alpha_m_list: plain PoE, cVAE.py:2081-2088)
+  // (no alpha_m_list in the end-to-end model: plain PoE, cVAE.py:2081-2088; in the DMVAE family the slots hold
+  //  WeightedDMVAE.weights, cVAE.py:1652)
+  if (d.head_kind != NMB_HEAD_ENDTOEND && (d.family != NMB_FAMILY_DMVAE || d.weighted))
     for (int m = 0; m < d.M; ++m) push(NMB_SLOT_ALPHA, m, 0, 1, 1, 1, d.alpha_off + m);
   for (int m = 0; m < d.M; ++m) {
     const ModDesc& q = d.mod[m];
@@ -360,7 +363,7 @@ int nmb_arch_slots(const NmbArch* arch, NmbSlot* slots, int32_t max_slots, int32
   }
   for (int m = 0; m < d.M; ++m) {
     const ModDesc& q = d.mod[m];
-    push(NMB_SLOT_LOGVAR_OUT, m, 0, 1, q.D, round4(q.D), q.lam_off);
+    if (d.family != NMB_FAMILY_DMVAE) push(NMB_SLOT_LOGVAR_OUT, m, 0, 1, q.D, round4(q.D), q.lam_off);   // VariationalDecoder has none
     for (int l = 0; l < d.L; ++l) push(NMB_SLOT_DEC, m, l, q.dec[l].out, q.dec[l].in, q.dec[l].ld, q.dec[l].off);
     push(NMB_SLOT_DEC_MEAN, m, 0, q.outl.out, q.outl.in, q.outl.ld, q.outl.off);
   }

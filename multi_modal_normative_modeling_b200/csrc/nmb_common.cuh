@@ -63,6 +63,10 @@ struct ArchDesc {
   long long s_bn[NMB_MAX_HEAD];                               // [2][bn_ld]: batch inverse std, scratch
   long long s_dev;                                            // [B][4]: deviation health, disease, contrastive sign, label
   int drop_w;                                                 // sum of the hidden widths (row length of drop_keep)
+  // NMB_FAMILY_DMVAE: S private + Zc shared latent dimensions
+  int family, S, Zc, weighted;
+  float beta;
+  long long s_dzs;                                            // [B][Z]: shared part of d(total)/dz summed over the decoders
   long long scratch_floats;
 };
 
@@ -94,6 +98,9 @@ inline int build_arch(const NmbArch& a, ArchDesc* d, const char** err) {
   if (a.combine < 0 || a.combine > NMB_COMBINE_MOPOE) return fail("No such combination method");
   if (a.loss_kind < 0 || a.loss_kind > NMB_LOSS_NEG_MSE) return fail("bad loss_kind");
   if (a.head_kind < NMB_HEAD_NONE || a.head_kind > NMB_HEAD_ENDTOEND) return fail("bad head_kind");
+  if (a.family != NMB_FAMILY_CVAE && a.family != NMB_FAMILY_DMVAE) return fail("bad family");
+  if (a.family == NMB_FAMILY_DMVAE && (a.n_hidden != 2 || a.c_dim != 0 || a.head_kind != NMB_HEAD_NONE || a.s_dim < 0))
+    return fail("NMB_FAMILY_DMVAE needs two hidden layers, c_dim == 0 (no covariates), no head and s_dim >= 0");
   if (a.head_kind == NMB_HEAD_ENDTOEND && 2 * a.n_mod > NMB_MAX_MOD) return fail("NMB_HEAD_ENDTOEND: at most 8 modalities");
   if (a.head_kind == NMB_HEAD_ENDTOEND && !(a.head_params[NMB_HP_DROPOUT] >= 0.f && a.head_params[NMB_HP_DROPOUT] < 1.f))
     return fail("dropout rate must be in [0, 1)");
@@ -172,6 +179,12 @@ inline int build_arch(const NmbArch& a, ArchDesc* d, const char** err) {
     d->ld_R = round4(d->sumD + 1); d->s_R = buf(d->ld_R); d->s_dR = buf(d->ld_R);
     for (int l = 0; l < d->HL; ++l) { d->ld_hh[l] = round4(d->head_w[l] + 1); d->s_hh[l] = buf(d->ld_hh[l]); }
     d->s_pred = buf(4); d->s_dpred = buf(4);
+  }
+  d->family = a.family; d->S = 0; d->Zc = Z; d->weighted = 0; d->beta = 1.f;
+  if (a.family == NMB_FAMILY_DMVAE) {
+    d->S = a.s_dim < Z ? a.s_dim : Z; d->Zc = Z - d->S; d->weighted = a.weighted ? 1 : 0; d->beta = a.beta;
+    d->combine = NMB_COMBINE_POE; d->loss_kind = NMB_LOSS_NEG_MSE; d->non_linear = 2;      // ReLU everywhere
+    d->s_dzs = buf(Z);
   }
   d->n_params = off;
   d->s_mub = buf(Z); d->s_lvb = buf(Z); d->s_eps = buf(Z); d->s_dz = buf(Z);

@@ -301,7 +301,7 @@ inline Program build_program(const ArchDesc& a, bool fwd_only = false) {
   Program P;
   const int M = a.M, L = a.L, Z = a.Z, C = a.C;
   if (2 * Z > 128 || Z + C + 1 > 128) return P;
-  if (a.head_kind) return P;                        // supervised heads run on the generic engines
+  if (a.head_kind || a.family) return P;            // supervised heads and the baseline families run on the generic engines
   for (int l = 0; l < L; ++l) if (a.hidden[l] > 127) return P;
   P.eligible = true;
   Layout& lay = P.lay;

@@ -843,6 +843,179 @@ __device__ void train_step_e2e(StepCtx& c, const float* eps_src, float* loss_out
   for (int m = 0; m < M; ++m) encoder_backward<TC>(c, ad, m);
 }
 
+// ---- DMVAE family (NMB_FAMILY_DMVAE: DMVAE / mmVAEPlus / WeightedDMVAE, cVAE.py:1454-1752, 1895-2002) ------------------
+// x_recon = sigmoid(fc_out(.)) (VariationalDecoder, :1477-1480); ll_m = -0.5 sum_d (x - x_recon)^2 averaged over the batch
+// (:1566); writes d(total)/d(pre-sigmoid) for total = ... - w_m ll_m.
+struct EpiReconSig {
+  const float* x; int ldx;
+  float* dxh; int ld;
+  float* keep;                    // x_recon [rows][ld] (always kept: peek / prediction)
+  float gscale;                   // w_m / B
+  float ll_acc;
+  __device__ __forceinline__ void one(float xt, float a, float& g, float& xh) {
+    xh = 1.f / (1.f + __expf(-a));
+    const float r = xt - xh;
+    ll_acc += -0.5f * r * r;
+    g = -gscale * r * xh * (1.f - xh);
+  }
+  template <int TN>
+  __device__ __forceinline__ void row(int m, int nb, int N, const float (&v)[TN]) {
+    const float* xr = x + (long long)m * ldx + nb;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      if (nb + 16 * j < N) {
+        float g, xh;
+        one(xr[16 * j], v[j], g, xh);
+        dxh[(long long)m * ld + nb + 16 * j] = g;
+        keep[(long long)m * ld + nb + 16 * j] = xh;
+      }
+    }
+  }
+  __device__ __forceinline__ void rowc(int m, int n0, int nvalid, const float (&v)[16]) {
+    float xt[16], g[16], xh[16];
+    load16(x + (long long)m * ldx + n0, nvalid, 0.f, xt);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float keep_acc = ll_acc;
+      one(xt[j], v[j], g[j], xh[j]);
+      if (j >= nvalid) ll_acc = keep_acc;
+    }
+    store16(dxh + (long long)m * ld + n0, nvalid, g);
+    store16(keep + (long long)m * ld + n0, nvalid, xh);
+  }
+};
+
+struct EpiStoreSig {   // prediction: x_recon = sigmoid(.)
+  float* dst; int ld;
+  template <int TN>
+  __device__ __forceinline__ void row(int m, int nb, int N, const float (&v)[TN]) {
+#pragma unroll
+    for (int j = 0; j < TN; ++j)
+      if (nb + 16 * j < N) dst[(long long)m * ld + nb + 16 * j] = 1.f / (1.f + __expf(-v[j]));
+  }
+  __device__ __forceinline__ void rowc(int m, int n0, int nvalid, const float (&v)[16]) {
+    float* d = dst + (long long)m * ld + n0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) if (j < nvalid) d[j] = 1.f / (1.f + __expf(-v[j]));
+  }
+};
+
+// Heads -> decoder inputs [z_shared (Zc) | mu_private_m (S) | 1] (:1535-1554).  Shared part: ProductOfExperts2 over the
+// modalities (:1482-1489), z = mu + eps * std; eps_mode as in latent_forward (eps_src: [rows][Z], the first Zc columns).  Returns this thread's
+// part of sum over (row, shared dim) of the KL integrand.
+__device__ float dmvae_latent_forward(const StepCtx& c, int eps_mode, const float* eps_src, uint32_t stream_id,
+                                      unsigned long long eps_step) {
+  const ArchDesc& a = *c.a;
+  const int Z = a.Z, M = a.M, Sd = a.S, Zc = a.Zc, n = c.rows * Zc;
+  float* S = c.scratch;
+  float kl = 0.f;
+  for (int g = threadIdx.x; g * 4 < n; g += kThreads) {
+    float nrm[4] = {0.f, 0.f, 0.f, 0.f};
+    if (eps_mode == 0) philox_normal4(c.mb->seed, eps_step, stream_id, (uint32_t)g, nrm);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int e = g * 4 + j;
+      if (e >= n) break;
+      const int b = e / Zc, z = e - b * Zc;
+      float mu[NMB_MAX_MOD], lv[NMB_MAX_MOD];
+      for (int m = 0; m < M; ++m) {
+        const float* h = S + a.mod[m].s_mulv + (long long)b * a.mod[m].ld_mulv;
+        mu[m] = h[Sd + z]; lv[m] = h[Z + Sd + z];
+      }
+      const Fused f = fuse_forward(mu, lv, M, NMB_COMBINE_POE, nullptr);
+      const float eps = eps_mode == 1 ? eps_src[b * Z + z] : (eps_mode == 2 ? 0.f : nrm[j]);   // injected: rows of `latent` entries
+      S[a.s_mub + e] = f.mu; S[a.s_lvb + e] = f.lv; S[a.s_eps + e] = eps;
+      const float zz = f.mu + eps * expf(0.5f * f.lv);
+      for (int m = 0; m < M; ++m) S[a.mod[m].s_g0 + (long long)b * a.mod[m].ld_g0 + z] = zz;
+      kl += -0.5f * (1.f + f.lv - f.mu * f.mu - expf(f.lv));
+    }
+  }
+  for (int m = 0; m < M; ++m) {
+    const ModDesc& q = a.mod[m];
+    for (int e = threadIdx.x; e < c.rows * Sd; e += kThreads) {
+      const int b = e / Sd, s = e - b * Sd;
+      S[q.s_g0 + (long long)b * q.ld_g0 + Zc + s] = S[q.s_mulv + (long long)b * q.ld_mulv + s];
+    }
+  }
+  __syncthreads();
+  return kl;
+}
+
+template <bool TC>
+__device__ void train_step_dmvae(StepCtx& c, const float* eps_src, float* loss_out) {
+  const ArchDesc& a = *c.a;
+  MemberDev& mb = *c.mb;
+  float* S = c.scratch;
+  float* P = mb.params;
+  const int M = a.M, Z = a.Z, Sd = a.S, Zc = a.Zc, rows = c.rows;
+  const float inv_rows = 1.f / rows;
+  float w[NMB_MAX_MOD], ll[NMB_MAX_MOD], wsum = 0.f;
+  for (int m = 0; m < M; ++m) { w[m] = a.weighted ? __ldcg(P + a.alpha_off + m) : 1.f; wsum += w[m]; }
+
+  // ---------------- forward (:1535-1556) ----------------
+  encoders_forward<TC>(c, c.xin);
+  float kl = dmvae_latent_forward(c, eps_src ? 1 : 0, eps_src, 0u, (unsigned long long)c.step);
+  kl = block_sum(kl, c.red) * inv_rows;
+  float ll_tot = 0.f;
+  for (int m = 0; m < M; ++m) {
+    const ModDesc& q = a.mod[m];
+    Opnd A = decoder_hidden<TC>(c, m);
+    EpiReconSig e;
+    e.x = c.xin[m] + (long long)c.row0 * q.ldx; e.ldx = q.ldx;
+    e.dxh = S + q.s_xh; e.ld = q.ld_xh; e.keep = S + q.s_xr;
+    e.gscale = w[m] * inv_rows; e.ll_acc = 0.f;
+    mm<TC>(c, rows, q.D, q.outl.in + 1, A, Opnd{P + q.outl.off, q.outl.ld, 1}, e);
+    ll[m] = block_sum(e.ll_acc, c.red) * inv_rows;
+    ll_tot += w[m] * ll[m];
+  }
+  if (loss_out && threadIdx.x == 0) {      // (:1562-1572; WeightedDMVAE :1693-1707 has beta = 1)
+    loss_out[0] = a.beta * wsum * kl - ll_tot; loss_out[1] = wsum * kl; loss_out[2] = ll_tot;
+  }
+
+  // ---------------- backward + Adam ----------------
+  const AdamCfg ad = make_adam(c);
+  for (int e = threadIdx.x; e < rows * Z; e += kThreads) S[a.s_dzs + e] = 0.f;
+  __syncthreads();
+  for (int m = 0; m < M; ++m) {
+    const ModDesc& q = a.mod[m];
+    decoder_backward<TC>(c, ad, m, 1.f, false, 0);          // d(total)/d[z_shared | mu_private_m] -> s_dz
+    __syncthreads();
+    for (int e = threadIdx.x; e < rows * Z; e += kThreads) {
+      const int b = e / Z, j = e - b * Z;
+      const float g = S[a.s_dz + e];
+      if (j < Zc) S[a.s_dzs + e] += g;
+      else {                                               // the private mean feeds only its own decoder; its logvar feeds nothing
+        float* d = S + q.s_dmulv + (long long)b * q.ld_mulv;
+        d[j - Zc] = g; d[Z + j - Zc] = 0.f;
+      }
+    }
+    if (a.weighted && threadIdx.x == 0) ad.apply(a.alpha_off + m, kl - ll[m]);      // d total / d weights[m]
+    __syncthreads();
+  }
+  {   // shared latent: reparameterisation, KL (weight beta * sum_m w_m) and the product of experts
+    const float klw = a.beta * wsum;
+    for (int e = threadIdx.x; e < rows * Zc; e += kThreads) {
+      const int b = e / Zc, z = e - b * Zc;
+      const float mub = S[a.s_mub + e], lvb = S[a.s_lvb + e], eps = S[a.s_eps + e], dz = S[a.s_dzs + b * Z + z];
+      const float sd = expf(0.5f * lvb);
+      const float dmu_bar = dz + klw * mub * inv_rows;
+      const float dlv_bar = dz * eps * sd * 0.5f + klw * (expf(lvb) - 1.f) * 0.5f * inv_rows;
+      float mu[NMB_MAX_MOD], lv[NMB_MAX_MOD], dmu[NMB_MAX_MOD], dlv[NMB_MAX_MOD];
+      for (int m = 0; m < M; ++m) {
+        const float* h = S + a.mod[m].s_mulv + (long long)b * a.mod[m].ld_mulv;
+        mu[m] = h[Sd + z]; lv[m] = h[Z + Sd + z];
+      }
+      fuse_backward(mu, lv, M, NMB_COMBINE_POE, nullptr, dmu_bar, dlv_bar, dmu, dlv, nullptr);
+      for (int m = 0; m < M; ++m) {
+        float* d = S + a.mod[m].s_dmulv + (long long)b * a.mod[m].ld_mulv;
+        d[Sd + z] = dmu[m]; d[Z + Sd + z] = dlv[m];
+      }
+    }
+    __syncthreads();
+  }
+  for (int m = 0; m < M; ++m) encoder_backward<TC>(c, ad, m);
+}
+
 // ---- one training step ---------------------------------------------------------------------
 template <bool TC>
 __device__ void train_step(StepCtx& c, const float* eps_src, float* loss_out) {
@@ -953,7 +1126,8 @@ __device__ __forceinline__ void train_body(const TrainLaunch& t, float* smem_f, 
       const float* eps = t.eps_override
           ? t.eps_override + ((long long)mi * t.stride_steps + i) * mb.batch * a.Z : nullptr;
       float* lo = t.loss_out ? t.loss_out + ((long long)mi * t.stride_steps + i) * ((t.flags & NMB_TRAIN_LOSS8) ? 8 : (t.flags & NMB_TRAIN_LOSS4) ? 4 : 3) : nullptr;
-      if (a.head_kind == NMB_HEAD_ENDTOEND) train_step_e2e<TC>(c, eps, lo);
+      if (a.family == NMB_FAMILY_DMVAE) train_step_dmvae<TC>(c, eps, lo);
+      else if (a.head_kind == NMB_HEAD_ENDTOEND) train_step_e2e<TC>(c, eps, lo);
       else train_step<TC>(c, eps, lo);
     }
     __syncthreads();
@@ -1033,6 +1207,19 @@ __device__ __forceinline__ void recon_body(const ReconLaunch& t, float* smem_f, 
         ? t.eps[item.member] + (long long)item.row0 * a.Z : nullptr;
     const int eps_mode = t.mode == NMB_RECON_GIVEN_Z ? 3 : (t.mode == NMB_RECON_MEAN ? 2 : (eps ? 1 : 0));
     // Philox test stream: counter "step" = row tile index so that tiles draw disjoint numbers
+    if (a.family == NMB_FAMILY_DMVAE) {      // pred_recon of the DMVAE family (cVAE.py:1574-1596): shared z sampled, private means
+      dmvae_latent_forward(c, eps_mode == 3 ? 2 : eps_mode, eps, 1u, (unsigned long long)(item.row0 / kMaxBatch));
+      for (int m = 0; m < a.M; ++m) {
+        const ModDesc& q = a.mod[m];
+        float* out = t.xhat[(long long)item.member * NMB_MAX_MOD + m];
+        if (!out) continue;
+        Opnd A = decoder_hidden<TC>(c, m);
+        EpiStoreSig e{out + (long long)item.row0 * q.D, q.D};
+        mm<TC>(c, item.rows, q.D, q.outl.in + 1, A, Opnd{mb.params + q.outl.off, q.outl.ld, 1}, e);
+      }
+      __syncthreads();
+      continue;
+    }
     latent_forward(c, xc, eps_mode, eps, 1u, (unsigned long long)(item.row0 / kMaxBatch));
     if (head_out && a.head_kind == NMB_HEAD_ENDTOEND) {
       // predict(): logits = classifier(z) in eval mode (running statistics, no dropout); the reference calls it on the

@@ -35,6 +35,14 @@ _SLOT_NAMES_E2E.update({
     _lib.SLOT_HEAD: "classifier.classifier.{l4}",
 })
 _BN_FIELDS = ("weight", "bias", "running_mean", "running_var", "num_batches_tracked")
+# VariationalEncoder / VariationalDecoder of the DMVAE family (cVAE.py:1454-1480)
+_SLOT_NAMES_DMVAE = {
+    _lib.SLOT_ENC: "encoder_list.{m}.fc{l1}",
+    _lib.SLOT_ENC_MEAN: "encoder_list.{m}.fc_mu",
+    _lib.SLOT_ENC_LOGVAR: "encoder_list.{m}.fc_logvar",
+    _lib.SLOT_DEC: "decoder_list.{m}.fc{l1}",
+    _lib.SLOT_DEC_MEAN: "decoder_list.{m}.fc_out",
+}
 
 
 def _loss_width(flags) -> int:
@@ -90,6 +98,11 @@ class MemberSpec:
     head_weight: float = 1.0               # lambda_reg
     head_params: Optional[dict] = None     # "endtoend": margin, w_contrastive, w_kl, w_rec, dropout (cVAE.py:2131, 2031)
     drop_keep: Optional[torch.Tensor] = None   # "endtoend": injected dropout keep flags [steps, batch, sum(head_hidden)]
+    # model family (f4): "dmvae" = DMVAE / mmVAEPlus (beta) / WeightedDMVAE (weighted); c_dim must be 0, two hidden layers
+    family: Optional[str] = None
+    s_dim: int = 0                         # private latent dimensions (the reference passes its c_dim)
+    weighted: bool = False
+    beta: float = 1.0
     y: Optional[torch.Tensor] = None       # head target per training row (float32 CUDA [N])
     row_order: Optional[torch.Tensor] = None   # int32 CUDA [epochs, n_mod, N]: per-epoch, per-modality loader permutations
     tag: object = None                     # caller bookkeeping, e.g. (fold, modality, seed)
@@ -116,11 +129,12 @@ class EnsembleTrainer:
         for s in self.specs:
             key = (tuple(s.input_dims), tuple(s.hidden), s.latent, s.c_dim, s.combine.lower(), s.loss_kind,
                    bool(s.non_linear), s.head, tuple(s.head_hidden) if s.head else (), float(s.head_weight) if s.head else 0.0,
-                   tuple(sorted((s.head_params or {}).items())))
+                   tuple(sorted((s.head_params or {}).items())), s.family, int(s.s_dim), bool(s.weighted), float(s.beta))
             if key not in cache:
                 arch = _lib.make_arch(s.input_dims, s.hidden, s.latent, s.c_dim, s.combine, s.loss_kind, s.non_linear,
                                       head=s.head, head_hidden=s.head_hidden, head_weight=s.head_weight,
-                                      head_params=s.head_params)
+                                      head_params=s.head_params, family=s.family, s_dim=s.s_dim, weighted=s.weighted,
+                                      beta=s.beta)
                 cache[key] = (arch, _lib.arch_slots(arch), _lib.arch_param_count(arch))
             arch, slots, npar = cache[key]
             s._arch = arch
@@ -217,10 +231,14 @@ class EnsembleTrainer:
         base = self.offsets[i]
         out = {}
         e2e = self.specs[i].head == "endtoend"
-        names = _SLOT_NAMES_E2E if e2e else _SLOT_NAMES
+        dmvae = self.specs[i].family == "dmvae"
+        names = _SLOT_NAMES_E2E if e2e else _SLOT_NAMES_DMVAE if dmvae else _SLOT_NAMES
         for s in self.slots[i]:
             seg = flat[base + s.offset: base + s.offset + s.rows * s.ld]
-            if s.kind == _lib.SLOT_ALPHA:
+            if s.kind == _lib.SLOT_ALPHA and dmvae:
+                if s.modality == 0:          # WeightedDMVAE.weights: one [M] vector (the slots are contiguous)
+                    out["weights"] = flat[base + s.offset: base + s.offset + len(self.specs[i].input_dims)]
+            elif s.kind == _lib.SLOT_ALPHA:
                 out[f"alpha_m_list.{s.modality}"] = flat[base + s.offset: base + s.offset + 1]
             elif s.kind in (_lib.SLOT_LOGVAR_OUT, _lib.SLOT_LOGVAR_OUT2):
                 pre = "decoder_list" if not e2e else ("decoder_list_health" if s.kind == _lib.SLOT_LOGVAR_OUT else "decoder_list_disease")
@@ -230,7 +248,7 @@ class EnsembleTrainer:
                     o = base + s.offset + r * s.ld
                     out[f"classifier.classifier.{4 * s.layer + 1}.{f}"] = flat[o: o + (s.cols if r < 4 else 1)].view(() if r == 4 else (s.cols,))
             else:
-                name = names[s.kind].format(m=s.modality, l=s.layer, l2=2 * s.layer, l4=4 * s.layer)
+                name = names[s.kind].format(m=s.modality, l=s.layer, l1=s.layer + 1, l2=2 * s.layer, l4=4 * s.layer)
                 mat = seg.view(s.rows, s.ld)
                 out[name + ".weight"] = mat[:, : s.cols]
                 out[name + ".bias"] = mat[:, s.cols]

@@ -415,3 +415,71 @@ def e2e_train_loop(model, xs, cs, labels, batch_size, epochs, eps_steps, keep_st
             log.append([float(out[k].detach()) for k in ("total", "kl", "ce", "rec_health", "rec_disease", "contrastive")])
             step += 1
     return np.asarray(log, dtype=np.float64)
+
+
+class OracleDMVAE(nn.Module):
+    """The DMVAE family of the baseline zoo: ``DMVAE`` (cVAE.py:1491-1618), ``mmVAEPlus`` (:1895-2002; identical code with
+    beta = 0.05) and ``WeightedDMVAE`` (:1620-1752; ``weights = |randn(M)|`` multiply each modality's kl and ll, beta unused).
+    VariationalEncoder / VariationalDecoder (:1454-1480): two ReLU layers, no covariates, sigmoid output.  The first s_dim
+    latent dimensions are private (passed on as their mean), the rest shared (ProductOfExperts2, :1482-1489)."""
+
+    def __init__(self, input_dim_list, hidden_dim, latent_dim, s_dim, learning_rate=1e-4, modalities=3, beta=1.0, weighted=False):
+        super().__init__()
+        self.modalities, self.s_dim, self.beta, self.weighted = modalities, s_dim, beta, weighted
+
+        def enc(d):
+            m = nn.Module()
+            m.fc1, m.fc2 = nn.Linear(d, hidden_dim[0]), nn.Linear(hidden_dim[0], hidden_dim[1])
+            m.fc_mu, m.fc_logvar = nn.Linear(hidden_dim[1], latent_dim), nn.Linear(hidden_dim[1], latent_dim)
+            return m
+
+        def dec(d):
+            m = nn.Module()
+            m.fc1, m.fc2, m.fc_out = nn.Linear(latent_dim, hidden_dim[1]), nn.Linear(hidden_dim[1], hidden_dim[0]), nn.Linear(hidden_dim[0], d)
+            return m
+        self.encoder_list = nn.ModuleList([enc(input_dim_list[i]) for i in range(modalities)])
+        self.decoder_list = nn.ModuleList([dec(input_dim_list[i]) for i in range(modalities)])
+        if weighted:
+            self.weights = nn.Parameter(torch.abs(torch.randn(modalities)))
+        self.optimizer1 = torch.optim.Adam(self.parameters(), lr=learning_rate)
+
+    def step_losses(self, xs, eps=None):
+        mu_s, mu_c, lv_c = [], [], []
+        for i, e in enumerate(self.encoder_list):
+            h = torch.relu(e.fc2(torch.relu(e.fc1(xs[i]))))
+            mu, lv = e.fc_mu(h), e.fc_logvar(h)
+            mu_s.append(mu[:, : self.s_dim]); mu_c.append(mu[:, self.s_dim:]); lv_c.append(lv[:, self.s_dim:])
+        mu_c, lv_c = torch.stack(mu_c), torch.stack(lv_c)
+        t = 1.0 / torch.exp(lv_c)
+        mu = torch.sum(mu_c * t, dim=0) / torch.sum(t, dim=0)
+        logvar = torch.log(1.0 / torch.sum(t, dim=0))
+        if eps is None:
+            eps = torch.randn_like(mu)
+        z = mu + eps * torch.exp(0.5 * logvar)
+        recons = []
+        for i, d in enumerate(self.decoder_list):
+            h = torch.relu(d.fc2(torch.relu(d.fc1(torch.cat((z, mu_s[i]), dim=1)))))
+            recons.append(torch.sigmoid(d.fc_out(h)))
+        kl = ll = 0
+        for i in range(self.modalities):
+            w = self.weights[i] if self.weighted else 1.0
+            kl = kl + w * (-0.5 * torch.sum(1 + logvar - mu.pow(2) - torch.exp(logvar), dim=1).mean(0))
+            ll = ll + w * (-0.5 * torch.sum((xs[i] - recons[i]) ** 2, dim=1).mean(0))
+        total = (kl - ll) if self.weighted else (kl * self.beta - ll)
+        return {"total": total, "kl": kl, "ll": ll, "mu_c": mu, "logvar_c": logvar, "x_recons": recons}
+
+
+def dmvae_train_loop(model, xs, batch_size, epochs, eps_steps, zc):
+    """Loop body of the train script (:177-199) for a DMVAE-family model.  Returns per-step (total, kl, ll)."""
+    n = xs[0].shape[0]
+    log, step = [], 0
+    for _ in range(epochs):
+        for lo in range(0, n, batch_size):
+            xb = [x[lo:lo + batch_size] for x in xs]
+            out = model.step_losses(xb, torch.as_tensor(eps_steps[step][: xb[0].shape[0], :zc]))
+            model.optimizer1.zero_grad()
+            out["total"].backward()
+            model.optimizer1.step()
+            log.append((float(out["total"].detach()), float(torch.as_tensor(out["kl"]).detach()), float(out["ll"].detach())))
+            step += 1
+    return np.asarray(log, dtype=np.float64)

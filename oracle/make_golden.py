@@ -158,7 +158,8 @@ def _knife_scan(model, run):
     pre, hooks = {}, []
     for pname, mod in model.named_modules():
         if isinstance(mod, torch.nn.Linear) and (".encoder_layers." in pname or ".decoder_layers." in pname
-                                                 or pname in ("regressor.0", "regressor.2")):
+                                                 or pname in ("regressor.0", "regressor.2")
+                                                 or pname.endswith((".fc1", ".fc2"))):
             def _keep(_m, _i, o, pname=pname):      # must return None: a returned value would replace the output
                 pre.setdefault(pname, []).append(o.detach().clone())
             hooks.append(mod.register_forward_hook(_keep))
@@ -823,6 +824,84 @@ def ref_mmjsd_case(ref, name, dims, hidden, z, c_dim, n, b, epochs, seed, n_age)
     print(name, "ok", losses[0], "->", losses[-1], "jsd", out["jsd0"])
 
 
+def ref_dmvae_case(ref, name, cls_name, dims, hidden, z, s_dim, n, b, epochs, seed, tries=300):
+    """f4: the UNMODIFIED DMVAE-family baselines (``DMVAE`` / ``mmVAEPlus`` / ``WeightedDMVAE``, cVAE.py:1491-1752,
+    1895-2002) through the training loop body (train script :177-199 with -Model <name>): VariationalEncoder /
+    VariationalDecoder without covariates, s_dim private latent dimensions per modality (the train script passes its
+    c_dim), the rest shared through ProductOfExperts2 and reparameterised (injected eps)."""
+    m = len(dims)
+    cls = getattr(ref, cls_name)
+    batches = _loop_batches(n, b)
+    zc = max(0, z - s_dim)
+
+    def build(sd):
+        rng = np.random.RandomState(sd)
+        torch.manual_seed(sd)
+        model = cls(input_dim_list=list(dims), hidden_dim=list(hidden), latent_dim=z, c_dim=s_dim, learning_rate=1e-4,
+                    modalities=m, non_linear=True)
+        xs = [rng.rand(n, d).astype(np.float32) * 1.4 - 0.2 for d in dims]       # around the sigmoid's range
+        eps = rng.randn(epochs * len(batches), b, z).astype(np.float32)
+        return model, rng, xs, eps
+
+    def fwd_loss(model, xt, eps, s_):
+        r0, rows = batches[s_ % len(batches)]
+        xb = [x[r0:r0 + rows] for x in xt]
+        with injected_eps([torch.from_numpy(eps[s_][:rows, :zc].copy())]):
+            fwd = model.forward_multimodal(xb, None, "poe")
+        return fwd, model.loss_function_multimodal(xb, fwd)
+
+    import contextlib, io
+    best = None
+    for t in range(tries):
+        sd = seed + 1000 * t
+        model, _, xs, eps = build(sd)
+        xt = [torch.from_numpy(x) for x in xs]
+        with contextlib.redirect_stdout(io.StringIO()):
+            kn = _knife_scan(model, lambda: fwd_loss(model, xt, eps, 0))
+        score = sum(len(v) for v in kn.values())
+        if best is None or score < best[0]:
+            best = (score, sd)
+        if score == 0:
+            break
+    seed = best[1]
+    print("  seed", seed, "knife edges:", best[0])
+    model, rng, xs, eps = build(seed)
+    xt = [torch.from_numpy(x) for x in xs]
+    out = {"cls": cls_name, "dims": np.array(dims), "hidden": np.array(hidden), "z": z, "s_dim": s_dim, "seed": seed, "n": n,
+           "batch": b, "epochs": epochs, "eps": eps, "beta": float(model.beta)}
+    for k, v in sd_np(model).items():
+        out["init/" + k] = v
+    for i, x in enumerate(xs):
+        out[f"x{i}"] = x
+    losses = []
+    with contextlib.redirect_stdout(io.StringIO()):          # WeightedDMVAE prints three lines per step
+        for s_ in range(epochs * len(batches)):
+            fwd, loss = fwd_loss(model, xt, eps, s_)
+            model.optimizer1.zero_grad()
+            loss["total"].backward()
+            if s_ == 0:
+                out["mu_c"] = fwd["mu_c"].detach().numpy().copy()
+                for i in range(m):
+                    out[f"xrecon{i}"] = fwd["x_recons"][i].detach().numpy().copy()
+                for k, pr in model.named_parameters():
+                    out["grad/" + k] = (pr.grad.detach().numpy().copy() if pr.grad is not None else np.zeros(tuple(pr.shape), np.float32))
+                    if pr.grad is None:
+                        out["nograd/" + k] = np.array(1)
+            model.optimizer1.step()
+            losses.append([float(loss["total"].detach()), float(torch.as_tensor(loss["kl"]).detach()), float(loss["ll"].detach())])
+    out["losses"] = np.array(losses, dtype=np.float64)
+    for k, v in sd_np(model).items():
+        out["final/" + k] = v
+    eps_t = rng.randn(n, z).astype(np.float32)
+    with torch.no_grad(), injected_eps([torch.from_numpy(eps_t[:, :zc].copy())]):
+        preds = model.pred_recon([pd.DataFrame(x) for x in xs], None, torch.device("cpu"), "poe")
+    out["eps_test"] = eps_t
+    for i in range(m):
+        out[f"pred{i}"] = preds[i]
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, "ok", losses[0], "->", losses[-1])
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     sys.path.insert(0, REF)
@@ -834,6 +913,12 @@ def main():
             sd = clean_seed(mm, [116, 116, 116, 348], [110, 110], 10, 29, 288, 256, 2, 46, 27, [comb])
             ref_loop_case(ref, "mm_M4_full_" + comb.lower(), [116, 116, 116, 348], [110, 110], 10, 29, 288, 256, comb, 2,
                           sd, 27, lean=lean)
+        return
+    if "--f4b" in sys.argv:
+        ref_dmvae_case(ref, "dmvae_M2_shared", "DMVAE", [13, 6], [11, 9], 7, 4, 23, 10, 3, 41)
+        ref_dmvae_case(ref, "mmvaeplus_M3_shared", "mmVAEPlus", [40, 24, 17], [32, 24], 12, 5, 150, 64, 2, 42)
+        ref_dmvae_case(ref, "wdmvae_M3_shared", "WeightedDMVAE", [40, 24, 17], [32, 24], 12, 5, 150, 64, 2, 43)
+        ref_dmvae_case(ref, "dmvae_M3_default", "DMVAE", [116, 116, 116], [110, 110], 10, 29, 288, 256, 2, 44)   # s_dim >= latent
         return
     if "--f4" in sys.argv:
         ref_mmjsd_case(ref, "mmjsd_M3", [116, 58, 30], [110, 110], 10, 29, 150, 128, 2, 31, 27)

@@ -1,0 +1,83 @@
+"""f4: the DMVAE family of the baseline zoo -- ``DMVAE`` / ``mmVAEPlus`` / ``WeightedDMVAE`` (cVAE.py:1491-1752,
+1895-2002) -- through the C ABI (``NMB_FAMILY_DMVAE``) on both generic engines, against vectors recorded from the
+unmodified reference classes (oracle/make_golden.py --f4b): private / shared latent split, ProductOfExperts2,
+sigmoid decoders with the 0.5 * SSE term, beta, learnable modality weights, and the default configuration whose
+shared latent is empty."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import assert_update_close, load, relerr, sub
+
+pytestmark = pytest.mark.gpu
+REL = 1e-4
+CASES = ["dmvae_M2_shared", "mmvaeplus_M3_shared", "wdmvae_M3_shared", "dmvae_M3_default"]
+ENGINES = ["tcs", "fp32"]
+
+
+def engine_flags(engine):
+    from multi_modal_normative_modeling_b200 import _lib
+    return {"tcs": _lib.TRAIN_TC_SIMPLE, "fp32": _lib.TRAIN_FP32}[engine]
+
+
+def make_trainer(g, sd_prefix="init/", keep_grads=True):
+    from multi_modal_normative_modeling_b200 import EnsembleTrainer, MemberSpec, pack_rows
+    dims = [int(d) for d in g["dims"]]
+    n = int(g["n"])
+    none = torch.zeros((n, 0), device="cuda")
+    xc = [pack_rows(torch.from_numpy(g[f"x{i}"]).cuda(), none) for i in range(len(dims))]
+    sd = {k: torch.from_numpy(v) for k, v in sub(g, sd_prefix).items()}
+    spec = MemberSpec(input_dims=dims, hidden=[int(h) for h in g["hidden"]], latent=int(g["z"]), c_dim=0, xc=xc,
+                      batch=int(g["batch"]), seed=3, state_dict=sd, family="dmvae", s_dim=int(g["s_dim"]),
+                      weighted=str(g["cls"]) == "WeightedDMVAE", beta=float(g["beta"]))
+    return EnsembleTrainer([spec], keep_grads=keep_grads), xc
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("name", CASES)
+def test_dmvae_family_step_vs_reference(golden_dir, name, engine):
+    from multi_modal_normative_modeling_b200 import _lib
+    g = load(golden_dir, name)
+    tr, _ = make_trainer(g)
+    assert tr.engine() == "tcgen05-generic"
+    flags = engine_flags(engine) | _lib.TRAIN_NO_ADAM | _lib.TRAIN_WRITE_GRADS | _lib.TRAIN_KEEP_ACTS
+    losses = tr.train_steps(1, eps=torch.from_numpy(g["eps"][:1]).cuda()[None], record_losses=True, flags=flags)
+    torch.cuda.synchronize()
+    assert np.allclose(losses[0, 0].cpu().numpy(), g["losses"][0], rtol=REL, atol=1e-7), (losses[0, 0], g["losses"][0])
+    _, _, xr = tr.peek(0)
+    for i in range(len(xr)):
+        assert relerr(xr[i].cpu().numpy(), g[f"xrecon{i}"]) < REL
+    grads = tr.state_dict(0, "grads")
+    assert set(grads) == set(sub(g, "init/"))                          # the reference's state_dict names, nothing else
+    for k, v in sub(g, "grad/").items():
+        got = grads[k].cpu().numpy().reshape(v.shape)
+        if np.abs(v).max() == 0:
+            assert np.abs(got).max() == 0, k                           # e.g. fc_logvar when there is no shared latent
+        else:
+            assert np.abs(got - v).max() / np.abs(v).max() < REL, (k, np.abs(got - v).max() / np.abs(v).max())
+    tr.close()
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("name", CASES)
+def test_dmvae_family_epochs_and_prediction_vs_reference(golden_dir, name, engine):
+    g = load(golden_dir, name)
+    tr, xc = make_trainer(g, keep_grads=False)
+    steps = g["eps"].shape[0]
+    losses = tr.train_steps(steps, eps=torch.from_numpy(g["eps"]).cuda()[None], record_losses=True, flags=engine_flags(engine))
+    torch.cuda.synchronize()
+    got, want = losses[0].cpu().numpy().astype(np.float64), g["losses"]
+    assert np.allclose(got[:, 0], want[:, 0], rtol=REL) and np.allclose(got[:, 2], want[:, 2], rtol=REL), (got, want)
+    assert np.allclose(got[:, 1], want[:, 1], rtol=10 * REL, atol=1e-7)
+    sd, init, g0 = tr.state_dict(0), sub(g, "init/"), sub(g, "grad/")
+    for k, v in sub(g, "final/").items():
+        assert_update_close(k, sd[k].cpu().numpy().reshape(v.shape), v, init[k], steps, 1e-4, engine == "fp32", g0.get(k),
+                            q99_tc=6e-2, mean_tc=1e-2)     # BF16x3: ReLU units that come to the kink after the first steps
+    tr.close()
+    # pred_recon (:1574-1596) of the trained model: shared z sampled, private means
+    tr, xc = make_trainer(g, sd_prefix="final/", keep_grads=False)
+    xhat, _, _ = tr.reconstruct([xc], mode="sample", eps=[torch.from_numpy(g["eps_test"]).cuda()],
+                                engine="fp32" if engine == "fp32" else "tcs")
+    for i in range(len(xc)):
+        assert relerr(xhat[0][i].cpu().numpy(), g[f"pred{i}"]) < REL, i
+    tr.close()
