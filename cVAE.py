@@ -6,3 +6,5 @@ from multi_modal_normative_modeling_b200.cVAE import (  # noqa: F401
 # the reference's cVAE module exports the END-TO-END SUPERVISED model (v2, cVAE.py:2021-2207) under this name; the different
 # class of the same name defined inside multimodal_kfold_cvae_nmmlp.py is multi_modal_normative_modeling_b200.cVAE's
 from multi_modal_normative_modeling_b200.e2e import Classifier, cVAE_multimodal_endtoend  # noqa: F401,E402
+from multi_modal_normative_modeling_b200.zoo import (  # noqa: F401,E402
+    DMVAE, ProductOfExperts2, VariationalDecoder, VariationalEncoder, WeightedDMVAE, mmVAEPlus)

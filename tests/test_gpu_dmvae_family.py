@@ -81,3 +81,66 @@ def test_dmvae_family_epochs_and_prediction_vs_reference(golden_dir, name, engin
     for i in range(len(xc)):
         assert relerr(xhat[0][i].cpu().numpy(), g[f"pred{i}"]) < REL, i
     tr.close()
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_dmvae_family_dropins_vs_reference(golden_dir, name):
+    """The drop-in classes through the reference loop (fwd -> loss -> zero_grad -> backward -> optimizer1.step()) with the
+    recorded eps fed through torch.randn, then pred_recon; FP32 engine, so the trajectory is held to the exact bound."""
+    import cVAE as shim
+    import pandas as pd
+    from multi_modal_normative_modeling_b200 import _lib
+    g = load(golden_dir, name)
+    dims = [int(d) for d in g["dims"]]
+    z, s_dim = int(g["z"]), int(g["s_dim"])
+    zc = max(0, z - s_dim)
+    torch.manual_seed(int(g["seed"]))
+    model = getattr(shim, str(g["cls"]))(dims, [int(h) for h in g["hidden"]], z, s_dim, learning_rate=1e-4, modalities=len(dims),
+                                         non_linear=True)
+    init = sub(g, "init/")
+    assert set(model.state_dict()) == set(init)
+    for k, v in model.state_dict().items():
+        assert np.array_equal(v.numpy(), init[k]), k
+    assert float(model.beta) == float(g["beta"])
+    model.to("cuda")
+    model._engine_flags = _lib.TRAIN_FP32
+    xs = [torch.from_numpy(g[f"x{i}"]).cuda() for i in range(len(dims))]
+    n, b = int(g["n"]), int(g["batch"])
+    real = torch.randn
+    log, s = [], 0
+    try:
+        for _ in range(int(g["epochs"])):
+            for r0 in range(0, n, b):
+                rows = min(b, n - r0)
+                torch.randn = lambda *a, **k: torch.from_numpy(g["eps"][s][:rows, :zc].copy()).to(k.get("device", "cpu"))
+                fwd = model.forward_multimodal([x[r0:r0 + rows] for x in xs], None, "poe")
+                torch.randn = real
+                loss = model.loss_function_multimodal([x[r0:r0 + rows] for x in xs], fwd)
+                if s == 0:
+                    assert fwd["mu_c"].shape == (rows, zc)
+                    if zc:
+                        assert relerr(fwd["mu_c"].detach().cpu().numpy(), g["mu_c"]) < REL
+                    assert relerr(fwd["x_recons"][0].detach().cpu().numpy(), g["xrecon0"]) < REL
+                model.optimizer1.zero_grad()
+                loss["total"].backward()
+                model.optimizer1.step()
+                log.append([float(loss[k].detach()) for k in ("total", "kl", "ll")])
+                s += 1
+    finally:
+        torch.randn = real
+    got, want = np.asarray(log), g["losses"]
+    assert np.allclose(got[:, 0], want[:, 0], rtol=REL) and np.allclose(got[:, 2], want[:, 2], rtol=REL), (got, want)
+    assert np.allclose(got[:, 1], want[:, 1], rtol=10 * REL, atol=1e-7)
+    sd, g0 = model.state_dict(), sub(g, "grad/")
+    for k, v in sub(g, "final/").items():
+        assert_update_close(k, sd[k].cpu().numpy(), v, init[k], s, 1e-4, True, g0.get(k))
+    torch.randn = lambda *a, **k: torch.from_numpy(g["eps_test"][:, :zc].copy()).to(k.get("device", "cpu"))
+    try:
+        preds = model.pred_recon([pd.DataFrame(g[f"x{i}"]) for i in range(len(dims))], None, None, "poe")
+    finally:
+        torch.randn = real
+    for i in range(len(dims)):
+        assert relerr(preds[i], g[f"pred{i}"]) < REL, i
+    devs = model.reconstruction_deviation_multimodal([g[f"x{i}"] for i in range(len(dims))], preds)
+    assert len(devs) == len(dims) and devs[0].shape == (n,)
+    model.close()
