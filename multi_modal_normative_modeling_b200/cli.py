@@ -34,7 +34,8 @@ import torch
 from sklearn.preprocessing import RobustScaler
 
 from . import scoring
-from .cVAE import cVAE_multimodal, cVAE_multimodal_endtoend
+from .cVAE import cVAE_multimodal, cVAE_multimodal_endtoend, mmJSD
+from .zoo import DMVAE, WeightedDMVAE, mmVAEPlus
 from .ensemble import EnsembleTrainer, MemberSpec, pack_rows
 from . import prologue
 from .pipeline import covariate_onehots
@@ -169,16 +170,35 @@ def cyclic_lr_schedule(n_steps, n_samples, batch_size=256, base_lr=1e-6, max_lr=
     return (base_lr + (max_lr - base_lr) * np.maximum(0, 1 - x_lr) * gamma ** cycle).astype(np.float32)
 
 
+# the train script's model_dict (:141-148); mvtCAE is not built
+MODEL_DICT = {"cVAE_multimodal": cVAE_multimodal, "mmJSD": mmJSD, "DMVAE": DMVAE, "WeightedDMVAE": WeightedDMVAE,
+              "mmVAEPlus": mmVAEPlus}
+
+
+def _without_covariates(packed: torch.Tensor, d: int) -> torch.Tensor:
+    """[x | c | 1] rows -> [x | 1] rows for the DMVAE family, whose encoders / decoders take no covariates."""
+    return pack_rows(packed[:, :d].contiguous(), torch.zeros((packed.shape[0], 0), device=packed.device))
+
+
+def _spec_kwargs(model, combine, nmmlp=False):
+    """MemberSpec keywords (c_dim, fusion, loss, family) that make an ensemble member compute what `model` computes."""
+    if isinstance(model, DMVAE):
+        return dict(c_dim=0, **model._family_kwargs())
+    if isinstance(model, mmJSD):
+        return dict(c_dim=29, combine="poe")                 # mmJSD ignores `combine` (cVAE.py:1400-1403)
+    return dict(c_dim=29, combine=combine, loss_kind="neg_mse" if nmmlp else "gauss_ll")
+
+
 def train_main(args, root=None):
     """All folds (x seeds) of one configuration in ONE fused launch."""
     root = Path(root or Path.cwd())
     args = fill_defaults(args)
-    if args.model != "cVAE_multimodal":
-        raise ValueError(f"Model '{args.model}' is not recognized. Available models are: cVAE_multimodal")
+    if args.model not in MODEL_DICT:
+        raise ValueError(f"Model '{args.model}' is not recognized. Available models are: {', '.join(MODEL_DICT)}")
     dev = _device()
     nmmlp = bool(getattr(args, "nmmlp", False))
     n_seeds = int(getattr(args, "ensemble_seeds", 1))
-    model_cls = cVAE_multimodal_endtoend if nmmlp else cVAE_multimodal
+    model_cls = cVAE_multimodal_endtoend if nmmlp else MODEL_DICT[args.model]
     participants_path, kfold_dir, model_dir = _paths(root, args.dataset_resourse)
     np.random.seed(42)                                       # train script :41-44
     rn.seed(42)
@@ -216,13 +236,14 @@ def train_main(args, root=None):
             lr_steps = torch.from_numpy(cyclic_lr_schedule(args.epochs * spe, n_samples)).to(dev)
         for s_ in range(n_seeds):
             torch.manual_seed(42 + s_)                        # train script :119 (seed 42 for member 0)
-            init = model_cls(dims, h_dim, z_dim, 29, learning_rate=0.0001, modalities=len(names),
-                             non_linear=True).state_dict()
-            specs.append(MemberSpec(dims, h_dim, z_dim, 29, xs, combine=args.combine,
-                                    loss_kind="neg_mse" if nmmlp else "gauss_ll", batch=256,
+            init_model = model_cls(dims, h_dim, z_dim, 29, learning_rate=0.0001, modalities=len(names), non_linear=True)
+            kw = _spec_kwargs(init_model, args.combine, nmmlp)
+            rows = xs if kw["c_dim"] else [_without_covariates(t, d) for t, d in zip(xs, dims)]
+            specs.append(MemberSpec(dims, h_dim, z_dim, xc=rows, batch=256,
                                     seed=(42 + s_) * 1000003 + fold, lr=0.0001, lr_steps=lr_steps,
-                                    state_dict={k: v.detach().clone() for k, v in init.items() if not k.startswith("mlp.")},
-                                    tag=(fold, s_)))
+                                    state_dict={k: v.detach().clone() for k, v in init_model.state_dict().items()
+                                                if not k.startswith("mlp.")},
+                                    tag=(fold, s_), **kw))
     print("train model")
     with _phase("train: ensemble create"):
         trainer = EnsembleTrainer(specs, device=dev)
@@ -302,10 +323,12 @@ def test_main(args, root=None):
             for m_, d_ in enumerate(widths[:-1]):
                 xcs[m_][:, d_:d_ + 29] = xcs[-1][:, widths[-1]:widths[-1] + 29]
         dims = [len(get_column_name(args.dataset_resourse, n)) for n in names]
-        specs.append(MemberSpec(dims, list(args.hz_para_list[:-1]), int(args.hz_para_list[-1]), 29, xcs,
-                                combine=args.combine, loss_kind="neg_mse" if nmmlp else "gauss_ll",
+        kw = _spec_kwargs(model, args.combine, nmmlp)          # the pickled class decides (cVAE_multimodal, mmJSD, DMVAE family)
+        if not kw["c_dim"]:
+            xcs = [_without_covariates(t, d) for t, d in zip(xcs, dims)]
+        specs.append(MemberSpec(dims, list(args.hz_para_list[:-1]), int(args.hz_para_list[-1]), xc=xcs,
                                 state_dict={k: v for k, v in model.state_dict().items() if not k.startswith("mlp.")},
-                                seed=4242 + fold))
+                                seed=4242 + fold, **kw))
         test_xc.append(xcs); test_frames.append(frames); test_x64.append(x64)
     trainer = EnsembleTrainer(specs, device=dev)
     xhat, _, _ = trainer.reconstruct(test_xc, mode="sample")   # z sampled at test time (cVAE.py:1207)

@@ -170,6 +170,15 @@ class DMVAE(_FusedBase):
     def configure_optimizers(self):
         return self.optimizer1
 
+    @classmethod
+    def from_ensemble(cls, trainer: EnsembleTrainer, i: int):
+        """Materialise ensemble member i as a reference-shaped module (for torch.save / pred_recon)."""
+        s = trainer.specs[i]
+        model = cls(list(s.input_dims), list(s.hidden), s.latent, s.s_dim, learning_rate=s.lr, modalities=len(s.input_dims),
+                    non_linear=True)
+        model.load_state_dict({k: v.cpu() for k, v in trainer.state_dict(i).items()}, strict=True)
+        return model.to(trainer.device)
+
     def reconstruction_deviation_multimodal(self, xes, x_preds):
         out = []
         for m in range(self.modalities):

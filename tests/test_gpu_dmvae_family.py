@@ -144,3 +144,40 @@ def test_dmvae_family_dropins_vs_reference(golden_dir, name):
     devs = model.reconstruction_deviation_multimodal([g[f"x{i}"] for i in range(len(dims))], preds)
     assert len(devs) == len(dims) and devs[0].shape == (n,)
     model.close()
+
+
+def test_train_test_programs_with_model_flag(tmp_path):
+    """``-Model`` of the train script (:141-148) on a synthetic HCPimage dataset: mmJSD == cVAE_multimodal with PoE bit for
+    bit (the same kernels, `combine` ignored); DMVAE / mmVAEPlus / WeightedDMVAE train, pickle as the drop-in classes
+    and go through the test program + group analysis; mvtCAE is refused."""
+    import argparse
+    import pandas as pd
+    from multi_modal_normative_modeling_b200 import cli, synthetic, zoo
+    synthetic.write_dataset(str(tmp_path), "HCPimage", n=200, seed=4)
+    base = dict(dataset_resourse="HCPimage", hz_para_list=[32, 24, 6], combine=None, procedure="SE-MoE", n_splits=2, epochs=3,
+                oversample_percentage=1, single_modality=None, base_learning_rate=1e-4, max_learning_rate=5e-3,
+                training_class="nm", ensemble_seeds=1, nmmlp=False)
+    a = cli.train_main(argparse.Namespace(model="mmJSD", **base), root=tmp_path)
+    poe = dict(base, procedure="SE-PoE")
+    b = cli.train_main(argparse.Namespace(model="cVAE_multimodal", **poe), root=tmp_path)
+    assert np.array_equal(a, b)                         # mmJSD with -P SE-MoE == cVAE_multimodal with PoE
+    with pytest.raises(ValueError, match="not recognized"):
+        cli.train_main(argparse.Namespace(model="mvtCAE", **base), root=tmp_path)
+    for model, cls in (("DMVAE", zoo.DMVAE), ("mmVAEPlus", zoo.mmVAEPlus), ("WeightedDMVAE", zoo.WeightedDMVAE)):
+        for hz in ([32, 24, 40], [32, 24, 6]):          # latent 40 > c_dim 29: 11 shared dimensions; latent 6: none (the default situation)
+            ns = dict(base, hz_para_list=hz)
+            losses = cli.train_main(argparse.Namespace(model=model, **ns), root=tmp_path)
+            assert losses.shape == (2, 3, 3) and np.isfinite(losses).all()
+            assert (losses[:, :, 1] > 0).all() if hz[-1] > 29 else (losses[:, :, 1] == 0).all()        # kl of the shared part
+            saved = torch.load(tmp_path / "outputs" / "kfold_analysis" / "supervised_cvae" / "001" / "cVAE_model.pkl",
+                               weights_only=False)
+            assert type(saved) is cls and saved.latent_dim == hz[-1]
+            cli.test_main(argparse.Namespace(model=model, **ns), root=tmp_path)
+            d = tmp_path / "deviation" / "supervised_cvae" / "HCPimage" / "SE-MoE" / "path_model" / "fMRI"
+            rec = pd.read_csv(d / "reconstruction_fMRI.csv").iloc[:, 4:].to_numpy()
+            nrm = pd.read_csv(d / "normalized_fMRI.csv").iloc[:, 4:].to_numpy()
+            roi = pd.read_csv(d / "reconstruction_error_roi_fMRI.csv").iloc[:, 4:].to_numpy()
+            assert rec.shape == (200, 116) and rec.min() >= 0.0 and rec.max() <= 1.0          # sigmoid decoders
+            assert np.abs((nrm - rec) ** 2 - roi).max() < 1e-4 * max(1.0, np.abs(roi).max())
+            summary = cli.analysis_main(argparse.Namespace(model=model, **ns), root=tmp_path)
+            assert 0.0 <= summary[0][2][0] <= 1.0
