@@ -54,8 +54,13 @@ enum { NMB_HP_MARGIN = 0, NMB_HP_W_CONTRASTIVE = 1, NMB_HP_W_KL = 2, NMB_HP_W_RE
  * shared (product of experts over the modalities, reparameterised); decoder m: [z_shared | mu_private_m] -> fc1 ReLU ->
  * fc2 ReLU -> sigmoid(fc_out); loss = sum_m w_m (beta * kl_shared + 0.5 * sum_d (x - x_recon)^2 / B).  With the
  * reference's defaults (s_dim = c_dim = 29 >= latent 10) there is no shared part and the model is M deterministic
- * autoencoders.  Requires n_hidden == 2, c_dim == 0 (packed rows are [x | 1]), head_kind == 0. */
-enum { NMB_FAMILY_CVAE = 0, NMB_FAMILY_DMVAE = 1 };
+ * autoencoders.  Requires n_hidden == 2, c_dim == 0 (packed rows are [x | 1]), head_kind == 0.
+ * NMB_FAMILY_MVTCAE = mvtCAE (cVAE.py:1754-1893): the cVAE_multimodal architecture (covariates, logvar_out, alphas) with
+ * total = sum_m (kl + 1e-5 * ll_m + beta * tc) -- the log-likelihood enters with a PLUS sign as written (:1862) -- where
+ * tc = - sum_i mean_m logsumexp_b mu_m[b, i] (:1846-1853; its first term cancels itself), beta = 1e-4; the fused variance is
+ * clamped to >= 1e-6 (:1815) and the 'poe' branch hands VARIANCES to ProductOfExperts2, which exponentiates them again
+ * (:1778, :1800): reproduced as written. */
+enum { NMB_FAMILY_CVAE = 0, NMB_FAMILY_DMVAE = 1, NMB_FAMILY_MVTCAE = 2 };
 
 /* Architecture of one ensemble member = the constructor arguments of
  * cVAE_multimodal(input_dim_list, hidden_dim, latent_dim, c_dim, ..., modalities, non_linear)
@@ -78,7 +83,7 @@ typedef struct {
   int32_t family;     /* NMB_FAMILY_* */
   int32_t s_dim;      /* NMB_FAMILY_DMVAE: private latent dimensions per modality (the reference passes c_dim) */
   int32_t weighted;   /* NMB_FAMILY_DMVAE: 1 = WeightedDMVAE (weights in the NMB_SLOT_ALPHA slots, total = kl - ll) */
-  float beta;         /* NMB_FAMILY_DMVAE: total = beta * kl - ll (1.0 DMVAE, 0.05 mmVAEPlus) */
+  float beta;         /* NMB_FAMILY_DMVAE: total = beta * kl - ll (1.0 DMVAE, 0.05 mmVAEPlus); NMB_FAMILY_MVTCAE: weight of tc (1e-4) */
 } NmbArch;
 
 /* One tensor of the reference's state_dict inside the packed per-model parameter buffer.

@@ -182,6 +182,8 @@ def make_arch(input_dims, hidden, latent, c_dim, combine="poe", loss_kind="gauss
             a.head_weight = 0.0
     if family in ("dmvae", 1):         # DMVAE / mmVAEPlus / WeightedDMVAE (cVAE.py:1491-1752, 1895-2002)
         a.family, a.s_dim, a.weighted, a.beta = 1, int(s_dim), int(bool(weighted)), float(beta)
+    elif family in ("mvtcae", 2):      # mvtCAE (cVAE.py:1754-1893): beta weighs the total-correlation term
+        a.family, a.beta = 2, float(beta)
     elif family not in (None, "cvae", 0):
         raise ValueError("unknown model family")
     return a

@@ -767,3 +767,65 @@ class mmJSD(cVAE_multimodal):
                 jsd = jsd + kl_divergence(Normal(mus[i], torch.exp(0.5 * logvars[i])),
                                           Normal(mus[j], torch.exp(0.5 * logvars[j]))).mean()
         return jsd / (n * (n - 1) / 2)
+
+
+class mvtCAE(cVAE_multimodal):
+    """The ``mvtCAE`` baseline (cVAE.py:1754-1893; ``-Model mvtCAE``), AS WRITTEN in the reference: the
+    cVAE_multimodal architecture and parameters, the fused variance clamped to >= 1e-6 (:1815), a 'poe' branch that hands
+    variances to ProductOfExperts2 (which exponentiates them again, :1778 / :1800), and
+    ``total = sum_m (kl + 1e-5 * ll_m + beta * tc)`` -- the log-likelihood with a plus sign (:1862), beta = 1e-4,
+    tc = - sum_i mean_m logsumexp_b mu_m[b, i] (:1846-1853).  One fused launch per step (``NMB_FAMILY_MVTCAE``) on the
+    generic engines; ``losses`` carries 'tc' as well."""
+
+    _head_kind = "mvtcae"        # (selects the 4-wide loss record; there is no head)
+    beta = 0.0001
+
+    def _head_kwargs(self):
+        return {"family": "mvtcae", "beta": float(self.beta)}
+
+    def _make_engine(self, dev, dims, combine, rows, keep_grads, names=None, with_head=False):
+        bufs = [torch.zeros((rows, _lib.packed_row_stride(int(d), self.c_dim)), dtype=torch.float32, device=dev) for d in dims]
+        spec = MemberSpec(dims, self._hidden, self.latent_dim, self.c_dim, bufs, combine=combine, non_linear=self._non_linear,
+                          batch=rows, lr=self.learning_rate, **self._head_kwargs())
+        eng = EnsembleTrainer([spec], device=dev, keep_grads=keep_grads)
+        eng._rows_buf = bufs
+        return eng
+
+    def _moments(self, dev):
+        if self.__dict__.get("_adam_m") is None:
+            n = _lib.arch_param_count(_lib.make_arch(self._dims, self._hidden, self.latent_dim, self.c_dim, "poe", "gauss_ll",
+                                                     self._non_linear, **self._head_kwargs()))
+            object.__setattr__(self, "_adam_m", torch.zeros(n, dtype=torch.float32, device=dev))
+            object.__setattr__(self, "_adam_v", torch.zeros(n, dtype=torch.float32, device=dev))
+            object.__setattr__(self, "_adam_t", 0)
+            return self._adam_m, self._adam_v
+        return super()._moments(dev)
+
+    def _infer_engine(self, combine):
+        dev = self._require_cuda()
+        key = ("infer", combine.lower(), str(dev))
+        eng = self._cache().get(key)
+        if eng is None:
+            eng = self._cache()[key] = self._make_engine(dev, self._dims, combine, 1, keep_grads=False)
+        self._load_weights(eng)
+        return eng
+
+    def forward_multimodal(self, xes, cs, combine):
+        self.zero_grad()
+        _lib.make_arch(self._dims, self._hidden, self.latent_dim, self.c_dim, combine)   # ValueError if unknown
+        outs = self._fused_forward(list(xes), list(cs), combine)
+        total, kl, ll, mu, logvar = outs[:5]
+        m = self.modalities
+        x_recons = [Normal(loc=outs[5 + i], scale=self.decoder_list[i].logvar_out.detach().exp().pow(0.5)) for i in range(m)]
+        fwd = {"x_recons": x_recons, "mu_multimodal": mu, "logvar_multimodal": logvar, "qz_x": mu}
+        self._remember(fwd, {"total": total, "kl": kl, "ll": ll, "tc": outs[5 + m]}, "mu_multimodal")
+        return fwd
+
+    def combine_latent(self, mus, variances, combine):
+        """(mu, clamped variance) as the reference computes them (:1795-1816)."""
+        if combine.lower() == "poe":
+            t = 1.0 / torch.exp(variances)
+            mu, var = torch.sum(mus * t, dim=0) / torch.sum(t, dim=0), torch.log(1.0 / torch.sum(t, dim=0))
+        else:
+            mu, var = fuse_latent(mus, variances, combine, list(self.alpha_m_list))
+        return mu, torch.clamp(var, min=1e-6)

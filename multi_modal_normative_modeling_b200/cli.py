@@ -34,7 +34,7 @@ import torch
 from sklearn.preprocessing import RobustScaler
 
 from . import scoring
-from .cVAE import cVAE_multimodal, cVAE_multimodal_endtoend, mmJSD
+from .cVAE import cVAE_multimodal, cVAE_multimodal_endtoend, mmJSD, mvtCAE
 from .zoo import DMVAE, WeightedDMVAE, mmVAEPlus
 from .ensemble import EnsembleTrainer, MemberSpec, pack_rows
 from . import prologue
@@ -170,9 +170,9 @@ def cyclic_lr_schedule(n_steps, n_samples, batch_size=256, base_lr=1e-6, max_lr=
     return (base_lr + (max_lr - base_lr) * np.maximum(0, 1 - x_lr) * gamma ** cycle).astype(np.float32)
 
 
-# the train script's model_dict (:141-148); mvtCAE is not built
+# the train script's model_dict (:141-148)
 MODEL_DICT = {"cVAE_multimodal": cVAE_multimodal, "mmJSD": mmJSD, "DMVAE": DMVAE, "WeightedDMVAE": WeightedDMVAE,
-              "mmVAEPlus": mmVAEPlus}
+              "mvtCAE": mvtCAE, "mmVAEPlus": mmVAEPlus}
 
 
 def _without_covariates(packed: torch.Tensor, d: int) -> torch.Tensor:
@@ -186,6 +186,8 @@ def _spec_kwargs(model, combine, nmmlp=False):
         return dict(c_dim=0, **model._family_kwargs())
     if isinstance(model, mmJSD):
         return dict(c_dim=29, combine="poe")                 # mmJSD ignores `combine` (cVAE.py:1400-1403)
+    if isinstance(model, mvtCAE):
+        return dict(c_dim=29, combine=combine, family="mvtcae", beta=float(model.beta))
     return dict(c_dim=29, combine=combine, loss_kind="neg_mse" if nmmlp else "gauss_ll")
 
 

@@ -113,7 +113,8 @@ NmbArch canonical(const NmbArch& a) {   // zero the unused tails so memcmp is me
     for (int i = 0; i < a.n_head_hidden && i < NMB_MAX_HEAD; ++i) c.head_hidden[i] = a.head_hidden[i];
     if (a.head_kind == NMB_HEAD_ENDTOEND) { for (int i = 0; i < 6; ++i) c.head_params[i] = a.head_params[i]; c.head_weight = 0.f; }
   }
-  if (a.family) { c.family = a.family; c.s_dim = a.s_dim; c.weighted = a.weighted ? 1 : 0; c.beta = a.beta; c.combine = 0; c.loss_kind = 0; c.non_linear = 1; }
+  if (a.family == NMB_FAMILY_DMVAE) { c.family = a.family; c.s_dim = a.s_dim; c.weighted = a.weighted ? 1 : 0; c.beta = a.beta; c.combine = 0; c.loss_kind = 0; c.non_linear = 1; }
+  else if (a.family) { c.family = a.family; c.beta = a.beta; }
   return c;
 }
 

@@ -98,7 +98,9 @@ inline int build_arch(const NmbArch& a, ArchDesc* d, const char** err) {
   if (a.combine < 0 || a.combine > NMB_COMBINE_MOPOE) return fail("No such combination method");
   if (a.loss_kind < 0 || a.loss_kind > NMB_LOSS_NEG_MSE) return fail("bad loss_kind");
   if (a.head_kind < NMB_HEAD_NONE || a.head_kind > NMB_HEAD_ENDTOEND) return fail("bad head_kind");
-  if (a.family != NMB_FAMILY_CVAE && a.family != NMB_FAMILY_DMVAE) return fail("bad family");
+  if (a.family < NMB_FAMILY_CVAE || a.family > NMB_FAMILY_MVTCAE) return fail("bad family");
+  if (a.family == NMB_FAMILY_MVTCAE && (a.head_kind != NMB_HEAD_NONE || a.loss_kind != NMB_LOSS_GAUSS_LL))
+    return fail("NMB_FAMILY_MVTCAE: Gaussian log-likelihood, no head");
   if (a.family == NMB_FAMILY_DMVAE && (a.n_hidden != 2 || a.c_dim != 0 || a.head_kind != NMB_HEAD_NONE || a.s_dim < 0))
     return fail("NMB_FAMILY_DMVAE needs two hidden layers, c_dim == 0 (no covariates), no head and s_dim >= 0");
   if (a.head_kind == NMB_HEAD_ENDTOEND && 2 * a.n_mod > NMB_MAX_MOD) return fail("NMB_HEAD_ENDTOEND: at most 8 modalities");
@@ -186,6 +188,7 @@ inline int build_arch(const NmbArch& a, ArchDesc* d, const char** err) {
     d->combine = NMB_COMBINE_POE; d->loss_kind = NMB_LOSS_NEG_MSE; d->non_linear = 2;      // ReLU everywhere
     d->s_dzs = buf(Z);
   }
+  if (a.family == NMB_FAMILY_MVTCAE) d->beta = a.beta;
   d->n_params = off;
   d->s_mub = buf(Z); d->s_lvb = buf(Z); d->s_eps = buf(Z); d->s_dz = buf(Z);
   d->ld_g = round4(maxw);

@@ -107,4 +107,46 @@ __device__ inline void fuse_backward(const float* mu, const float* lv, int M, in
 }
 
 
+// ---- mvtCAE's fusion as written (cVAE.py:1778, 1795-1816) ---------------------------------------------------------
+// 'poe' hands VARIANCES v_m = exp(lv_m) to ProductOfExperts2, which treats them as log-variances: T_m = 1 / exp(v_m),
+// mu = sum mu_m T_m / sum T_m, "variance" = log(1 / sum T_m).  Every branch then clamps the variance to >= 1e-6.
+// Returns the fused (mu, log clamp(var)); *clamped tells the backward pass that the variance path carries no gradient.
+__device__ inline Fused fuse_forward_mvtcae(const float* mu, const float* lv, int M, int combine, const float* w, bool* clamped) {
+  Fused f;
+  float var;
+  if (combine == NMB_COMBINE_POE) {
+    float s = 0.f, num = 0.f;
+    for (int m = 0; m < M; ++m) { const float t = expf(-expf(lv[m])); s += t; num += mu[m] * t; }
+    f.mu = num / s;
+    var = logf(1.f / s);
+  } else {
+    const int M1 = M;      // (mvtCAE has no single-modality shortcut)
+    if (M1 == 1 && combine != NMB_COMBINE_MOPOE) { f.mu = mu[0]; var = expf(lv[0]); }
+    else { const Fused g = fuse_forward(mu, lv, M, combine, w); f.mu = g.mu; var = expf(g.lv); }
+  }
+  *clamped = !(var >= 1e-6f);
+  f.lv = logf(*clamped ? 1e-6f : var);
+  return f;
+}
+
+__device__ inline void fuse_backward_mvtcae(const float* mu, const float* lv, int M, int combine, const float* w, bool clamped,
+                                            float dmu_bar, float dlv_bar, float* dmu, float* dlv, float* dw) {
+  if (clamped) dlv_bar = 0.f;
+  if (combine != NMB_COMBINE_POE) {
+    if (dw) for (int m = 0; m < M; ++m) dw[m] = 0.f;
+    fuse_backward(mu, lv, M, combine, w, dmu_bar, dlv_bar, dmu, dlv, dw);
+    return;
+  }
+  float T[NMB_MAX_MOD], v[NMB_MAX_MOD], s = 0.f, num = 0.f;
+  for (int m = 0; m < M; ++m) { v[m] = expf(lv[m]); T[m] = expf(-v[m]); s += T[m]; num += mu[m] * T[m]; }
+  const float pmu = num / s, var = logf(1.f / s);
+  const float ds = clamped ? 0.f : -(dlv_bar / var) / s;         // var = -log s
+  for (int m = 0; m < M; ++m) {
+    dmu[m] = dmu_bar * T[m] / s;
+    const float dT = dmu_bar * (mu[m] - pmu) / s + ds;
+    dlv[m] = dT * (-T[m]) * v[m];
+    if (dw) dw[m] = 0.f;
+  }
+}
+
 }  // namespace nmb

@@ -331,7 +331,9 @@ __device__ float latent_forward(const StepCtx& c, const float* const* xc, int ep
         const float* h = S + a.mod[m].s_mulv + (long long)b * a.mod[m].ld_mulv;
         mu[m] = h[z]; lv[m] = h[Z + z];
       }
-      const Fused f = fuse_forward(mu, lv, M, a.combine, w);
+      bool clamped;
+      const Fused f = a.family == NMB_FAMILY_MVTCAE ? fuse_forward_mvtcae(mu, lv, M, a.combine, w, &clamped)
+                                                    : fuse_forward(mu, lv, M, a.combine, w);
       const float eps = eps_mode == 1 ? eps_src[e] : nrm[j];
       S[a.s_mub + e] = f.mu; S[a.s_lvb + e] = f.lv; S[a.s_eps + e] = eps;
       const float zz = f.mu + eps * expf(0.5f * f.lv);
@@ -462,6 +464,7 @@ __device__ void head_fold(const StepCtx& c, int m) {
 }
 
 __device__ void e2e_fold(const StepCtx& c, int m);
+__device__ void scale_dxh(const StepCtx& c, int m, float s);
 
 // Backward of decoder set m (logvar_out, decoder_mean_layer, hidden layers down to dz) fused with Adam.
 //   lam_scale: weight of the reconstruction term in the total (1; w_rec for the end-to-end model)
@@ -498,6 +501,7 @@ __device__ void decoder_backward(const StepCtx& c, const AdamCfg& ad, int m, flo
     }
     if (fold == 1) head_fold(c, m);
     else if (fold == 2) e2e_fold(c, m);
+    else if (fold == 3) scale_dxh(c, m, lam_scale);
     int cur = 0;
     // decoder_mean_layer
     {
@@ -551,7 +555,13 @@ __device__ void latent_backward(const StepCtx& c, const AdamCfg& ad, float klw) 
         const float* h = S + a.mod[m].s_mulv + (long long)b * a.mod[m].ld_mulv;
         mu[m] = h[z]; lv[m] = h[Z + z];
       }
-      fuse_backward(mu, lv, M, a.combine, w, dmu_bar, dlv_bar, dmu, dlv, gpoe ? dw : nullptr);
+      if (a.family == NMB_FAMILY_MVTCAE) {
+        bool clamped;
+        fuse_forward_mvtcae(mu, lv, M, a.combine, w, &clamped);
+        fuse_backward_mvtcae(mu, lv, M, a.combine, w, clamped, dmu_bar, dlv_bar, dmu, dlv, gpoe ? dw : nullptr);
+      } else {
+        fuse_backward(mu, lv, M, a.combine, w, dmu_bar, dlv_bar, dmu, dlv, gpoe ? dw : nullptr);
+      }
       for (int m = 0; m < M; ++m) {
         float* d = S + a.mod[m].s_dmulv + (long long)b * a.mod[m].ld_mulv;
         d[z] = dmu[m]; d[Z + z] = dlv[m];
@@ -1016,6 +1026,46 @@ __device__ void train_step_dmvae(StepCtx& c, const float* eps_src, float* loss_o
   for (int m = 0; m < M; ++m) encoder_backward<TC>(c, ad, m);
 }
 
+// ---- mvtCAE (NMB_FAMILY_MVTCAE, cVAE.py:1754-1893) -----------------------------------------------------------------
+// total_correlation as written (:1846-1853): log_qz_xi = lse - mean(lse) of a scalar = 0, so
+//   tc = - sum_i mean_m logsumexp_b mu_m[b, i]   (mu_m = the per-modality encoder means, qz_xs).
+// grad_coef == 0: returns tc (all threads).  grad_coef != 0: adds grad_coef * d tc / d mu_m[b, i] = -grad_coef / M *
+// softmax_b(mu_m[:, i])[b] to the head gradients (s_dmulv).
+__device__ float mvtcae_tc(const StepCtx& c, float grad_coef) {
+  const ArchDesc& a = *c.a;
+  float* S = c.scratch;
+  const int M = a.M, Z = a.Z, rows = c.rows;
+  float acc = 0.f;
+  for (int p = threadIdx.x; p < M * Z; p += kThreads) {
+    const int m = p / Z, i = p - m * Z;
+    const float* mu = S + a.mod[m].s_mulv + i;
+    const int ld = a.mod[m].ld_mulv;
+    float mx = mu[0];
+    for (int b = 1; b < rows; ++b) mx = fmaxf(mx, mu[(long long)b * ld]);
+    float se = 0.f;
+    for (int b = 0; b < rows; ++b) se += expf(mu[(long long)b * ld] - mx);
+    acc -= (mx + logf(se)) / M;
+    if (grad_coef != 0.f) {
+      float* d = S + a.mod[m].s_dmulv + i;
+      for (int b = 0; b < rows; ++b) d[(long long)b * ld] += -grad_coef / M * expf(mu[(long long)b * ld] - mx) / se;
+    }
+  }
+  if (grad_coef != 0.f) { __syncthreads(); return 0.f; }
+  return block_sum(acc, c.red);
+}
+
+// d(total)/d(x_recon) of mvtCAE: the log-likelihood enters the total with weight +1e-5 instead of -1 (:1862)
+__device__ void scale_dxh(const StepCtx& c, int m, float s) {
+  const ModDesc& q = c.a->mod[m];
+  float* dxh = c.scratch + q.s_xh;
+  __syncthreads();
+  for (int e = threadIdx.x; e < c.rows * q.D; e += kThreads) {
+    const int b = e / q.D, n = e - b * q.D;
+    dxh[(long long)b * q.ld_xh + n] *= s;
+  }
+  __syncthreads();
+}
+
 // ---- one training step ---------------------------------------------------------------------
 template <bool TC>
 __device__ void train_step(StepCtx& c, const float* eps_src, float* loss_out) {
@@ -1049,12 +1099,16 @@ __device__ void train_step(StepCtx& c, const float* eps_src, float* loss_out) {
   const AdamCfg ad = make_adam(c);
   float head_loss = 0.f;
   if (a.head_kind) head_loss = head_step<TC>(c, ad);
+  const bool mvt = a.family == NMB_FAMILY_MVTCAE;
+  const float tc = mvt ? mvtcae_tc(c, 0.f) : 0.f;
   if (loss_out && threadIdx.x == 0) {
     loss_out[0] = M * kl - ll_sum + a.head_weight * head_loss; loss_out[1] = M * kl; loss_out[2] = ll_sum;   // cVAE.py:1187-1196
-    if (c.flags & NMB_TRAIN_LOSS4) loss_out[3] = head_loss;                                                // cVAE.py:2343-2345
+    if (mvt) loss_out[0] = M * kl + 1e-5f * ll_sum + M * a.beta * tc;                                        // cVAE.py:1858-1868
+    if (c.flags & NMB_TRAIN_LOSS4) loss_out[3] = mvt ? M * tc : head_loss;                                   // cVAE.py:2343-2345 / losses['tc']
   }
-  for (int m = 0; m < M; ++m) decoder_backward<TC>(c, ad, m, 1.f, m > 0, a.head_kind ? 1 : 0);
+  for (int m = 0; m < M; ++m) decoder_backward<TC>(c, ad, m, mvt ? -1e-5f : 1.f, m > 0, mvt ? 3 : (a.head_kind ? 1 : 0));
   latent_backward(c, ad, (float)M);
+  if (mvt) mvtcae_tc(c, M * a.beta);
   for (int m = 0; m < M; ++m) encoder_backward<TC>(c, ad, m);
 }
 

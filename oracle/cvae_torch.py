@@ -483,3 +483,34 @@ def dmvae_train_loop(model, xs, batch_size, epochs, eps_steps, zc):
             log.append((float(out["total"].detach()), float(torch.as_tensor(out["kl"]).detach()), float(out["ll"].detach())))
             step += 1
     return np.asarray(log, dtype=np.float64)
+
+
+class OracleMvtCAE(OracleCVAEMultimodal):
+    """``mvtCAE`` (cVAE.py:1754-1893) as written: the cVAE_multimodal architecture; the fused variance is clamped to >= 1e-6
+    (:1815); the 'poe' branch hands VARIANCES to ProductOfExperts2, which exponentiates them again and returns a
+    log-variance that is then used as the variance (:1778, :1800); total = sum_m (kl + 1e-5 ll_m + beta tc) with the
+    log-likelihood entering with a plus sign (:1862) and tc = - sum_i mean_m logsumexp_b mu_m[b, i] (:1846-1853)."""
+
+    beta = 0.0001
+
+    def latent(self, xs, cs, combine):
+        enc = [self.encoder_list[i](xs[i], cs[i]) for i in range(self.modalities)]
+        mus = torch.stack([e[0] for e in enc])
+        variances = torch.exp(torch.stack([e[1] for e in enc]))
+        if combine.lower() == "poe":
+            t = 1.0 / torch.exp(variances)
+            mu_mm, var_mm = torch.sum(mus * t, dim=0) / torch.sum(t, dim=0), torch.log(1.0 / torch.sum(t, dim=0))
+        else:
+            mu_mm, var_mm = fuse_latent(mus, variances, combine, list(self.alpha_m_list))
+        self._mus = mus
+        return mu_mm, torch.log(torch.clamp(var_mm, min=1e-6))
+
+    def step_losses(self, xs, cs, combine, eps=None):
+        out = super().step_losses(xs, cs, combine, eps)      # its kl / ll sums are the reference's losses['kl'] / ['ll']
+        m = self.modalities
+        tc = 0
+        for i in range(out["mu"].shape[1]):
+            tc = tc - torch.stack([self._mus[j][:, i].logsumexp(dim=0) for j in range(m)]).mean(dim=0)
+        out["tc"] = m * tc
+        out["total"] = out["kl"] + 0.00001 * out["ll"] + self.beta * out["tc"]
+        return out

@@ -902,6 +902,48 @@ def ref_dmvae_case(ref, name, cls_name, dims, hidden, z, s_dim, n, b, epochs, se
     print(name, "ok", losses[0], "->", losses[-1])
 
 
+def ref_mvtcae_case(ref, name, dims, hidden, z, c_dim, n, b, combine, epochs, seed, n_age):
+    """f4: the UNMODIFIED ``mvtCAE`` baseline (cVAE.py:1754-1893) through the training loop body: clamped fused variance,
+    the 'poe' branch that exponentiates variances again, total = sum_m (kl + 1e-5 ll_m + beta tc)."""
+    sd0 = clean_seed(ref.mvtCAE, dims, hidden, z, c_dim, n, b, epochs, seed, n_age, [combine])
+    model, next_draw, rng, xs, c, eps = _build_case(ref.mvtCAE, dims, hidden, z, c_dim, n, b, epochs, sd0, n_age)
+    out = {"dims": np.array(dims), "hidden": np.array(hidden), "z": z, "c_dim": c_dim, "seed": sd0, "next_draw": next_draw,
+           "n": n, "batch": b, "epochs": epochs, "c": c, "eps": eps, "combine": combine, "beta": float(model.beta)}
+    for k, v in sd_np(model).items():
+        out["init/" + k] = v
+    for i, x in enumerate(xs):
+        out[f"x{i}"] = x
+    xt, ct = [torch.from_numpy(x) for x in xs], torch.from_numpy(c).long()
+    losses, s_ = [], 0
+    for _ in range(epochs):
+        for r0, rows in _loop_batches(n, b):
+            xb, cb = [x[r0:r0 + rows] for x in xt], [ct[r0:r0 + rows] for _ in dims]
+            with injected_eps([torch.from_numpy(eps[s_][:rows])]):
+                fwd = model.forward_multimodal(xb, cb, combine)
+            loss = model.loss_function_multimodal(xb, fwd)
+            model.optimizer1.zero_grad()
+            loss["total"].backward()
+            if s_ == 0:
+                out["mu"] = fwd["mu_multimodal"].detach().numpy().copy()
+                out["logvar"] = fwd["logvar_multimodal"].detach().numpy().copy()
+                for k, p_ in model.named_parameters():
+                    out["grad/" + k] = p_.grad.detach().numpy().copy() if p_.grad is not None else np.zeros(tuple(p_.shape), np.float32)
+            model.optimizer1.step()
+            losses.append([float(loss[k].detach()) for k in ("total", "kl", "ll", "tc")])
+            s_ += 1
+    out["losses"] = np.array(losses, dtype=np.float64)
+    for k, v in sd_np(model).items():
+        out["final/" + k] = v
+    eps_t = rng.randn(n, z).astype(np.float32)
+    with injected_eps([torch.from_numpy(eps_t)]):
+        preds = model.pred_recon([pd.DataFrame(x.astype(np.float64)) for x in xs], c, torch.device("cpu"), combine)
+    out["eps_test"] = eps_t
+    for i in range(len(dims)):
+        out[f"pred{i}"] = preds[i]
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, "ok", losses[0], "->", losses[-1])
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     sys.path.insert(0, REF)
@@ -913,6 +955,12 @@ def main():
             sd = clean_seed(mm, [116, 116, 116, 348], [110, 110], 10, 29, 288, 256, 2, 46, 27, [comb])
             ref_loop_case(ref, "mm_M4_full_" + comb.lower(), [116, 116, 116, 348], [110, 110], 10, 29, 288, 256, comb, 2,
                           sd, 27, lean=lean)
+        return
+    if "--f4c" in sys.argv:
+        ref_mvtcae_case(ref, "mvtcae_M3_gpoe", [40, 24, 17], [32, 24], 8, 7, 150, 64, "gPoE", 2, 51, 5)
+        ref_mvtcae_case(ref, "mvtcae_M2_poe", [13, 6], [11, 9], 4, 7, 23, 10, "poe", 3, 52, 5)
+        ref_mvtcae_case(ref, "mvtcae_M3_mopoe", [13, 6, 21], [11, 9], 4, 7, 23, 10, "MoPoE", 3, 53, 5)
+        ref_mvtcae_case(ref, "mvtcae_M1_poe", [13], [11, 9], 4, 7, 23, 10, "PoE", 3, 54, 5)       # one expert: the 'variance' is not clamped
         return
     if "--f4b" in sys.argv:
         ref_dmvae_case(ref, "dmvae_M2_shared", "DMVAE", [13, 6], [11, 9], 7, 4, 23, 10, 3, 41)

@@ -149,7 +149,7 @@ def test_dmvae_family_dropins_vs_reference(golden_dir, name):
 def test_train_test_programs_with_model_flag(tmp_path):
     """``-Model`` of the train script (:141-148) on a synthetic HCPimage dataset: mmJSD == cVAE_multimodal with PoE bit for
     bit (the same kernels, `combine` ignored); DMVAE / mmVAEPlus / WeightedDMVAE train, pickle as the drop-in classes
-    and go through the test program + group analysis; mvtCAE is refused."""
+    and go through the test program + group analysis, and so does mvtCAE; an unknown name is refused."""
     import argparse
     import pandas as pd
     from multi_modal_normative_modeling_b200 import cli, synthetic, zoo
@@ -162,7 +162,14 @@ def test_train_test_programs_with_model_flag(tmp_path):
     b = cli.train_main(argparse.Namespace(model="cVAE_multimodal", **poe), root=tmp_path)
     assert np.array_equal(a, b)                         # mmJSD with -P SE-MoE == cVAE_multimodal with PoE
     with pytest.raises(ValueError, match="not recognized"):
-        cli.train_main(argparse.Namespace(model="mvtCAE", **base), root=tmp_path)
+        cli.train_main(argparse.Namespace(model="VAE", **base), root=tmp_path)
+    from multi_modal_normative_modeling_b200.cVAE import mvtCAE
+    mv = dict(base, procedure="SE-gPoE")
+    losses = cli.train_main(argparse.Namespace(model="mvtCAE", **mv), root=tmp_path)
+    assert np.isfinite(losses).all() and (losses[:, :, 0] < 50).all()        # total = sum_m (kl + 1e-5 ll + 1e-4 tc): O(1)
+    assert type(torch.load(tmp_path / "outputs" / "kfold_analysis" / "supervised_cvae" / "000" / "cVAE_model.pkl", weights_only=False)) is mvtCAE
+    cli.test_main(argparse.Namespace(model="mvtCAE", **mv), root=tmp_path)
+    assert 0.0 <= cli.analysis_main(argparse.Namespace(model="mvtCAE", **mv), root=tmp_path)[0][2][0] <= 1.0
     for model, cls in (("DMVAE", zoo.DMVAE), ("mmVAEPlus", zoo.mmVAEPlus), ("WeightedDMVAE", zoo.WeightedDMVAE)):
         for hz in ([32, 24, 40], [32, 24, 6]):          # latent 40 > c_dim 29: 11 shared dimensions; latent 6: none (the default situation)
             ns = dict(base, hz_para_list=hz)
