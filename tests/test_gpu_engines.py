@@ -173,3 +173,59 @@ def test_reconstruct_reusing_the_training_kernels_weight_planes(workload):
     torch.cuda.synchronize()
     assert torch.equal(c.xhat_test, d.xhat_test) and not torch.equal(c.xhat_test, a.xhat_test)
     tr.close(); other.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("engine", ["tcs", "fp32"])
+def test_mixed_ensemble_of_every_model_kind_equals_members_alone(engine):
+    """One launch over members of EVERY model kind the generic engines serve -- plain cVAE_multimodal, regression head,
+    end-to-end head, DMVAE family (shared + private latents, weighted), mvtCAE -- with different shapes: each member's
+    losses and parameters are bit-identical to training it alone (per-architecture tables, scratch slots and the work
+    queue do not leak between members)."""
+    from multi_modal_normative_modeling_b200 import EnsembleTrainer, MemberSpec, pack_rows, _lib
+    rng = np.random.RandomState(0)
+    n = 150
+
+    def rows(dims, c):
+        ct = torch.from_numpy(c).cuda()
+        return [pack_rows(torch.from_numpy(rng.rand(n, d).astype(np.float32)).cuda(), ct) for d in dims]
+    onehot = np.zeros((n, 7), np.float32); onehot[np.arange(n), rng.randint(0, 5, n)] = 1; onehot[np.arange(n), 5 + rng.randint(0, 2, n)] = 1
+    raw = np.stack([rng.uniform(22, 36, n), rng.randint(1, 3, n)], 1).astype(np.float32)
+    none = np.zeros((n, 0), np.float32)
+    y_reg = torch.from_numpy((rng.randn(n) * 4 + 17).astype(np.float32)).cuda()
+    y_cls = torch.from_numpy((rng.rand(n) > 0.5).astype(np.float32)).cuda()
+    order = torch.from_numpy(np.stack([np.stack([rng.permutation(n) for _ in range(2)]) for _ in range(2)]).astype(np.int32)).cuda()
+
+    def specs():
+        return [
+            MemberSpec([20, 9], [16, 12], 5, 7, rows([20, 9], onehot), combine="gpoe", batch=64, seed=1),
+            MemberSpec([13, 6], [11, 9], 4, 2, rows([13, 6], raw), combine="poe", batch=64, seed=2, head="regression", y=y_reg,
+                       row_order=order),
+            MemberSpec([17], [14, 10], 6, 7, rows([17], onehot), batch=64, seed=3, head="endtoend", head_hidden=[12, 8], y=y_cls),
+            MemberSpec([15, 11, 8], [12, 10], 9, 0, rows([15, 11, 8], none), batch=64, seed=4, family="dmvae", s_dim=4, weighted=True),
+            MemberSpec([10, 10], [9, 9], 3, 7, rows([10, 10], onehot), combine="mopoe", batch=64, seed=5, family="mvtcae", beta=1e-4),
+        ]
+    flag = {"tcs": _lib.TRAIN_TC_SIMPLE, "fp32": _lib.TRAIN_FP32}[engine]
+    rng = np.random.RandomState(0)
+    all_specs = specs()
+    torch.manual_seed(0)
+    tr = EnsembleTrainer(all_specs)
+    init = torch.randn(tr.total_params, device="cuda") * 0.05
+    tr.params.copy_(init)
+    for i, sp in enumerate(all_specs):              # BatchNorm scale / running variance and the DMVAE weights start at 1
+        for k, v in tr._views(i, tr.params).items():
+            if k.endswith("running_var") or k == "weights" or (".classifier." in k and k.split(".")[2] in ("1", "5") and k.endswith("weight")):
+                v.fill_(1.0)
+    start = tr.params.clone()
+    losses = tr.train_steps(5, record_losses=True, flags=flag)
+    torch.cuda.synchronize()
+    assert torch.isfinite(losses).all()
+    for i, sp in enumerate(all_specs):
+        one = EnsembleTrainer([sp])
+        one.params.copy_(start[tr.offsets[i]: tr.offsets[i] + tr.n_params[i]])
+        lo = one.train_steps(5, record_losses=True, flags=flag)
+        torch.cuda.synchronize()
+        assert torch.equal(lo[0], losses[i]), i
+        assert torch.equal(one.params, tr.params[tr.offsets[i]: tr.offsets[i] + tr.n_params[i]]), i
+        one.close()
+    tr.close()
