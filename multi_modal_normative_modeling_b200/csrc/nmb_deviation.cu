@@ -111,7 +111,46 @@ __global__ void __launch_bounds__(256) deviation_kernel(SegTable t) {
   const int lane = threadIdx.x & 31;
   const int warps = (blockDim.x >> 5) * gridDim.x;
   const bool vec = (d & 3) == 0;
-  for (int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += warps) {
+  int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (vec && d <= 128) {
+    // the usual widths (<= 128 ROIs: one float4 per lane and row): two rows per warp pass, all four loads of a lane in
+    // flight before the first use, so that a warp keeps ~2 KB of reads outstanding instead of ~1 KB
+    const int j = lane * 4;
+    const bool on = j < d;
+    float4 mu = make_float4(0.f, 0.f, 0.f, 0.f), sd = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (zs && on) { mu = *reinterpret_cast<const float4*>(stats + j); sd = *reinterpret_cast<const float4*>(stats + d + j); }
+    for (; i < n; i += 2 * warps) {
+      const int i2 = i + warps;
+      const bool two = i2 < n;
+      float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), b0 = a0, a1 = a0, b1 = a0;
+      if (on) {
+        a0 = *reinterpret_cast<const float4*>(x + (long long)i * ldx + j);
+        b0 = *reinterpret_cast<const float4*>(xh + (long long)i * d + j);
+        if (two) {
+          a1 = *reinterpret_cast<const float4*>(x + (long long)i2 * ldx + j);
+          b1 = *reinterpret_cast<const float4*>(xh + (long long)i2 * d + j);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        if (k == 1 && !two) break;
+        const float4 a = k ? a1 : a0, b = k ? b1 : b0;
+        const long long row = k ? i2 : i;
+        float4 r = make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
+        r.x *= r.x; r.y *= r.y; r.z *= r.z; r.w *= r.w;
+        float acc = (r.x + r.y) + (r.z + r.w);
+        if (on) {
+          if (roi) *reinterpret_cast<float4*>(roi + row * d + j) = r;
+          if (zs) *reinterpret_cast<float4*>(zs + row * d + j) =
+              make_float4((r.x - mu.x) / sd.x, (r.y - mu.y) / sd.y, (r.z - mu.z) / sd.z, (r.w - mu.w) / sd.w);
+        }
+        acc = warp_sum(acc);
+        if (subj && lane == 0) subj[row] = acc / d;
+      }
+    }
+    return;
+  }
+  for (; i < n; i += warps) {
     const float* xr = x + (long long)i * ldx;
     const float* hr = xh + (long long)i * d;
     float acc = 0.f;
