@@ -64,11 +64,29 @@ __global__ void __launch_bounds__(256) stats_kernel(SegTable t) {
   double sum = 0.0, sq = 0.0;
   int cnt = 0;
   if (col < d) {
-    for (int i = rg; i < n; i += 8) {
-      if (mask && !mask[i]) continue;
-      const float r = x[(long long)i * ldx + col] - xh[(long long)i * d + col];
-      const double r2 = (double)(r * r);
-      sum += r2; sq += r2 * r2; ++cnt;
+    // four rows of this thread's row group per pass: the mask bytes and the eight loads are issued before the first use
+    // (one row per pass kept ~2 KB of reads in flight per CTA); accumulation stays in row order, so the sums are unchanged
+    for (int i0 = rg; i0 < n; i0 += 32) {
+      float xv[4], hv[4];
+      bool ok[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + 8 * u;
+        ok[u] = i < n && (!mask || mask[i]);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + 8 * u;
+        xv[u] = ok[u] ? x[(long long)i * ldx + col] : 0.f;
+        hv[u] = ok[u] ? xh[(long long)i * d + col] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (!ok[u]) continue;
+        const float r = xv[u] - hv[u];
+        const double r2 = (double)(r * r);
+        sum += r2; sq += r2 * r2; ++cnt;
+      }
     }
   }
   __shared__ double s_sum[8][32], s_sq[8][32];
