@@ -28,8 +28,6 @@ print("gather           gpu %.3f ms  host-issue %.3f ms  wall %.3f ms" % timed(l
 lib, st = sc.lib, torch.cuda.current_stream().cuda_stream
 calls = {
  "reconstruct both": lambda: lib.nmb_ensemble_reconstruct_sets(tr.handle, 2, sc.t_xc_both, sc.t_rows_both, sc.mode, None, sc.t_hat_both, None, None, st),
- "reconstruct train": lambda: lib.nmb_ensemble_reconstruct(tr.handle, sc.t_xc_tr, sc.t_rows_tr, sc.mode, None, sc.t_hat_tr, None, None, st),
- "reconstruct test": lambda: lib.nmb_ensemble_reconstruct(tr.handle, sc.t_xc_te, sc.t_rows_te, sc.mode, None, sc.t_hat_te, None, None, st),
  "stats": lambda: lib.nmb_normative_stats(sc.n_seg, sc.s_x_tr, sc.s_ldx, sc.s_hat_tr, sc.s_mask, sc.s_ntr, sc.s_d, sc.s_stats, st),
  "deviation": lambda: lib.nmb_deviation(sc.n_seg, sc.s_x_te, sc.s_ldx, sc.s_hat_te, sc.s_stats, sc.s_nte, sc.s_d, sc.s_roi, sc.s_z, sc.s_subj, st),
  "auc roi": lambda: lib.nmb_auc(sc.n_seg, sc.s_z, sc.s_lab, sc.s_nte, sc.s_d, sc.s_auc_roi, None, st),
