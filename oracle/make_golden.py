@@ -944,6 +944,41 @@ def ref_mvtcae_case(ref, name, dims, hidden, z, c_dim, n, b, combine, epochs, se
     print(name, "ok", losses[0], "->", losses[-1])
 
 
+def e2e_ids_case():
+    """f3: the reference's own ``utils.generate_kfold_ids_endtoend`` (utils.py:19-42) run in a scratch directory on the
+    synthetic subject table: fold ids of the end-to-end program (KFold over HC + others, bootstrap on the legacy numpy RNG)."""
+    import tempfile
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from multi_modal_normative_modeling_b200 import synthetic
+    subj = synthetic.make_subjects(160, seed=5)
+    cwd = os.getcwd()
+    out = {}
+    with tempfile.TemporaryDirectory() as d:
+        os.chdir(d)
+        try:
+            # utils.py imports nilearn at module level (not in this image): the function is cut out with ast and executed
+            # verbatim against its own dependencies (KFold, pandas, numpy, PROJECT_ROOT = cwd)
+            import ast
+            from pathlib import Path
+            from sklearn.model_selection import KFold
+            src = open(os.path.join(REF, "utils.py")).read()
+            node = [n_ for n_ in ast.parse(src).body if isinstance(n_, ast.FunctionDef) and n_.name == "generate_kfold_ids_endtoend"][0]
+            ns = {"KFold": KFold, "pd": pd, "np": np, "PROJECT_ROOT": Path.cwd()}
+            exec(compile(ast.Module(body=[node], type_ignores=[]), os.path.join(REF, "utils.py"), "exec"), ns)
+            np.random.seed(42)
+            import contextlib, io
+            with contextlib.redirect_stdout(io.StringIO()):
+                ns["generate_kfold_ids_endtoend"](subj[subj["DIA"] == 1], subj[subj["DIA"] != 1], oversample_percentage=1, n_splits=3)
+            for f in range(3):
+                base = os.path.join(d, "outputs", "kfold_analysis_endtoend")
+                out[f"train/{f}"] = open(os.path.join(base, f"train_ids_{f:03d}.csv"), "rb").read()
+                out[f"test/{f}"] = open(os.path.join(base, f"test_ids_{f:03d}.csv"), "rb").read()
+        finally:
+            os.chdir(cwd)
+    np.savez_compressed(os.path.join(OUT, "e2e_fold_ids.npz"), **{k: np.frombuffer(v, dtype=np.uint8) for k, v in out.items()})
+    print("e2e_fold_ids ok", {k: len(v) for k, v in out.items()})
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     sys.path.insert(0, REF)
@@ -955,6 +990,9 @@ def main():
             sd = clean_seed(mm, [116, 116, 116, 348], [110, 110], 10, 29, 288, 256, 2, 46, 27, [comb])
             ref_loop_case(ref, "mm_M4_full_" + comb.lower(), [116, 116, 116, 348], [110, 110], 10, 29, 288, 256, comb, 2,
                           sd, 27, lean=lean)
+        return
+    if "--f3ids" in sys.argv:
+        e2e_ids_case()
         return
     if "--f4c" in sys.argv:
         ref_mvtcae_case(ref, "mvtcae_M3_gpoe", [40, 24, 17], [32, 24], 8, 7, 150, 64, "gPoE", 2, 51, 5)

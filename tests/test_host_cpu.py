@@ -291,3 +291,49 @@ def test_native_csv_writer_is_byte_identical_to_pandas(tmp_path, dtype):
         df.to_csv(tmp_path / "ref.csv", index=False)
         cli.write_csv(df, tmp_path / "new.csv")
         assert (tmp_path / "new.csv").read_bytes() == (tmp_path / "ref.csv").read_bytes()
+
+
+def test_endtoend_fold_ids_byte_identical_to_reference(tmp_path, golden_dir):
+    """f3: ``e2e.generate_kfold_ids_endtoend`` writes the files the reference's utils.generate_kfold_ids_endtoend
+    (utils.py:19-42) writes -- same KFold over HC + others, same bootstrap draws from the legacy numpy stream -- byte for
+    byte (recorded by oracle/make_golden.py --f3ids from the unmodified function)."""
+    from multi_modal_normative_modeling_b200 import e2e, synthetic
+    g = np.load(os.path.join(golden_dir, "e2e_fold_ids.npz"))
+    subj = synthetic.make_subjects(160, seed=5)
+    np.random.seed(42)
+    d = e2e.generate_kfold_ids_endtoend(tmp_path, subj[subj["DIA"] == 1], subj[subj["DIA"] != 1], oversample_percentage=1, n_splits=3)
+    for f in range(3):
+        assert (d / f"train_ids_{f:03d}.csv").read_bytes() == g[f"train/{f}"].tobytes(), f
+        assert (d / f"test_ids_{f:03d}.csv").read_bytes() == g[f"test/{f}"].tobytes(), f
+
+
+def test_regression_loader_orders_replay_the_shuffling_loaders():
+    """f3: ``regression.loader_orders`` == the row order the reference's per-modality ``DataLoader(shuffle=True)`` loaders
+    yield epoch after epoch (..._regression.py:94, 121-122) from the same CPU generator state: three loaders over real
+    (x, c, fi) datasets iterated with zip, two epochs, then the generator states agree as well."""
+    import torch
+    from multi_modal_normative_modeling_b200 import regression
+    n, b, m, epochs = 45, 16, 3, 2
+
+    class DS(torch.utils.data.Dataset):                   # MyDataset_labels_with_fi-shaped: (x, c, fi), plus the row id
+        def __len__(self):
+            return n
+
+        def __getitem__(self, i):
+            return torch.zeros(4), torch.zeros(2), torch.zeros(1), i
+    torch.manual_seed(123)
+    loaders = [torch.utils.data.DataLoader(DS(), batch_size=b, shuffle=True) for _ in range(m)]
+    want = np.empty((epochs, m, n), dtype=np.int32)
+    for ep in range(epochs):
+        rows = [[] for _ in range(m)]
+        for batch_list in zip(*loaders):
+            for k, batch in enumerate(batch_list):
+                rows[k].append(batch[3].numpy())
+        for k in range(m):
+            want[ep, k] = np.concatenate(rows[k])
+    after_ref = torch.randn(3)
+    torch.manual_seed(123)
+    got = regression.loader_orders(n, b, epochs, m)
+    after = torch.randn(3)
+    assert np.array_equal(got, want) and torch.equal(after, after_ref)
+    assert not np.array_equal(got[0, 0], got[0, 1])        # the modalities of one minibatch are different subjects
