@@ -337,3 +337,45 @@ def test_regression_loader_orders_replay_the_shuffling_loaders():
     after = torch.randn(3)
     assert np.array_equal(got, want) and torch.equal(after, after_ref)
     assert not np.array_equal(got[0, 0], got[0, 1])        # the modalities of one minibatch are different subjects
+
+
+def _cut_function(path, name, ns):
+    """A function of a reference script that cannot be imported here (tensorflow / nilearn at module level), cut out with
+    ast and executed verbatim.  Only available in the build container: the GPU box has no /root/reference."""
+    import ast
+    src = open(path).read()
+    node = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == name][0]
+    exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
+    return ns[name]
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/multimodal_kfold_cvae_nmpmcont.py"), reason="reference sources not present")
+def test_f3_host_functions_vs_reference_sources():
+    """f3 host side against the reference's OWN functions executed from its sources: ``process_dataset`` of the end-to-end
+    program (nmpmcont :75-123: RobustScaler, rank-quantile one-hots, labels) and ``evaluate_regression`` of the regression
+    trainer (:30-35)."""
+    import pandas as pd
+    from sklearn.metrics import mean_absolute_error, mean_squared_error, r2_score
+    from sklearn.preprocessing import RobustScaler
+    from multi_modal_normative_modeling_b200 import e2e, regression, synthetic
+    from multi_modal_normative_modeling_b200.utils import COLUMNS_NAME_AAL116
+    subj = synthetic.make_subjects(120, seed=9)
+    x = synthetic.make_modality(subj, 116, seed=10)
+    df = pd.concat([subj.reset_index(drop=True), pd.DataFrame(x, columns=list(COLUMNS_NAME_AAL116))], axis=1)
+    ref_pd = _cut_function("/root/reference/multimodal_kfold_cvae_nmpmcont.py", "process_dataset",
+                           {"RobustScaler": RobustScaler, "pd": pd, "np": np})
+    want = ref_pd(df, list(COLUMNS_NAME_AAL116), scaler=None, fit_scaler=True, hc_label=1)
+    got = e2e.process_dataset(df, list(COLUMNS_NAME_AAL116), None, True, 1)
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and np.array_equal(got[2], want[2])
+    te = df.iloc[::3]
+    want_t = ref_pd(te, list(COLUMNS_NAME_AAL116), scaler=want[3], fit_scaler=False, hc_label=1)
+    got_t = e2e.process_dataset(te, list(COLUMNS_NAME_AAL116), got[3], False, 1)
+    assert np.array_equal(got_t[0], want_t[0]) and np.array_equal(got_t[1], want_t[1]) and np.array_equal(got_t[2], want_t[2])
+    ref_ev = _cut_function("/root/reference/multimodal_kfold_train_cvae_supervised_regression.py", "evaluate_regression",
+                           {"np": np, "mean_squared_error": mean_squared_error, "mean_absolute_error": mean_absolute_error,
+                            "r2_score": r2_score})
+    rng = np.random.RandomState(0)
+    yt, yp = rng.normal(105, 15, (50, 1)).astype(np.float32), rng.normal(105, 15, (50, 1)).astype(np.float32)
+    a, b = ref_ev(yt, yp), regression.evaluate_regression(yt, yp)
+    for k in ("RMSE", "MAE", "R2", "MAPE"):
+        assert abs(float(a[k]) - b[k]) <= 1e-5 * max(1.0, abs(float(a[k]))), (k, a[k], b[k])
