@@ -239,7 +239,7 @@ def test_mmjsd_baseline_dropin_vs_reference(golden_dir, engine):
         # FP32 engine: the reference's trajectory to 2e-4 of the largest update on 99 % of the elements (measured 1e-5).
         # Default engine (BF16x3; batch 128 -> the generic one): after the first Adam step one hidden unit of encoder 0 sits
         # within rounding distance of the leaky-relu kink for one of the 22 samples of the ragged batch and takes the other
-        # branch (tools/diag_traj.py: that step's gradient agrees with the FP32 engine to 4e-5 in the median and differs by
+        # branch (tests/tools/diag_traj.py: that step's gradient agrees with the FP32 engine to 4e-5 in the median and differs by
         # 6e-2 in ONE row of encoder 0 / layer 1, hence by a rank-one term in layer 0).  The fixture's knife-edge scan
         # (oracle/make_golden.py::clean_seed) covers the initial weights only, so the looser bound applies here.
         assert_update_close(k, sd[k].cpu().numpy(), v, init[k], s, 1e-4, engine == "fp32", g0.get(k), q99_tc=6e-2, mean_tc=1e-2)

@@ -98,7 +98,7 @@ def test_e2e_epochs_with_adam_vs_reference(golden_dir, name, engine):
             # kink after the first Adam steps take the other branch (the fixture's knife-edge scan covers the initial
             # weights only); in the 44-row ragged batch one sample is 1/44 of the gradient, and Adam's normalisation turns
             # the rank-one difference into visible steps on the encoders (measured q99 3e-2 on encoder 0, 4e-3 elsewhere;
-            # same mechanism as tools/diag_traj.py shows for the mmJSD fixture).  The end-to-end program trains on the
+            # same mechanism as tests/tools/diag_traj.py shows for the mmJSD fixture).  The end-to-end program trains on the
             # bit-stable FP32 engine (e2e.py); the BF16x3 engine is held to the looser bound below.
             assert_update_close(k, got_k, v, init[k], steps, 1e-4, engine == "fp32", g0.get(k), q99_tc=6e-2, mean_tc=1e-2)
     tr.close()

@@ -2,7 +2,7 @@
 hidden 110/110, latent 10, batch 128, shuffling loaders) trained in one launch of the generic engines, against the
 oracle's restatement of the reference loop (torch CPU, all host threads) on the same fold."""
 import json, os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from multi_modal_normative_modeling_b200 import EnsembleTrainer, MemberSpec, pack_rows, _lib
 from multi_modal_normative_modeling_b200.regression import loader_orders

@@ -12,5 +12,5 @@ ncu --set full --clock-control none --import-source on --kernel-name-base mangle
 python tools/trace_tcp.py 1 33 42 > gpurun_out/trace_${P}_d116.txt 2>&1
 python tools/trace_tcp.py 1 46 84 big > gpurun_out/trace_${P}_d348.txt 2>&1
 python tools/time_cli.py > gpurun_out/cli_$P.json 2> gpurun_out/cli_$P.err
-python tools/time_f3.py > gpurun_out/f3_$P.json 2> gpurun_out/f3_$P.err
+python tests/tools/time_f3.py > gpurun_out/f3_$P.json 2> gpurun_out/f3_$P.err
 ls -la gpurun_out/${P}_*
